@@ -1,0 +1,51 @@
+#!/bin/bash
+# oracle/build_ref.sh -- TEST INFRASTRUCTURE.
+# Compiles the reference's own CPU hot path from the sources WHERE THEY LIE under
+# $MILC_REF (default /root/reference) into oracle/_ref/ (git-ignored, travels to
+# the GPU box).  This is our own short recipe, not the reference's build system;
+# the flags are the ones its default vanilla build uses (Makefile:814-818:
+# -DDBLSTORE_FN -DFEWSUMS -DD_FN_GATHER13, libraries/Make_vanilla: -O3 -DFAST).
+# Outputs:
+#   oracle/_ref/libmilcref.so       double precision, single thread
+#   oracle/_ref/libmilcref_omp.so   double precision, OpenMP site loops (-DOMP)
+#   oracle/_ref/libmilcref_f.so     single precision (MILC_PRECISION=1), single thread
+# Nothing is written to $MILC_REF and no reference source is copied into the repo.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${MILC_REF:-/root/reference}"
+OUT="$HERE/_ref"
+if [ ! -d "$REF/generic_ks" ]; then
+  echo "build_ref.sh: reference tree not found at $REF (nothing to do)"; exit 0
+fi
+mkdir -p "$OUT/gen"
+# the reference's own make copies the chosen action header to quark_action.h
+# (ks_imp_utilities/Make_template:118-119); it is a build artefact, not source.
+cp "$REF/generic_ks/imp_actions/hisq/hisq_u3_action.h" "$OUT/gen/quark_action.h"
+
+LIBSRC=$(cd "$REF/libraries" && ls *.c | grep -v "^prefetch32.c$\|^prefetch64.c$")
+GEN="com_vanilla.c layout_hyper_prime.c make_lattice.c field_utilities.c ranstuff.c"
+GKS="dslash_fn_dblstore.c fn_links_milc.c d_congrad5_fn_milc.c ks_multicg_offset.c fermion_links_fn_twist_milc.c"
+
+build_variant() {  # name precision extra-flags
+  local name="$1" prec="$2" extra="$3"
+  local obj="$OUT/obj_$name"
+  mkdir -p "$obj"
+  local CF="-O3 -fPIC -std=gnu99 -w $extra -DMILC_PRECISION=$prec -DFAST"
+  local AF="$CF -DDBLSTORE_FN -DFEWSUMS -DD_FN_GATHER13 -DC_GLOBAL_INLINE -DFN -DHAVE_KS \
+            -D_FILE_OFFSET_BITS=64 -I$HERE/ref_harness -I$OUT/gen"
+  local jobs=()
+  for f in $LIBSRC; do
+    echo "gcc -c $CF $REF/libraries/$f -o $obj/lib_${f%.c}.o"
+  done > "$obj/cmds.txt"
+  for f in $GEN; do echo "gcc -c $AF -I$REF/generic $REF/generic/$f -o $obj/gen_${f%.c}.o"; done >> "$obj/cmds.txt"
+  for f in $GKS; do echo "gcc -c $AF -I$REF/generic_ks $REF/generic_ks/$f -o $obj/gks_${f%.c}.o"; done >> "$obj/cmds.txt"
+  echo "gcc -c $AF -I$REF/generic_ks $HERE/ref_harness/harness.c -o $obj/harness.o" >> "$obj/cmds.txt"
+  # a few library files are platform-specific and may not compile; they are not on the path
+  xargs -P "$(nproc)" -I{} sh -c '{} 2>/dev/null || echo "skip: {}" | cut -c1-200 >&2' < "$obj/cmds.txt"
+  gcc -shared $extra -o "$OUT/libmilcref$name.so" "$obj"/*.o -lm
+  echo "built $OUT/libmilcref$name.so"
+}
+
+build_variant ""     2 ""
+build_variant "_omp" 2 "-fopenmp -DOMP"
+build_variant "_f"   1 ""

@@ -1,0 +1,144 @@
+/* oracle/ref_harness/harness.c -- TEST INFRASTRUCTURE, not product code.
+ *
+ * Thin C glue that exposes the UNMODIFIED reference CPU hot path (compiled from
+ * its own sources under /root/reference by oracle/build_ref.sh into
+ * oracle/_ref/libmilcref*.so) through a ctypes-friendly ABI.  It plays the role
+ * an application's control.c/setup.c plays in MILC:
+ *   - layout + neighbour tables  (ks_spectrum/setup.c:30-61, 1405-1445)
+ *   - fn_links_t filled from caller-provided fat/long arrays
+ *     (generic_ks/fn_links_milc.c:245-302) + back links for the dblstore dslash
+ *   - dslash_fn_field            (generic_ks/dslash_fn_dblstore.c:285-304)
+ *   - ks_congrad_parity_cpu      (generic_ks/d_congrad5_fn_milc.c:60-407)
+ *   - ks_multicg_offset_field_cpu(generic_ks/ks_multicg_offset.c:63-505)
+ * Used only by tests/, bench.py's cpu_baseline / --impl reference legs and the
+ * golden-vector generator.  Nothing in the product links or loads it.
+ */
+#define CONTROL
+#include "generic_ks_includes.h"
+#include "../include/fn_links.h"
+#include <string.h>
+
+static fn_links_t *h_fn = NULL;
+static int h_ready = 0;
+
+/* Third-neighbour map: same arithmetic as every MILC KS application's setup.c
+   (ks_spectrum/setup.c:1427-1445).  It is static there, so the harness has to
+   supply its own. */
+static void h_third_neighbor(int x, int y, int z, int t, int *dirpt, int FB,
+                             int *xp, int *yp, int *zp, int *tp) {
+  int dir = (FB == FORWARDS) ? *dirpt : OPP_DIR(*dirpt);
+  *xp = x; *yp = y; *zp = z; *tp = t;
+  switch (dir) {
+  case XUP:   *xp = (x + 3) % nx; break;
+  case XDOWN: *xp = (x + 4 * nx - 3) % nx; break;
+  case YUP:   *yp = (y + 3) % ny; break;
+  case YDOWN: *yp = (y + 4 * ny - 3) % ny; break;
+  case ZUP:   *zp = (z + 3) % nz; break;
+  case ZDOWN: *zp = (z + 4 * nz - 3) % nz; break;
+  case TUP:   *tp = (t + 3) % nt; break;
+  case TDOWN: *tp = (t + 4 * nt - 3) % nt; break;
+  default: printf("h_third_neighbor: bad direction\n"); exit(1);
+  }
+}
+
+int milcref_precision(void) { return MILC_PRECISION; }
+int milcref_sizeof_real(void) { return (int)sizeof(Real); }
+
+/* One lattice geometry per process (MILC's globals are process-wide). */
+int milcref_init(int lx, int ly, int lz, int lt) {
+  int i;
+  if (h_ready) {
+    if (lx == nx && ly == ny && lz == nz && lt == nt) return 0;
+    return -1;
+  }
+  initialize_machine(NULL, NULL);
+  nx = lx; ny = ly; nz = lz; nt = lt;
+  volume = nx * ny * nz * nt;
+  this_node = mynode();
+  number_of_nodes = numnodes();
+  total_iters = 0;
+  phases_in = 1;
+  setup_layout();
+  make_lattice();
+  make_nn_gathers();
+  for (i = XUP; i <= TUP; i++)
+    make_gather(h_third_neighbor, &i, WANT_INVERSE, ALLOW_EVEN_ODD, SWITCH_PARITY);
+  sort_eight_gathers(X3UP);
+  h_ready = 1;
+  return 0;
+}
+
+long milcref_sites_on_node(void) { return (long)sites_on_node; }
+int milcref_node_index(int x, int y, int z, int t) { return (int)node_index(x, y, z, t); }
+int milcref_total_iters(void) { return total_iters; }
+
+/* fat, lng: su3_matrix[4*sites_on_node] in MILC order (fat[4*i+dir]), Real precision. */
+int milcref_set_links(const Real *fat, const Real *lng, double eps_naik) {
+  if (!h_ready) return -1;
+  if (h_fn != NULL) destroy_fn_links(h_fn);
+  h_fn = create_fn_links();
+  memcpy(h_fn->fat, fat, sizeof(su3_matrix) * 4 * sites_on_node);
+  memcpy(h_fn->lng, lng, sizeof(su3_matrix) * 4 * sites_on_node);
+  h_fn->eps_naik = eps_naik;
+#ifdef DBLSTORE_FN
+  load_fn_backlinks(h_fn);
+#endif
+  return 0;
+}
+
+void milcref_dslash(const Real *src, Real *dest, int parity) {
+  dslash_fn_field((su3_vector *)src, (su3_vector *)dest, parity, h_fn);
+}
+
+/* out[0..6] = final_rsq, final_relrsq, size_r, size_relr, final_iters, final_restart, converged */
+static void h_unpack(const quark_invert_control *qic, double *out) {
+  out[0] = qic->final_rsq; out[1] = qic->final_relrsq;
+  out[2] = qic->size_r;    out[3] = qic->size_relr;
+  out[4] = qic->final_iters; out[5] = qic->final_restart; out[6] = qic->converged;
+}
+
+int milcref_congrad(const Real *src, Real *dest, double m, int parity,
+                    int max, int nrest, double resid, double relresid, double *out) {
+  quark_invert_control qic;
+  int it;
+  memset(&qic, 0, sizeof(qic));
+  qic.prec = MILC_PRECISION; qic.min = 0; qic.max = max; qic.nrestart = nrest;
+  qic.parity = parity; qic.start_flag = 1; qic.nsrc = 1;
+  qic.resid = resid; qic.relresid = relresid;
+  it = ks_congrad_parity_cpu((su3_vector *)src, (su3_vector *)dest, &qic, (Real)m, h_fn);
+  h_unpack(&qic, out);
+  return it;
+}
+
+/* psim: num_offsets contiguous fields of sites_on_node su3_vectors; out: 7 doubles per offset */
+int milcref_multicg(const Real *src, Real *psim, const double *offsets, int num_offsets,
+                    int parity, int max, int nrest, double resid, double relresid,
+                    double *out) {
+  quark_invert_control *qic = (quark_invert_control *)calloc(num_offsets, sizeof(*qic));
+  ks_param *ksp = (ks_param *)calloc(num_offsets, sizeof(*ksp));
+  su3_vector **pp = (su3_vector **)malloc(num_offsets * sizeof(*pp));
+  int j, it;
+  for (j = 0; j < num_offsets; j++) {
+    qic[j].prec = MILC_PRECISION; qic[j].max = max; qic[j].nrestart = nrest;
+    qic[j].parity = parity; qic[j].nsrc = 1;
+    qic[j].resid = resid; qic[j].relresid = relresid;
+    ksp[j].offset = offsets[j];
+    pp[j] = (su3_vector *)psim + (size_t)j * sites_on_node;
+  }
+  it = ks_multicg_offset_field_cpu((su3_vector *)src, pp, ksp, num_offsets, qic, h_fn);
+  for (j = 0; j < num_offsets; j++) h_unpack(&qic[j], out + 7 * j);
+  free(qic); free(ksp); free(pp);
+  return it;
+}
+
+/* Back-to-back dslash timing for the CPU baseline.  Returns seconds per
+   dslash_fn_field call on one parity (src is read on the other parity). */
+double milcref_time_dslash(const Real *src, Real *dest, int parity, int ncalls) {
+  int k;
+  double t0;
+  dslash_fn_field((su3_vector *)src, (su3_vector *)dest, parity, h_fn); /* warm */
+  t0 = dclock();
+  for (k = 0; k < ncalls; k++)
+    dslash_fn_field((su3_vector *)src, (su3_vector *)dest, parity, h_fn);
+  return (dclock() - t0) / ncalls;
+}

@@ -1,0 +1,55 @@
+/* oracle/ref_harness/lattice.h -- TEST INFRASTRUCTURE, not product code.
+ *
+ * Minimal application header that lets the reference's own hot-path sources
+ * (generic_ks/dslash_fn_dblstore.c, d_congrad5_fn_milc.c, ks_multicg_offset.c,
+ * fn_links_milc.c, generic/com_vanilla.c, layout_hyper_prime.c, make_lattice.c)
+ * compile WHERE THEY LIE under /root/reference, into oracle/_ref/.  Every MILC
+ * application supplies its own lattice.h (cf. ks_spectrum/lattice.h:24-124); this
+ * one declares only the globals and site members those files touch.
+ */
+#ifndef _LATTICE_H
+#define _LATTICE_H
+
+#include "defines.h"
+#include "params.h"
+#include "../include/random.h"
+#include "../include/io_lat.h"
+#include "../include/generic_ks.h"
+#include "../include/fermion_links.h"
+#include "../include/su3.h"
+
+typedef struct {
+  short x, y, z, t;
+  char parity;
+  int index;
+  int space1;
+  su3_matrix link[4] ALIGNMENT;
+  Real phase[4];
+} site;
+
+#ifdef CONTROL
+#define EXTERN
+#else
+#define EXTERN extern
+#endif
+
+EXTERN int nx, ny, nz, nt;
+EXTERN int iseed;
+EXTERN int niter, nrestart;
+EXTERN int volume;
+EXTERN params param;
+EXTERN int total_iters;
+EXTERN Real u0, mass;
+EXTERN Real rsqmin, rsqprop;
+EXTERN size_t sites_on_node;
+EXTERN size_t even_sites_on_node;
+EXTERN size_t odd_sites_on_node;
+EXTERN int number_of_nodes;
+EXTERN int this_node;
+EXTERN int phases_in;
+EXTERN site *lattice;
+
+#define N_POINTERS 16
+EXTERN char **gen_pt[N_POINTERS];
+
+#endif /* _LATTICE_H */
