@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- HISQ staggered solve benchmark (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one complete single-mass HISQ CG solve (4m^2 - D^2) x = b, mass 0.05, from a zero
+initial guess to the requested residual, on the synthetic random-SU(3) 32^3x64 lattice
+(BASELINE.json configs[1]).  The metric is MILC's own: GFLOP/s = 1187 flop x V x iterations /
+time (generic_ks/d_congrad5_fn_milc.c:81-83,390-396), so it compares directly with the
+reference's `CONGRAD5:` lines and is independent of the iteration count.
+
+  value     solve with source/solution resident in HBM (CUDA events on the library stream)
+  e2e       same solve through the host-buffer C-ABI call (b200ks_congrad = the
+            ks_congrad_parity_gpu seam): pinned host source + guess copied H2D and the solution
+            copied D2H inside the timed region, every step
+  roofline  the dominant kernel (dslash_kernel, double): algorithmic bytes 2400 B/site x Vh
+            sites per launch / live CUDA-event launch time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference
+            the reference's own CPU solver (oracle/_ref, built from /root/reference sources with
+            OpenMP) on the box's host cores, on a bounded sample (fixed iteration count) of the
+            same workload
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+EVEN, ODD = 2, 1
+DIMS = (32, 32, 32, 64)
+MASS = 0.05
+RESID = 1e-10
+NITER, NRESTART = 2000, 10
+CG_FLOP_PER_SITE = 1187.0      # d_congrad5_fn_milc.c:81-83
+DSLASH_FLOP_PER_SITE = 1146.0  # 16 x 66 + 15 x 6
+DSLASH_BYTES_PER_SITE = {2: 2400.0, 1: 1200.0}  # w*(8*18 + 8*18 + 6 + 6)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per dslash launch from the committed ncu --set full summary, if any."""
+    p = os.path.join(ROOT, "profiles", "dslash_ncu_summary.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["dram_bytes_per_launch"])
+        except Exception:
+            return None
+    return None
+
+
+def make_workload(dims):
+    from milc_qcd_b200 import fields as F
+    fat, lng = F.make_links(dims, seed=1234)
+    src = F.make_source(dims, seed=5678, parity=EVEN)
+    return fat, lng, src
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_sample(dims, fat, lng, src, iters, repeats=1):
+    """Times the reference's CPU CG (oracle/_ref, OpenMP over all host cores; or the oracle
+    port if _ref was not built) for a fixed number of iterations.  Returns (gflops, meta)."""
+    from oracle import pyoracle
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    V = int(np.prod(dims))
+    times = []
+    if pyoracle.ref_available("_omp"):
+        kind = "reference"
+        ref = pyoracle.MilcRef(dims, "_omp")
+        ref.set_links(fat, lng)
+        for _ in range(repeats):
+            x = np.zeros_like(src)
+            t0 = time.perf_counter()
+            it, q = ref.congrad(src, x, MASS, EVEN, iters, 1, RESID)
+            times.append((time.perf_counter() - t0, it))
+        impl = "MILC d_congrad5_fn_milc.c + dslash_fn_dblstore.c (oracle/_ref, -O3 -DFAST -DOMP)"
+    else:
+        kind = "port"
+        o = pyoracle.Oracle()
+        for _ in range(repeats):
+            x = np.zeros_like(src)
+            t0 = time.perf_counter()
+            it, q = o.congrad(dims, fat, lng, src, x, MASS, EVEN, iters, 1, RESID)
+            times.append((time.perf_counter() - t0, it))
+        impl = "oracle/ks_oracle.c port (OpenMP dslash)"
+    return times, dict(kind=kind, cores=cores, impl=impl, V=V)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path on the host cores, bounded sample."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    dims = DIMS
+    V = int(np.prod(dims))
+    fat, lng, src = make_workload(dims)
+    iters = 10  # + the initial and the final true-residual evaluation = 11 counted iterations
+    times, meta = cpu_reference_sample(dims, fat, lng, src, iters, repeats=args.warmup + args.steps)
+    timed = times[args.warmup:]
+    tot_t = sum(t for t, _ in timed)
+    tot_it = sum(it for _, it in timed)
+    gflops = CG_FLOP_PER_SITE * V * tot_it / tot_t / 1e9
+    sample = "CG capped at %d iterations per step on the full 32^3x64 workload (%d counted iterations/step)" % (
+        iters, timed[0][1])
+    line = {
+        "impl": "reference", "metric": "hisq_cg_gflops", "value": gflops, "unit": "GFLOP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / max(len(timed), 1), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "HISQ single-mass CG, mass 0.05, synthetic random-SU(3) 32^3x64 (BASELINE configs[1])",
+                   "lattice": list(dims), "implementation": meta["impl"]},
+        "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": meta["cores"], "kind": meta["kind"],
+                         "sample": sample},
+        "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    from milc_qcd_b200 import api
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run" % args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    if world > 1:
+        raise SystemExit("bench.py: multi-GPU solve not implemented yet in this revision")
+    torch.cuda.set_device(local_rank)
+    dims = DIMS
+    V = int(np.prod(dims))
+    Vh = V // 2
+
+    t_gen = time.perf_counter()
+    fat, lng, src = make_workload(dims)
+    t_gen = time.perf_counter() - t_gen
+    ctx = api.Context(dims, device=local_rank)
+    t_up = time.perf_counter()
+    ctx.load_links(fat, lng)
+    t_up = time.perf_counter() - t_up
+    stream = torch.cuda.ExternalStream(ctx.lib.b200ks_stream(ctx.h))
+
+    # resident vectors
+    vb, vx = ctx.vec_create(), ctx.vec_create()
+    ctx.vec_upload(vb, src, EVEN)
+
+    def solve_resident():
+        ctx.vec_zero(vx, EVEN)
+        return ctx.congrad_dev(vb, vx, MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=args.mixed)
+
+    # pinned host buffers for the end-to-end leg
+    pin_b = torch.from_numpy(src).pin_memory()
+    pin_x = torch.zeros_like(pin_b).pin_memory()
+    hb, hx = pin_b.numpy(), pin_x.numpy()
+
+    def solve_host():
+        hx[:Vh] = 0
+        return ctx.congrad(hb, hx, MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=args.mixed)
+
+    for _ in range(args.warmup):
+        it, res = solve_resident()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    iters_total, dev_s = 0, 0.0
+    for _ in range(args.steps):
+        it, res = solve_resident()
+        iters_total += it
+        dev_s += res["device_seconds"]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+
+    # dominant-kernel roofline, live
+    n_ds = 100
+    ds_ms = {p: ctx.dslash_time(p, EVEN, n_ds) for p in (2, 1)}
+    clocks = sampler.stop()
+
+    # end-to-end leg (host buffers)
+    solve_host()
+    torch.cuda.synchronize()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    t_w = time.perf_counter()
+    it_e2e = 0
+    for _ in range(args.steps):
+        it, res_h = solve_host()
+        it_e2e += it
+    e3.record(stream)
+    torch.cuda.synchronize()
+    t_w = time.perf_counter() - t_w
+    ms_e2e = max(e2.elapsed_time(e3), 1e3 * t_w)
+
+    # independent true-residual check of the last host solution (device operator)
+    vt, vr = ctx.vec_create(), ctx.vec_create()
+    ctx.vec_upload(vr, hx, EVEN)
+    ctx.dslash_dev(vr, vt, ODD)
+    ctx.dslash_dev(vt, vt, EVEN)
+    tt = np.zeros_like(src)
+    ctx.vec_download(vt, tt, EVEN)
+    r = src[:Vh] - (4 * MASS * MASS * hx[:Vh] - tt[:Vh])
+    true_resid = float(np.linalg.norm(r) / np.linalg.norm(src[:Vh]))
+
+    value = CG_FLOP_PER_SITE * V * iters_total / (ms_total * 1e-3) / 1e9
+    e2e_value = CG_FLOP_PER_SITE * V * it_e2e / (ms_e2e * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    ach = DSLASH_BYTES_PER_SITE[2] * Vh / (ds_ms[2] * 1e-3) / 1e9
+    half_bytes = Vh * 6 * 8
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            times, meta = cpu_reference_sample(dims, fat, lng, src, 10, repeats=2)
+            t, itc = times[-1]
+            cpu = {"value": CG_FLOP_PER_SITE * V * itc / t / 1e9, "unit": "GFLOP/s", "cores": meta["cores"],
+                   "kind": meta["kind"],
+                   "sample": "CG capped at 10 iterations (%d counted) on the full 32^3x64 workload, %s" % (itc, meta["impl"])}
+        except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
+            cpu = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
+
+    line = {
+        "metric": "hisq_cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64" if args.mixed == 0 else "f64 outer / f32 inner", "data": "synthetic",
+        "config": {"workload": "HISQ single-mass CG, mass 0.05, resid 1e-10, synthetic random-SU(3) 32^3x64 (BASELINE configs[1])",
+                   "lattice": list(dims), "l2": "links (2.4 GB) exceed L2 every dslash; no flush needed",
+                   "flop_convention": "MILC 1187 flop/site/iteration", "mixed_precision": args.mixed},
+        "cg_iters_per_solve": iters_total / args.steps, "cg_time_to_solution_s": ms_total * 1e-3 / args.steps,
+        "cg_device_seconds": dev_s / args.steps, "true_residual": true_resid, "converged": res["converged"],
+        "dslash_gflops": {"f64": DSLASH_FLOP_PER_SITE * Vh / (ds_ms[2] * 1e-3) / 1e9,
+                          "f32": DSLASH_FLOP_PER_SITE * Vh / (ds_ms[1] * 1e-3) / 1e9},
+        "dslash_ms": {"f64": ds_ms[2], "f32": ds_ms[1]},
+        "roofline": {"bound": "hbm", "kernel": "dslash_kernel<double> (recon 18/18)", "achieved": ach, "peak": peak,
+                     "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": ncu_traffic(),
+                     "algorithmic_bytes_per_launch": DSLASH_BYTES_PER_SITE[2] * Vh,
+                     "f32_achieved": DSLASH_BYTES_PER_SITE[1] * Vh / (ds_ms[1] * 1e-3) / 1e9},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": 2 * half_bytes,
+                "d2h_bytes_per_step": half_bytes, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks,
+        "setup": {"gen_links_s": t_gen, "load_links_s": t_up, "device_bytes": ctx.device_bytes()},
+    }
+    print(json.dumps(line))
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mixed", type=int, default=0, help="0 pure double, 1 double/single, 2 double/half")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

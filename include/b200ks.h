@@ -1,0 +1,166 @@
+/* include/b200ks.h -- C ABI of the B200-native improved-staggered (HISQ/asqtad) solver.
+ *
+ * Plain C, plain pointers and sizes; no MILC types, no torch types.  This is the
+ * drop-in boundary for ONE hot path of milc-qcd/milc_qcd: the fat+Naik Dirac stencil
+ * inside the single-mass CG and the multi-shift CG.  Each entry point names the
+ * reference interface it replaces (paths relative to the MILC tree).
+ *
+ * Host arrays are MILC's own layout:
+ *   site index i = node_index(x,y,z,t): lex = x + nx*(y + ny*(z + nz*t)), even sites
+ *   first (lex/2) then odd ((lex+V)/2)          generic/layout_hyper_prime.c:509-520
+ *   su3_vector  = 3 complex  (re,im) -> 6 reals  include/milc_datatypes.h:49,56
+ *   su3_matrix  = e[row][col] complex -> 18 reals, links stored fat[4*i+dir], dir=X,Y,Z,T
+ *                                               generic_ks/dslash_fn.c:453,458
+ * host_prec is MILC_PRECISION of the caller: 1 = float arrays, 2 = double arrays.
+ *
+ * Error convention: functions return 0 on success and a negative B200KS_E* code on
+ * failure; b200ks_last_error() gives the message.  The MILC-facing shims turn a failure
+ * into MILC's own convention, printf + terminate(1) (generic/com_vanilla.c:203-211).
+ * There is NO CPU fallback: without a usable sm_100 device b200ks_create fails.
+ *
+ * Threading: like the reference (file-static temporaries, generic_ks/dslash_fn.c:26-28)
+ * a context is single-threaded and non-reentrant.
+ */
+#ifndef B200KS_H
+#define B200KS_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200KS_VERSION 100
+
+/* parity codes, include/macros.h:68-70 */
+#define B200KS_EVEN 2
+#define B200KS_ODD 1
+#define B200KS_EVENANDODD 3
+
+/* device arithmetic/storage precision of a solve or a dslash */
+#define B200KS_PREC_HALF 0   /* int16 fixed point + fp32 site norm (inner solves only) */
+#define B200KS_PREC_SINGLE 1
+#define B200KS_PREC_DOUBLE 2
+
+#define B200KS_EINVAL (-1)
+#define B200KS_ECUDA (-2)
+#define B200KS_ENOMEM (-3)
+#define B200KS_ESTATE (-4)
+#define B200KS_ECOMM (-5)
+
+#define B200KS_MAX_SHIFTS 32 /* MAX_MMINV_NMASSES, include/imp_ferm_links.h:485 */
+
+typedef struct b200ks_ctx b200ks_ctx;
+
+/* Solver controls = the fields of quark_invert_control the solvers read
+ * (include/generic_quark_types.h:167-190) + QudaInvertArgs_t.mixed_precision
+ * (generic_ks/d_congrad5_fn_gpu.c:104-111). */
+typedef struct {
+  int parity;          /* B200KS_EVEN or B200KS_ODD (qic->parity)                    */
+  int max_iter;        /* iterations per restart (qic->max)                          */
+  int nrestart;        /* max restarts (qic->nrestart)                               */
+  double resid;        /* target sqrt(|r|^2/|b|^2), NOT squared (qic->resid)         */
+  double relresid;     /* Fermilab relative residual target, 0 = unused              */
+  int mixed_precision; /* 0 pure double; 1 double outer + single inner; 2 + half     */
+  int check_interval;  /* host convergence poll every n iterations; 0 = default      */
+} b200ks_invert_args;
+
+/* Solver outputs = the fields the solvers write back into quark_invert_control
+ * (generic_ks/d_congrad5_fn_milc.c:125-133,220-225,350-354,370-381). */
+typedef struct {
+  double final_rsq;    /* true |r|^2/|b|^2 at exit                                   */
+  double final_relrsq; /* Fermilab relative residual at exit                         */
+  double size_r;       /* last recursive |r|^2/|b|^2                                 */
+  double size_relr;
+  int final_iters;
+  int final_restart;
+  int converged;
+  double device_seconds; /* CUDA-event time of the solve proper (no host<->device copies) */
+} b200ks_invert_result;
+
+int b200ks_version(void);
+const char *b200ks_last_error(void);
+
+/* Number of sm_100 devices visible (0 => nothing can run; callers must fail loudly). */
+int b200ks_device_count(void);
+
+/* Single-GPU context for an nx*ny*nz*nt lattice on CUDA device `device`.
+ * Replaces initialize_quda()/qudaInit (generic/milc_to_quda_utilities.c:11-44). */
+b200ks_ctx *b200ks_create(const int latsize[4], int device);
+
+/* One-rank-per-GPU context: global lattice `latsize` split over `grid[4]` ranks
+ * (t first, then z: grid = {1,1,gz,gt}); this process owns the sub-lattice at grid
+ * coordinates derived from `rank` (t slowest).  nccl_unique_id is the 128-byte
+ * ncclUniqueId shared by all ranks (obtain with b200ks_comm_unique_id on rank 0 and
+ * broadcast it by any means).  Host arrays passed to this context are the LOCAL
+ * sub-lattice in MILC order, exactly what a MILC MPI rank holds
+ * (generic/layout_hyper_prime.c:186-229). */
+b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4], int rank, int nranks,
+                               const void *nccl_unique_id, int device);
+int b200ks_comm_unique_id(void *out128);
+
+void b200ks_destroy(b200ks_ctx *ctx);
+
+/* Upload fat and long links (MILC order, su3_matrix[4*V]) and re-lay them out on the
+ * device.  Replaces the implicit link refresh of the QUDA seam
+ * (generic_ks/d_congrad5_fn_gpu.c:121-126).  long_recon = 18 or 13. */
+int b200ks_load_links(b200ks_ctx *ctx, const void *fat, const void *lng, int host_prec,
+                      int long_recon);
+
+/* dest(parity sites) = D src.  Only `parity` sites of dest are written; src == dest is
+ * legal for EVEN/ODD.  Replaces dslash_fn_field (generic_ks/dslash_fn.c:306-356,
+ * generic_ks/dslash_fn_dblstore.c:285-304). */
+int b200ks_dslash(b200ks_ctx *ctx, const void *src, void *dest, int parity, int host_prec);
+
+/* Single-mass CG: (4 m^2 - D D) dest = src on args->parity; dest = initial guess in,
+ * solution out.  Replaces ks_congrad_parity_gpu / qudaInvert
+ * (generic_ks/d_congrad5_fn_gpu.c:35-172) with the CPU algorithm's semantics
+ * (generic_ks/d_congrad5_fn_milc.c:60-407).  Returns iterations (>= 0) or an error. */
+int b200ks_congrad(b200ks_ctx *ctx, const void *src, void *dest, double mass,
+                   const b200ks_invert_args *args, b200ks_invert_result *res, int host_prec);
+
+/* Multi-shift CG: (offset_j - D D) psim[j] = src for all j.  psim[j] are zeroed first.
+ * Replaces ks_multicg_offset_field_gpu / qudaMultishiftInvert
+ * (generic_ks/ks_multicg_offset_gpu.c:38-252) with the CPU algorithm's semantics
+ * (generic_ks/ks_multicg_offset.c:63-505).  res has num_offsets entries. */
+int b200ks_multicg(b200ks_ctx *ctx, const void *src, void *const *psim, const double *offsets,
+                   int num_offsets, const b200ks_invert_args *args, b200ks_invert_result *res,
+                   int host_prec);
+
+/* ---- device-resident interface (benchmarks, resident solve sequences) -------------- */
+
+/* Device colour-vector fields of one context, double precision, both parities. */
+int b200ks_vec_create(b200ks_ctx *ctx);             /* returns handle >= 0 */
+int b200ks_vec_free(b200ks_ctx *ctx, int vec);
+int b200ks_vec_upload(b200ks_ctx *ctx, int vec, const void *host, int parity, int host_prec);
+int b200ks_vec_download(b200ks_ctx *ctx, int vec, void *host, int parity, int host_prec);
+int b200ks_vec_zero(b200ks_ctx *ctx, int vec, int parity);
+int b200ks_vec_gaussian(b200ks_ctx *ctx, int vec, int parity, unsigned long long seed);
+int b200ks_vec_norm2(b200ks_ctx *ctx, int vec, int parity, double *out);
+
+/* Synthetic HISQ-like links generated on the device (for volumes whose host copy
+ * would not fit in host RAM, SURVEY.md section 7 "Host memory at the 96^3x192 point"). */
+int b200ks_links_synthetic(b200ks_ctx *ctx, unsigned long long seed, int long_recon);
+
+int b200ks_dslash_dev(b200ks_ctx *ctx, int vsrc, int vdest, int parity, int prec);
+int b200ks_congrad_dev(b200ks_ctx *ctx, int vsrc, int vdest, double mass,
+                       const b200ks_invert_args *args, b200ks_invert_result *res);
+int b200ks_multicg_dev(b200ks_ctx *ctx, int vsrc, const int *vpsim, const double *offsets,
+                       int num_offsets, const b200ks_invert_args *args,
+                       b200ks_invert_result *res);
+
+/* Times n back-to-back dslash launches (one parity) with CUDA events on the library's
+ * stream; returns milliseconds per launch in *ms_per_launch. */
+int b200ks_dslash_time(b200ks_ctx *ctx, int prec, int parity, int n, double *ms_per_launch);
+
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+long long b200ks_launch_count(b200ks_ctx *ctx);
+/* Raw CUDA stream (cudaStream_t) the library launches on, for external event timing. */
+void *b200ks_stream(b200ks_ctx *ctx);
+/* Bytes of device memory held by the context. */
+size_t b200ks_device_bytes(b200ks_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200KS_H */

@@ -1,0 +1,284 @@
+"""Host-side (numpy) face of libb200ks, mirroring the reference's operator interface.
+
+The names, argument meaning and outputs follow MILC's solver API for this path
+(``include/imp_ferm_links.h:47-282``):
+
+* :func:`dslash_fn_field`            <- ``dslash_fn_field(src, dest, parity, fn)``
+* :func:`ks_congrad_parity_gpu`      <- ``ks_congrad_parity_gpu(src, dest, qic, mass, fn)``
+* :func:`ks_congrad_field`           <- ``ks_congrad_field`` (EVEN / ODD / EVENANDODD fan-out,
+  ``generic_ks/d_congrad5_fn.c:16-60``)
+* :func:`ks_multicg_offset_field_gpu` <- ``ks_multicg_offset_field_gpu(src, psim, ksp, n, qic, fn)``
+
+with :class:`quark_invert_control`, :class:`ks_param` and :class:`fn_links_t` mirroring
+``include/generic_quark_types.h:131-139,167-190`` and ``include/fn_links.h:12-20``.  All of it
+is a thin veneer over the C ABI in ``include/b200ks.h``; the compute is hand-written CUDA.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import EVEN, ODD, EVENANDODD, InvertArgs, InvertResult, check
+
+
+@dataclass
+class quark_invert_control:
+    """include/generic_quark_types.h:167-190 (fields used by the KS solvers)."""
+    prec: int = 2
+    min: int = 0
+    max: int = 500
+    nrestart: int = 5
+    parity: int = EVEN
+    start_flag: int = 1
+    nsrc: int = 1
+    resid: float = 1e-10
+    relresid: float = 0.0
+    final_rsq: float = 0.0
+    final_relrsq: float = 0.0
+    size_r: float = 0.0
+    size_relr: float = 0.0
+    converged: int = 1
+    final_iters: int = 0
+    final_restart: int = 0
+    # not in MILC: selects the inner precision like the HALF_MIXED / MAX_MIXED build macros
+    mixed_precision: int = 0
+    device_seconds: float = 0.0
+
+
+@dataclass
+class ks_param:
+    """include/generic_quark_types.h:131-139."""
+    mass: float = 0.0
+    offset: float = 0.0
+    residue: float = 0.0
+    naik_term_epsilon: float = 0.0
+    naik_term_epsilon_index: int = 0
+
+
+@dataclass
+class fn_links_t:
+    """include/fn_links.h:12-20: fat[4*i+dir], lng[4*i+dir] as (V,4,3,3,2) arrays."""
+    fat: np.ndarray = None
+    lng: np.ndarray = None
+    eps_naik: float = 0.0
+    notify_quda_new_links: int = 1
+    dims: tuple = field(default=None)
+
+
+def _host_prec(a):
+    if a.dtype == np.float64:
+        return 2
+    if a.dtype == np.float32:
+        return 1
+    raise TypeError("MILC fields are float32 (PRECISION=1) or float64 (PRECISION=2)")
+
+
+def _ptr(a):
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous (MILC host layout)")
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One lattice on one GPU (``b200ks_create``)."""
+
+    def __init__(self, dims, device=0):
+        self.lib = _lib.load()
+        self.dims = tuple(int(d) for d in dims)
+        arr = (C.c_int * 4)(*self.dims)
+        self.h = self.lib.b200ks_create(arr, device)
+        if not self.h:
+            raise _lib.B200KSError("b200ks_create failed: %s" % self.lib.b200ks_last_error().decode())
+        self.volume = int(np.prod(self.dims))
+        self._links_of = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200ks_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- links -----------------------------------------------------------------------------
+    def load_links(self, fat, lng, long_recon=18):
+        if fat.dtype != lng.dtype:
+            raise TypeError("fat and lng must have the same precision")
+        n = self.volume * 4 * 18
+        if fat.size != n or lng.size != n:
+            raise ValueError("links must hold su3_matrix[4*volume]")
+        check(self.lib.b200ks_load_links(self.h, _ptr(fat), _ptr(lng), _host_prec(fat), long_recon),
+              "b200ks_load_links")
+
+    def ensure_links(self, fn):
+        """Device link cache keyed like the QUDA seam (fn identity + notify flag,
+        generic_ks/d_congrad5_fn_gpu.c:121-126)."""
+        if self._links_of is not fn or fn.notify_quda_new_links:
+            self.load_links(fn.fat, fn.lng)
+            self._links_of = fn
+            fn.notify_quda_new_links = 0
+
+    # -- host-buffer operators ------------------------------------------------------------------
+    def dslash(self, src, dest, parity):
+        check(self.lib.b200ks_dslash(self.h, _ptr(src), _ptr(dest), parity, _host_prec(src)), "b200ks_dslash")
+        return dest
+
+    def congrad(self, src, dest, mass, parity, max_iter, nrestart, resid, relresid=0.0,
+                mixed_precision=0, check_interval=0):
+        args = InvertArgs(parity, max_iter, nrestart, resid, relresid, mixed_precision, check_interval)
+        res = InvertResult()
+        it = check(self.lib.b200ks_congrad(self.h, _ptr(src), _ptr(dest), mass, C.byref(args), C.byref(res),
+                                           _host_prec(src)), "b200ks_congrad")
+        return it, res.as_dict()
+
+    def multicg(self, src, psim, offsets, parity, max_iter, nrestart, resid, mixed_precision=0,
+                check_interval=0):
+        n = len(offsets)
+        args = InvertArgs(parity, max_iter, nrestart, resid, 0.0, mixed_precision, check_interval)
+        res = (InvertResult * max(n, 1))()
+        offs = (C.c_double * max(n, 1))(*[float(o) for o in offsets])
+        ptrs = (C.c_void_p * max(n, 1))(*[p.ctypes.data for p in psim])
+        it = check(self.lib.b200ks_multicg(self.h, _ptr(src), ptrs, offs, n, C.byref(args), res,
+                                           _host_prec(src)), "b200ks_multicg")
+        return it, [res[j].as_dict() for j in range(n)]
+
+    # -- device-resident interface --------------------------------------------------------------
+    def vec_create(self):
+        return check(self.lib.b200ks_vec_create(self.h), "b200ks_vec_create")
+
+    def vec_free(self, v):
+        check(self.lib.b200ks_vec_free(self.h, v), "b200ks_vec_free")
+
+    def vec_upload(self, v, host, parity=EVENANDODD):
+        check(self.lib.b200ks_vec_upload(self.h, v, _ptr(host), parity, _host_prec(host)), "b200ks_vec_upload")
+
+    def vec_download(self, v, host, parity=EVENANDODD):
+        check(self.lib.b200ks_vec_download(self.h, v, _ptr(host), parity, _host_prec(host)), "b200ks_vec_download")
+        return host
+
+    def vec_zero(self, v, parity=EVENANDODD):
+        check(self.lib.b200ks_vec_zero(self.h, v, parity), "b200ks_vec_zero")
+
+    def vec_norm2(self, v, parity=EVENANDODD):
+        out = C.c_double()
+        check(self.lib.b200ks_vec_norm2(self.h, v, parity, C.byref(out)), "b200ks_vec_norm2")
+        return out.value
+
+    def dslash_dev(self, vsrc, vdest, parity, prec=2):
+        check(self.lib.b200ks_dslash_dev(self.h, vsrc, vdest, parity, prec), "b200ks_dslash_dev")
+
+    def congrad_dev(self, vsrc, vdest, mass, parity, max_iter, nrestart, resid, relresid=0.0,
+                    mixed_precision=0, check_interval=0):
+        args = InvertArgs(parity, max_iter, nrestart, resid, relresid, mixed_precision, check_interval)
+        res = InvertResult()
+        it = check(self.lib.b200ks_congrad_dev(self.h, vsrc, vdest, mass, C.byref(args), C.byref(res)),
+                   "b200ks_congrad_dev")
+        return it, res.as_dict()
+
+    def multicg_dev(self, vsrc, vpsim, offsets, parity, max_iter, nrestart, resid, mixed_precision=0,
+                    check_interval=0):
+        n = len(offsets)
+        args = InvertArgs(parity, max_iter, nrestart, resid, 0.0, mixed_precision, check_interval)
+        res = (InvertResult * max(n, 1))()
+        offs = (C.c_double * max(n, 1))(*[float(o) for o in offsets])
+        hs = (C.c_int * max(n, 1))(*vpsim)
+        it = check(self.lib.b200ks_multicg_dev(self.h, vsrc, hs, offs, n, C.byref(args), res), "b200ks_multicg_dev")
+        return it, [res[j].as_dict() for j in range(n)]
+
+    def dslash_time(self, prec, parity, n):
+        out = C.c_double()
+        check(self.lib.b200ks_dslash_time(self.h, prec, parity, n, C.byref(out)), "b200ks_dslash_time")
+        return out.value
+
+    def launch_count(self):
+        return int(self.lib.b200ks_launch_count(self.h))
+
+    def device_bytes(self):
+        return int(self.lib.b200ks_device_bytes(self.h))
+
+
+# ---- MILC-named operators ------------------------------------------------------------------------
+_ctx_cache = {}
+
+
+def _context_for(fn):
+    dims = tuple(fn.dims)
+    ctx = _ctx_cache.get(dims)
+    if ctx is None:
+        ctx = _ctx_cache[dims] = Context(dims)
+    ctx.ensure_links(fn)
+    return ctx
+
+
+def finalize():
+    """qudaFinalize analogue: drop cached contexts."""
+    for ctx in _ctx_cache.values():
+        ctx.close()
+    _ctx_cache.clear()
+
+
+def dslash_fn_field(src, dest, parity, fn):
+    """generic_ks/dslash_fn.c:306-356: dest(parity) = D src."""
+    if fn is None:
+        raise ValueError("dslash_fn_field: invalid fn links!")
+    ctx = _context_for(fn)
+    if parity == EVENANDODD and src is dest:
+        raise ValueError("in-place dslash needs a single parity")
+    return ctx.dslash(src, dest, parity)
+
+
+def _store(qic, res):
+    for k in ("final_rsq", "final_relrsq", "size_r", "size_relr", "final_iters", "final_restart",
+              "converged", "device_seconds"):
+        setattr(qic, k, res[k])
+
+
+def ks_congrad_parity_gpu(t_src, t_dest, qic, mass, fn):
+    """generic_ks/d_congrad5_fn_gpu.c:35-172 with the CPU solver's semantics
+    (generic_ks/d_congrad5_fn_milc.c:60-407).  Returns iterations, fills qic."""
+    if fn is None:
+        raise ValueError("ks_congrad_parity_gpu: Called with NULL fn")
+    if qic.parity not in (EVEN, ODD):
+        raise ValueError("ks_congrad_parity_gpu: Unrecognised parity")
+    ctx = _context_for(fn)
+    it, res = ctx.congrad(t_src, t_dest, mass, qic.parity, qic.max, qic.nrestart, qic.resid, qic.relresid,
+                          qic.mixed_precision)
+    _store(qic, res)
+    return it
+
+
+def ks_congrad_field(src, dest, qic, mass, fn):
+    """generic_ks/d_congrad5_fn.c:16-60: EVENANDODD = EVEN solve then ODD solve."""
+    iters = 0
+    want = qic.parity
+    try:
+        for par in ((EVEN, ODD) if want == EVENANDODD else (want,)):
+            qic.parity = par
+            iters += ks_congrad_parity_gpu(src, dest, qic, mass, fn)
+    finally:
+        qic.parity = want
+    return iters
+
+
+def ks_multicg_offset_field_gpu(src, psim, ksp, num_offsets, qic, fn):
+    """generic_ks/ks_multicg_offset_gpu.c:38-252 with the CPU algorithm's semantics
+    (generic_ks/ks_multicg_offset.c:63-505).  qic is a list with one entry per offset."""
+    if num_offsets == 0:
+        return 0
+    if qic[0].relresid != 0.0:
+        raise ValueError("ks_multicg_offset_field_gpu: GPU code does not yet support a Fermilab-type relative residual")
+    if qic[0].parity == EVENANDODD:
+        raise ValueError("ks_multicg_offset_field_gpu: EVENANDODD not supported")
+    if fn is None:
+        raise ValueError("ks_multicg_offset_field: Called with NULL fn")
+    ctx = _context_for(fn)
+    offsets = [ksp[j].offset for j in range(num_offsets)]
+    it, res = ctx.multicg(src, psim[:num_offsets], offsets, qic[0].parity, qic[0].max, qic[0].nrestart,
+                          qic[0].resid, qic[0].mixed_precision)
+    for j in range(num_offsets):
+        _store(qic[j], res[j])
+    return it

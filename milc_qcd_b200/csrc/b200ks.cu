@@ -1,0 +1,878 @@
+// b200ks.cu -- context, field management, solver drivers and the C ABI of libb200ks.
+//
+// Reference behaviour reproduced here (paths relative to the MILC tree):
+//   single-mass CG   generic_ks/d_congrad5_fn_milc.c:60-407   (restart/true-residual logic,
+//                    FEWSUMS arithmetic, iteration counting, qic outputs)
+//   multi-shift CG   generic_ks/ks_multicg_offset.c:63-505
+//   dslash           generic_ks/dslash_fn_dblstore.c:311-562
+// The boundary these replace is the QUDA seam: d_congrad5_fn_gpu.c:35-172,
+// ks_multicg_offset_gpu.c:38-252, dslash_fn.c:306-344.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/b200ks.h"
+#include "blas.cuh"
+#include "dslash.cuh"
+
+using namespace b200ks;
+
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(B200KS_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+  } while (0)
+#define CHK(call)                  \
+  do {                             \
+    int r_ = (call);               \
+    if (r_ < 0) return r_;         \
+  } while (0)
+
+struct DevVec {          // one colour-vector field, both parities
+  void *p[2] = {nullptr, nullptr};
+  int prec = 0;          // B200KS_PREC_*
+};
+
+struct Links {           // fat + long links of one precision, both parities
+  void *fat[2] = {nullptr, nullptr};
+  void *lng[2] = {nullptr, nullptr};
+  bool valid = false;
+};
+
+struct b200ks_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int global[4];
+  Geom g;
+  Links links[3];        // indexed by B200KS_PREC_*
+  int link_master = 0;   // precision the links were loaded at
+  std::vector<DevVec *> user;   // user handles (double)
+  std::vector<DevVec *> pool[3];  // solver temporaries by precision
+  ReduceWs ws;
+  int max_blocks = 0;
+  CgState *d_state = nullptr;
+  CgState *h_state = nullptr;   // pinned mirror
+  double *d_scal = nullptr;     // scratch result slots
+  double *h_scal = nullptr;     // pinned
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  long long launches = 0;
+  size_t bytes = 0;
+};
+
+static size_t real_size(int prec) { return prec == B200KS_PREC_DOUBLE ? 8 : 4; }
+static int nblocks(int n) { return (n + kBlock - 1) / kBlock; }
+
+static int dev_alloc(b200ks_ctx *c, void **p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess)
+    return fail(B200KS_ENOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+  c->bytes += bytes;
+  return 0;
+}
+static void dev_free(b200ks_ctx *c, void *p, size_t bytes) {
+  if (p) {
+    cudaFree(p);
+    c->bytes -= bytes;
+  }
+}
+
+static size_t vec_bytes(const b200ks_ctx *c, int prec) { return (size_t)3 * c->g.stride * 2 * real_size(prec); }
+static size_t link_bytes(const b200ks_ctx *c, int prec) { return (size_t)36 * c->g.lstride * 2 * real_size(prec); }
+
+static int vec_new(b200ks_ctx *c, int prec, DevVec **out) {
+  DevVec *v = new DevVec;
+  v->prec = prec;
+  for (int p = 0; p < 2; p++) {
+    int r = dev_alloc(c, &v->p[p], vec_bytes(c, prec));
+    if (r < 0) { delete v; return r; }
+    cudaMemsetAsync(v->p[p], 0, vec_bytes(c, prec), c->stream);
+  }
+  *out = v;
+  return 0;
+}
+static void vec_delete(b200ks_ctx *c, DevVec *v) {
+  if (!v) return;
+  for (int p = 0; p < 2; p++) dev_free(c, v->p[p], vec_bytes(c, v->prec));
+  delete v;
+}
+// temporaries are pooled per precision and reused across solves
+static int pool_get(b200ks_ctx *c, int prec, size_t k, DevVec **out) {
+  if (c->pool[prec].size() <= k) c->pool[prec].resize(k + 1, nullptr);
+  if (!c->pool[prec][k]) CHK(vec_new(c, prec, &c->pool[prec][k]));
+  *out = c->pool[prec][k];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int b200ks_version(void) { return B200KS_VERSION; }
+extern "C" const char *b200ks_last_error(void) { return g_err.c_str(); }
+
+extern "C" int b200ks_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  int ok = 0;
+  for (int d = 0; d < n; d++) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, d) == cudaSuccess && pr.major >= 10) ok++;
+  }
+  return ok;
+}
+
+static int setup_geom(b200ks_ctx *c, const int local[4], const int part[4]) {
+  Geom &g = c->g;
+  for (int d = 0; d < 4; d++) {
+    if (local[d] < 2 || (local[d] & 1))
+      return fail(B200KS_EINVAL, "lattice extents must be even and >= 2 (staggered checkerboard, generic_ks/rephase.c:14-16)");
+    g.L[d] = local[d];
+    g.part[d] = part[d];
+  }
+  g.Lxh = g.L[0] / 2;
+  long long vol = (long long)g.L[0] * g.L[1] * g.L[2] * g.L[3];
+  if (vol / 2 > (1ll << 30)) return fail(B200KS_EINVAL, "local volume too large for 32-bit site indices");
+  g.Vh = (int)(vol / 2);
+  int sites = g.Vh, lsites = g.Vh;
+  for (int d = 0; d < 4; d++) {
+    g.faceh[d] = g.Vh / g.L[d];
+    g.ghost[d][0] = g.ghost[d][1] = 0;
+    g.lghost[d] = 0;
+    if (g.part[d]) {
+      if (d < 2) return fail(B200KS_EINVAL, "only z and t may be partitioned");
+      if (g.L[d] < 6) return fail(B200KS_EINVAL, "partitioned extent must be >= 6 (depth-3 ghost zones)");
+      g.ghost[d][0] = sites; sites += 3 * g.faceh[d];
+      g.ghost[d][1] = sites; sites += 3 * g.faceh[d];
+      g.lghost[d] = lsites; lsites += 3 * g.faceh[d];
+    }
+  }
+  g.stride = (sites + 63) / 64 * 64;
+  g.lstride = (lsites + 63) / 64 * 64;
+  g.origin_parity = 0;
+  return 0;
+}
+
+static b200ks_ctx *create_common(const int latsize[4], const int local[4], const int part[4], int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fail(B200KS_ECUDA, "no CUDA device: libb200ks has no CPU fallback");
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) { fail(B200KS_EINVAL, "bad device ordinal"); return nullptr; }
+  cudaDeviceProp pr;
+  cudaGetDeviceProperties(&pr, device);
+  if (pr.major < 10) {
+    fail(B200KS_ECUDA, std::string("device ") + pr.name + " is not sm_100 class; libb200ks ships sm_100a code only");
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { fail(B200KS_ECUDA, "cudaSetDevice failed"); return nullptr; }
+  b200ks_ctx *c = new b200ks_ctx;
+  c->device = device;
+  memcpy(c->global, latsize, sizeof(c->global));
+  if (setup_geom(c, local, part) < 0) { delete c; return nullptr; }
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  c->max_blocks = nblocks(c->g.Vh) + 8;
+  void *p = nullptr;
+  ok = ok && dev_alloc(c, &p, sizeof(double) * 4 * c->max_blocks) == 0;
+  c->ws.partials = (double *)p;
+  ok = ok && dev_alloc(c, &p, sizeof(unsigned) * 8) == 0;
+  c->ws.counter = (unsigned *)p;
+  if (ok) cudaMemset(c->ws.counter, 0, sizeof(unsigned) * 8);
+  ok = ok && dev_alloc(c, &p, sizeof(CgState)) == 0;
+  c->d_state = (CgState *)p;
+  ok = ok && dev_alloc(c, &p, sizeof(double) * 64) == 0;
+  c->d_scal = (double *)p;
+  ok = ok && cudaMallocHost(&c->h_state, sizeof(CgState)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&c->h_scal, sizeof(double) * 64) == cudaSuccess;
+  ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+  if (!ok) {
+    if (g_err.empty()) fail(B200KS_ECUDA, "context allocation failed");
+    b200ks_destroy(c);
+    return nullptr;
+  }
+  memset(c->h_state, 0, sizeof(CgState));
+  return c;
+}
+
+extern "C" b200ks_ctx *b200ks_create(const int latsize[4], int device) {
+  const int part[4] = {0, 0, 0, 0};
+  return create_common(latsize, latsize, part, device);
+}
+
+extern "C" void b200ks_destroy(b200ks_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto v : c->user) vec_delete(c, v);
+  for (int k = 0; k < 3; k++) {
+    for (auto v : c->pool[k]) vec_delete(c, v);
+    for (int p = 0; p < 2; p++) {
+      cudaFree(c->links[k].fat[p]);
+      cudaFree(c->links[k].lng[p]);
+    }
+  }
+  cudaFree(c->ws.partials);
+  cudaFree(c->ws.counter);
+  cudaFree(c->d_state);
+  cudaFree(c->d_scal);
+  if (c->h_state) cudaFreeHost(c->h_state);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" long long b200ks_launch_count(b200ks_ctx *c) { return c ? c->launches : 0; }
+extern "C" void *b200ks_stream(b200ks_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" size_t b200ks_device_bytes(b200ks_ctx *c) { return c ? c->bytes : 0; }
+
+#define LAUNCH(c, kern, grid, ...)                                       \
+  do {                                                                   \
+    kern<<<(grid), kBlock, 0, (c)->stream>>>(__VA_ARGS__);               \
+    (c)->launches++;                                                     \
+  } while (0)
+#define LAUNCH1(c, kern, ...)                                            \
+  do {                                                                   \
+    kern<<<1, 1, 0, (c)->stream>>>(__VA_ARGS__);                         \
+    (c)->launches++;                                                     \
+  } while (0)
+
+static int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(B200KS_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// links
+static int links_alloc(b200ks_ctx *c, int prec) {
+  Links &L = c->links[prec];
+  for (int p = 0; p < 2; p++) {
+    if (!L.fat[p]) CHK(dev_alloc(c, &L.fat[p], link_bytes(c, prec)));
+    if (!L.lng[p]) CHK(dev_alloc(c, &L.lng[p], link_bytes(c, prec)));
+  }
+  return 0;
+}
+
+template <typename T, typename TH>
+static void pack_links_T(b200ks_ctx *c, void *dst, const void *staged) {
+  LAUNCH(c, (pack_link_kernel<T, TH>), nblocks(c->g.Vh), (typename Vec2<T>::type *)dst, (const TH *)staged,
+         c->g.lstride, c->g.Vh);
+}
+
+extern "C" int b200ks_load_links(b200ks_ctx *c, const void *fat, const void *lng, int host_prec, int long_recon) {
+  if (!c || !fat || !lng) return fail(B200KS_EINVAL, "b200ks_load_links: null argument");
+  if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
+  if (long_recon != 18) return fail(B200KS_EINVAL, "long_recon: only 18 is implemented");
+  CU(cudaSetDevice(c->device));
+  const int prec = host_prec;  // master copy at the caller's precision
+  CHK(links_alloc(c, prec));
+  const size_t hs = host_prec == 2 ? 8 : 4;
+  const size_t half_bytes = (size_t)c->g.Vh * 72 * hs;
+  void *stage = nullptr;
+  CHK(dev_alloc(c, &stage, half_bytes));
+  for (int which = 0; which < 2; which++) {
+    const char *h = (const char *)(which == 0 ? fat : lng);
+    for (int p = 0; p < 2; p++) {
+      CU(cudaMemcpyAsync(stage, h + (size_t)p * half_bytes, half_bytes, cudaMemcpyHostToDevice, c->stream));
+      void *dst = which == 0 ? c->links[prec].fat[p] : c->links[prec].lng[p];
+      if (prec == 2) pack_links_T<double, double>(c, dst, stage);
+      else pack_links_T<float, float>(c, dst, stage);
+    }
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  dev_free(c, stage, half_bytes);
+  CHK(check_launch("pack_link_kernel"));
+  c->link_master = prec;
+  for (int k = 0; k < 3; k++) c->links[k].valid = (k == prec);
+  return 0;
+}
+
+// make sure links exist at precision `prec` (device-side down-conversion of the master copy)
+static int links_ensure(b200ks_ctx *c, int prec) {
+  if (c->link_master == 0) return fail(B200KS_ESTATE, "links not loaded (call b200ks_load_links first)");
+  if (c->links[prec].valid) return 0;
+  if (prec == B200KS_PREC_HALF) return fail(B200KS_EINVAL, "half-precision links not implemented yet");
+  CHK(links_alloc(c, prec));
+  const int m = c->link_master;
+  for (int p = 0; p < 2; p++) {
+    for (int which = 0; which < 2; which++) {
+      void *d = which ? c->links[prec].lng[p] : c->links[prec].fat[p];
+      const void *s = which ? c->links[m].lng[p] : c->links[m].fat[p];
+      if (prec == 1 && m == 2)
+        LAUNCH(c, (convert_link_kernel<float, double>), nblocks(c->g.Vh), (float2 *)d, (const double2 *)s, c->g.lstride, c->g.Vh);
+      else if (prec == 2 && m == 1)
+        LAUNCH(c, (convert_link_kernel<double, float>), nblocks(c->g.Vh), (double2 *)d, (const float2 *)s, c->g.lstride, c->g.Vh);
+    }
+  }
+  CHK(check_launch("convert_link_kernel"));
+  c->links[prec].valid = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dslash launcher.  par_out = parity bit of the output sites.
+struct Epi {
+  int kind = 0;            // 0 store, 1 xpay, 2 xpay + dots
+  double s = 0;
+  const DevVec *w = nullptr;
+  const DevVec *r = nullptr;
+  double *red = nullptr;
+  const int *stop = nullptr;
+};
+
+template <typename T>
+static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, const Epi &e) {
+  using T2 = typename Vec2<T>::type;
+  const int prec = sizeof(T) == 8 ? 2 : 1;
+  const Links &L = c->links[prec];
+  DslashArg<T> a;
+  a.g = c->g;
+  a.par = par_out;
+  a.fat_this = (const T2 *)L.fat[par_out];
+  a.lng_this = (const T2 *)L.lng[par_out];
+  a.fat_other = (const T2 *)L.fat[par_out ^ 1];
+  a.lng_other = (const T2 *)L.lng[par_out ^ 1];
+  a.in = (const T2 *)in.p[par_out ^ 1];
+  a.out = (T2 *)out.p[par_out];
+  a.w = e.w ? (const T2 *)e.w->p[par_out] : nullptr;
+  a.r = e.r ? (const T2 *)e.r->p[par_out] : nullptr;
+  a.s = (T)e.s;
+  a.ws = c->ws;
+  a.red = e.red;
+  a.stop = e.stop;
+  a.site_begin = 0;
+  a.site_end = c->g.Vh;
+  a.ghost_mode = 0;
+  const int grid = nblocks(c->g.Vh);
+  if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, 0>), grid, a);
+  else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, 0>), grid, a);
+  else LAUNCH(c, (dslash_kernel<T, 2, 0>), grid, a);
+  return 0;
+}
+
+static int dslash_any(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, const Epi &e) {
+  if (in.prec != out.prec) return fail(B200KS_EINVAL, "dslash: precision mismatch");
+  CHK(links_ensure(c, in.prec));
+  if (in.prec == 2) return dslash_T<double>(c, in, out, par_out, e);
+  if (in.prec == 1) return dslash_T<float>(c, in, out, par_out, e);
+  return fail(B200KS_EINVAL, "dslash: unsupported precision");
+}
+
+static int parity_bit(int parity) { return parity == B200KS_ODD ? 1 : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// host <-> device colour vectors.  Host halves: even block first, then odd (MILC order).
+template <typename T, typename TH>
+static void pack_vec_T(b200ks_ctx *c, void *d, const void *st) {
+  LAUNCH(c, (pack_vec_kernel<T, TH>), nblocks(c->g.Vh), (typename Vec2<T>::type *)d, (const TH *)st, c->g.stride, c->g.Vh);
+}
+template <typename T, typename TH>
+static void unpack_vec_T(b200ks_ctx *c, void *st, const void *d) {
+  LAUNCH(c, (unpack_vec_kernel<T, TH>), nblocks(c->g.Vh), (TH *)st, (const typename Vec2<T>::type *)d, c->g.stride, c->g.Vh);
+}
+
+static int upload(b200ks_ctx *c, DevVec &v, const void *host, int parity, int host_prec) {
+  if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
+  const size_t hs = host_prec == 2 ? 8 : 4;
+  const size_t half_bytes = (size_t)c->g.Vh * 6 * hs;
+  void *stage = nullptr;
+  CHK(dev_alloc(c, &stage, half_bytes));
+  for (int p = 0; p < 2; p++) {
+    if (!((parity == B200KS_EVENANDODD) || (parity == B200KS_EVEN && p == 0) || (parity == B200KS_ODD && p == 1))) continue;
+    CU(cudaMemcpyAsync(stage, (const char *)host + (size_t)p * half_bytes, half_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (v.prec == 2 && host_prec == 2) pack_vec_T<double, double>(c, v.p[p], stage);
+    else if (v.prec == 2 && host_prec == 1) pack_vec_T<double, float>(c, v.p[p], stage);
+    else if (v.prec == 1 && host_prec == 2) pack_vec_T<float, double>(c, v.p[p], stage);
+    else pack_vec_T<float, float>(c, v.p[p], stage);
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  dev_free(c, stage, half_bytes);
+  return check_launch("pack_vec_kernel");
+}
+
+static int download(b200ks_ctx *c, const DevVec &v, void *host, int parity, int host_prec) {
+  if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
+  const size_t hs = host_prec == 2 ? 8 : 4;
+  const size_t half_bytes = (size_t)c->g.Vh * 6 * hs;
+  void *stage = nullptr;
+  CHK(dev_alloc(c, &stage, half_bytes));
+  for (int p = 0; p < 2; p++) {
+    if (!((parity == B200KS_EVENANDODD) || (parity == B200KS_EVEN && p == 0) || (parity == B200KS_ODD && p == 1))) continue;
+    if (v.prec == 2 && host_prec == 2) unpack_vec_T<double, double>(c, stage, v.p[p]);
+    else if (v.prec == 2 && host_prec == 1) unpack_vec_T<double, float>(c, stage, v.p[p]);
+    else if (v.prec == 1 && host_prec == 2) unpack_vec_T<float, double>(c, stage, v.p[p]);
+    else unpack_vec_T<float, float>(c, stage, v.p[p]);
+    CU(cudaMemcpyAsync((char *)host + (size_t)p * half_bytes, stage, half_bytes, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  dev_free(c, stage, half_bytes);
+  return check_launch("unpack_vec_kernel");
+}
+
+static int norm2(b200ks_ctx *c, const DevVec &v, int pbit, double *out) {
+  if (v.prec == 2)
+    LAUNCH(c, (norm2_kernel<double>), nblocks(c->g.Vh), (const double2 *)v.p[pbit], c->g.stride, c->g.Vh, c->ws, c->d_scal);
+  else
+    LAUNCH(c, (norm2_kernel<float>), nblocks(c->g.Vh), (const float2 *)v.p[pbit], c->g.stride, c->g.Vh, c->ws, c->d_scal);
+  CU(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *out = c->h_scal[0];
+  return check_launch("norm2_kernel");
+}
+
+static int zero_half(b200ks_ctx *c, DevVec &v, int pbit) {
+  CU(cudaMemsetAsync(v.p[pbit], 0, vec_bytes(c, v.prec), c->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// user vector handles
+static DevVec *uvec(b200ks_ctx *c, int h) {
+  if (!c || h < 0 || h >= (int)c->user.size() || !c->user[h]) {
+    fail(B200KS_EINVAL, "bad vector handle");
+    return nullptr;
+  }
+  return c->user[h];
+}
+extern "C" int b200ks_vec_create(b200ks_ctx *c) {
+  if (!c) return fail(B200KS_EINVAL, "null context");
+  CU(cudaSetDevice(c->device));
+  DevVec *v = nullptr;
+  CHK(vec_new(c, 2, &v));
+  for (size_t k = 0; k < c->user.size(); k++)
+    if (!c->user[k]) { c->user[k] = v; return (int)k; }
+  c->user.push_back(v);
+  return (int)c->user.size() - 1;
+}
+extern "C" int b200ks_vec_free(b200ks_ctx *c, int h) {
+  DevVec *v = uvec(c, h);
+  if (!v) return B200KS_EINVAL;
+  cudaStreamSynchronize(c->stream);
+  vec_delete(c, v);
+  c->user[h] = nullptr;
+  return 0;
+}
+extern "C" int b200ks_vec_upload(b200ks_ctx *c, int h, const void *host, int parity, int host_prec) {
+  DevVec *v = uvec(c, h);
+  if (!v || !host) return fail(B200KS_EINVAL, "b200ks_vec_upload: bad argument");
+  CU(cudaSetDevice(c->device));
+  return upload(c, *v, host, parity, host_prec);
+}
+extern "C" int b200ks_vec_download(b200ks_ctx *c, int h, void *host, int parity, int host_prec) {
+  DevVec *v = uvec(c, h);
+  if (!v || !host) return fail(B200KS_EINVAL, "b200ks_vec_download: bad argument");
+  CU(cudaSetDevice(c->device));
+  return download(c, *v, host, parity, host_prec);
+}
+extern "C" int b200ks_vec_zero(b200ks_ctx *c, int h, int parity) {
+  DevVec *v = uvec(c, h);
+  if (!v) return B200KS_EINVAL;
+  if (parity & B200KS_EVEN) CHK(zero_half(c, *v, 0));
+  if (parity & B200KS_ODD) CHK(zero_half(c, *v, 1));
+  return 0;
+}
+extern "C" int b200ks_vec_norm2(b200ks_ctx *c, int h, int parity, double *out) {
+  DevVec *v = uvec(c, h);
+  if (!v || !out) return fail(B200KS_EINVAL, "b200ks_vec_norm2: bad argument");
+  double s = 0, t = 0;
+  if (parity & B200KS_EVEN) { CHK(norm2(c, *v, 0, &t)); s += t; }
+  if (parity & B200KS_ODD) { CHK(norm2(c, *v, 1, &t)); s += t; }
+  *out = s;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dslash entry points
+static int dslash_parity(b200ks_ctx *c, const DevVec &in, DevVec &out, int parity) {
+  Epi e;
+  if (parity == B200KS_EVENANDODD) {
+    CHK(dslash_any(c, in, out, 0, e));
+    CHK(dslash_any(c, in, out, 1, e));
+    return 0;
+  }
+  if (parity != B200KS_EVEN && parity != B200KS_ODD) return fail(B200KS_EINVAL, "unrecognised parity");
+  return dslash_any(c, in, out, parity_bit(parity), e);
+}
+
+extern "C" int b200ks_dslash_dev(b200ks_ctx *c, int vsrc, int vdest, int parity, int prec) {
+  DevVec *s = uvec(c, vsrc), *d = uvec(c, vdest);
+  if (!s || !d) return B200KS_EINVAL;
+  if (prec != B200KS_PREC_DOUBLE) return fail(B200KS_EINVAL, "b200ks_dslash_dev: user vectors are double");
+  if (s == d && parity == B200KS_EVENANDODD) return fail(B200KS_EINVAL, "in-place dslash needs a single parity");
+  CU(cudaSetDevice(c->device));
+  CHK(dslash_parity(c, *s, *d, parity));
+  return check_launch("dslash_kernel");
+}
+
+extern "C" int b200ks_dslash(b200ks_ctx *c, const void *src, void *dest, int parity, int host_prec) {
+  if (!c || !src || !dest) return fail(B200KS_EINVAL, "b200ks_dslash: null argument");
+  CU(cudaSetDevice(c->device));
+  DevVec *in = nullptr, *out = nullptr;
+  const int prec = host_prec == 1 ? 1 : 2;
+  CHK(pool_get(c, prec, 0, &in));
+  CHK(pool_get(c, prec, 1, &out));
+  const int src_par = parity == B200KS_EVENANDODD ? B200KS_EVENANDODD : (parity == B200KS_EVEN ? B200KS_ODD : B200KS_EVEN);
+  CHK(upload(c, *in, src, src_par, host_prec));
+  CHK(dslash_parity(c, *in, *out, parity));
+  CHK(check_launch("dslash_kernel"));
+  return download(c, *out, dest, parity, host_prec);
+}
+
+extern "C" int b200ks_dslash_time(b200ks_ctx *c, int prec, int parity, int n, double *ms) {
+  if (!c || !ms || n <= 0) return fail(B200KS_EINVAL, "b200ks_dslash_time: bad argument");
+  if (prec != 1 && prec != 2) return fail(B200KS_EINVAL, "b200ks_dslash_time: prec must be 1 or 2");
+  CU(cudaSetDevice(c->device));
+  DevVec *in = nullptr, *out = nullptr;
+  CHK(pool_get(c, prec, 0, &in));
+  CHK(pool_get(c, prec, 1, &out));
+  CHK(links_ensure(c, prec));
+  Epi e;
+  const int pb = parity_bit(parity);
+  for (int k = 0; k < 3; k++) CHK(dslash_any(c, *in, *out, pb, e));
+  CU(cudaEventRecord(c->ev0, c->stream));
+  for (int k = 0; k < n; k++) CHK(dslash_any(c, *in, *out, pb, e));
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  float t = 0;
+  CU(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+  *ms = (double)t / n;
+  return check_launch("dslash_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-mass CG, pure precision T (double for the reference-parity solver)
+static int state_push(b200ks_ctx *c) {
+  CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(CgState), cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+static int state_pull(b200ks_ctx *c) {
+  CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+template <typename T>
+static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, const b200ks_invert_args &args,
+                     b200ks_invert_result &res) {
+  using T2 = typename Vec2<T>::type;
+  const int prec = sizeof(T) == 8 ? 2 : 1;
+  const int pb = parity_bit(args.parity), ob = pb ^ 1;
+  const Geom &g = c->g;
+  const int grid = nblocks(g.Vh);
+  const int niter = args.max_iter, max_restarts = args.nrestart;
+  const double rsqmin = args.resid * args.resid, relrsqmin = args.relresid * args.relresid;
+  const double msq_x4 = 4.0 * mass * mass;
+  const int max_cg = max_restarts * niter;
+  const bool rel = relrsqmin > 0;
+  const int batch = args.check_interval > 0 ? args.check_interval : 8;
+
+  res = b200ks_invert_result();
+  res.converged = 1;
+  res.size_relr = 1.0;
+
+  double source_norm = 0;
+  CHK(norm2(c, b, pb, &source_norm));
+  if (source_norm == 0.0) {  // d_congrad5_fn_milc.c:136-152
+    CHK(zero_half(c, x, pb));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  DevVec *ttt, *p, *r;
+  CHK(pool_get(c, prec, 2, &ttt));
+  CHK(pool_get(c, prec, 3, &p));
+  CHK(pool_get(c, prec, 4, &r));
+
+  CgState &h = *c->h_state;
+  memset(&h, 0, sizeof(h));
+  h.source_norm = source_norm;
+  h.rsqmin = rsqmin;
+  h.relrsqmin = relrsqmin;
+  h.size_r = 0;
+  h.size_relr = 1.0;
+  h.niter = niter;
+  h.half_volume = 0.5 * (double)c->global[0] * c->global[1] * c->global[2] * c->global[3];
+
+  int iteration = 0, nrestart = 0;
+  double relrsq = 1.0;
+  CU(cudaEventRecord(c->ev0, c->stream));
+  for (;;) {
+    // (re)start from the true residual, d_congrad5_fn_milc.c:177-240
+    {
+      Epi e0, e1;
+      CHK(dslash_T<T>(c, x, *ttt, ob, e0));
+      e1.kind = 1; e1.s = -msq_x4; e1.w = &x;
+      CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
+      if (rel)
+        LAUNCH(c, (cg_restart_kernel<T, true>), grid, (const T2 *)b.p[pb], (const T2 *)ttt->p[pb], (const T2 *)x.p[pb],
+               (T2 *)r->p[pb], (T2 *)p->p[pb], g.stride, g.Vh, c->ws, c->d_scal);
+      else
+        LAUNCH(c, (cg_restart_kernel<T, false>), grid, (const T2 *)b.p[pb], (const T2 *)ttt->p[pb], (const T2 *)x.p[pb],
+               (T2 *)r->p[pb], (T2 *)p->p[pb], g.stride, g.Vh, c->ws, c->d_scal);
+      CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      CHK(check_launch("cg restart"));
+      const double rsq = c->h_scal[0];
+      if (rel) relrsq = sqrt(c->h_scal[1] / h.half_volume);
+      res.final_rsq = rsq / source_norm;
+      res.final_relrsq = relrsq;
+      iteration++;
+      if (iteration >= max_cg || nrestart >= max_restarts ||
+          ((rsqmin <= 0 || rsqmin > res.final_rsq) && (relrsqmin <= 0 || relrsqmin > res.final_relrsq)))
+        break;
+      nrestart++;
+      h.rsq = rsq;
+      h.cur = 0;
+      h.actual[0] = rsq;
+      h.iter = iteration;
+      h.stop = 0;
+      h.size_relr = relrsq;
+      CHK(state_push(c));
+    }
+    // iterate until the device raises the stop flag (restart interval or recursive
+    // residual under target), polling once per batch
+    for (;;) {
+      for (int k = 0; k < batch; k++) {
+        Epi e0, e1;
+        e0.stop = &c->d_state->stop;
+        CHK(dslash_T<T>(c, *p, *ttt, ob, e0));
+        e1.kind = 2; e1.s = -msq_x4; e1.w = p; e1.r = r; e1.red = c->d_state->red; e1.stop = &c->d_state->stop;
+        CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
+        if (rel)
+          LAUNCH(c, (cg_update_kernel<T, true>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
+                 g.stride, g.Vh, c->d_state, c->ws);
+        else
+          LAUNCH(c, (cg_update_kernel<T, false>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
+                 g.stride, g.Vh, c->d_state, c->ws);
+        LAUNCH1(c, cg_scalar_kernel, c->d_state, rel ? 1 : 0, prec == 1 ? 1 : 0);
+      }
+      CHK(state_pull(c));
+      CHK(check_launch("cg iterate"));
+      if (h.stop) break;
+    }
+    iteration = h.iter;
+    res.size_r = h.size_r;
+    res.size_relr = h.size_relr;
+    res.final_iters = iteration;
+    res.final_restart = nrestart;
+  }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  res.device_seconds = ms * 1e-3;
+  res.final_iters = iteration;
+  res.final_restart = nrestart;
+  res.converged = (nrestart == max_restarts || iteration == max_cg) ? 0 : 1;
+  return iteration;
+}
+
+static int check_args(const b200ks_invert_args *a) {
+  if (!a) return fail(B200KS_EINVAL, "null invert args");
+  if (a->parity != B200KS_EVEN && a->parity != B200KS_ODD)
+    return fail(B200KS_EINVAL, "Unrecognised parity (EVEN or ODD required, generic_ks/d_congrad5_fn_gpu.c:95-102)");
+  if (a->max_iter <= 0 || a->nrestart <= 0) return fail(B200KS_EINVAL, "max_iter and nrestart must be positive");
+  return 0;
+}
+
+static int congrad_any(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, const b200ks_invert_args &args,
+                       b200ks_invert_result &res) {
+  CHK(links_ensure(c, 2));
+  if (args.mixed_precision != 0) return fail(B200KS_EINVAL, "mixed precision not implemented yet");
+  return congrad_T<double>(c, b, x, mass, args, res);
+}
+
+extern "C" int b200ks_congrad_dev(b200ks_ctx *c, int vsrc, int vdest, double mass, const b200ks_invert_args *args,
+                                  b200ks_invert_result *res) {
+  DevVec *b = uvec(c, vsrc), *x = uvec(c, vdest);
+  if (!b || !x || !res) return fail(B200KS_EINVAL, "b200ks_congrad_dev: bad argument");
+  if (b == x) return fail(B200KS_EINVAL, "source and solution must be different fields");
+  CHK(check_args(args));
+  CU(cudaSetDevice(c->device));
+  return congrad_any(c, *b, *x, mass, *args, *res);
+}
+
+extern "C" int b200ks_congrad(b200ks_ctx *c, const void *src, void *dest, double mass, const b200ks_invert_args *args,
+                              b200ks_invert_result *res, int host_prec) {
+  if (!c || !src || !dest || !res) return fail(B200KS_EINVAL, "b200ks_congrad: null argument");
+  CHK(check_args(args));
+  CU(cudaSetDevice(c->device));
+  DevVec *b = nullptr, *x = nullptr;
+  CHK(pool_get(c, 2, 0, &b));
+  CHK(pool_get(c, 2, 1, &x));
+  CHK(upload(c, *b, src, args->parity, host_prec));
+  CHK(upload(c, *x, dest, args->parity, host_prec));
+  int it = congrad_any(c, *b, *x, mass, *args, *res);
+  if (it < 0) return it;
+  CHK(download(c, *x, dest, args->parity, host_prec));
+  return it;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-shift CG
+template <typename T>
+static int multicg_T(b200ks_ctx *c, const DevVec &b, DevVec *const *psim, const double *offsets, int n,
+                     const b200ks_invert_args &args, b200ks_invert_result *res) {
+  using T2 = typename Vec2<T>::type;
+  const int prec = sizeof(T) == 8 ? 2 : 1;
+  const int pb = parity_bit(args.parity), ob = pb ^ 1;
+  const Geom &g = c->g;
+  const int grid = nblocks(g.Vh);
+  const int niter = args.max_iter * args.nrestart;
+  const double rsqmin = args.resid * args.resid;
+  const int batch = args.check_interval > 0 ? args.check_interval : 8;
+
+  for (int j = 0; j < n; j++) {
+    res[j] = b200ks_invert_result();
+    res[j].converged = 1;
+  }
+  DevVec *ttt, *r;
+  CHK(pool_get(c, prec, 2, &ttt));
+  CHK(pool_get(c, prec, 4, &r));
+  MsPtrs ptrs;
+  memset(&ptrs, 0, sizeof(ptrs));
+  std::vector<DevVec *> pm(n);
+  for (int j = 0; j < n; j++) {
+    CHK(pool_get(c, prec, 5 + j, &pm[j]));
+    ptrs.x[j] = psim[j]->p[pb];
+    ptrs.pm[j] = pm[j]->p[pb];
+  }
+  CgState &h = *c->h_state;
+  memset(&h, 0, sizeof(h));
+  double offset_low = 1.0e+20;
+  int j_low = -1;
+  for (int j = 0; j < n; j++) {  // ks_multicg_offset.c:181-194
+    h.shifts[j] = offsets[j];
+    if (offsets[j] < offset_low) { offset_low = offsets[j]; j_low = j; }
+  }
+  for (int j = 0; j < n; j++)
+    if (j != j_low) h.shifts[j] -= h.shifts[j_low];
+  const double shift0 = -h.shifts[j_low];
+
+  LAUNCH(c, (ms_init_kernel<T>), grid, ptrs, n, (const T2 *)b.p[pb], (T2 *)r->p[pb], g.stride, g.Vh, c->ws, c->d_scal);
+  CU(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CHK(check_launch("ms_init_kernel"));
+  const double source_norm = c->h_scal[0];
+  int iteration = 0;
+  if (source_norm == 0.0) {  // :238-275
+    for (int j = 0; j < n; j++) res[j].final_iters = iteration;
+    return iteration;
+  }
+  iteration++;
+  h.source_norm = source_norm;
+  h.rsqstop = rsqmin * source_norm;
+  h.rsq = source_norm;
+  h.n = h.n_now = n;
+  h.j_low = j_low;
+  h.iter = iteration;
+  h.max_iter = niter;
+  for (int j = 0; j < n; j++) {
+    h.zeta_im1[j] = h.zeta_i[j] = 1.0;
+    h.beta_im1[j] = -1.0;
+    h.alpha[j] = 0.0;
+  }
+  CHK(state_push(c));
+  CU(cudaEventRecord(c->ev0, c->stream));
+  DevVec *cgp = pm[j_low];  // cg_p is pm[j_low] (ks_multicg_offset.c:20-24)
+  for (;;) {
+    for (int k = 0; k < batch; k++) {
+      Epi e0, e1;
+      e0.stop = &c->d_state->stop;
+      CHK(dslash_T<T>(c, *cgp, *ttt, ob, e0));
+      e1.kind = 2; e1.s = shift0; e1.w = cgp; e1.r = nullptr; e1.red = c->d_state->red; e1.stop = &c->d_state->stop;
+      CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
+      LAUNCH(c, (ms_resid_kernel<T>), grid, (T2 *)r->p[pb], (const T2 *)ttt->p[pb], g.stride, g.Vh, c->d_state, c->ws);
+      LAUNCH1(c, ms_scalar_kernel, c->d_state);
+      LAUNCH(c, (ms_update_kernel<T>), grid, ptrs, (const T2 *)r->p[pb], g.stride, g.Vh, c->d_state);
+      LAUNCH1(c, ms_scroll_kernel, c->d_state);
+    }
+    CHK(state_pull(c));
+    CHK(check_launch("multicg iterate"));
+    if (h.stop) break;
+  }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  iteration = h.iter;
+  const bool conv = (h.rsqstop > 0 && h.rsq <= h.rsqstop);
+  for (int j = 0; j < n; j++) {
+    res[j].final_rsq = h.rsq / source_norm;
+    res[j].size_r = res[j].final_rsq;
+    res[j].final_iters = iteration;
+    res[j].converged = conv ? 1 : 0;
+    res[j].device_seconds = ms * 1e-3;
+  }
+  return iteration;
+}
+
+static int check_ms_args(const double *offsets, int n, const b200ks_invert_args *args) {
+  CHK(check_args(args));
+  if (n < 0 || n > B200KS_MAX_SHIFTS) return fail(B200KS_EINVAL, "num_offsets out of range");
+  if (args->relresid != 0.)
+    return fail(B200KS_EINVAL, "multi-shift: Fermilab-type relative residual not supported (generic_ks/ks_multicg_offset_gpu.c:55-58)");
+  for (int j = 0; j < n; j++)
+    if (!(offsets[j] > 0)) return fail(B200KS_EINVAL, "ks_multicg_offset_field: Called with nonpositive offset");
+  return 0;
+}
+
+extern "C" int b200ks_multicg_dev(b200ks_ctx *c, int vsrc, const int *vpsim, const double *offsets, int n,
+                                  const b200ks_invert_args *args, b200ks_invert_result *res) {
+  if (!c || !res || (n > 0 && (!vpsim || !offsets))) return fail(B200KS_EINVAL, "b200ks_multicg_dev: bad argument");
+  CHK(check_ms_args(offsets, n, args));
+  if (n == 0) return 0;
+  DevVec *b = uvec(c, vsrc);
+  if (!b) return B200KS_EINVAL;
+  std::vector<DevVec *> ps(n);
+  for (int j = 0; j < n; j++) {
+    ps[j] = uvec(c, vpsim[j]);
+    if (!ps[j] || ps[j] == b) return fail(B200KS_EINVAL, "bad solution handle");
+  }
+  CU(cudaSetDevice(c->device));
+  CHK(links_ensure(c, 2));
+  if (args->mixed_precision != 0) return fail(B200KS_EINVAL, "mixed precision not implemented yet");
+  return multicg_T<double>(c, *b, ps.data(), offsets, n, *args, res);
+}
+
+extern "C" int b200ks_multicg(b200ks_ctx *c, const void *src, void *const *psim, const double *offsets, int n,
+                              const b200ks_invert_args *args, b200ks_invert_result *res, int host_prec) {
+  if (!c || !src || !res || (n > 0 && (!psim || !offsets))) return fail(B200KS_EINVAL, "b200ks_multicg: null argument");
+  CHK(check_ms_args(offsets, n, args));
+  if (n == 0) return 0;
+  CU(cudaSetDevice(c->device));
+  CHK(links_ensure(c, 2));
+  if (args->mixed_precision != 0) return fail(B200KS_EINVAL, "mixed precision not implemented yet");
+  DevVec *b = nullptr;
+  CHK(pool_get(c, 2, 0, &b));
+  CHK(upload(c, *b, src, args->parity, host_prec));
+  std::vector<DevVec *> ps(n);
+  for (int j = 0; j < n; j++) CHK(pool_get(c, 2, 5 + B200KS_MAX_SHIFTS + j, &ps[j]));
+  int it = multicg_T<double>(c, *b, ps.data(), offsets, n, *args, res);
+  if (it < 0) return it;
+  for (int j = 0; j < n; j++) CHK(download(c, *ps[j], psim[j], args->parity, host_prec));
+  return it;
+}
+
+// ---------------------------------------------------------------------------------------------
+// not yet implemented pieces of the ABI (fail loudly, never silently)
+extern "C" b200ks_ctx *b200ks_create_dist(const int *, const int *, int, int, const void *, int) {
+  fail(B200KS_EINVAL, "b200ks_create_dist: multi-GPU contexts are not implemented yet");
+  return nullptr;
+}
+extern "C" int b200ks_comm_unique_id(void *) { return fail(B200KS_ECOMM, "b200ks_comm_unique_id: not implemented yet"); }
+extern "C" int b200ks_vec_gaussian(b200ks_ctx *, int, int, unsigned long long) {
+  return fail(B200KS_EINVAL, "b200ks_vec_gaussian: not implemented yet");
+}
+extern "C" int b200ks_links_synthetic(b200ks_ctx *, unsigned long long, int) {
+  return fail(B200KS_EINVAL, "b200ks_links_synthetic: not implemented yet");
+}

@@ -1,0 +1,396 @@
+// blas.cuh -- fused CG vector updates, device-side scalar recurrences and re-layout kernels.
+//
+// The solvers never bring a scalar back to the host inside the iteration: every dot
+// product lands in a device slot (grid_reduce, common.cuh), the kernels that need
+// a = -rsq/pkp etc. recompute it from those slots, and a one-thread "scalar" kernel
+// advances the recurrence and raises a stop flag that turns every later kernel of the
+// already-enqueued batch into a no-op.  The host polls the flag once per batch.
+#pragma once
+#include "common.cuh"
+
+namespace b200ks {
+
+// ---- device-resident solver state ------------------------------------------------------
+struct CgState {
+  // single-mass CG (generic_ks/d_congrad5_fn_milc.c)
+  double red[3];       // pkp, c_tr, c_tt of the current iteration (dslash epilogue)
+  double rsq;          // recursive |r|^2 (FEWSUMS expansion value, :339)
+  double actual[2];    // directly summed |r|^2, ping-pong (actual_rsq, :283,318-336)
+  double upd[2];       // reduction target of the update kernel: {sum |r|^2, sum |r_s|^2/|x_s|^2}
+  double relsum;       // sum |r_s|^2/|x_s|^2 (Fermilab residual, :37-56)
+  double source_norm;
+  double rsqmin, relrsqmin;
+  double size_r, size_relr;
+  double half_volume;  // global sites per parity, for the relative residue
+  int iter;            // iterations done (counts multiplications by M^+M, :223,310)
+  int niter;           // restart interval
+  int stop;            // 0 run, 1 stop requested (this iteration completes), 2 stopped
+  int cur;             // ping-pong index into actual[]
+  // multi-shift CG (generic_ks/ks_multicg_offset.c)
+  int n, n_now, j_low;
+  int max_iter;
+  double rsq_new, oldrsq, rsqstop;
+  double shifts[kMaxShifts];
+  double zeta_i[kMaxShifts], zeta_im1[kMaxShifts], zeta_ip1[kMaxShifts];
+  double beta_i[kMaxShifts], beta_im1[kMaxShifts], alpha[kMaxShifts];
+  // mixed precision (reliable updates)
+  double maxrr;        // max recursive |r|^2 since the last reliable update
+  double delta2;       // reliable-update threshold squared
+  int reliable;        // 1 => host must perform a reliable update
+  int pad_;
+};
+
+// ---- plain reductions --------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock) norm2_kernel(const typename Vec2<T>::type *v, int stride,
+                                                       int n, ReduceWs ws, double *out) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  double s[1] = {0};
+  if (i < n) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const auto a = v[(size_t)c * stride + i];
+      s[0] += (double)a.x * a.x + (double)a.y * a.y;
+    }
+  }
+  grid_reduce<1>(s, ws, out);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) zero_kernel(typename Vec2<T>::type *v, int stride, int n) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  typename Vec2<T>::type z;
+  z.x = 0;
+  z.y = 0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) v[(size_t)c * stride + i] = z;
+}
+
+template <typename TD, typename TS>
+__global__ void __launch_bounds__(kBlock) convert_kernel(typename Vec2<TD>::type *d,
+                                                         const typename Vec2<TS>::type *s, int stride,
+                                                         int n) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const auto a = s[(size_t)c * stride + i];
+    typename Vec2<TD>::type o;
+    o.x = (TD)a.x;
+    o.y = (TD)a.y;
+    d[(size_t)c * stride + i] = o;
+  }
+}
+
+// ---- single-mass CG ------------------------------------------------------------------------
+// (re)start: ttt already holds D D x - 4m^2 x (= -A x).  r = b + ttt ; p = r ;
+// red: |r|^2 and (optionally) sum |r_s|^2/|x_s|^2.       d_congrad5_fn_milc.c:199-218
+template <typename T, bool kRel>
+__global__ void __launch_bounds__(kBlock)
+cg_restart_kernel(const typename Vec2<T>::type *b, const typename Vec2<T>::type *ttt,
+                  const typename Vec2<T>::type *x, typename Vec2<T>::type *r,
+                  typename Vec2<T>::type *p, int stride, int n, ReduceWs ws, double *out) {
+  using T2 = typename Vec2<T>::type;
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  double s[2] = {0, 0};
+  if (i < n) {
+    double rn = 0, xn = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const T2 bv = b[(size_t)c * stride + i], tv = ttt[(size_t)c * stride + i];
+      T2 rv;
+      rv.x = bv.x + tv.x;
+      rv.y = bv.y + tv.y;
+      r[(size_t)c * stride + i] = rv;
+      p[(size_t)c * stride + i] = rv;
+      rn += (double)rv.x * rv.x + (double)rv.y * rv.y;
+      if (kRel) {
+        const T2 xv = x[(size_t)c * stride + i];
+        xn += (double)xv.x * xv.x + (double)xv.y * xv.y;
+      }
+    }
+    s[0] = rn;
+    if (kRel) s[1] = (xn == 0) ? 1.0 : rn / xn;
+  }
+  grid_reduce<2>(s, ws, out);
+}
+
+// One fused update per iteration (the reference's FEWSUMS arithmetic, :301-345,363-367):
+//   a = -rsq/pkp ; rsq' = oldrsq + 2a c_tr + a^2 c_tt ; b = rsq'/oldrsq
+//   x += a p ; r += a ttt ; p = r + b p ; actual' = sum |r|^2 (summed for the NEXT iteration)
+// Every thread derives a, b from the device slots; nothing is mutated here except the
+// reduction target actual[next].
+template <typename T, bool kRel>
+__global__ void __launch_bounds__(kBlock)
+cg_update_kernel(typename Vec2<T>::type *x, typename Vec2<T>::type *r, typename Vec2<T>::type *p,
+                 const typename Vec2<T>::type *ttt, int stride, int n, CgState *st, ReduceWs ws) {
+  using T2 = typename Vec2<T>::type;
+  if (st->stop) return;
+  const double rsq = st->rsq, oldrsq = st->actual[st->cur];
+  const double pkp = st->red[0], c_tr = st->red[1], c_tt = st->red[2];
+  const T a = (T)(-rsq / pkp);
+  const double rsq_new = oldrsq + 2.0 * (double)a * c_tr + (double)a * (double)a * c_tt;
+  const T bb = (T)(rsq_new / oldrsq);
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  double s[2] = {0, 0};
+  if (i < n) {
+    double rn = 0, xn = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const size_t o = (size_t)c * stride + i;
+      T2 xv = x[o], rv = r[o], pv = p[o];
+      const T2 tv = ttt[o];
+      xv.x = fma(a, pv.x, xv.x);
+      xv.y = fma(a, pv.y, xv.y);
+      rv.x = fma(a, tv.x, rv.x);
+      rv.y = fma(a, tv.y, rv.y);
+      pv.x = fma(bb, pv.x, rv.x);
+      pv.y = fma(bb, pv.y, rv.y);
+      x[o] = xv;
+      r[o] = rv;
+      p[o] = pv;
+      rn += (double)rv.x * rv.x + (double)rv.y * rv.y;
+      if (kRel) xn += (double)xv.x * xv.x + (double)xv.y * xv.y;
+    }
+    s[0] = rn;
+    if (kRel) s[1] = (xn == 0) ? 1.0 : rn / xn;
+  }
+  grid_reduce<2>(s, ws, st->upd);
+}
+
+// One thread: advance the recurrence after cg_update_kernel and decide whether the host
+// has to look (restart interval reached, or recursive residual under the target).
+// Mirrors d_congrad5_fn_milc.c:177-179,310,339,350-354.
+__global__ void cg_scalar_kernel(CgState *st, int use_rel, int single) {
+  if (st->stop) { st->stop = 2; return; }
+  const double rsq = st->rsq, oldrsq = st->actual[st->cur];
+  const double a = single ? (double)(float)(-rsq / st->red[0]) : -rsq / st->red[0];
+  st->actual[st->cur ^ 1] = st->upd[0];
+  st->relsum = st->upd[1];
+  const double rsq_new = oldrsq + 2.0 * a * st->red[1] + a * a * st->red[2];
+  st->rsq = rsq_new;
+  st->cur ^= 1;
+  st->iter += 1;
+  st->size_r = rsq_new / st->source_norm;
+  if (use_rel) st->size_relr = sqrt(st->relsum / st->half_volume);
+  const bool hit_r = (st->rsqmin <= 0 || st->rsqmin > st->size_r);
+  const bool hit_rel = (st->relrsqmin <= 0 || st->relrsqmin > st->size_relr);
+  if ((st->iter % st->niter == 0) || (hit_r && hit_rel)) st->stop = 1;
+  // reliable-update trigger for the mixed-precision solver
+  if (st->delta2 > 0) {
+    if (rsq_new > st->maxrr) st->maxrr = rsq_new;
+    if (rsq_new < st->delta2 * st->maxrr) { st->reliable = 1; st->stop = 1; }
+  }
+}
+
+// ---- multi-shift CG --------------------------------------------------------------------------
+// r += beta_low * ttt ; rsq_new = |r|^2          ks_multicg_offset.c:365-368
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+ms_resid_kernel(typename Vec2<T>::type *r, const typename Vec2<T>::type *ttt, int stride, int n,
+                CgState *st, ReduceWs ws) {
+  using T2 = typename Vec2<T>::type;
+  if (st->stop) return;
+  const T beta = (T)(-st->rsq / st->red[0]);
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  double s[1] = {0};
+  if (i < n) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const size_t o = (size_t)c * stride + i;
+      T2 rv = r[o];
+      const T2 tv = ttt[o];
+      rv.x = fma(beta, tv.x, rv.x);
+      rv.y = fma(beta, tv.y, rv.y);
+      r[o] = rv;
+      s[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
+    }
+  }
+  grid_reduce<1>(s, ws, &st->rsq_new);
+}
+
+// One thread: the zeta/beta/alpha recurrences with the reference's zero guards and
+// trailing-shift dropping, the convergence test and the scroll.
+// ks_multicg_offset.c:322-355,381,429-444,456-460.
+__global__ void ms_scalar_kernel(CgState *st) {
+  if (st->stop) { st->stop = 2; return; }
+  const int jl = st->j_low;
+  const double rsq = st->rsq, pkp = st->red[0];
+  st->oldrsq = rsq;
+  st->iter += 1;
+  st->beta_i[jl] = -rsq / pkp;
+  st->zeta_ip1[jl] = 1.0;
+  for (int j = 0; j < st->n_now; j++) {
+    if (j == jl) continue;
+    st->zeta_ip1[j] = st->zeta_i[j] * st->zeta_im1[j] * st->beta_im1[jl];
+    const double c1 = st->beta_i[jl] * st->alpha[jl] * (st->zeta_im1[j] - st->zeta_i[j]);
+    const double c2 = st->zeta_im1[j] * st->beta_im1[jl] * (1.0 + st->shifts[j] * st->beta_i[jl]);
+    if (c1 + c2 != 0.0) st->zeta_ip1[j] /= c1 + c2;
+    else st->zeta_ip1[j] = 0.0;
+    if (st->zeta_i[j] != 0.0) {
+      st->beta_i[j] = st->beta_i[jl] * st->zeta_ip1[j] / st->zeta_i[j];
+    } else {
+      st->zeta_ip1[j] = 0.0;
+      st->beta_i[j] = 0.0;
+      if (j == st->n_now - 1 && j > jl) st->n_now--;
+    }
+  }
+  const double rsq_new = st->rsq_new;
+  st->rsq = rsq_new;
+  st->size_r = rsq_new / st->source_norm;
+  if (st->rsqstop > 0 && rsq_new <= st->rsqstop) { st->stop = 1; return; }
+  st->alpha[jl] = rsq_new / rsq;
+  for (int j = 0; j < st->n_now; j++) {
+    if (j == jl) continue;
+    if (st->zeta_i[j] * st->beta_i[jl] != 0.0)
+      st->alpha[j] = st->alpha[jl] * st->zeta_ip1[j] * st->beta_i[j] / (st->zeta_i[j] * st->beta_i[jl]);
+    else st->alpha[j] = 0.0;
+  }
+  if (st->iter >= st->max_iter) st->stop = 1;
+}
+
+// Scroll after the vector update has consumed zeta_ip1/alpha (kept separate so the vector
+// kernel reads a consistent set).
+__global__ void ms_scroll_kernel(CgState *st) {
+  if (st->stop) return;
+  for (int j = 0; j < st->n_now; j++) {
+    st->beta_im1[j] = st->beta_i[j];
+    st->zeta_im1[j] = st->zeta_i[j];
+    st->zeta_i[j] = st->zeta_ip1[j];
+  }
+}
+
+struct MsPtrs {
+  void *x[kMaxShifts];
+  void *pm[kMaxShifts];
+};
+
+// All shifts in one pass:  x_j += beta_j pm_j ;  pm_j = zeta_ip1_j r + alpha_j pm_j.
+// (ks_multicg_offset.c:358-362,446-453, fused: each x_j, pm_j is read and written once
+// per iteration, r is read once for all shifts.)  When stop == 1 (converged in this
+// iteration) only the x update is applied, which is the state the reference returns.
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+ms_update_kernel(const MsPtrs ptrs, const typename Vec2<T>::type *r, int stride, int n,
+                 const CgState *st) {
+  using T2 = typename Vec2<T>::type;
+  const int stop = st->stop;
+  if (stop == 2) return;
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  T2 rv[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) rv[c] = r[(size_t)c * stride + i];
+  const int nn = st->n_now;
+  for (int j = 0; j < nn; j++) {
+    const T beta = (T)st->beta_i[j], zeta = (T)st->zeta_ip1[j], alpha = (T)st->alpha[j];
+    T2 *x = (T2 *)ptrs.x[j];
+    T2 *pm = (T2 *)ptrs.pm[j];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const size_t o = (size_t)c * stride + i;
+      T2 xv = x[o], pv = pm[o];
+      xv.x = fma(beta, pv.x, xv.x);
+      xv.y = fma(beta, pv.y, xv.y);
+      x[o] = xv;
+      if (stop == 0) {
+        pv.x = fma(alpha, pv.x, zeta * rv[c].x);
+        pv.y = fma(alpha, pv.y, zeta * rv[c].y);
+        pm[o] = pv;
+      }
+    }
+  }
+}
+
+// r = b ; pm_j = b ; x_j = 0 ; source_norm               ks_multicg_offset.c:223-235
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+ms_init_kernel(const MsPtrs ptrs, int nshift, const typename Vec2<T>::type *b,
+               typename Vec2<T>::type *r, int stride, int n, ReduceWs ws, double *out) {
+  using T2 = typename Vec2<T>::type;
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  double s[1] = {0};
+  if (i < n) {
+    T2 z;
+    z.x = 0;
+    z.y = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const size_t o = (size_t)c * stride + i;
+      const T2 bv = b[o];
+      r[o] = bv;
+      s[0] += (double)bv.x * bv.x + (double)bv.y * bv.y;
+      for (int j = 0; j < nshift; j++) {
+        ((T2 *)ptrs.x[j])[o] = z;
+        ((T2 *)ptrs.pm[j])[o] = bv;
+      }
+    }
+  }
+  grid_reduce<1>(s, ws, out);
+}
+
+// ---- MILC host layout <-> device layout ---------------------------------------------------------
+// Colour vectors: host su3_vector[V] (AoS, 6 reals/site) for one parity block starting at
+// host site offset `hoff`  ->  device SoA.  TH = host real type, T = device real type.
+template <typename T, typename TH>
+__global__ void __launch_bounds__(kBlock)
+pack_vec_kernel(typename Vec2<T>::type *d, const TH *h, int stride, int n) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const TH *s = h + (size_t)6 * i;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    typename Vec2<T>::type o;
+    o.x = (T)s[2 * c];
+    o.y = (T)s[2 * c + 1];
+    d[(size_t)c * stride + i] = o;
+  }
+}
+template <typename T, typename TH>
+__global__ void __launch_bounds__(kBlock)
+unpack_vec_kernel(TH *h, const typename Vec2<T>::type *d, int stride, int n) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  TH *s = h + (size_t)6 * i;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const auto o = d[(size_t)c * stride + i];
+    s[2 * c] = (TH)o.x;
+    s[2 * c + 1] = (TH)o.y;
+  }
+}
+// Links: host su3_matrix[4*V] as [site][dir][9 complex]  ->  device [dir][9][site].
+// Runs once per gauge field; each thread walks its site's 576 contiguous bytes (the
+// strided reads are absorbed by L1/L2), the SoA writes are coalesced.
+template <typename T, typename TH>
+__global__ void __launch_bounds__(kBlock)
+pack_link_kernel(typename Vec2<T>::type *d, const TH *h, int lstride, int n) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const TH *s = h + (size_t)72 * i;
+#pragma unroll 6
+  for (int m = 0; m < 36; m++) {  // m = dir*9 + e
+    typename Vec2<T>::type o;
+    o.x = (T)s[2 * m];
+    o.y = (T)s[2 * m + 1];
+    d[(size_t)m * lstride + i] = o;
+  }
+}
+
+template <typename TD, typename TS>
+__global__ void __launch_bounds__(kBlock)
+convert_link_kernel(typename Vec2<TD>::type *d, const typename Vec2<TS>::type *s, int lstride, int n) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+#pragma unroll 6
+  for (int m = 0; m < 36; m++) {
+    const auto a = s[(size_t)m * lstride + i];
+    typename Vec2<TD>::type o;
+    o.x = (TD)a.x;
+    o.y = (TD)a.y;
+    d[(size_t)m * lstride + i] = o;
+  }
+}
+
+}  // namespace b200ks

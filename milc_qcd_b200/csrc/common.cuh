@@ -1,0 +1,179 @@
+// common.cuh -- device-side building blocks shared by all kernels of libb200ks.
+//
+// Device data layout:
+//   * checkerboarded: every field is split into an EVEN and an ODD half; inside a half a
+//     site is addressed by cb = lex >> 1 with lex = x + Lx*(y + Ly*(z + Lz*t)), which is
+//     exactly MILC's index inside a parity block (generic/layout_hyper_prime.c:509-520),
+//     so host<->device re-layout is a pure AoS<->SoA transpose, no permutation.
+//   * structure of arrays of complex pairs: colour vector element c of site cb lives at
+//     v[c*stride + cb] (T2 = double2/float2), link element e = 3*row+col of direction mu
+//     at U[(mu*9 + e)*stride + cb].  Consecutive threads = consecutive cb = consecutive
+//     16-byte (double2) words: every warp load is one fully coalesced 512-byte request.
+//   * ghost zones (multi-GPU) are appended after the Vh interior sites of each half.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace b200ks {
+
+constexpr int kBlock = 128;           // threads per CTA for site kernels
+constexpr int kMaxShifts = 32;
+
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+// Local lattice geometry (per GPU).  part[d] != 0 means direction d is split across
+// GPUs and neighbours beyond the local extent live in the ghost zone.
+struct Geom {
+  int L[4];        // local extents
+  int Lxh;         // L[0]/2
+  int Vh;          // local sites per parity
+  int stride;      // spinor field stride in sites (Vh + ghost sites, padded)
+  int lstride;     // link field stride in sites (Vh + backward ghost sites, padded)
+  int part[4];
+  int faceh[4];    // sites per parity in one slice orthogonal to d
+  int ghost[4][2]; // first ghost site of (d, 0=behind | 1=ahead) in a spinor half
+  int lghost[4];   // first backward-ghost site of d in a link half
+  int origin_parity;  // parity of the local origin in the global lattice
+};
+
+struct Coord { int x, y, z, t, xh; };
+
+// cb index -> local coordinates, for a site of the given local parity bit (0 even, 1 odd).
+__device__ __forceinline__ Coord site_coord(const Geom &g, int idx, int par) {
+  Coord c;
+  c.xh = idx % g.Lxh;
+  int r = idx / g.Lxh;
+  c.y = r % g.L[1];
+  r /= g.L[1];
+  c.z = r % g.L[2];
+  c.t = r / g.L[2];
+  c.x = 2 * c.xh + ((c.y + c.z + c.t + par) & 1);
+  return c;
+}
+
+// Index (inside the opposite-parity half) of the neighbour of site (idx,c) displaced by
+// h in direction D (h = +-1, +-3).  Non-partitioned directions wrap periodically
+// (generic/com_vanilla.c:619-645, ks_spectrum/setup.c:1427-1445).  Partitioned
+// directions index the ghost zone.  kLink selects link-field ghosts (backward only).
+template <int D, bool kLink = false>
+__device__ __forceinline__ int neighbor(const Geom &g, int idx, const Coord &c, int h) {
+  if (D == 0) {
+    int xn = c.x + h;
+    if (xn >= g.L[0]) xn -= g.L[0];
+    if (xn >= g.L[0]) xn -= g.L[0];  // extent 2 with a 3-hop wraps twice
+    if (xn < 0) xn += g.L[0];
+    if (xn < 0) xn += g.L[0];
+    return idx - c.xh + (xn >> 1);
+  }
+  const int coord = (D == 1) ? c.y : (D == 2) ? c.z : c.t;
+  const int ext = g.L[D];
+  const int sstride = (D == 1) ? g.Lxh : (D == 2) ? g.Lxh * g.L[1] : g.Lxh * g.L[1] * g.L[2];
+  int cn = coord + h;
+  if (D >= 2 && g.part[D]) {
+    if (cn < 0) {
+      // slice -3,-2,-1 -> ghost slice 0,1,2 ; position inside the slice = idx minus this
+      // site's own slice offset
+      const int inslice = idx - coord * sstride - ((D == 2) ? c.t * sstride * ext : 0);
+      const int within = (D == 2) ? inslice + c.t * sstride : inslice;  // (z-slab: keep t-major)
+      return (kLink ? g.lghost[D] : g.ghost[D][0]) + (cn + 3) * g.faceh[D] + within;
+    }
+    if (cn >= ext) {
+      const int inslice = idx - coord * sstride - ((D == 2) ? c.t * sstride * ext : 0);
+      const int within = (D == 2) ? inslice + c.t * sstride : inslice;
+      return g.ghost[D][1] + (cn - ext) * g.faceh[D] + within;
+    }
+    return idx + h * sstride;
+  }
+  if (cn >= ext) cn -= ext;
+  if (cn >= ext) cn -= ext;
+  if (cn < 0) cn += ext;
+  if (cn < 0) cn += ext;
+  return idx + (cn - coord) * sstride;
+}
+
+// ---- complex helpers on T2 -----------------------------------------------------------
+template <typename T2, typename T>
+__device__ __forceinline__ void cmad(T &re, T &im, const T2 a, const T2 b) {  // += a*b
+  re = fma(a.x, b.x, re);
+  re = fma(-a.y, b.y, re);
+  im = fma(a.x, b.y, im);
+  im = fma(a.y, b.x, im);
+}
+template <typename T2, typename T>
+__device__ __forceinline__ void cmad_conj(T &re, T &im, const T2 a, const T2 b) {  // += conj(a)*b
+  re = fma(a.x, b.x, re);
+  re = fma(a.y, b.y, re);
+  im = fma(a.x, b.y, im);
+  im = fma(-a.y, b.x, im);
+}
+
+// ---- cache-hinted loads ----------------------------------------------------------------
+// Links are streamed once per dslash: evict-first so they do not push the neighbour
+// spinors (each re-read 16x) out of L2.  Spinors take the default (read-only) path.
+__device__ __forceinline__ double2 ld_stream(const double2 *p) { return __ldcs(p); }
+__device__ __forceinline__ float2 ld_stream(const float2 *p) { return __ldcs(p); }
+__device__ __forceinline__ double2 ld_keep(const double2 *p) { return __ldg(p); }
+__device__ __forceinline__ float2 ld_keep(const float2 *p) { return __ldg(p); }
+
+// ---- deterministic grid reduction ------------------------------------------------------
+// Each CTA reduces N doubles with warp shuffles + shared memory and writes one partial;
+// the CTA that takes the last ticket sums all partials in a fixed order and stores the
+// result.  The order depends only on (gridDim, blockDim), so results are reproducible
+// run to run (MILC's site-loop sums are reproducible too; atomics would not be).
+struct ReduceWs {
+  double *partials;        // [maxBlocks * N]
+  unsigned int *counter;   // zero-initialised; reset by the last CTA
+};
+
+template <int N>
+__device__ __forceinline__ void grid_reduce(double (&v)[N], const ReduceWs ws, double *out) {
+  __shared__ double sm[N][kBlock / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    double s = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sm[k][warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      double s = 0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; w++) s += sm[k][w];
+      ws.partials[(size_t)blockIdx.x * N + k] = s;
+    }
+    __threadfence();
+    const unsigned ticket = atomicAdd(ws.counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    double s = 0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kBlock)
+      s += __ldcg(&ws.partials[(size_t)b * N + k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if (lane == 0) sm[k][warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; w++) tot += sm[k][w];
+      out[k] = tot;
+    }
+  }
+  if (threadIdx.x == 0) *ws.counter = 0;
+}
+
+}  // namespace b200ks

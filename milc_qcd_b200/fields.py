@@ -48,15 +48,15 @@ def coords_lex(dims):
 
 
 def random_su3(rng, n):
-    """n Haar-ish random SU(3) matrices, complex128 (n,3,3): QR of a Ginibre matrix,
-    phases fixed, determinant divided out."""
-    a = rng.standard_normal((n, 3, 3)) + 1j * rng.standard_normal((n, 3, 3))
-    q, r = np.linalg.qr(a)
-    d = np.diagonal(r, axis1=1, axis2=2)
-    q = q * (d / np.abs(d))[:, None, :]
-    det = np.linalg.det(q)
-    q = q * (det ** (-1.0 / 3.0))[:, None, None]
-    return q
+    """n Haar-distributed SU(3) matrices, complex128 (n,3,3): Gram-Schmidt on two Gaussian
+    rows, third row = conjugate cross product (so det = 1 exactly)."""
+    a = rng.standard_normal((n, 3)) + 1j * rng.standard_normal((n, 3))
+    b = rng.standard_normal((n, 3)) + 1j * rng.standard_normal((n, 3))
+    a /= np.sqrt(np.sum(np.abs(a) ** 2, axis=1))[:, None]
+    b -= np.sum(np.conj(a) * b, axis=1)[:, None] * a
+    b /= np.sqrt(np.sum(np.abs(b) ** 2, axis=1))[:, None]
+    c = np.conj(np.cross(a, b))
+    return np.stack([a, b, c], axis=1)
 
 
 def _c2r(a):

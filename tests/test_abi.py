@@ -1,0 +1,54 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/b200ks.h declares, and fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200ks_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from milc_qcd_b200 import _lib, build
+    build.build_all()
+    lib = _lib.load()
+    declared = _declared("b200ks.h")
+    assert len(declared) >= 20
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    assert set(declared) == bound, (set(declared) ^ bound)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.b200ks_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    from milc_qcd_b200 import _lib
+    lib = _lib.load()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.b200ks_device_count() == 0
+    dims = (C.c_int * 4)(4, 4, 4, 4)
+    assert not lib.b200ks_create(dims, 0)
+    assert b"no CPU fallback" in lib.b200ks_last_error()
+    from milc_qcd_b200 import api
+    with pytest.raises(_lib.B200KSError):
+        api.Context((4, 4, 4, 4))
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (or the reference build)."""
+    pkg = os.path.join(ROOT, "milc_qcd_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".c", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "libmilcref" not in txt, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f

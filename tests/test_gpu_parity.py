@@ -1,0 +1,209 @@
+"""GPU parity tests: the CUDA path (through the C ABI, host MILC-layout buffers) against the
+CPU oracle on the same seeded inputs.  Tolerances are the ones BASELINE.json's north_star
+states: one dslash to <= 1e-13 relative (double), converged solutions within 10x the requested
+residual, iteration counts within 2% in pure double."""
+import numpy as np
+import pytest
+
+from conftest import fields_for
+
+pytestmark = pytest.mark.gpu
+
+EVEN, ODD, EVENANDODD = 2, 1, 3
+DSLASH_TOL = 1e-13  # north_star: relative error of one dslash application in double
+
+SIZES = [(6, 6, 6, 6), (8, 8, 8, 8), (8, 12, 6, 10), (4, 4, 4, 4), (2, 2, 2, 2), (16, 8, 4, 6)]
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from milc_qcd_b200 import api
+    yield api
+    api.finalize()
+
+
+@pytest.mark.parametrize("dims", SIZES)
+@pytest.mark.parametrize("parity", [EVEN, ODD, EVENANDODD])
+def test_dslash_matches_oracle(api, oracle, dims, parity):
+    fat, lng, src = fields_for(dims)
+    ctx = api.Context(dims)
+    ctx.load_links(fat, lng)
+    want = oracle.dslash(dims, fat, lng, src, parity)
+    sentinel = 7.25
+    got = np.full_like(src, sentinel)
+    ctx.dslash(src, got, parity)
+    V = src.shape[0]
+    sl = slice(0, V // 2) if parity == EVEN else slice(V // 2, V) if parity == ODD else slice(0, V)
+    assert rel_err(got[sl], want[sl]) <= DSLASH_TOL
+    # only `parity` sites may be written (the other half holds live data in MILC, mat_invert.c:365-393)
+    mask = np.ones(V, bool)
+    mask[sl] = False
+    assert np.all(got[mask] == sentinel)
+    ctx.close()
+
+
+def test_dslash_inplace_and_single_precision(api, oracle):
+    dims = (8, 8, 8, 8)
+    fat, lng, src = fields_for(dims)
+    ctx = api.Context(dims)
+    ctx.load_links(fat, lng)
+    want = oracle.dslash(dims, fat, lng, src, EVEN)
+    buf = src.copy()
+    ctx.dslash(buf, buf, EVEN)  # src == dest is legal for one parity (d_congrad5_fn_milc.c:197)
+    V = src.shape[0]
+    assert rel_err(buf[:V // 2], want[:V // 2]) <= DSLASH_TOL
+    assert np.array_equal(buf[V // 2:], src[V // 2:])
+    ctx.close()
+    # MILC_PRECISION=1 callers hand over float arrays
+    ctx = api.Context(dims)
+    ctx.load_links(fat.astype(np.float32), lng.astype(np.float32))
+    got = np.zeros(src.shape, np.float32)
+    ctx.dslash(src.astype(np.float32), got, EVEN)
+    assert rel_err(got[:V // 2].astype(np.float64), want[:V // 2]) <= 2e-6
+    ctx.close()
+
+
+def test_dslash_linearity_and_antihermiticity(api):
+    """Size-independent properties: D is linear and anti-Hermitian (<a|D b> = -<D a|b>^*)."""
+    from milc_qcd_b200 import fields as F
+    dims = (8, 8, 8, 16)
+    fat, lng, a = fields_for(dims)
+    b = F.make_source(dims, seed=99, parity=EVENANDODD)
+    ctx = api.Context(dims)
+    ctx.load_links(fat, lng)
+    Da, Db, Dab = np.zeros_like(a), np.zeros_like(a), np.zeros_like(a)
+    ctx.dslash(a, Da, EVENANDODD)
+    ctx.dslash(b, Db, EVENANDODD)
+    ctx.dslash(2.0 * a - 0.5 * b, Dab, EVENANDODD)
+    assert rel_err(Dab, 2.0 * Da - 0.5 * Db) < 1e-13
+
+    def cdot(u, v):
+        uc = u[..., 0] + 1j * u[..., 1]
+        vc = v[..., 0] + 1j * v[..., 1]
+        return np.vdot(uc, vc)
+    lhs, rhs = cdot(a, Db), -cdot(Da, b)
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+    ctx.close()
+
+
+@pytest.mark.parametrize("dims,parity", [((6, 6, 6, 6), EVEN), ((8, 8, 8, 8), ODD), ((8, 12, 6, 10), EVEN)])
+def test_congrad_matches_oracle(api, oracle, dims, parity):
+    from milc_qcd_b200 import fields as F
+    fat, lng, _ = fields_for(dims)
+    src = F.make_source(dims, seed=5678, parity=parity)
+    mass, resid = 0.05, 1e-10
+    x_ref = np.zeros_like(src)
+    it_ref, q_ref = oracle.congrad(dims, fat, lng, src, x_ref, mass, parity, 500, 5, resid)
+    fn = api.fn_links_t(fat=fat, lng=lng, dims=dims)
+    qic = api.quark_invert_control(max=500, nrestart=5, parity=parity, resid=resid)
+    x = np.zeros_like(src)
+    it = api.ks_congrad_parity_gpu(src, x, qic, mass, fn)
+    assert qic.converged == 1 and q_ref["converged"] == 1
+    assert abs(it - it_ref) <= max(2, 0.02 * it_ref)          # iterations within 2%
+    assert qic.final_iters == it
+    assert qic.final_rsq < resid ** 2
+    # solution agrees to within 10x the requested residual (relative to |x|)
+    assert np.linalg.norm(x - x_ref) <= 10 * resid * np.linalg.norm(x_ref) * _cond(mass)
+    # independent true-residual check with the oracle's operator
+    V = src.shape[0]
+    sl = slice(0, V // 2) if parity == EVEN else slice(V // 2, V)
+    op = EVEN if parity == ODD else ODD
+    t = oracle.dslash(dims, fat, lng, x, op)
+    t = oracle.dslash(dims, fat, lng, t, parity)
+    r = src[sl] - (4 * mass * mass * x[sl] - t[sl])
+    assert np.linalg.norm(r) / np.linalg.norm(src[sl]) <= 10 * resid
+    # other parity of dest untouched
+    mask = np.ones(V, bool)
+    mask[sl] = False
+    assert np.all(x[mask] == 0)
+
+
+def _cond(mass):
+    # |dx| <= |A^-1| |dr|: the solution error bound carries 1/(4 m^2) relative to the residual bound
+    return 1.0 / (4 * mass * mass)
+
+
+def test_congrad_initial_guess_restart_and_zero_source(api, oracle):
+    from milc_qcd_b200 import fields as F
+    dims = (6, 6, 6, 6)
+    fat, lng, _ = fields_for(dims)
+    fn = api.fn_links_t(fat=fat, lng=lng, dims=dims)
+    src = F.make_source(dims, seed=11, parity=EVEN)
+    # zero source -> zero solution, 0 iterations (d_congrad5_fn_milc.c:136-152)
+    x = np.ones_like(src)
+    qic = api.quark_invert_control(max=100, nrestart=2, parity=EVEN, resid=1e-8)
+    assert api.ks_congrad_parity_gpu(np.zeros_like(src), x, qic, 0.05, fn) == 0
+    V = src.shape[0]
+    assert np.all(x[:V // 2] == 0) and np.all(x[V // 2:] == 1)
+    # iteration cap: niter*nrestart reached -> converged = 0, same count as the oracle
+    x = np.zeros_like(src)
+    qic = api.quark_invert_control(max=7, nrestart=3, parity=EVEN, resid=1e-12)
+    it = api.ks_congrad_parity_gpu(src, x, qic, 0.05, fn)
+    xo = np.zeros_like(src)
+    ito, qo = oracle.congrad(dims, fat, lng, src, xo, 0.05, EVEN, 7, 3, 1e-12)
+    assert (it, qic.converged, qic.final_restart) == (ito, qo["converged"], qo["final_restart"])
+    assert np.abs(x - xo).max() <= 1e-9 * np.abs(xo).max()
+    # a converged solution as initial guess returns after the first true-residual check
+    qic = api.quark_invert_control(max=500, nrestart=5, parity=EVEN, resid=1e-9)
+    x = np.zeros_like(src)
+    api.ks_congrad_parity_gpu(src, x, qic, 0.05, fn)
+    qic2 = api.quark_invert_control(max=500, nrestart=5, parity=EVEN, resid=1e-8)
+    assert api.ks_congrad_parity_gpu(src, x, qic2, 0.05, fn) == 1
+
+
+@pytest.mark.parametrize("dims,nshift", [((6, 6, 6, 6), 11), ((8, 8, 8, 8), 3), ((8, 12, 6, 10), 12)])
+def test_multicg_matches_oracle(api, oracle, dims, nshift):
+    from milc_qcd_b200 import fields as F
+    fat, lng, _ = fields_for(dims)
+    src = F.make_source(dims, seed=4321, parity=EVEN)
+    offsets = F.rhmc_offsets(nshift, 0.05)
+    offsets = np.roll(offsets, 2)  # smallest shift not first: exercises j_low
+    resid = 1e-8
+    it_ref, p_ref, q_ref = oracle.multicg(dims, fat, lng, src, offsets, EVEN, 2000, 1, resid)
+    fn = api.fn_links_t(fat=fat, lng=lng, dims=dims)
+    qic = [api.quark_invert_control(max=2000, nrestart=1, parity=EVEN, resid=resid) for _ in range(nshift)]
+    ksp = [api.ks_param(offset=o) for o in offsets]
+    psim = [np.full_like(src, 3.0) for _ in range(nshift)]  # initial guess must be ignored (:230)
+    for p in psim:
+        p[src.shape[0] // 2:] = -2.0
+    it = api.ks_multicg_offset_field_gpu(src, psim, ksp, nshift, qic, fn)
+    assert abs(it - it_ref) <= max(2, 0.02 * it_ref)
+    V = src.shape[0]
+    for j in range(nshift):
+        assert qic[j].converged == 1 and qic[j].final_iters == it
+        assert qic[j].final_rsq <= resid ** 2
+        assert np.all(psim[j][V // 2:] == -2.0)  # odd half untouched
+        # true residual of every shift, computed independently with the oracle operator
+        t = oracle.dslash(dims, fat, lng, psim[j], ODD)
+        t = oracle.dslash(dims, fat, lng, t, EVEN)
+        r = src[:V // 2] - (offsets[j] * psim[j][:V // 2] - t[:V // 2])
+        assert np.linalg.norm(r) / np.linalg.norm(src[:V // 2]) <= 10 * resid
+        assert np.linalg.norm(psim[j][:V // 2] - p_ref[j][:V // 2]) <= 1e-6 * np.linalg.norm(p_ref[j][:V // 2])
+
+
+def test_golden_reference_vectors(api):
+    """Committed outputs of the reference's own compiled CPU path (tests/golden/make_golden.py)."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "ref_l6666_synth.npz")
+    g = np.load(path)
+    dims = tuple(int(d) for d in g["dims"])
+    fat, lng, src = g["fat"], g["lng"], g["src"]
+    ctx = api.Context(dims)
+    ctx.load_links(fat, lng)
+    got = np.zeros_like(src)
+    ctx.dslash(src, got, EVENANDODD)
+    assert rel_err(got, g["dslash"]) <= DSLASH_TOL
+    ctx.close()
+    fn = api.fn_links_t(fat=fat, lng=lng, dims=dims)
+    qic = api.quark_invert_control(max=int(g["cg_niter"]), nrestart=int(g["cg_nrestart"]), parity=EVEN,
+                                   resid=float(g["cg_resid"]))
+    x = np.zeros_like(src)
+    it = api.ks_congrad_parity_gpu(g["cg_src"], x, qic, float(g["mass"]), fn)
+    assert abs(it - int(g["cg_iters"])) <= max(2, 0.02 * int(g["cg_iters"]))
+    V = src.shape[0]
+    assert np.linalg.norm(x[:V // 2] - g["cg_x"][:V // 2]) <= 10 * float(g["cg_resid"]) * _cond(float(g["mass"])) * \
+        np.linalg.norm(g["cg_x"][:V // 2])

@@ -1,0 +1,138 @@
+"""CPU tests that PIN the oracle (oracle/ks_oracle.c):
+  * against the committed golden vectors produced by the reference's own compiled CPU path
+    (tests/golden/ref_l6666_synth.npz, generator tests/golden/make_golden.py);
+  * live against oracle/_ref/libmilcref.so (the reference's sources compiled by
+    oracle/build_ref.sh) whenever that library is present.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, fields_for
+
+EVEN, ODD, EVENANDODD = 2, 1, 3
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_l6666_synth.npz")
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def test_node_index_is_milc_layout(oracle):
+    from milc_qcd_b200 import fields as F
+    dims = (4, 6, 2, 8)
+    perm = F.lex_to_milc(dims)
+    nx, ny, nz, nt = dims
+    assert sorted(perm) == list(range(nx * ny * nz * nt))
+    for (x, y, z, t) in [(0, 0, 0, 0), (1, 0, 0, 0), (3, 5, 1, 7), (2, 3, 1, 4)]:
+        lex = x + nx * (y + ny * (z + nz * t))
+        assert oracle.node_index(dims, x, y, z, t) == perm[lex]
+    V = nx * ny * nz * nt
+    assert oracle.node_index(dims, 0, 0, 0, 0) == 0 and oracle.node_index(dims, 1, 0, 0, 0) == V // 2
+
+
+def test_oracle_dslash_golden(oracle):
+    g = np.load(GOLDEN)
+    dims = tuple(int(d) for d in g["dims"])
+    got = oracle.dslash(dims, g["fat"], g["lng"], g["src"], EVENANDODD)
+    assert rel_err(got, g["dslash"]) < 1e-14
+
+
+def test_oracle_dslash_only_writes_parity(oracle):
+    dims = (4, 4, 4, 4)
+    fat, lng, src = fields_for(dims)
+    full = oracle.dslash(dims, fat, lng, src, EVENANDODD)
+    V = src.shape[0]
+    for par, sl in ((EVEN, slice(0, V // 2)), (ODD, slice(V // 2, V))):
+        dest = np.full_like(src, 5.0)
+        oracle.dslash(dims, fat, lng, src, par, dest)
+        assert np.array_equal(dest[sl], full[sl])
+        mask = np.ones(V, bool)
+        mask[sl] = False
+        assert np.all(dest[mask] == 5.0)
+    buf = src.copy()
+    oracle.dslash(dims, fat, lng, buf, EVEN, buf)  # in place, one parity
+    assert np.array_equal(buf[:V // 2], full[:V // 2])
+
+
+def test_oracle_congrad_golden(oracle):
+    g = np.load(GOLDEN)
+    dims = tuple(int(d) for d in g["dims"])
+    x = np.zeros_like(g["cg_src"])
+    it, q = oracle.congrad(dims, g["fat"], g["lng"], g["cg_src"], x, float(g["mass"]), EVEN,
+                           int(g["cg_niter"]), int(g["cg_nrestart"]), float(g["cg_resid"]))
+    assert abs(it - int(g["cg_iters"])) <= 2
+    assert q["converged"] == 1 and q["final_restart"] == int(g["cg_final_restart"])
+    assert np.linalg.norm(x - g["cg_x"]) <= 1e-9 * np.linalg.norm(g["cg_x"])
+
+
+def test_oracle_multicg_golden(oracle):
+    g = np.load(GOLDEN)
+    dims = tuple(int(d) for d in g["dims"])
+    it, psim, q = oracle.multicg(dims, g["fat"], g["lng"], g["cg_src"], g["ms_offsets"], EVEN, 2000, 1,
+                                 float(g["ms_resid"]))
+    assert abs(it - int(g["ms_iters"])) <= 1
+    V = g["cg_src"].shape[0]
+    assert np.linalg.norm(psim[:, :V // 2] - g["ms_psim"]) <= 1e-8 * np.linalg.norm(g["ms_psim"])
+    assert all(qq["converged"] == 1 for qq in q)
+
+
+def test_oracle_zero_source_and_iteration_cap(oracle):
+    dims = (4, 4, 4, 4)
+    fat, lng, src = fields_for(dims)
+    x = np.ones_like(src)
+    it, q = oracle.congrad(dims, fat, lng, np.zeros_like(src), x, 0.05, EVEN, 10, 2, 1e-8)
+    V = src.shape[0]
+    assert it == 0 and np.all(x[:V // 2] == 0) and np.all(x[V // 2:] == 1)
+    x = np.zeros_like(src)
+    src_e = src.copy()
+    src_e[V // 2:] = 0
+    it, q = oracle.congrad(dims, fat, lng, src_e, x, 0.01, EVEN, 5, 2, 1e-14)
+    # restart(1) + 4 iterations, restart(6) + 4 iterations, restart(11) >= max_cg: the reference counts
+    # every true-residual evaluation as an iteration (d_congrad5_fn_milc.c:223)
+    assert it == 11 and q["converged"] == 0
+
+
+_LIVE = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+from milc_qcd_b200 import fields as F
+from oracle.pyoracle import Oracle, MilcRef, EVEN, ODD, EVENANDODD
+dims = %(dims)r
+fat, lng = F.make_links(dims, seed=77)
+src = F.make_source(dims, seed=78, parity=EVENANDODD)
+o, r = Oracle(), MilcRef(dims)
+for c in [(0,0,0,0),(1,0,0,0),(3,1,2,5),(dims[0]-1,dims[1]-1,dims[2]-1,dims[3]-1)]:
+    assert o.node_index(dims,*c) == r.node_index(*c)
+r.set_links(fat, lng)
+for par in (EVEN, ODD, EVENANDODD):
+    a, b = o.dslash(dims, fat, lng, src, par), r.dslash(src, par)
+    assert np.abs(a-b).max() <= 1e-14*np.abs(b).max(), par
+se = F.make_source(dims, seed=79, parity=ODD)
+x0, x1 = np.zeros_like(se), np.zeros_like(se)
+i0, q0 = o.congrad(dims, fat, lng, se, x0, 0.1, ODD, 300, 5, 1e-9)
+i1, q1 = r.congrad(se, x1, 0.1, ODD, 300, 5, 1e-9)
+assert abs(i0-i1) <= 2 and q0['converged'] == q1['converged'] == 1
+assert q0['final_restart'] == q1['final_restart']
+assert np.linalg.norm(x0-x1) <= 1e-8*np.linalg.norm(x1)
+offs = F.rhmc_offsets(9, 0.1)[::-1].copy()
+i0, p0, _ = o.multicg(dims, fat, lng, se, offs, ODD, 3000, 1, 1e-7)
+i1, p1, _ = r.multicg(se, offs, ODD, 3000, 1, 1e-7)
+assert i0 == i1 or abs(i0-i1) <= 1
+assert np.linalg.norm(p0-p1) <= 1e-8*np.linalg.norm(p1)
+print('LIVE-OK')
+"""
+
+
+@pytest.mark.parametrize("dims", [(8, 12, 6, 10), (4, 4, 4, 8)])
+def test_oracle_matches_compiled_reference_live(dims):
+    from oracle.pyoracle import ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref/libmilcref.so not built (needs /root/reference)")
+    # MILC keeps its geometry in process globals: one subprocess per lattice size
+    out = subprocess.run([sys.executable, "-c", _LIVE % dict(root=ROOT, dims=dims)], capture_output=True,
+                         text=True, timeout=600)
+    assert "LIVE-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
