@@ -4,7 +4,10 @@
     python -m milc_qcd_b200.build --force
 
 Outputs (git-ignored, shipped to the GPU box by gpurun):
-    milc_qcd_b200/libb200ks.so       CUDA kernels + the C ABI (include/b200ks.h)
+    milc_qcd_b200/libb200ks.so        CUDA kernels + the C ABI (include/b200ks.h) + the quda* symbols
+                                      MILC's own GPU glue binds (include/quda_milc_interface.h)
+    milc_qcd_b200/libb200ks_milc.so   MILC-named solver symbols (include/b200ks_milc.h), PRECISION=2
+    milc_qcd_b200/libb200ks_milc_f.so same, PRECISION=1
 """
 import os
 import subprocess
@@ -40,8 +43,23 @@ def build_cuda(force=False, verbose=False):
     return out
 
 
+def build_milc_shim(force=False):
+    """Route-1 boundary (MILC-named symbols), double and single MILC_PRECISION builds."""
+    outs = []
+    src = os.path.join(HERE, "csrc_milc", "milc_shim.c")
+    deps = [src, os.path.join(ROOT, "include", "b200ks_milc.h"), os.path.join(ROOT, "include", "b200ks.h")]
+    for prec, name in ((2, "libb200ks_milc.so"), (1, "libb200ks_milc_f.so")):
+        out = os.path.join(HERE, name)
+        if force or _newer(out, deps):
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=gnu99", "-Wall", "-DMILC_PRECISION=%d" % prec,
+                                   "-I", os.path.join(ROOT, "include"), "-o", out, src,
+                                   "-L", HERE, "-lb200ks", "-Wl,-rpath,$ORIGIN"])
+        outs.append(out)
+    return outs
+
+
 def build_all(force=False, verbose=False):
-    return [build_cuda(force, verbose)]
+    return [build_cuda(force, verbose)] + build_milc_shim(force)
 
 
 if __name__ == "__main__":

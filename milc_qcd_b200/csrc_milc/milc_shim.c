@@ -1,0 +1,251 @@
+/* milc_shim.c -- route-1 boundary: MILC's GPU solver symbols on the b200ks C ABI.
+ *
+ * Same job as the reference's QUDA glue (generic_ks/d_congrad5_fn_gpu.c:35-172,
+ * generic_ks/ks_multicg_offset_gpu.c:26-252, generic_ks/dslash_fn.c:306-344): initialise the
+ * qic outputs, take the zero-source shortcut on the host, keep the device link cache in
+ * step with `fn`, call the solver, write back the results.  Differences by design: the
+ * solver behind it follows the CPU algorithm (restarts, true-residual stop, iteration
+ * counting), so qic->final_restart, size_r and total_iters are filled like the CPU path does.
+ *
+ * Standalone: cc -Iinclude milc_shim.c -lb200ks  (mirror types from include/b200ks_milc.h).
+ * In a MILC tree: compile with -DB200KS_IN_MILC next to generic_ks_includes.h.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef B200KS_IN_MILC
+#include "generic_ks_includes.h"
+#include "b200ks_milc.h"
+#define NX nx
+#define NY ny
+#define NZ nz
+#define NT nt
+#define SITES ((size_t)sites_on_node)
+#define TOTAL_ITERS total_iters
+#define FATAL(status) terminate(status)
+#if defined(MAX_MIXED)
+#define MIXED 2
+#elif defined(HALF_MIXED)
+#define MIXED 1
+#else
+#define MIXED 0
+#endif
+#else
+#include "b200ks_milc.h"
+static int s_dims[4] = {0, 0, 0, 0};
+static int s_total_iters = 0;
+static int s_mixed = 0;
+#define NX s_dims[0]
+#define NY s_dims[1]
+#define NZ s_dims[2]
+#define NT s_dims[3]
+#define SITES ((size_t)s_dims[0] * s_dims[1] * s_dims[2] * s_dims[3])
+#define TOTAL_ITERS s_total_iters
+#define MIXED s_mixed
+static void FATAL(int status) {
+  printf("Termination: node 0, status = %d\n", status);
+  fflush(stdout);
+  exit(status);
+}
+#endif
+
+#include "b200ks.h"
+
+static b200ks_ctx *s_ctx = NULL;
+static imp_ferm_links_t *fn_last = NULL; /* ks_multicg_offset_gpu.c:26-36 */
+
+imp_ferm_links_t *get_fn_last(void) { return fn_last; }
+void set_fn_last(imp_ferm_links_t *fn_last_new) { fn_last = fn_last_new; }
+
+#ifndef B200KS_IN_MILC
+void b200ks_milc_setup(int lx, int ly, int lz, int lt, int mixed_precision) {
+  if (s_ctx && (lx != NX || ly != NY || lz != NZ || lt != NT)) {
+    b200ks_destroy(s_ctx);
+    s_ctx = NULL;
+    fn_last = NULL;
+  }
+  s_dims[0] = lx; s_dims[1] = ly; s_dims[2] = lz; s_dims[3] = lt;
+  s_mixed = mixed_precision;
+}
+void b200ks_milc_finalize(void) {
+  if (s_ctx) b200ks_destroy(s_ctx);
+  s_ctx = NULL;
+  fn_last = NULL;
+}
+int b200ks_milc_total_iters(void) { return s_total_iters; }
+#endif
+
+static void die(const char *myname) {
+  printf("%s(0): libb200ks: %s\n", myname, b200ks_last_error());
+  FATAL(1);
+}
+
+static b200ks_ctx *context(const char *myname) {
+  if (s_ctx == NULL) {
+    int dims[4];
+    dims[0] = NX; dims[1] = NY; dims[2] = NZ; dims[3] = NT;
+    s_ctx = b200ks_create(dims, 0);
+    if (s_ctx == NULL) die(myname);
+  }
+  return s_ctx;
+}
+
+/* d_congrad5_fn_gpu.c:121-126: refresh the device links when fn changed or was rebuilt */
+static void refresh_links(const char *myname, imp_ferm_links_t *fn) {
+  if (fn != fn_last || fn->notify_quda_new_links) {
+    if (b200ks_load_links(context(myname), fn->fat, fn->lng, MILC_PRECISION, 18) < 0) die(myname);
+    fn->notify_quda_new_links = 0; /* cancel_quda_notification(fn) */
+    fn_last = fn;
+  }
+}
+
+static double source_norm(const su3_vector *v, int parity) {
+  size_t lo = (parity == ODD) ? SITES / 2 : 0, hi = (parity == EVEN) ? SITES / 2 : SITES, i;
+  double s = 0;
+  const Real *r = (const Real *)v;
+  for (i = 6 * lo; i < 6 * hi; i++) s += (double)r[i] * (double)r[i];
+  return s;
+}
+
+int ks_congrad_parity_gpu(su3_vector *t_src, su3_vector *t_dest, quark_invert_control *qic, Real mass,
+                          imp_ferm_links_t *fn) {
+  char myname[] = "ks_congrad_parity_gpu";
+  b200ks_invert_args a;
+  b200ks_invert_result r;
+  int iters;
+
+  qic->size_r = 0;
+  qic->size_relr = 0;
+  qic->final_iters = 0;
+  qic->final_restart = 0;
+  qic->converged = 1;
+  qic->final_rsq = 0.;
+  qic->final_relrsq = 0.;
+
+  if (fn == NULL) {
+    printf("%s(0): Called with NULL fn\n", myname);
+    FATAL(1);
+  }
+  if (qic->parity != EVEN && qic->parity != ODD) {
+    printf("%s: Unrecognised parity\n", myname);
+    FATAL(2);
+  }
+  /* trivial solution (d_congrad5_fn_gpu.c:63-89) */
+  if (source_norm(t_src, qic->parity) == 0.0) {
+    size_t lo = (qic->parity == ODD) ? SITES / 2 : 0;
+    memset(t_dest + lo, 0, (SITES / 2) * sizeof(su3_vector));
+    return 0;
+  }
+  refresh_links(myname, fn);
+  memset(&a, 0, sizeof(a));
+  a.parity = qic->parity;
+  a.max_iter = qic->max;
+  a.nrestart = qic->nrestart;
+  a.resid = qic->resid;
+  a.relresid = qic->relresid;
+  a.mixed_precision = (qic->prec == 1) ? (MIXED ? MIXED : 1) : MIXED;
+  if (MILC_PRECISION == 2 && qic->prec == 2) a.mixed_precision = MIXED;
+  iters = b200ks_congrad(context(myname), t_src, t_dest, (double)mass, &a, &r, MILC_PRECISION);
+  if (iters < 0) die(myname);
+  qic->final_rsq = (Real)r.final_rsq;
+  qic->final_relrsq = (Real)r.final_relrsq;
+  qic->size_r = (Real)r.size_r;
+  qic->size_relr = (Real)r.size_relr;
+  qic->final_iters = r.final_iters;
+  qic->final_restart = r.final_restart;
+  qic->converged = r.converged;
+  TOTAL_ITERS += iters;
+  return iters;
+}
+
+/* block solver = loop over sources, like the reference (d_congrad5_fn_milc.c:409-417) */
+int ks_congrad_block_parity_gpu(int nsrc, su3_vector **t_src, su3_vector **t_dest, quark_invert_control *qic,
+                                Real mass, imp_ferm_links_t *fn) {
+  int iters = 0, i;
+  for (i = 0; i < nsrc; i++) iters += ks_congrad_parity_gpu(t_src[i], t_dest[i], qic, mass, fn);
+  return iters;
+}
+
+int ks_multicg_offset_field_gpu(su3_vector *src, su3_vector **psim, ks_param *ksp, int num_offsets,
+                                quark_invert_control *qic, imp_ferm_links_t *fn) {
+  char myname[] = "ks_multicg_offset_field_gpu";
+  b200ks_invert_args a;
+  b200ks_invert_result r[B200KS_MAX_SHIFTS];
+  double offsets[B200KS_MAX_SHIFTS];
+  int j, iters;
+
+  if (qic[0].relresid != 0.) {
+    printf("%s: GPU code does not yet support a Fermilab-type relative residual\n", myname);
+    FATAL(1);
+  }
+  for (j = 0; j < num_offsets; j++) {
+    qic[j].final_rsq = 0.;
+    qic[j].final_relrsq = 0.;
+    qic[j].size_r = 0.;
+    qic[j].size_relr = 0.;
+    qic[j].final_iters = 0;
+    qic[j].final_restart = 0;
+    qic[j].converged = 1;
+  }
+  if (num_offsets == 0) return 0;
+  if (num_offsets > B200KS_MAX_SHIFTS) {
+    printf("%s: more than %d offsets\n", myname, B200KS_MAX_SHIFTS);
+    FATAL(1);
+  }
+  if (fn == NULL) {
+    printf("%s(0): Called with NULL fn\n", myname);
+    FATAL(1);
+  }
+  if (qic[0].parity == EVENANDODD) {
+    printf("%s: EVENANDODD not supported\n", myname);
+    FATAL(1);
+  }
+  if (qic[0].parity != EVEN && qic[0].parity != ODD) {
+    printf("%s: Unrecognised parity\n", myname);
+    FATAL(2);
+  }
+  for (j = 0; j < num_offsets; j++) {
+    if (ksp[j].offset <= 0) { /* ks_multicg_offset.c:139-145 */
+      printf("ks_multicg_offset_field(0): Called with nonpositive offset %e\n", (double)ksp[j].offset);
+      FATAL(1);
+    }
+    offsets[j] = ksp[j].offset;
+  }
+  if (source_norm(src, qic[0].parity) == 0.0) {
+    size_t lo = (qic[0].parity == ODD) ? SITES / 2 : 0;
+    for (j = 0; j < num_offsets; j++) memset(psim[j] + lo, 0, (SITES / 2) * sizeof(su3_vector));
+    return 0;
+  }
+  refresh_links(myname, fn);
+  memset(&a, 0, sizeof(a));
+  a.parity = qic[0].parity;
+  a.max_iter = qic[0].max;
+  a.nrestart = qic[0].nrestart;
+  a.resid = qic[0].resid;
+  a.mixed_precision = MIXED ? 1 : 0; /* never half with multi-shift (ks_multicg_offset_gpu.c:165-170) */
+  iters = b200ks_multicg(context(myname), src, (void *const *)psim, offsets, num_offsets, &a, r, MILC_PRECISION);
+  if (iters < 0) die(myname);
+  for (j = 0; j < num_offsets; j++) {
+    qic[j].final_rsq = (Real)r[j].final_rsq;
+    qic[j].size_r = (Real)r[j].size_r;
+    qic[j].final_iters = r[j].final_iters;
+    qic[j].converged = r[j].converged;
+  }
+  TOTAL_ITERS += iters;
+  return iters;
+}
+
+void dslash_fn_field(su3_vector *src, su3_vector *dest, int parity, fn_links_t *fn) {
+  char myname[] = "dslash_fn_field";
+  if (fn == NULL) {
+    printf("dslash_fn_field_special: invalid fn links!\n");
+    FATAL(1);
+  }
+  if (parity != EVEN && parity != ODD && parity != EVENANDODD) {
+    printf("%s: Unrecognised parity\n", myname);
+    FATAL(2);
+  }
+  refresh_links(myname, fn);
+  if (b200ks_dslash(context(myname), src, dest, parity, MILC_PRECISION) < 0) die(myname);
+}
