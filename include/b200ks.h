@@ -141,6 +141,8 @@ int b200ks_vec_norm2(b200ks_ctx *ctx, int vec, int parity, double *out);
 /* Synthetic HISQ-like links generated on the device (for volumes whose host copy
  * would not fit in host RAM, SURVEY.md section 7 "Host memory at the 96^3x192 point"). */
 int b200ks_links_synthetic(b200ks_ctx *ctx, unsigned long long seed, int long_recon);
+/* Read the device links back in MILC host layout (local sub-lattice). */
+int b200ks_links_download(b200ks_ctx *ctx, void *fat, void *lng, int host_prec);
 
 int b200ks_dslash_dev(b200ks_ctx *ctx, int vsrc, int vdest, int parity, int prec);
 int b200ks_congrad_dev(b200ks_ctx *ctx, int vsrc, int vdest, double mass,

@@ -49,6 +49,7 @@ SYMBOLS = [
     ("b200ks_vec_gaussian", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_ulonglong]),
     ("b200ks_vec_norm2", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("b200ks_links_synthetic", C.c_int, [C.c_void_p, C.c_ulonglong, C.c_int]),
+    ("b200ks_links_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ("b200ks_dslash_dev", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("b200ks_congrad_dev", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(InvertArgs),
                                      C.POINTER(InvertResult)]),

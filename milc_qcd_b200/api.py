@@ -83,11 +83,21 @@ def _ptr(a):
 class Context:
     """One lattice on one GPU (``b200ks_create``)."""
 
-    def __init__(self, dims, device=0):
+    def __init__(self, dims, device=0, grid=None, rank=0, nranks=1, nccl_id=None):
+        """Single GPU: Context(dims).  One rank per GPU: Context(global_dims, device, grid, rank,
+        nranks, nccl_id) with nccl_id from :func:`comm_unique_id` on rank 0, broadcast by the
+        caller; host arrays are then the LOCAL sub-lattice (see milc_qcd_b200.dist)."""
         self.lib = _lib.load()
-        self.dims = tuple(int(d) for d in dims)
-        arr = (C.c_int * 4)(*self.dims)
-        self.h = self.lib.b200ks_create(arr, device)
+        self.global_dims = tuple(int(d) for d in dims)
+        arr = (C.c_int * 4)(*self.global_dims)
+        if grid is None or nranks == 1:
+            self.dims = self.global_dims
+            self.h = self.lib.b200ks_create(arr, device)
+        else:
+            self.dims = tuple(self.global_dims[d] // int(grid[d]) for d in range(4))
+            garr = (C.c_int * 4)(*[int(g) for g in grid])
+            buf = C.create_string_buffer(bytes(nccl_id), 128)
+            self.h = self.lib.b200ks_create_dist(arr, garr, rank, nranks, buf, device)
         if not self.h:
             raise _lib.B200KSError("b200ks_create failed: %s" % self.lib.b200ks_last_error().decode())
         self.volume = int(np.prod(self.dims))
@@ -189,6 +199,18 @@ class Context:
         it = check(self.lib.b200ks_multicg_dev(self.h, vsrc, hs, offs, n, C.byref(args), res), "b200ks_multicg_dev")
         return it, [res[j].as_dict() for j in range(n)]
 
+    def vec_gaussian(self, v, parity, seed):
+        check(self.lib.b200ks_vec_gaussian(self.h, v, parity, seed), "b200ks_vec_gaussian")
+
+    def links_synthetic(self, seed, long_recon=18):
+        check(self.lib.b200ks_links_synthetic(self.h, seed, long_recon), "b200ks_links_synthetic")
+
+    def links_download(self, dtype=np.float64):
+        fat = np.zeros((self.volume, 4, 3, 3, 2), dtype=dtype)
+        lng = np.zeros_like(fat)
+        check(self.lib.b200ks_links_download(self.h, _ptr(fat), _ptr(lng), _host_prec(fat)), "b200ks_links_download")
+        return fat, lng
+
     def dslash_time(self, prec, parity, n):
         out = C.c_double()
         check(self.lib.b200ks_dslash_time(self.h, prec, parity, n, C.byref(out)), "b200ks_dslash_time")
@@ -199,6 +221,13 @@ class Context:
 
     def device_bytes(self):
         return int(self.lib.b200ks_device_bytes(self.h))
+
+
+def comm_unique_id():
+    """128-byte ncclUniqueId for b200ks_create_dist (call on rank 0, broadcast to the others)."""
+    buf = C.create_string_buffer(128)
+    check(_lib.load().b200ks_comm_unique_id(buf), "b200ks_comm_unique_id")
+    return bytes(buf.raw)
 
 
 # ---- MILC-named operators ------------------------------------------------------------------------

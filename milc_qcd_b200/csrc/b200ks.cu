@@ -16,7 +16,9 @@
 
 #include "../../include/b200ks.h"
 #include "blas.cuh"
+#include "comm.cuh"
 #include "dslash.cuh"
+#include "synth.cuh"
 
 using namespace b200ks;
 
@@ -67,6 +69,7 @@ struct b200ks_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long launches = 0;
   size_t bytes = 0;
+  Comm comm;             // one-rank-per-GPU decomposition (nranks == 1: unused)
 };
 
 static size_t real_size(int prec) { return prec == B200KS_PREC_DOUBLE ? 8 : 4; }
@@ -128,19 +131,21 @@ extern "C" int b200ks_device_count(void) {
   return ok;
 }
 
-static int setup_geom(b200ks_ctx *c, const int local[4], const int part[4]) {
+static int setup_geom(b200ks_ctx *c, const int local[4], const int part[4], const int origin[4]) {
   Geom &g = c->g;
   for (int d = 0; d < 4; d++) {
     if (local[d] < 2 || (local[d] & 1))
       return fail(B200KS_EINVAL, "lattice extents must be even and >= 2 (staggered checkerboard, generic_ks/rephase.c:14-16)");
     g.L[d] = local[d];
     g.part[d] = part[d];
+    g.origin[d] = origin[d];
+    g.G[d] = c->global[d];
   }
   g.Lxh = g.L[0] / 2;
   long long vol = (long long)g.L[0] * g.L[1] * g.L[2] * g.L[3];
   if (vol / 2 > (1ll << 30)) return fail(B200KS_EINVAL, "local volume too large for 32-bit site indices");
   g.Vh = (int)(vol / 2);
-  int sites = g.Vh, lsites = g.Vh;
+  int gsites = 0, lsites = g.Vh;
   for (int d = 0; d < 4; d++) {
     g.faceh[d] = g.Vh / g.L[d];
     g.ghost[d][0] = g.ghost[d][1] = 0;
@@ -148,18 +153,19 @@ static int setup_geom(b200ks_ctx *c, const int local[4], const int part[4]) {
     if (g.part[d]) {
       if (d < 2) return fail(B200KS_EINVAL, "only z and t may be partitioned");
       if (g.L[d] < 6) return fail(B200KS_EINVAL, "partitioned extent must be >= 6 (depth-3 ghost zones)");
-      g.ghost[d][0] = sites; sites += 3 * g.faceh[d];
-      g.ghost[d][1] = sites; sites += 3 * g.faceh[d];
+      g.ghost[d][0] = g.Vh + gsites; gsites += 3 * g.faceh[d];
+      g.ghost[d][1] = g.Vh + gsites; gsites += 3 * g.faceh[d];
       g.lghost[d] = lsites; lsites += 3 * g.faceh[d];
     }
   }
-  g.stride = (sites + 63) / 64 * 64;
+  g.stride = (g.Vh + 63) / 64 * 64;
+  g.gstride = (gsites + 63) / 64 * 64;
   g.lstride = (lsites + 63) / 64 * 64;
-  g.origin_parity = 0;
   return 0;
 }
 
-static b200ks_ctx *create_common(const int latsize[4], const int local[4], const int part[4], int device) {
+static b200ks_ctx *create_common(const int latsize[4], const int local[4], const int part[4], const int origin[4],
+                                 int device) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -177,7 +183,7 @@ static b200ks_ctx *create_common(const int latsize[4], const int local[4], const
   b200ks_ctx *c = new b200ks_ctx;
   c->device = device;
   memcpy(c->global, latsize, sizeof(c->global));
-  if (setup_geom(c, local, part) < 0) { delete c; return nullptr; }
+  if (setup_geom(c, local, part, origin) < 0) { delete c; return nullptr; }
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
   c->max_blocks = nblocks(c->g.Vh) + 8;
   void *p = nullptr;
@@ -203,8 +209,8 @@ static b200ks_ctx *create_common(const int latsize[4], const int local[4], const
 }
 
 extern "C" b200ks_ctx *b200ks_create(const int latsize[4], int device) {
-  const int part[4] = {0, 0, 0, 0};
-  return create_common(latsize, latsize, part, device);
+  const int part[4] = {0, 0, 0, 0}, origin[4] = {0, 0, 0, 0};
+  return create_common(latsize, latsize, part, origin, device);
 }
 
 extern "C" void b200ks_destroy(b200ks_ctx *c) {
@@ -219,6 +225,14 @@ extern "C" void b200ks_destroy(b200ks_ctx *c) {
       cudaFree(c->links[k].lng[p]);
     }
   }
+  if (c->comm.halo) nccl().CommDestroy(c->comm.halo);
+  if (c->comm.red) nccl().CommDestroy(c->comm.red);
+  cudaFree(c->comm.ghost[0]);
+  cudaFree(c->comm.zsend);
+  cudaFree(c->comm.ext_sites);
+  if (c->comm.ev_ready) cudaEventDestroy(c->comm.ev_ready);
+  if (c->comm.ev_done) cudaEventDestroy(c->comm.ev_done);
+  if (c->comm.stream) cudaStreamDestroy(c->comm.stream);
   cudaFree(c->ws.partials);
   cudaFree(c->ws.counter);
   cudaFree(c->d_state);
@@ -257,10 +271,69 @@ static int check_launch(const char *what) {
 static int links_alloc(b200ks_ctx *c, int prec) {
   Links &L = c->links[prec];
   for (int p = 0; p < 2; p++) {
-    if (!L.fat[p]) CHK(dev_alloc(c, &L.fat[p], link_bytes(c, prec)));
-    if (!L.lng[p]) CHK(dev_alloc(c, &L.lng[p], link_bytes(c, prec)));
+    if (!L.fat[p]) {
+      CHK(dev_alloc(c, &L.fat[p], link_bytes(c, prec)));
+      CU(cudaMemsetAsync(L.fat[p], 0, link_bytes(c, prec), c->stream));
+    }
+    if (!L.lng[p]) {
+      CHK(dev_alloc(c, &L.lng[p], link_bytes(c, prec)));
+      CU(cudaMemsetAsync(L.lng[p], 0, link_bytes(c, prec), c->stream));
+    }
   }
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// communication helpers (no-ops on a single GPU)
+#define NC(call)                                                                                   \
+  do {                                                                                             \
+    int e_ = (call);                                                                               \
+    if (e_ != ncclSuccess)                                                                         \
+      return fail(B200KS_ECOMM, std::string(#call) + ": " +                                        \
+                                    (nccl().GetErrorString ? nccl().GetErrorString(e_) : "NCCL error")); \
+  } while (0)
+
+static int allreduce(b200ks_ctx *c, double *dptr, int n) {
+  if (c->comm.nranks == 1) return 0;
+  NC(nccl().AllReduce(dptr, dptr, (size_t)n, ncclDouble, ncclSum, c->comm.red, c->stream));
+  return 0;
+}
+
+// Backward hops across a partition boundary need the links stored on the backward
+// neighbour (sites -3..-1).  Links are static: exchange once per load, into the tail of
+// every link component array of direction d.
+template <typename T>
+static int exchange_link_ghosts_T(b200ks_ctx *c, int prec) {
+  using T2 = typename Vec2<T>::type;
+  const Geom &g = c->g;
+  Comm &cm = c->comm;
+  if (cm.nranks == 1) return 0;
+  for (int d = 2; d < 4; d++) {
+    if (!g.part[d]) continue;
+    const size_t face3 = (size_t)3 * g.faceh[d];
+    T2 *buf = nullptr;
+    if (d == 2) CHK(dev_alloc(c, (void **)&buf, 9 * face3 * sizeof(T2)));
+    for (int which = 0; which < 2; which++)
+      for (int p = 0; p < 2; p++) {
+        T2 *U = (T2 *)(which ? c->links[prec].lng[p] : c->links[prec].fat[p]);
+        if (d == 2)
+          LAUNCH(c, (pack_zhigh_links_kernel<T>), nblocks((int)(9 * face3)), buf, U, g, d);
+        NC(nccl().GroupStart());
+        for (int e = 0; e < 9; e++) {
+          T2 *comp = U + (size_t)(d * 9 + e) * g.lstride;
+          const T2 *src = (d == 3) ? comp + (size_t)(g.L[3] - 3) * g.faceh[3] : buf + e * face3;
+          NC(nccl().Send(src, face3 * sizeof(T2), ncclChar, cm.nbr[d][1], cm.halo, c->stream));
+          NC(nccl().Recv(comp + g.lghost[d], face3 * sizeof(T2), ncclChar, cm.nbr[d][0], cm.halo, c->stream));
+        }
+        NC(nccl().GroupEnd());
+      }
+    CU(cudaStreamSynchronize(c->stream));
+    if (buf) dev_free(c, buf, 9 * face3 * sizeof(T2));
+  }
+  return check_launch("exchange_link_ghosts");
+}
+static int exchange_link_ghosts(b200ks_ctx *c, int prec) {
+  return prec == 2 ? exchange_link_ghosts_T<double>(c, prec) : exchange_link_ghosts_T<float>(c, prec);
 }
 
 template <typename T, typename TH>
@@ -292,6 +365,7 @@ extern "C" int b200ks_load_links(b200ks_ctx *c, const void *fat, const void *lng
   CU(cudaStreamSynchronize(c->stream));
   dev_free(c, stage, half_bytes);
   CHK(check_launch("pack_link_kernel"));
+  CHK(exchange_link_ghosts(c, prec));
   c->link_master = prec;
   for (int k = 0; k < 3; k++) c->links[k].valid = (k == prec);
   return 0;
@@ -309,9 +383,9 @@ static int links_ensure(b200ks_ctx *c, int prec) {
       void *d = which ? c->links[prec].lng[p] : c->links[prec].fat[p];
       const void *s = which ? c->links[m].lng[p] : c->links[m].fat[p];
       if (prec == 1 && m == 2)
-        LAUNCH(c, (convert_link_kernel<float, double>), nblocks(c->g.Vh), (float2 *)d, (const double2 *)s, c->g.lstride, c->g.Vh);
+        LAUNCH(c, (convert_link_kernel<float, double>), nblocks(c->g.lstride), (float2 *)d, (const double2 *)s, c->g.lstride, c->g.lstride);
       else if (prec == 2 && m == 1)
-        LAUNCH(c, (convert_link_kernel<double, float>), nblocks(c->g.Vh), (double2 *)d, (const float2 *)s, c->g.lstride, c->g.Vh);
+        LAUNCH(c, (convert_link_kernel<double, float>), nblocks(c->g.lstride), (double2 *)d, (const float2 *)s, c->g.lstride, c->g.lstride);
     }
   }
   CHK(check_launch("convert_link_kernel"));
@@ -326,9 +400,42 @@ struct Epi {
   double s = 0;
   const DevVec *w = nullptr;
   const DevVec *r = nullptr;
-  double *red = nullptr;
+  double *red = nullptr;      // reduction slots (interior pass / single GPU)
+  double *red_ext = nullptr;  // reduction slots of the exterior pass (multi-GPU)
   const int *stop = nullptr;
 };
+
+// Depth-3 halo of `in` (parity half pin): z faces are packed, t faces are sent straight
+// from the field; everything travels as one NCCL group on the comm stream while the
+// interior pass runs on the compute stream.
+template <typename T>
+static int halo_start(b200ks_ctx *c, const DevVec &in, int pin) {
+  using T2 = typename Vec2<T>::type;
+  const Geom &g = c->g;
+  Comm &cm = c->comm;
+  const T2 *f = (const T2 *)in.p[pin];
+  T2 *ghost = (T2 *)cm.ghost[0];
+  T2 *zs = (T2 *)cm.zsend;
+  if (g.part[2]) LAUNCH(c, (pack_zface_kernel<T>), nblocks(6 * g.faceh[2]), zs, f, g);
+  CU(cudaEventRecord(cm.ev_ready, c->stream));
+  CU(cudaStreamWaitEvent(cm.stream, cm.ev_ready, 0));
+  NC(nccl().GroupStart());
+  for (int d = 2; d < 4; d++) {
+    if (!g.part[d]) continue;
+    const size_t face3 = (size_t)3 * g.faceh[d], bytes = face3 * sizeof(T2);
+    for (int q = 0; q < 3; q++) {
+      const T2 *lo = (d == 3) ? f + (size_t)q * g.stride : zs + (size_t)(0 * 3 + q) * face3;
+      const T2 *hi = (d == 3) ? f + (size_t)q * g.stride + (size_t)(g.L[3] - 3) * g.faceh[3] : zs + (size_t)(1 * 3 + q) * face3;
+      NC(nccl().Send(hi, bytes, ncclChar, cm.nbr[d][1], cm.halo, cm.stream));
+      NC(nccl().Send(lo, bytes, ncclChar, cm.nbr[d][0], cm.halo, cm.stream));
+      NC(nccl().Recv(ghost + (size_t)q * g.gstride + (g.ghost[d][0] - g.Vh), bytes, ncclChar, cm.nbr[d][0], cm.halo, cm.stream));
+      NC(nccl().Recv(ghost + (size_t)q * g.gstride + (g.ghost[d][1] - g.Vh), bytes, ncclChar, cm.nbr[d][1], cm.halo, cm.stream));
+    }
+  }
+  NC(nccl().GroupEnd());
+  CU(cudaEventRecord(cm.ev_done, cm.stream));
+  return 0;
+}
 
 template <typename T>
 static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, const Epi &e) {
@@ -343,6 +450,7 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
   a.fat_other = (const T2 *)L.fat[par_out ^ 1];
   a.lng_other = (const T2 *)L.lng[par_out ^ 1];
   a.in = (const T2 *)in.p[par_out ^ 1];
+  a.gin = (const T2 *)c->comm.ghost[0];
   a.out = (T2 *)out.p[par_out];
   a.w = e.w ? (const T2 *)e.w->p[par_out] : nullptr;
   a.r = e.r ? (const T2 *)e.r->p[par_out] : nullptr;
@@ -350,13 +458,28 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
   a.ws = c->ws;
   a.red = e.red;
   a.stop = e.stop;
-  a.site_begin = 0;
-  a.site_end = c->g.Vh;
-  a.ghost_mode = 0;
+  a.sites = nullptr;
+  a.nsites = c->g.Vh;
   const int grid = nblocks(c->g.Vh);
-  if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, 0>), grid, a);
-  else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, 0>), grid, a);
-  else LAUNCH(c, (dslash_kernel<T, 2, 0>), grid, a);
+  if (c->comm.nranks == 1) {
+    if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, 0>), grid, a);
+    else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, 0>), grid, a);
+    else LAUNCH(c, (dslash_kernel<T, 2, 0>), grid, a);
+    return 0;
+  }
+  // multi-GPU: halo exchange || interior pass, then the exterior pass on the boundary sites
+  CHK(halo_start<T>(c, in, par_out ^ 1));
+  if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, 1>), grid, a);
+  else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, 1>), grid, a);
+  else LAUNCH(c, (dslash_kernel<T, 2, 1>), grid, a);
+  CU(cudaStreamWaitEvent(c->stream, c->comm.ev_done, 0));
+  a.sites = c->comm.ext_sites;
+  a.nsites = c->comm.n_ext;
+  a.red = e.red_ext;
+  const int egrid = nblocks(c->comm.n_ext);
+  if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, 2>), egrid, a);
+  else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, 2>), egrid, a);
+  else LAUNCH(c, (dslash_kernel<T, 2, 2>), egrid, a);
   return 0;
 }
 
@@ -424,6 +547,7 @@ static int norm2(b200ks_ctx *c, const DevVec &v, int pbit, double *out) {
     LAUNCH(c, (norm2_kernel<double>), nblocks(c->g.Vh), (const double2 *)v.p[pbit], c->g.stride, c->g.Vh, c->ws, c->d_scal);
   else
     LAUNCH(c, (norm2_kernel<float>), nblocks(c->g.Vh), (const float2 *)v.p[pbit], c->g.stride, c->g.Vh, c->ws, c->d_scal);
+  CHK(allreduce(c, c->d_scal, 1));
   CU(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   *out = c->h_scal[0];
@@ -574,6 +698,7 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
   const double msq_x4 = 4.0 * mass * mass;
   const int max_cg = max_restarts * niter;
   const bool rel = relrsqmin > 0;
+  const bool multi = c->comm.nranks > 1;
   const int batch = args.check_interval > 0 ? args.check_interval : 8;
 
   res = b200ks_invert_result();
@@ -618,6 +743,7 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
       else
         LAUNCH(c, (cg_restart_kernel<T, false>), grid, (const T2 *)b.p[pb], (const T2 *)ttt->p[pb], (const T2 *)x.p[pb],
                (T2 *)r->p[pb], (T2 *)p->p[pb], g.stride, g.Vh, c->ws, c->d_scal);
+      CHK(allreduce(c, c->d_scal, 2));
       CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       CU(cudaStreamSynchronize(c->stream));
       CHK(check_launch("cg restart"));
@@ -631,8 +757,10 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
         break;
       nrestart++;
       h.rsq = rsq;
-      h.cur = 0;
-      h.actual[0] = rsq;
+      // oldrsq of the first iteration.  Without the relative residual, upd[] is all-reduced
+      // together with red[] inside the iteration, so only rank 0 carries the value.
+      h.upd[0] = (multi && !rel && c->comm.rank != 0) ? 0.0 : rsq;
+      h.upd[1] = 0;
       h.iter = iteration;
       h.stop = 0;
       h.size_relr = relrsq;
@@ -645,14 +773,20 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
         Epi e0, e1;
         e0.stop = &c->d_state->stop;
         CHK(dslash_T<T>(c, *p, *ttt, ob, e0));
-        e1.kind = 2; e1.s = -msq_x4; e1.w = p; e1.r = r; e1.red = c->d_state->red; e1.stop = &c->d_state->stop;
+        e1.kind = 2; e1.s = -msq_x4; e1.w = p; e1.r = r; e1.red = c->d_state->red; e1.red_ext = c->d_state->red_ext;
+        e1.stop = &c->d_state->stop;
         CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
+        if (multi) {  // one all-reduce per iteration: {pkp, c_tr, c_tt} + last update's |r|^2
+          LAUNCH1(c, combine_red_kernel, c->d_state, 3);
+          CHK(allreduce(c, c->d_state->red, rel ? 3 : 5));
+        }
         if (rel)
           LAUNCH(c, (cg_update_kernel<T, true>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
                  g.stride, g.Vh, c->d_state, c->ws);
         else
           LAUNCH(c, (cg_update_kernel<T, false>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
                  g.stride, g.Vh, c->d_state, c->ws);
+        if (multi && rel) CHK(allreduce(c, c->d_state->upd_next, 2));
         LAUNCH1(c, cg_scalar_kernel, c->d_state, rel ? 1 : 0, prec == 1 ? 1 : 0);
       }
       CHK(state_pull(c));
@@ -759,6 +893,7 @@ static int multicg_T(b200ks_ctx *c, const DevVec &b, DevVec *const *psim, const 
   const double shift0 = -h.shifts[j_low];
 
   LAUNCH(c, (ms_init_kernel<T>), grid, ptrs, n, (const T2 *)b.p[pb], (T2 *)r->p[pb], g.stride, g.Vh, c->ws, c->d_scal);
+  CHK(allreduce(c, c->d_scal, 1));
   CU(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CHK(check_launch("ms_init_kernel"));
@@ -789,9 +924,15 @@ static int multicg_T(b200ks_ctx *c, const DevVec &b, DevVec *const *psim, const 
       Epi e0, e1;
       e0.stop = &c->d_state->stop;
       CHK(dslash_T<T>(c, *cgp, *ttt, ob, e0));
-      e1.kind = 2; e1.s = shift0; e1.w = cgp; e1.r = nullptr; e1.red = c->d_state->red; e1.stop = &c->d_state->stop;
+      e1.kind = 2; e1.s = shift0; e1.w = cgp; e1.r = nullptr; e1.red = c->d_state->red; e1.red_ext = c->d_state->red_ext;
+      e1.stop = &c->d_state->stop;
       CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
+      if (c->comm.nranks > 1) {
+        LAUNCH1(c, combine_red_kernel, c->d_state, 1);
+        CHK(allreduce(c, c->d_state->red, 1));
+      }
       LAUNCH(c, (ms_resid_kernel<T>), grid, (T2 *)r->p[pb], (const T2 *)ttt->p[pb], g.stride, g.Vh, c->d_state, c->ws);
+      CHK(allreduce(c, &c->d_state->rsq_new, 1));
       LAUNCH1(c, ms_scalar_kernel, c->d_state);
       LAUNCH(c, (ms_update_kernel<T>), grid, ptrs, (const T2 *)r->p[pb], g.stride, g.Vh, c->d_state);
       LAUNCH1(c, ms_scroll_kernel, c->d_state);
@@ -864,15 +1005,151 @@ extern "C" int b200ks_multicg(b200ks_ctx *c, const void *src, void *const *psim,
 }
 
 // ---------------------------------------------------------------------------------------------
-// not yet implemented pieces of the ABI (fail loudly, never silently)
-extern "C" b200ks_ctx *b200ks_create_dist(const int *, const int *, int, int, const void *, int) {
-  fail(B200KS_EINVAL, "b200ks_create_dist: multi-GPU contexts are not implemented yet");
-  return nullptr;
+// one-rank-per-GPU contexts
+extern "C" int b200ks_comm_unique_id(void *out128) {
+  if (!out128) return fail(B200KS_EINVAL, "b200ks_comm_unique_id: null argument");
+  if (!nccl().ok) return fail(B200KS_ECOMM, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  NC(nccl().GetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
+  return 0;
 }
-extern "C" int b200ks_comm_unique_id(void *) { return fail(B200KS_ECOMM, "b200ks_comm_unique_id: not implemented yet"); }
-extern "C" int b200ks_vec_gaussian(b200ks_ctx *, int, int, unsigned long long) {
-  return fail(B200KS_EINVAL, "b200ks_vec_gaussian: not implemented yet");
+
+extern "C" b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4], int rank, int nranks,
+                                          const void *nccl_unique_id, int device) {
+  if (!latsize || !grid) { fail(B200KS_EINVAL, "b200ks_create_dist: null argument"); return nullptr; }
+  if (grid[0] != 1 || grid[1] != 1 || grid[2] < 1 || grid[3] < 1 || grid[2] * grid[3] != nranks || rank < 0 || rank >= nranks) {
+    fail(B200KS_EINVAL, "b200ks_create_dist: grid must be {1,1,gz,gt} with gz*gt == nranks");
+    return nullptr;
+  }
+  int local[4], part[4], origin[4], coord[4] = {0, 0, rank % grid[2], rank / grid[2]};
+  for (int d = 0; d < 4; d++) {
+    if (latsize[d] % grid[d]) { fail(B200KS_EINVAL, "lattice extent not divisible by the rank grid"); return nullptr; }
+    local[d] = latsize[d] / grid[d];
+    part[d] = grid[d] > 1;
+    origin[d] = coord[d] * local[d];
+  }
+  if (nranks == 1) return create_common(latsize, local, part, origin, device);
+  if (!nccl_unique_id) { fail(B200KS_EINVAL, "b200ks_create_dist: null nccl_unique_id"); return nullptr; }
+  if (!nccl().ok) { fail(B200KS_ECOMM, "libnccl.so.2 could not be loaded"); return nullptr; }
+  b200ks_ctx *c = create_common(latsize, local, part, origin, device);
+  if (!c) return nullptr;
+  Comm &cm = c->comm;
+  cm.rank = rank;
+  cm.nranks = nranks;
+  for (int d = 0; d < 4; d++) { cm.grid[d] = grid[d]; cm.coord[d] = coord[d]; }
+  auto rank_of = [&](int zc, int tc) { return ((tc + grid[3]) % grid[3]) * grid[2] + (zc + grid[2]) % grid[2]; };
+  cm.nbr[2][0] = rank_of(coord[2] - 1, coord[3]);
+  cm.nbr[2][1] = rank_of(coord[2] + 1, coord[3]);
+  cm.nbr[3][0] = rank_of(coord[2], coord[3] - 1);
+  cm.nbr[3][1] = rank_of(coord[2], coord[3] + 1);
+  auto init = [&]() -> int {
+    ncclUniqueId ids[2];
+    memcpy(ids, nccl_unique_id, sizeof(ncclUniqueId));
+    // the second communicator (all-reduces) gets its id from rank 0 over the first one
+    NC(nccl().CommInitRank(&cm.halo, nranks, ids[0], rank));
+    CU(cudaStreamCreateWithFlags(&cm.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&cm.ev_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&cm.ev_done, cudaEventDisableTiming));
+    char *d_id = nullptr;
+    CU(cudaMalloc(&d_id, sizeof(ncclUniqueId)));
+    if (rank == 0) {
+      NC(nccl().GetUniqueId(&ids[1]));
+      CU(cudaMemcpy(d_id, &ids[1], sizeof(ncclUniqueId), cudaMemcpyHostToDevice));
+    } else {
+      CU(cudaMemset(d_id, 0, sizeof(ncclUniqueId)));
+    }
+    // broadcast by all-reduce(sum) of bytes widened to doubles would be wasteful; send/recv it
+    NC(nccl().GroupStart());
+    if (rank == 0) {
+      for (int r = 1; r < nranks; r++) NC(nccl().Send(d_id, sizeof(ncclUniqueId), ncclChar, r, cm.halo, c->stream));
+    } else {
+      NC(nccl().Recv(d_id, sizeof(ncclUniqueId), ncclChar, 0, cm.halo, c->stream));
+    }
+    NC(nccl().GroupEnd());
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(&ids[1], d_id, sizeof(ncclUniqueId), cudaMemcpyDeviceToHost));
+    cudaFree(d_id);
+    NC(nccl().CommInitRank(&cm.red, nranks, ids[1], rank));
+    // ghost buffer, z send buffer (sized for double), boundary-site list
+    const Geom &g = c->g;
+    CHK(dev_alloc(c, &cm.ghost[0], (size_t)3 * g.gstride * sizeof(double2)));
+    CU(cudaMemset(cm.ghost[0], 0, (size_t)3 * g.gstride * sizeof(double2)));
+    if (g.part[2]) CHK(dev_alloc(c, &cm.zsend, (size_t)18 * g.faceh[2] * sizeof(double2)));
+    std::vector<int> ext;
+    const int S2 = g.Lxh * g.L[1];
+    for (int t = 0; t < g.L[3]; t++)
+      for (int z = 0; z < g.L[2]; z++) {
+        const bool b = (g.part[3] && (t < 3 || t >= g.L[3] - 3)) || (g.part[2] && (z < 3 || z >= g.L[2] - 3));
+        if (!b) continue;
+        const int base = (t * g.L[2] + z) * S2;
+        for (int k = 0; k < S2; k++) ext.push_back(base + k);
+      }
+    cm.n_ext = (int)ext.size();
+    CHK(dev_alloc(c, (void **)&cm.ext_sites, sizeof(int) * ext.size()));
+    CU(cudaMemcpy(cm.ext_sites, ext.data(), sizeof(int) * ext.size(), cudaMemcpyHostToDevice));
+    return 0;
+  };
+  if (init() < 0) {
+    b200ks_destroy(c);
+    return nullptr;
+  }
+  return c;
 }
-extern "C" int b200ks_links_synthetic(b200ks_ctx *, unsigned long long, int) {
-  return fail(B200KS_EINVAL, "b200ks_links_synthetic: not implemented yet");
+
+// ---------------------------------------------------------------------------------------------
+// synthetic fields on the device, link read-back
+extern "C" int b200ks_vec_gaussian(b200ks_ctx *c, int h, int parity, unsigned long long seed) {
+  DevVec *v = uvec(c, h);
+  if (!v) return B200KS_EINVAL;
+  CU(cudaSetDevice(c->device));
+  for (int p = 0; p < 2; p++) {
+    if (!((parity == B200KS_EVENANDODD) || (parity == B200KS_EVEN && p == 0) || (parity == B200KS_ODD && p == 1))) continue;
+    LAUNCH(c, (synth_vec_kernel<double>), nblocks(c->g.Vh), (double2 *)v->p[p], c->g, p, (uint64_t)seed);
+  }
+  return check_launch("synth_vec_kernel");
+}
+
+extern "C" int b200ks_links_synthetic(b200ks_ctx *c, unsigned long long seed, int long_recon) {
+  if (!c) return fail(B200KS_EINVAL, "null context");
+  if (long_recon != 18) return fail(B200KS_EINVAL, "long_recon: only 18 is implemented");
+  CU(cudaSetDevice(c->device));
+  CHK(links_alloc(c, 2));
+  int lsites = c->g.Vh;
+  for (int d = 2; d < 4; d++)
+    if (c->g.part[d]) lsites = c->g.lghost[d] + 3 * c->g.faceh[d];
+  for (int p = 0; p < 2; p++)
+    LAUNCH(c, (synth_links_kernel<double>), nblocks(lsites), (double2 *)c->links[2].fat[p], (double2 *)c->links[2].lng[p],
+           c->g, p, (uint64_t)seed, 0.05, -1.0 / 24.0, lsites);
+  CU(cudaStreamSynchronize(c->stream));
+  CHK(check_launch("synth_links_kernel"));
+  c->link_master = 2;
+  for (int k = 0; k < 3; k++) c->links[k].valid = (k == 2);
+  return 0;
+}
+
+extern "C" int b200ks_links_download(b200ks_ctx *c, void *fat, void *lng, int host_prec) {
+  if (!c || !fat || !lng) return fail(B200KS_EINVAL, "b200ks_links_download: null argument");
+  if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
+  if (c->link_master == 0) return fail(B200KS_ESTATE, "links not loaded");
+  CU(cudaSetDevice(c->device));
+  const int m = c->link_master;
+  const size_t hs = host_prec == 2 ? 8 : 4;
+  const size_t half_bytes = (size_t)c->g.Vh * 72 * hs;
+  void *stage = nullptr;
+  CHK(dev_alloc(c, &stage, half_bytes));
+  for (int which = 0; which < 2; which++)
+    for (int p = 0; p < 2; p++) {
+      const void *src = which ? c->links[m].lng[p] : c->links[m].fat[p];
+      const int grid = nblocks(c->g.Vh);
+      if (m == 2 && host_prec == 2) LAUNCH(c, (unpack_link_kernel<double, double>), grid, (double *)stage, (const double2 *)src, c->g.lstride, c->g.Vh);
+      else if (m == 2 && host_prec == 1) LAUNCH(c, (unpack_link_kernel<double, float>), grid, (float *)stage, (const double2 *)src, c->g.lstride, c->g.Vh);
+      else if (m == 1 && host_prec == 2) LAUNCH(c, (unpack_link_kernel<float, double>), grid, (double *)stage, (const float2 *)src, c->g.lstride, c->g.Vh);
+      else LAUNCH(c, (unpack_link_kernel<float, float>), grid, (float *)stage, (const float2 *)src, c->g.lstride, c->g.Vh);
+      char *h = (char *)(which ? lng : fat);
+      CU(cudaMemcpyAsync(h + (size_t)p * half_bytes, stage, half_bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+  CU(cudaStreamSynchronize(c->stream));
+  dev_free(c, stage, half_bytes);
+  return check_launch("unpack_link_kernel");
 }

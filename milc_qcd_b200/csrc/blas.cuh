@@ -13,11 +13,13 @@ namespace b200ks {
 // ---- device-resident solver state ------------------------------------------------------
 struct CgState {
   // single-mass CG (generic_ks/d_congrad5_fn_milc.c)
+  // red[3] and upd[2] are contiguous on purpose: multi-GPU solves all-reduce them together
   double red[3];       // pkp, c_tr, c_tt of the current iteration (dslash epilogue)
+  double upd[2];       // {sum |r|^2 (actual_rsq, :283,318-336), sum |r_s|^2/|x_s|^2} of the
+                       // PREVIOUS update = this iteration's oldrsq
+  double red_ext[3];   // multi-GPU: the exterior pass's share of red[]
+  double upd_next[2];  // reduction target of the update kernel; becomes upd[] afterwards
   double rsq;          // recursive |r|^2 (FEWSUMS expansion value, :339)
-  double actual[2];    // directly summed |r|^2, ping-pong (actual_rsq, :283,318-336)
-  double upd[2];       // reduction target of the update kernel: {sum |r|^2, sum |r_s|^2/|x_s|^2}
-  double relsum;       // sum |r_s|^2/|x_s|^2 (Fermilab residual, :37-56)
   double source_norm;
   double rsqmin, relrsqmin;
   double size_r, size_relr;
@@ -25,7 +27,7 @@ struct CgState {
   int iter;            // iterations done (counts multiplications by M^+M, :223,310)
   int niter;           // restart interval
   int stop;            // 0 run, 1 stop requested (this iteration completes), 2 stopped
-  int cur;             // ping-pong index into actual[]
+  int cur;             // (unused)
   // multi-shift CG (generic_ks/ks_multicg_offset.c)
   int n, n_now, j_low;
   int max_iter;
@@ -127,7 +129,7 @@ cg_update_kernel(typename Vec2<T>::type *x, typename Vec2<T>::type *r, typename 
                  const typename Vec2<T>::type *ttt, int stride, int n, CgState *st, ReduceWs ws) {
   using T2 = typename Vec2<T>::type;
   if (st->stop) return;
-  const double rsq = st->rsq, oldrsq = st->actual[st->cur];
+  const double rsq = st->rsq, oldrsq = st->upd[0];
   const double pkp = st->red[0], c_tr = st->red[1], c_tt = st->red[2];
   const T a = (T)(-rsq / pkp);
   const double rsq_new = oldrsq + 2.0 * (double)a * c_tr + (double)a * (double)a * c_tt;
@@ -156,24 +158,33 @@ cg_update_kernel(typename Vec2<T>::type *x, typename Vec2<T>::type *r, typename 
     s[0] = rn;
     if (kRel) s[1] = (xn == 0) ? 1.0 : rn / xn;
   }
-  grid_reduce<2>(s, ws, st->upd);
+  // safe although other CTAs read st->upd at their start: the last ticket is taken only
+  // after every CTA has passed that read
+  grid_reduce<2>(s, ws, st->upd_next);
 }
 
 // One thread: advance the recurrence after cg_update_kernel and decide whether the host
 // has to look (restart interval reached, or recursive residual under the target).
 // Mirrors d_congrad5_fn_milc.c:177-179,310,339,350-354.
+// multi-GPU: fold the exterior pass's partial sums into red[] before the all-reduce
+__global__ void combine_red_kernel(CgState *st, int n) {
+  if (st->stop) return;
+  for (int k = 0; k < n; k++) st->red[k] += st->red_ext[k];
+}
+
 __global__ void cg_scalar_kernel(CgState *st, int use_rel, int single) {
   if (st->stop) { st->stop = 2; return; }
-  const double rsq = st->rsq, oldrsq = st->actual[st->cur];
+  const double rsq = st->rsq, oldrsq = st->upd[0];
   const double a = single ? (double)(float)(-rsq / st->red[0]) : -rsq / st->red[0];
-  st->actual[st->cur ^ 1] = st->upd[0];
-  st->relsum = st->upd[1];
   const double rsq_new = oldrsq + 2.0 * a * st->red[1] + a * a * st->red[2];
+  // upd_next holds this rank's share; with several GPUs it is summed over ranks together
+  // with the next iteration's red[] (or right away when the relative residual is in use)
+  st->upd[0] = st->upd_next[0];
+  st->upd[1] = st->upd_next[1];
   st->rsq = rsq_new;
-  st->cur ^= 1;
   st->iter += 1;
   st->size_r = rsq_new / st->source_norm;
-  if (use_rel) st->size_relr = sqrt(st->relsum / st->half_volume);
+  if (use_rel) st->size_relr = sqrt(st->upd_next[1] / st->half_volume);
   const bool hit_r = (st->rsqmin <= 0 || st->rsqmin > st->size_r);
   const bool hit_rel = (st->relrsqmin <= 0 || st->relrsqmin > st->size_relr);
   if ((st->iter % st->niter == 0) || (hit_r && hit_rel)) st->stop = 1;

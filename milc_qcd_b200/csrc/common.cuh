@@ -30,13 +30,15 @@ struct Geom {
   int L[4];        // local extents
   int Lxh;         // L[0]/2
   int Vh;          // local sites per parity
-  int stride;      // spinor field stride in sites (Vh + ghost sites, padded)
+  int stride;      // colour-vector field stride in sites (Vh padded)
+  int gstride;     // ghost-buffer stride in sites (all ghost sites of one half, padded)
   int lstride;     // link field stride in sites (Vh + backward ghost sites, padded)
   int part[4];
   int faceh[4];    // sites per parity in one slice orthogonal to d
-  int ghost[4][2]; // first ghost site of (d, 0=behind | 1=ahead) in a spinor half
-  int lghost[4];   // first backward-ghost site of d in a link half
-  int origin_parity;  // parity of the local origin in the global lattice
+  int ghost[4][2]; // Vh + first ghost-buffer site of (d, 0=behind | 1=ahead)
+  int lghost[4];   // first backward-ghost site of d in a link half (tail of the link field)
+  int origin[4];   // global coordinates of the local origin (even in every direction)
+  int G[4];        // global extents
 };
 
 struct Coord { int x, y, z, t, xh; };

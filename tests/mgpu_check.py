@@ -1,0 +1,148 @@
+"""Multi-GPU parity program, launched by tests/test_multigpu.py (or by hand) as
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P tests/mgpu_check.py [--dims 8 8 12 16]
+
+One rank per GPU.  The global synthetic lattice is generated on every rank (small sizes), each
+rank hands its LOCAL sub-lattice (MILC per-node order) to a distributed context, and the
+gathered results are checked on rank 0 against the CPU oracle on the GLOBAL lattice: dslash to
+1e-13, CG / multi-shift CG iteration counts and solutions as in the single-GPU parity tests.
+Also checks that the device-side synthetic generator is independent of the decomposition.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+EVEN, ODD, EVENANDODD = 2, 1, 3
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from milc_qcd_b200 import api, dist as D, fields as F
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dims", type=int, nargs=4, default=[8, 8, 12, 24])
+    ap.add_argument("--grid", type=int, nargs=4, default=None)
+    args = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("gloo")
+    dims = tuple(args.dims)
+    grid = tuple(args.grid) if args.grid else D.rank_grid(world)
+
+    ids = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx = api.Context(dims, device=local_rank, grid=grid, rank=rank, nranks=world, nccl_id=ids[0])
+
+    fat, lng = F.make_links(dims, seed=1234)
+    src = F.make_source(dims, seed=1235, parity=EVENANDODD)
+    lfat, llng = D.scatter_field(fat, dims, grid, rank), D.scatter_field(lng, dims, grid, rank)
+    lsrc = D.scatter_field(src, dims, grid, rank)
+    ctx.load_links(lfat, llng)
+
+    def gather(local):
+        parts = [None] * world
+        dist.all_gather_object(parts, local)
+        return D.gather_field(parts, dims, grid)
+
+    ok = True
+    report = []
+
+    def check(name, cond, detail=""):
+        nonlocal ok
+        ok = ok and bool(cond)
+        report.append("%s %s %s" % ("PASS" if cond else "FAIL", name, detail))
+
+    if rank == 0:
+        from oracle.pyoracle import Oracle
+        o = Oracle()
+
+    # --- dslash, all parities
+    for par in (EVEN, ODD, EVENANDODD):
+        ldst = np.zeros_like(lsrc)
+        ctx.dslash(lsrc, ldst, par)
+        got = gather(ldst)
+        if rank == 0:
+            want = o.dslash(dims, fat, lng, src, par)
+            V = src.shape[0]
+            sl = slice(0, V // 2) if par == EVEN else slice(V // 2, V) if par == ODD else slice(0, V)
+            err = np.abs(got[sl] - want[sl]).max() / np.abs(want[sl]).max()
+            check("dslash parity %d" % par, err <= 1e-13, "rel err %.2e" % err)
+
+    # --- single-mass CG
+    mass, resid = 0.05, 1e-9
+    b = F.make_source(dims, seed=5678, parity=EVEN)
+    lb = D.scatter_field(b, dims, grid, rank)
+    lx = np.zeros_like(lb)
+    it, res = ctx.congrad(lb, lx, mass, EVEN, 500, 5, resid)
+    x = gather(lx)
+    if rank == 0:
+        xo = np.zeros_like(b)
+        ito, qo = o.congrad(dims, fat, lng, b, xo, mass, EVEN, 500, 5, resid)
+        check("cg iterations", abs(it - ito) <= max(2, 0.02 * ito), "%d vs oracle %d" % (it, ito))
+        check("cg converged", res["converged"] == 1 and res["final_rsq"] < resid ** 2, "final_rsq %.2e" % res["final_rsq"])
+        e = np.linalg.norm(x - xo) / np.linalg.norm(xo)
+        check("cg solution", e <= 10 * resid / (4 * mass * mass), "rel diff %.2e" % e)
+    # with the Fermilab relative residual switched on (extra all-reduce path)
+    lx2 = np.zeros_like(lb)
+    it2, res2 = ctx.congrad(lb, lx2, mass, EVEN, 500, 5, resid, relresid=1e-3)
+    x2 = gather(lx2)
+    if rank == 0:
+        xo2 = np.zeros_like(b)
+        ito2, qo2 = o.congrad(dims, fat, lng, b, xo2, mass, EVEN, 500, 5, resid, relresid=1e-3)
+        check("cg relresid iterations", abs(it2 - ito2) <= max(2, 0.02 * ito2), "%d vs oracle %d" % (it2, ito2))
+        check("cg relresid value", abs(res2["final_relrsq"] - qo2["final_relrsq"]) <= 1e-6 * qo2["final_relrsq"] + 1e-12,
+              "%.6e vs %.6e" % (res2["final_relrsq"], qo2["final_relrsq"]))
+
+    # --- multi-shift CG
+    offsets = np.roll(F.rhmc_offsets(7, mass), 3)
+    lps = [np.zeros_like(lb) for _ in offsets]
+    itm, resm = ctx.multicg(lb, lps, offsets, EVEN, 3000, 1, 1e-8)
+    ps = [gather(p) for p in lps]
+    if rank == 0:
+        itmo, pso, qmo = o.multicg(dims, fat, lng, b, offsets, EVEN, 3000, 1, 1e-8)
+        check("multicg iterations", abs(itm - itmo) <= max(2, 0.02 * itmo), "%d vs oracle %d" % (itm, itmo))
+        V = b.shape[0]
+        e = max(np.linalg.norm(ps[j][:V // 2] - pso[j][:V // 2]) / np.linalg.norm(pso[j][:V // 2]) for j in range(len(offsets)))
+        check("multicg solutions", e <= 1e-6, "max rel diff %.2e" % e)
+
+    # --- device generator is decomposition independent and produces the documented structure
+    ctx.links_synthetic(4242)
+    sf, sl_ = ctx.links_download()
+    gf, gl = gather(sf), gather(sl_)
+    v = ctx.vec_create()
+    w = ctx.vec_create()
+    ctx.vec_gaussian(v, EVENANDODD, 99)
+    ctx.dslash_dev(v, w, EVENANDODD)
+    lv, lw = np.zeros_like(lsrc), np.zeros_like(lsrc)
+    ctx.vec_download(v, lv)
+    ctx.vec_download(w, lw)
+    gv, gw = gather(lv), gather(lw)
+    if rank == 0:
+        want = o.dslash(dims, gf, gl, gv, EVENANDODD)
+        err = np.abs(gw - want).max() / np.abs(want).max()
+        check("dslash on device-generated links (ghost links generated in place)", err <= 1e-13, "rel err %.2e" % err)
+        lc = gl[..., 0] + 1j * gl[..., 1]
+        uu = lc @ np.conj(np.swapaxes(lc, -1, -2)) * 24.0 ** 2
+        check("synthetic long links are c3 * U(3)", np.abs(uu - np.eye(3)).max() < 1e-12)
+        np.save(os.path.join(ROOT, "gpurun_out", "synth_links_fat_n%d.npy" % world), gf[:64])
+        ref = os.path.join(ROOT, "gpurun_out", "synth_links_fat_n1.npy")
+        if world > 1 and os.path.exists(ref):
+            check("synthetic links independent of decomposition", np.array_equal(np.load(ref), gf[:64]))
+        print("\n".join(report))
+        print("MGPU-OK" if ok else "MGPU-FAIL", "ranks", world, "grid", grid, "dims", dims)
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
