@@ -198,56 +198,77 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
-    from milc_qcd_b200 import api
+    from milc_qcd_b200 import api, dist as D
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local_rank = env_int("LOCAL_RANK", 0)
     if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run" % args.gpus)
+        raise SystemExit("bench.py --gpus %d must be launched with %d ranks (torch.distributed.run), got WORLD_SIZE=%d"
+                         % (args.gpus, args.gpus, world))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
-    if world > 1:
-        raise SystemExit("bench.py: multi-GPU solve not implemented yet in this revision")
     torch.cuda.set_device(local_rank)
-    dims = DIMS
+    multi = world > 1
+    if multi:
+        import torch.distributed as dist
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local_rank))
+    # N = 1: BASELINE configs[1] (32^3x64).  N > 1: configs[3], strong scaling of 64^3x96.
+    dims = tuple(args.lattice) if args.lattice else (DIMS if not multi else (64, 64, 64, 96))
     V = int(np.prod(dims))
-    Vh = V // 2
+    grid = D.rank_grid(world)
+    if multi:
+        ids = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx = api.Context(dims, device=local_rank, grid=grid, rank=rank, nranks=world, nccl_id=ids[0])
+    else:
+        ctx = api.Context(dims, device=local_rank)
+    Vl = ctx.volume
+    Vlh = Vl // 2
 
+    # synthetic inputs are generated on the device from global coordinates (identical for every
+    # decomposition); the host copies used by the e2e leg and the CPU baseline are read back
     t_gen = time.perf_counter()
-    fat, lng, src = make_workload(dims)
+    ctx.links_synthetic(1234)
+    vb, vx = ctx.vec_create(), ctx.vec_create()
+    ctx.vec_gaussian(vb, EVEN, 5678)
+    torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
-    ctx = api.Context(dims, device=local_rank)
-    t_up = time.perf_counter()
-    ctx.load_links(fat, lng)
-    t_up = time.perf_counter() - t_up
     stream = torch.cuda.ExternalStream(ctx.lib.b200ks_stream(ctx.h))
 
-    # resident vectors
-    vb, vx = ctx.vec_create(), ctx.vec_create()
-    ctx.vec_upload(vb, src, EVEN)
+    def barrier():
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not multi:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def solve_resident():
         ctx.vec_zero(vx, EVEN)
         return ctx.congrad_dev(vb, vx, MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=args.mixed)
 
-    # pinned host buffers for the end-to-end leg
-    pin_b = torch.from_numpy(src).pin_memory()
-    pin_x = torch.zeros_like(pin_b).pin_memory()
+    # pinned host buffers (local sub-lattice, MILC order) for the end-to-end leg
+    pin_b = torch.zeros((Vl, 3, 2), dtype=torch.float64).pin_memory()
+    pin_x = torch.zeros((Vl, 3, 2), dtype=torch.float64).pin_memory()
     hb, hx = pin_b.numpy(), pin_x.numpy()
+    ctx.vec_download(vb, hb, EVEN)
 
     def solve_host():
-        hx[:Vh] = 0
+        hx[:Vlh] = 0
         return ctx.congrad(hb, hx, MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=args.mixed)
 
     for _ in range(args.warmup):
         it, res = solve_resident()
-    torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     e0.record(stream)
     iters_total, dev_s = 0, 0.0
     for _ in range(args.steps):
@@ -255,19 +276,22 @@ def run_b200(args):
         iters_total += it
         dev_s += res["device_seconds"]
     e1.record(stream)
-    torch.cuda.synchronize()
-    ms_total = e0.elapsed_time(e1)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count() - l0
 
-    # dominant-kernel roofline, live
+    # dominant-kernel roofline, live: back-to-back dslash launches (halo exchange included for N > 1)
     n_ds = 100
-    ds_ms = {p: ctx.dslash_time(p, EVEN, n_ds) for p in (2, 1)}
+    ds_ms = {}
+    for p in (2, 1):
+        barrier()
+        ds_ms[p] = max_over_ranks(ctx.dslash_time(p, EVEN, n_ds))
     clocks = sampler.stop()
 
-    # end-to-end leg (host buffers)
+    # end-to-end leg (host buffers through the ks_congrad_parity_gpu-style call)
     solve_host()
-    torch.cuda.synchronize()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e2.record(stream)
     t_w = time.perf_counter()
     it_e2e = 0
@@ -275,61 +299,79 @@ def run_b200(args):
         it, res_h = solve_host()
         it_e2e += it
     e3.record(stream)
-    torch.cuda.synchronize()
+    barrier()
     t_w = time.perf_counter() - t_w
-    ms_e2e = max(e2.elapsed_time(e3), 1e3 * t_w)
+    ms_e2e = max_over_ranks(max(e2.elapsed_time(e3), 1e3 * t_w))
 
-    # independent true-residual check of the last host solution (device operator)
+    # independent true-residual check of the last host solution (device operator, global norms)
     vt, vr = ctx.vec_create(), ctx.vec_create()
     ctx.vec_upload(vr, hx, EVEN)
     ctx.dslash_dev(vr, vt, ODD)
     ctx.dslash_dev(vt, vt, EVEN)
-    tt = np.zeros_like(src)
+    tt = np.zeros((Vl, 3, 2))
     ctx.vec_download(vt, tt, EVEN)
-    r = src[:Vh] - (4 * MASS * MASS * hx[:Vh] - tt[:Vh])
-    true_resid = float(np.linalg.norm(r) / np.linalg.norm(src[:Vh]))
+    r = hb[:Vlh] - (4 * MASS * MASS * hx[:Vlh] - tt[:Vlh])
+    rr, bb = float(np.sum(r * r)), float(np.sum(hb[:Vlh] ** 2))
+    if multi:
+        t2 = torch.tensor([rr, bb], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t2)
+        rr, bb = float(t2[0]), float(t2[1])
+    true_resid = (rr / bb) ** 0.5
 
     value = CG_FLOP_PER_SITE * V * iters_total / (ms_total * 1e-3) / 1e9
     e2e_value = CG_FLOP_PER_SITE * V * it_e2e / (ms_e2e * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    ach = DSLASH_BYTES_PER_SITE[2] * Vh / (ds_ms[2] * 1e-3) / 1e9
-    half_bytes = Vh * 6 * 8
+    ach = DSLASH_BYTES_PER_SITE[2] * Vlh / (ds_ms[2] * 1e-3) / 1e9   # per GPU
+    half_bytes = Vlh * 6 * 8
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not multi and rank == 0:
         try:
-            times, meta = cpu_reference_sample(dims, fat, lng, src, 10, repeats=2)
+            fat, lng = ctx.links_download()
+            times, meta = cpu_reference_sample(dims, fat, lng, hb, 10, repeats=2)
             t, itc = times[-1]
             cpu = {"value": CG_FLOP_PER_SITE * V * itc / t / 1e9, "unit": "GFLOP/s", "cores": meta["cores"],
                    "kind": meta["kind"],
-                   "sample": "CG capped at 10 iterations (%d counted) on the full 32^3x64 workload, %s" % (itc, meta["impl"])}
+                   "sample": "CG capped at 10 iterations (%d counted) on the full %s workload, same links and source, %s"
+                             % (itc, "x".join(map(str, dims)), meta["impl"])}
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
             cpu = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
 
-    line = {
-        "metric": "hisq_cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64" if args.mixed == 0 else "f64 outer / f32 inner", "data": "synthetic",
-        "config": {"workload": "HISQ single-mass CG, mass 0.05, resid 1e-10, synthetic random-SU(3) 32^3x64 (BASELINE configs[1])",
-                   "lattice": list(dims), "l2": "links (2.4 GB) exceed L2 every dslash; no flush needed",
-                   "flop_convention": "MILC 1187 flop/site/iteration", "mixed_precision": args.mixed},
-        "cg_iters_per_solve": iters_total / args.steps, "cg_time_to_solution_s": ms_total * 1e-3 / args.steps,
-        "cg_device_seconds": dev_s / args.steps, "true_residual": true_resid, "converged": res["converged"],
-        "dslash_gflops": {"f64": DSLASH_FLOP_PER_SITE * Vh / (ds_ms[2] * 1e-3) / 1e9,
-                          "f32": DSLASH_FLOP_PER_SITE * Vh / (ds_ms[1] * 1e-3) / 1e9},
-        "dslash_ms": {"f64": ds_ms[2], "f32": ds_ms[1]},
-        "roofline": {"bound": "hbm", "kernel": "dslash_kernel<double> (recon 18/18)", "achieved": ach, "peak": peak,
-                     "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": ncu_traffic(),
-                     "algorithmic_bytes_per_launch": DSLASH_BYTES_PER_SITE[2] * Vh,
-                     "f32_achieved": DSLASH_BYTES_PER_SITE[1] * Vh / (ds_ms[1] * 1e-3) / 1e9},
-        "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": 2 * half_bytes,
-                "d2h_bytes_per_step": half_bytes, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clocks,
-        "setup": {"gen_links_s": t_gen, "load_links_s": t_up, "device_bytes": ctx.device_bytes()},
-    }
-    print(json.dumps(line))
+    if rank == 0:
+        lat = "x".join(map(str, dims))
+        line = {
+            "metric": "hisq_cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64" if args.mixed == 0 else "f64 outer / f32 inner", "data": "synthetic",
+            "config": {"workload": "HISQ single-mass CG, mass 0.05, resid 1e-10, synthetic random-SU(3) %s (%s)"
+                                   % (lat, "BASELINE configs[1]" if dims == DIMS else "BASELINE configs[3], strong scaling"
+                                      if dims == (64, 64, 64, 96) else "custom lattice"),
+                       "lattice": list(dims), "rank_grid": list(grid), "local_lattice": list(ctx.dims),
+                       "l2": "links (%.1f GB per GPU) exceed L2 every dslash; no flush needed" % (2 * 144 * 4 * Vl / 1e9),
+                       "flop_convention": "MILC 1187 flop/site/iteration", "mixed_precision": args.mixed,
+                       "halo": "depth-3 ghosts, NCCL send/recv overlapped with the interior pass" if multi else "none"},
+            "cg_iters_per_solve": iters_total / args.steps, "cg_time_to_solution_s": ms_total * 1e-3 / args.steps,
+            "cg_device_seconds": dev_s / args.steps, "true_residual": true_resid, "converged": res["converged"],
+            "dslash_gflops": {"f64": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[2] * 1e-3) / 1e9,
+                              "f32": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[1] * 1e-3) / 1e9},
+            "dslash_ms": {"f64": ds_ms[2], "f32": ds_ms[1]},
+            "roofline": {"bound": "hbm", "kernel": "dslash_kernel<double> (recon 18/18)", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                         "traffic": ncu_traffic() if dims == DIMS else None,
+                         "algorithmic_bytes_per_launch": DSLASH_BYTES_PER_SITE[2] * Vlh,
+                         "note": "per GPU; for N > 1 the launch time includes the halo exchange and the exterior pass",
+                         "f32_achieved": DSLASH_BYTES_PER_SITE[1] * Vlh / (ds_ms[1] * 1e-3) / 1e9},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": 2 * half_bytes * world,
+                    "d2h_bytes_per_step": half_bytes * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks,
+            "setup": {"gen_fields_s": t_gen, "device_bytes": ctx.device_bytes()},
+        }
+        print(json.dumps(line))
     ctx.close()
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
@@ -341,6 +383,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mixed", type=int, default=0, help="0 pure double, 1 double/single, 2 double/half")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lattice", type=int, nargs=4, default=None, help="override the lattice (nx ny nz nt)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
