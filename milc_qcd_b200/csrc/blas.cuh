@@ -195,6 +195,56 @@ __global__ void cg_scalar_kernel(CgState *st, int use_rel, int single) {
   }
 }
 
+// ---- mixed precision: double outer solution, single inner Krylov vectors -----------------------
+// x(double) += x_lo(float) ; x_lo = 0      (before every true-residual evaluation)
+__global__ void __launch_bounds__(kBlock)
+mixed_accumulate_kernel(double2 *x, float2 *x_lo, int stride, int n) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const size_t o = (size_t)c * stride + i;
+    double2 xv = x[o];
+    const float2 lv = x_lo[o];
+    xv.x += (double)lv.x;
+    xv.y += (double)lv.y;
+    x[o] = xv;
+    x_lo[o] = make_float2(0.f, 0.f);
+  }
+}
+
+// Reliable update: ttt holds D D x - 4m^2 x in double.  r_true = b + ttt replaces the
+// single-precision recursive residual; the search direction keeps its Krylov history and is
+// only shifted by the residual correction (p = r + b p_old with the corrected r).
+// first != 0: start of the solve, p = r.
+__global__ void __launch_bounds__(kBlock)
+mixed_reliable_kernel(const double2 *b, const double2 *ttt, float2 *r_lo, float2 *p_lo, int stride, int n,
+                      int first, ReduceWs ws, double *out) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  double s[2] = {0, 0};
+  if (i < n) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const size_t o = (size_t)c * stride + i;
+      const double2 bv = b[o], tv = ttt[o];
+      const double rx = bv.x + tv.x, ry = bv.y + tv.y;
+      const float2 ro = r_lo[o];
+      const float2 rn = make_float2((float)rx, (float)ry);
+      r_lo[o] = rn;
+      if (first) {
+        p_lo[o] = rn;
+      } else {
+        float2 pv = p_lo[o];
+        pv.x += rn.x - ro.x;
+        pv.y += rn.y - ro.y;
+        p_lo[o] = pv;
+      }
+      s[0] += rx * rx + ry * ry;
+    }
+  }
+  grid_reduce<2>(s, ws, out);
+}
+
 // ---- multi-shift CG --------------------------------------------------------------------------
 // r += beta_low * ttt ; rsq_new = |r|^2          ks_multicg_offset.c:365-368
 template <typename T>

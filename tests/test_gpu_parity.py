@@ -122,6 +122,31 @@ def test_congrad_matches_oracle(api, oracle, dims, parity):
     assert np.all(x[mask] == 0)
 
 
+@pytest.mark.parametrize("dims,parity", [((8, 8, 8, 8), EVEN), ((8, 12, 6, 10), ODD)])
+def test_mixed_precision_congrad_reaches_double_residual(api, oracle, dims, parity):
+    """double outer / single inner with reliable updates: same answer, true residual in double."""
+    from milc_qcd_b200 import fields as F
+    fat, lng, _ = fields_for(dims)
+    src = F.make_source(dims, seed=5678, parity=parity)
+    mass, resid = 0.05, 1e-10
+    x_ref = np.zeros_like(src)
+    it_ref, q_ref = oracle.congrad(dims, fat, lng, src, x_ref, mass, parity, 500, 5, resid)
+    fn = api.fn_links_t(fat=fat, lng=lng, dims=dims)
+    qic = api.quark_invert_control(max=500, nrestart=5, parity=parity, resid=resid, mixed_precision=1)
+    x = np.zeros_like(src)
+    it = api.ks_congrad_parity_gpu(src, x, qic, mass, fn)
+    assert qic.converged == 1 and qic.final_rsq < resid ** 2
+    assert it <= 1.25 * it_ref + 10          # reliable updates cost a few extra iterations, not a restart
+    V = src.shape[0]
+    sl = slice(0, V // 2) if parity == EVEN else slice(V // 2, V)
+    op = EVEN if parity == ODD else ODD
+    t = oracle.dslash(dims, fat, lng, x, op)
+    t = oracle.dslash(dims, fat, lng, t, parity)
+    r = src[sl] - (4 * mass * mass * x[sl] - t[sl])
+    assert np.linalg.norm(r) / np.linalg.norm(src[sl]) <= 10 * resid
+    assert np.linalg.norm(x - x_ref) <= 10 * resid * np.linalg.norm(x_ref) * _cond(mass)
+
+
 def _cond(mass):
     # |dx| <= |A^-1| |dr|: the solution error bound carries 1/(4 m^2) relative to the residual bound
     return 1.0 / (4 * mass * mass)
