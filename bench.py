@@ -43,7 +43,9 @@ RESID = 1e-10
 NITER, NRESTART = 2000, 10
 CG_FLOP_PER_SITE = 1187.0      # d_congrad5_fn_milc.c:81-83
 DSLASH_FLOP_PER_SITE = 1146.0  # 16 x 66 + 15 x 6
-DSLASH_BYTES_PER_SITE = {2: 2400.0, 1: 1200.0}  # w*(8*18 + 8*18 + 6 + 6)
+# algorithmic bytes per output site = w*(8*R_fat + 8*R_long + 6 + 6), w = bytes/real
+def dslash_bytes_per_site(prec, long_reals):
+    return (8.0 if prec == 2 else 4.0) * (8 * 18 + 8 * long_reals + 12)
 
 
 def env_int(name, default):
@@ -114,12 +116,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per dslash launch from the committed ncu --set full summary, if any."""
+def ncu_traffic(prec, long_reals):
+    """dram bytes per dslash launch from the committed ncu --set full summaries, if any."""
     p = os.path.join(ROOT, "profiles", "dslash_ncu_summary.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["dram_bytes_per_launch"])
+            for row in json.load(open(p))["kernels"]:
+                if row["prec"] == prec and row["long_reals"] == long_reals:
+                    return float(row["dram_bytes_per_launch"])
         except Exception:
             return None
     return None
@@ -227,7 +231,8 @@ def run_b200(args):
     # synthetic inputs are generated on the device from global coordinates (identical for every
     # decomposition); the host copies used by the e2e leg and the CPU baseline are read back
     t_gen = time.perf_counter()
-    ctx.links_synthetic(1234)
+    ctx.links_synthetic(1234, args.long_recon)
+    long_reals = 2 * ctx.long_link_info()[0]
     vb, vx = ctx.vec_create(), ctx.vec_create()
     ctx.vec_gaussian(vb, EVEN, 5678)
     torch.cuda.synchronize()
@@ -247,9 +252,9 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def solve_resident():
+    def solve_resident(mixed=args.mixed):
         ctx.vec_zero(vx, EVEN)
-        return ctx.congrad_dev(vb, vx, MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=args.mixed)
+        return ctx.congrad_dev(vb, vx, MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=mixed)
 
     # pinned host buffers (local sub-lattice, MILC order) for the end-to-end leg
     pin_b = torch.zeros((Vl, 3, 2), dtype=torch.float64).pin_memory()
@@ -280,6 +285,17 @@ def run_b200(args):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count() - l0
 
+    # the other precision mode of the same solve, for the record (not the headline)
+    other = 0 if args.mixed else 1
+    solve_resident(other)
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record(stream)
+    it_o, res_o = solve_resident(other)
+    e5.record(stream)
+    barrier()
+    ms_other = max_over_ranks(e4.elapsed_time(e5))
+
     # dominant-kernel roofline, live: back-to-back dslash launches (halo exchange included for N > 1)
     n_ds = 100
     ds_ms = {}
@@ -302,6 +318,13 @@ def run_b200(args):
     barrier()
     t_w = time.perf_counter() - t_w
     ms_e2e = max_over_ranks(max(e2.elapsed_time(e3), 1e3 * t_w))
+    # where the end-to-end time goes: the same three phases issued as separate calls (diagnostic)
+    vu = ctx.vec_create()
+    t0 = time.perf_counter(); ctx.vec_upload(vu, hb, EVEN); ctx.vec_upload(vu, hx, EVEN); t_up = time.perf_counter() - t0
+    t0 = time.perf_counter(); ctx.vec_download(vu, hx, EVEN); t_dn = time.perf_counter() - t0
+    t0 = time.perf_counter(); hx[:Vlh] = 0; t_zero = time.perf_counter() - t0
+    ctx.vec_free(vu)
+    solve_host()
 
     # independent true-residual check of the last host solution (device operator, global norms)
     vt, vr = ctx.vec_create(), ctx.vec_create()
@@ -321,7 +344,9 @@ def run_b200(args):
     value = CG_FLOP_PER_SITE * V * iters_total / (ms_total * 1e-3) / 1e9
     e2e_value = CG_FLOP_PER_SITE * V * it_e2e / (ms_e2e * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    ach = DSLASH_BYTES_PER_SITE[2] * Vlh / (ds_ms[2] * 1e-3) / 1e9   # per GPU
+    kp = 1 if args.mixed else 2   # precision of the dslash that dominates the timed solve
+    bps = {p: dslash_bytes_per_site(p, long_reals) for p in (1, 2)}
+    ach = {p: bps[p] * Vlh / (ds_ms[p] * 1e-3) / 1e9 for p in (1, 2)}   # per GPU
     half_bytes = Vlh * 6 * 8
 
     cpu = None
@@ -342,12 +367,14 @@ def run_b200(args):
         line = {
             "metric": "hisq_cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64" if args.mixed == 0 else "f64 outer / f32 inner", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64" if args.mixed == 0 else "f64 (solution, true residuals) / f32 (inner Krylov vectors)",
+            "data": "synthetic",
             "config": {"workload": "HISQ single-mass CG, mass 0.05, resid 1e-10, synthetic random-SU(3) %s (%s)"
                                    % (lat, "BASELINE configs[1]" if dims == DIMS else "BASELINE configs[3], strong scaling"
                                       if dims == (64, 64, 64, 96) else "custom lattice"),
                        "lattice": list(dims), "rank_grid": list(grid), "local_lattice": list(ctx.dims),
-                       "l2": "links (%.1f GB per GPU) exceed L2 every dslash; no flush needed" % (2 * 144 * 4 * Vl / 1e9),
+                       "l2": "links streamed by every dslash (%.2f GB per GPU at the inner precision) exceed the 126 MB L2; no flush needed"
+                             % ((4 if args.mixed else 8) * (18 + long_reals) * 4 * Vl / 1e9),
                        "flop_convention": "MILC 1187 flop/site/iteration", "mixed_precision": args.mixed,
                        "halo": "depth-3 ghosts, NCCL send/recv overlapped with the interior pass" if multi else "none"},
             "cg_iters_per_solve": iters_total / args.steps, "cg_time_to_solution_s": ms_total * 1e-3 / args.steps,
@@ -355,15 +382,22 @@ def run_b200(args):
             "dslash_gflops": {"f64": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[2] * 1e-3) / 1e9,
                               "f32": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[1] * 1e-3) / 1e9},
             "dslash_ms": {"f64": ds_ms[2], "f32": ds_ms[1]},
-            "roofline": {"bound": "hbm", "kernel": "dslash_kernel<double> (recon 18/18)", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-                         "traffic": ncu_traffic() if dims == DIMS else None,
-                         "algorithmic_bytes_per_launch": DSLASH_BYTES_PER_SITE[2] * Vlh,
+            "roofline": {"bound": "hbm", "kernel": "dslash_kernel<%s> (fat 18 / long %d reals per link)"
+                                                   % ("float" if kp == 1 else "double", long_reals),
+                         "achieved": ach[kp], "peak": peak,
+                         "unit": "GB/s", "frac": ach[kp] / peak, "peak_source": peak_src,
+                         "traffic": ncu_traffic(kp, long_reals) if dims == DIMS else None,
+                         "algorithmic_bytes_per_launch": bps[kp] * Vlh, "algorithmic_bytes_per_site": bps[kp],
                          "note": "per GPU; for N > 1 the launch time includes the halo exchange and the exterior pass",
-                         "f32_achieved": DSLASH_BYTES_PER_SITE[1] * Vlh / (ds_ms[1] * 1e-3) / 1e9},
+                         "f64": {"achieved": ach[2], "frac": ach[2] / peak, "bytes_per_site": bps[2]},
+                         "f32": {"achieved": ach[1], "frac": ach[1] / peak, "bytes_per_site": bps[1]}},
+            "other_precision_mode": {"mixed_precision": other, "value": CG_FLOP_PER_SITE * V * it_o / (ms_other * 1e-3) / 1e9,
+                                     "unit": "GFLOP/s", "cg_iters": it_o, "cg_time_to_solution_s": ms_other * 1e-3,
+                                     "final_rsq": res_o["final_rsq"]},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": 2 * half_bytes * world,
-                    "d2h_bytes_per_step": half_bytes * world, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": half_bytes * world, "ms_per_step": ms_e2e / args.steps,
+                    "phases_ms": {"h2d_src_and_guess": 1e3 * t_up, "d2h_solution": 1e3 * t_dn, "host_zero_guess": 1e3 * t_zero}},
             "gpu_launches": launches, "clocks": clocks,
             "setup": {"gen_fields_s": t_gen, "device_bytes": ctx.device_bytes()},
         }
@@ -381,7 +415,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mixed", type=int, default=0, help="0 pure double, 1 double/single, 2 double/half")
+    ap.add_argument("--mixed", type=int, default=1,
+                    help="0 pure double; 1 (default, BASELINE configs[1] 'mixed-precision CG') double solution and "
+                         "true residuals with single-precision Krylov vectors and reliable updates")
+    ap.add_argument("--long-recon", type=int, default=0, help="long-link storage: 18, 14 or 0 = decided on the data")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lattice", type=int, nargs=4, default=None, help="override the lattice (nx ny nz nt)")
     args = ap.parse_args()

@@ -103,9 +103,22 @@ void b200ks_destroy(b200ks_ctx *ctx);
 
 /* Upload fat and long links (MILC order, su3_matrix[4*V]) and re-lay them out on the
  * device.  Replaces the implicit link refresh of the QUDA seam
- * (generic_ks/d_congrad5_fn_gpu.c:121-126).  long_recon = 18 or 13. */
+ * (generic_ks/d_congrad5_fn_gpu.c:121-126).
+ * long_recon selects the device storage of the long (Naik) links:
+ *   18  full matrices;
+ *   14  two rows + one complex factor f with row3 = f*conj(row1 x row2) -- exact for links
+ *       that are (real scalar) x U(3), which HISQ/asqtad long links are
+ *       (generic_ks/fermion_links_hisq_load_milc.c builds them as c_naik * W W W from the
+ *       unitarised W links).  Every link is tested on load; a misfit above 1e-13 (double
+ *       hosts) is an error;
+ *    0  automatic: 14 when every link passes that test, else 18.
+ * (Thirteen reals -- QUDA's reconstruct-13 -- would need a sincos per link and breaks the
+ * 16-byte word the kernels load; 14 keeps 89 % of its traffic saving.) */
 int b200ks_load_links(b200ks_ctx *ctx, const void *fat, const void *lng, int host_prec,
                       int long_recon);
+/* Storage chosen for the long links (7 or 9 complex per link) and the worst misfit measured
+ * by the load-time test (-1 when long_recon == 18 skipped it). */
+int b200ks_long_link_info(b200ks_ctx *ctx, int *ncomplex_per_link, double *misfit);
 
 /* dest(parity sites) = D src.  Only `parity` sites of dest are written; src == dest is
  * legal for EVEN/ODD.  Replaces dslash_fn_field (generic_ks/dslash_fn.c:306-356,

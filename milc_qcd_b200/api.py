@@ -115,7 +115,13 @@ class Context:
             pass
 
     # -- links -----------------------------------------------------------------------------
-    def load_links(self, fat, lng, long_recon=18):
+    def long_link_info(self):
+        """(complex numbers stored per long link: 9 or 7, worst load-time misfit)."""
+        nc, dev = C.c_int(), C.c_double()
+        check(self.lib.b200ks_long_link_info(self.h, C.byref(nc), C.byref(dev)), "b200ks_long_link_info")
+        return nc.value, dev.value
+
+    def load_links(self, fat, lng, long_recon=0):
         if fat.dtype != lng.dtype:
             raise TypeError("fat and lng must have the same precision")
         n = self.volume * 4 * 18
@@ -202,7 +208,7 @@ class Context:
     def vec_gaussian(self, v, parity, seed):
         check(self.lib.b200ks_vec_gaussian(self.h, v, parity, seed), "b200ks_vec_gaussian")
 
-    def links_synthetic(self, seed, long_recon=18):
+    def links_synthetic(self, seed, long_recon=0):
         check(self.lib.b200ks_links_synthetic(self.h, seed, long_recon), "b200ks_links_synthetic")
 
     def links_download(self, dtype=np.float64):

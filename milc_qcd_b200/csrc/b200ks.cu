@@ -49,6 +49,7 @@ struct Links {           // fat + long links of one precision, both parities
   void *fat[2] = {nullptr, nullptr};
   void *lng[2] = {nullptr, nullptr};
   bool valid = false;
+  int lng_nc = 9;        // complex numbers stored per long link: 9 full, 7 = two rows + U(3) factor
 };
 
 struct b200ks_ctx {
@@ -69,6 +70,10 @@ struct b200ks_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long launches = 0;
   size_t bytes = 0;
+  void *stage = nullptr;        // persistent host<->device re-layout staging buffer
+  size_t stage_bytes = 0;
+  double long_dev = -1;         // worst misfit of the long links against (scalar x U(3)), -1 = not measured
+  unsigned long long *d_dev = nullptr;
   Comm comm;             // one-rank-per-GPU decomposition (nranks == 1: unused)
 };
 
@@ -90,7 +95,19 @@ static void dev_free(b200ks_ctx *c, void *p, size_t bytes) {
 }
 
 static size_t vec_bytes(const b200ks_ctx *c, int prec) { return (size_t)3 * c->g.stride * 2 * real_size(prec); }
-static size_t link_bytes(const b200ks_ctx *c, int prec) { return (size_t)36 * c->g.lstride * 2 * real_size(prec); }
+static size_t link_bytes(const b200ks_ctx *c, int prec, int nc = 9) { return (size_t)4 * nc * c->g.lstride * 2 * real_size(prec); }
+
+// staging buffer for host<->device re-layout, grown on demand and kept (a cudaMalloc/cudaFree
+// pair per transfer costs more than the transfer at small volumes)
+static int stage_get(b200ks_ctx *c, size_t bytes, void **out) {
+  if (c->stage_bytes < bytes) {
+    if (c->stage) { cudaStreamSynchronize(c->stream); dev_free(c, c->stage, c->stage_bytes); c->stage = nullptr; c->stage_bytes = 0; }
+    CHK(dev_alloc(c, &c->stage, bytes));
+    c->stage_bytes = bytes;
+  }
+  *out = c->stage;
+  return 0;
+}
 
 static int vec_new(b200ks_ctx *c, int prec, DevVec **out) {
   DevVec *v = new DevVec;
@@ -233,6 +250,8 @@ extern "C" void b200ks_destroy(b200ks_ctx *c) {
   if (c->comm.ev_ready) cudaEventDestroy(c->comm.ev_ready);
   if (c->comm.ev_done) cudaEventDestroy(c->comm.ev_done);
   if (c->comm.stream) cudaStreamDestroy(c->comm.stream);
+  cudaFree(c->stage);
+  cudaFree(c->d_dev);
   cudaFree(c->ws.partials);
   cudaFree(c->ws.counter);
   cudaFree(c->d_state);
@@ -268,18 +287,24 @@ static int check_launch(const char *what) {
 
 // ---------------------------------------------------------------------------------------------
 // links
-static int links_alloc(b200ks_ctx *c, int prec) {
+static int links_alloc(b200ks_ctx *c, int prec, int nc) {
   Links &L = c->links[prec];
   for (int p = 0; p < 2; p++) {
     if (!L.fat[p]) {
       CHK(dev_alloc(c, &L.fat[p], link_bytes(c, prec)));
       CU(cudaMemsetAsync(L.fat[p], 0, link_bytes(c, prec), c->stream));
     }
+    if (L.lng[p] && L.lng_nc != nc) {
+      CU(cudaStreamSynchronize(c->stream));
+      dev_free(c, L.lng[p], link_bytes(c, prec, L.lng_nc));
+      L.lng[p] = nullptr;
+    }
     if (!L.lng[p]) {
-      CHK(dev_alloc(c, &L.lng[p], link_bytes(c, prec)));
-      CU(cudaMemsetAsync(L.lng[p], 0, link_bytes(c, prec), c->stream));
+      CHK(dev_alloc(c, &L.lng[p], link_bytes(c, prec, nc)));
+      CU(cudaMemsetAsync(L.lng[p], 0, link_bytes(c, prec, nc), c->stream));
     }
   }
+  L.lng_nc = nc;
   return 0;
 }
 
@@ -342,17 +367,79 @@ static void pack_links_T(b200ks_ctx *c, void *dst, const void *staged) {
          c->g.lstride, c->g.Vh);
 }
 
+static int check_recon(int long_recon) {
+  if (long_recon != 18 && long_recon != 14 && long_recon != 0)
+    return fail(B200KS_EINVAL, "long_recon must be 18 (full), 14 (two rows + U(3) factor) or 0 (automatic)");
+  return 0;
+}
+
+// Long links of a real HISQ/asqtad action are (real scalar) x U(3); such links are stored as
+// two rows + one complex factor (14 reals, dslash.cuh load_long).  The test is made on the
+// data: every link, ghosts included, must reproduce its third row to `tol`.  long_recon 0
+// keeps the full matrices when the test fails, 14 makes a failure an error.
+static int compress_long(b200ks_ctx *c, int prec, int long_recon) {
+  c->long_dev = -1;
+  if (long_recon == 18) return 0;
+  Links &L = c->links[prec];
+  const Geom &g = c->g;
+  if (!c->d_dev) CHK(dev_alloc(c, (void **)&c->d_dev, sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(c->d_dev, 0, sizeof(unsigned long long), c->stream));
+  for (int p = 0; p < 2; p++) {
+    if (prec == 2) LAUNCH(c, (long_deviation_kernel<double>), nblocks(g.lstride), (const double2 *)L.lng[p], g.lstride, g.lstride, c->d_dev);
+    else LAUNCH(c, (long_deviation_kernel<float>), nblocks(g.lstride), (const float2 *)L.lng[p], g.lstride, g.lstride, c->d_dev);
+  }
+  unsigned long long bits = 0;
+  CU(cudaMemcpyAsync(&bits, c->d_dev, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CHK(check_launch("long_deviation_kernel"));
+  double dev;
+  memcpy(&dev, &bits, sizeof(dev));
+  if (c->comm.nranks > 1) {  // every rank must take the same decision
+    double *d = c->d_scal;
+    CU(cudaMemcpyAsync(d, &dev, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NC(nccl().AllReduce(d, d, 1, ncclDouble, ncclMax, c->comm.red, c->stream));
+    CU(cudaMemcpyAsync(&dev, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  c->long_dev = dev;
+  const double tol = prec == 2 ? 1e-13 : 5e-6;
+  if (!(dev <= tol)) {
+    if (long_recon == 14)
+      return fail(B200KS_EINVAL, "long_recon 14: long links are not (scalar x U(3)) to working precision, misfit " + std::to_string(dev));
+    return 0;  // automatic: keep the full matrices
+  }
+  for (int p = 0; p < 2; p++) {
+    void *z = nullptr;
+    CHK(dev_alloc(c, &z, link_bytes(c, prec, 7)));
+    if (prec == 2) LAUNCH(c, (compress_long_kernel<double>), nblocks(g.lstride), (double2 *)z, (const double2 *)L.lng[p], g.lstride, g.lstride);
+    else LAUNCH(c, (compress_long_kernel<float>), nblocks(g.lstride), (float2 *)z, (const float2 *)L.lng[p], g.lstride, g.lstride);
+    CU(cudaStreamSynchronize(c->stream));
+    dev_free(c, L.lng[p], link_bytes(c, prec, 9));
+    L.lng[p] = z;
+  }
+  L.lng_nc = 7;
+  return check_launch("compress_long_kernel");
+}
+
+extern "C" int b200ks_long_link_info(b200ks_ctx *c, int *ncomplex, double *misfit) {
+  if (!c) return fail(B200KS_EINVAL, "null context");
+  if (c->link_master == 0) return fail(B200KS_ESTATE, "links not loaded");
+  if (ncomplex) *ncomplex = c->links[c->link_master].lng_nc;
+  if (misfit) *misfit = c->long_dev;
+  return 0;
+}
+
 extern "C" int b200ks_load_links(b200ks_ctx *c, const void *fat, const void *lng, int host_prec, int long_recon) {
   if (!c || !fat || !lng) return fail(B200KS_EINVAL, "b200ks_load_links: null argument");
   if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
-  if (long_recon != 18) return fail(B200KS_EINVAL, "long_recon: only 18 is implemented");
+  CHK(check_recon(long_recon));
   CU(cudaSetDevice(c->device));
   const int prec = host_prec;  // master copy at the caller's precision
-  CHK(links_alloc(c, prec));
+  CHK(links_alloc(c, prec, 9));
   const size_t hs = host_prec == 2 ? 8 : 4;
   const size_t half_bytes = (size_t)c->g.Vh * 72 * hs;
   void *stage = nullptr;
-  CHK(dev_alloc(c, &stage, half_bytes));
+  CHK(stage_get(c, half_bytes, &stage));
   for (int which = 0; which < 2; which++) {
     const char *h = (const char *)(which == 0 ? fat : lng);
     for (int p = 0; p < 2; p++) {
@@ -363,12 +450,11 @@ extern "C" int b200ks_load_links(b200ks_ctx *c, const void *fat, const void *lng
     }
   }
   CU(cudaStreamSynchronize(c->stream));
-  dev_free(c, stage, half_bytes);
   CHK(check_launch("pack_link_kernel"));
   CHK(exchange_link_ghosts(c, prec));
   c->link_master = prec;
   for (int k = 0; k < 3; k++) c->links[k].valid = (k == prec);
-  return 0;
+  return compress_long(c, prec, long_recon);
 }
 
 // make sure links exist at precision `prec` (device-side down-conversion of the master copy)
@@ -376,16 +462,18 @@ static int links_ensure(b200ks_ctx *c, int prec) {
   if (c->link_master == 0) return fail(B200KS_ESTATE, "links not loaded (call b200ks_load_links first)");
   if (c->links[prec].valid) return 0;
   if (prec == B200KS_PREC_HALF) return fail(B200KS_EINVAL, "half-precision links not implemented yet");
-  CHK(links_alloc(c, prec));
   const int m = c->link_master;
+  const int nc = c->links[m].lng_nc;
+  CHK(links_alloc(c, prec, nc));
   for (int p = 0; p < 2; p++) {
     for (int which = 0; which < 2; which++) {
       void *d = which ? c->links[prec].lng[p] : c->links[prec].fat[p];
       const void *s = which ? c->links[m].lng[p] : c->links[m].fat[p];
+      const int ncomp = which ? 4 * nc : 36;
       if (prec == 1 && m == 2)
-        LAUNCH(c, (convert_link_kernel<float, double>), nblocks(c->g.lstride), (float2 *)d, (const double2 *)s, c->g.lstride, c->g.lstride);
+        LAUNCH(c, (convert_link_kernel<float, double>), nblocks(c->g.lstride), (float2 *)d, (const double2 *)s, c->g.lstride, c->g.lstride, ncomp);
       else if (prec == 2 && m == 1)
-        LAUNCH(c, (convert_link_kernel<double, float>), nblocks(c->g.lstride), (double2 *)d, (const float2 *)s, c->g.lstride, c->g.lstride);
+        LAUNCH(c, (convert_link_kernel<double, float>), nblocks(c->g.lstride), (double2 *)d, (const float2 *)s, c->g.lstride, c->g.lstride, ncomp);
     }
   }
   CHK(check_launch("convert_link_kernel"));
@@ -461,25 +549,33 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
   a.sites = nullptr;
   a.nsites = c->g.Vh;
   const int grid = nblocks(c->g.Vh);
+  const bool z7 = L.lng_nc == 7;
+#define DSLASH_LAUNCH(kMode, grid_)                                                        \
+  do {                                                                                     \
+    if (z7) {                                                                              \
+      if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, kMode, 7>), grid_, a);               \
+      else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, kMode, 7>), grid_, a);          \
+      else LAUNCH(c, (dslash_kernel<T, 2, kMode, 7>), grid_, a);                           \
+    } else {                                                                               \
+      if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, kMode, 9>), grid_, a);               \
+      else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, kMode, 9>), grid_, a);          \
+      else LAUNCH(c, (dslash_kernel<T, 2, kMode, 9>), grid_, a);                           \
+    }                                                                                      \
+  } while (0)
   if (c->comm.nranks == 1) {
-    if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, 0>), grid, a);
-    else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, 0>), grid, a);
-    else LAUNCH(c, (dslash_kernel<T, 2, 0>), grid, a);
+    DSLASH_LAUNCH(0, grid);
     return 0;
   }
   // multi-GPU: halo exchange || interior pass, then the exterior pass on the boundary sites
   CHK(halo_start<T>(c, in, par_out ^ 1));
-  if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, 1>), grid, a);
-  else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, 1>), grid, a);
-  else LAUNCH(c, (dslash_kernel<T, 2, 1>), grid, a);
+  DSLASH_LAUNCH(1, grid);
   CU(cudaStreamWaitEvent(c->stream, c->comm.ev_done, 0));
   a.sites = c->comm.ext_sites;
   a.nsites = c->comm.n_ext;
   a.red = e.red_ext;
   const int egrid = nblocks(c->comm.n_ext);
-  if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, 2>), egrid, a);
-  else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, 2>), egrid, a);
-  else LAUNCH(c, (dslash_kernel<T, 2, 2>), egrid, a);
+  DSLASH_LAUNCH(2, egrid);
+#undef DSLASH_LAUNCH
   return 0;
 }
 
@@ -508,10 +604,11 @@ static int upload(b200ks_ctx *c, DevVec &v, const void *host, int parity, int ho
   if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
   const size_t hs = host_prec == 2 ? 8 : 4;
   const size_t half_bytes = (size_t)c->g.Vh * 6 * hs;
-  void *stage = nullptr;
-  CHK(dev_alloc(c, &stage, half_bytes));
+  char *stage2 = nullptr;
+  CHK(stage_get(c, 2 * half_bytes, (void **)&stage2));
   for (int p = 0; p < 2; p++) {
     if (!((parity == B200KS_EVENANDODD) || (parity == B200KS_EVEN && p == 0) || (parity == B200KS_ODD && p == 1))) continue;
+    void *stage = stage2 + (size_t)p * half_bytes;
     CU(cudaMemcpyAsync(stage, (const char *)host + (size_t)p * half_bytes, half_bytes, cudaMemcpyHostToDevice, c->stream));
     if (v.prec == 2 && host_prec == 2) pack_vec_T<double, double>(c, v.p[p], stage);
     else if (v.prec == 2 && host_prec == 1) pack_vec_T<double, float>(c, v.p[p], stage);
@@ -519,7 +616,6 @@ static int upload(b200ks_ctx *c, DevVec &v, const void *host, int parity, int ho
     else pack_vec_T<float, float>(c, v.p[p], stage);
   }
   CU(cudaStreamSynchronize(c->stream));
-  dev_free(c, stage, half_bytes);
   return check_launch("pack_vec_kernel");
 }
 
@@ -527,10 +623,11 @@ static int download(b200ks_ctx *c, const DevVec &v, void *host, int parity, int 
   if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
   const size_t hs = host_prec == 2 ? 8 : 4;
   const size_t half_bytes = (size_t)c->g.Vh * 6 * hs;
-  void *stage = nullptr;
-  CHK(dev_alloc(c, &stage, half_bytes));
+  char *stage2 = nullptr;
+  CHK(stage_get(c, 2 * half_bytes, (void **)&stage2));
   for (int p = 0; p < 2; p++) {
     if (!((parity == B200KS_EVENANDODD) || (parity == B200KS_EVEN && p == 0) || (parity == B200KS_ODD && p == 1))) continue;
+    void *stage = stage2 + (size_t)p * half_bytes;
     if (v.prec == 2 && host_prec == 2) unpack_vec_T<double, double>(c, stage, v.p[p]);
     else if (v.prec == 2 && host_prec == 1) unpack_vec_T<double, float>(c, stage, v.p[p]);
     else if (v.prec == 1 && host_prec == 2) unpack_vec_T<float, double>(c, stage, v.p[p]);
@@ -538,7 +635,6 @@ static int download(b200ks_ctx *c, const DevVec &v, void *host, int parity, int 
     CU(cudaMemcpyAsync((char *)host + (size_t)p * half_bytes, stage, half_bytes, cudaMemcpyDeviceToHost, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
-  dev_free(c, stage, half_bytes);
   return check_launch("unpack_vec_kernel");
 }
 
@@ -1239,9 +1335,9 @@ extern "C" int b200ks_vec_gaussian(b200ks_ctx *c, int h, int parity, unsigned lo
 
 extern "C" int b200ks_links_synthetic(b200ks_ctx *c, unsigned long long seed, int long_recon) {
   if (!c) return fail(B200KS_EINVAL, "null context");
-  if (long_recon != 18) return fail(B200KS_EINVAL, "long_recon: only 18 is implemented");
+  CHK(check_recon(long_recon));
   CU(cudaSetDevice(c->device));
-  CHK(links_alloc(c, 2));
+  CHK(links_alloc(c, 2, 9));
   int lsites = c->g.Vh;
   for (int d = 2; d < 4; d++)
     if (c->g.part[d]) lsites = c->g.lghost[d] + 3 * c->g.faceh[d];
@@ -1252,7 +1348,7 @@ extern "C" int b200ks_links_synthetic(b200ks_ctx *c, unsigned long long seed, in
   CHK(check_launch("synth_links_kernel"));
   c->link_master = 2;
   for (int k = 0; k < 3; k++) c->links[k].valid = (k == 2);
-  return 0;
+  return compress_long(c, 2, long_recon);
 }
 
 extern "C" int b200ks_links_download(b200ks_ctx *c, void *fat, void *lng, int host_prec) {
@@ -1264,11 +1360,17 @@ extern "C" int b200ks_links_download(b200ks_ctx *c, void *fat, void *lng, int ho
   const size_t hs = host_prec == 2 ? 8 : 4;
   const size_t half_bytes = (size_t)c->g.Vh * 72 * hs;
   void *stage = nullptr;
-  CHK(dev_alloc(c, &stage, half_bytes));
+  CHK(stage_get(c, half_bytes, &stage));
   for (int which = 0; which < 2; which++)
     for (int p = 0; p < 2; p++) {
       const void *src = which ? c->links[m].lng[p] : c->links[m].fat[p];
       const int grid = nblocks(c->g.Vh);
+      if (which && c->links[m].lng_nc == 7) {
+        if (m == 2 && host_prec == 2) LAUNCH(c, (unpack_long7_kernel<double, double>), grid, (double *)stage, (const double2 *)src, c->g.lstride, c->g.Vh);
+        else if (m == 2 && host_prec == 1) LAUNCH(c, (unpack_long7_kernel<double, float>), grid, (float *)stage, (const double2 *)src, c->g.lstride, c->g.Vh);
+        else if (m == 1 && host_prec == 2) LAUNCH(c, (unpack_long7_kernel<float, double>), grid, (double *)stage, (const float2 *)src, c->g.lstride, c->g.Vh);
+        else LAUNCH(c, (unpack_long7_kernel<float, float>), grid, (float *)stage, (const float2 *)src, c->g.lstride, c->g.Vh);
+      } else
       if (m == 2 && host_prec == 2) LAUNCH(c, (unpack_link_kernel<double, double>), grid, (double *)stage, (const double2 *)src, c->g.lstride, c->g.Vh);
       else if (m == 2 && host_prec == 1) LAUNCH(c, (unpack_link_kernel<double, float>), grid, (float *)stage, (const double2 *)src, c->g.lstride, c->g.Vh);
       else if (m == 1 && host_prec == 2) LAUNCH(c, (unpack_link_kernel<float, double>), grid, (double *)stage, (const float2 *)src, c->g.lstride, c->g.Vh);
@@ -1277,6 +1379,5 @@ extern "C" int b200ks_links_download(b200ks_ctx *c, void *fat, void *lng, int ho
       CU(cudaMemcpyAsync(h + (size_t)p * half_bytes, stage, half_bytes, cudaMemcpyDeviceToHost, c->stream));
     }
   CU(cudaStreamSynchronize(c->stream));
-  dev_free(c, stage, half_bytes);
   return check_launch("unpack_link_kernel");
 }

@@ -439,18 +439,123 @@ pack_link_kernel(typename Vec2<T>::type *d, const TH *h, int lstride, int n) {
   }
 }
 
+// ncomp = 4 * (complex numbers per link): 36 for full matrices, 28 for compressed long links
 template <typename TD, typename TS>
 __global__ void __launch_bounds__(kBlock)
-convert_link_kernel(typename Vec2<TD>::type *d, const typename Vec2<TS>::type *s, int lstride, int n) {
+convert_link_kernel(typename Vec2<TD>::type *d, const typename Vec2<TS>::type *s, int lstride, int n, int ncomp) {
   const int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
-#pragma unroll 6
-  for (int m = 0; m < 36; m++) {
+#pragma unroll 4
+  for (int m = 0; m < ncomp; m++) {
     const auto a = s[(size_t)m * lstride + i];
     typename Vec2<TD>::type o;
     o.x = (TD)a.x;
     o.y = (TD)a.y;
     d[(size_t)m * lstride + i] = o;
+  }
+}
+
+// ---- long-link compression (two rows + one complex U(3) factor, see dslash.cuh load_long) ------
+// Least-squares factor f with row3 = f * conj(row1 x row2), and the relative misfit
+// max_k |row3_k - f c_k| / |row1| that decides whether compression is legitimate.
+template <typename T>
+__device__ __forceinline__ void long_factor(const typename Vec2<T>::type (&U)[9], double &fx, double &fy, double &dev) {
+  double cx[3], cy[3], nn = 0, px = 0, py = 0, n1 = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+    const double ar = U[k1].x, ai = U[k1].y, br = U[3 + k2].x, bi = U[3 + k2].y;
+    const double er = U[k2].x, ei = U[k2].y, gr = U[3 + k1].x, gi = U[3 + k1].y;
+    cx[k] = (ar * br - ai * bi) - (er * gr - ei * gi);
+    cy[k] = -((ar * bi + ai * br) - (er * gi + ei * gr));
+    nn += cx[k] * cx[k] + cy[k] * cy[k];
+    // row3_k * conj(c_k)
+    px += (double)U[6 + k].x * cx[k] + (double)U[6 + k].y * cy[k];
+    py += (double)U[6 + k].y * cx[k] - (double)U[6 + k].x * cy[k];
+    n1 += (double)U[k].x * U[k].x + (double)U[k].y * U[k].y;
+  }
+  if (nn == 0) {  // zero link (padding): any f works
+    fx = fy = 0;
+    double r3 = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) r3 += (double)U[6 + k].x * U[6 + k].x + (double)U[6 + k].y * U[6 + k].y;
+    dev = (r3 == 0) ? 0.0 : 1.0;
+    return;
+  }
+  fx = px / nn;
+  fy = py / nn;
+  double d2 = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double rx = U[6 + k].x - (fx * cx[k] - fy * cy[k]);
+    const double ry = U[6 + k].y - (fx * cy[k] + fy * cx[k]);
+    d2 = fmax(d2, rx * rx + ry * ry);
+  }
+  dev = sqrt(d2 / n1);
+}
+
+// max misfit over all links of one parity half -> *out (bits of a non-negative double, atomicMax)
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+long_deviation_kernel(const typename Vec2<T>::type *lng, int lstride, int n, unsigned long long *out) {
+  using T2 = typename Vec2<T>::type;
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  double worst = 0;
+  if (i < n) {
+    for (int mu = 0; mu < 4; mu++) {
+      T2 U[9];
+#pragma unroll
+      for (int e = 0; e < 9; e++) U[e] = lng[(size_t)(mu * 9 + e) * lstride + i];
+      double fx, fy, dev;
+      long_factor<T>(U, fx, fy, dev);
+      if (!(dev <= worst)) worst = (dev == dev) ? dev : 1.0;   // NaN counts as a failure
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  if ((threadIdx.x & 31) == 0 && worst > 0) atomicMax(out, (unsigned long long)__double_as_longlong(worst));
+}
+
+// [mu][9][site] -> [mu][7][site]
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+compress_long_kernel(typename Vec2<T>::type *dst, const typename Vec2<T>::type *src, int lstride, int n) {
+  using T2 = typename Vec2<T>::type;
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  for (int mu = 0; mu < 4; mu++) {
+    T2 U[9];
+#pragma unroll
+    for (int e = 0; e < 9; e++) U[e] = src[(size_t)(mu * 9 + e) * lstride + i];
+    double fx, fy, dev;
+    long_factor<T>(U, fx, fy, dev);
+#pragma unroll
+    for (int e = 0; e < 6; e++) dst[(size_t)(mu * 7 + e) * lstride + i] = U[e];
+    T2 f;
+    f.x = (T)fx;
+    f.y = (T)fy;
+    dst[(size_t)(mu * 7 + 6) * lstride + i] = f;
+  }
+}
+
+// compressed device long links -> host su3_matrix[4*V] layout
+template <typename T, typename TH>
+__global__ void __launch_bounds__(kBlock)
+unpack_long7_kernel(TH *h, const typename Vec2<T>::type *d, int lstride, int n) {
+  using T2 = typename Vec2<T>::type;
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  TH *s = h + (size_t)72 * i;
+  for (int mu = 0; mu < 4; mu++) {
+    T2 U[9];
+#pragma unroll
+    for (int e = 0; e < 6; e++) U[e] = d[(size_t)(mu * 7 + e) * lstride + i];
+    reconstruct_row3<T, T2>(U, d[(size_t)(mu * 7 + 6) * lstride + i]);
+#pragma unroll
+    for (int e = 0; e < 9; e++) {
+      s[2 * (mu * 9 + e)] = (TH)U[e].x;
+      s[2 * (mu * 9 + e) + 1] = (TH)U[e].y;
+    }
   }
 }
 

@@ -17,7 +17,7 @@ typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
 enum { ncclInt8 = 0, ncclChar = 0, ncclFloat64 = 8, ncclDouble = 8 };  // nccl.h ncclDataType_t
-enum { ncclSum = 0 };
+enum { ncclSum = 0, ncclMax = 2 };  // nccl.h ncclRedOp_t
 
 struct NcclApi {
   void *handle = nullptr;

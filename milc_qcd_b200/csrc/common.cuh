@@ -112,6 +112,27 @@ __device__ __forceinline__ void cmad_conj(T &re, T &im, const T2 a, const T2 b) 
   im = fma(-a.y, b.x, im);
 }
 
+// row3 = f * conj(row1 x row2) for a matrix that is (real scalar) x U(3); see load_long.
+template <typename T, typename T2>
+__device__ __forceinline__ void reconstruct_row3(T2 (&U)[9], const T2 f) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+    // c = conj(U[k1] * U[3+k2] - U[k2] * U[3+k1])
+    T cr = U[k1].x * U[3 + k2].x;
+    cr = fma(-U[k1].y, U[3 + k2].y, cr);
+    cr = fma(-U[k2].x, U[3 + k1].x, cr);
+    cr = fma(U[k2].y, U[3 + k1].y, cr);
+    T ci = U[k1].x * U[3 + k2].y;
+    ci = fma(U[k1].y, U[3 + k2].x, ci);
+    ci = fma(-U[k2].x, U[3 + k1].y, ci);
+    ci = fma(-U[k2].y, U[3 + k1].x, ci);
+    ci = -ci;
+    U[6 + k].x = fma(f.x, cr, -f.y * ci);
+    U[6 + k].y = fma(f.x, ci, f.y * cr);
+  }
+}
+
 // ---- cache-hinted loads ----------------------------------------------------------------
 // Links are streamed once per dslash: evict-first so they do not push the neighbour
 // spinors (each re-read 16x) out of L2.  Spinors take the default (read-only) path.

@@ -74,6 +74,24 @@ __device__ __forceinline__ void load_link(const T2 *U, int lstride, int mu, int 
   for (int e = 0; e < 9; e++) o[e] = ld_stream(p + (size_t)e * lstride);
 }
 
+// Long (Naik) links are a real scalar times a U(3) matrix (c_naik * W W W with KS/boundary
+// signs folded in, generic_ks/fermion_links_hisq_load_milc.c; c3 * U U U for asqtad), so the
+// third row is redundant: row3 = f * conj(row1 x row2) with one complex number f = det(V)/s
+// per link.  kNc == 7 reads the compressed form {row1, row2, f} = 14 reals instead of 18 and
+// rebuilds row 3 in registers (9 complex multiplies against 32 bytes of HBM traffic).
+template <typename T, typename T2, int kNc>
+__device__ __forceinline__ void load_long(const T2 *U, int lstride, int mu, int i, T2 (&o)[9]) {
+  if (kNc == 9) {
+    load_link<T, T2>(U, lstride, mu, i, o);
+    return;
+  }
+  const T2 *p = U + (size_t)mu * 7 * lstride + i;
+#pragma unroll
+  for (int e = 0; e < 6; e++) o[e] = ld_stream(p + (size_t)e * lstride);
+  const T2 f = ld_stream(p + (size_t)6 * lstride);
+  reconstruct_row3<T, T2>(o, f);
+}
+
 // acc += U v
 template <typename T, typename T2>
 __device__ __forceinline__ void mat_vec_add(const T2 (&U)[9], const T2 (&v)[3], T (&acc)[6]) {
@@ -94,7 +112,7 @@ __device__ __forceinline__ void adj_mat_vec_sub(const T2 (&U)[9], const T2 (&v)[
   for (int k = 0; k < 6; k++) acc[k] -= t[k];
 }
 
-template <typename T, int D, int kMode>
+template <typename T, int D, int kMode, int kNc>
 __device__ __forceinline__ void hop_dir(const DslashArg<T> &a, int idx, const Coord &c, T (&acc)[6]) {
   using T2 = typename Vec2<T>::type;
   const Geom &g = a.g;
@@ -112,12 +130,14 @@ __device__ __forceinline__ void hop_dir(const DslashArg<T> &a, int idx, const Co
     const bool lng = (hop & 1);
     const int n = neighbor<D, false>(g, idx, c, h);
     if (hop < 2) {
-      load_link<T, T2>(lng ? a.lng_this : a.fat_this, g.lstride, D, idx, U);
+      if (lng) load_long<T, T2, kNc>(a.lng_this, g.lstride, D, idx, U);
+      else load_link<T, T2>(a.fat_this, g.lstride, D, idx, U);
       load_vec<T, T2>(a, n, part, v);
       mat_vec_add<T, T2>(U, v, acc);
     } else {
       const int nl = part ? neighbor<D, true>(g, idx, c, h) : n;
-      load_link<T, T2>(lng ? a.lng_other : a.fat_other, g.lstride, D, nl, U);
+      if (lng) load_long<T, T2, kNc>(a.lng_other, g.lstride, D, nl, U);
+      else load_link<T, T2>(a.fat_other, g.lstride, D, nl, U);
       load_vec<T, T2>(a, n, part, v);
       adj_mat_vec_sub<T, T2>(U, v, acc);
     }
@@ -132,7 +152,8 @@ __device__ __forceinline__ bool is_boundary(const Geom &g, const Coord &c) {
 }
 
 // kEpi: 0 plain store, 1 xpay, 2 xpay + 3 fused dots.  kMode: see the header comment.
-template <typename T, int kEpi, int kMode>
+// kNc: complex numbers stored per long link (9 = full matrix, 7 = two rows + U(3) factor).
+template <typename T, int kEpi, int kMode, int kNc>
 __global__ void __launch_bounds__(kBlock) dslash_kernel(const DslashArg<T> a) {
   using T2 = typename Vec2<T>::type;
   if (a.stop != nullptr && *a.stop) return;
@@ -151,10 +172,10 @@ __global__ void __launch_bounds__(kBlock) dslash_kernel(const DslashArg<T> a) {
         acc[2 * q + 1] = o.y;
       }
     }
-    hop_dir<T, 0, kMode>(a, idx, c, acc);
-    hop_dir<T, 1, kMode>(a, idx, c, acc);
-    hop_dir<T, 2, kMode>(a, idx, c, acc);
-    hop_dir<T, 3, kMode>(a, idx, c, acc);
+    hop_dir<T, 0, kMode, kNc>(a, idx, c, acc);
+    hop_dir<T, 1, kMode, kNc>(a, idx, c, acc);
+    hop_dir<T, 2, kMode, kNc>(a, idx, c, acc);
+    hop_dir<T, 3, kMode, kNc>(a, idx, c, acc);
     const bool do_epi = (kMode != 1) || !is_boundary(a.g, c);
     if (kEpi >= 1 && do_epi) {
 #pragma unroll

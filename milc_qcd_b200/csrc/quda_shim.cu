@@ -59,7 +59,7 @@ void ensure_links(const char *where, const void *fat, const void *lng, int ext_p
   static const int always = env_int("B200KS_ALWAYS_RELOAD_LINKS", 1);
   const bool fresh = (num_iters && *num_iters == -1) || fat != S.fat || lng != S.lng || ext_prec != S.link_prec;
   if (fresh || always) {
-    if (b200ks_load_links(S.ctx, fat, lng, ext_prec, 18) < 0) die(where);
+    if (b200ks_load_links(S.ctx, fat, lng, ext_prec, 0) < 0) die(where);
     S.fat = fat;
     S.lng = lng;
     S.link_prec = ext_prec;

@@ -94,7 +94,7 @@ static b200ks_ctx *context(const char *myname) {
 /* d_congrad5_fn_gpu.c:121-126: refresh the device links when fn changed or was rebuilt */
 static void refresh_links(const char *myname, imp_ferm_links_t *fn) {
   if (fn != fn_last || fn->notify_quda_new_links) {
-    if (b200ks_load_links(context(myname), fn->fat, fn->lng, MILC_PRECISION, 18) < 0) die(myname);
+    if (b200ks_load_links(context(myname), fn->fat, fn->lng, MILC_PRECISION, 0) < 0) die(myname);
     fn->notify_quda_new_links = 0; /* cancel_quda_notification(fn) */
     fn_last = fn;
   }

@@ -50,7 +50,7 @@ def launches(path, tag):
     print(open(out).read())
 
 
-def full(path, tag, kernel_match="dslash_kernel<double, 0"):
+def full(path, tag):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -69,18 +69,24 @@ def full(path, tag, kernel_match="dslash_kernel<double, 0"):
         v = float(r[i].replace(",", ""))
         u = units[i].lower()
         return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1}.get(u, 1)
+    import re
+    kernels = []
     for r in rows[2:]:
-        if kernel_match in r[hdr.index("Kernel Name")]:
-            tr = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
-            js = {"tag": tag, "kernel": r[hdr.index("Kernel Name")], "dram_bytes_per_launch": tr,
-                  "dram_bytes_read": val(r, "dram__bytes_read.sum"), "dram_bytes_write": val(r, "dram__bytes_write.sum"),
-                  "gpu_time_us": float(r[hdr.index("gpu__time_duration.sum")]),
-                  "source": os.path.basename(path), "lattice": "32x32x32x64"}
-            json.dump(js, open(os.path.join(HERE, "dslash_ncu_summary.json"), "w"), indent=1)
-            print(js)
-            break
+        name = r[hdr.index("Kernel Name")]
+        m = re.search(r"dslash_kernel<(double|float), (\d), (\d), (\d)>", name)
+        if not m:
+            continue
+        tr = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
+        kernels.append({"kernel": name, "prec": 2 if m.group(1) == "double" else 1, "epilogue": int(m.group(2)),
+                        "mode": int(m.group(3)), "long_reals": 2 * int(m.group(4)), "dram_bytes_per_launch": tr,
+                        "dram_bytes_read": val(r, "dram__bytes_read.sum"),
+                        "dram_bytes_write": val(r, "dram__bytes_write.sum"),
+                        "gpu_time_us": float(r[hdr.index("gpu__time_duration.sum")])})
+    js = {"tag": tag, "source": os.path.basename(path), "lattice": "32x32x32x64", "kernels": kernels}
+    json.dump(js, open(os.path.join(HERE, "dslash_ncu_summary.json"), "w"), indent=1)
+    print(json.dumps(js, indent=1))
 
 
 if __name__ == "__main__":
     launches(sys.argv[1], sys.argv[3])
-    full(sys.argv[2], sys.argv[3], *(sys.argv[4:5]))
+    full(sys.argv[2], sys.argv[3])

@@ -28,10 +28,12 @@ def api():
 
 @pytest.mark.parametrize("dims", SIZES)
 @pytest.mark.parametrize("parity", [EVEN, ODD, EVENANDODD])
-def test_dslash_matches_oracle(api, oracle, dims, parity):
+@pytest.mark.parametrize("long_recon", [18, 14])
+def test_dslash_matches_oracle(api, oracle, dims, parity, long_recon):
     fat, lng, src = fields_for(dims)
     ctx = api.Context(dims)
-    ctx.load_links(fat, lng)
+    ctx.load_links(fat, lng, long_recon)
+    assert ctx.long_link_info()[0] == (9 if long_recon == 18 else 7)
     want = oracle.dslash(dims, fat, lng, src, parity)
     sentinel = 7.25
     got = np.full_like(src, sentinel)
@@ -64,6 +66,46 @@ def test_dslash_inplace_and_single_precision(api, oracle):
     got = np.zeros(src.shape, np.float32)
     ctx.dslash(src.astype(np.float32), got, EVEN)
     assert rel_err(got[:V // 2].astype(np.float64), want[:V // 2]) <= 2e-6
+    ctx.close()
+
+
+def test_long_link_compression_is_decided_on_the_data(api, oracle):
+    """long_recon 0 (what the MILC-facing shims pass) compresses long links to two rows + a U(3)
+    factor only when every link is (real scalar) x U(3); generic matrices keep all 18 reals and
+    an explicit request for 14 is refused.  The device copy reads back as the input."""
+    dims = (8, 6, 4, 6)
+    fat, lng, src = fields_for(dims)
+    V = src.shape[0]
+    ctx = api.Context(dims)
+    ctx.load_links(fat, lng)  # automatic
+    nc, misfit = ctx.long_link_info()
+    assert nc == 7 and 0 <= misfit <= 1e-13
+    f2, l2 = ctx.links_download()
+    assert np.array_equal(f2, fat)
+    assert np.abs(l2 - lng).max() <= 1e-15
+    # float hosts (MILC_PRECISION=1): same decision at single-precision tolerance
+    ctx.load_links(fat.astype(np.float32), lng.astype(np.float32))
+    assert ctx.long_link_info()[0] == 7
+    got = np.zeros(src.shape, np.float32)
+    ctx.dslash(src.astype(np.float32), got, EVENANDODD)
+    assert rel_err(got.astype(np.float64), oracle.dslash(dims, fat, lng, src, EVENANDODD)) <= 2e-6
+    # non-unitary "long" links: the fat links of the same field stand in for them
+    ctx.load_links(fat, fat)
+    nc, misfit = ctx.long_link_info()
+    assert nc == 9 and misfit > 1e-6
+    got = np.zeros_like(src)
+    ctx.dslash(src, got, EVENANDODD)
+    assert rel_err(got, oracle.dslash(dims, fat, fat, src, EVENANDODD)) <= DSLASH_TOL
+    with pytest.raises(Exception, match="long_recon 14"):
+        ctx.load_links(fat, fat, 14)
+    # a single perturbed element anywhere must be noticed
+    bad = lng.copy()
+    bad[V - 1, 3, 2, 1, 0] += 1e-9
+    ctx.load_links(fat, bad)
+    assert ctx.long_link_info()[0] == 9
+    got = np.zeros_like(src)
+    ctx.dslash(src, got, EVENANDODD)
+    assert rel_err(got, oracle.dslash(dims, fat, bad, src, EVENANDODD)) <= DSLASH_TOL
     ctx.close()
 
 
