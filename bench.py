@@ -376,7 +376,9 @@ def run_b200(args):
                        "l2": "links streamed by every dslash (%.2f GB per GPU at the inner precision) exceed the 126 MB L2; no flush needed"
                              % ((4 if args.mixed else 8) * (18 + long_reals) * 4 * Vl / 1e9),
                        "flop_convention": "MILC 1187 flop/site/iteration", "mixed_precision": args.mixed,
-                       "halo": "depth-3 ghosts, NCCL send/recv overlapped with the interior pass" if multi else "none"},
+                       "halo": {0: "none", 1: "depth-3 ghosts, NCCL send/recv overlapped with the interior launch",
+                                2: "depth-3 ghosts pushed into the neighbours' peer-mapped ghost buffers (NVLink stores), "
+                                   "interior-first single-launch stencil acquiring arrival flags"}[ctx.halo_mode()]},
             "cg_iters_per_solve": iters_total / args.steps, "cg_time_to_solution_s": ms_total * 1e-3 / args.steps,
             "cg_device_seconds": dev_s / args.steps, "true_residual": true_resid, "converged": res["converged"],
             "dslash_gflops": {"f64": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[2] * 1e-3) / 1e9,

@@ -98,6 +98,12 @@ b200ks_ctx *b200ks_create(const int latsize[4], int device);
 b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4], int rank, int nranks,
                                const void *nccl_unique_id, int device);
 int b200ks_comm_unique_id(void *out128);
+/* How this context exchanges halos: 0 = nothing partitioned, 1 = ncclSend/ncclRecv,
+ * 2 = peer-to-peer pushes into the neighbours' mapped ghost buffers (default; set
+ * B200KS_HALO=nccl to force 1).  B200KS_FORCE_PARTITION=z|t|zt makes b200ks_create_dist treat
+ * an unsplit direction as partitioned with the rank as its own neighbour (testing/profiling
+ * of the halo path on fewer GPUs). */
+int b200ks_halo_mode(b200ks_ctx *ctx);
 
 void b200ks_destroy(b200ks_ctx *ctx);
 

@@ -90,13 +90,13 @@ class Context:
         self.lib = _lib.load()
         self.global_dims = tuple(int(d) for d in dims)
         arr = (C.c_int * 4)(*self.global_dims)
-        if grid is None or nranks == 1:
+        if grid is None:
             self.dims = self.global_dims
             self.h = self.lib.b200ks_create(arr, device)
         else:
             self.dims = tuple(self.global_dims[d] // int(grid[d]) for d in range(4))
             garr = (C.c_int * 4)(*[int(g) for g in grid])
-            buf = C.create_string_buffer(bytes(nccl_id), 128)
+            buf = C.create_string_buffer(bytes(nccl_id), 128) if nccl_id is not None else None
             self.h = self.lib.b200ks_create_dist(arr, garr, rank, nranks, buf, device)
         if not self.h:
             raise _lib.B200KSError("b200ks_create failed: %s" % self.lib.b200ks_last_error().decode())
@@ -221,6 +221,10 @@ class Context:
         out = C.c_double()
         check(self.lib.b200ks_dslash_time(self.h, prec, parity, n, C.byref(out)), "b200ks_dslash_time")
         return out.value
+
+    def halo_mode(self):
+        """0 no partitioned direction, 1 NCCL send/recv halos, 2 peer-to-peer push halos."""
+        return check(self.lib.b200ks_halo_mode(self.h), "b200ks_halo_mode")
 
     def launch_count(self):
         return int(self.lib.b200ks_launch_count(self.h))

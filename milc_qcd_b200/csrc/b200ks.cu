@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -244,6 +245,11 @@ extern "C" void b200ks_destroy(b200ks_ctx *c) {
   }
   if (c->comm.halo) nccl().CommDestroy(c->comm.halo);
   if (c->comm.red) nccl().CommDestroy(c->comm.red);
+  for (int k = 0; k < 4; k++)
+    if (c->comm.p2p.opened[k]) cudaIpcCloseMemHandle(c->comm.p2p.opened[k]);
+  cudaFree(c->comm.p2p.block);
+  cudaFree(c->comm.p2p.ticket);
+  cudaFree(c->comm.p2p.err);
   cudaFree(c->comm.ghost[0]);
   cudaFree(c->comm.zsend);
   cudaFree(c->comm.ext_sites);
@@ -332,10 +338,11 @@ static int exchange_link_ghosts_T(b200ks_ctx *c, int prec) {
   using T2 = typename Vec2<T>::type;
   const Geom &g = c->g;
   Comm &cm = c->comm;
-  if (cm.nranks == 1) return 0;
+  if (!cm.active) return 0;
   for (int d = 2; d < 4; d++) {
     if (!g.part[d]) continue;
     const size_t face3 = (size_t)3 * g.faceh[d];
+    const bool self = cm.nbr[d][1] == cm.rank;   // one rank in this direction: the ghost is our own far side
     T2 *buf = nullptr;
     if (d == 2) CHK(dev_alloc(c, (void **)&buf, 9 * face3 * sizeof(T2)));
     for (int which = 0; which < 2; which++)
@@ -343,14 +350,18 @@ static int exchange_link_ghosts_T(b200ks_ctx *c, int prec) {
         T2 *U = (T2 *)(which ? c->links[prec].lng[p] : c->links[prec].fat[p]);
         if (d == 2)
           LAUNCH(c, (pack_zhigh_links_kernel<T>), nblocks((int)(9 * face3)), buf, U, g, d);
-        NC(nccl().GroupStart());
+        if (!self) NC(nccl().GroupStart());
         for (int e = 0; e < 9; e++) {
           T2 *comp = U + (size_t)(d * 9 + e) * g.lstride;
           const T2 *src = (d == 3) ? comp + (size_t)(g.L[3] - 3) * g.faceh[3] : buf + e * face3;
-          NC(nccl().Send(src, face3 * sizeof(T2), ncclChar, cm.nbr[d][1], cm.halo, c->stream));
-          NC(nccl().Recv(comp + g.lghost[d], face3 * sizeof(T2), ncclChar, cm.nbr[d][0], cm.halo, c->stream));
+          if (self) {
+            CU(cudaMemcpyAsync(comp + g.lghost[d], src, face3 * sizeof(T2), cudaMemcpyDeviceToDevice, c->stream));
+          } else {
+            NC(nccl().Send(src, face3 * sizeof(T2), ncclChar, cm.nbr[d][1], cm.halo, c->stream));
+            NC(nccl().Recv(comp + g.lghost[d], face3 * sizeof(T2), ncclChar, cm.nbr[d][0], cm.halo, c->stream));
+          }
         }
-        NC(nccl().GroupEnd());
+        if (!self) NC(nccl().GroupEnd());
       }
     CU(cudaStreamSynchronize(c->stream));
     if (buf) dev_free(c, buf, 9 * face3 * sizeof(T2));
@@ -483,6 +494,8 @@ static int links_ensure(b200ks_ctx *c, int prec) {
 
 // ---------------------------------------------------------------------------------------------
 // dslash launcher.  par_out = parity bit of the output sites.
+constexpr long long kHaloTimeoutCycles = 20000000000ll;   // ~10 s at 2 GHz
+
 struct Epi {
   int kind = 0;            // 0 store, 1 xpay, 2 xpay + dots
   double s = 0;
@@ -496,11 +509,51 @@ struct Epi {
 // Depth-3 halo of `in` (parity half pin): z faces are packed, t faces are sent straight
 // from the field; everything travels as one NCCL group on the comm stream while the
 // interior pass runs on the compute stream.
+static unsigned long long *p2p_flags(char *block) { return (unsigned long long *)block; }
+static char *p2p_ghost(const P2P &pp, char *block, unsigned long long seq) {
+  return block + kP2PFlagBytes + (size_t)(seq & 1ull) * pp.ghost_bytes;
+}
+
+// Peer-to-peer exchange `seq`: one push kernel on the (high-priority) comm stream, concurrent
+// with the interior pass.  Returns the ghost buffer the stencil kernels of this exchange read.
 template <typename T>
-static int halo_start(b200ks_ctx *c, const DevVec &in, int pin) {
+static int halo_push(b200ks_ctx *c, const DevVec &in, int pin, const int *stop) {
   using T2 = typename Vec2<T>::type;
   const Geom &g = c->g;
   Comm &cm = c->comm;
+  P2P &pp = cm.p2p;
+  pp.seq++;
+  PushArg a;
+  memset(&a, 0, sizeof(a));
+  int n = 0;
+  for (int d = 2; d < 4; d++) {
+    if (!g.part[d]) continue;
+    n += 6 * g.faceh[d];
+    for (int side = 0; side < 2; side++) {
+      char *peer = pp.peer_block[d - 2][side];
+      a.dst[d - 2][side] = p2p_ghost(pp, peer, pp.seq);
+      a.flag[d - 2][side] = p2p_flags(peer) + (d - 2) * 2 + (side ? 0 : 1);
+    }
+  }
+  a.seq = pp.seq;
+  a.ticket = pp.ticket;
+  a.stop = stop;
+  CU(cudaEventRecord(cm.ev_ready, c->stream));
+  CU(cudaStreamWaitEvent(cm.stream, cm.ev_ready, 0));
+  const int pgrid = std::min((n + kPushBlock - 1) / kPushBlock, cm.push_ctas);
+  push_halo_kernel<T><<<pgrid, kPushBlock, 0, cm.stream>>>(a, (const T2 *)in.p[pin], g);
+  c->launches++;
+  // whatever later overwrites `in` on the compute stream must not overtake the push reading it
+  CU(cudaEventRecord(cm.ev_done, cm.stream));
+  return 0;
+}
+
+template <typename T>
+static int halo_start(b200ks_ctx *c, const DevVec &in, int pin, const int *stop) {
+  using T2 = typename Vec2<T>::type;
+  const Geom &g = c->g;
+  Comm &cm = c->comm;
+  if (cm.p2p.on) return halo_push<T>(c, in, pin, stop);
   const T2 *f = (const T2 *)in.p[pin];
   T2 *ghost = (T2 *)cm.ghost[0];
   T2 *zs = (T2 *)cm.zsend;
@@ -546,8 +599,17 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
   a.ws = c->ws;
   a.red = e.red;
   a.stop = e.stop;
-  a.sites = nullptr;
+  a.sites = c->comm.ext_sites;
   a.nsites = c->g.Vh;
+  a.n_int = c->comm.n_int;
+  a.n_ext = c->comm.n_ext;
+  a.nb_int = nblocks(c->comm.n_int);
+  a.blk0 = 0;
+  a.halo_flags = nullptr;
+  a.halo_seq = 0;
+  a.halo_mask = 0;
+  a.halo_err = nullptr;
+  a.halo_timeout = kHaloTimeoutCycles;
   const int grid = nblocks(c->g.Vh);
   const bool z7 = L.lng_nc == 7;
 #define DSLASH_LAUNCH(kMode, grid_)                                                        \
@@ -562,19 +624,33 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
       else LAUNCH(c, (dslash_kernel<T, 2, kMode, 9>), grid_, a);                           \
     }                                                                                      \
   } while (0)
-  if (c->comm.nranks == 1) {
+  if (!c->comm.active) {
     DSLASH_LAUNCH(0, grid);
     return 0;
   }
-  // multi-GPU: halo exchange || interior pass, then the exterior pass on the boundary sites
-  CHK(halo_start<T>(c, in, par_out ^ 1));
-  DSLASH_LAUNCH(1, grid);
+  const int nb_ext = nblocks(c->comm.n_ext);
+  CHK(halo_start<T>(c, in, par_out ^ 1, e.stop));
+  if (c->comm.p2p.on) {
+    // one launch: interior CTAs first (overlapping the neighbours' pushes), then the boundary
+    // CTAs, each of which acquires the arrival flags of this exchange before it reads ghosts
+    P2P &pp = c->comm.p2p;
+    a.gin = (const T2 *)p2p_ghost(pp, pp.block, pp.seq);
+    a.halo_flags = p2p_flags(pp.block);
+    a.halo_seq = pp.seq;
+    a.halo_mask = (c->g.part[2] ? 3 : 0) | (c->g.part[3] ? 12 : 0);
+    a.halo_err = pp.err;
+    DSLASH_LAUNCH(1, a.nb_int + nb_ext);
+    CU(cudaStreamWaitEvent(c->stream, c->comm.ev_done, 0));
+    return 0;
+  }
+  // NCCL halos: interior launch || exchange, stream event, boundary launch (its reductions go
+  // to red_ext and are folded in by combine_red_kernel)
+  if (a.nb_int > 0) DSLASH_LAUNCH(1, a.nb_int);
+  else if (e.kind == 2) CU(cudaMemsetAsync(e.red, 0, 3 * sizeof(double), c->stream));
   CU(cudaStreamWaitEvent(c->stream, c->comm.ev_done, 0));
-  a.sites = c->comm.ext_sites;
-  a.nsites = c->comm.n_ext;
+  a.blk0 = a.nb_int;
   a.red = e.red_ext;
-  const int egrid = nblocks(c->comm.n_ext);
-  DSLASH_LAUNCH(2, egrid);
+  DSLASH_LAUNCH(1, nb_ext);
 #undef DSLASH_LAUNCH
   return 0;
 }
@@ -585,6 +661,15 @@ static int dslash_any(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out,
   if (in.prec == 2) return dslash_T<double>(c, in, out, par_out, e);
   if (in.prec == 1) return dslash_T<float>(c, in, out, par_out, e);
   return fail(B200KS_EINVAL, "dslash: unsupported precision");
+}
+
+static int halo_check(b200ks_ctx *c) {
+  if (!c->comm.p2p.on) return 0;
+  int e = 0;
+  CU(cudaMemcpyAsync(&e, c->comm.p2p.err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (e) return fail(B200KS_ECOMM, "halo exchange timed out waiting for face " + std::to_string(e - 1) + " (a neighbour rank stopped?)");
+  return 0;
 }
 
 static int parity_bit(int parity) { return parity == B200KS_ODD ? 1 : 0; }
@@ -731,6 +816,7 @@ extern "C" int b200ks_dslash_dev(b200ks_ctx *c, int vsrc, int vdest, int parity,
   if (s == d && parity == B200KS_EVENANDODD) return fail(B200KS_EINVAL, "in-place dslash needs a single parity");
   CU(cudaSetDevice(c->device));
   CHK(dslash_parity(c, *s, *d, parity));
+  CHK(halo_check(c));
   return check_launch("dslash_kernel");
 }
 
@@ -766,6 +852,7 @@ extern "C" int b200ks_dslash_time(b200ks_ctx *c, int prec, int parity, int n, do
   float t = 0;
   CU(cudaEventElapsedTime(&t, c->ev0, c->ev1));
   *ms = (double)t / n;
+  CHK(halo_check(c));
   return check_launch("dslash_kernel");
 }
 
@@ -778,7 +865,7 @@ static int state_push(b200ks_ctx *c) {
 static int state_pull(b200ks_ctx *c) {
   CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  return 0;
+  return halo_check(c);
 }
 
 template <typename T>
@@ -794,7 +881,7 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
   const double msq_x4 = 4.0 * mass * mass;
   const int max_cg = max_restarts * niter;
   const bool rel = relrsqmin > 0;
-  const bool multi = c->comm.nranks > 1;
+  const bool multi = c->comm.active;
   const int batch = args.check_interval > 0 ? args.check_interval : 8;
 
   res = b200ks_invert_result();
@@ -873,7 +960,7 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
         e1.stop = &c->d_state->stop;
         CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
         if (multi) {  // one all-reduce per iteration: {pkp, c_tr, c_tt} + last update's |r|^2
-          LAUNCH1(c, combine_red_kernel, c->d_state, 3);
+          if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 3);
           CHK(allreduce(c, c->d_state->red, rel ? 3 : 5));
         }
         if (rel)
@@ -923,7 +1010,7 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
   const double rsqmin = args.resid * args.resid;
   const double msq_x4 = 4.0 * mass * mass;
   const int max_cg = max_restarts * niter;
-  const bool multi = c->comm.nranks > 1;
+  const bool multi = c->comm.active;
   const int batch = args.check_interval > 0 ? args.check_interval : 8;
   const double delta = 0.1;
   if (args.relresid != 0) return fail(B200KS_EINVAL, "mixed precision: Fermilab relative residual not supported");
@@ -994,7 +1081,7 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
         f1.stop = &c->d_state->stop;
         CHK(dslash_T<float>(c, *ttt_lo, *ttt_lo, pb, f1));
         if (multi) {
-          LAUNCH1(c, combine_red_kernel, c->d_state, 3);
+          if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 3);
           CHK(allreduce(c, c->d_state->red, 5));
         }
         LAUNCH(c, (cg_update_kernel<float, false>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
@@ -1151,8 +1238,8 @@ static int multicg_T(b200ks_ctx *c, const DevVec &b, DevVec *const *psim, const 
       e1.kind = 2; e1.s = shift0; e1.w = cgp; e1.r = nullptr; e1.red = c->d_state->red; e1.red_ext = c->d_state->red_ext;
       e1.stop = &c->d_state->stop;
       CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
-      if (c->comm.nranks > 1) {
-        LAUNCH1(c, combine_red_kernel, c->d_state, 1);
+      if (c->comm.active) {
+        if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 1);
         CHK(allreduce(c, c->d_state->red, 1));
       }
       LAUNCH(c, (ms_resid_kernel<T>), grid, (T2 *)r->p[pb], (const T2 *)ttt->p[pb], g.stride, g.Vh, c->d_state, c->ws);
@@ -1238,6 +1325,122 @@ extern "C" int b200ks_comm_unique_id(void *out128) {
   return 0;
 }
 
+// Ghost buffers, boundary-site list, peer mappings: everything a context with at least one
+// partitioned direction needs.  Peer-to-peer halos are the default; B200KS_HALO=nccl selects
+// the ncclSend/ncclRecv path (also the fallback when the peer mapping cannot be set up).
+static int comm_setup(b200ks_ctx *c) {
+  Comm &cm = c->comm;
+  const Geom &g = c->g;
+  cm.active = true;
+  int lo = 0, hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CU(cudaStreamCreateWithPriority(&cm.stream, cudaStreamNonBlocking, hi));
+  CU(cudaEventCreateWithFlags(&cm.ev_ready, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&cm.ev_done, cudaEventDisableTiming));
+  std::vector<int> ext;
+  const int S2 = g.Lxh * g.L[1];
+  for (int t = 0; t < g.L[3]; t++)
+    for (int z = 0; z < g.L[2]; z++) {
+      const bool b = (g.part[3] && (t < 3 || t >= g.L[3] - 3)) || (g.part[2] && (z < 3 || z >= g.L[2] - 3));
+      if (!b) continue;
+      const int base = (t * g.L[2] + z) * S2;
+      for (int k = 0; k < S2; k++) ext.push_back(base + k);
+    }
+  cm.n_ext = (int)ext.size();
+  cm.n_int = g.Vh - cm.n_ext;
+  CHK(dev_alloc(c, (void **)&cm.ext_sites, sizeof(int) * ext.size()));
+  CU(cudaMemcpy(cm.ext_sites, ext.data(), sizeof(int) * ext.size(), cudaMemcpyHostToDevice));
+
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  cm.push_ctas = getenv("B200KS_PUSH_CTAS") ? std::max(1, atoi(getenv("B200KS_PUSH_CTAS"))) : sms;
+  const char *mode = getenv("B200KS_HALO");
+  const bool want_p2p = !(mode && strcmp(mode, "nccl") == 0);
+  if (cm.nranks == 1 && !want_p2p) return fail(B200KS_EINVAL, "a self-partitioned single rank needs the peer-to-peer halo path");
+  P2P &pp = cm.p2p;
+  if (want_p2p) {
+    pp.ghost_bytes = (size_t)3 * g.gstride * sizeof(double2);
+    const size_t bytes = kP2PFlagBytes + 2 * pp.ghost_bytes;
+    CHK(dev_alloc(c, (void **)&pp.block, bytes));
+    CU(cudaMemset(pp.block, 0, bytes));
+    void *q = nullptr;
+    CHK(dev_alloc(c, &q, sizeof(unsigned)));
+    pp.ticket = (unsigned *)q;
+    CHK(dev_alloc(c, &q, sizeof(int)));
+    pp.err = (int *)q;
+    CU(cudaMemset(pp.ticket, 0, sizeof(unsigned)));
+    CU(cudaMemset(pp.err, 0, sizeof(int)));
+    bool ok = true;
+    std::vector<cudaIpcMemHandle_t> handles(cm.nranks);
+    if (cm.nranks > 1) {
+      cudaIpcMemHandle_t mine;
+      ok = cudaIpcGetMemHandle(&mine, pp.block) == cudaSuccess;
+      if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
+      // every rank learns every handle (and whether every export worked) through one all-gather
+      char *d_h = nullptr;
+      const size_t hb = sizeof(cudaIpcMemHandle_t) + 8;
+      CU(cudaMalloc(&d_h, hb * (cm.nranks + 1)));
+      char tmp[sizeof(cudaIpcMemHandle_t) + 8] = {0};
+      memcpy(tmp, &mine, sizeof(mine));
+      tmp[sizeof(mine)] = ok ? 1 : 0;
+      CU(cudaMemcpy(d_h + hb * cm.nranks, tmp, hb, cudaMemcpyHostToDevice));
+      NC(nccl().AllGather(d_h + hb * cm.nranks, d_h, hb, ncclChar, cm.red, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      std::vector<char> all(hb * cm.nranks);
+      CU(cudaMemcpy(all.data(), d_h, all.size(), cudaMemcpyDeviceToHost));
+      cudaFree(d_h);
+      for (int r = 0; r < cm.nranks; r++) {
+        memcpy(&handles[r], all.data() + hb * r, sizeof(cudaIpcMemHandle_t));
+        ok = ok && all[hb * r + sizeof(cudaIpcMemHandle_t)] == 1;
+      }
+    }
+    int nopen = 0;
+    int opened_rank[4];
+    for (int d = 2; d < 4 && ok; d++)
+      for (int side = 0; side < 2 && ok; side++) {
+        const int r = cm.nbr[d][side];
+        if (!g.part[d]) continue;
+        if (r == cm.rank) { pp.peer_block[d - 2][side] = pp.block; continue; }
+        char *ptr = nullptr;
+        for (int k = 0; k < nopen; k++)
+          if (opened_rank[k] == r) ptr = (char *)pp.opened[k];
+        if (!ptr) {
+          void *vp = nullptr;
+          if (cudaIpcOpenMemHandle(&vp, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+            break;
+          }
+          pp.opened[nopen] = vp;
+          opened_rank[nopen++] = r;
+          ptr = (char *)vp;
+        }
+        pp.peer_block[d - 2][side] = ptr;
+      }
+    if (cm.nranks > 1) {  // all or nothing: a rank that could not map a neighbour sends everyone to NCCL
+      double flag = ok ? 0.0 : 1.0;
+      CU(cudaMemcpy(c->d_scal, &flag, sizeof(double), cudaMemcpyHostToDevice));
+      NC(nccl().AllReduce(c->d_scal, c->d_scal, 1, ncclDouble, ncclSum, cm.red, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      CU(cudaMemcpy(&flag, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost));
+      ok = flag == 0.0;
+    }
+    pp.on = ok;
+    if (!ok && cm.nranks == 1) return fail(B200KS_ECOMM, "peer-to-peer halo setup failed");
+  }
+  if (!pp.on) {  // NCCL halos: one ghost buffer + a packed z send buffer
+    CHK(dev_alloc(c, &cm.ghost[0], (size_t)3 * g.gstride * sizeof(double2)));
+    CU(cudaMemset(cm.ghost[0], 0, (size_t)3 * g.gstride * sizeof(double2)));
+    if (g.part[2]) CHK(dev_alloc(c, &cm.zsend, (size_t)18 * g.faceh[2] * sizeof(double2)));
+  }
+  return 0;
+}
+
+extern "C" int b200ks_halo_mode(b200ks_ctx *c) {
+  if (!c) return fail(B200KS_EINVAL, "null context");
+  return !c->comm.active ? 0 : c->comm.p2p.on ? 2 : 1;
+}
+
 extern "C" b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4], int rank, int nranks,
                                           const void *nccl_unique_id, int device) {
   if (!latsize || !grid) { fail(B200KS_EINVAL, "b200ks_create_dist: null argument"); return nullptr; }
@@ -1246,15 +1449,23 @@ extern "C" b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4
     return nullptr;
   }
   int local[4], part[4], origin[4], coord[4] = {0, 0, rank % grid[2], rank / grid[2]};
+  // B200KS_FORCE_PARTITION=z|t|zt: treat an unsplit direction as partitioned with this rank
+  // as its own neighbour, so the whole halo machinery runs (and can be profiled) on fewer GPUs
+  const char *force = getenv("B200KS_FORCE_PARTITION");
+  bool any = false;
   for (int d = 0; d < 4; d++) {
     if (latsize[d] % grid[d]) { fail(B200KS_EINVAL, "lattice extent not divisible by the rank grid"); return nullptr; }
     local[d] = latsize[d] / grid[d];
     part[d] = grid[d] > 1;
+    if (d >= 2 && force && strchr(force, d == 2 ? 'z' : 't')) part[d] = 1;
+    any = any || part[d];
     origin[d] = coord[d] * local[d];
   }
-  if (nranks == 1) return create_common(latsize, local, part, origin, device);
-  if (!nccl_unique_id) { fail(B200KS_EINVAL, "b200ks_create_dist: null nccl_unique_id"); return nullptr; }
-  if (!nccl().ok) { fail(B200KS_ECOMM, "libnccl.so.2 could not be loaded"); return nullptr; }
+  if (!any) return create_common(latsize, local, part, origin, device);
+  if (nranks > 1) {
+    if (!nccl_unique_id) { fail(B200KS_EINVAL, "b200ks_create_dist: null nccl_unique_id"); return nullptr; }
+    if (!nccl().ok) { fail(B200KS_ECOMM, "libnccl.so.2 could not be loaded"); return nullptr; }
+  }
   b200ks_ctx *c = create_common(latsize, local, part, origin, device);
   if (!c) return nullptr;
   Comm &cm = c->comm;
@@ -1267,51 +1478,32 @@ extern "C" b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4
   cm.nbr[3][0] = rank_of(coord[2], coord[3] - 1);
   cm.nbr[3][1] = rank_of(coord[2], coord[3] + 1);
   auto init = [&]() -> int {
-    ncclUniqueId ids[2];
-    memcpy(ids, nccl_unique_id, sizeof(ncclUniqueId));
-    // the second communicator (all-reduces) gets its id from rank 0 over the first one
-    NC(nccl().CommInitRank(&cm.halo, nranks, ids[0], rank));
-    CU(cudaStreamCreateWithFlags(&cm.stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&cm.ev_ready, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&cm.ev_done, cudaEventDisableTiming));
-    char *d_id = nullptr;
-    CU(cudaMalloc(&d_id, sizeof(ncclUniqueId)));
-    if (rank == 0) {
-      NC(nccl().GetUniqueId(&ids[1]));
-      CU(cudaMemcpy(d_id, &ids[1], sizeof(ncclUniqueId), cudaMemcpyHostToDevice));
-    } else {
-      CU(cudaMemset(d_id, 0, sizeof(ncclUniqueId)));
-    }
-    // broadcast by all-reduce(sum) of bytes widened to doubles would be wasteful; send/recv it
-    NC(nccl().GroupStart());
-    if (rank == 0) {
-      for (int r = 1; r < nranks; r++) NC(nccl().Send(d_id, sizeof(ncclUniqueId), ncclChar, r, cm.halo, c->stream));
-    } else {
-      NC(nccl().Recv(d_id, sizeof(ncclUniqueId), ncclChar, 0, cm.halo, c->stream));
-    }
-    NC(nccl().GroupEnd());
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaMemcpy(&ids[1], d_id, sizeof(ncclUniqueId), cudaMemcpyDeviceToHost));
-    cudaFree(d_id);
-    NC(nccl().CommInitRank(&cm.red, nranks, ids[1], rank));
-    // ghost buffer, z send buffer (sized for double), boundary-site list
-    const Geom &g = c->g;
-    CHK(dev_alloc(c, &cm.ghost[0], (size_t)3 * g.gstride * sizeof(double2)));
-    CU(cudaMemset(cm.ghost[0], 0, (size_t)3 * g.gstride * sizeof(double2)));
-    if (g.part[2]) CHK(dev_alloc(c, &cm.zsend, (size_t)18 * g.faceh[2] * sizeof(double2)));
-    std::vector<int> ext;
-    const int S2 = g.Lxh * g.L[1];
-    for (int t = 0; t < g.L[3]; t++)
-      for (int z = 0; z < g.L[2]; z++) {
-        const bool b = (g.part[3] && (t < 3 || t >= g.L[3] - 3)) || (g.part[2] && (z < 3 || z >= g.L[2] - 3));
-        if (!b) continue;
-        const int base = (t * g.L[2] + z) * S2;
-        for (int k = 0; k < S2; k++) ext.push_back(base + k);
+    if (nranks > 1) {
+      ncclUniqueId ids[2];
+      memcpy(ids, nccl_unique_id, sizeof(ncclUniqueId));
+      // the second communicator (all-reduces) gets its id from rank 0 over the first one
+      NC(nccl().CommInitRank(&cm.halo, nranks, ids[0], rank));
+      char *d_id = nullptr;
+      CU(cudaMalloc(&d_id, sizeof(ncclUniqueId)));
+      if (rank == 0) {
+        NC(nccl().GetUniqueId(&ids[1]));
+        CU(cudaMemcpy(d_id, &ids[1], sizeof(ncclUniqueId), cudaMemcpyHostToDevice));
+      } else {
+        CU(cudaMemset(d_id, 0, sizeof(ncclUniqueId)));
       }
-    cm.n_ext = (int)ext.size();
-    CHK(dev_alloc(c, (void **)&cm.ext_sites, sizeof(int) * ext.size()));
-    CU(cudaMemcpy(cm.ext_sites, ext.data(), sizeof(int) * ext.size(), cudaMemcpyHostToDevice));
-    return 0;
+      NC(nccl().GroupStart());
+      if (rank == 0) {
+        for (int r = 1; r < nranks; r++) NC(nccl().Send(d_id, sizeof(ncclUniqueId), ncclChar, r, cm.halo, c->stream));
+      } else {
+        NC(nccl().Recv(d_id, sizeof(ncclUniqueId), ncclChar, 0, cm.halo, c->stream));
+      }
+      NC(nccl().GroupEnd());
+      CU(cudaStreamSynchronize(c->stream));
+      CU(cudaMemcpy(&ids[1], d_id, sizeof(ncclUniqueId), cudaMemcpyDeviceToHost));
+      cudaFree(d_id);
+      NC(nccl().CommInitRank(&cm.red, nranks, ids[1], rank));
+    }
+    return comm_setup(c);
   };
   if (init() < 0) {
     b200ks_destroy(c);

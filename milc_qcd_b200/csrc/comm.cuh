@@ -4,8 +4,12 @@
 // The reference exchanges halos with MPI point-to-point "gathers" re-armed every CG
 // iteration (generic/com_mpi.c, generic_ks/d_congrad5_fn_milc.c:264-272) and sums scalars with
 // MPI_Allreduce (g_doublesum / g_vecdoublesum).  Here every rank is one B200 of an NVSwitch
-// box: halos are ncclSend/ncclRecv groups over NVLink on a dedicated stream, overlapped with
-// the interior stencil pass; scalars are ncclAllReduce on the compute stream.
+// box.  Halos: every rank maps its neighbours' ghost buffers (CUDA IPC) and a push kernel
+// stores its boundary slices straight into them over NVLink, then raises an arrival flag in the
+// neighbour's memory; the consumer waits on its own flags with a one-warp kernel in front of the
+// exterior stencil pass.  No copy engine, no NCCL proxy, no host involvement per exchange.
+// (ncclSend/ncclRecv groups remain as the fallback when peer mapping is unavailable, and for
+// the one-time link-ghost exchange.)  Scalars are ncclAllReduce on the compute stream.
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -27,6 +31,7 @@ struct NcclApi {
   int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
@@ -47,16 +52,36 @@ inline NcclApi &nccl() {
   B200KS_SYM(Send, "ncclSend");
   B200KS_SYM(Recv, "ncclRecv");
   B200KS_SYM(AllReduce, "ncclAllReduce");
+  B200KS_SYM(AllGather, "ncclAllGather");
   B200KS_SYM(GroupStart, "ncclGroupStart");
   B200KS_SYM(GroupEnd, "ncclGroupEnd");
   B200KS_SYM(GetErrorString, "ncclGetErrorString");
 #undef B200KS_SYM
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce &&
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce && api.AllGather &&
            api.GroupStart && api.GroupEnd;
   return api;
 }
 
+// Peer-to-peer halo state.  One cudaMalloc block per rank, exported by cudaIpcGetMemHandle:
+//   [ arrival flags: 4 x u64 (z-behind, z-ahead, t-behind, t-ahead), padded to 256 B ]
+//   [ ghost buffer 0 ][ ghost buffer 1 ]     each 3 colours x gstride sites x sizeof(double2)
+// Ghost buffers alternate by exchange sequence number: a neighbour can be at most one
+// exchange ahead (its next push needs our halo of the current one), so two buffers suffice.
+struct P2P {
+  bool on = false;
+  char *block = nullptr;            // own block
+  size_t ghost_bytes = 0;           // bytes of one ghost buffer
+  char *peer_block[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [d-2][0 backward | 1 forward] neighbour's block
+  void *opened[4] = {nullptr, nullptr, nullptr, nullptr};              // cudaIpcOpenMemHandle results to close
+  unsigned long long seq = 0;       // exchange sequence number (host mirror)
+  unsigned *ticket = nullptr;       // push-kernel CTA ticket
+  int *err = nullptr;               // device word: nonzero = a halo wait timed out
+};
+constexpr size_t kP2PFlagBytes = 256;
+
 struct Comm {
+  bool active = false;   // some direction is partitioned (nranks > 1, or a forced self-partition)
+  P2P p2p;
   int rank = 0, nranks = 1;
   int grid[4] = {1, 1, 1, 1};
   int coord[4] = {0, 0, 0, 0};
@@ -68,8 +93,9 @@ struct Comm {
   void *ghost[2] = {nullptr, nullptr};   // ghost buffers (double-sized), ping-pong by dslash
   void *zsend = nullptr;                 // packed z faces
   int *ext_sites = nullptr;              // boundary-site list for the exterior pass
-  int n_ext = 0;
-  int flip = 0;
+  int n_ext = 0;                         // boundary sites per parity (within 3 slices of a partitioned face)
+  int n_int = 0;                         // the rest
+  int push_ctas = 148;                   // CTAs of the halo push kernel (one per SM by default)
 };
 
 }  // namespace b200ks

@@ -21,12 +21,18 @@
 //
 // Multi-GPU (lattice split in t, then z; depth-3 ghost zones, the reference's
 // D_FN_GATHER13 observation that the 1-hop halo is a subset of the 3-hop halo,
-// dslash_fn_dblstore.c:344-416):
-//   kMode 0 : single GPU, every hop
-//   kMode 1 : interior pass over all sites -- hops that stay on this GPU; the epilogue is
-//             applied only to sites with no ghost hop, boundary sites store raw partial sums
-//   kMode 2 : exterior pass over the boundary-site list -- adds the hops that read the ghost
-//             buffer (filled by the halo exchange that overlapped kMode 1), then the epilogue
+// dslash_fn_dblstore.c:344-416).  Every site is computed exactly once, with all 16 hops and
+// its epilogue:
+//   kMode 0 : single GPU, all sites
+//   kMode 1 : partitioned lattice.  The grid is ordered: the first nb_int CTAs take the
+//             interior sites (at least 3 slices away from every partitioned face; no hop
+//             leaves the GPU), the remaining CTAs take the boundary sites (site list), whose
+//             hops across a partitioned face read the ghost buffer and the backward-ghost tail
+//             of the link fields.  With peer-to-peer halos it is ONE launch: CTAs are issued in
+//             index order, so the interior CTAs stream while the neighbours' push kernels fill
+//             the ghost buffer, and each boundary CTA first acquires the arrival flags
+//             (halo_flags/halo_seq).  With NCCL halos the two ranges are two launches (blk0
+//             selects the range) separated by a stream event.
 #pragma once
 #include "common.cuh"
 
@@ -50,8 +56,16 @@ struct DslashArg {
   ReduceWs ws;
   double *red;          // device result slots for the fused reductions
   const int *stop;      // device flag: nonzero => solver already converged, do nothing
-  const int *sites;     // kMode 2: list of boundary sites
-  int nsites;           // number of threads' worth of work (Vh, or length of `sites`)
+  const int *sites;     // kMode 1: list of boundary sites
+  int nsites;           // kMode 0: Vh
+  int n_int, n_ext;     // kMode 1: interior / boundary site counts
+  int nb_int;           // kMode 1: CTAs covering the interior sites
+  int blk0;             // kMode 1: logical index of this launch's first CTA
+  const unsigned long long *halo_flags;  // kMode 1, peer-to-peer: arrival flags to acquire (nullptr: none)
+  unsigned long long halo_seq;
+  int halo_mask;
+  int *halo_err;
+  long long halo_timeout;
 };
 
 template <typename T, typename T2>
@@ -113,20 +127,14 @@ __device__ __forceinline__ void adj_mat_vec_sub(const T2 (&U)[9], const T2 (&v)[
 }
 
 template <typename T, int D, int kMode, int kNc>
-__device__ __forceinline__ void hop_dir(const DslashArg<T> &a, int idx, const Coord &c, T (&acc)[6]) {
+__device__ __forceinline__ void hop_dir(const DslashArg<T> &a, int idx, const Coord &c, bool bnd, T (&acc)[6]) {
   using T2 = typename Vec2<T>::type;
   const Geom &g = a.g;
   T2 U[9], v[3];
-  const int coord = (D == 0) ? c.x : (D == 1) ? c.y : (D == 2) ? c.z : c.t;
-  const bool part = (kMode != 0) && (D >= 2) && g.part[D];
-  if (kMode == 2 && !part) return;
+  const bool part = (kMode == 1) && (D >= 2) && bnd && g.part[D];
 #pragma unroll
   for (int hop = 0; hop < 4; hop++) {
     const int h = (hop == 0) ? 1 : (hop == 1) ? 3 : (hop == 2) ? -1 : -3;
-    if (kMode != 0) {
-      const bool is_ghost = part && (coord + h < 0 || coord + h >= g.L[D]);
-      if ((kMode == 1) == is_ghost) continue;
-    }
     const bool lng = (hop & 1);
     const int n = neighbor<D, false>(g, idx, c, h);
     if (hop < 2) {
@@ -144,40 +152,69 @@ __device__ __forceinline__ void hop_dir(const DslashArg<T> &a, int idx, const Co
   }
 }
 
-__device__ __forceinline__ bool is_boundary(const Geom &g, const Coord &c) {
-  bool b = false;
-  if (g.part[2]) b = b || (c.z < 3) || (c.z >= g.L[2] - 3);
-  if (g.part[3]) b = b || (c.t < 3) || (c.t >= g.L[3] - 3);
-  return b;
+// k-th interior site (kMode 1): z and t run over [3, L-3) in partitioned directions
+__device__ __forceinline__ int interior_site(const Geom &g, int k) {
+  const int S2 = g.Lxh * g.L[1];
+  const int zi = g.part[2] ? g.L[2] - 6 : g.L[2];
+  const int r = k % S2, q = k / S2;
+  const int z = q % zi + (g.part[2] ? 3 : 0);
+  const int t = q / zi + (g.part[3] ? 3 : 0);
+  return (t * g.L[2] + z) * S2 + r;
 }
 
 // kEpi: 0 plain store, 1 xpay, 2 xpay + 3 fused dots.  kMode: see the header comment.
 // kNc: complex numbers stored per long link (9 = full matrix, 7 = two rows + U(3) factor).
+// Spin (bounded) until every expected face of exchange `seq` has arrived; flags live in this
+// GPU's memory and are raised by the neighbours' push kernels (push_halo_kernel).
+__device__ __forceinline__ void acquire_halo(const unsigned long long *flags, unsigned long long seq, int mask, int *err,
+                                             long long max_cycles) {
+  const long long t0 = clock64();
+  for (int f = 0; f < 4; f++) {
+    if (!((mask >> f) & 1)) continue;
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + f) : "memory");
+      if (v >= seq) break;
+      if (clock64() - t0 > max_cycles) {
+        *err = 1 + f;
+        break;
+      }
+    }
+  }
+}
+
 template <typename T, int kEpi, int kMode, int kNc>
 __global__ void __launch_bounds__(kBlock) dslash_kernel(const DslashArg<T> a) {
   using T2 = typename Vec2<T>::type;
   if (a.stop != nullptr && *a.stop) return;
-  const int k = blockIdx.x * kBlock + threadIdx.x;
-  const bool active = k < a.nsites;
+  int k = blockIdx.x * kBlock + threadIdx.x;
+  bool active = k < a.nsites;
+  bool bnd = false;
+  if (kMode == 1) {
+    const int b = blockIdx.x + a.blk0;
+    bnd = b >= a.nb_int;
+    if (bnd) {
+      k = (b - a.nb_int) * kBlock + threadIdx.x;
+      active = k < a.n_ext;
+      if (a.halo_flags != nullptr) {
+        if (threadIdx.x == 0) acquire_halo(a.halo_flags, a.halo_seq, a.halo_mask, a.halo_err, a.halo_timeout);
+        __syncthreads();
+      }
+    } else {
+      k = b * kBlock + threadIdx.x;
+      active = k < a.n_int;
+    }
+  }
   double red[3] = {0, 0, 0};
   if (active) {
-    const int idx = (kMode == 2) ? a.sites[k] : k;
+    const int idx = (kMode == 0) ? k : bnd ? a.sites[k] : interior_site(a.g, k);
     const Coord c = site_coord(a.g, idx, a.par);
     T acc[6] = {0, 0, 0, 0, 0, 0};
-    if (kMode == 2) {
-#pragma unroll
-      for (int q = 0; q < 3; q++) {
-        const T2 o = a.out[(size_t)q * a.g.stride + idx];
-        acc[2 * q] = o.x;
-        acc[2 * q + 1] = o.y;
-      }
-    }
-    hop_dir<T, 0, kMode, kNc>(a, idx, c, acc);
-    hop_dir<T, 1, kMode, kNc>(a, idx, c, acc);
-    hop_dir<T, 2, kMode, kNc>(a, idx, c, acc);
-    hop_dir<T, 3, kMode, kNc>(a, idx, c, acc);
-    const bool do_epi = (kMode != 1) || !is_boundary(a.g, c);
-    if (kEpi >= 1 && do_epi) {
+    hop_dir<T, 0, kMode, kNc>(a, idx, c, bnd, acc);
+    hop_dir<T, 1, kMode, kNc>(a, idx, c, bnd, acc);
+    hop_dir<T, 2, kMode, kNc>(a, idx, c, bnd, acc);
+    hop_dir<T, 3, kMode, kNc>(a, idx, c, bnd, acc);
+    if (kEpi >= 1) {
 #pragma unroll
       for (int q = 0; q < 3; q++) {
         const T2 wv = a.w[(size_t)q * a.g.stride + idx];
@@ -223,6 +260,76 @@ pack_zface_kernel(typename Vec2<T>::type *buf, const typename Vec2<T>::type *v, 
   const int idx = (t * g.L[2] + z) * S2 + r2;
 #pragma unroll
   for (int c = 0; c < 3; c++) buf[(size_t)(side * 3 + c) * face3 + r] = v[(size_t)c * g.stride + idx];
+}
+
+// ---- peer-to-peer halo push (comm.cuh P2P) ------------------------------------------------------
+// Stores this rank's 3 low and 3 high slices of every partitioned direction into the
+// neighbours' ghost buffers (mapped peer memory, NVLink stores), then the last CTA raises the
+// arrival flags.  Low slices land in the backward neighbour's "ahead" zone, high slices in the
+// forward neighbour's "behind" zone; all ranks share one local geometry, so offsets are ours.
+struct PushArg {
+  void *dst[2][2];        // [d-2][0: our low slices | 1: our high slices] destination ghost buffer
+  unsigned long long *flag[2][2];   // arrival flag to raise at that destination
+  unsigned long long seq;
+  unsigned *ticket;
+  const int *stop;        // solver stop flag: a stopped solver's stencil launches are no-ops, so is this
+};
+
+constexpr int kPushBlock = 256;
+
+// A few long-lived CTAs (one per SM at most) with a grid-stride loop: remote stores are
+// fire-and-forget, so a CTA keeps issuing until its share is done and pays the NVLink round
+// trip once, at the fence.  (Many short CTAs would each sit in an SM slot for a round trip,
+// starving the concurrent interior stencil CTAs of slots.)
+template <typename T>
+__global__ void __launch_bounds__(kPushBlock)
+push_halo_kernel(const PushArg a, const typename Vec2<T>::type *v, const Geom g) {
+  using T2 = typename Vec2<T>::type;
+  if (a.stop != nullptr && *a.stop) return;
+  const int nz = g.part[2] ? 6 * g.faceh[2] : 0;
+  const int nt = g.part[3] ? 6 * g.faceh[3] : 0;
+  const int S2 = g.Lxh * g.L[1];
+  for (int k = blockIdx.x * kPushBlock + threadIdx.x; k < nz + nt; k += gridDim.x * kPushBlock) {
+    const int d = (k < nz) ? 2 : 3;
+    const int r = (k < nz) ? k : k - nz;
+    const int face3 = 3 * g.faceh[d];
+    const int side = r / face3;
+    const int r2 = r - side * face3;
+    const int slice = r2 / g.faceh[d];
+    const int within = r2 - slice * g.faceh[d];
+    int idx;
+    if (d == 3) {
+      idx = (side ? g.L[3] - 3 + slice : slice) * g.faceh[3] + within;
+    } else {
+      const int t = within / S2, rr = within - t * S2;
+      idx = (t * g.L[2] + (side ? g.L[2] - 3 + slice : slice)) * S2 + rr;
+    }
+    const int off = (g.ghost[d][side ? 0 : 1] - g.Vh) + slice * g.faceh[d] + within;
+    T2 *dst = (T2 *)a.dst[d - 2][side];
+    T2 x[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) x[c] = v[(size_t)c * g.stride + idx];
+#pragma unroll
+    for (int c = 0; c < 3; c++) dst[(size_t)c * g.gstride + off] = x[c];
+  }
+  // release: the CTA barrier orders every thread's stores before thread 0's system fence
+  // (fence cumulativity), which orders them before the ticket and, in the last CTA, the flags
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x < 4) {
+    const int d2 = threadIdx.x >> 1, side = threadIdx.x & 1;
+    __threadfence_system();
+    // atomicMax, not a store: flags only ever move forward, whatever order two exchanges'
+    // updates reach the neighbour in
+    if (g.part[d2 + 2]) atomicMax_system(a.flag[d2][side], a.seq);
+  }
+  if (threadIdx.x == 0) *a.ticket = 0;
 }
 
 }  // namespace b200ks

@@ -274,3 +274,42 @@ def test_golden_reference_vectors(api):
     V = src.shape[0]
     assert np.linalg.norm(x[:V // 2] - g["cg_x"][:V // 2]) <= 10 * float(g["cg_resid"]) * _cond(float(g["mass"])) * \
         np.linalg.norm(g["cg_x"][:V // 2])
+
+
+@pytest.mark.parametrize("force,dims", [("t", (8, 6, 8, 12)), ("z", (8, 6, 8, 12)), ("zt", (8, 6, 8, 12)),
+                                        ("zt", (4, 4, 6, 6)), ("t", (6, 4, 14, 6))])
+def test_forced_self_partition_runs_the_halo_path_on_one_gpu(api, oracle, force, dims, monkeypatch):
+    """B200KS_FORCE_PARTITION makes one GPU its own neighbour: ghost links, the peer-to-peer push
+    kernel, arrival flags, the interior/exterior split and the split reductions all run, and must
+    reproduce the oracle exactly as the unpartitioned kernels do."""
+    monkeypatch.setenv("B200KS_FORCE_PARTITION", force)   # extent 6 = no interior sites at all
+    fat, lng, src = fields_for(dims)
+    ctx = api.Context(dims, grid=(1, 1, 1, 1), rank=0, nranks=1)
+    assert ctx.halo_mode() == 2
+    ctx.load_links(fat, lng)
+    V = src.shape[0]
+    for parity in (EVEN, ODD, EVENANDODD):
+        got = np.zeros_like(src)
+        ctx.dslash(src, got, parity)
+        want = oracle.dslash(dims, fat, lng, src, parity)
+        sl = slice(0, V // 2) if parity == EVEN else slice(V // 2, V) if parity == ODD else slice(0, V)
+        assert rel_err(got[sl], want[sl]) <= DSLASH_TOL
+    b = src.copy()
+    b[V // 2:] = 0
+    for mixed in (0, 1):
+        x = np.zeros_like(b)
+        it, res = ctx.congrad(b, x, 0.05, EVEN, 500, 5, 1e-9, mixed_precision=mixed)
+        xo = np.zeros_like(b)
+        ito, qo = oracle.congrad(dims, fat, lng, b, xo, 0.05, EVEN, 500, 5, 1e-9)
+        assert res["converged"] == 1
+        assert abs(it - ito) <= (max(2, 0.02 * ito) if mixed == 0 else 0.25 * ito)
+        assert np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
+    from milc_qcd_b200 import fields as F
+    offsets = np.roll(F.rhmc_offsets(5, 0.05), 2)
+    ps = [np.zeros_like(b) for _ in offsets]
+    itm, resm = ctx.multicg(b, ps, offsets, EVEN, 3000, 1, 1e-8)
+    itmo, pso, qmo = oracle.multicg(dims, fat, lng, b, offsets, EVEN, 3000, 1, 1e-8)
+    assert abs(itm - itmo) <= max(2, 0.02 * itmo)
+    for j in range(len(offsets)):
+        assert np.linalg.norm(ps[j][:V // 2] - pso[j][:V // 2]) <= 1e-6 * np.linalg.norm(pso[j][:V // 2])
+    ctx.close()
