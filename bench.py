@@ -172,6 +172,12 @@ def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
+    # The b200 arm's workload at this N: 32^3x64 (N = 1) or the 64^3x96 strong-scaling lattice
+    # (N > 1).  The CPU sample always runs on the 32^3x64 lattice of the same synthetic ensemble:
+    # 64^3x96 double links are 29 GB plus MILC's back-link copy, beyond a bounded CPU run, and
+    # GFLOP/s (flop per site-iteration / time) is an intensive quantity.
+    multi = args.gpus > 1
+    arm_dims = (64, 64, 64, 96) if multi else DIMS
     dims = DIMS
     V = int(np.prod(dims))
     fat, lng, src = make_workload(dims)
@@ -181,15 +187,17 @@ def run_reference(args):
     tot_t = sum(t for t, _ in timed)
     tot_it = sum(it for _, it in timed)
     gflops = CG_FLOP_PER_SITE * V * tot_it / tot_t / 1e9
-    sample = "CG capped at %d iterations per step on the full 32^3x64 workload (%d counted iterations/step)" % (
-        iters, timed[0][1])
+    sample = "CG capped at %d iterations per step (%d counted iterations/step) on a 32^3x64 lattice of the workload's synthetic ensemble%s" % (
+        iters, timed[0][1], " (sub-volume sample of 64^3x96)" if multi else " (the full workload lattice)")
+    lat = "x".join(map(str, arm_dims))
     line = {
         "impl": "reference", "metric": "hisq_cg_gflops", "value": gflops, "unit": "GFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(len(timed), 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "HISQ single-mass CG, mass 0.05, synthetic random-SU(3) 32^3x64 (BASELINE configs[1])",
-                   "lattice": list(dims), "implementation": meta["impl"]},
+        "config": {"workload": "HISQ single-mass CG, mass 0.05, resid 1e-10, synthetic random-SU(3) %s (%s)"
+                               % (lat, "BASELINE configs[3], strong scaling" if multi else "BASELINE configs[1]"),
+                   "lattice": list(arm_dims), "sample_lattice": list(dims), "implementation": meta["impl"]},
         "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": meta["cores"], "kind": meta["kind"],
                          "sample": sample},
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
