@@ -45,6 +45,8 @@ CG_FLOP_PER_SITE = 1187.0      # d_congrad5_fn_milc.c:81-83
 DSLASH_FLOP_PER_SITE = 1146.0  # 16 x 66 + 15 x 6
 # algorithmic bytes per output site = w*(8*R_fat + 8*R_long + 6 + 6), w = bytes/real
 def dslash_bytes_per_site(prec, long_reals):
+    if prec == 0:   # 16-bit links, 16-bit colour vectors + one fp32 scale per site (in and out)
+        return 2.0 * (8 * 18 + 8 * long_reals) + 2 * 16
     return (8.0 if prec == 2 else 4.0) * (8 * 18 + 8 * long_reals + 12)
 
 
@@ -293,21 +295,27 @@ def run_b200(args):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count() - l0
 
-    # the other precision mode of the same solve, for the record (not the headline)
-    other = 0 if args.mixed else 1
-    solve_resident(other)
-    barrier()
-    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e4.record(stream)
-    it_o, res_o = solve_resident(other)
-    e5.record(stream)
-    barrier()
-    ms_other = max_over_ranks(e4.elapsed_time(e5))
+    # the other precision modes of the same solve, for the record (not the headline)
+    others = []
+    for other in (0, 1, 2):
+        if other == args.mixed:
+            continue
+        solve_resident(other)
+        barrier()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record(stream)
+        it_o, res_o = solve_resident(other)
+        e5.record(stream)
+        barrier()
+        ms_other = max_over_ranks(e4.elapsed_time(e5))
+        others.append({"mixed_precision": other, "value": CG_FLOP_PER_SITE * V * it_o / (ms_other * 1e-3) / 1e9,
+                       "unit": "GFLOP/s", "cg_iters": it_o, "cg_time_to_solution_s": ms_other * 1e-3,
+                       "final_rsq": res_o["final_rsq"]})
 
     # dominant-kernel roofline, live: back-to-back dslash launches (halo exchange included for N > 1)
     n_ds = 100
     ds_ms = {}
-    for p in (2, 1):
+    for p in (2, 1, 0):
         barrier()
         ds_ms[p] = max_over_ranks(ctx.dslash_time(p, EVEN, n_ds))
     clocks = sampler.stop()
@@ -352,9 +360,9 @@ def run_b200(args):
     value = CG_FLOP_PER_SITE * V * iters_total / (ms_total * 1e-3) / 1e9
     e2e_value = CG_FLOP_PER_SITE * V * it_e2e / (ms_e2e * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    kp = 1 if args.mixed else 2   # precision of the dslash that dominates the timed solve
-    bps = {p: dslash_bytes_per_site(p, long_reals) for p in (1, 2)}
-    ach = {p: bps[p] * Vlh / (ds_ms[p] * 1e-3) / 1e9 for p in (1, 2)}   # per GPU
+    kp = {0: 2, 1: 1, 2: 0}[args.mixed]   # storage precision of the stencil that dominates the timed solve
+    bps = {p: dslash_bytes_per_site(p, long_reals) for p in (0, 1, 2)}
+    ach = {p: bps[p] * Vlh / (ds_ms[p] * 1e-3) / 1e9 for p in (0, 1, 2)}   # per GPU
     half_bytes = Vlh * 6 * 8
 
     cpu = None
@@ -375,14 +383,16 @@ def run_b200(args):
         line = {
             "metric": "hisq_cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64" if args.mixed == 0 else "f64 (solution, true residuals) / f32 (inner Krylov vectors)",
+            "vs_baseline": None,
+            "dtype": {0: "f64", 1: "f64 (solution, true residuals) / f32 (inner Krylov vectors)",
+                      2: "f64 (solution, true residuals) / f32 arithmetic on 16-bit links and search direction (inner iteration)"}[args.mixed],
             "data": "synthetic",
             "config": {"workload": "HISQ single-mass CG, mass 0.05, resid 1e-10, synthetic random-SU(3) %s (%s)"
                                    % (lat, "BASELINE configs[1]" if dims == DIMS else "BASELINE configs[3], strong scaling"
                                       if dims == (64, 64, 64, 96) else "custom lattice"),
                        "lattice": list(dims), "rank_grid": list(grid), "local_lattice": list(ctx.dims),
                        "l2": "links streamed by every dslash (%.2f GB per GPU at the inner precision) exceed the 126 MB L2; no flush needed"
-                             % ((4 if args.mixed else 8) * (18 + long_reals) * 4 * Vl / 1e9),
+                             % ({0: 8, 1: 4, 2: 2}[args.mixed] * (18 + long_reals) * 4 * Vl / 1e9),
                        "flop_convention": "MILC 1187 flop/site/iteration", "mixed_precision": args.mixed,
                        "halo": {0: "none", 1: "depth-3 ghosts, NCCL send/recv overlapped with the interior launch",
                                 2: "depth-3 ghosts pushed into the neighbours' peer-mapped ghost buffers (NVLink stores), "
@@ -390,20 +400,21 @@ def run_b200(args):
             "cg_iters_per_solve": iters_total / args.steps, "cg_time_to_solution_s": ms_total * 1e-3 / args.steps,
             "cg_device_seconds": dev_s / args.steps, "true_residual": true_resid, "converged": res["converged"],
             "dslash_gflops": {"f64": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[2] * 1e-3) / 1e9,
-                              "f32": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[1] * 1e-3) / 1e9},
-            "dslash_ms": {"f64": ds_ms[2], "f32": ds_ms[1]},
-            "roofline": {"bound": "hbm", "kernel": "dslash_kernel<%s> (fat 18 / long %d reals per link)"
-                                                   % ("float" if kp == 1 else "double", long_reals),
+                              "f32": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[1] * 1e-3) / 1e9,
+                              "16bit": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[0] * 1e-3) / 1e9},
+            "dslash_ms": {"f64": ds_ms[2], "f32": ds_ms[1], "16bit": ds_ms[0]},
+            "roofline": {"bound": "hbm", "kernel": "%s (fat 18 / long %d reals per link)"
+                                                   % ({0: "dslash_half_kernel", 1: "dslash_kernel<float>", 2: "dslash_kernel<double>"}[kp],
+                                                      long_reals),
                          "achieved": ach[kp], "peak": peak,
                          "unit": "GB/s", "frac": ach[kp] / peak, "peak_source": peak_src,
                          "traffic": ncu_traffic(kp, long_reals) if dims == DIMS else None,
                          "algorithmic_bytes_per_launch": bps[kp] * Vlh, "algorithmic_bytes_per_site": bps[kp],
                          "note": "per GPU; for N > 1 the launch time includes the halo exchange and the exterior pass",
                          "f64": {"achieved": ach[2], "frac": ach[2] / peak, "bytes_per_site": bps[2]},
-                         "f32": {"achieved": ach[1], "frac": ach[1] / peak, "bytes_per_site": bps[1]}},
-            "other_precision_mode": {"mixed_precision": other, "value": CG_FLOP_PER_SITE * V * it_o / (ms_other * 1e-3) / 1e9,
-                                     "unit": "GFLOP/s", "cg_iters": it_o, "cg_time_to_solution_s": ms_other * 1e-3,
-                                     "final_rsq": res_o["final_rsq"]},
+                         "f32": {"achieved": ach[1], "frac": ach[1] / peak, "bytes_per_site": bps[1]},
+                         "16bit": {"achieved": ach[0], "frac": ach[0] / peak, "bytes_per_site": bps[0]}},
+            "other_precision_modes": others,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": 2 * half_bytes * world,
                     "d2h_bytes_per_step": half_bytes * world, "ms_per_step": ms_e2e / args.steps,
@@ -425,9 +436,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mixed", type=int, default=1,
-                    help="0 pure double; 1 (default, BASELINE configs[1] 'mixed-precision CG') double solution and "
-                         "true residuals with single-precision Krylov vectors and reliable updates")
+    ap.add_argument("--mixed", type=int, default=2,
+                    help="0 pure double; 1 double solution and true residuals with single-precision Krylov vectors and "
+                         "reliable updates; 2 (default; BASELINE configs[1] 'mixed-precision CG', north_star 'single- or "
+                         "half-precision inner solve') additionally 16-bit links and search direction in the stencil")
     ap.add_argument("--long-recon", type=int, default=0, help="long-link storage: 18, 14 or 0 = decided on the data")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lattice", type=int, nargs=4, default=None, help="override the lattice (nx ny nz nt)")

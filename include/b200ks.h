@@ -61,7 +61,9 @@ typedef struct {
   int nrestart;        /* max restarts (qic->nrestart)                               */
   double resid;        /* target sqrt(|r|^2/|b|^2), NOT squared (qic->resid)         */
   double relresid;     /* Fermilab relative residual target, 0 = unused              */
-  int mixed_precision; /* 0 pure double; 1 double outer + single inner; 2 + half     */
+  int mixed_precision; /* 0 pure double; 1 double solution/true residuals + single-precision
+                          Krylov vectors (HALF_MIXED); 2 additionally 16-bit links and search
+                          direction in the stencil (MAX_MIXED); both with reliable updates    */
   int check_interval;  /* host convergence poll every n iterations; 0 = default      */
 } b200ks_invert_args;
 
@@ -163,6 +165,8 @@ int b200ks_links_synthetic(b200ks_ctx *ctx, unsigned long long seed, int long_re
 /* Read the device links back in MILC host layout (local sub-lattice). */
 int b200ks_links_download(b200ks_ctx *ctx, void *fat, void *lng, int host_prec);
 
+/* prec = B200KS_PREC_DOUBLE applies the double stencil; SINGLE / HALF apply the stencil the
+ * mixed solvers iterate with to device-converted copies and widen the result. */
 int b200ks_dslash_dev(b200ks_ctx *ctx, int vsrc, int vdest, int parity, int prec);
 int b200ks_congrad_dev(b200ks_ctx *ctx, int vsrc, int vdest, double mass,
                        const b200ks_invert_args *args, b200ks_invert_result *res);

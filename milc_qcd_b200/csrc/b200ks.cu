@@ -19,6 +19,7 @@
 #include "blas.cuh"
 #include "comm.cuh"
 #include "dslash.cuh"
+#include "half.cuh"
 #include "synth.cuh"
 
 using namespace b200ks;
@@ -73,12 +74,13 @@ struct b200ks_ctx {
   size_t bytes = 0;
   void *stage = nullptr;        // persistent host<->device re-layout staging buffer
   size_t stage_bytes = 0;
+  float half_k[3] = {0, 0, 0};  // 16-bit links: scale/32767 of fat components, long rows, long factor
   double long_dev = -1;         // worst misfit of the long links against (scalar x U(3)), -1 = not measured
   unsigned long long *d_dev = nullptr;
   Comm comm;             // one-rank-per-GPU decomposition (nranks == 1: unused)
 };
 
-static size_t real_size(int prec) { return prec == B200KS_PREC_DOUBLE ? 8 : 4; }
+static size_t real_size(int prec) { return prec == B200KS_PREC_DOUBLE ? 8 : prec == B200KS_PREC_SINGLE ? 4 : 2; }
 static int nblocks(int n) { return (n + kBlock - 1) / kBlock; }
 
 static int dev_alloc(b200ks_ctx *c, void **p, size_t bytes) {
@@ -95,7 +97,10 @@ static void dev_free(b200ks_ctx *c, void *p, size_t bytes) {
   }
 }
 
-static size_t vec_bytes(const b200ks_ctx *c, int prec) { return (size_t)3 * c->g.stride * 2 * real_size(prec); }
+// half (prec 0): 4 planes of 32-bit words (3 colours as 2 x u16 + the site scale), half.cuh
+static size_t vec_bytes(const b200ks_ctx *c, int prec) {
+  return prec == B200KS_PREC_HALF ? (size_t)16 * c->g.stride : (size_t)3 * c->g.stride * 2 * real_size(prec);
+}
 static size_t link_bytes(const b200ks_ctx *c, int prec, int nc = 9) { return (size_t)4 * nc * c->g.lstride * 2 * real_size(prec); }
 
 // staging buffer for host<->device re-layout, grown on demand and kept (a cudaMalloc/cudaFree
@@ -468,14 +473,68 @@ extern "C" int b200ks_load_links(b200ks_ctx *c, const void *fat, const void *lng
   return compress_long(c, prec, long_recon);
 }
 
+// 16-bit copy of the master links: one scale per field (fat components, long rows, long factor),
+// the same on every rank so that a ghost link and its owner's copy dequantise identically.
+static int links_quantize(b200ks_ctx *c, int m, int nc) {
+  const Geom &g = c->g;
+  unsigned *d_max = nullptr;
+  CHK(dev_alloc(c, (void **)&d_max, 3 * sizeof(unsigned)));
+  CU(cudaMemsetAsync(d_max, 0, 3 * sizeof(unsigned), c->stream));
+  const int grid = nblocks(g.lstride);
+  for (int p = 0; p < 2; p++) {
+    if (m == 2) {
+      LAUNCH(c, (link_absmax_kernel<double>), grid, (const double2 *)c->links[m].fat[p], g.lstride, g.lstride, 9, 0, 9, d_max + 0);
+      LAUNCH(c, (link_absmax_kernel<double>), grid, (const double2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, 0, nc == 7 ? 6 : 9, d_max + 1);
+      if (nc == 7) LAUNCH(c, (link_absmax_kernel<double>), grid, (const double2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, 6, 7, d_max + 2);
+    } else {
+      LAUNCH(c, (link_absmax_kernel<float>), grid, (const float2 *)c->links[m].fat[p], g.lstride, g.lstride, 9, 0, 9, d_max + 0);
+      LAUNCH(c, (link_absmax_kernel<float>), grid, (const float2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, 0, nc == 7 ? 6 : 9, d_max + 1);
+      if (nc == 7) LAUNCH(c, (link_absmax_kernel<float>), grid, (const float2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, 6, 7, d_max + 2);
+    }
+  }
+  unsigned bits[3];
+  CU(cudaMemcpyAsync(bits, d_max, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  dev_free(c, d_max, 3 * sizeof(unsigned));
+  double mx[3];
+  for (int k = 0; k < 3; k++) {
+    float f;
+    memcpy(&f, &bits[k], sizeof(f));
+    mx[k] = f;
+  }
+  if (c->comm.nranks > 1) {
+    CU(cudaMemcpyAsync(c->d_scal, mx, sizeof(mx), cudaMemcpyHostToDevice, c->stream));
+    NC(nccl().AllReduce(c->d_scal, c->d_scal, 3, ncclDouble, ncclMax, c->comm.red, c->stream));
+    CU(cudaMemcpyAsync(mx, c->d_scal, sizeof(mx), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  float inv[3];
+  for (int k = 0; k < 3; k++) {
+    c->half_k[k] = (float)(mx[k] / 32767.0);
+    inv[k] = mx[k] > 0 ? (float)(32767.0 / mx[k]) : 0.f;
+  }
+  for (int p = 0; p < 2; p++) {
+    if (m == 2) {
+      LAUNCH(c, (quantize_link_kernel<double>), grid, (uint32_t *)c->links[0].fat[p], (const double2 *)c->links[m].fat[p], g.lstride, g.lstride, 9, inv[0], inv[0]);
+      LAUNCH(c, (quantize_link_kernel<double>), grid, (uint32_t *)c->links[0].lng[p], (const double2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, inv[1], inv[2]);
+    } else {
+      LAUNCH(c, (quantize_link_kernel<float>), grid, (uint32_t *)c->links[0].fat[p], (const float2 *)c->links[m].fat[p], g.lstride, g.lstride, 9, inv[0], inv[0]);
+      LAUNCH(c, (quantize_link_kernel<float>), grid, (uint32_t *)c->links[0].lng[p], (const float2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, inv[1], inv[2]);
+    }
+  }
+  CHK(check_launch("quantize_link_kernel"));
+  c->links[0].valid = true;
+  return 0;
+}
+
 // make sure links exist at precision `prec` (device-side down-conversion of the master copy)
 static int links_ensure(b200ks_ctx *c, int prec) {
   if (c->link_master == 0) return fail(B200KS_ESTATE, "links not loaded (call b200ks_load_links first)");
   if (c->links[prec].valid) return 0;
-  if (prec == B200KS_PREC_HALF) return fail(B200KS_EINVAL, "half-precision links not implemented yet");
   const int m = c->link_master;
   const int nc = c->links[m].lng_nc;
   CHK(links_alloc(c, prec, nc));
+  if (prec == B200KS_PREC_HALF) return links_quantize(c, m, nc);
   for (int p = 0; p < 2; p++) {
     for (int which = 0; which < 2; which++) {
       void *d = which ? c->links[prec].lng[p] : c->links[prec].fat[p];
@@ -516,9 +575,8 @@ static char *p2p_ghost(const P2P &pp, char *block, unsigned long long seq) {
 
 // Peer-to-peer exchange `seq`: one push kernel on the (high-priority) comm stream, concurrent
 // with the interior pass.  Returns the ghost buffer the stencil kernels of this exchange read.
-template <typename T>
+template <typename E, int NP, bool kTile>
 static int halo_push(b200ks_ctx *c, const DevVec &in, int pin, const int *stop) {
-  using T2 = typename Vec2<T>::type;
   const Geom &g = c->g;
   Comm &cm = c->comm;
   P2P &pp = cm.p2p;
@@ -541,7 +599,7 @@ static int halo_push(b200ks_ctx *c, const DevVec &in, int pin, const int *stop) 
   CU(cudaEventRecord(cm.ev_ready, c->stream));
   CU(cudaStreamWaitEvent(cm.stream, cm.ev_ready, 0));
   const int pgrid = std::min((n + kPushBlock - 1) / kPushBlock, cm.push_ctas);
-  push_halo_kernel<T><<<pgrid, kPushBlock, 0, cm.stream>>>(a, (const T2 *)in.p[pin], g);
+  push_halo_kernel<E, NP, kTile><<<pgrid, kPushBlock, 0, cm.stream>>>(a, (const E *)in.p[pin], g);
   c->launches++;
   // whatever later overwrites `in` on the compute stream must not overtake the push reading it
   CU(cudaEventRecord(cm.ev_done, cm.stream));
@@ -553,7 +611,7 @@ static int halo_start(b200ks_ctx *c, const DevVec &in, int pin, const int *stop)
   using T2 = typename Vec2<T>::type;
   const Geom &g = c->g;
   Comm &cm = c->comm;
-  if (cm.p2p.on) return halo_push<T>(c, in, pin, stop);
+  if (cm.p2p.on) return halo_push<T2, 3, false>(c, in, pin, stop);
   const T2 *f = (const T2 *)in.p[pin];
   T2 *ghost = (T2 *)cm.ghost[0];
   T2 *zs = (T2 *)cm.zsend;
@@ -652,6 +710,66 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
   a.red = e.red_ext;
   DSLASH_LAUNCH(1, nb_ext);
 #undef DSLASH_LAUNCH
+  return 0;
+}
+
+// 16-bit stencil (half.cuh).  kind 0: out_h (half) = D in.  kind 2: out_f (float) = D in + s*w_h
+// with the three fused dot products against w_h (half) and r (float).
+static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *out_f, int par_out, int kind, double s_,
+                       const DevVec *w_h, const DevVec *r, double *red, const int *stop) {
+  const Links &L = c->links[0];
+  DslashHArg a;
+  memset(&a, 0, sizeof(a));
+  a.g = c->g;
+  a.par = par_out;
+  for (int p = 0; p < 2; p++) {
+    a.L.fat[p] = (const uint32_t *)L.fat[p];
+    a.L.lng[p] = (const uint32_t *)L.lng[p];
+  }
+  a.L.fat_k = c->half_k[0];
+  a.L.lng_k = c->half_k[1];
+  a.L.f_k = c->half_k[2];
+  a.in = (const uint32_t *)in.p[par_out ^ 1];
+  a.out_h = out_h ? (uint32_t *)out_h->p[par_out] : nullptr;
+  a.out_f = out_f ? (float2 *)out_f->p[par_out] : nullptr;
+  a.w_h = w_h ? (const uint32_t *)w_h->p[par_out] : nullptr;
+  a.r = r ? (const float2 *)r->p[par_out] : nullptr;
+  a.s = (float)s_;
+  a.ws = c->ws;
+  a.red = red;
+  a.stop = stop;
+  a.sites = c->comm.ext_sites;
+  a.nsites = c->g.Vh;
+  a.n_int = c->comm.n_int;
+  a.n_ext = c->comm.n_ext;
+  a.nb_int = nblocks(c->comm.n_int);
+  a.halo_timeout = kHaloTimeoutCycles;
+  const bool z7 = L.lng_nc == 7;
+#define DSLASH_H_LAUNCH(kMode, grid_)                                                       \
+  do {                                                                                      \
+    if (z7) {                                                                               \
+      if (kind == 0) LAUNCH(c, (dslash_half_kernel<0, kMode, 7>), grid_, a);                \
+      else LAUNCH(c, (dslash_half_kernel<2, kMode, 7>), grid_, a);                          \
+    } else {                                                                                \
+      if (kind == 0) LAUNCH(c, (dslash_half_kernel<0, kMode, 9>), grid_, a);                \
+      else LAUNCH(c, (dslash_half_kernel<2, kMode, 9>), grid_, a);                          \
+    }                                                                                       \
+  } while (0)
+  if (!c->comm.active) {
+    DSLASH_H_LAUNCH(0, nblocks(c->g.Vh));
+    return 0;
+  }
+  if (!c->comm.p2p.on) return fail(B200KS_ESTATE, "16-bit stencil needs the peer-to-peer halo path");
+  CHK((halo_push<uint32_t, 4, true>(c, in, par_out ^ 1, stop)));
+  P2P &pp = c->comm.p2p;
+  a.gin = (const uint32_t *)p2p_ghost(pp, pp.block, pp.seq);
+  a.halo_flags = p2p_flags(pp.block);
+  a.halo_seq = pp.seq;
+  a.halo_mask = (c->g.part[2] ? 3 : 0) | (c->g.part[3] ? 12 : 0);
+  a.halo_err = pp.err;
+  DSLASH_H_LAUNCH(1, a.nb_int + nblocks(c->comm.n_ext));
+  CU(cudaStreamWaitEvent(c->stream, c->comm.ev_done, 0));
+#undef DSLASH_H_LAUNCH
   return 0;
 }
 
@@ -812,10 +930,35 @@ static int dslash_parity(b200ks_ctx *c, const DevVec &in, DevVec &out, int parit
 extern "C" int b200ks_dslash_dev(b200ks_ctx *c, int vsrc, int vdest, int parity, int prec) {
   DevVec *s = uvec(c, vsrc), *d = uvec(c, vdest);
   if (!s || !d) return B200KS_EINVAL;
-  if (prec != B200KS_PREC_DOUBLE) return fail(B200KS_EINVAL, "b200ks_dslash_dev: user vectors are double");
+  if (prec != B200KS_PREC_DOUBLE && prec != B200KS_PREC_SINGLE && prec != B200KS_PREC_HALF)
+    return fail(B200KS_EINVAL, "b200ks_dslash_dev: unknown precision");
   if (s == d && parity == B200KS_EVENANDODD) return fail(B200KS_EINVAL, "in-place dslash needs a single parity");
   CU(cudaSetDevice(c->device));
-  CHK(dslash_parity(c, *s, *d, parity));
+  if (prec == B200KS_PREC_DOUBLE) {
+    CHK(dslash_parity(c, *s, *d, parity));
+  } else {
+    // user vectors are double: run the low-precision stencil on converted copies (what the
+    // inner iteration of a mixed solve applies) and widen the result
+    DevVec *in = nullptr, *out = nullptr;
+    CHK(pool_get(c, prec, 6, &in));
+    CHK(pool_get(c, prec, 7, &out));
+    CHK(links_ensure(c, prec));
+    const int grid = nblocks(c->g.Vh);
+    for (int pbit = 0; pbit < 2; pbit++) {
+      if (!(parity & (pbit ? B200KS_ODD : B200KS_EVEN))) continue;
+      const int ib = pbit ^ 1;
+      if (prec == 1) {
+        LAUNCH(c, (convert_kernel<float, double>), grid, (float2 *)in->p[ib], (const double2 *)s->p[ib], c->g.stride, c->g.Vh);
+        Epi e;
+        CHK(dslash_T<float>(c, *in, *out, pbit, e));
+        LAUNCH(c, (convert_kernel<double, float>), grid, (double2 *)d->p[pbit], (const float2 *)out->p[pbit], c->g.stride, c->g.Vh);
+      } else {
+        LAUNCH(c, vec_d2h_kernel, grid, (uint32_t *)in->p[ib], (const double2 *)s->p[ib], c->g.stride, c->g.Vh);
+        CHK(dslash_half(c, *in, out, nullptr, pbit, 0, 0.0, nullptr, nullptr, nullptr, nullptr));
+        LAUNCH(c, vec_h2d_kernel, grid, (double2 *)d->p[pbit], (const uint32_t *)out->p[pbit], c->g.stride, c->g.Vh);
+      }
+    }
+  }
   CHK(halo_check(c));
   return check_launch("dslash_kernel");
 }
@@ -836,7 +979,7 @@ extern "C" int b200ks_dslash(b200ks_ctx *c, const void *src, void *dest, int par
 
 extern "C" int b200ks_dslash_time(b200ks_ctx *c, int prec, int parity, int n, double *ms) {
   if (!c || !ms || n <= 0) return fail(B200KS_EINVAL, "b200ks_dslash_time: bad argument");
-  if (prec != 1 && prec != 2) return fail(B200KS_EINVAL, "b200ks_dslash_time: prec must be 1 or 2");
+  if (prec != 0 && prec != 1 && prec != 2) return fail(B200KS_EINVAL, "b200ks_dslash_time: prec must be 0, 1 or 2");
   CU(cudaSetDevice(c->device));
   DevVec *in = nullptr, *out = nullptr;
   CHK(pool_get(c, prec, 0, &in));
@@ -844,9 +987,13 @@ extern "C" int b200ks_dslash_time(b200ks_ctx *c, int prec, int parity, int n, do
   CHK(links_ensure(c, prec));
   Epi e;
   const int pb = parity_bit(parity);
-  for (int k = 0; k < 3; k++) CHK(dslash_any(c, *in, *out, pb, e));
+  auto one = [&]() -> int {
+    if (prec == 0) return dslash_half(c, *in, out, nullptr, pb, 0, 0.0, nullptr, nullptr, nullptr, nullptr);
+    return dslash_any(c, *in, *out, pb, e);
+  };
+  for (int k = 0; k < 3; k++) CHK(one());
   CU(cudaEventRecord(c->ev0, c->stream));
-  for (int k = 0; k < n; k++) CHK(dslash_any(c, *in, *out, pb, e));
+  for (int k = 0; k < n; k++) CHK(one());
   CU(cudaEventRecord(c->ev1, c->stream));
   CU(cudaEventSynchronize(c->ev1));
   float t = 0;
@@ -1002,7 +1149,7 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
 // (d_congrad5_fn_milc.c:177-240); the inner precision is what MILC's HALF_MIXED build asks of the
 // QUDA seam (d_congrad5_fn_gpu.c:104-111).
 static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, const b200ks_invert_args &args,
-                         b200ks_invert_result &res) {
+                         b200ks_invert_result &res, bool half = false, int iter0 = 0, int upd0 = 0) {
   const int pb = parity_bit(args.parity), ob = pb ^ 1;
   const Geom &g = c->g;
   const int grid = nblocks(g.Vh);
@@ -1025,13 +1172,17 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
     CU(cudaStreamSynchronize(c->stream));
     return 0;
   }
-  CHK(links_ensure(c, 1));
-  DevVec *ttt_d, *x_lo, *r_lo, *p_lo, *ttt_lo;
+  CHK(links_ensure(c, half ? 0 : 1));
+  DevVec *ttt_d, *x_lo, *r_lo, *p_lo, *ttt_lo, *p_h = nullptr, *t_h = nullptr;
   CHK(pool_get(c, 2, 2, &ttt_d));
   CHK(pool_get(c, 1, 2, &ttt_lo));
   CHK(pool_get(c, 1, 3, &p_lo));
   CHK(pool_get(c, 1, 4, &r_lo));
   CHK(pool_get(c, 1, 5, &x_lo));
+  if (half) {   // 16-bit search direction and intermediate D p; r, x and A p stay float
+    CHK(pool_get(c, 0, 0, &p_h));
+    CHK(pool_get(c, 0, 1, &t_h));
+  }
   CHK(zero_half(c, *x_lo, pb));
 
   CgState &h = *c->h_state;
@@ -1043,7 +1194,8 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
   h.delta2 = delta * delta;
   h.half_volume = 0.5 * (double)c->global[0] * c->global[1] * c->global[2] * c->global[3];
 
-  int iteration = 0, nupdates = 0;
+  int iteration = iter0, nupdates = upd0, weak = 0;
+  double last_true = -1;
   CU(cudaEventRecord(c->ev0, c->stream));
   for (bool first = true;; first = false) {
     // reliable update = true residual in double
@@ -1052,8 +1204,12 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
     CHK(dslash_T<double>(c, x, *ttt_d, ob, e0));
     e1.kind = 1; e1.s = -msq_x4; e1.w = &x;
     CHK(dslash_T<double>(c, *ttt_d, *ttt_d, pb, e1));
-    LAUNCH(c, mixed_reliable_kernel, grid, (const double2 *)b.p[pb], (const double2 *)ttt_d->p[pb], (float2 *)r_lo->p[pb],
-           (float2 *)p_lo->p[pb], g.stride, g.Vh, first ? 1 : 0, c->ws, c->d_scal);
+    if (half)
+      LAUNCH(c, mixed_reliable_half_kernel, grid, (const double2 *)b.p[pb], (const double2 *)ttt_d->p[pb], (float2 *)r_lo->p[pb],
+             (uint32_t *)p_h->p[pb], g.stride, g.Vh, first ? 1 : 0, c->ws, c->d_scal);
+    else
+      LAUNCH(c, mixed_reliable_kernel, grid, (const double2 *)b.p[pb], (const double2 *)ttt_d->p[pb], (float2 *)r_lo->p[pb],
+             (float2 *)p_lo->p[pb], g.stride, g.Vh, first ? 1 : 0, c->ws, c->d_scal);
     CHK(allreduce(c, c->d_scal, 2));
     CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1064,6 +1220,22 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
     const bool hit = (rsqmin <= 0 || rsqmin > res.final_rsq);
     if (iteration >= max_cg || hit) break;
     nupdates++;
+    if (half) {
+      // 16-bit storage stops paying when a whole reliable cycle no longer halves the true
+      // residual (quantisation error x condition number ~ 1): finish with the single-precision
+      // inner iteration from the solution reached so far
+      weak = (last_true > 0 && rsq > 0.25 * last_true) ? weak + 1 : 0;
+      last_true = rsq;
+      if (weak >= 3) {
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaEventSynchronize(c->ev1));
+        float ms_half = 0;
+        CU(cudaEventElapsedTime(&ms_half, c->ev0, c->ev1));
+        const int it = congrad_mixed(c, b, x, mass, args, res, false, iteration, nupdates);
+        res.device_seconds += ms_half * 1e-3;
+        return it;
+      }
+    }
     h.rsq = rsq;
     h.upd[0] = (multi && c->comm.rank != 0) ? 0.0 : rsq;
     h.upd[1] = 0;
@@ -1074,18 +1246,27 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
     CHK(state_push(c));
     for (;;) {
       for (int k = 0; k < batch; k++) {
-        Epi f0, f1;
-        f0.stop = &c->d_state->stop;
-        CHK(dslash_T<float>(c, *p_lo, *ttt_lo, ob, f0));
-        f1.kind = 2; f1.s = -msq_x4; f1.w = p_lo; f1.r = r_lo; f1.red = c->d_state->red; f1.red_ext = c->d_state->red_ext;
-        f1.stop = &c->d_state->stop;
-        CHK(dslash_T<float>(c, *ttt_lo, *ttt_lo, pb, f1));
+        if (half) {
+          CHK(dslash_half(c, *p_h, t_h, nullptr, ob, 0, 0.0, nullptr, nullptr, nullptr, &c->d_state->stop));
+          CHK(dslash_half(c, *t_h, nullptr, ttt_lo, pb, 2, -msq_x4, p_h, r_lo, c->d_state->red, &c->d_state->stop));
+        } else {
+          Epi f0, f1;
+          f0.stop = &c->d_state->stop;
+          CHK(dslash_T<float>(c, *p_lo, *ttt_lo, ob, f0));
+          f1.kind = 2; f1.s = -msq_x4; f1.w = p_lo; f1.r = r_lo; f1.red = c->d_state->red; f1.red_ext = c->d_state->red_ext;
+          f1.stop = &c->d_state->stop;
+          CHK(dslash_T<float>(c, *ttt_lo, *ttt_lo, pb, f1));
+        }
         if (multi) {
           if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 3);
           CHK(allreduce(c, c->d_state->red, 5));
         }
-        LAUNCH(c, (cg_update_kernel<float, false>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
-               (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws);
+        if (half)
+          LAUNCH(c, cg_update_half_kernel, grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (uint32_t *)p_h->p[pb],
+                 (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws);
+        else
+          LAUNCH(c, (cg_update_kernel<float, false>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
+                 (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws);
         LAUNCH1(c, cg_scalar_kernel, c->d_state, 0, 1);
       }
       CHK(state_pull(c));
@@ -1101,7 +1282,7 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
       g1.kind = 1; g1.s = -msq_x4; g1.w = &x;
       CHK(dslash_T<double>(c, *ttt_d, *ttt_d, pb, g1));
       LAUNCH(c, mixed_reliable_kernel, grid, (const double2 *)b.p[pb], (const double2 *)ttt_d->p[pb], (float2 *)r_lo->p[pb],
-             (float2 *)p_lo->p[pb], g.stride, g.Vh, 1, c->ws, c->d_scal);
+             (float2 *)p_lo->p[pb], g.stride, g.Vh, 1, c->ws, c->d_scal);   // (p_lo is scratch here)
       CHK(allreduce(c, c->d_scal, 2));
       CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       CU(cudaStreamSynchronize(c->stream));
@@ -1131,8 +1312,12 @@ static int check_args(const b200ks_invert_args *a) {
 static int congrad_any(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, const b200ks_invert_args &args,
                        b200ks_invert_result &res) {
   CHK(links_ensure(c, 2));
-  // mixed_precision 2 (down to half) currently runs the single-precision inner solve
-  if (args.mixed_precision != 0 && args.relresid == 0) return congrad_mixed(c, b, x, mass, args, res);
+  // mixed_precision 1: single-precision inner iteration; 2: 16-bit stencil operands (needs
+  // peer-to-peer halos when the lattice is partitioned, else it runs as 1)
+  if (args.mixed_precision != 0 && args.relresid == 0) {
+    const bool half = args.mixed_precision >= 2 && (!c->comm.active || c->comm.p2p.on);
+    return congrad_mixed(c, b, x, mass, args, res, half);
+  }
   return congrad_T<double>(c, b, x, mass, args, res);
 }
 

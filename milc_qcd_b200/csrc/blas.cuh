@@ -137,7 +137,7 @@ cg_update_kernel(typename Vec2<T>::type *x, typename Vec2<T>::type *r, typename 
   const int i = blockIdx.x * kBlock + threadIdx.x;
   double s[2] = {0, 0};
   if (i < n) {
-    double rn = 0, xn = 0;
+    T rn = 0, xn = 0;   // per-site sums in the working precision, summed over sites in double
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       const size_t o = (size_t)c * stride + i;
@@ -152,11 +152,11 @@ cg_update_kernel(typename Vec2<T>::type *x, typename Vec2<T>::type *r, typename 
       x[o] = xv;
       r[o] = rv;
       p[o] = pv;
-      rn += (double)rv.x * rv.x + (double)rv.y * rv.y;
-      if (kRel) xn += (double)xv.x * xv.x + (double)xv.y * xv.y;
+      rn = fma(rv.x, rv.x, fma(rv.y, rv.y, rn));
+      if (kRel) xn = fma(xv.x, xv.x, fma(xv.y, xv.y, xn));
     }
     s[0] = rn;
-    if (kRel) s[1] = (xn == 0) ? 1.0 : rn / xn;
+    if (kRel) s[1] = (xn == 0) ? 1.0 : (double)rn / (double)xn;
   }
   // safe although other CTAs read st->upd at their start: the last ticket is taken only
   // after every CTA has passed that read

@@ -215,20 +215,26 @@ __global__ void __launch_bounds__(kBlock) dslash_kernel(const DslashArg<T> a) {
     hop_dir<T, 2, kMode, kNc>(a, idx, c, bnd, acc);
     hop_dir<T, 3, kMode, kNc>(a, idx, c, bnd, acc);
     if (kEpi >= 1) {
+      // per-site sums in the working precision (MILC's su3_rdot / magsq_su3vec return Real),
+      // accumulated over sites in double (d_congrad5_fn_milc.c:210,293)
+      T s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
       for (int q = 0; q < 3; q++) {
         const T2 wv = a.w[(size_t)q * a.g.stride + idx];
         acc[2 * q] = fma(a.s, wv.x, acc[2 * q]);
         acc[2 * q + 1] = fma(a.s, wv.y, acc[2 * q + 1]);
         if (kEpi == 2) {
-          red[0] += (double)wv.x * (double)acc[2 * q] + (double)wv.y * (double)acc[2 * q + 1];
-          red[2] += (double)acc[2 * q] * (double)acc[2 * q] + (double)acc[2 * q + 1] * (double)acc[2 * q + 1];
+          s0 = fma(wv.x, acc[2 * q], fma(wv.y, acc[2 * q + 1], s0));
+          s2 = fma(acc[2 * q], acc[2 * q], fma(acc[2 * q + 1], acc[2 * q + 1], s2));
           if (a.r != nullptr) {
             const T2 rv = a.r[(size_t)q * a.g.stride + idx];
-            red[1] += (double)rv.x * (double)acc[2 * q] + (double)rv.y * (double)acc[2 * q + 1];
+            s1 = fma(rv.x, acc[2 * q], fma(rv.y, acc[2 * q + 1], s1));
           }
         }
       }
+      red[0] = s0;
+      red[1] = s1;
+      red[2] = s2;
     }
 #pragma unroll
     for (int q = 0; q < 3; q++) {
@@ -281,10 +287,12 @@ constexpr int kPushBlock = 256;
 // fire-and-forget, so a CTA keeps issuing until its share is done and pays the NVLink round
 // trip once, at the fence.  (Many short CTAs would each sit in an SM slot for a round trip,
 // starving the concurrent interior stencil CTAs of slots.)
-template <typename T>
+// E = element type of one plane (double2 / float2: 3 colour planes, plane stride = field
+// stride; uint32_t with kTile: the 4 planes of a 16-bit colour vector in the tiled layout
+// [site/32][plane][site%32] of half.cuh), NP = planes.
+template <typename E, int NP, bool kTile>
 __global__ void __launch_bounds__(kPushBlock)
-push_halo_kernel(const PushArg a, const typename Vec2<T>::type *v, const Geom g) {
-  using T2 = typename Vec2<T>::type;
+push_halo_kernel(const PushArg a, const E *v, const Geom g) {
   if (a.stop != nullptr && *a.stop) return;
   const int nz = g.part[2] ? 6 * g.faceh[2] : 0;
   const int nt = g.part[3] ? 6 * g.faceh[3] : 0;
@@ -305,12 +313,21 @@ push_halo_kernel(const PushArg a, const typename Vec2<T>::type *v, const Geom g)
       idx = (t * g.L[2] + (side ? g.L[2] - 3 + slice : slice)) * S2 + rr;
     }
     const int off = (g.ghost[d][side ? 0 : 1] - g.Vh) + slice * g.faceh[d] + within;
-    T2 *dst = (T2 *)a.dst[d - 2][side];
-    T2 x[3];
+    E *dst = (E *)a.dst[d - 2][side];
+    E x[NP];
+    if (kTile) {
+      const E *sp = v + (((unsigned)idx >> 5) * (unsigned)(NP * 32) + ((unsigned)idx & 31u));
+      E *dp = dst + (((unsigned)off >> 5) * (unsigned)(NP * 32) + ((unsigned)off & 31u));
 #pragma unroll
-    for (int c = 0; c < 3; c++) x[c] = v[(size_t)c * g.stride + idx];
+      for (int c = 0; c < NP; c++) x[c] = sp[32 * c];
 #pragma unroll
-    for (int c = 0; c < 3; c++) dst[(size_t)c * g.gstride + off] = x[c];
+      for (int c = 0; c < NP; c++) dp[32 * c] = x[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < NP; c++) x[c] = v[(size_t)c * g.stride + idx];
+#pragma unroll
+      for (int c = 0; c < NP; c++) dst[(size_t)c * g.gstride + off] = x[c];
+    }
   }
   // release: the CTA barrier orders every thread's stores before thread 0's system fence
   // (fence cumulativity), which orders them before the ticket and, in the last CTA, the flags

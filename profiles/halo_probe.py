@@ -12,7 +12,7 @@ from milc_qcd_b200 import api  # noqa: E402
 EVEN = 2
 dims = tuple(int(x) for x in sys.argv[1:5]) if len(sys.argv) >= 5 else (64, 64, 32, 24)
 out = {}
-for force in ("", "t", "zt"):
+for force in ("", "zt"):
     if force:
         os.environ["B200KS_FORCE_PARTITION"] = force
     else:
@@ -22,9 +22,9 @@ for force in ("", "t", "zt"):
     vb, vx = ctx.vec_create(), ctx.vec_create()
     ctx.vec_gaussian(vb, EVEN, 5678)
     row = {"halo_mode": ctx.halo_mode()}
-    for prec in (2, 1):
-        row["dslash_ms_f%d" % (32 * prec)] = ctx.dslash_time(prec, EVEN, 200)
-    for mixed in (0, 1):
+    for prec in (2, 1, 0):
+        row["dslash_ms_f%d" % (32 * prec if prec else 16)] = ctx.dslash_time(prec, EVEN, 200)
+    for mixed in (0, 1, 2):
         ctx.vec_zero(vx, EVEN)
         it, res = ctx.congrad_dev(vb, vx, 0.05, EVEN, 2000, 10, 1e-10, mixed_precision=mixed)
         ctx.vec_zero(vx, EVEN)

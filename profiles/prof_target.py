@@ -14,8 +14,8 @@ ctx.links_synthetic(1234, int(os.environ.get("LONG_RECON", "0")))
 print("long links: %d complex per link, misfit %.2e" % ctx.long_link_info())
 vb, vx = ctx.vec_create(), ctx.vec_create()
 ctx.vec_gaussian(vb, EVEN, 5678)
-for mixed in (1, 0):
+for mixed in (2, 1, 0):
     ctx.vec_zero(vx, EVEN)
-    it, res = ctx.congrad_dev(vb, vx, 0.05, EVEN, 24, 1, 1e-10, mixed_precision=mixed)
+    it, res = ctx.congrad_dev(vb, vx, 0.05, EVEN, 24, 1, 1e-10, mixed_precision=mixed)  # 24 iterations: several launches of every stencil variant
     print("mixed", mixed, "iters", it, "rsq", res["final_rsq"])
 ctx.close()

@@ -74,11 +74,16 @@ def full(path, tag):
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
         m = re.search(r"dslash_kernel<(double|float), (\d), (\d), (\d)>", name)
-        if not m:
+        mh = re.search(r"dslash_half_kernel<(\d), (\d), (\d)>", name)
+        if not m and not mh:
             continue
         tr = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
-        kernels.append({"kernel": name, "prec": 2 if m.group(1) == "double" else 1, "epilogue": int(m.group(2)),
-                        "mode": int(m.group(3)), "long_reals": 2 * int(m.group(4)), "dram_bytes_per_launch": tr,
+        if mh:
+            prec, epi, mode, nc = 0, int(mh.group(1)), int(mh.group(2)), int(mh.group(3))
+        else:
+            prec, epi, mode, nc = (2 if m.group(1) == "double" else 1), int(m.group(2)), int(m.group(3)), int(m.group(4))
+        kernels.append({"kernel": name, "prec": prec, "epilogue": epi,
+                        "mode": mode, "long_reals": 2 * nc, "dram_bytes_per_launch": tr,
                         "dram_bytes_read": val(r, "dram__bytes_read.sum"),
                         "dram_bytes_write": val(r, "dram__bytes_write.sum"),
                         "gpu_time_us": float(r[hdr.index("gpu__time_duration.sum")])})
