@@ -67,6 +67,8 @@ struct b200ks_ctx {
   int max_blocks = 0;
   CgState *d_state = nullptr;
   CgState *h_state = nullptr;   // pinned mirror
+  CgState *h_snap[2] = {nullptr, nullptr};   // pinned snapshots for the pipelined convergence poll
+  cudaEvent_t ev_snap[2] = {nullptr, nullptr};
   double *d_scal = nullptr;     // scratch result slots
   double *h_scal = nullptr;     // pinned
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -221,6 +223,10 @@ static b200ks_ctx *create_common(const int latsize[4], const int local[4], const
   c->d_scal = (double *)p;
   ok = ok && cudaMallocHost(&c->h_state, sizeof(CgState)) == cudaSuccess;
   ok = ok && cudaMallocHost(&c->h_scal, sizeof(double) * 64) == cudaSuccess;
+  for (int k = 0; k < 2; k++) {
+    ok = ok && cudaMallocHost(&c->h_snap[k], sizeof(CgState)) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_snap[k], cudaEventDisableTiming) == cudaSuccess;
+  }
   ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
   if (!ok) {
     if (g_err.empty()) fail(B200KS_ECUDA, "context allocation failed");
@@ -269,6 +275,10 @@ extern "C" void b200ks_destroy(b200ks_ctx *c) {
   cudaFree(c->d_scal);
   if (c->h_state) cudaFreeHost(c->h_state);
   if (c->h_scal) cudaFreeHost(c->h_scal);
+  for (int k = 0; k < 2; k++) {
+    if (c->h_snap[k]) cudaFreeHost(c->h_snap[k]);
+    if (c->ev_snap[k]) cudaEventDestroy(c->ev_snap[k]);
+  }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1015,6 +1025,30 @@ static int state_pull(b200ks_ctx *c) {
   return halo_check(c);
 }
 
+// Runs `one_iteration` in batches until the device raises the stop flag.  The device decides
+// when to stop and every kernel enqueued after that is a no-op, so the host stays one batch
+// ahead of its own convergence poll: batch k+1 is enqueued before the state snapshot taken
+// after batch k is looked at, and the GPU never idles on a host round trip.
+template <typename F>
+static int run_batches(b200ks_ctx *c, int batch, const char *what, F one_iteration) {
+  auto enqueue = [&](int slot) -> int {
+    for (int k = 0; k < batch; k++) CHK(one_iteration());
+    CU(cudaMemcpyAsync(c->h_snap[slot], c->d_state, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev_snap[slot], c->stream));
+    return 0;
+  };
+  int k = 0;
+  CHK(enqueue(0));
+  for (;;) {
+    CHK(enqueue((k + 1) & 1));
+    CU(cudaEventSynchronize(c->ev_snap[k & 1]));
+    if (c->h_snap[k & 1]->stop) break;
+    k++;
+  }
+  CHK(state_pull(c));   // drains the no-op batch still in flight; final state
+  return check_launch(what);
+}
+
 template <typename T>
 static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, const b200ks_invert_args &args,
                      b200ks_invert_result &res) {
@@ -1098,31 +1132,30 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
     }
     // iterate until the device raises the stop flag (restart interval or recursive
     // residual under target), polling once per batch
-    for (;;) {
-      for (int k = 0; k < batch; k++) {
-        Epi e0, e1;
-        e0.stop = &c->d_state->stop;
-        CHK(dslash_T<T>(c, *p, *ttt, ob, e0));
-        e1.kind = 2; e1.s = -msq_x4; e1.w = p; e1.r = r; e1.red = c->d_state->red; e1.red_ext = c->d_state->red_ext;
-        e1.stop = &c->d_state->stop;
-        CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
-        if (multi) {  // one all-reduce per iteration: {pkp, c_tr, c_tt} + last update's |r|^2
-          if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 3);
-          CHK(allreduce(c, c->d_state->red, rel ? 3 : 5));
-        }
-        if (rel)
-          LAUNCH(c, (cg_update_kernel<T, true>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
-                 g.stride, g.Vh, c->d_state, c->ws);
-        else
-          LAUNCH(c, (cg_update_kernel<T, false>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
-                 g.stride, g.Vh, c->d_state, c->ws);
-        if (multi && rel) CHK(allreduce(c, c->d_state->upd_next, 2));
+    const int fuse = (multi && rel) ? 0 : (1 | (rel ? 2 : 0) | (prec == 1 ? 4 : 0));
+    CHK(run_batches(c, batch, "cg iterate", [&]() -> int {
+      Epi e0, e1;
+      e0.stop = &c->d_state->stop;
+      CHK(dslash_T<T>(c, *p, *ttt, ob, e0));
+      e1.kind = 2; e1.s = -msq_x4; e1.w = p; e1.r = r; e1.red = c->d_state->red; e1.red_ext = c->d_state->red_ext;
+      e1.stop = &c->d_state->stop;
+      CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
+      if (multi) {  // one all-reduce per iteration: {pkp, c_tr, c_tt} + last update's |r|^2
+        if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 3);
+        CHK(allreduce(c, c->d_state->red, rel ? 3 : 5));
+      }
+      if (rel)
+        LAUNCH(c, (cg_update_kernel<T, true>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
+               g.stride, g.Vh, c->d_state, c->ws, fuse);
+      else
+        LAUNCH(c, (cg_update_kernel<T, false>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
+               g.stride, g.Vh, c->d_state, c->ws, fuse);
+      if (!fuse) {   // the relative residual needs its own all-reduce before the scalar step
+        CHK(allreduce(c, c->d_state->upd_next, 2));
         LAUNCH1(c, cg_scalar_kernel, c->d_state, rel ? 1 : 0, prec == 1 ? 1 : 0);
       }
-      CHK(state_pull(c));
-      CHK(check_launch("cg iterate"));
-      if (h.stop) break;
-    }
+      return 0;
+    }));
     iteration = h.iter;
     res.size_r = h.size_r;
     res.size_relr = h.size_relr;
@@ -1244,35 +1277,30 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
     h.iter = iteration;
     h.stop = 0;
     CHK(state_push(c));
-    for (;;) {
-      for (int k = 0; k < batch; k++) {
-        if (half) {
-          CHK(dslash_half(c, *p_h, t_h, nullptr, ob, 0, 0.0, nullptr, nullptr, nullptr, &c->d_state->stop));
-          CHK(dslash_half(c, *t_h, nullptr, ttt_lo, pb, 2, -msq_x4, p_h, r_lo, c->d_state->red, &c->d_state->stop));
-        } else {
-          Epi f0, f1;
-          f0.stop = &c->d_state->stop;
-          CHK(dslash_T<float>(c, *p_lo, *ttt_lo, ob, f0));
-          f1.kind = 2; f1.s = -msq_x4; f1.w = p_lo; f1.r = r_lo; f1.red = c->d_state->red; f1.red_ext = c->d_state->red_ext;
-          f1.stop = &c->d_state->stop;
-          CHK(dslash_T<float>(c, *ttt_lo, *ttt_lo, pb, f1));
-        }
-        if (multi) {
-          if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 3);
-          CHK(allreduce(c, c->d_state->red, 5));
-        }
-        if (half)
-          LAUNCH(c, cg_update_half_kernel, grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (uint32_t *)p_h->p[pb],
-                 (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws);
-        else
-          LAUNCH(c, (cg_update_kernel<float, false>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
-                 (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws);
-        LAUNCH1(c, cg_scalar_kernel, c->d_state, 0, 1);
+    CHK(run_batches(c, batch, "mixed cg iterate", [&]() -> int {
+      if (half) {
+        CHK(dslash_half(c, *p_h, t_h, nullptr, ob, 0, 0.0, nullptr, nullptr, nullptr, &c->d_state->stop));
+        CHK(dslash_half(c, *t_h, nullptr, ttt_lo, pb, 2, -msq_x4, p_h, r_lo, c->d_state->red, &c->d_state->stop));
+      } else {
+        Epi f0, f1;
+        f0.stop = &c->d_state->stop;
+        CHK(dslash_T<float>(c, *p_lo, *ttt_lo, ob, f0));
+        f1.kind = 2; f1.s = -msq_x4; f1.w = p_lo; f1.r = r_lo; f1.red = c->d_state->red; f1.red_ext = c->d_state->red_ext;
+        f1.stop = &c->d_state->stop;
+        CHK(dslash_T<float>(c, *ttt_lo, *ttt_lo, pb, f1));
       }
-      CHK(state_pull(c));
-      CHK(check_launch("mixed cg iterate"));
-      if (h.stop) break;
-    }
+      if (multi) {
+        if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 3);
+        CHK(allreduce(c, c->d_state->red, 5));
+      }
+      if (half)
+        LAUNCH(c, cg_update_half_kernel, grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (uint32_t *)p_h->p[pb],
+               (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, 1 | 4);
+      else
+        LAUNCH(c, (cg_update_kernel<float, false>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
+               (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, 1 | 4);
+      return 0;
+    }));
     iteration = h.iter;
     res.size_r = h.size_r;
     if (iteration >= max_cg) {  // budget exhausted: one last true residual for the report
@@ -1415,28 +1443,24 @@ static int multicg_T(b200ks_ctx *c, const DevVec &b, DevVec *const *psim, const 
   CHK(state_push(c));
   CU(cudaEventRecord(c->ev0, c->stream));
   DevVec *cgp = pm[j_low];  // cg_p is pm[j_low] (ks_multicg_offset.c:20-24)
-  for (;;) {
-    for (int k = 0; k < batch; k++) {
-      Epi e0, e1;
-      e0.stop = &c->d_state->stop;
-      CHK(dslash_T<T>(c, *cgp, *ttt, ob, e0));
-      e1.kind = 2; e1.s = shift0; e1.w = cgp; e1.r = nullptr; e1.red = c->d_state->red; e1.red_ext = c->d_state->red_ext;
-      e1.stop = &c->d_state->stop;
-      CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
-      if (c->comm.active) {
-        if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 1);
-        CHK(allreduce(c, c->d_state->red, 1));
-      }
-      LAUNCH(c, (ms_resid_kernel<T>), grid, (T2 *)r->p[pb], (const T2 *)ttt->p[pb], g.stride, g.Vh, c->d_state, c->ws);
-      CHK(allreduce(c, &c->d_state->rsq_new, 1));
-      LAUNCH1(c, ms_scalar_kernel, c->d_state);
-      LAUNCH(c, (ms_update_kernel<T>), grid, ptrs, (const T2 *)r->p[pb], g.stride, g.Vh, c->d_state);
-      LAUNCH1(c, ms_scroll_kernel, c->d_state);
+  CHK(run_batches(c, batch, "multicg iterate", [&]() -> int {
+    Epi e0, e1;
+    e0.stop = &c->d_state->stop;
+    CHK(dslash_T<T>(c, *cgp, *ttt, ob, e0));
+    e1.kind = 2; e1.s = shift0; e1.w = cgp; e1.r = nullptr; e1.red = c->d_state->red; e1.red_ext = c->d_state->red_ext;
+    e1.stop = &c->d_state->stop;
+    CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
+    if (c->comm.active) {
+      if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 1);
+      CHK(allreduce(c, c->d_state->red, 1));
     }
-    CHK(state_pull(c));
-    CHK(check_launch("multicg iterate"));
-    if (h.stop) break;
-  }
+    LAUNCH(c, (ms_resid_kernel<T>), grid, (T2 *)r->p[pb], (const T2 *)ttt->p[pb], g.stride, g.Vh, c->d_state, c->ws);
+    CHK(allreduce(c, &c->d_state->rsq_new, 1));
+    LAUNCH1(c, ms_scalar_kernel, c->d_state);
+    LAUNCH(c, (ms_update_kernel<T>), grid, ptrs, (const T2 *)r->p[pb], g.stride, g.Vh, c->d_state);
+    LAUNCH1(c, ms_scroll_kernel, c->d_state);
+    return 0;
+  }));
   CU(cudaEventRecord(c->ev1, c->stream));
   CU(cudaEventSynchronize(c->ev1));
   float ms = 0;

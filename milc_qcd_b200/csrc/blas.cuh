@@ -118,6 +118,33 @@ cg_restart_kernel(const typename Vec2<T>::type *b, const typename Vec2<T>::type 
   grid_reduce<2>(s, ws, out);
 }
 
+// One thread: advance the recurrence after the vector update and decide whether the host has
+// to look (restart interval reached, or recursive residual under the target).
+// Mirrors d_congrad5_fn_milc.c:177-179,310,339,350-354.
+__device__ __forceinline__ void cg_scalar_step(CgState *st, int use_rel, int single) {
+  if (st->stop) { st->stop = 2; return; }
+  const double rsq = st->rsq, oldrsq = st->upd[0];
+  const double a = single ? (double)(float)(-rsq / st->red[0]) : -rsq / st->red[0];
+  const double rsq_new = oldrsq + 2.0 * a * st->red[1] + a * a * st->red[2];
+  // upd_next holds this rank's share; with several GPUs it is summed over ranks together
+  // with the next iteration's red[] (or right away when the relative residual is in use)
+  st->upd[0] = st->upd_next[0];
+  st->upd[1] = st->upd_next[1];
+  st->rsq = rsq_new;
+  st->iter += 1;
+  st->size_r = rsq_new / st->source_norm;
+  if (use_rel) st->size_relr = sqrt(st->upd_next[1] / st->half_volume);
+  const bool hit_r = (st->rsqmin <= 0 || st->rsqmin > st->size_r);
+  const bool hit_rel = (st->relrsqmin <= 0 || st->relrsqmin > st->size_relr);
+  if ((st->iter % st->niter == 0) || (hit_r && hit_rel)) st->stop = 1;
+  // reliable-update trigger for the mixed-precision solver
+  if (st->delta2 > 0) {
+    if (rsq_new > st->maxrr) st->maxrr = rsq_new;
+    if (rsq_new < st->delta2 * st->maxrr) { st->reliable = 1; st->stop = 1; }
+  }
+}
+__global__ void cg_scalar_kernel(CgState *st, int use_rel, int single) { cg_scalar_step(st, use_rel, single); }
+
 // One fused update per iteration (the reference's FEWSUMS arithmetic, :301-345,363-367):
 //   a = -rsq/pkp ; rsq' = oldrsq + 2a c_tr + a^2 c_tt ; b = rsq'/oldrsq
 //   x += a p ; r += a ttt ; p = r + b p ; actual' = sum |r|^2 (summed for the NEXT iteration)
@@ -126,7 +153,7 @@ cg_restart_kernel(const typename Vec2<T>::type *b, const typename Vec2<T>::type 
 template <typename T, bool kRel>
 __global__ void __launch_bounds__(kBlock)
 cg_update_kernel(typename Vec2<T>::type *x, typename Vec2<T>::type *r, typename Vec2<T>::type *p,
-                 const typename Vec2<T>::type *ttt, int stride, int n, CgState *st, ReduceWs ws) {
+                 const typename Vec2<T>::type *ttt, int stride, int n, CgState *st, ReduceWs ws, int fuse_scalar) {
   using T2 = typename Vec2<T>::type;
   if (st->stop) return;
   const double rsq = st->rsq, oldrsq = st->upd[0];
@@ -159,8 +186,11 @@ cg_update_kernel(typename Vec2<T>::type *x, typename Vec2<T>::type *r, typename 
     if (kRel) s[1] = (xn == 0) ? 1.0 : (double)rn / (double)xn;
   }
   // safe although other CTAs read st->upd at their start: the last ticket is taken only
-  // after every CTA has passed that read
-  grid_reduce<2>(s, ws, st->upd_next);
+  // after every CTA has passed that read.  For the same reason the CTA that writes the totals
+  // can advance the scalar recurrence right away (fuse_scalar: bit 0 on, bit 1 use_rel, bit 2
+  // single) instead of leaving it to a one-thread kernel -- one launch less per iteration.
+  const bool last = grid_reduce<2>(s, ws, st->upd_next);
+  if (last && fuse_scalar && threadIdx.x == 0) cg_scalar_step(st, (fuse_scalar >> 1) & 1, (fuse_scalar >> 2) & 1);
 }
 
 // One thread: advance the recurrence after cg_update_kernel and decide whether the host
@@ -172,28 +202,6 @@ __global__ void combine_red_kernel(CgState *st, int n) {
   for (int k = 0; k < n; k++) st->red[k] += st->red_ext[k];
 }
 
-__global__ void cg_scalar_kernel(CgState *st, int use_rel, int single) {
-  if (st->stop) { st->stop = 2; return; }
-  const double rsq = st->rsq, oldrsq = st->upd[0];
-  const double a = single ? (double)(float)(-rsq / st->red[0]) : -rsq / st->red[0];
-  const double rsq_new = oldrsq + 2.0 * a * st->red[1] + a * a * st->red[2];
-  // upd_next holds this rank's share; with several GPUs it is summed over ranks together
-  // with the next iteration's red[] (or right away when the relative residual is in use)
-  st->upd[0] = st->upd_next[0];
-  st->upd[1] = st->upd_next[1];
-  st->rsq = rsq_new;
-  st->iter += 1;
-  st->size_r = rsq_new / st->source_norm;
-  if (use_rel) st->size_relr = sqrt(st->upd_next[1] / st->half_volume);
-  const bool hit_r = (st->rsqmin <= 0 || st->rsqmin > st->size_r);
-  const bool hit_rel = (st->relrsqmin <= 0 || st->relrsqmin > st->size_relr);
-  if ((st->iter % st->niter == 0) || (hit_r && hit_rel)) st->stop = 1;
-  // reliable-update trigger for the mixed-precision solver
-  if (st->delta2 > 0) {
-    if (rsq_new > st->maxrr) st->maxrr = rsq_new;
-    if (rsq_new < st->delta2 * st->maxrr) { st->reliable = 1; st->stop = 1; }
-  }
-}
 
 // ---- mixed precision: double outer solution, single inner Krylov vectors -----------------------
 // x(double) += x_lo(float) ; x_lo = 0      (before every true-residual evaluation)

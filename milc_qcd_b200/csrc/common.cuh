@@ -151,8 +151,9 @@ struct ReduceWs {
   unsigned int *counter;   // zero-initialised; reset by the last CTA
 };
 
+// Returns true in the CTA that wrote the totals (all of its threads), false elsewhere.
 template <int N>
-__device__ __forceinline__ void grid_reduce(double (&v)[N], const ReduceWs ws, double *out) {
+__device__ __forceinline__ bool grid_reduce(double (&v)[N], const ReduceWs ws, double *out) {
   __shared__ double sm[N][kBlock / 32];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -177,7 +178,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[N], const ReduceWs ws, d
     is_last = (ticket == gridDim.x - 1);
   }
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) return false;
   __threadfence();
 #pragma unroll
   for (int k = 0; k < N; k++) {
@@ -197,6 +198,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[N], const ReduceWs ws, d
     }
   }
   if (threadIdx.x == 0) *ws.counter = 0;
+  return true;
 }
 
 }  // namespace b200ks

@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(kBlock, 6) dslash_half_kernel(const DslashHArg
 
 // x += a p ; r += a ttt ; p = r + b p (re-quantised) ; sum |r|^2.   x, r, ttt float; p half.
 __global__ void __launch_bounds__(kBlock)
-cg_update_half_kernel(float2 *x, float2 *r, uint32_t *p_h, const float2 *ttt, int stride, int n, CgState *st, ReduceWs ws) {
+cg_update_half_kernel(float2 *x, float2 *r, uint32_t *p_h, const float2 *ttt, int stride, int n, CgState *st, ReduceWs ws,
+                      int fuse_scalar) {
   if (st->stop) return;
   const double rsq = st->rsq, oldrsq = st->upd[0];
   const double pkp = st->red[0], c_tr = st->red[1], c_tt = st->red[2];
@@ -295,7 +296,8 @@ cg_update_half_kernel(float2 *x, float2 *r, uint32_t *p_h, const float2 *ttt, in
     store_vec_h(p_h, i, pn);
     s[0] = rn;
   }
-  grid_reduce<2>(s, ws, st->upd_next);
+  const bool last = grid_reduce<2>(s, ws, st->upd_next);
+  if (last && fuse_scalar && threadIdx.x == 0) cg_scalar_step(st, (fuse_scalar >> 1) & 1, (fuse_scalar >> 2) & 1);
 }
 
 // Reliable update with a half search direction (see mixed_reliable_kernel in blas.cuh).
