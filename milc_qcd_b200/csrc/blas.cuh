@@ -40,6 +40,12 @@ struct CgState {
   double delta2;       // reliable-update threshold squared
   int reliable;        // 1 => host must perform a reliable update
   int pad_;
+  // multi-shift: per-shift freeze.  The residual of shift j is zeta_j * r, so once
+  // zeta_j^2 |r|^2 <= freeze * rsqstop the shift is finished and its two vectors drop out of
+  // the update sweep (freeze = 0: never -- the reference iterates every shift to the end,
+  // ks_multicg_offset_gpu.c:138-152 "iterate until breakdown").
+  double freeze;
+  int frozen[kMaxShifts];
 };
 
 // ---- plain reductions --------------------------------------------------------------------
@@ -309,6 +315,9 @@ __global__ void ms_scalar_kernel(CgState *st) {
   st->rsq = rsq_new;
   st->size_r = rsq_new / st->source_norm;
   if (st->rsqstop > 0 && rsq_new <= st->rsqstop) { st->stop = 1; return; }
+  if (st->freeze > 0)
+    for (int j = 0; j < st->n_now; j++)
+      if (j != jl && !st->frozen[j] && st->zeta_ip1[j] * st->zeta_ip1[j] * rsq_new <= st->freeze * st->rsqstop) st->frozen[j] = 2;
   st->alpha[jl] = rsq_new / rsq;
   for (int j = 0; j < st->n_now; j++) {
     if (j == jl) continue;
@@ -323,6 +332,8 @@ __global__ void ms_scalar_kernel(CgState *st) {
 // kernel reads a consistent set).
 __global__ void ms_scroll_kernel(CgState *st) {
   if (st->stop) return;
+  for (int j = 0; j < st->n_now; j++)
+    if (st->frozen[j] == 2) st->frozen[j] = 1;   // its last x update has just been applied
   for (int j = 0; j < st->n_now; j++) {
     st->beta_im1[j] = st->beta_i[j];
     st->zeta_im1[j] = st->zeta_i[j];
@@ -353,6 +364,7 @@ ms_update_kernel(const MsPtrs ptrs, const typename Vec2<T>::type *r, int stride,
   for (int c = 0; c < 3; c++) rv[c] = r[(size_t)c * stride + i];
   const int nn = st->n_now;
   for (int j = 0; j < nn; j++) {
+    if (st->frozen[j] == 1) continue;   // finished shift: x_j is final, pm_j is dead
     const T beta = (T)st->beta_i[j], zeta = (T)st->zeta_ip1[j], alpha = (T)st->alpha[j];
     T2 *x = (T2 *)ptrs.x[j];
     T2 *pm = (T2 *)ptrs.pm[j];

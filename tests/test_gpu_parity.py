@@ -301,6 +301,36 @@ def test_multicg_matches_oracle(api, oracle, dims, nshift):
         assert np.linalg.norm(psim[j][:V // 2] - p_ref[j][:V // 2]) <= 1e-6 * np.linalg.norm(p_ref[j][:V // 2])
 
 
+@pytest.mark.parametrize("mixed", [1, 2])
+def test_mixed_precision_multicg_polishes_every_shift_to_the_double_residual(api, oracle, mixed):
+    """MILC's HALF_MIXED/MAX_MIXED flow (ks_multicg.c:181-208): single-precision multi-shift
+    recurrence, then each shift polished by the mixed single-mass CG until its true (double)
+    residual meets the target.  Same answers as the reference's double multi-shift."""
+    from milc_qcd_b200 import fields as F
+    dims = (8, 8, 8, 12)
+    fat, lng, src = fields_for(dims)
+    V = src.shape[0]
+    b = src.copy()
+    b[V // 2:] = 0
+    offsets = np.roll(F.rhmc_offsets(6, 0.05), 2)
+    resid = 1e-6   # a molecular-dynamics tolerance: tighter targets are routed to the double recurrence
+    ctx = api.Context(dims)
+    ctx.load_links(fat, lng)
+    ps = [np.full_like(b, 3.5) for _ in offsets]   # outputs are overwritten, the guess is ignored
+    it, res = ctx.multicg(b, ps, offsets, EVEN, 3000, 1, resid, mixed_precision=mixed)
+    assert it > 0 and res[0]["final_iters"] < it   # recurrence + polish iterations were counted
+    ito, pso, qo = oracle.multicg(dims, fat, lng, b, offsets, EVEN, 3000, 1, resid)
+    assert all(r["converged"] == 1 and r["final_rsq"] < resid ** 2 for r in res)
+    for j, off in enumerate(offsets):
+        e = np.linalg.norm(ps[j][:V // 2] - pso[j][:V // 2]) / np.linalg.norm(pso[j][:V // 2])
+        assert e <= 10 * resid / off, (j, e)
+        assert np.all(ps[j][V // 2:] == 3.5)
+        t = oracle.dslash(dims, fat, lng, oracle.dslash(dims, fat, lng, ps[j], ODD), EVEN)
+        r = b[:V // 2] - (off * ps[j][:V // 2] - t[:V // 2])
+        assert np.linalg.norm(r) <= 2 * resid * np.linalg.norm(b[:V // 2])
+    ctx.close()
+
+
 def test_golden_reference_vectors(api):
     """Committed outputs of the reference's own compiled CPU path (tests/golden/make_golden.py)."""
     import os
