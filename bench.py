@@ -505,6 +505,82 @@ def run_multishift(args):
     return 0
 
 
+def run_block(args):
+    """--workload block: multi-right-hand-side (block) CG, the ks_congrad_block_parity_gpu /
+    qudaInvertMsrc seam, on the BASELINE configs[1] lattice.  Secondary line: for K = 1..4 sources
+    the K-wide stencil (links loaded once for K colour vectors) and the block solve against K
+    single solves of the same precision mode, device-resident, CUDA events."""
+    import torch
+    from milc_qcd_b200 import api
+    local_rank = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local_rank)
+    dims = tuple(args.lattice) if args.lattice else DIMS
+    V = int(np.prod(dims))
+    ctx = api.Context(dims, device=local_rank)
+    ctx.links_synthetic(1234, args.long_recon)
+    long_reals = 2 * ctx.long_link_info()[0]
+    stream = torch.cuda.ExternalStream(ctx.lib.b200ks_stream(ctx.h))
+    peak, peak_src = measured_peak()
+    kmax = 4
+    vb = [ctx.vec_create() for _ in range(kmax)]
+    vx = [ctx.vec_create() for _ in range(kmax)]
+    for k in range(kmax):
+        ctx.vec_gaussian(vb[k], EVEN, 5678 + 101 * k)
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), out
+
+    stencil = []
+    for prec, w in ((2, 8.0), (1, 4.0)):
+        for k in range(1, kmax + 1):
+            ms = ctx.dslash_block_time(prec, k, EVEN, 50)
+            bytes_launch = w * (8 * 18 + 8 * long_reals + 12 * k) * V / 2
+            stencil.append({"prec": "f64" if prec == 2 else "f32", "nrhs": k, "ms_per_launch": ms,
+                            "gflops": DSLASH_FLOP_PER_SITE * k * V / 2 / (ms * 1e-3) / 1e9,
+                            "algorithmic_bytes_per_launch": bytes_launch,
+                            "achieved_gbs": bytes_launch / (ms * 1e-3) / 1e9,
+                            "frac_of_peak": bytes_launch / (ms * 1e-3) / 1e9 / peak})
+    rows = []
+    for mixed in (0, 1):
+        singles = []
+        for k in range(kmax):
+            ctx.vec_zero(vx[k], EVEN)
+            ms, (it, res) = timed(lambda: ctx.congrad_dev(vb[k], vx[k], MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=mixed))
+            singles.append((ms, it))
+        for k in range(2, kmax + 1):
+            best = None
+            for rep in range(2):
+                for q in range(k):
+                    ctx.vec_zero(vx[q], EVEN)
+                ms, (tot, res) = timed(lambda: ctx.congrad_block_dev(vb[:k], vx[:k], MASS, EVEN, NITER, NRESTART, RESID,
+                                                                     mixed_precision=mixed))
+                if best is None or ms < best[0]:
+                    best = (ms, tot, res)
+            ms, tot, res = best
+            ms_single = sum(t for t, _ in singles[:k])
+            rows.append({"mixed_precision": mixed, "nsrc": k, "seconds": ms * 1e-3, "iterations_total": tot,
+                         "gflops_milc_convention": CG_FLOP_PER_SITE * V * tot / (ms * 1e-3) / 1e9,
+                         "seconds_k_single_solves": ms_single * 1e-3, "iterations_k_single_solves": sum(i for _, i in singles[:k]),
+                         "speedup_vs_single_solves": ms_single / ms,
+                         "worst_final_rsq": max(r["final_rsq"] for r in res), "converged": min(r["converged"] for r in res)})
+    best = max(rows, key=lambda r: r["gflops_milc_convention"])
+    print(json.dumps({"metric": "hisq_block_cg_gflops", "unit": "GFLOP/s", "n_gpus": 1, "higher_is_better": True, "data": "synthetic",
+                      "value": best["gflops_milc_convention"],
+                      "config": {"workload": "HISQ block CG (1..4 sources at once), mass %.2f, resid %g, synthetic random-SU(3) %s"
+                                             % (MASS, RESID, "x".join(map(str, dims))),
+                                 "lattice": list(dims), "flop_convention": "MILC 1187 flop/site/iteration/source"},
+                      "stencil": stencil, "rows": rows, "peak_gbs": peak, "peak_source": peak_src,
+                      "device_bytes": ctx.device_bytes()}))
+    ctx.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -518,13 +594,16 @@ def main():
     ap.add_argument("--long-recon", type=int, default=0, help="long-link storage: 18, 14 or 0 = decided on the data")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lattice", type=int, nargs=4, default=None, help="override the lattice (nx ny nz nt)")
-    ap.add_argument("--workload", default="cg", choices=["cg", "multishift"],
-                    help="cg (default, the driver's line): single-mass CG; multishift: BASELINE configs[2]")
+    ap.add_argument("--workload", default="cg", choices=["cg", "multishift", "block"],
+                    help="cg (default, the driver's line): single-mass CG; multishift: BASELINE configs[2]; "
+                         "block: multi-right-hand-side CG (ks_congrad_block_parity seam)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "multishift":
         return run_multishift(args)
+    if args.workload == "block":
+        return run_block(args)
     return run_b200(args)
 
 

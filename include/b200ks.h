@@ -140,6 +140,22 @@ int b200ks_dslash(b200ks_ctx *ctx, const void *src, void *dest, int parity, int 
 int b200ks_congrad(b200ks_ctx *ctx, const void *src, void *dest, double mass,
                    const b200ks_invert_args *args, b200ks_invert_result *res, int host_prec);
 
+/* Block (multi-right-hand-side) single-mass CG: nsrc independent systems
+ * (4 m^2 - D D) dest[k] = src[k] with one mass and one set of links, solved K <= 4 at a time
+ * by a stencil that loads every link once for the K colour vectors (link traffic per
+ * right-hand side / K).  Replaces ks_congrad_block_parity_gpu / qudaInvertMsrc
+ * (generic_ks/d_congrad5_fn_gpu.c:175-312); the CPU reference is a loop of single solves
+ * (generic_ks/d_congrad5_fn_milc.c:409-417).  Per right-hand side the result is that of
+ * b200ks_congrad: with mixed_precision 0 the same arithmetic, iteration counts and restarts
+ * (a right-hand side that stops early idles until the others have); with mixed_precision != 0
+ * single-precision Krylov vectors with joint reliable updates.  res has nsrc entries
+ * (device_seconds = time of the group of <= 4 the source was solved in).  Returns the total
+ * number of iterations like the reference loop.  Partitioned (multi-GPU) contexts and the
+ * Fermilab relative residual run the loop. */
+int b200ks_congrad_block(b200ks_ctx *ctx, int nsrc, const void *const *src, void *const *dest,
+                         double mass, const b200ks_invert_args *args, b200ks_invert_result *res,
+                         int host_prec);
+
 /* Multi-shift CG: (offset_j - D D) psim[j] = src for all j.  psim[j] are zeroed first.
  * Replaces ks_multicg_offset_field_gpu / qudaMultishiftInvert
  * (generic_ks/ks_multicg_offset_gpu.c:38-252) with the CPU algorithm's semantics
@@ -173,6 +189,15 @@ int b200ks_congrad_dev(b200ks_ctx *ctx, int vsrc, int vdest, double mass,
 int b200ks_multicg_dev(b200ks_ctx *ctx, int vsrc, const int *vpsim, const double *offsets,
                        int num_offsets, const b200ks_invert_args *args,
                        b200ks_invert_result *res);
+
+int b200ks_congrad_block_dev(b200ks_ctx *ctx, int nsrc, const int *vsrc, const int *vdest, double mass,
+                             const b200ks_invert_args *args, b200ks_invert_result *res);
+/* D applied to nrhs (1..4) device vectors in one pass (prec DOUBLE or SINGLE), and its timing
+ * probe (milliseconds per launch of the nrhs-wide stencil). */
+int b200ks_dslash_block_dev(b200ks_ctx *ctx, int nrhs, const int *vsrc, const int *vdest, int parity,
+                            int prec);
+int b200ks_dslash_block_time(b200ks_ctx *ctx, int prec, int nrhs, int parity, int n,
+                             double *ms_per_launch);
 
 /* Times n back-to-back dslash launches (one parity) with CUDA events on the library's
  * stream; returns milliseconds per launch in *ms_per_launch. */

@@ -56,6 +56,12 @@ SYMBOLS = [
                                      C.POINTER(InvertResult)]),
     ("b200ks_multicg_dev", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double),
                                      C.c_int, C.POINTER(InvertArgs), C.POINTER(InvertResult)]),
+    ("b200ks_congrad_block", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double,
+                                       C.POINTER(InvertArgs), C.POINTER(InvertResult), C.c_int]),
+    ("b200ks_congrad_block_dev", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_double,
+                                           C.POINTER(InvertArgs), C.POINTER(InvertResult)]),
+    ("b200ks_dslash_block_dev", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int]),
+    ("b200ks_dslash_block_time", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("b200ks_dslash_time", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("b200ks_halo_mode", C.c_int, [C.c_void_p]),
     ("b200ks_launch_count", C.c_longlong, [C.c_void_p]),

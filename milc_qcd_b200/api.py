@@ -7,6 +7,7 @@ The names, argument meaning and outputs follow MILC's solver API for this path
 * :func:`ks_congrad_parity_gpu`      <- ``ks_congrad_parity_gpu(src, dest, qic, mass, fn)``
 * :func:`ks_congrad_field`           <- ``ks_congrad_field`` (EVEN / ODD / EVENANDODD fan-out,
   ``generic_ks/d_congrad5_fn.c:16-60``)
+* :func:`ks_congrad_block_parity_gpu` <- ``ks_congrad_block_parity_gpu(nsrc, src[], dest[], qic, mass, fn)``
 * :func:`ks_multicg_offset_field_gpu` <- ``ks_multicg_offset_field_gpu(src, psim, ksp, n, qic, fn)``
 
 with :class:`quark_invert_control`, :class:`ks_param` and :class:`fn_links_t` mirroring
@@ -151,6 +152,19 @@ class Context:
                                            _host_prec(src)), "b200ks_congrad")
         return it, res.as_dict()
 
+    def congrad_block(self, srcs, dests, mass, parity, max_iter, nrestart, resid, relresid=0.0,
+                      mixed_precision=0, check_interval=0):
+        """b200ks_congrad_block: len(srcs) systems, solved up to four at a time."""
+        n = len(srcs)
+        args = InvertArgs(parity, max_iter, nrestart, resid, relresid, mixed_precision, check_interval)
+        res = (InvertResult * max(n, 1))()
+        sp = (C.c_void_p * max(n, 1))(*[_ptr(a).value for a in srcs])
+        dp = (C.c_void_p * max(n, 1))(*[_ptr(a).value for a in dests])
+        prec = _host_prec(srcs[0]) if n else 2
+        it = check(self.lib.b200ks_congrad_block(self.h, n, sp, dp, mass, C.byref(args), res, prec),
+                   "b200ks_congrad_block")
+        return it, [res[j].as_dict() for j in range(n)]
+
     def multicg(self, src, psim, offsets, parity, max_iter, nrestart, resid, mixed_precision=0,
                 check_interval=0):
         n = len(offsets)
@@ -194,6 +208,28 @@ class Context:
         it = check(self.lib.b200ks_congrad_dev(self.h, vsrc, vdest, mass, C.byref(args), C.byref(res)),
                    "b200ks_congrad_dev")
         return it, res.as_dict()
+
+    def congrad_block_dev(self, vsrcs, vdests, mass, parity, max_iter, nrestart, resid, relresid=0.0,
+                          mixed_precision=0, check_interval=0):
+        n = len(vsrcs)
+        args = InvertArgs(parity, max_iter, nrestart, resid, relresid, mixed_precision, check_interval)
+        res = (InvertResult * max(n, 1))()
+        vs = (C.c_int * max(n, 1))(*vsrcs)
+        vd = (C.c_int * max(n, 1))(*vdests)
+        it = check(self.lib.b200ks_congrad_block_dev(self.h, n, vs, vd, mass, C.byref(args), res),
+                   "b200ks_congrad_block_dev")
+        return it, [res[j].as_dict() for j in range(n)]
+
+    def dslash_block_dev(self, vsrcs, vdests, parity, prec=2):
+        n = len(vsrcs)
+        vs = (C.c_int * n)(*vsrcs)
+        vd = (C.c_int * n)(*vdests)
+        check(self.lib.b200ks_dslash_block_dev(self.h, n, vs, vd, parity, prec), "b200ks_dslash_block_dev")
+
+    def dslash_block_time(self, prec, nrhs, parity, n):
+        out = C.c_double()
+        check(self.lib.b200ks_dslash_block_time(self.h, prec, nrhs, parity, n, C.byref(out)), "b200ks_dslash_block_time")
+        return out.value
 
     def multicg_dev(self, vsrc, vpsim, offsets, parity, max_iter, nrestart, resid, mixed_precision=0,
                     check_interval=0):
@@ -287,6 +323,24 @@ def ks_congrad_parity_gpu(t_src, t_dest, qic, mass, fn):
     it, res = ctx.congrad(t_src, t_dest, mass, qic.parity, qic.max, qic.nrestart, qic.resid, qic.relresid,
                           qic.mixed_precision)
     _store(qic, res)
+    return it
+
+
+def ks_congrad_block_parity_gpu(nsrc, t_src, t_dest, qic, mass, fn):
+    """generic_ks/d_congrad5_fn_gpu.c:175-312 (the CPU reference is a loop of single solves,
+    generic_ks/d_congrad5_fn_milc.c:409-417).  Returns the total iterations; qic reports the
+    worst right-hand side, as the QUDA glue does with the one residual it gets back."""
+    if fn is None:
+        raise ValueError("ks_congrad_block_parity_gpu: Called with NULL fn")
+    if qic.parity not in (EVEN, ODD):
+        raise ValueError("ks_congrad_block_parity_gpu: Unrecognised parity")
+    ctx = _context_for(fn)
+    it, res = ctx.congrad_block(t_src[:nsrc], t_dest[:nsrc], mass, qic.parity, qic.max, qic.nrestart, qic.resid,
+                                qic.relresid, qic.mixed_precision)
+    if res:
+        worst = max(res, key=lambda r: r["final_rsq"])
+        _store(qic, dict(worst, final_iters=it, converged=int(all(r["converged"] for r in res)),
+                         final_restart=max(r["final_restart"] for r in res)))
     return it
 
 

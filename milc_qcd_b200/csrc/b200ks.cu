@@ -20,6 +20,7 @@
 #include "comm.cuh"
 #include "dslash.cuh"
 #include "half.cuh"
+#include "mrhs.cuh"
 #include "synth.cuh"
 
 using namespace b200ks;
@@ -65,9 +66,9 @@ struct b200ks_ctx {
   std::vector<DevVec *> pool[3];  // solver temporaries by precision
   ReduceWs ws;
   int max_blocks = 0;
-  CgState *d_state = nullptr;
-  CgState *h_state = nullptr;   // pinned mirror
-  CgState *h_snap[2] = {nullptr, nullptr};   // pinned snapshots for the pipelined convergence poll
+  CgState *d_state = nullptr;   // kMaxRhs consecutive states; single solves use the first
+  CgState *h_state = nullptr;   // pinned mirror (kMaxRhs)
+  CgState *h_snap[2] = {nullptr, nullptr};   // pinned snapshots for the pipelined convergence poll (kMaxRhs each)
   cudaEvent_t ev_snap[2] = {nullptr, nullptr};
   double *d_scal = nullptr;     // scratch result slots
   double *h_scal = nullptr;     // pinned
@@ -212,19 +213,19 @@ static b200ks_ctx *create_common(const int latsize[4], const int local[4], const
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
   c->max_blocks = nblocks(c->g.Vh) + 8;
   void *p = nullptr;
-  ok = ok && dev_alloc(c, &p, sizeof(double) * 4 * c->max_blocks) == 0;
+  ok = ok && dev_alloc(c, &p, sizeof(double) * 4 * kMaxRhs * c->max_blocks) == 0;
   c->ws.partials = (double *)p;
   ok = ok && dev_alloc(c, &p, sizeof(unsigned) * 8) == 0;
   c->ws.counter = (unsigned *)p;
   if (ok) cudaMemset(c->ws.counter, 0, sizeof(unsigned) * 8);
-  ok = ok && dev_alloc(c, &p, sizeof(CgState)) == 0;
+  ok = ok && dev_alloc(c, &p, sizeof(CgState) * kMaxRhs) == 0;
   c->d_state = (CgState *)p;
   ok = ok && dev_alloc(c, &p, sizeof(double) * 64) == 0;
   c->d_scal = (double *)p;
-  ok = ok && cudaMallocHost(&c->h_state, sizeof(CgState)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&c->h_state, sizeof(CgState) * kMaxRhs) == cudaSuccess;
   ok = ok && cudaMallocHost(&c->h_scal, sizeof(double) * 64) == cudaSuccess;
   for (int k = 0; k < 2; k++) {
-    ok = ok && cudaMallocHost(&c->h_snap[k], sizeof(CgState)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_snap[k], sizeof(CgState) * kMaxRhs) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_snap[k], cudaEventDisableTiming) == cudaSuccess;
   }
   ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
@@ -233,7 +234,7 @@ static b200ks_ctx *create_common(const int latsize[4], const int local[4], const
     b200ks_destroy(c);
     return nullptr;
   }
-  memset(c->h_state, 0, sizeof(CgState));
+  memset(c->h_state, 0, sizeof(CgState) * kMaxRhs);
   return c;
 }
 
@@ -1015,12 +1016,12 @@ extern "C" int b200ks_dslash_time(b200ks_ctx *c, int prec, int parity, int n, do
 
 // ---------------------------------------------------------------------------------------------
 // single-mass CG, pure precision T (double for the reference-parity solver)
-static int state_push(b200ks_ctx *c) {
-  CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(CgState), cudaMemcpyHostToDevice, c->stream));
+static int state_push(b200ks_ctx *c, int nst = 1) {
+  CU(cudaMemcpyAsync(c->d_state, c->h_state, sizeof(CgState) * nst, cudaMemcpyHostToDevice, c->stream));
   return 0;
 }
-static int state_pull(b200ks_ctx *c) {
-  CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+static int state_pull(b200ks_ctx *c, int nst = 1) {
+  CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(CgState) * nst, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return halo_check(c);
 }
@@ -1029,11 +1030,12 @@ static int state_pull(b200ks_ctx *c) {
 // when to stop and every kernel enqueued after that is a no-op, so the host stays one batch
 // ahead of its own convergence poll: batch k+1 is enqueued before the state snapshot taken
 // after batch k is looked at, and the GPU never idles on a host round trip.
-template <typename F>
-static int run_batches(b200ks_ctx *c, int batch, const char *what, F one_iteration) {
+// nst solver states are snapshotted; should_stop(snapshot) ends the loop (block solves).
+template <typename F, typename P>
+static int run_batches_n(b200ks_ctx *c, int batch, int nst, const char *what, F one_iteration, P should_stop) {
   auto enqueue = [&](int slot) -> int {
     for (int k = 0; k < batch; k++) CHK(one_iteration());
-    CU(cudaMemcpyAsync(c->h_snap[slot], c->d_state, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_snap[slot], c->d_state, sizeof(CgState) * nst, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev_snap[slot], c->stream));
     return 0;
   };
@@ -1042,11 +1044,15 @@ static int run_batches(b200ks_ctx *c, int batch, const char *what, F one_iterati
   for (;;) {
     CHK(enqueue((k + 1) & 1));
     CU(cudaEventSynchronize(c->ev_snap[k & 1]));
-    if (c->h_snap[k & 1]->stop) break;
+    if (should_stop((const CgState *)c->h_snap[k & 1])) break;
     k++;
   }
-  CHK(state_pull(c));   // drains the no-op batch still in flight; final state
+  CHK(state_pull(c, nst));   // drains the no-op batch still in flight; final state
   return check_launch(what);
+}
+template <typename F>
+static int run_batches(b200ks_ctx *c, int batch, const char *what, F one_iteration) {
+  return run_batches_n(c, batch, 1, what, one_iteration, [](const CgState *s) { return s[0].stop != 0; });
 }
 
 template <typename T>
@@ -1373,6 +1379,475 @@ extern "C" int b200ks_congrad(b200ks_ctx *c, const void *src, void *dest, double
   if (it < 0) return it;
   CHK(download(c, *x, dest, args->parity, host_prec));
   return it;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block (multi-right-hand-side) single-mass CG: mrhs.cuh stencil, K <= kMaxRhs sources per pass.
+// Replaces ks_congrad_block_parity_gpu / qudaInvertMsrc (generic_ks/d_congrad5_fn_gpu.c:175-312);
+// the CPU reference is a loop of single solves (d_congrad5_fn_milc.c:409-417).
+struct MSlot {
+  const DevVec *in = nullptr;
+  DevVec *out = nullptr;
+  const DevVec *w = nullptr, *r = nullptr;
+  double *red = nullptr;
+  const int *stop = nullptr;
+};
+
+template <typename T, int K>
+static int dslash_mrhs_K(b200ks_ctx *c, const MSlot *sl, int par_out, int kind, double s) {
+  using T2 = typename Vec2<T>::type;
+  const int prec = sizeof(T) == 8 ? 2 : 1;
+  const Links &L = c->links[prec];
+  DslashMArg<T, K> a;
+  a.g = c->g;
+  a.par = par_out;
+  a.fat_this = (const T2 *)L.fat[par_out];
+  a.lng_this = (const T2 *)L.lng[par_out];
+  a.fat_other = (const T2 *)L.fat[par_out ^ 1];
+  a.lng_other = (const T2 *)L.lng[par_out ^ 1];
+  for (int k = 0; k < K; k++) {
+    a.in[k] = (const T2 *)sl[k].in->p[par_out ^ 1];
+    a.out[k] = (T2 *)sl[k].out->p[par_out];
+    a.w[k] = sl[k].w ? (const T2 *)sl[k].w->p[par_out] : nullptr;
+    a.r[k] = sl[k].r ? (const T2 *)sl[k].r->p[par_out] : nullptr;
+    a.red[k] = sl[k].red;
+    a.stop[k] = sl[k].stop;
+  }
+  a.s = (T)s;
+  a.ws = c->ws;
+  a.nsites = c->g.Vh;
+  const int grid = nblocks(c->g.Vh);
+  if (L.lng_nc == 7) {
+    if (kind == 0) LAUNCH(c, (dslash_mrhs_kernel<T, 0, K, 7>), grid, a);
+    else LAUNCH(c, (dslash_mrhs_kernel<T, 2, K, 7>), grid, a);
+  } else {
+    if (kind == 0) LAUNCH(c, (dslash_mrhs_kernel<T, 0, K, 9>), grid, a);
+    else LAUNCH(c, (dslash_mrhs_kernel<T, 2, K, 9>), grid, a);
+  }
+  return 0;
+}
+
+// kind 0: out_k = D in_k ; kind 2: out_k = D in_k + s w_k with the three fused dots per slot
+template <typename T>
+static int dslash_mrhs(b200ks_ctx *c, const MSlot *sl, int n, int par_out, int kind, double s) {
+  if (c->comm.active) return fail(B200KS_ESTATE, "multi-right-hand-side stencil: single-GPU contexts only");
+  if (kind != 0 && kind != 2) return fail(B200KS_EINVAL, "dslash_mrhs: kind must be 0 or 2");
+  switch (n) {
+    case 1: {
+      Epi e;
+      e.kind = kind; e.s = s; e.w = sl[0].w; e.r = sl[0].r; e.red = sl[0].red; e.stop = sl[0].stop;
+      return dslash_T<T>(c, *sl[0].in, *sl[0].out, par_out, e);
+    }
+    case 2: return dslash_mrhs_K<T, 2>(c, sl, par_out, kind, s);
+    case 3: return dslash_mrhs_K<T, 3>(c, sl, par_out, kind, s);
+    case 4: return dslash_mrhs_K<T, 4>(c, sl, par_out, kind, s);
+  }
+  return fail(B200KS_EINVAL, "dslash_mrhs: 1..4 right-hand sides per pass");
+}
+
+struct BlockRhs {
+  const DevVec *b = nullptr;
+  DevVec *x = nullptr;
+  DevVec *ttt = nullptr, *p = nullptr, *r = nullptr, *xlo = nullptr;   // pool temporaries of this slot
+  double source_norm = 0;
+  int iteration = 0, nrestart = 0;
+  bool done = false, first = true;
+};
+
+constexpr size_t kBlockPool = 5 + 2 * B200KS_MAX_SHIFTS;   // first pool index of the block solver's temporaries
+
+// Block CG, one precision (T = double is the reference-parity solver).  Every right-hand side
+// runs its own recurrence (own a, b, residuals, restart counter, stop flag) in lockstep with
+// the others; one that raises its stop flag idles until all live ones have, then the true
+// residuals are evaluated together.  Per right-hand side this is the arithmetic of congrad_T
+// -- same iteration counts, same bits.
+template <typename T>
+static int congrad_block_T(b200ks_ctx *c, int n, BlockRhs *rhs, double mass, const b200ks_invert_args &args,
+                           b200ks_invert_result *res) {
+  using T2 = typename Vec2<T>::type;
+  const int prec = sizeof(T) == 8 ? 2 : 1;
+  const int pb = parity_bit(args.parity), ob = pb ^ 1;
+  const Geom &g = c->g;
+  const int grid = nblocks(g.Vh);
+  const int niter = args.max_iter, max_restarts = args.nrestart;
+  const double rsqmin = args.resid * args.resid;
+  const double msq_x4 = 4.0 * mass * mass;
+  const int max_cg = max_restarts * niter;
+  const int batch = args.check_interval > 0 ? args.check_interval : 8;
+  CgState *h = c->h_state;
+  memset(h, 0, sizeof(CgState) * kMaxRhs);
+  for (int k = 0; k < n; k++) {
+    CHK(pool_get(c, prec, kBlockPool + 4 * k + 0, &rhs[k].ttt));
+    CHK(pool_get(c, prec, kBlockPool + 4 * k + 1, &rhs[k].p));
+    CHK(pool_get(c, prec, kBlockPool + 4 * k + 2, &rhs[k].r));
+  }
+  CU(cudaEventRecord(c->ev0, c->stream));
+  for (;;) {
+    // (re)start every live right-hand side from its true residual, d_congrad5_fn_milc.c:177-240
+    int nlive = 0;
+    for (int k = 0; k < n; k++) {
+      if (rhs[k].done) continue;
+      Epi e0, e1;
+      CHK(dslash_T<T>(c, *rhs[k].x, *rhs[k].ttt, ob, e0));
+      e1.kind = 1; e1.s = -msq_x4; e1.w = rhs[k].x;
+      CHK(dslash_T<T>(c, *rhs[k].ttt, *rhs[k].ttt, pb, e1));
+      LAUNCH(c, (cg_restart_kernel<T, false>), grid, (const T2 *)rhs[k].b->p[pb], (const T2 *)rhs[k].ttt->p[pb],
+             (const T2 *)rhs[k].x->p[pb], (T2 *)rhs[k].r->p[pb], (T2 *)rhs[k].p->p[pb], g.stride, g.Vh, c->ws, c->d_scal + 2 * k);
+    }
+    CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * kMaxRhs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CHK(check_launch("block cg restart"));
+    for (int k = 0; k < n; k++) {
+      if (rhs[k].done) { h[k].stop = 2; continue; }
+      const double rsq = c->h_scal[2 * k];
+      res[k].final_rsq = rsq / rhs[k].source_norm;
+      res[k].final_relrsq = 1.0;
+      rhs[k].iteration++;
+      if (rhs[k].iteration >= max_cg || rhs[k].nrestart >= max_restarts || (rsqmin <= 0 || rsqmin > res[k].final_rsq)) {
+        rhs[k].done = true;
+        h[k].stop = 2;
+        continue;
+      }
+      rhs[k].nrestart++;
+      nlive++;
+      h[k].source_norm = rhs[k].source_norm;
+      h[k].rsqmin = rsqmin;
+      h[k].relrsqmin = 0;
+      h[k].size_relr = 1.0;
+      h[k].niter = niter;
+      h[k].half_volume = 0.5 * (double)c->global[0] * c->global[1] * c->global[2] * c->global[3];
+      h[k].rsq = rsq;
+      h[k].upd[0] = rsq;
+      h[k].upd[1] = 0;
+      h[k].iter = rhs[k].iteration;
+      h[k].stop = 0;
+    }
+    if (nlive == 0) break;
+    MSlot s0[kMaxRhs], s1[kMaxRhs];
+    int slot_rhs[kMaxRhs], ns = 0;
+    for (int k = 0; k < n; k++) {
+      if (rhs[k].done) continue;
+      s0[ns].in = rhs[k].p; s0[ns].out = rhs[k].ttt; s0[ns].stop = &c->d_state[k].stop;
+      s1[ns].in = rhs[k].ttt; s1[ns].out = rhs[k].ttt; s1[ns].w = rhs[k].p; s1[ns].r = rhs[k].r;
+      s1[ns].red = c->d_state[k].red; s1[ns].stop = &c->d_state[k].stop;
+      slot_rhs[ns++] = k;
+    }
+    CHK(state_push(c, n));
+    const int fuse = 1 | (prec == 1 ? 4 : 0);
+    CHK(run_batches_n(c, batch, n, "block cg iterate",
+                      [&]() -> int {
+                        CHK(dslash_mrhs<T>(c, s0, ns, ob, 0, 0.0));
+                        CHK(dslash_mrhs<T>(c, s1, ns, pb, 2, -msq_x4));
+                        for (int q = 0; q < ns; q++) {
+                          const int k = slot_rhs[q];
+                          LAUNCH(c, (cg_update_kernel<T, false>), grid, (T2 *)rhs[k].x->p[pb], (T2 *)rhs[k].r->p[pb],
+                                 (T2 *)rhs[k].p->p[pb], (const T2 *)rhs[k].ttt->p[pb], g.stride, g.Vh, c->d_state + k, c->ws, fuse);
+                        }
+                        return 0;
+                      },
+                      [&](const CgState *s) {
+                        for (int q = 0; q < ns; q++)
+                          if (s[slot_rhs[q]].stop == 0) return false;
+                        return true;
+                      }));
+    for (int q = 0; q < ns; q++) {
+      const int k = slot_rhs[q];
+      rhs[k].iteration = h[k].iter;
+      res[k].size_r = h[k].size_r;
+      res[k].size_relr = h[k].size_relr;
+    }
+  }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  int total = 0;
+  for (int k = 0; k < n; k++) {
+    res[k].device_seconds = ms * 1e-3;
+    res[k].final_iters = rhs[k].iteration;
+    res[k].final_restart = rhs[k].nrestart;
+    res[k].converged = (rhs[k].nrestart == max_restarts || rhs[k].iteration == max_cg) ? 0 : 1;
+    total += rhs[k].iteration;
+  }
+  return total;
+}
+
+// Mixed-precision block CG: double solutions and true residuals, single-precision Krylov
+// vectors iterated K at a time (congrad_mixed for K right-hand sides).  As soon as ANY live
+// right-hand side asks for a reliable update (or meets its target, or reaches the restart
+// interval) all of them get one: an early reliable update is harmless, and nobody idles.
+static int congrad_block_mixed(b200ks_ctx *c, int n, BlockRhs *rhs, double mass, const b200ks_invert_args &args,
+                               b200ks_invert_result *res) {
+  const int pb = parity_bit(args.parity), ob = pb ^ 1;
+  const Geom &g = c->g;
+  const int grid = nblocks(g.Vh);
+  const int niter = args.max_iter, max_restarts = args.nrestart;
+  const double rsqmin = args.resid * args.resid;
+  const double msq_x4 = 4.0 * mass * mass;
+  const int max_cg = max_restarts * niter;
+  const int batch = args.check_interval > 0 ? args.check_interval : 8;
+  const double delta = 0.1;
+  CHK(links_ensure(c, 1));
+  DevVec *ttt_d = nullptr;
+  CHK(pool_get(c, 2, 2, &ttt_d));
+  for (int k = 0; k < n; k++) {
+    CHK(pool_get(c, 1, kBlockPool + 4 * k + 0, &rhs[k].ttt));
+    CHK(pool_get(c, 1, kBlockPool + 4 * k + 1, &rhs[k].p));
+    CHK(pool_get(c, 1, kBlockPool + 4 * k + 2, &rhs[k].r));
+    CHK(pool_get(c, 1, kBlockPool + 4 * k + 3, &rhs[k].xlo));
+    CHK(zero_half(c, *rhs[k].xlo, pb));
+  }
+  CgState *h = c->h_state;
+  memset(h, 0, sizeof(CgState) * kMaxRhs);
+  CU(cudaEventRecord(c->ev0, c->stream));
+  for (;;) {
+    // joint reliable update: x += x_lo, r = b - A x in double, p shifted by the correction
+    for (int k = 0; k < n; k++) {
+      if (rhs[k].done) continue;
+      if (!rhs[k].first)
+        LAUNCH(c, mixed_accumulate_kernel, grid, (double2 *)rhs[k].x->p[pb], (float2 *)rhs[k].xlo->p[pb], g.stride, g.Vh);
+      Epi e0, e1;
+      CHK(dslash_T<double>(c, *rhs[k].x, *ttt_d, ob, e0));
+      e1.kind = 1; e1.s = -msq_x4; e1.w = rhs[k].x;
+      CHK(dslash_T<double>(c, *ttt_d, *ttt_d, pb, e1));
+      LAUNCH(c, mixed_reliable_kernel, grid, (const double2 *)rhs[k].b->p[pb], (const double2 *)ttt_d->p[pb],
+             (float2 *)rhs[k].r->p[pb], (float2 *)rhs[k].p->p[pb], g.stride, g.Vh, rhs[k].first ? 1 : 0, c->ws, c->d_scal + 2 * k);
+      rhs[k].first = false;
+    }
+    CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * kMaxRhs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CHK(check_launch("block mixed reliable update"));
+    int nlive = 0;
+    for (int k = 0; k < n; k++) {
+      if (rhs[k].done) { h[k].stop = 2; continue; }
+      const double rsq = c->h_scal[2 * k];
+      res[k].final_rsq = rsq / rhs[k].source_norm;
+      rhs[k].iteration++;
+      if (rhs[k].iteration >= max_cg || (rsqmin <= 0 || rsqmin > res[k].final_rsq)) {
+        rhs[k].done = true;
+        h[k].stop = 2;
+        continue;
+      }
+      rhs[k].nrestart++;
+      nlive++;
+      h[k].source_norm = rhs[k].source_norm;
+      h[k].rsqmin = rsqmin;
+      h[k].relrsqmin = 0;
+      h[k].size_relr = 1.0;
+      h[k].niter = niter;
+      h[k].delta2 = delta * delta;
+      h[k].half_volume = 0.5 * (double)c->global[0] * c->global[1] * c->global[2] * c->global[3];
+      h[k].rsq = rsq;
+      h[k].upd[0] = rsq;
+      h[k].upd[1] = 0;
+      h[k].maxrr = rsq;
+      h[k].reliable = 0;
+      h[k].iter = rhs[k].iteration;
+      h[k].stop = 0;
+    }
+    if (nlive == 0) break;
+    MSlot s0[kMaxRhs], s1[kMaxRhs];
+    int slot_rhs[kMaxRhs], ns = 0;
+    for (int k = 0; k < n; k++) {
+      if (rhs[k].done) continue;
+      s0[ns].in = rhs[k].p; s0[ns].out = rhs[k].ttt; s0[ns].stop = &c->d_state[k].stop;
+      s1[ns].in = rhs[k].ttt; s1[ns].out = rhs[k].ttt; s1[ns].w = rhs[k].p; s1[ns].r = rhs[k].r;
+      s1[ns].red = c->d_state[k].red; s1[ns].stop = &c->d_state[k].stop;
+      slot_rhs[ns++] = k;
+    }
+    CHK(state_push(c, n));
+    CHK(run_batches_n(c, batch, n, "block mixed cg iterate",
+                      [&]() -> int {
+                        CHK(dslash_mrhs<float>(c, s0, ns, ob, 0, 0.0));
+                        CHK(dslash_mrhs<float>(c, s1, ns, pb, 2, -msq_x4));
+                        for (int q = 0; q < ns; q++) {
+                          const int k = slot_rhs[q];
+                          LAUNCH(c, (cg_update_kernel<float, false>), grid, (float2 *)rhs[k].xlo->p[pb], (float2 *)rhs[k].r->p[pb],
+                                 (float2 *)rhs[k].p->p[pb], (const float2 *)rhs[k].ttt->p[pb], g.stride, g.Vh, c->d_state + k, c->ws, 1 | 4);
+                        }
+                        return 0;
+                      },
+                      [&](const CgState *s) {
+                        for (int q = 0; q < ns; q++)
+                          if (s[slot_rhs[q]].stop != 0) return true;
+                        return false;
+                      }));
+    for (int q = 0; q < ns; q++) {
+      const int k = slot_rhs[q];
+      rhs[k].iteration = h[k].iter;
+      res[k].size_r = h[k].size_r;
+    }
+  }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  int total = 0;
+  for (int k = 0; k < n; k++) {
+    res[k].device_seconds = ms * 1e-3;
+    res[k].final_iters = rhs[k].iteration;
+    res[k].final_restart = rhs[k].nrestart;
+    res[k].converged = (rsqmin <= 0 || rsqmin > res[k].final_rsq) ? 1 : 0;
+    total += rhs[k].iteration;
+  }
+  return total;
+}
+
+// Front end: groups of <= kMaxRhs sources.  Zero sources take the reference's shortcut
+// (d_congrad5_fn_milc.c:136-152); a partitioned context or the Fermilab relative residual fall
+// back to the loop the reference's own block solver is.
+static int congrad_block_any(b200ks_ctx *c, int nsrc, DevVec *const *b, DevVec *const *x, double mass,
+                             const b200ks_invert_args &args, b200ks_invert_result *res) {
+  CHK(links_ensure(c, 2));
+  const int pb = parity_bit(args.parity);
+  int total = 0;
+  if (c->comm.active || args.relresid != 0) {
+    for (int k = 0; k < nsrc; k++) {
+      const int it = congrad_any(c, *b[k], *x[k], mass, args, res[k]);
+      if (it < 0) return it;
+      total += it;
+    }
+    return total;
+  }
+  for (int k0 = 0; k0 < nsrc; k0 += kMaxRhs) {
+    BlockRhs rhs[kMaxRhs];
+    b200ks_invert_result *rres[kMaxRhs];
+    b200ks_invert_result gres[kMaxRhs];
+    int n = 0;
+    for (int k = k0; k < nsrc && k < k0 + kMaxRhs; k++) {
+      res[k] = b200ks_invert_result();
+      res[k].converged = 1;
+      res[k].size_relr = 1.0;
+      double sn = 0;
+      CHK(norm2(c, *b[k], pb, &sn));
+      if (sn == 0.0) {
+        CHK(zero_half(c, *x[k], pb));
+        continue;
+      }
+      rhs[n].b = b[k];
+      rhs[n].x = x[k];
+      rhs[n].source_norm = sn;
+      gres[n] = res[k];
+      rres[n++] = &res[k];
+    }
+    if (n == 0) continue;
+    int it;
+    if (n == 1) it = congrad_any(c, *rhs[0].b, *rhs[0].x, mass, args, gres[0]);
+    else if (args.mixed_precision != 0) it = congrad_block_mixed(c, n, rhs, mass, args, gres);
+    else it = congrad_block_T<double>(c, n, rhs, mass, args, gres);
+    if (it < 0) return it;
+    for (int q = 0; q < n; q++) *rres[q] = gres[q];
+    total += it;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return total;
+}
+
+extern "C" int b200ks_congrad_block_dev(b200ks_ctx *c, int nsrc, const int *vsrc, const int *vdest, double mass,
+                                        const b200ks_invert_args *args, b200ks_invert_result *res) {
+  if (!c || !res || nsrc < 0 || (nsrc > 0 && (!vsrc || !vdest))) return fail(B200KS_EINVAL, "b200ks_congrad_block_dev: bad argument");
+  CHK(check_args(args));
+  std::vector<DevVec *> b(nsrc), x(nsrc);
+  for (int k = 0; k < nsrc; k++) {
+    b[k] = uvec(c, vsrc[k]);
+    x[k] = uvec(c, vdest[k]);
+    if (!b[k] || !x[k]) return B200KS_EINVAL;
+    if (b[k] == x[k]) return fail(B200KS_EINVAL, "source and solution must be different fields");
+    for (int j = 0; j < k; j++)
+      if (x[j] == x[k] || x[j] == b[k] || b[j] == x[k]) return fail(B200KS_EINVAL, "block solve: solution fields must be distinct");
+  }
+  CU(cudaSetDevice(c->device));
+  return congrad_block_any(c, nsrc, b.data(), x.data(), mass, *args, res);
+}
+
+extern "C" int b200ks_congrad_block(b200ks_ctx *c, int nsrc, const void *const *src, void *const *dest, double mass,
+                                    const b200ks_invert_args *args, b200ks_invert_result *res, int host_prec) {
+  if (!c || !res || nsrc < 0 || (nsrc > 0 && (!src || !dest))) return fail(B200KS_EINVAL, "b200ks_congrad_block: null argument");
+  CHK(check_args(args));
+  CU(cudaSetDevice(c->device));
+  int total = 0;
+  for (int k0 = 0; k0 < nsrc; k0 += kMaxRhs) {   // host staging vectors are reused group by group
+    const int n = std::min(kMaxRhs, nsrc - k0);
+    DevVec *b[kMaxRhs], *x[kMaxRhs];
+    for (int q = 0; q < n; q++) {
+      if (!src[k0 + q] || !dest[k0 + q]) return fail(B200KS_EINVAL, "b200ks_congrad_block: null field");
+      CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q, &b[q]));
+      CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q + 1, &x[q]));
+      CHK(upload(c, *b[q], src[k0 + q], args->parity, host_prec));
+      CHK(upload(c, *x[q], dest[k0 + q], args->parity, host_prec));
+    }
+    const int it = congrad_block_any(c, n, b, x, mass, *args, res + k0);
+    if (it < 0) return it;
+    for (int q = 0; q < n; q++) CHK(download(c, *x[q], dest[k0 + q], args->parity, host_prec));
+    total += it;
+  }
+  return total;
+}
+
+// D applied to nrhs device vectors at once (double or single stencil on converted copies)
+extern "C" int b200ks_dslash_block_dev(b200ks_ctx *c, int nrhs, const int *vsrc, const int *vdest, int parity, int prec) {
+  if (!c || nrhs < 1 || nrhs > kMaxRhs || !vsrc || !vdest) return fail(B200KS_EINVAL, "b200ks_dslash_block_dev: 1..4 fields");
+  if (prec != B200KS_PREC_DOUBLE && prec != B200KS_PREC_SINGLE) return fail(B200KS_EINVAL, "b200ks_dslash_block_dev: double or single");
+  if (parity != B200KS_EVEN && parity != B200KS_ODD && parity != B200KS_EVENANDODD) return fail(B200KS_EINVAL, "unrecognised parity");
+  CU(cudaSetDevice(c->device));
+  CHK(links_ensure(c, prec));
+  const int grid = nblocks(c->g.Vh);
+  MSlot sl[kMaxRhs];
+  DevVec *s[kMaxRhs], *d[kMaxRhs], *in[kMaxRhs], *out[kMaxRhs];
+  for (int k = 0; k < nrhs; k++) {
+    s[k] = uvec(c, vsrc[k]);
+    d[k] = uvec(c, vdest[k]);
+    if (!s[k] || !d[k]) return B200KS_EINVAL;
+    if (s[k] == d[k] && parity == B200KS_EVENANDODD) return fail(B200KS_EINVAL, "in-place dslash needs a single parity");
+    in[k] = s[k];
+    out[k] = d[k];
+    if (prec == 1) {
+      CHK(pool_get(c, 1, kBlockPool + 4 * k + 0, &in[k]));
+      CHK(pool_get(c, 1, kBlockPool + 4 * k + 1, &out[k]));
+    }
+    sl[k].in = in[k];
+    sl[k].out = out[k];
+  }
+  for (int pbit = 0; pbit < 2; pbit++) {
+    if (!(parity & (pbit ? B200KS_ODD : B200KS_EVEN))) continue;
+    if (prec == 1)
+      for (int k = 0; k < nrhs; k++)
+        LAUNCH(c, (convert_kernel<float, double>), grid, (float2 *)in[k]->p[pbit ^ 1], (const double2 *)s[k]->p[pbit ^ 1], c->g.stride, c->g.Vh);
+    if (prec == 2) CHK(dslash_mrhs<double>(c, sl, nrhs, pbit, 0, 0.0));
+    else CHK(dslash_mrhs<float>(c, sl, nrhs, pbit, 0, 0.0));
+    if (prec == 1)
+      for (int k = 0; k < nrhs; k++)
+        LAUNCH(c, (convert_kernel<double, float>), grid, (double2 *)d[k]->p[pbit], (const float2 *)out[k]->p[pbit], c->g.stride, c->g.Vh);
+  }
+  return check_launch("dslash_mrhs_kernel");
+}
+
+extern "C" int b200ks_dslash_block_time(b200ks_ctx *c, int prec, int nrhs, int parity, int n, double *ms) {
+  if (!c || !ms || n <= 0 || nrhs < 1 || nrhs > kMaxRhs) return fail(B200KS_EINVAL, "b200ks_dslash_block_time: bad argument");
+  if (prec != 1 && prec != 2) return fail(B200KS_EINVAL, "b200ks_dslash_block_time: prec must be 1 or 2");
+  CU(cudaSetDevice(c->device));
+  CHK(links_ensure(c, prec));
+  MSlot sl[kMaxRhs];
+  DevVec *in[kMaxRhs], *out[kMaxRhs];
+  for (int k = 0; k < nrhs; k++) {
+    CHK(pool_get(c, prec, kBlockPool + 4 * k + 0, &in[k]));
+    CHK(pool_get(c, prec, kBlockPool + 4 * k + 1, &out[k]));
+    sl[k].in = in[k];
+    sl[k].out = out[k];
+  }
+  const int pb = parity_bit(parity);
+  auto one = [&]() -> int {
+    return prec == 2 ? dslash_mrhs<double>(c, sl, nrhs, pb, 0, 0.0) : dslash_mrhs<float>(c, sl, nrhs, pb, 0, 0.0);
+  };
+  for (int k = 0; k < 3; k++) CHK(one());
+  CU(cudaEventRecord(c->ev0, c->stream));
+  for (int k = 0; k < n; k++) CHK(one());
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  float t = 0;
+  CU(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+  *ms = (double)t / n;
+  return check_launch("dslash_mrhs_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,187 @@
+// mrhs.cuh -- the fat + Naik stencil applied to K right-hand sides in one pass.
+//
+// The reference's block solver (ks_congrad_block_parity, generic_ks/d_congrad5_fn_milc.c:409-417)
+// is a loop over sources, and so is every multi-source caller above it (the stochastic current
+// estimators, generic_ks/f_meas_current.c:339,417-419,515-519; the three colours of a point
+// source in ks_spectrum).  Each solve streams the same 16 links per site again.  The stencil is
+// HBM-bound and 95 % of its bytes are links (2048 of 2144 per site in double), so applying it to
+// K colour vectors at once divides the link traffic per right-hand side by K:
+//
+//     bytes per site per right-hand side = (8*R_fat + 8*R_long) * w / K + 12 w
+//     double 18/14: 2144 (K=1) -> 1120 (K=2) -> 779 (K=3) -> 608 (K=4)
+//
+// One thread per output site as in dslash.cuh; every link is loaded once into registers and
+// multiplied into the K neighbour vectors.  The arithmetic per right-hand side is the same
+// sequence of fused multiply-adds as dslash_kernel's, and the fused reductions use the same
+// summation tree, so a block solve reproduces K single solves bit for bit.
+//
+// Single GPU (kMode 0) only: a partitioned context runs block solves as a loop.
+#pragma once
+#include "blas.cuh"
+#include "dslash.cuh"
+
+namespace b200ks {
+
+constexpr int kMaxRhs = 4;   // right-hand sides per pass (register budget: 12 accumulators each in double)
+
+template <typename T, int K>
+struct DslashMArg {
+  using T2 = typename Vec2<T>::type;
+  Geom g;
+  int par;              // parity bit of the OUTPUT sites
+  const T2 *fat_this, *lng_this, *fat_other, *lng_other;
+  const T2 *in[K];      // input colour vectors (opposite parity)
+  T2 *out[K];           // outputs (this parity)
+  const T2 *w[K];       // kEpi 2: xpay operands (this parity)
+  const T2 *r[K];       // kEpi 2: second dot operands
+  double *red[K];       // kEpi 2: three reduction slots per right-hand side
+  const int *stop[K];   // per-right-hand-side stop flag (nullptr: always live)
+  T s;
+  ReduceWs ws;          // partials sized for 3*K values per CTA
+  int nsites;
+};
+
+// grid_reduce (common.cuh) with a destination per value; dst(k) == nullptr drops value k.
+// Same summation order per value as grid_reduce, hence the same bits.
+template <int N, typename Dst>
+__device__ __forceinline__ void grid_reduce_to(double (&v)[N], const ReduceWs ws, Dst dst) {
+  __shared__ double sm[N][kBlock / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    double s = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sm[k][warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      double s = 0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; w++) s += sm[k][w];
+      ws.partials[(size_t)blockIdx.x * N + k] = s;
+    }
+    __threadfence();
+    const unsigned ticket = atomicAdd(ws.counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    double s = 0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kBlock) s += __ldcg(&ws.partials[(size_t)b * N + k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if (lane == 0) sm[k][warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; w++) tot += sm[k][w];
+      double *o = dst(k);
+      if (o != nullptr) *o = tot;
+    }
+  }
+  if (threadIdx.x == 0) *ws.counter = 0;
+}
+
+// the four hops of direction D for all K right-hand sides: each link is loaded once
+template <typename T, int D, int K, int kNc>
+__device__ __forceinline__ void hop_dir_m(const DslashMArg<T, K> &a, int idx, const Coord &c, T (&acc)[K][6]) {
+  using T2 = typename Vec2<T>::type;
+  const Geom &g = a.g;
+  T2 U[9], v[3];
+#pragma unroll
+  for (int hop = 0; hop < 4; hop++) {
+    const int h = (hop == 0) ? 1 : (hop == 1) ? 3 : (hop == 2) ? -1 : -3;
+    const bool lng = (hop & 1);
+    const int n = neighbor<D, false>(g, idx, c, h);
+    if (hop < 2) {
+      if (lng) load_long<T, T2, kNc>(a.lng_this, g.lstride, D, idx, U);
+      else load_link<T, T2>(a.fat_this, g.lstride, D, idx, U);
+    } else {
+      if (lng) load_long<T, T2, kNc>(a.lng_other, g.lstride, D, n, U);
+      else load_link<T, T2>(a.fat_other, g.lstride, D, n, U);
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) v[q] = ld_keep(a.in[k] + (size_t)q * g.stride + n);
+      if (hop < 2) mat_vec_add<T, T2>(U, v, acc[k]);
+      else adj_mat_vec_sub<T, T2>(U, v, acc[k]);
+    }
+  }
+}
+
+// kEpi 0: out_k = D in_k.   kEpi 2: out_k = D in_k + s*w_k and red_k = {<w|out>, <out|r>, |out|^2}.
+// A right-hand side whose stop flag is set is computed (no divergence in the hop loop) but
+// neither stored nor reduced; when every flag is set the launch is a no-op.
+// (register caps: double 3 CTAs per SM (<= 168), float 5 (<= 102) or 4 at K = 4 (<= 128), so that
+// enough link loads are in flight per SM)
+template <typename T, int kEpi, int K, int kNc>
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? 3 : (K == 4 ? 4 : 5)) dslash_mrhs_kernel(const DslashMArg<T, K> a) {
+  using T2 = typename Vec2<T>::type;
+  bool live[K];
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    live[k] = (a.stop[k] == nullptr) || (*a.stop[k] == 0);
+    any = any || live[k];
+  }
+  if (!any) return;
+  const int idx = blockIdx.x * kBlock + threadIdx.x;
+  double red[3 * K];
+#pragma unroll
+  for (int j = 0; j < 3 * K; j++) red[j] = 0;
+  if (idx < a.nsites) {
+    const Coord c = site_coord(a.g, idx, a.par);
+    T acc[K][6];
+#pragma unroll
+    for (int k = 0; k < K; k++)
+#pragma unroll
+      for (int j = 0; j < 6; j++) acc[k][j] = 0;
+    hop_dir_m<T, 0, K, kNc>(a, idx, c, acc);
+    hop_dir_m<T, 1, K, kNc>(a, idx, c, acc);
+    hop_dir_m<T, 2, K, kNc>(a, idx, c, acc);
+    hop_dir_m<T, 3, K, kNc>(a, idx, c, acc);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (!live[k]) continue;
+      if (kEpi == 2) {
+        // same per-site arithmetic as dslash_kernel's epilogue (working precision per site,
+        // double over sites; d_congrad5_fn_milc.c:210,293)
+        T s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          const T2 wv = a.w[k][(size_t)q * a.g.stride + idx];
+          acc[k][2 * q] = fma(a.s, wv.x, acc[k][2 * q]);
+          acc[k][2 * q + 1] = fma(a.s, wv.y, acc[k][2 * q + 1]);
+          s0 = fma(wv.x, acc[k][2 * q], fma(wv.y, acc[k][2 * q + 1], s0));
+          s2 = fma(acc[k][2 * q], acc[k][2 * q], fma(acc[k][2 * q + 1], acc[k][2 * q + 1], s2));
+          const T2 rv = a.r[k][(size_t)q * a.g.stride + idx];
+          s1 = fma(rv.x, acc[k][2 * q], fma(rv.y, acc[k][2 * q + 1], s1));
+        }
+        red[3 * k] = s0;
+        red[3 * k + 1] = s1;
+        red[3 * k + 2] = s2;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        T2 o;
+        o.x = acc[k][2 * q];
+        o.y = acc[k][2 * q + 1];
+        a.out[k][(size_t)q * a.g.stride + idx] = o;
+      }
+    }
+  }
+  if (kEpi == 2)
+    grid_reduce_to<3 * K>(red, a.ws, [&](int j) -> double * { return live[j / 3] ? a.red[j / 3] + (j % 3) : nullptr; });
+}
+
+}  // namespace b200ks

@@ -175,22 +175,33 @@ void qudaInvertMsrc(int external_precision, int quda_precision, double mass, Qud
                     double target_residual, double target_fermilab_residual, const void *const fat,
                     const void *const lng, void **sourceArray, void **solutionArray, double *const final_residual,
                     double *const final_fermilab_residual, int *num_iters, int num_src) {
-  // same contract as the reference's block solver, which is a loop over sources
-  // (generic_ks/d_congrad5_fn_milc.c:409-417)
-  int total = 0;
+  // all sources at once through the multi-right-hand-side CG; reports the worst residual and the
+  // total iteration count (what the reference's loop, d_congrad5_fn_milc.c:409-417, returns)
+  static const char where[] = "qudaInvertMsrc";
+  (void)quda_precision;
+  ensure_ctx(where);
+  ensure_links(where, fat, lng, external_precision, num_iters);
+  b200ks_invert_args a;
+  memset(&a, 0, sizeof(a));
+  a.parity = milc_parity(inv_args.evenodd, where);
+  split_iters(inv_args.max_iter, &a);
+  a.resid = target_residual;
+  a.relresid = target_fermilab_residual;
+  a.mixed_precision = inv_args.mixed_precision;
+  std::vector<b200ks_invert_result> r(num_src > 0 ? num_src : 1);
+  const int it = b200ks_congrad_block(S.ctx, num_src, (const void *const *)sourceArray, (void *const *)solutionArray, mass, &a,
+                                      r.data(), external_precision);
+  if (it < 0) die(where);
   double worst = 0, worst_rel = 0;
   for (int k = 0; k < num_src; k++) {
-    int it = (k == 0) ? *num_iters : 0;
-    double fr = 0, frel = 0;
-    qudaInvert(external_precision, quda_precision, mass, inv_args, target_residual, target_fermilab_residual, fat, lng,
-               sourceArray[k], solutionArray[k], &fr, &frel, &it);
-    total += it;
-    if (fr > worst) worst = fr;
-    if (frel > worst_rel) worst_rel = frel;
+    worst = std::max(worst, sqrt(r[k].final_rsq));
+    worst_rel = std::max(worst_rel, r[k].final_relrsq);
   }
   *final_residual = worst;
   *final_fermilab_residual = worst_rel;
-  *num_iters = total;
+  *num_iters = it;
+  if (S.verbosity >= QUDA_VERBOSE)
+    printf("qudaInvertMsrc: %d sources, %d iterations in total, worst true |r|/|b| = %e\n", num_src, it, worst);
 }
 
 void qudaMultishiftInvert(int external_precision, int precision, int num_offsets, double *const offset,

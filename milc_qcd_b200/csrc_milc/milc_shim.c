@@ -159,11 +159,64 @@ int ks_congrad_parity_gpu(su3_vector *t_src, su3_vector *t_dest, quark_invert_co
   return iters;
 }
 
-/* block solver = loop over sources, like the reference (d_congrad5_fn_milc.c:409-417) */
+/* Block solver: all sources go to the multi-right-hand-side CG (b200ks_congrad_block).  The CPU
+ * reference is a loop over sources (d_congrad5_fn_milc.c:409-417); qic reports what the loop
+ * would leave behind where that is well defined (total iterations, converged = all converged)
+ * and the worst residual, like the QUDA glue (d_congrad5_fn_gpu.c:283-296). */
+#define B200KS_MAX_BLOCK 64
 int ks_congrad_block_parity_gpu(int nsrc, su3_vector **t_src, su3_vector **t_dest, quark_invert_control *qic,
                                 Real mass, imp_ferm_links_t *fn) {
-  int iters = 0, i;
-  for (i = 0; i < nsrc; i++) iters += ks_congrad_parity_gpu(t_src[i], t_dest[i], qic, mass, fn);
+  char myname[] = "ks_congrad_block_parity_gpu";
+  b200ks_invert_args a;
+  b200ks_invert_result r[B200KS_MAX_BLOCK];
+  int iters, k;
+
+  qic->size_r = 0;
+  qic->size_relr = 0;
+  qic->final_iters = 0;
+  qic->final_restart = 0;
+  qic->converged = 1;
+  qic->final_rsq = 0.;
+  qic->final_relrsq = 0.;
+  if (nsrc <= 0) return 0;
+  if (nsrc > B200KS_MAX_BLOCK) { /* very wide blocks: in chunks */
+    int done = 0, tot = 0;
+    while (done < nsrc) {
+      int n = nsrc - done < B200KS_MAX_BLOCK ? nsrc - done : B200KS_MAX_BLOCK;
+      tot += ks_congrad_block_parity_gpu(n, t_src + done, t_dest + done, qic, mass, fn);
+      done += n;
+    }
+    return tot;
+  }
+  if (fn == NULL) {
+    printf("%s(0): Called with NULL fn\n", myname);
+    FATAL(1);
+  }
+  if (qic->parity != EVEN && qic->parity != ODD) {
+    printf("%s: Unrecognised parity\n", myname);
+    FATAL(2);
+  }
+  refresh_links(myname, fn);
+  memset(&a, 0, sizeof(a));
+  a.parity = qic->parity;
+  a.max_iter = qic->max;
+  a.nrestart = qic->nrestart;
+  a.resid = qic->resid;
+  a.relresid = qic->relresid;
+  a.mixed_precision = (qic->prec == 1) ? (MIXED ? MIXED : 1) : MIXED;
+  if (MILC_PRECISION == 2 && qic->prec == 2) a.mixed_precision = MIXED;
+  iters = b200ks_congrad_block(context(myname), nsrc, (const void *const *)t_src, (void *const *)t_dest, (double)mass, &a, r,
+                               MILC_PRECISION);
+  if (iters < 0) die(myname);
+  for (k = 0; k < nsrc; k++) {
+    if (r[k].final_rsq > qic->final_rsq) qic->final_rsq = (Real)r[k].final_rsq;
+    if (r[k].final_relrsq > qic->final_relrsq) qic->final_relrsq = (Real)r[k].final_relrsq;
+    if (r[k].size_r > qic->size_r) qic->size_r = (Real)r[k].size_r;
+    if (r[k].final_restart > qic->final_restart) qic->final_restart = r[k].final_restart;
+    if (!r[k].converged) qic->converged = 0;
+  }
+  qic->final_iters = iters;
+  TOTAL_ITERS += iters;
   return iters;
 }
 
