@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200ks.so")
+# B200KS_LIB: load another build of the same library (kernel-variant probes under profiles/)
+LIB_PATH = os.environ.get("B200KS_LIB") or os.path.join(HERE, "libb200ks.so")
 
 EVEN, ODD, EVENANDODD = 2, 1, 3
 PREC_HALF, PREC_SINGLE, PREC_DOUBLE = 0, 1, 2

@@ -197,8 +197,11 @@ __device__ __forceinline__ void hop_pair_h(const DslashHArg &a, int idx, const C
 }
 
 // kEpi 0: out_h = D in.   kEpi 2: out_f = D in + s*w_h, red = {<w|out>, <out|r>, |out|^2}.
+#ifndef B200KS_HALF_MINBLOCKS
+#define B200KS_HALF_MINBLOCKS 6   // CTAs per SM the register allocation is held to (80 registers)
+#endif
 template <int kEpi, int kMode, int kNc>
-__global__ void __launch_bounds__(kBlock, 6) dslash_half_kernel(const DslashHArg a) {
+__global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_kernel(const DslashHArg a) {
   if (a.stop != nullptr && *a.stop) return;
   int k = blockIdx.x * kBlock + threadIdx.x;
   bool active = k < a.nsites;

@@ -1,0 +1,63 @@
+"""Times the 16-bit stencil and the mixed_precision-2 CG for several builds of libb200ks
+(profiles/variants/*.so, built with different -D flags; see profiles/variants/README).  Each
+build runs in its own process (B200KS_LIB selects the library).  Output: one JSON per build.
+
+    python profiles/variant_probe.py            # driver: all variants
+    python profiles/variant_probe.py --one      # worker: the library named by B200KS_LIB
+"""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def one():
+    from milc_qcd_b200 import api
+    dims = (32, 32, 32, 64)
+    ctx = api.Context(dims)
+    ctx.links_synthetic(1234, 0)
+    out = {"lib": os.environ.get("B200KS_LIB", "default")}
+    for prec in (0, 1):
+        ts = [ctx.dslash_time(prec, 2, 100) for _ in range(3)]
+        out["dslash_ms_prec%d" % prec] = min(ts)
+    vb, vx = ctx.vec_create(), ctx.vec_create()
+    ctx.vec_gaussian(vb, 2, 5678)
+    best = None
+    for rep in range(3):
+        ctx.vec_zero(vx, 2)
+        it, res = ctx.congrad_dev(vb, vx, 0.05, 2, 2000, 10, 1e-10, mixed_precision=2)
+        if best is None or res["device_seconds"] < best[1]:
+            best = (it, res["device_seconds"], res["final_rsq"])
+    out["cg_mixed2"] = {"iters": best[0], "seconds": best[1], "final_rsq": best[2]}
+    print("VARIANT " + json.dumps(out))
+    ctx.close()
+
+
+def main():
+    libs = [None] + sorted(glob.glob(os.path.join(ROOT, "profiles", "variants", "*.so")))
+    rows = []
+    for lib in libs:
+        env = dict(os.environ)
+        if lib:
+            env["B200KS_LIB"] = lib
+        else:
+            env.pop("B200KS_LIB", None)
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=env, capture_output=True, text=True,
+                           timeout=300)
+        for line in p.stdout.splitlines():
+            if line.startswith("VARIANT "):
+                rows.append(json.loads(line[8:]))
+        if p.returncode != 0:
+            rows.append({"lib": lib, "error": p.stderr[-400:]})
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "variant_probe.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+    print(json.dumps(rows, indent=1))
+
+
+if __name__ == "__main__":
+    one() if "--one" in sys.argv else main()
