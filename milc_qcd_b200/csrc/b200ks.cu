@@ -307,6 +307,34 @@ static int check_launch(const char *what) {
   return 0;
 }
 
+// second stage of a two-stage reduction (blas.cuh reduce_finish_kernel): one CTA per slot
+static void launch_finish(b200ks_ctx *c, const FinishArg &a, int nslots) {
+  reduce_finish_kernel<<<nslots, kFinishThreads, 0, c->stream>>>(a);
+  c->launches++;
+}
+static FinishSlot finish_slot(const double *partials, int stride, int nval, double *out, CgState *st, const int *stop) {
+  FinishSlot f;
+  f.partials = partials; f.stride = stride; f.nval = nval; f.out = out; f.st = st; f.stop = stop;
+  return f;
+}
+// the stencil's three fused dot products of one right-hand side
+static void finish_dots(b200ks_ctx *c, int nblk, double *red, const int *stop) {
+  FinishArg f;
+  memset(&f, 0, sizeof(f));
+  f.s[0] = finish_slot(c->ws.partials, 3, 3, red, nullptr, stop);
+  f.nblk = nblk;
+  launch_finish(c, f, 1);
+}
+// the update kernel's sums of state `st` + its scalar recurrence (flags as cg_update_kernel's fuse_scalar)
+static void finish_update(b200ks_ctx *c, int nblk, CgState *st, int flags) {
+  FinishArg f;
+  memset(&f, 0, sizeof(f));
+  f.s[0] = finish_slot(c->ws.partials, 2, 2, st->upd_next, st, &st->stop);
+  f.nblk = nblk;
+  f.scalar_flags = flags & 7;
+  launch_finish(c, f, 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // links
 static int links_alloc(b200ks_ctx *c, int prec, int nc) {
@@ -679,6 +707,7 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
   a.halo_mask = 0;
   a.halo_err = nullptr;
   a.halo_timeout = kHaloTimeoutCycles;
+  a.two_stage = (e.kind == 2 && !c->comm.active) ? 1 : 0;
   const int grid = nblocks(c->g.Vh);
   const bool z7 = L.lng_nc == 7;
 #define DSLASH_LAUNCH(kMode, grid_)                                                        \
@@ -695,6 +724,7 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
   } while (0)
   if (!c->comm.active) {
     DSLASH_LAUNCH(0, grid);
+    if (a.two_stage) finish_dots(c, grid, e.red, e.stop);
     return 0;
   }
   const int nb_ext = nblocks(c->comm.n_ext);
@@ -767,7 +797,9 @@ static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *o
     }                                                                                       \
   } while (0)
   if (!c->comm.active) {
+    a.two_stage = kind == 2 ? 1 : 0;
     DSLASH_H_LAUNCH(0, nblocks(c->g.Vh));
+    if (a.two_stage) finish_dots(c, nblocks(c->g.Vh), red, stop);
     return 0;
   }
   if (!c->comm.p2p.on) return fail(B200KS_ESTATE, "16-bit stencil needs the peer-to-peer halo path");
@@ -1138,7 +1170,8 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
     }
     // iterate until the device raises the stop flag (restart interval or recursive
     // residual under target), polling once per batch
-    const int fuse = (multi && rel) ? 0 : (1 | (rel ? 2 : 0) | (prec == 1 ? 4 : 0));
+    // single GPU: two-stage reductions (bit 3), the finish kernel runs the scalar recurrence
+    const int fuse = (multi && rel) ? 0 : (1 | (rel ? 2 : 0) | (prec == 1 ? 4 : 0) | (multi ? 0 : 8));
     CHK(run_batches(c, batch, "cg iterate", [&]() -> int {
       Epi e0, e1;
       e0.stop = &c->d_state->stop;
@@ -1156,6 +1189,7 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
       else
         LAUNCH(c, (cg_update_kernel<T, false>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
                g.stride, g.Vh, c->d_state, c->ws, fuse);
+      if (fuse & 8) finish_update(c, grid, c->d_state, fuse);
       if (!fuse) {   // the relative residual needs its own all-reduce before the scalar step
         CHK(allreduce(c, c->d_state->upd_next, 2));
         LAUNCH1(c, cg_scalar_kernel, c->d_state, rel ? 1 : 0, prec == 1 ? 1 : 0);
@@ -1299,12 +1333,14 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
         if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 3);
         CHK(allreduce(c, c->d_state->red, 5));
       }
+      const int fuse = 1 | 4 | (multi ? 0 : 8);
       if (half)
         LAUNCH(c, cg_update_half_kernel, grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (uint32_t *)p_h->p[pb],
-               (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, 1 | 4);
+               (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse);
       else
         LAUNCH(c, (cg_update_kernel<float, false>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
-               (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, 1 | 4);
+               (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse);
+      if (fuse & 8) finish_update(c, grid, c->d_state, fuse);
       return 0;
     }));
     iteration = h.iter;
@@ -1410,7 +1446,6 @@ static int dslash_mrhs_K(b200ks_ctx *c, const MSlot *sl, int par_out, int kind, 
     a.out[k] = (T2 *)sl[k].out->p[par_out];
     a.w[k] = sl[k].w ? (const T2 *)sl[k].w->p[par_out] : nullptr;
     a.r[k] = sl[k].r ? (const T2 *)sl[k].r->p[par_out] : nullptr;
-    a.red[k] = sl[k].red;
     a.stop[k] = sl[k].stop;
   }
   a.s = (T)s;
@@ -1423,6 +1458,13 @@ static int dslash_mrhs_K(b200ks_ctx *c, const MSlot *sl, int par_out, int kind, 
   } else {
     if (kind == 0) LAUNCH(c, (dslash_mrhs_kernel<T, 0, K, 9>), grid, a);
     else LAUNCH(c, (dslash_mrhs_kernel<T, 2, K, 9>), grid, a);
+  }
+  if (kind == 2) {   // slot k's three sums: values 3k..3k+2 of every CTA's 3K partials
+    FinishArg f;
+    memset(&f, 0, sizeof(f));
+    for (int k = 0; k < K; k++) f.s[k] = finish_slot(c->ws.partials + 3 * k, 3 * K, 3, sl[k].red, nullptr, sl[k].stop);
+    f.nblk = grid;
+    launch_finish(c, f, K);
   }
   return 0;
 }
@@ -1533,16 +1575,24 @@ static int congrad_block_T(b200ks_ctx *c, int n, BlockRhs *rhs, double mass, con
       slot_rhs[ns++] = k;
     }
     CHK(state_push(c, n));
-    const int fuse = 1 | (prec == 1 ? 4 : 0);
+    const int fuse = 1 | (prec == 1 ? 4 : 0) | 8;
     CHK(run_batches_n(c, batch, n, "block cg iterate",
                       [&]() -> int {
                         CHK(dslash_mrhs<T>(c, s0, ns, ob, 0, 0.0));
                         CHK(dslash_mrhs<T>(c, s1, ns, pb, 2, -msq_x4));
-                        for (int q = 0; q < ns; q++) {
+                        FinishArg f;
+                        memset(&f, 0, sizeof(f));
+                        for (int q = 0; q < ns; q++) {   // each update kernel has its own partial-sum region
                           const int k = slot_rhs[q];
+                          ReduceWs wq = c->ws;
+                          wq.partials += (size_t)2 * q * c->max_blocks;
                           LAUNCH(c, (cg_update_kernel<T, false>), grid, (T2 *)rhs[k].x->p[pb], (T2 *)rhs[k].r->p[pb],
-                                 (T2 *)rhs[k].p->p[pb], (const T2 *)rhs[k].ttt->p[pb], g.stride, g.Vh, c->d_state + k, c->ws, fuse);
+                                 (T2 *)rhs[k].p->p[pb], (const T2 *)rhs[k].ttt->p[pb], g.stride, g.Vh, c->d_state + k, wq, fuse);
+                          f.s[q] = finish_slot(wq.partials, 2, 2, c->d_state[k].upd_next, c->d_state + k, &c->d_state[k].stop);
                         }
+                        f.nblk = grid;
+                        f.scalar_flags = fuse & 7;
+                        launch_finish(c, f, ns);
                         return 0;
                       },
                       [&](const CgState *s) {
@@ -1660,11 +1710,19 @@ static int congrad_block_mixed(b200ks_ctx *c, int n, BlockRhs *rhs, double mass,
                       [&]() -> int {
                         CHK(dslash_mrhs<float>(c, s0, ns, ob, 0, 0.0));
                         CHK(dslash_mrhs<float>(c, s1, ns, pb, 2, -msq_x4));
+                        FinishArg f;
+                        memset(&f, 0, sizeof(f));
                         for (int q = 0; q < ns; q++) {
                           const int k = slot_rhs[q];
+                          ReduceWs wq = c->ws;
+                          wq.partials += (size_t)2 * q * c->max_blocks;
                           LAUNCH(c, (cg_update_kernel<float, false>), grid, (float2 *)rhs[k].xlo->p[pb], (float2 *)rhs[k].r->p[pb],
-                                 (float2 *)rhs[k].p->p[pb], (const float2 *)rhs[k].ttt->p[pb], g.stride, g.Vh, c->d_state + k, c->ws, 1 | 4);
+                                 (float2 *)rhs[k].p->p[pb], (const float2 *)rhs[k].ttt->p[pb], g.stride, g.Vh, c->d_state + k, wq, 1 | 4 | 8);
+                          f.s[q] = finish_slot(wq.partials, 2, 2, c->d_state[k].upd_next, c->d_state + k, &c->d_state[k].stop);
                         }
+                        f.nblk = grid;
+                        f.scalar_flags = 1 | 4;
+                        launch_finish(c, f, ns);
                         return 0;
                       },
                       [&](const CgState *s) {

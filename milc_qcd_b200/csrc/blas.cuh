@@ -151,6 +151,64 @@ __device__ __forceinline__ void cg_scalar_step(CgState *st, int use_rel, int sin
 }
 __global__ void cg_scalar_kernel(CgState *st, int use_rel, int single) { cg_scalar_step(st, use_rel, single); }
 
+// Second stage of the two-stage reductions (common.cuh block_partials): CTA j adds up slot j's
+// per-CTA partial sums and, for the update kernel's sums, advances the scalar recurrence.
+// 1024 threads so that the 8192 x 3 partials of a 32^3x64 stencil are one round of loads per
+// thread (the same sum by the last CTA of the producing kernel -- 128 threads, 64 dependent
+// rounds -- cost 10-20 us per launch, which is what the fused kernels lost against their bytes).
+// Fixed order (thread t: CTAs t, t+1024, ...; warp tree; then the 32 warps) => reproducible, and
+// the same bits for a block solve and for single solves.  A stopped solver's launch is a no-op.
+struct FinishSlot {
+  const double *partials;  // value k of CTA b at partials[b * stride + k]
+  int stride, nval;        // nval <= 3
+  double *out;
+  CgState *st;             // scalar step target (scalar_flags != 0)
+  const int *stop;
+};
+struct FinishArg {
+  FinishSlot s[kMaxRhs];
+  int nblk;
+  int scalar_flags;        // 0: sums only; else bit 0 on, bit 1 use_rel, bit 2 single (cg_scalar_step)
+};
+constexpr int kFinishThreads = 1024;
+__global__ void __launch_bounds__(kFinishThreads) reduce_finish_kernel(const FinishArg a) {
+  const FinishSlot &f = a.s[blockIdx.x];
+  if (f.stop != nullptr && *f.stop) return;
+  __shared__ double sm[3][kFinishThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double s[3] = {0, 0, 0};
+  for (int b0 = threadIdx.x; b0 < a.nblk; b0 += 4 * kFinishThreads) {
+    double t[4][3];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int b = b0 + j * kFinishThreads;
+#pragma unroll
+      for (int k = 0; k < 3; k++) t[j][k] = (b < a.nblk && k < f.nval) ? __ldcg(&f.partials[(size_t)b * f.stride + k]) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) s[k] += t[j][k];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if (lane == 0) sm[k][warp] = s[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      double v = sm[k][lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && k < f.nval) f.out[k] = v;
+    }
+    if (a.scalar_flags && lane == 0) cg_scalar_step(f.st, (a.scalar_flags >> 1) & 1, (a.scalar_flags >> 2) & 1);
+  }
+}
+
 // One fused update per iteration (the reference's FEWSUMS arithmetic, :301-345,363-367):
 //   a = -rsq/pkp ; rsq' = oldrsq + 2a c_tr + a^2 c_tt ; b = rsq'/oldrsq
 //   x += a p ; r += a ttt ; p = r + b p ; actual' = sum |r|^2 (summed for the NEXT iteration)
@@ -195,6 +253,10 @@ cg_update_kernel(typename Vec2<T>::type *x, typename Vec2<T>::type *r, typename 
   // after every CTA has passed that read.  For the same reason the CTA that writes the totals
   // can advance the scalar recurrence right away (fuse_scalar: bit 0 on, bit 1 use_rel, bit 2
   // single) instead of leaving it to a one-thread kernel -- one launch less per iteration.
+  if (fuse_scalar & 8) {   // two-stage: reduce_finish_kernel sums the partials and advances the recurrence
+    block_partials<2>(s, ws.partials);
+    return;
+  }
   const bool last = grid_reduce<2>(s, ws, st->upd_next);
   if (last && fuse_scalar && threadIdx.x == 0) cg_scalar_step(st, (fuse_scalar >> 1) & 1, (fuse_scalar >> 2) & 1);
 }

@@ -19,6 +19,7 @@ namespace b200ks {
 
 constexpr int kBlock = 128;           // threads per CTA for site kernels
 constexpr int kMaxShifts = 32;
+constexpr int kMaxRhs = 4;            // right-hand sides per pass of the block solver (mrhs.cuh)
 
 template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
@@ -199,6 +200,32 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[N], const ReduceWs ws, d
   }
   if (threadIdx.x == 0) *ws.counter = 0;
   return true;
+}
+
+// ---- two-stage variant (single-GPU solver loops) ----------------------------------------------
+// grid_reduce's last CTA adds up gridDim.x x N partial sums with 128 threads: 64 dependent rounds
+// of L2 loads at 32^3x64, 10-20 us during which the GPU is otherwise idle (the 16-bit stencil with
+// fused dots ran 13 % slower than its bytes explain, the update kernels 40 %).  Inside the solver
+// loops the CTAs therefore only store their partial sums; a one-CTA, 1024-thread kernel
+// (reduce_finish_kernel, blas.cuh) adds them up in one round and runs the scalar recurrence.
+template <int N>
+__device__ __forceinline__ void block_partials(double (&v)[N], double *partials) {
+  __shared__ double sm[N][kBlock / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    double s = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sm[k][warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; w++) s += sm[threadIdx.x][w];
+    partials[(size_t)blockIdx.x * N + threadIdx.x] = s;
+  }
 }
 
 }  // namespace b200ks

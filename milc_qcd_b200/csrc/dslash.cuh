@@ -66,6 +66,7 @@ struct DslashArg {
   int halo_mask;
   int *halo_err;
   long long halo_timeout;
+  int two_stage;        // kEpi 2: store per-CTA partial sums only (reduce_finish_kernel adds them up)
 };
 
 template <typename T, typename T2>
@@ -244,7 +245,10 @@ __global__ void __launch_bounds__(kBlock) dslash_kernel(const DslashArg<T> a) {
       a.out[(size_t)q * a.g.stride + idx] = o;
     }
   }
-  if (kEpi == 2) grid_reduce<3>(red, a.ws, a.red);
+  if (kEpi == 2) {
+    if (a.two_stage) block_partials<3>(red, a.ws.partials);
+    else grid_reduce<3>(red, a.ws, a.red);
+  }
 }
 
 // z faces are strided in memory (3 z-slices for every t): gather them into a contiguous

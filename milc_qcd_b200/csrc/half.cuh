@@ -99,6 +99,7 @@ struct DslashHArg {
   int halo_mask;
   int *halo_err;
   long long halo_timeout;
+  int two_stage;         // kEpi 2: store per-CTA partial sums only (reduce_finish_kernel adds them up)
 };
 
 // ---- packed fp32 helpers (sm_100 FFMA2 / FADD2 / FMUL2) -------------------------------------------
@@ -122,8 +123,13 @@ __device__ __forceinline__ void hop_pair_h(const DslashHArg &a, int idx, const C
   const int lA = !kBack ? idx : partA ? neighbor<DA, true>(g, idx, c, h) : nA;
   const int lB = !kBack ? idx : partB ? neighbor<DB, true>(g, idx, c, h) : nB;
   const uint32_t *links = kLong ? a.L.lng[kBack ? a.par ^ 1 : a.par] : a.L.fat[kBack ? a.par ^ 1 : a.par];
+#ifdef B200KS_PROBE_NOLINKLOAD   // diagnostic build: every site reads the links of tile 0 (L1-resident) => compute time only
+  const uint32_t *uA = links + (threadIdx.x & 31) + DA * nc * 32;
+  const uint32_t *uB = links + (threadIdx.x & 31) + DB * nc * 32;
+#else
   const uint32_t *uA = links + tile_base(lA, 4 * nc) + DA * nc * 32;
   const uint32_t *uB = links + tile_base(lB, 4 * nc) + DB * nc * 32;
+#endif
 
   const float2 mB = make_float2(-kHalfBias, -kHalfBias), pB = make_float2(kHalfBias, kHalfBias);
   const float2 neg1 = make_float2(-1.f, -1.f);
@@ -147,6 +153,21 @@ __device__ __forceinline__ void hop_pair_h(const DslashHArg &a, int idx, const C
     ure[e] = padd(make_float2(magic_lo(wa), magic_lo(wb)), mB);
     uim[e] = padd(make_float2(magic_hi(wa), magic_hi(wb)), mB);
   }
+#ifdef B200KS_PROBE_NOMATH       // diagnostic build: loads only (same addresses, same order) => memory time only
+  {
+    float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int e = 0; e < nload; e++) sum = padd(sum, padd(ure[e], uim[e]));
+#pragma unroll
+    for (int k = 0; k < 3; k++) sum = padd(sum, padd(vre[k], vim[k]));
+    if (nc == 7) {
+      const uint32_t wa = __ldcs(uA + 32 * 6), wb = __ldcs(uB + 32 * 6);
+      sum = padd(sum, make_float2(magic_lo(wa), magic_lo(wb)));
+    }
+    acc[0] = pfma(make_float2(kvA, kvB), sum, acc[0]);
+    return;
+  }
+#endif
   if (nc == 7) {  // row3 = f * conj(row1 x row2), f brought to the rows' integer grid
     const uint32_t wa = __ldcs(uA + 32 * 6), wb = __ldcs(uB + 32 * 6);
     const float fk = a.L.f_k * a.L.lng_k;
@@ -261,7 +282,10 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
       red[2] = s2;
     }
   }
-  if (kEpi == 2) grid_reduce<3>(red, a.ws, a.red);
+  if (kEpi == 2) {
+    if (a.two_stage) block_partials<3>(red, a.ws.partials);
+    else grid_reduce<3>(red, a.ws, a.red);
+  }
 }
 
 // x += a p ; r += a ttt ; p = r + b p (re-quantised) ; sum |r|^2.   x, r, ttt float; p half.
@@ -298,6 +322,10 @@ cg_update_half_kernel(float2 *x, float2 *r, uint32_t *p_h, const float2 *ttt, in
     }
     store_vec_h(p_h, i, pn);
     s[0] = rn;
+  }
+  if (fuse_scalar & 8) {   // two-stage: reduce_finish_kernel sums the partials and advances the recurrence
+    block_partials<2>(s, ws.partials);
+    return;
   }
   const bool last = grid_reduce<2>(s, ws, st->upd_next);
   if (last && fuse_scalar && threadIdx.x == 0) cg_scalar_step(st, (fuse_scalar >> 1) & 1, (fuse_scalar >> 2) & 1);

@@ -12,8 +12,9 @@
 //
 // One thread per output site as in dslash.cuh; every link is loaded once into registers and
 // multiplied into the K neighbour vectors.  The arithmetic per right-hand side is the same
-// sequence of fused multiply-adds as dslash_kernel's, and the fused reductions use the same
-// summation tree, so a block solve reproduces K single solves bit for bit.
+// sequence of fused multiply-adds as dslash_kernel's, and the fused reductions (two-stage:
+// block_partials + reduce_finish_kernel) use the same summation tree, so a block solve reproduces
+// K single solves bit for bit.
 //
 // Single GPU (kMode 0) only: a partitioned context runs block solves as a loop.
 #pragma once
@@ -22,7 +23,7 @@
 
 namespace b200ks {
 
-constexpr int kMaxRhs = 4;   // right-hand sides per pass (register budget: 12 accumulators each in double)
+// kMaxRhs = 4 right-hand sides per pass (common.cuh): 12 accumulator registers each in double
 
 template <typename T, int K>
 struct DslashMArg {
@@ -34,62 +35,11 @@ struct DslashMArg {
   T2 *out[K];           // outputs (this parity)
   const T2 *w[K];       // kEpi 2: xpay operands (this parity)
   const T2 *r[K];       // kEpi 2: second dot operands
-  double *red[K];       // kEpi 2: three reduction slots per right-hand side
   const int *stop[K];   // per-right-hand-side stop flag (nullptr: always live)
   T s;
-  ReduceWs ws;          // partials sized for 3*K values per CTA
+  ReduceWs ws;          // kEpi 2: per-CTA partial sums [CTA][3*K] (slot k: values 3k..3k+2)
   int nsites;
 };
-
-// grid_reduce (common.cuh) with a destination per value; dst(k) == nullptr drops value k.
-// Same summation order per value as grid_reduce, hence the same bits.
-template <int N, typename Dst>
-__device__ __forceinline__ void grid_reduce_to(double (&v)[N], const ReduceWs ws, Dst dst) {
-  __shared__ double sm[N][kBlock / 32];
-  __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < N; k++) {
-    double s = v[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sm[k][warp] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-      double s = 0;
-#pragma unroll
-      for (int w = 0; w < kBlock / 32; w++) s += sm[k][w];
-      ws.partials[(size_t)blockIdx.x * N + k] = s;
-    }
-    __threadfence();
-    const unsigned ticket = atomicAdd(ws.counter, 1u);
-    is_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-#pragma unroll
-  for (int k = 0; k < N; k++) {
-    double s = 0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += kBlock) s += __ldcg(&ws.partials[(size_t)b * N + k]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    __syncthreads();
-    if (lane == 0) sm[k][warp] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot = 0;
-#pragma unroll
-      for (int w = 0; w < kBlock / 32; w++) tot += sm[k][w];
-      double *o = dst(k);
-      if (o != nullptr) *o = tot;
-    }
-  }
-  if (threadIdx.x == 0) *ws.counter = 0;
-}
 
 // the four hops of direction D for all K right-hand sides: each link is loaded once
 template <typename T, int D, int K, int kNc>
@@ -180,8 +130,9 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? 3 : (K == 4 ? 4 : 5))
       }
     }
   }
-  if (kEpi == 2)
-    grid_reduce_to<3 * K>(red, a.ws, [&](int j) -> double * { return live[j / 3] ? a.red[j / 3] + (j % 3) : nullptr; });
+  // two-stage reduction: per-CTA partial sums [3*K] here, reduce_finish_kernel (one CTA per slot,
+  // skipping stopped ones) adds them up in grid_reduce's order
+  if (kEpi == 2) block_partials<3 * K>(red, a.ws.partials);
 }
 
 }  // namespace b200ks

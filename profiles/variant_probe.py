@@ -24,6 +24,13 @@ def one():
     for prec in (0, 1):
         ts = [ctx.dslash_time(prec, 2, 100) for _ in range(3)]
         out["dslash_ms_prec%d" % prec] = min(ts)
+    if "probe_" in out["lib"]:      # diagnostic builds (no math / no link loads): stencil timings only
+        for prec in (0,):
+            out["dslash_ms_long_prec%d" % prec] = ctx.dslash_time(prec, 2, 3000)
+        print("VARIANT " + json.dumps(out))
+        ctx.close()
+        return
+    out["dslash_ms_long_prec0"] = ctx.dslash_time(0, 2, 3000)
     vb, vx = ctx.vec_create(), ctx.vec_create()
     ctx.vec_gaussian(vb, 2, 5678)
     best = None
@@ -33,6 +40,27 @@ def one():
         if best is None or res["device_seconds"] < best[1]:
             best = (it, res["device_seconds"], res["final_rsq"])
     out["cg_mixed2"] = {"iters": best[0], "seconds": best[1], "final_rsq": best[2]}
+    for mixed in (0, 1):
+        best = None
+        for rep in range(2):
+            ctx.vec_zero(vx, 2)
+            it, res = ctx.congrad_dev(vb, vx, 0.05, 2, 2000, 10, 1e-10, mixed_precision=mixed)
+            if best is None or res["device_seconds"] < best[1]:
+                best = (it, res["device_seconds"])
+        out["cg_mixed%d" % mixed] = {"iters": best[0], "seconds": best[1]}
+    vbs = [ctx.vec_create() for _ in range(4)]
+    vxs = [ctx.vec_create() for _ in range(4)]
+    for k in range(4):
+        ctx.vec_gaussian(vbs[k], 2, 5678 + 101 * k)
+    for mixed in (0, 1):
+        best = None
+        for rep in range(2):
+            for k in range(4):
+                ctx.vec_zero(vxs[k], 2)
+            it, res = ctx.congrad_block_dev(vbs, vxs, 0.05, 2, 2000, 10, 1e-10, mixed_precision=mixed)
+            if best is None or res[0]["device_seconds"] < best[1]:
+                best = (it, res[0]["device_seconds"])
+        out["block4_mixed%d" % mixed] = {"iters": best[0], "seconds": best[1]}
     print("VARIANT " + json.dumps(out))
     ctx.close()
 
