@@ -124,7 +124,8 @@ def ncu_traffic(prec, long_reals):
     if os.path.exists(p):
         try:
             for row in json.load(open(p))["kernels"]:
-                if row["prec"] == prec and row["long_reals"] == long_reals:
+                if (row["prec"] == prec and row["long_reals"] == long_reals and row.get("nrhs", 1) == 1
+                        and row.get("epilogue", 0) == 0 and row.get("mode", 0) == 0):
                     return float(row["dram_bytes_per_launch"])
         except Exception:
             return None

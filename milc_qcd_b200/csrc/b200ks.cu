@@ -168,6 +168,9 @@ static int setup_geom(b200ks_ctx *c, const int local[4], const int part[4], cons
     g.G[d] = c->global[d];
   }
   g.Lxh = g.L[0] / 2;
+  g.dLxh = make_fastdiv(g.Lxh);
+  g.dL1 = make_fastdiv(g.L[1]);
+  g.dL2 = make_fastdiv(g.L[2]);
   long long vol = (long long)g.L[0] * g.L[1] * g.L[2] * g.L[3];
   if (vol / 2 > (1ll << 30)) return fail(B200KS_EINVAL, "local volume too large for 32-bit site indices");
   g.Vh = (int)(vol / 2);

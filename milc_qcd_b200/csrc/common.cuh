@@ -25,6 +25,24 @@ template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 
+// Division by a lattice extent: q = (umulhi(m, n) + n) >> l (Granlund-Montgomery), exact for
+// 0 <= n < 2^31.  The extents are kernel arguments, so a plain `/` is a 35-instruction reciprocal
+// sequence; three of them opened every stencil thread before its first load could issue.
+struct FastDiv {
+  unsigned m;
+  int l;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.l = 0;
+  while ((1ll << f.l) < d) f.l++;
+  f.m = (unsigned)((((unsigned long long)1 << 32) * (((unsigned long long)1 << f.l) - (unsigned long long)d)) / (unsigned long long)d + 1ull);
+  return f;
+}
+__device__ __forceinline__ int fast_div(int n, const FastDiv f) {
+  return (int)((__umulhi(f.m, (unsigned)n) + (unsigned)n) >> f.l);
+}
+
 // Local lattice geometry (per GPU).  part[d] != 0 means direction d is split across
 // GPUs and neighbours beyond the local extent live in the ghost zone.
 struct Geom {
@@ -40,6 +58,7 @@ struct Geom {
   int lghost[4];   // first backward-ghost site of d in a link half (tail of the link field)
   int origin[4];   // global coordinates of the local origin (even in every direction)
   int G[4];        // global extents
+  FastDiv dLxh, dL1, dL2;   // division by Lxh, L[1], L[2]
 };
 
 struct Coord { int x, y, z, t, xh; };
@@ -47,12 +66,12 @@ struct Coord { int x, y, z, t, xh; };
 // cb index -> local coordinates, for a site of the given local parity bit (0 even, 1 odd).
 __device__ __forceinline__ Coord site_coord(const Geom &g, int idx, int par) {
   Coord c;
-  c.xh = idx % g.Lxh;
-  int r = idx / g.Lxh;
-  c.y = r % g.L[1];
-  r /= g.L[1];
-  c.z = r % g.L[2];
-  c.t = r / g.L[2];
+  const int r1 = fast_div(idx, g.dLxh);
+  c.xh = idx - r1 * g.Lxh;
+  const int r2 = fast_div(r1, g.dL1);
+  c.y = r1 - r2 * g.L[1];
+  c.t = fast_div(r2, g.dL2);
+  c.z = r2 - c.t * g.L[2];
   c.x = 2 * c.xh + ((c.y + c.z + c.t + par) & 1);
   return c;
 }
@@ -63,12 +82,16 @@ __device__ __forceinline__ Coord site_coord(const Geom &g, int idx, int par) {
 // directions index the ghost zone.  kLink selects link-field ghosts (backward only).
 template <int D, bool kLink = false>
 __device__ __forceinline__ int neighbor(const Geom &g, int idx, const Coord &c, int h) {
+  // (h is a compile-time constant at every call site: only the wrap on its side survives)
   if (D == 0) {
     int xn = c.x + h;
-    if (xn >= g.L[0]) xn -= g.L[0];
-    if (xn >= g.L[0]) xn -= g.L[0];  // extent 2 with a 3-hop wraps twice
-    if (xn < 0) xn += g.L[0];
-    if (xn < 0) xn += g.L[0];
+    if (h > 0) {
+      if (xn >= g.L[0]) xn -= g.L[0];
+      if (h > 1 && xn >= g.L[0]) xn -= g.L[0];  // extent 2 with a 3-hop wraps twice
+    } else {
+      if (xn < 0) xn += g.L[0];
+      if (h < -1 && xn < 0) xn += g.L[0];
+    }
     return idx - c.xh + (xn >> 1);
   }
   const int coord = (D == 1) ? c.y : (D == 2) ? c.z : c.t;
@@ -90,10 +113,13 @@ __device__ __forceinline__ int neighbor(const Geom &g, int idx, const Coord &c, 
     }
     return idx + h * sstride;
   }
-  if (cn >= ext) cn -= ext;
-  if (cn >= ext) cn -= ext;
-  if (cn < 0) cn += ext;
-  if (cn < 0) cn += ext;
+  if (h > 0) {
+    if (cn >= ext) cn -= ext;
+    if (h > 1 && cn >= ext) cn -= ext;
+  } else {
+    if (cn < 0) cn += ext;
+    if (h < -1 && cn < 0) cn += ext;
+  }
   return idx + (cn - coord) * sstride;
 }
 

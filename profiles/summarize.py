@@ -56,6 +56,7 @@ def full(path, tag):
     hdr, units = rows[0], rows[1]
     idx = [hdr.index(k) for k in KEEP if k in hdr]
     out = os.path.join(HERE, "dslash_ncu_%s.csv" % tag)
+    rows = rows[:2] + [r for r in rows[2:] if len(r) == len(hdr)]
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
         w.writerow([hdr[i] for i in idx])
@@ -75,23 +76,38 @@ def full(path, tag):
         name = r[hdr.index("Kernel Name")]
         m = re.search(r"dslash_kernel<(double|float), (\d), (\d), (\d)>", name)
         mh = re.search(r"dslash_half_kernel<(\d), (\d), (\d)>", name)
-        if not m and not mh:
+        mm = re.search(r"dslash_mrhs_kernel<(double|float), (\d), (\d), (\d)>", name)
+        if not m and not mh and not mm:
             continue
         tr = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
+        nrhs = 1
         if mh:
             prec, epi, mode, nc = 0, int(mh.group(1)), int(mh.group(2)), int(mh.group(3))
+        elif mm:
+            prec, epi, mode, nc = (2 if mm.group(1) == "double" else 1), int(mm.group(2)), 0, int(mm.group(4))
+            nrhs = int(mm.group(3))
         else:
             prec, epi, mode, nc = (2 if m.group(1) == "double" else 1), int(m.group(2)), int(m.group(3)), int(m.group(4))
-        kernels.append({"kernel": name, "prec": prec, "epilogue": epi,
+        if any(k["kernel"] == name for k in kernels):
+            continue   # first launch of each variant
+        kernels.append({"kernel": name, "prec": prec, "epilogue": epi, "nrhs": nrhs, "tag": tag,
                         "mode": mode, "long_reals": 2 * nc, "dram_bytes_per_launch": tr,
                         "dram_bytes_read": val(r, "dram__bytes_read.sum"),
                         "dram_bytes_write": val(r, "dram__bytes_write.sum"),
                         "gpu_time_us": float(r[hdr.index("gpu__time_duration.sum")])})
+    # kernels not in this capture keep the entry of the capture they were last seen in
+    sp = os.path.join(HERE, "dslash_ncu_summary.json")
+    if os.path.exists(sp):
+        for k in json.load(open(sp)).get("kernels", []):
+            if not any(n["kernel"] == k["kernel"] for n in kernels):
+                kernels.append(k)
     js = {"tag": tag, "source": os.path.basename(path), "lattice": "32x32x32x64", "kernels": kernels}
-    json.dump(js, open(os.path.join(HERE, "dslash_ncu_summary.json"), "w"), indent=1)
+    json.dump(js, open(sp, "w"), indent=1)
     print(json.dumps(js, indent=1))
 
 
 if __name__ == "__main__":
-    launches(sys.argv[1], sys.argv[3])
-    full(sys.argv[2], sys.argv[3])
+    if os.path.exists(sys.argv[1]):
+        launches(sys.argv[1], sys.argv[3])
+    if os.path.exists(sys.argv[2]):
+        full(sys.argv[2], sys.argv[3])
