@@ -51,12 +51,16 @@ def launches(path, tag):
 
 
 def full(path, tag):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # path: an .ncu-rep, or the raw CSV page exported from it on the GPU box (ncu -i rep --page raw --csv)
+    raw = open(path).read() if path.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = [hdr.index(k) for k in KEEP if k in hdr]
     out = os.path.join(HERE, "dslash_ncu_%s.csv" % tag)
-    rows = rows[:2] + [r for r in rows[2:] if len(r) == len(hdr)]
+    ti = hdr.index("gpu__time_duration.sum")
+    # (launches of an already-stopped solver are ~8 us no-ops: not stencil measurements)
+    rows = rows[:2] + [r for r in rows[2:] if len(r) == len(hdr) and float(r[ti].replace(",", "")) > 20.0]
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
         w.writerow([hdr[i] for i in idx])
