@@ -710,7 +710,6 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
   a.halo_mask = 0;
   a.halo_err = nullptr;
   a.halo_timeout = kHaloTimeoutCycles;
-  a.two_stage = (e.kind == 2 && !c->comm.active) ? 1 : 0;
   const int grid = nblocks(c->g.Vh);
   const bool z7 = L.lng_nc == 7;
 #define DSLASH_LAUNCH(kMode, grid_)                                                        \
@@ -727,7 +726,7 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
   } while (0)
   if (!c->comm.active) {
     DSLASH_LAUNCH(0, grid);
-    if (a.two_stage) finish_dots(c, grid, e.red, e.stop);
+    if (e.kind == 2) finish_dots(c, grid, e.red, e.stop);   // kMode 0 stores partial sums only
     return 0;
   }
   const int nb_ext = nblocks(c->comm.n_ext);
@@ -800,9 +799,8 @@ static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *o
     }                                                                                       \
   } while (0)
   if (!c->comm.active) {
-    a.two_stage = kind == 2 ? 1 : 0;
     DSLASH_H_LAUNCH(0, nblocks(c->g.Vh));
-    if (a.two_stage) finish_dots(c, nblocks(c->g.Vh), red, stop);
+    if (kind == 2) finish_dots(c, nblocks(c->g.Vh), red, stop);   // kMode 0 stores partial sums only
     return 0;
   }
   if (!c->comm.p2p.on) return fail(B200KS_ESTATE, "16-bit stencil needs the peer-to-peer halo path");

@@ -207,11 +207,32 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[N], const ReduceWs ws, d
   __syncthreads();
   if (!is_last) return false;
   __threadfence();
+  // partial sums of CTAs t, t+128, ...: four CTAs' loads are issued before their (in-order)
+  // additions, so the ~gridDim/128 dependent L2 round trips become ~gridDim/512
+  double tot_k[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) tot_k[k] = 0;
+  {
+    const int G = (int)gridDim.x;
+    int b = threadIdx.x;
+    for (; b + 3 * kBlock < G; b += 4 * kBlock) {
+      double t[4][N];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int k = 0; k < N; k++) t[j][k] = __ldcg(&ws.partials[(size_t)(b + j * kBlock) * N + k]);
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int k = 0; k < N; k++) tot_k[k] += t[j][k];
+    }
+    for (; b < G; b += kBlock)
+#pragma unroll
+      for (int k = 0; k < N; k++) tot_k[k] += __ldcg(&ws.partials[(size_t)b * N + k]);
+  }
 #pragma unroll
   for (int k = 0; k < N; k++) {
-    double s = 0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += kBlock)
-      s += __ldcg(&ws.partials[(size_t)b * N + k]);
+    double s = tot_k[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     __syncthreads();

@@ -66,7 +66,6 @@ struct DslashArg {
   int halo_mask;
   int *halo_err;
   long long halo_timeout;
-  int two_stage;        // kEpi 2: store per-CTA partial sums only (reduce_finish_kernel adds them up)
 };
 
 template <typename T, typename T2>
@@ -184,8 +183,9 @@ __device__ __forceinline__ void acquire_halo(const unsigned long long *flags, un
   }
 }
 
+// (register caps keep 5 CTAs per SM in double and 8 in float whatever epilogue is compiled in)
 template <typename T, int kEpi, int kMode, int kNc>
-__global__ void __launch_bounds__(kBlock) dslash_kernel(const DslashArg<T> a) {
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? 5 : 8) dslash_kernel(const DslashArg<T> a) {
   using T2 = typename Vec2<T>::type;
   if (a.stop != nullptr && *a.stop) return;
   int k = blockIdx.x * kBlock + threadIdx.x;
@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(kBlock) dslash_kernel(const DslashArg<T> a) {
       a.out[(size_t)q * a.g.stride + idx] = o;
     }
   }
-  if (kEpi == 2) {
-    if (a.two_stage) block_partials<3>(red, a.ws.partials);
+  if (kEpi == 2) {   // single GPU (kMode 0): two-stage, reduce_finish_kernel follows; partitioned: in-kernel
+    if (kMode == 0) block_partials<3>(red, a.ws.partials);
     else grid_reduce<3>(red, a.ws, a.red);
   }
 }

@@ -99,7 +99,6 @@ struct DslashHArg {
   int halo_mask;
   int *halo_err;
   long long halo_timeout;
-  int two_stage;         // kEpi 2: store per-CTA partial sums only (reduce_finish_kernel adds them up)
 };
 
 // ---- packed fp32 helpers (sm_100 FFMA2 / FADD2 / FMUL2) -------------------------------------------
@@ -282,8 +281,8 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
       red[2] = s2;
     }
   }
-  if (kEpi == 2) {
-    if (a.two_stage) block_partials<3>(red, a.ws.partials);
+  if (kEpi == 2) {   // single GPU (kMode 0): two-stage, reduce_finish_kernel follows; partitioned: in-kernel
+    if (kMode == 0) block_partials<3>(red, a.ws.partials);
     else grid_reduce<3>(red, a.ws, a.red);
   }
 }
