@@ -164,6 +164,39 @@ int b200ks_multicg(b200ks_ctx *ctx, const void *src, void *const *psim, const do
                    int num_offsets, const b200ks_invert_args *args, b200ks_invert_result *res,
                    int host_prec);
 
+/* ---- fermion-link construction ---------------------------
+ * Links are su3_matrix[4*V] in MILC order (link[4*i+dir]) with KS phases and boundary signs
+ * in (phases_in = 1); path_coeff = {one_link, naik, three_staple, five_staple, seven_staple,
+ * lepage} (asqtad_coeffs_t, include/ks_action_paths.h:23-30).  Double precision on the device
+ * whatever host_prec is.  Single-GPU contexts.
+ *
+ * b200ks_ks_links: fatlink = smeared inlink, longlink (may be NULL) = naik * U U U.
+ *   Replaces load_fatlinks_cpu + load_lnglinks (generic_ks/fermion_links_fn_load_milc.c:45-275)
+ *   = qudaLoadKSLink (generic_ks/fermion_links_fn_load_gpu.c:36,67).
+ * b200ks_unitarized_links: vlink (may be NULL) = smeared inlink, wlink = its U(3) projection
+ *   W = V (V^+ V)^-1/2.  Replaces load_V_from_U + load_Y_from_V with UNITARIZE_ANALYTIC
+ *   (generic_ks/fermion_links_hisq_load_milc.c:118-340, su3_mat_op.c:828-1205)
+ *   = qudaLoadUnitarizedLink (fermion_links_fn_load_gpu.c:108).  *nsvd (may be NULL) returns how
+ *   many links took the SVD branch (HISQ_REUNIT_ALLOW_SVD; thresholds 1e-8 as in
+ *   ks_imp_rhmc/Make_template:204-206, or B200KS_REUNIT_ALLOW_SVD / _SVD_REL_ERROR /
+ *   _SVD_ABS_ERROR in the environment).
+ * b200ks_hisq_links: the whole chain U -> V -> W -> (fat, long) of create_hisq_links_milc
+ *   (fermion_links_hisq_load_milc.c:684-713, one Naik epsilon) with the intermediate fields
+ *   resident: coeff1 = level-1 (fat7), coeff2 = level-2 coefficients; any output may be NULL. */
+int b200ks_ks_links(b200ks_ctx *ctx, const double *path_coeff, const void *inlink, void *fatlink,
+                    void *longlink, int host_prec);
+int b200ks_unitarized_links(b200ks_ctx *ctx, const double *path_coeff, const void *inlink, void *vlink,
+                            void *wlink, int host_prec, long long *nsvd);
+int b200ks_hisq_links(b200ks_ctx *ctx, const double *coeff1, const double *coeff2, const void *inlink,
+                      void *vlink, void *wlink, void *fatlink, void *longlink, int host_prec,
+                      long long *nsvd);
+/* Benchmark face: the chain on Haar-random thin links generated on the device, `reps` times,
+ * CUDA-event milliseconds per chain; b200ks_hisq_links_fetch reads back field `which` of the last
+ * chain (0 input, 1 V, 2 W, 3 fat, 4 long) for the CPU comparison. */
+int b200ks_hisq_links_time(b200ks_ctx *ctx, const double *coeff1, const double *coeff2,
+                           unsigned long long seed, int reps, double *ms_per_chain, long long *nsvd);
+int b200ks_hisq_links_fetch(b200ks_ctx *ctx, int which, void *host, int host_prec);
+
 /* ---- device-resident interface (benchmarks, resident solve sequences) -------------- */
 
 /* Device colour-vector fields of one context, double precision, both parities. */

@@ -13,7 +13,8 @@
  * therefore links the unmodified MILC tree against libb200ks.
  * Exactly these symbols are required (link-probed): qudaInit,
  * qudaSetMPICommHandle, qudaFinalize, qudaAllocatePinned, qudaFreePinned, qudaInvert,
- * qudaInvertMsrc, qudaMultishiftInvert, qudaDslash (+ qudaMomAction for ks_imp_rhmc).
+ * qudaInvertMsrc, qudaMultishiftInvert, qudaDslash (+ qudaMomAction for ks_imp_rhmc);
+ * WANT_FL_GPU=true additionally binds qudaLoadKSLink and qudaLoadUnitarizedLink.
  */
 #ifndef QUDA_MILC_INTERFACE_H
 #define QUDA_MILC_INTERFACE_H
@@ -100,6 +101,23 @@ void qudaDslash(int external_precision, int quda_precision, QudaInvertArgs_t inv
 
 /* ks_imp_rhmc/d_action_rhmc.c:102-105: sum over sites and directions of |mom|^2 - 4 */
 double qudaMomAction(int precision, QudaMILCSiteArg_t *arg);
+
+/* ---- fermion-link construction (-DUSE_FL_GPU: make WANT_FL_GPU=true, Makefile:453-455) ------
+ * generic_ks/fermion_links_fn_load_gpu.c:18-123.  path_coeff = {one_link, naik, three_staple,
+ * five_staple, seven_staple, lepage}; links are su3_matrix[4*sites_on_node] in MILC order with
+ * KS phases and boundary signs in. */
+typedef struct {
+  int su3_source;  /* the incoming links are SU(3) (only a hint; not used here) */
+} QudaFatLinkArgs_t;
+
+/* fatlink = smeared inlink (load_fatlinks_cpu), longlink (may be NULL) = naik * three-link product
+ * (load_lnglinks); called by load_fatlinks_gpu / load_fatlonglinks_gpu. */
+void qudaLoadKSLink(int precision, QudaFatLinkArgs_t fatlink_args, const double path_coeff[6], void *inlink,
+                    void *fatlink, void *longlink);
+/* fatlink (may be NULL) = smeared inlink, ulink = its U(3) projection (u3_unitarize_analytic);
+ * called by load_hisq_aux_links_gpu with the level-1 (fat7) coefficients. */
+void qudaLoadUnitarizedLink(int precision, QudaFatLinkArgs_t fatlink_args, const double path_coeff[6], void *inlink,
+                            void *fatlink, void *ulink);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,14 @@ SYMBOLS = [
                                            C.POINTER(InvertArgs), C.POINTER(InvertResult)]),
     ("b200ks_dslash_block_dev", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int]),
     ("b200ks_dslash_block_time", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    ("b200ks_ks_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    ("b200ks_unitarized_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.POINTER(C.c_longlong)]),
+    ("b200ks_hisq_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]),
+    ("b200ks_hisq_links_time", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_ulonglong, C.c_int,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    ("b200ks_hisq_links_fetch", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     ("b200ks_dslash_time", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("b200ks_halo_mode", C.c_int, [C.c_void_p]),
     ("b200ks_launch_count", C.c_longlong, [C.c_void_p]),

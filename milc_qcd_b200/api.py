@@ -139,6 +139,58 @@ class Context:
             self._links_of = fn
             fn.notify_quda_new_links = 0
 
+    # -- fermion-link construction -----------------------------------
+    # {one_link, naik, three_staple, five_staple, seven_staple, lepage} of the reference's HISQ
+    # action (generic_ks/imp_actions/hisq/hisq_u3_action.h:33-37,74-81)
+    HISQ_FAT7 = (1.0 / 8.0, 0.0, -1.0 / 16.0, 1.0 / 64.0, -1.0 / 384.0, 0.0)
+    HISQ_ASQTAD_LIKE = (1.0, -1.0 / 24.0, -1.0 / 16.0, 1.0 / 64.0, -1.0 / 384.0, -1.0 / 8.0)
+
+    @staticmethod
+    def _coeffs(c):
+        if len(c) != 6:
+            raise ValueError("path coefficients: {one_link, naik, three_staple, five_staple, seven_staple, lepage}")
+        return (C.c_double * 6)(*[float(x) for x in c])
+
+    def ks_links(self, links, coeffs, want_long=True):
+        """load_fatlinks + load_lnglinks (qudaLoadKSLink): returns (fat, lng or None)."""
+        fat = np.zeros_like(links)
+        lng = np.zeros_like(links) if want_long else None
+        check(self.lib.b200ks_ks_links(self.h, self._coeffs(coeffs), _ptr(links), _ptr(fat),
+                                       _ptr(lng) if want_long else None, _host_prec(links)), "b200ks_ks_links")
+        return fat, lng
+
+    def unitarized_links(self, links, coeffs, want_v=True):
+        """fat7 smear + U(3) projection (qudaLoadUnitarizedLink): returns (V or None, W, svd count)."""
+        V = np.zeros_like(links) if want_v else None
+        W = np.zeros_like(links)
+        n = C.c_longlong(0)
+        check(self.lib.b200ks_unitarized_links(self.h, self._coeffs(coeffs), _ptr(links), _ptr(V) if want_v else None,
+                                               _ptr(W), _host_prec(links), C.byref(n)), "b200ks_unitarized_links")
+        return V, W, n.value
+
+    def hisq_links(self, links, coeffs1=None, coeffs2=None):
+        """create_hisq_links_milc's chain U -> V -> W -> (fat, lng), intermediate fields resident."""
+        out = {k: np.zeros_like(links) for k in ("V", "W", "fat", "lng")}
+        n = C.c_longlong(0)
+        check(self.lib.b200ks_hisq_links(self.h, self._coeffs(self.HISQ_FAT7 if coeffs1 is None else coeffs1),
+                                         self._coeffs(self.HISQ_ASQTAD_LIKE if coeffs2 is None else coeffs2), _ptr(links), _ptr(out["V"]),
+                                         _ptr(out["W"]), _ptr(out["fat"]), _ptr(out["lng"]), _host_prec(links),
+                                         C.byref(n)), "b200ks_hisq_links")
+        out["nsvd"] = n.value
+        return out
+
+    def hisq_links_time(self, seed, reps, coeffs1=None, coeffs2=None):
+        ms, n = C.c_double(), C.c_longlong(0)
+        check(self.lib.b200ks_hisq_links_time(self.h, self._coeffs(self.HISQ_FAT7 if coeffs1 is None else coeffs1),
+                                              self._coeffs(self.HISQ_ASQTAD_LIKE if coeffs2 is None else coeffs2), seed, reps, C.byref(ms),
+                                              C.byref(n)), "b200ks_hisq_links_time")
+        return ms.value, n.value
+
+    def hisq_links_fetch(self, which, dtype=np.float64):
+        out = np.zeros((self.volume, 4, 3, 3, 2), dtype=dtype)
+        check(self.lib.b200ks_hisq_links_fetch(self.h, which, _ptr(out), _host_prec(out)), "b200ks_hisq_links_fetch")
+        return out
+
     # -- host-buffer operators ------------------------------------------------------------------
     def dslash(self, src, dest, parity):
         check(self.lib.b200ks_dslash(self.h, _ptr(src), _ptr(dest), parity, _host_prec(src)), "b200ks_dslash")

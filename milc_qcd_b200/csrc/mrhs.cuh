@@ -74,8 +74,18 @@ __device__ __forceinline__ void hop_dir_m(const DslashMArg<T, K> &a, int idx, co
 // neither stored nor reduced; when every flag is set the launch is a no-op.
 // (register caps: double 3 CTAs per SM (<= 168), float 5 (<= 102) or 4 at K = 4 (<= 128), so that
 // enough link loads are in flight per SM)
+#ifndef B200KS_MRHS_MINB_D
+#define B200KS_MRHS_MINB_D 3
+#endif
+#ifndef B200KS_MRHS_MINB_F4
+#define B200KS_MRHS_MINB_F4 4
+#endif
+#ifndef B200KS_MRHS_MINB_F
+#define B200KS_MRHS_MINB_F 5
+#endif
 template <typename T, int kEpi, int K, int kNc>
-__global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? 3 : (K == 4 ? 4 : 5)) dslash_mrhs_kernel(const DslashMArg<T, K> a) {
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? B200KS_MRHS_MINB_D : (K == 4 ? B200KS_MRHS_MINB_F4 : B200KS_MRHS_MINB_F))
+dslash_mrhs_kernel(const DslashMArg<T, K> a) {
   using T2 = typename Vec2<T>::type;
   bool live[K];
   bool any = false;

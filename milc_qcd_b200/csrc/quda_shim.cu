@@ -243,6 +243,22 @@ void qudaDslash(int external_precision, int quda_precision, QudaInvertArgs_t inv
   if (num_iters) *num_iters = 0;
 }
 
+void qudaLoadKSLink(int precision, QudaFatLinkArgs_t, const double path_coeff[6], void *inlink, void *fatlink,
+                    void *longlink) {
+  static const char where[] = "qudaLoadKSLink";
+  ensure_ctx(where);
+  if (b200ks_ks_links(S.ctx, path_coeff, inlink, fatlink, longlink, precision) < 0) die(where);
+}
+
+void qudaLoadUnitarizedLink(int precision, QudaFatLinkArgs_t, const double path_coeff[6], void *inlink, void *fatlink,
+                            void *ulink) {
+  static const char where[] = "qudaLoadUnitarizedLink";
+  ensure_ctx(where);
+  long long nsvd = 0;
+  if (b200ks_unitarized_links(S.ctx, path_coeff, inlink, fatlink, ulink, precision, &nsvd) < 0) die(where);
+  if (S.verbosity >= QUDA_VERBOSE) printf("qudaLoadUnitarizedLink: %lld links took the SVD branch\n", nsvd);
+}
+
 double qudaMomAction(int precision, QudaMILCSiteArg_t *arg) {
   static const char where[] = "qudaMomAction";
   ensure_ctx(where);

@@ -104,6 +104,30 @@ def make_links(dims, seed=1234, fat_noise=0.05, c3=-1.0 / 24.0, eps_naik=0.0, dt
     return _c2r(fat_m).astype(dtype), _c2r(lng_m).astype(dtype)
 
 
+def make_thin_links(dims, seed=4321, spread=0.4, dtype=np.float64):
+    """Thin SU(3) gauge links with KS phases and the antiperiodic time boundary folded in
+    (what a MILC application hands to the fermion-link construction after rephase(ON),
+    generic_ks/rephase.c:83-115, phases_in = 1), MILC host layout (V,4,3,3,2).
+    U = exp(i * spread * H), H Gaussian Hermitian traceless: spread ~ 0.4 resembles a
+    thermalised configuration, spread >= 3 is close to Haar-random (strong coupling)."""
+    nx, ny, nz, nt = dims
+    V = volume(dims)
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((4 * V, 3, 3)) + 1j * rng.standard_normal((4 * V, 3, 3))
+    h = 0.5 * (a + np.conj(np.swapaxes(a, 1, 2)))
+    h -= np.trace(h, axis1=1, axis2=2)[:, None, None] * np.eye(3) / 3.0
+    w, v = np.linalg.eigh(h)
+    U = (v * np.exp(1j * spread * w)[:, None, :]) @ np.conj(np.swapaxes(v, 1, 2))
+    U = U.reshape(nt, nz, ny, nx, 4, 3, 3)
+    eta = ks_phases(dims).reshape(nt, nz, ny, nx, 4)
+    U = U * eta[..., None, None]
+    U[nt - 1, ..., 3, :, :] *= -1.0
+    perm = lex_to_milc(dims)
+    out = np.empty((V, 4, 3, 3), dtype=np.complex128)
+    out[perm] = U.reshape(V, 4, 3, 3)
+    return _c2r(out).astype(dtype)
+
+
 def make_source(dims, seed=5678, parity=EVEN, dtype=np.float64):
     """Gaussian random colour vector on `parity` sites (zero elsewhere), shape (V,3,2)."""
     V = volume(dims)

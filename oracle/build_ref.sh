@@ -25,13 +25,18 @@ cp "$REF/generic_ks/imp_actions/hisq/hisq_u3_action.h" "$OUT/gen/quark_action.h"
 LIBSRC=$(cd "$REF/libraries" && ls *.c | grep -v "^prefetch32.c$\|^prefetch64.c$")
 GEN="com_vanilla.c layout_hyper_prime.c make_lattice.c field_utilities.c ranstuff.c"
 GKS="dslash_fn_dblstore.c fn_links_milc.c d_congrad5_fn_milc.c ks_multicg_offset.c fermion_links_fn_twist_milc.c"
+# HISQ link construction: U -> V (fat7) -> W (U(3) projection) -> fat, long
+GEN="$GEN general_staple.c path_product.c gauge_utilities.c project_su3_hit.c reunitarize2.c stout_smear.c"
+GKS="$GKS fermion_links_hisq_load_milc.c fermion_links_fn_load_milc.c ks_action_paths_hisq.c su3_mat_op.c rephase.c"
 
 build_variant() {  # name precision extra-flags
   local name="$1" prec="$2" extra="$3"
   local obj="$OUT/obj_$name"
   mkdir -p "$obj"
   local CF="-O3 -fPIC -std=gnu99 -w $extra -DMILC_PRECISION=$prec -DFAST"
+  # (-DHISQ_REUNIT_*: the reunitarisation flags of the RHMC build, ks_imp_rhmc/Make_template:204-206)
   local AF="$CF -DDBLSTORE_FN -DFEWSUMS -DD_FN_GATHER13 -DC_GLOBAL_INLINE -DFN -DHAVE_KS \
+            -DHISQ_REUNIT_ALLOW_SVD -DHISQ_REUNIT_SVD_REL_ERROR=1e-8 -DHISQ_REUNIT_SVD_ABS_ERROR=1e-8 \
             -D_FILE_OFFSET_BITS=64 -I$HERE/ref_harness -I$OUT/gen"
   local jobs=()
   for f in $LIBSRC; do

@@ -25,8 +25,8 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build_oracle(force=False):
     so = os.path.join(HERE, "liboracle.so")
-    src = os.path.join(HERE, "ks_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ("ks_oracle.c", "ks_links_oracle.c")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", HERE, "-s", "-B", "liboracle.so"])
     return so
 
@@ -80,6 +80,53 @@ class Oracle:
         return it, psim, [_qic(out[7 * j:7 * j + 7]) for j in range(n)]
 
 
+class LinksOracle:
+    """ctypes face of ks_links_oracle.c (HISQ/asqtad link construction).  MILC host layout, float64."""
+    # the reference's HISQ coefficients (generic_ks/imp_actions/hisq/hisq_u3_action.h:33-37,74-81):
+    # {one_link, naik, three_staple, five_staple, seven_staple, lepage}
+    FAT7 = (1.0 / 8.0, 0.0, -1.0 / 16.0, 1.0 / 64.0, -1.0 / 384.0, 0.0)
+    ASQTAD_LIKE = (1.0, -1.0 / 24.0, -1.0 / 16.0, 1.0 / 64.0, -1.0 / 384.0, -1.0 / 8.0)
+
+    def __init__(self):
+        self.lib = C.CDLL(build_oracle())
+        L = self.lib
+        L.ksl_smear.restype = None
+        L.ksl_smear.argtypes = [_ip, _dp, _dp, _dp, C.c_void_p]
+        L.ksl_unitarize.restype = C.c_long
+        L.ksl_unitarize.argtypes = [_dp, _dp, C.c_long, C.c_int, C.c_double, C.c_double]
+        L.ksl_hisq_links.restype = C.c_long
+        L.ksl_hisq_links.argtypes = [_ip, _dp, _dp, _dp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_double, C.c_double]
+
+    @staticmethod
+    def _dims(dims):
+        return np.ascontiguousarray(dims, dtype=np.int32)
+
+    def smear(self, dims, links, coeffs, want_long=True):
+        links = np.ascontiguousarray(links, np.float64)
+        fat = np.zeros_like(links)
+        lng = np.zeros_like(links) if want_long else None
+        self.lib.ksl_smear(self._dims(dims), np.ascontiguousarray(coeffs, np.float64), links, fat,
+                           lng.ctypes.data if want_long else None)
+        return fat, lng
+
+    def unitarize(self, V, allow_svd=True, svd_rel=1e-8, svd_abs=1e-8):
+        V = np.ascontiguousarray(V, np.float64)
+        W = np.zeros_like(V)
+        n = self.lib.ksl_unitarize(V, W, V.size // 18, int(allow_svd), svd_rel, svd_abs)
+        return W, int(n)
+
+    def hisq_links(self, dims, links, coeffs1=None, coeffs2=None, allow_svd=True, svd_rel=1e-8, svd_abs=1e-8):
+        links = np.ascontiguousarray(links, np.float64)
+        out = {k: np.zeros_like(links) for k in ("V", "W", "fat", "lng")}
+        c1 = np.ascontiguousarray(self.FAT7 if coeffs1 is None else coeffs1, np.float64)
+        c2 = np.ascontiguousarray(self.ASQTAD_LIKE if coeffs2 is None else coeffs2, np.float64)
+        out["nsvd"] = int(self.lib.ksl_hisq_links(self._dims(dims), c1, c2, links, out["V"].ctypes.data,
+                                                  out["W"].ctypes.data, out["fat"].ctypes.data,
+                                                  out["lng"].ctypes.data, int(allow_svd), svd_rel, svd_abs))
+        return out
+
+
 def _qic(o):
     return dict(final_rsq=o[0], final_relrsq=o[1], size_r=o[2], size_relr=o[3],
                 final_iters=int(o[4]), final_restart=int(o[5]), converged=int(o[6]))
@@ -115,6 +162,10 @@ class MilcRef:
                                       C.c_double, _dp]
         L.milcref_time_dslash.restype = C.c_double
         L.milcref_time_dslash.argtypes = [rp, rp, C.c_int, C.c_int]
+        ro = np.ctypeslib.ndpointer(dtype=self.dtype, flags="C_CONTIGUOUS")
+        L.milcref_hisq_links.argtypes = [rp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _dp]
+        L.milcref_smear.argtypes = [rp, _dp, ro, C.c_void_p]
+        L.milcref_unitarize.argtypes = [rp, ro, C.c_long]
         self.dims = tuple(int(d) for d in dims)
         if L.milcref_init(*self.dims) != 0:
             raise RuntimeError("MilcRef: process already initialised with another geometry")
@@ -149,6 +200,35 @@ class MilcRef:
         it = self.lib.milcref_multicg(src, psim, offsets, n, parity, niter, nrestart, resid,
                                       relresid, out)
         return it, psim, [_qic(out[7 * j:7 * j + 7]) for j in range(n)]
+
+    # -- HISQ link construction --------------------------------
+    def hisq_links(self, links):
+        """The reference's create_hisq_links_milc on thin links (V,4,3,3,2) with KS phases in.
+        Returns dict(V, W, fat, lng, coeffs[3][6], nsvd)."""
+        links = np.ascontiguousarray(links, self.dtype)
+        out = {k: np.zeros_like(links) for k in ("V", "W", "fat", "lng")}
+        coeffs = np.zeros(18)
+        nsvd = self.lib.milcref_hisq_links(links, out["V"].ctypes.data, out["W"].ctypes.data,
+                                           out["fat"].ctypes.data, out["lng"].ctypes.data, coeffs)
+        out["coeffs"] = coeffs.reshape(3, 6)
+        out["nsvd"] = nsvd
+        return out
+
+    def smear(self, links, coeffs, want_long=True):
+        """load_fatlinks_cpu (+ load_lnglinks) with {one_link, naik, 3-, 5-, 7-staple, lepage}."""
+        links = np.ascontiguousarray(links, self.dtype)
+        fat = np.zeros_like(links)
+        lng = np.zeros_like(links) if want_long else None
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        self.lib.milcref_smear(links, c, fat, lng.ctypes.data if want_long else None)
+        return fat, lng
+
+    def unitarize(self, V):
+        """u3_unitarize_analytic on every matrix of V (..., 3, 3, 2); returns (W, svd count)."""
+        V = np.ascontiguousarray(V, self.dtype)
+        W = np.zeros_like(V)
+        n = self.lib.milcref_unitarize(V, W, V.size // 18)
+        return W, n
 
     def time_dslash(self, src, parity, ncalls):
         src = np.ascontiguousarray(src, self.dtype)

@@ -16,6 +16,10 @@
 #define CONTROL
 #include "generic_ks_includes.h"
 #include "../include/fn_links.h"
+#include "../include/ks_action_paths.h"
+#include "../include/fermion_links_milc.h"
+#include "../include/info.h"
+#include "../include/su3_mat_op.h"
 #include <string.h>
 
 static fn_links_t *h_fn = NULL;
@@ -141,4 +145,91 @@ double milcref_time_dslash(const Real *src, Real *dest, int parity, int ncalls) 
   for (k = 0; k < ncalls; k++)
     dslash_fn_field((su3_vector *)src, (su3_vector *)dest, parity, h_fn);
   return (dclock() - t0) / ncalls;
+}
+
+/* ---- HISQ link construction --------------------------------------
+ * The reference's own chain, create_hisq_links_milc (generic_ks/fermion_links_hisq_load_milc.c:
+ * 684-713): U -> V (fat7, load_fatlinks_cpu) -> Y = W (U(3) projection, u3_unitarize_analytic)
+ * -> fat, long (asqtad-like smear of W + Naik, load_fatlinks_cpu + load_lnglinks), with the
+ * reference's own path tables and coefficients (ks_action_paths_hisq.c, hisq_u3_action.h).
+ * links: su3_matrix[4*sites_on_node], KS phases and boundary signs already in (phases_in = 1).
+ * Outputs (each su3_matrix[4*sites_on_node], any may be NULL): V, W, fat, lng.
+ * coeffs[18]: {one_link, naik, three_staple, five_staple, seven_staple, lepage} of p1, p2, p3.
+ * Returns the number of links that took the SVD branch. */
+static ks_action_paths_hisq *h_ap = NULL;
+
+static void h_coeffs(double *c, const asqtad_coeffs_t *a) {
+  c[0] = a->one_link; c[1] = a->naik; c[2] = a->three_staple;
+  c[3] = a->five_staple; c[4] = a->seven_staple; c[5] = a->lepage;
+}
+
+int milcref_hisq_links(const Real *links, Real *V, Real *W, Real *fat, Real *lng, double *coeffs) {
+  info_t info = INFO_ZERO;
+  fn_links_t *fn[1] = {NULL};
+  fn_links_t *fn_deps = NULL;
+  hisq_auxiliary_t *aux = NULL;
+  double eps[1] = {0.0};
+  size_t bytes = sizeof(su3_matrix) * 4 * sites_on_node;
+  int nsvd;
+  if (!h_ready) return -1;
+  if (h_ap == NULL) {
+    h_ap = create_path_table_hisq();
+    make_path_table_hisq(h_ap, 1, eps);
+  }
+  create_hisq_links_milc(&info, fn, &fn_deps, &aux, h_ap, (su3_matrix *)links, 0, 0);
+  nsvd = INFO_HISQ_SVD_COUNTER(&info);
+  if (V) memcpy(V, aux->V_link, bytes);
+  if (W) memcpy(W, aux->W_unitlink, bytes);
+  if (fat) memcpy(fat, get_fatlinks(fn[0]), bytes);
+  if (lng) memcpy(lng, get_lnglinks(fn[0]), bytes);
+  if (coeffs) {
+    h_coeffs(coeffs, &h_ap->p1.act_path_coeff);
+    h_coeffs(coeffs + 6, &h_ap->p2.act_path_coeff);
+    h_coeffs(coeffs + 12, &h_ap->p3.act_path_coeff);
+  }
+  destroy_hisq_links_milc(h_ap, aux, fn, fn_deps);
+  return nsvd;
+}
+
+/* One smearing level on its own: fat (and lng if not NULL) from `links` with the given six
+ * coefficients -- load_fatlinks_cpu + load_lnglinks (generic_ks/fermion_links_fn_load_milc.c:
+ * 45-107,120-275) with the level-2 path table (the Naik paths carry coeffs[1]). */
+int milcref_smear(const Real *links, const double *coeffs, Real *fat, Real *lng) {
+  info_t info = INFO_ZERO;
+  ks_component_paths p;
+  double eps[1] = {0.0};
+  int k;
+  if (!h_ready) return -1;
+  if (h_ap == NULL) {
+    h_ap = create_path_table_hisq();
+    make_path_table_hisq(h_ap, 1, eps);
+  }
+  p = h_ap->p2;
+  p.act_path_coeff.one_link = coeffs[0]; p.act_path_coeff.naik = coeffs[1];
+  p.act_path_coeff.three_staple = coeffs[2]; p.act_path_coeff.five_staple = coeffs[3];
+  p.act_path_coeff.seven_staple = coeffs[4]; p.act_path_coeff.lepage = coeffs[5];
+  load_fatlinks_cpu(&info, (su3_matrix *)fat, &p, (su3_matrix *)links);
+  if (lng) {
+    /* load_lnglinks reads the coefficient from the path table: scale a copy of the Naik paths */
+    Q_path *q = (Q_path *)malloc(sizeof(Q_path) * p.num_q_paths);
+    double naik0 = h_ap->p2.act_path_coeff.naik;
+    memcpy(q, p.q_paths, sizeof(Q_path) * p.num_q_paths);
+    for (k = 0; k < p.num_q_paths; k++)
+      if (q[k].length == 3 && q[k].dir[0] == q[k].dir[1] && q[k].dir[1] == q[k].dir[2])
+        q[k].coeff *= (Real)(coeffs[1] / naik0);
+    p.q_paths = q;
+    load_lnglinks(&info, (su3_matrix *)lng, &p, (su3_matrix *)links);
+    free(q);
+  }
+  return 0;
+}
+
+/* W = U(3) projection of every link of V (u3_unitarize_analytic, generic_ks/su3_mat_op.c:828-1205,
+ * with the SVD branch as compiled: -DHISQ_REUNIT_ALLOW_SVD, thresholds 1e-8).  Returns SVD count. */
+int milcref_unitarize(const Real *V, Real *W, long nlinks) {
+  info_t info = INFO_ZERO;
+  long k;
+  for (k = 0; k < nlinks; k++)
+    u3_unitarize_analytic(&info, (su3_matrix *)V + k, (su3_matrix *)W + k);
+  return INFO_HISQ_SVD_COUNTER(&info);
 }

@@ -31,6 +31,9 @@ def one():
         ctx.close()
         return
     out["dslash_ms_long_prec0"] = ctx.dslash_time(0, 2, 3000)
+    for prec in (1, 2):
+        for k in (3, 4):
+            out["dslash_block_ms_prec%d_k%d" % (prec, k)] = min(ctx.dslash_block_time(prec, k, 2, 100) for _ in range(2))
     vb, vx = ctx.vec_create(), ctx.vec_create()
     ctx.vec_gaussian(vb, 2, 5678)
     best = None

@@ -136,3 +136,91 @@ def test_oracle_matches_compiled_reference_live(dims):
     out = subprocess.run([sys.executable, "-c", _LIVE % dict(root=ROOT, dims=dims)], capture_output=True,
                          text=True, timeout=600)
     assert "LIVE-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+# ---- HISQ link construction (oracle/ks_links_oracle.c) -------------------------------------------
+GOLDEN_LINKS = os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_links.npz")
+
+
+@pytest.fixture(scope="module")
+def links_oracle():
+    from oracle.pyoracle import LinksOracle
+    return LinksOracle()
+
+
+@pytest.mark.parametrize("tag,tol_w", [("smooth", 1e-13), ("rough", 1e-10)])
+def test_links_oracle_golden(links_oracle, tag, tol_w):
+    """The restated chain U -> V -> W -> (fat, long) against the reference's own
+    create_hisq_links_milc output (tests/golden/make_golden_links.py), with the reference's
+    coefficients; the rough field exercises the SVD branch."""
+    from milc_qcd_b200 import fields as F
+    g = np.load(GOLDEN_LINKS)
+    dims = tuple(int(d) for d in g["dims"])
+    U = F.make_thin_links(dims, seed=4321, spread=float(g[tag + "_spread"]))
+    assert np.allclose(g["coeffs"][0], links_oracle.FAT7) and np.allclose(g["coeffs"][1], links_oracle.ASQTAD_LIKE)
+    o = links_oracle.hisq_links(dims, U)
+    assert o["nsvd"] == int(g[tag + "_nsvd"])
+    assert rel_err(o["V"], g[tag + "_V"]) < 1e-14
+    assert rel_err(o["W"], g[tag + "_W"]) < tol_w
+    assert rel_err(o["fat"], g[tag + "_fat"]) < tol_w
+    assert rel_err(o["lng"], g[tag + "_lng"]) < tol_w
+    # the pieces on their own
+    fat, lng = links_oracle.smear(dims, g[tag + "_W"], links_oracle.ASQTAD_LIKE)
+    assert rel_err(fat, g[tag + "_fat"]) < 1e-14 and rel_err(lng, g[tag + "_lng"]) < 1e-14
+    W, n = links_oracle.unitarize(g[tag + "_V"])
+    assert n == int(g[tag + "_nsvd"]) and rel_err(W, g[tag + "_W"]) < tol_w
+    Wc = W[..., 0] + 1j * W[..., 1]
+    assert np.abs(Wc @ np.conj(np.swapaxes(Wc, -1, -2)) - np.eye(3)).max() < 1e-10
+
+
+def test_links_oracle_svd_branch_and_degenerate_inputs(links_oracle):
+    """Analytic and SVD branches agree where both are valid; unit matrices (degenerate
+    eigenvalues, S = 0) and scaled unitary matrices project onto themselves."""
+    rng = np.random.default_rng(5)
+    V = rng.standard_normal((200, 3, 3, 2))
+    Wa, na = links_oracle.unitarize(V, allow_svd=False)
+    Ws, ns = links_oracle.unitarize(V, allow_svd=True, svd_rel=0.0, svd_abs=1e300)   # force the SVD branch
+    assert na == 0 and ns == 200
+    assert np.abs(Wa - Ws).max() < 1e-9
+    eye = np.zeros((3, 3, 3, 2))
+    for k, s in enumerate((1.0, 2.5, -0.3)):
+        eye[k, range(3), range(3), 0] = s
+    W, n = links_oracle.unitarize(eye, allow_svd=False)
+    assert np.abs(W - np.sign(eye) * (eye != 0)).max() < 1e-14
+
+
+_LIVE_LINKS = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+from milc_qcd_b200 import fields as F
+from oracle.pyoracle import LinksOracle, MilcRef
+dims = %(dims)r
+o, r = LinksOracle(), MilcRef(dims)
+for spread, tol in ((0.4, 1e-13), (5.0, 1e-9)):
+    U = F.make_thin_links(dims, seed=99, spread=spread)
+    a, b = o.hisq_links(dims, U), r.hisq_links(U)
+    assert abs(a['nsvd'] - b['nsvd']) <= 1, (a['nsvd'], b['nsvd'])
+    for k in ('V', 'W', 'fat', 'lng'):
+        assert np.abs(a[k] - b[k]).max() <= tol * np.abs(b[k]).max(), (spread, k, np.abs(a[k] - b[k]).max())
+    # one smearing level with other coefficients (asqtad, tadpole-improved with u0 = 0.86)
+    u0 = 0.86
+    c = (5.0/8.0, -1.0/(24*u0**2), -1.0/(16*u0**2), 1.0/(64*u0**4), -1.0/(384*u0**6), -1.0/(16*u0**4))
+    fa, la = o.smear(dims, U, c)
+    fb, lb = r.smear(U, c)
+    assert np.abs(fa - fb).max() <= 1e-14 * np.abs(fb).max() and np.abs(la - lb).max() <= 1e-14 * np.abs(lb).max()
+    # one link only: the reference skips the staples
+    fa, _ = o.smear(dims, U, (0.125, -1/24., 0, 0, 0, 0), want_long=False)
+    fb, _ = r.smear(U, (0.125, -1/24., 0, 0, 0, 0), want_long=False)
+    assert np.abs(fa - fb).max() <= 1e-15
+print('LIVE-OK')
+"""
+
+
+@pytest.mark.parametrize("dims", [(4, 6, 4, 8), (6, 4, 8, 4)])
+def test_links_oracle_matches_compiled_reference_live(dims):
+    from oracle.pyoracle import ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref/libmilcref.so not built (needs /root/reference)")
+    out = subprocess.run([sys.executable, "-c", _LIVE_LINKS % dict(root=ROOT, dims=dims)], capture_output=True,
+                         text=True, timeout=600)
+    assert "LIVE-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
