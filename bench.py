@@ -624,6 +624,77 @@ def run_block(args):
     return 0
 
 
+def run_links(args):
+    """--workload links: HISQ fermion-link construction on the
+    BASELINE configs[1] lattice: U -> V (fat7) -> W (U(3) projection) -> fat, long, the chain MILC
+    runs for every new gauge field.  value: chains per second with everything resident (CUDA
+    events); e2e: the host-buffer call (thin links H2D, fat + long links D2H inside the timed
+    region); cpu_baseline: the reference's own create_hisq_links_milc (oracle/_ref, OpenMP) on the
+    same input; flop convention: the reference's 2 x 61632 + 1728 flop per site for the two
+    smearing levels and the Naik links (fermion_links_fn_load_milc.c:106,268), projection not counted."""
+    import torch
+    from milc_qcd_b200 import api
+    local_rank = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local_rank)
+    dims = tuple(args.lattice) if args.lattice else DIMS
+    V = int(np.prod(dims))
+    flop = (2 * 61632.0 + 1728.0) * V
+    ctx = api.Context(dims, device=local_rank)
+    for _ in range(max(1, args.warmup)):
+        ms, nsvd = ctx.hisq_links_time(1234, 1)
+    ms, nsvd = ctx.hisq_links_time(1234, max(1, args.steps))
+    U = ctx.hisq_links_fetch(0)
+    fat_dev, lng_dev = ctx.hisq_links_fetch(3), ctx.hisq_links_fetch(4)
+    # end to end: pinned host links in, fat + long out
+    pin = [torch.zeros(U.shape, dtype=torch.float64).pin_memory() for _ in range(3)]
+    hU, hF, hL = (p.numpy() for p in pin)
+    hU[...] = U
+    import ctypes as C
+    c1, c2 = ctx._coeffs(ctx.HISQ_FAT7), ctx._coeffs(ctx.HISQ_ASQTAD_LIKE)
+
+    def chain_host():
+        n = C.c_longlong(0)
+        api.check(ctx.lib.b200ks_hisq_links(ctx.h, c1, c2, hU.ctypes.data, None, None, hF.ctypes.data, hL.ctypes.data, 2,
+                                            C.byref(n)), "b200ks_hisq_links")
+    chain_host()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        chain_host()
+    ms_e2e = 1e3 * (time.perf_counter() - t0) / max(1, args.steps)
+    same = bool(np.array_equal(hF, fat_dev) and np.array_equal(hL, lng_dev))
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import pyoracle
+            cores = os.cpu_count() or 1
+            os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+            if pyoracle.ref_available("_omp"):
+                ref = pyoracle.MilcRef(dims, "_omp")
+                t0 = time.perf_counter()
+                r = ref.hisq_links(U)
+                t_cpu = time.perf_counter() - t0
+                err = {k: float(np.abs(r[k] - x).max() / np.abs(r[k]).max()) for k, x in (("fat", fat_dev), ("lng", lng_dev))}
+                cpu = {"value": flop / t_cpu / 1e9, "unit": "GFLOP/s", "seconds": t_cpu, "cores": cores, "kind": "reference",
+                       "sample": "one full chain on the same %s thin links, create_hisq_links_milc (oracle/_ref, -O3 -DOMP)"
+                                 % "x".join(map(str, dims)),
+                       "svd_branch_links": r["nsvd"], "max_rel_diff_gpu_vs_reference": err}
+        except Exception as ex:
+            cpu = {"value": None, "kind": "unavailable", "sample": repr(ex)}
+    # bytes per chain: 72 staple passes per level read 6 matrices + read/write the fat link (+ staple store)
+    print(json.dumps({"metric": "hisq_link_construction_gflops", "unit": "GFLOP/s", "n_gpus": 1, "higher_is_better": True,
+                      "data": "synthetic", "value": flop / (ms * 1e-3) / 1e9, "ms_per_chain": ms,
+                      "config": {"workload": "HISQ link construction U->V->W->(fat,long), Haar-random thin links %s"
+                                             % "x".join(map(str, dims)), "lattice": list(dims),
+                                 "flop_convention": "MILC: 61632 flop/site per smearing level + 1728 for the Naik links"},
+                      "svd_branch_links": nsvd,
+                      "e2e": {"value": flop / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_chain": ms_e2e,
+                              "h2d_bytes_per_step": int(U.nbytes), "d2h_bytes_per_step": int(2 * U.nbytes),
+                              "same_bits_as_resident_chain": same},
+                      "cpu_baseline": cpu, "device_bytes": ctx.device_bytes()}))
+    ctx.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -637,9 +708,10 @@ def main():
     ap.add_argument("--long-recon", type=int, default=0, help="long-link storage: 18, 14 or 0 = decided on the data")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lattice", type=int, nargs=4, default=None, help="override the lattice (nx ny nz nt)")
-    ap.add_argument("--workload", default="cg", choices=["cg", "multishift", "block"],
+    ap.add_argument("--workload", default="cg", choices=["cg", "multishift", "block", "links"],
                     help="cg (default, the driver's line): single-mass CG; multishift: BASELINE configs[2]; "
-                         "block: multi-right-hand-side CG (ks_congrad_block_parity seam)")
+                         "block: multi-right-hand-side CG (ks_congrad_block_parity seam); "
+                         "links: HISQ fermion-link construction (qudaLoadUnitarizedLink / qudaLoadKSLink seam)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -647,6 +719,8 @@ def main():
         return run_multishift(args)
     if args.workload == "block":
         return run_block(args)
+    if args.workload == "links":
+        return run_links(args)
     return run_b200(args)
 
 

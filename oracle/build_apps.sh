@@ -11,6 +11,8 @@
 #                                                -DUSE_CG_GPU, Makefile:419-474) but linked to
 #                                                milc_qcd_b200/libb200ks.so through
 #                                                include/quda_milc_interface.h  (route 2)
+#   ks_spectrum_hisq_b200fl su3_rhmc_hisq_b200fl as _b200 plus -DUSE_FL_GPU (WANT_FL_GPU=true): the
+#                                                HISQ links are built on the GPU as well
 #
 # It also stages the sample inputs, golden outputs, tolerance files and sample lattices the
 # reference's own regression uses (ks_spectrum/test, ks_imp_rhmc/test, binary_samples) into
@@ -75,6 +77,11 @@ build_app() {  # name appdir flavour(cpu|b200) appfiles generic gks defs
   local dsl="dslash_fn_dblstore" extra_gen="" extra_gks=""
   if [ "$flav" = "b200" ]; then
     fl="$fl $GPU_FLAGS"; dsl="dslash_fn"; extra_gen="milc_to_quda_utilities"; extra_gks="d_congrad5_fn_gpu ks_multicg_offset_gpu"
+  elif [ "$flav" = "b200fl" ]; then
+    # additionally WANT_FL_GPU=true (Makefile:453-455, Make_template_combos:167-171,190): the fermion
+    # links are built through qudaLoadUnitarizedLink / qudaLoadKSLink
+    fl="$fl $GPU_FLAGS -DUSE_FL_GPU"; dsl="dslash_fn"; extra_gen="milc_to_quda_utilities"
+    extra_gks="d_congrad5_fn_gpu ks_multicg_offset_gpu fermion_links_fn_load_gpu"
   else
     fl="$fl $CPU_FLAGS"
   fi
@@ -93,7 +100,7 @@ build_app() {  # name appdir flavour(cpu|b200) appfiles generic gks defs
   [ "$name" = "ks_spectrum_hisq" ] && echo "gcc -c $fl $REF/generic_wilson/gammas.c -o $obj/gw_gammas.o" >> "$obj/cmds.txt"
   xargs -d '\n' -P "$(nproc)" -I{} bash -c {} < "$obj/cmds.txt"
   local exe="$OUT/apps/${name}_${flav}"
-  if [ "$flav" = "b200" ]; then
+  if [ "$flav" != "cpu" ]; then
     g++ -o "$exe" "$obj"/*.o "$LIBOBJ"/*.o -L"$ROOT/milc_qcd_b200" -lb200ks \
         -Wl,-rpath,'$ORIGIN/../../../milc_qcd_b200' -L/usr/local/cuda/lib64 -lcudart -lm
   else
@@ -102,7 +109,7 @@ build_app() {  # name appdir flavour(cpu|b200) appfiles generic gks defs
   echo "built $exe"
 }
 
-for flav in cpu b200; do
+for flav in cpu b200 b200fl; do
   build_app ks_spectrum_hisq ks_spectrum "$flav" "$SPEC_APP" "$SPEC_GENERIC" "$SPEC_GKS" "$SPEC_DEFS"
   build_app su3_rhmc_hisq ks_imp_rhmc "$flav" "$RHMC_APP" "$RHMC_GENERIC" "$RHMC_GKS" "$RHMC_DEFS"
 done

@@ -129,3 +129,32 @@ def test_su3_rhmc_hisq_on_libb200ks_matches_reference_goldens(tmp_path):
         pytest.skip("oracle/_ref/apps not built")
     out = check_rhmc("su3_rhmc_hisq_b200", tmp_path)
     assert any("multicg_offset_QUDA" in ln for ln in out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["nd", "spectrum2"])
+def test_ks_spectrum_hisq_with_gpu_link_construction_matches_reference_goldens(case, tmp_path):
+    """-DUSE_FL_GPU build (WANT_FL_GPU=true): the HISQ links themselves are built by libb200ks
+    (qudaLoadUnitarizedLink + qudaLoadKSLink), then the solves run on them; same goldens."""
+    if not _have("ks_spectrum_hisq_b200fl"):
+        pytest.skip("oracle/_ref/apps not built")
+    out = check_spectrum("ks_spectrum_hisq_b200fl", case, tmp_path, stdout_strict=False)
+    assert any("fn_QUDA" in ln or "multicg_offset_QUDA" in ln for ln in out), "solves did not go through the GPU seam"
+
+
+@pytest.mark.gpu
+def test_su3_rhmc_hisq_with_gpu_link_construction_matches_reference_goldens(tmp_path):
+    """A full RHMC trajectory: links rebuilt on the GPU after every gauge update."""
+    if not _have("su3_rhmc_hisq_b200fl"):
+        pytest.skip("oracle/_ref/apps not built")
+    out = check_rhmc("su3_rhmc_hisq_b200fl", tmp_path)
+    assert any("multicg_offset_QUDA" in ln for ln in out)
+
+
+def test_b200fl_apps_bind_the_link_construction_symbols():
+    if not _have("ks_spectrum_hisq_b200fl"):
+        pytest.skip("oracle/_ref/apps not built")
+    for app in ("ks_spectrum_hisq_b200fl", "su3_rhmc_hisq_b200fl"):
+        nm = subprocess.run(["nm", "-D", "--undefined-only", os.path.join(APPS, app)], capture_output=True, text=True).stdout
+        used = {ln.split()[-1] for ln in nm.splitlines() if " quda" in ln}
+        assert {"qudaLoadKSLink", "qudaLoadUnitarizedLink"} <= used, (app, used)
