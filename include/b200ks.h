@@ -164,6 +164,27 @@ int b200ks_multicg(b200ks_ctx *ctx, const void *src, void *const *psim, const do
                    int num_offsets, const b200ks_invert_args *args, b200ks_invert_result *res,
                    int host_prec);
 
+/* ---- device-resident solve sequences ----------------------
+ * b200ks_mat_invert_uml: dst = M^-1 src, M = D + 2m, on BOTH parities for nsrc sources, the
+ *   sequence of mat_invert_uml_field / mat_invert_block_uml (generic_ks/mat_invert.c:328-402,
+ *   409-475): tmp = M^+ src; even solve (M^+ M) dst_e = tmp_e starting from dst_e; odd sites
+ *   reconstructed, dst_o = (src_o - D_oe dst_e)/2m; odd solve from that guess.  One upload of
+ *   src and dst, one download of dst per source; the sources go through the block solver four at
+ *   a time.  args->parity is ignored; res[2k], res[2k+1] = even and odd solve of source k;
+ *   returns the total number of iterations (MILC: qic->final_iters = even + odd).
+ * b200ks_multicg_rational: multi-shift solve + what its RHMC callers do next, on the device:
+ *   fill_other != 0: psim[j](other parity) = D psim[j], both parities returned -- the input the
+ *     fermion force wants (ks_imp_rhmc/update_h_rhmc.c:75-86, one dslash_field per shift);
+ *   residues != NULL: dest(parity) = residues[0] src + sum_j residues[j+1] psim[j], ks_rateval
+ *     (ks_imp_rhmc/ks_ratinv.c:121-138); psim may then be NULL and only dest travels back. */
+int b200ks_mat_invert_uml(b200ks_ctx *ctx, int nsrc, const void *const *src, void *const *dst, double mass,
+                          const b200ks_invert_args *args, b200ks_invert_result *res, int host_prec);
+int b200ks_mat_invert_uml_dev(b200ks_ctx *ctx, int nsrc, const int *vsrc, const int *vdst, double mass,
+                              const b200ks_invert_args *args, b200ks_invert_result *res);
+int b200ks_multicg_rational(b200ks_ctx *ctx, const void *src, void *const *psim, void *dest,
+                            const double *offsets, const double *residues, int num_offsets, int fill_other,
+                            const b200ks_invert_args *args, b200ks_invert_result *res, int host_prec);
+
 /* ---- fermion-link construction ---------------------------
  * Links are su3_matrix[4*V] in MILC order (link[4*i+dir]) with KS phases and boundary signs
  * in (phases_in = 1); path_coeff = {one_link, naik, three_staple, five_staple, seven_staple,

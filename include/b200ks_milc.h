@@ -111,6 +111,13 @@ int ks_congrad_block_parity_gpu(int nsrc, su3_vector **t_src, su3_vector **t_des
 int ks_multicg_offset_field_gpu(su3_vector *src, su3_vector **psim, ks_param *ksp, int num_offsets,
                                 quark_invert_control *qic, imp_ferm_links_t *fn);
 void dslash_fn_field(su3_vector *src, su3_vector *dest, int parity, fn_links_t *fn);
+/* Optional (no seam in the reference: a maintainer maps the names under USE_CG_GPU, see
+ * INTEGRATION.md): the UML propagator solve as one device-resident sequence, prototypes of
+ * mat_invert_uml_field / mat_invert_block_uml (generic_ks/mat_invert.c:328-402,409-475). */
+int mat_invert_uml_field_gpu(su3_vector *src, su3_vector *dst, quark_invert_control *qic, Real mass,
+                             imp_ferm_links_t *fn);
+int mat_invert_block_uml_gpu(int nsrc, su3_vector **src, su3_vector **dst, quark_invert_control *qic, Real mass,
+                             imp_ferm_links_t *fn);
 imp_ferm_links_t *get_fn_last(void);
 void set_fn_last(imp_ferm_links_t *fn_last_new);
 

@@ -63,6 +63,13 @@ SYMBOLS = [
                                            C.POINTER(InvertArgs), C.POINTER(InvertResult)]),
     ("b200ks_dslash_block_dev", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int]),
     ("b200ks_dslash_block_time", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    ("b200ks_mat_invert_uml", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double,
+                                        C.POINTER(InvertArgs), C.POINTER(InvertResult), C.c_int]),
+    ("b200ks_mat_invert_uml_dev", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_double,
+                                            C.POINTER(InvertArgs), C.POINTER(InvertResult)]),
+    ("b200ks_multicg_rational", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(InvertArgs),
+                                          C.POINTER(InvertResult), C.c_int]),
     ("b200ks_ks_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ("b200ks_unitarized_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.POINTER(C.c_longlong)]),

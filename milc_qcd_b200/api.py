@@ -217,6 +217,33 @@ class Context:
                    "b200ks_congrad_block")
         return it, [res[j].as_dict() for j in range(n)]
 
+    def mat_invert_uml(self, srcs, dsts, mass, max_iter, nrestart, resid, relresid=0.0, mixed_precision=0):
+        """b200ks_mat_invert_uml: dst_k = (D + 2m)^-1 src_k on both parities, resident sequence."""
+        n = len(srcs)
+        args = InvertArgs(EVEN, max_iter, nrestart, resid, relresid, mixed_precision, 0)
+        res = (InvertResult * (2 * n))()
+        sp = (C.c_void_p * n)(*[_ptr(a).value for a in srcs])
+        dp = (C.c_void_p * n)(*[_ptr(a).value for a in dsts])
+        it = check(self.lib.b200ks_mat_invert_uml(self.h, n, sp, dp, mass, C.byref(args), res, _host_prec(srcs[0])),
+                   "b200ks_mat_invert_uml")
+        return it, [(res[2 * k].as_dict(), res[2 * k + 1].as_dict()) for k in range(n)]
+
+    def multicg_rational(self, src, offsets, parity, max_iter, nrestart, resid, residues=None, want_psim=True,
+                         fill_other=False, mixed_precision=0):
+        """b200ks_multicg_rational: returns (iterations, psim list or None, dest or None, results)."""
+        n = len(offsets)
+        args = InvertArgs(parity, max_iter, nrestart, resid, 0.0, mixed_precision, 0)
+        res = (InvertResult * n)()
+        offs = (C.c_double * n)(*[float(o) for o in offsets])
+        psim = [np.zeros_like(src) for _ in range(n)] if want_psim else None
+        ptrs = (C.c_void_p * n)(*[p.ctypes.data for p in psim]) if want_psim else None
+        dest = np.zeros_like(src) if residues is not None else None
+        rr = (C.c_double * (n + 1))(*[float(r) for r in residues]) if residues is not None else None
+        it = check(self.lib.b200ks_multicg_rational(self.h, _ptr(src), ptrs, _ptr(dest) if dest is not None else None,
+                                                    offs, rr, n, int(fill_other), C.byref(args), res, _host_prec(src)),
+                   "b200ks_multicg_rational")
+        return it, psim, dest, [res[j].as_dict() for j in range(n)]
+
     def multicg(self, src, psim, offsets, parity, max_iter, nrestart, resid, mixed_precision=0,
                 check_interval=0):
         n = len(offsets)
@@ -393,6 +420,33 @@ def ks_congrad_block_parity_gpu(nsrc, t_src, t_dest, qic, mass, fn):
         worst = max(res, key=lambda r: r["final_rsq"])
         _store(qic, dict(worst, final_iters=it, converged=int(all(r["converged"] for r in res)),
                          final_restart=max(r["final_restart"] for r in res)))
+    return it
+
+
+def mat_invert_uml_field(src, dst, qic, mass, fn):
+    """generic_ks/mat_invert.c:328-402 as one device-resident sequence (b200ks_mat_invert_uml):
+    dst = (D + 2m)^-1 src on all sites.  Returns the iterations of both solves; qic->final_iters
+    is their sum, the other outputs are the odd solve's, as in the reference."""
+    if fn is None:
+        raise ValueError("mat_invert_uml_field: Called with NULL fn")
+    ctx = _context_for(fn)
+    it, res = ctx.mat_invert_uml([src], [dst], mass, qic.max, qic.nrestart, qic.resid, qic.relresid, qic.mixed_precision)
+    even, odd = res[0]
+    _store(qic, dict(odd, final_iters=even["final_iters"] + odd["final_iters"]))
+    qic.parity = ODD
+    return it
+
+
+def mat_invert_block_uml(nsrc, src, dst, qic, mass, fn):
+    """generic_ks/mat_invert.c:409-475: the same sequence for nsrc sources through the block solver."""
+    if fn is None:
+        raise ValueError("mat_invert_block_uml: Called with NULL fn")
+    ctx = _context_for(fn)
+    it, res = ctx.mat_invert_uml(src[:nsrc], dst[:nsrc], mass, qic.max, qic.nrestart, qic.resid, qic.relresid,
+                                 qic.mixed_precision)
+    worst = max((r for pair in res for r in pair), key=lambda r: r["final_rsq"])
+    _store(qic, dict(worst, final_iters=it, converged=int(all(r["converged"] for pair in res for r in pair))))
+    qic.parity = ODD
     return it
 
 

@@ -2103,6 +2103,138 @@ extern "C" int b200ks_multicg(b200ks_ctx *c, const void *src, void *const *psim,
   return it;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// device-resident solve sequences: what MILC strings together from
+// host-buffer calls, here with every intermediate vector staying in HBM.
+static void axpby_d(b200ks_ctx *c, DevVec &out, double a, const DevVec &x, double b, const DevVec *y, int pbit) {
+  LAUNCH(c, (axpby_kernel<double>), nblocks(c->g.Vh), (double2 *)out.p[pbit], a, (const double2 *)x.p[pbit], b,
+         y ? (const double2 *)y->p[pbit] : (const double2 *)nullptr, c->g.stride, c->g.Vh);
+}
+
+// mat_invert_uml_field / mat_invert_block_uml (generic_ks/mat_invert.c:328-402,409-475) for nsrc
+// sources: tmp = M^+ src (both parities), even solve (M^+ M) dst_e = tmp_e from the guess in dst_e,
+// dst_o = (src_o - D_oe dst_e)/2m, odd solve from that guess ("polish").  res[2*k], res[2*k+1]: the
+// even and the odd solve of source k.  Returns the total number of iterations.
+static int uml_any(b200ks_ctx *c, int nsrc, DevVec *const *src, DevVec *const *dst, double mass,
+                   const b200ks_invert_args &args_in, b200ks_invert_result *res) {
+  if (mass == 0.0) return fail(B200KS_EINVAL, "mat_invert_uml: the odd-site reconstruction divides by 2m");
+  CHK(links_ensure(c, 2));
+  std::vector<DevVec *> tmp(nsrc);
+  DevVec *ttt = nullptr;
+  CHK(pool_get(c, 2, 2, &ttt));
+  for (int k = 0; k < nsrc; k++) {
+    CHK(pool_get(c, 2, kBlockPool + 6 * kMaxRhs + 64 + k, &tmp[k]));
+    Epi e;   // tmp = -(D src - 2m src) = M^+ src, mat_invert.c:56-75 (ks_dirac_adj_op)
+    e.kind = 1; e.s = -2.0 * mass; e.w = src[k];
+    for (int pbit = 0; pbit < 2; pbit++) {
+      CHK(dslash_T<double>(c, *src[k], *tmp[k], pbit, e));
+      axpby_d(c, *tmp[k], -1.0, *tmp[k], 0.0, nullptr, pbit);
+    }
+  }
+  b200ks_invert_args args = args_in;
+  std::vector<b200ks_invert_result> r(nsrc);
+  int total = 0;
+  args.parity = B200KS_EVEN;
+  int it = congrad_block_any(c, nsrc, tmp.data(), dst, mass, args, r.data());
+  if (it < 0) return it;
+  total += it;
+  for (int k = 0; k < nsrc; k++) {
+    res[2 * k] = r[k];
+    Epi e;   // dst_o = (src_o - D dst_e) / 2m
+    CHK(dslash_T<double>(c, *dst[k], *ttt, 1, e));
+    axpby_d(c, *dst[k], 1.0 / (2.0 * mass), *src[k], -1.0 / (2.0 * mass), ttt, 1);
+  }
+  args.parity = B200KS_ODD;
+  it = congrad_block_any(c, nsrc, tmp.data(), dst, mass, args, r.data());
+  if (it < 0) return it;
+  total += it;
+  for (int k = 0; k < nsrc; k++) res[2 * k + 1] = r[k];
+  CHK(halo_check(c));
+  return total;
+}
+
+extern "C" int b200ks_mat_invert_uml_dev(b200ks_ctx *c, int nsrc, const int *vsrc, const int *vdst, double mass,
+                                         const b200ks_invert_args *args, b200ks_invert_result *res) {
+  if (!c || !res || nsrc < 1 || !vsrc || !vdst || !args) return fail(B200KS_EINVAL, "b200ks_mat_invert_uml_dev: bad argument");
+  if (args->max_iter <= 0 || args->nrestart <= 0) return fail(B200KS_EINVAL, "max_iter and nrestart must be positive");
+  std::vector<DevVec *> s(nsrc), d(nsrc);
+  for (int k = 0; k < nsrc; k++) {
+    s[k] = uvec(c, vsrc[k]);
+    d[k] = uvec(c, vdst[k]);
+    if (!s[k] || !d[k]) return B200KS_EINVAL;
+    if (s[k] == d[k]) return fail(B200KS_EINVAL, "source and solution must be different fields");
+  }
+  CU(cudaSetDevice(c->device));
+  return uml_any(c, nsrc, s.data(), d.data(), mass, *args, res);
+}
+
+extern "C" int b200ks_mat_invert_uml(b200ks_ctx *c, int nsrc, const void *const *src, void *const *dst, double mass,
+                                     const b200ks_invert_args *args, b200ks_invert_result *res, int host_prec) {
+  if (!c || !res || nsrc < 1 || !src || !dst || !args) return fail(B200KS_EINVAL, "b200ks_mat_invert_uml: bad argument");
+  if (args->max_iter <= 0 || args->nrestart <= 0) return fail(B200KS_EINVAL, "max_iter and nrestart must be positive");
+  CU(cudaSetDevice(c->device));
+  int total = 0;
+  for (int k0 = 0; k0 < nsrc; k0 += kMaxRhs) {
+    const int n = std::min(kMaxRhs, nsrc - k0);
+    DevVec *s[kMaxRhs], *d[kMaxRhs];
+    for (int q = 0; q < n; q++) {
+      if (!src[k0 + q] || !dst[k0 + q]) return fail(B200KS_EINVAL, "b200ks_mat_invert_uml: null field");
+      CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q, &s[q]));
+      CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q + 1, &d[q]));
+      CHK(upload(c, *s[q], src[k0 + q], B200KS_EVENANDODD, host_prec));
+      CHK(upload(c, *d[q], dst[k0 + q], B200KS_EVENANDODD, host_prec));
+    }
+    const int it = uml_any(c, n, s, d, mass, *args, res + 2 * k0);
+    if (it < 0) return it;
+    for (int q = 0; q < n; q++) CHK(download(c, *d[q], dst[k0 + q], B200KS_EVENANDODD, host_prec));
+    total += it;
+  }
+  return total;
+}
+
+// Multi-shift solve followed, on the device, by what its RHMC callers do with the solutions:
+//   fill_other != 0 : psim_j(other parity) = D psim_j for every shift -- the fermion force wants
+//                     both parities (ks_imp_rhmc/update_h_rhmc.c:82-84); psim[j] then receive both
+//   residues != NULL: dest = residues[0]*src + sum_j residues[j+1]*psim_j on args->parity, the
+//                     rational function itself (ks_rateval, ks_imp_rhmc/ks_ratinv.c:121-138); only
+//                     dest travels back (psim may be NULL)
+extern "C" int b200ks_multicg_rational(b200ks_ctx *c, const void *src, void *const *psim, void *dest, const double *offsets,
+                                       const double *residues, int n, int fill_other, const b200ks_invert_args *args,
+                                       b200ks_invert_result *res, int host_prec) {
+  if (!c || !src || !res || n < 1 || !offsets) return fail(B200KS_EINVAL, "b200ks_multicg_rational: bad argument");
+  if (residues && !dest) return fail(B200KS_EINVAL, "b200ks_multicg_rational: residues without dest");
+  CHK(check_ms_args(offsets, n, args));
+  CU(cudaSetDevice(c->device));
+  CHK(links_ensure(c, 2));
+  const int pb = parity_bit(args->parity);
+  DevVec *b = nullptr, *acc = nullptr;
+  CHK(pool_get(c, 2, 0, &b));
+  CHK(upload(c, *b, src, args->parity, host_prec));
+  std::vector<DevVec *> ps(n);
+  for (int j = 0; j < n; j++) CHK(pool_get(c, 2, 5 + B200KS_MAX_SHIFTS + j, &ps[j]));
+  const int it = multicg_any(c, *b, ps.data(), offsets, n, *args, res);
+  if (it < 0) return it;
+  if (residues) {
+    CHK(pool_get(c, 2, 1, &acc));
+    axpby_d(c, *acc, residues[0], *b, 0.0, nullptr, pb);
+    for (int j = 0; j < n; j++) axpby_d(c, *acc, 1.0, *acc, residues[j + 1], ps[j], pb);
+    CHK(download(c, *acc, dest, args->parity, host_prec));
+  }
+  if (psim) {
+    if (fill_other) {
+      Epi e;
+      for (int j = 0; j < n; j++) CHK(dslash_T<double>(c, *ps[j], *ps[j], pb ^ 1, e));
+      CHK(halo_check(c));
+    }
+    for (int j = 0; j < n; j++) {
+      if (!psim[j]) return fail(B200KS_EINVAL, "b200ks_multicg_rational: null solution field");
+      CHK(download(c, *ps[j], psim[j], fill_other ? B200KS_EVENANDODD : args->parity, host_prec));
+    }
+  }
+  return it;
+}
+
 // ---------------------------------------------------------------------------------------------
 // one-rank-per-GPU contexts
 extern "C" int b200ks_comm_unique_id(void *out128) {

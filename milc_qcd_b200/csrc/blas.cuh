@@ -91,6 +91,30 @@ __global__ void __launch_bounds__(kBlock) convert_kernel(typename Vec2<TD>::type
   }
 }
 
+// out = a*x + b*y on one parity half (out may alias x or y); y == nullptr: out = a*x
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+axpby_kernel(typename Vec2<T>::type *out, T a, const typename Vec2<T>::type *x, T b, const typename Vec2<T>::type *y,
+             int stride, int n) {
+  using T2 = typename Vec2<T>::type;
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const size_t o = (size_t)c * stride + i;
+    const T2 xv = x[o];
+    T2 r;
+    r.x = a * xv.x;
+    r.y = a * xv.y;
+    if (y != nullptr) {
+      const T2 yv = y[o];
+      r.x = fma(b, yv.x, r.x);
+      r.y = fma(b, yv.y, r.y);
+    }
+    out[o] = r;
+  }
+}
+
 // ---- single-mass CG ------------------------------------------------------------------------
 // (re)start: ttt already holds D D x - 4m^2 x (= -A x).  r = b + ttt ; p = r ;
 // red: |r|^2 and (optionally) sum |r_s|^2/|x_s|^2.       d_congrad5_fn_milc.c:199-218

@@ -220,6 +220,61 @@ int ks_congrad_block_parity_gpu(int nsrc, su3_vector **t_src, su3_vector **t_des
   return iters;
 }
 
+/* mat_invert_uml_field / mat_invert_block_uml (generic_ks/mat_invert.c:328-402,409-475) as one
+ * device-resident sequence: M^+ src, even solve, odd reconstruction, odd polish. */
+int mat_invert_block_uml_gpu(int nsrc, su3_vector **src, su3_vector **dst, quark_invert_control *qic, Real mass,
+                             imp_ferm_links_t *fn) {
+  char myname[] = "mat_invert_block_uml_gpu";
+  b200ks_invert_args a;
+  b200ks_invert_result r[2 * B200KS_MAX_BLOCK];
+  int iters, k;
+
+  qic->size_r = 0;
+  qic->size_relr = 0;
+  qic->final_iters = 0;
+  qic->final_restart = 0;
+  qic->converged = 1;
+  qic->final_rsq = 0.;
+  qic->final_relrsq = 0.;
+  if (nsrc <= 0) return 0;
+  if (nsrc > B200KS_MAX_BLOCK) {
+    printf("%s: more than %d sources\n", myname, B200KS_MAX_BLOCK);
+    FATAL(1);
+  }
+  if (fn == NULL) {
+    printf("%s(0): Called with NULL fn\n", myname);
+    FATAL(1);
+  }
+  refresh_links(myname, fn);
+  memset(&a, 0, sizeof(a));
+  a.parity = EVEN;
+  a.max_iter = qic->max;
+  a.nrestart = qic->nrestart;
+  a.resid = qic->resid;
+  a.relresid = qic->relresid;
+  a.mixed_precision = (qic->prec == 1) ? (MIXED ? MIXED : 1) : MIXED;
+  if (MILC_PRECISION == 2 && qic->prec == 2) a.mixed_precision = MIXED;
+  iters = b200ks_mat_invert_uml(context(myname), nsrc, (const void *const *)src, (void *const *)dst, (double)mass, &a, r,
+                                MILC_PRECISION);
+  if (iters < 0) die(myname);
+  for (k = 0; k < 2 * nsrc; k++) {
+    if (r[k].final_rsq > qic->final_rsq) qic->final_rsq = (Real)r[k].final_rsq;
+    if (r[k].final_relrsq > qic->final_relrsq) qic->final_relrsq = (Real)r[k].final_relrsq;
+    if (r[k].size_r > qic->size_r) qic->size_r = (Real)r[k].size_r;
+    if (r[k].final_restart > qic->final_restart) qic->final_restart = r[k].final_restart;
+    if (!r[k].converged) qic->converged = 0;
+  }
+  qic->final_iters = iters;
+  qic->parity = ODD; /* the state the reference leaves behind (mat_invert.c:392) */
+  TOTAL_ITERS += iters;
+  return iters;
+}
+
+int mat_invert_uml_field_gpu(su3_vector *src, su3_vector *dst, quark_invert_control *qic, Real mass,
+                             imp_ferm_links_t *fn) {
+  return mat_invert_block_uml_gpu(1, &src, &dst, qic, mass, fn);
+}
+
 int ks_multicg_offset_field_gpu(su3_vector *src, su3_vector **psim, ks_param *ksp, int num_offsets,
                                 quark_invert_control *qic, imp_ferm_links_t *fn) {
   char myname[] = "ks_multicg_offset_field_gpu";
