@@ -116,7 +116,7 @@ void dslash_fn_field(su3_vector *src, su3_vector *dest, int parity, fn_links_t *
  * mat_invert_uml_field / mat_invert_block_uml (generic_ks/mat_invert.c:328-402,409-475). */
 int mat_invert_uml_field_gpu(su3_vector *src, su3_vector *dst, quark_invert_control *qic, Real mass,
                              imp_ferm_links_t *fn);
-int mat_invert_block_uml_gpu(int nsrc, su3_vector **src, su3_vector **dst, quark_invert_control *qic, Real mass,
+int mat_invert_block_uml_gpu(su3_vector **src, su3_vector **dst, Real mass, int nsrc, quark_invert_control *qic,
                              imp_ferm_links_t *fn);
 imp_ferm_links_t *get_fn_last(void);
 void set_fn_last(imp_ferm_links_t *fn_last_new);

@@ -437,7 +437,7 @@ def mat_invert_uml_field(src, dst, qic, mass, fn):
     return it
 
 
-def mat_invert_block_uml(nsrc, src, dst, qic, mass, fn):
+def mat_invert_block_uml(src, dst, mass, nsrc, qic, fn):
     """generic_ks/mat_invert.c:409-475: the same sequence for nsrc sources through the block solver."""
     if fn is None:
         raise ValueError("mat_invert_block_uml: Called with NULL fn")

@@ -222,7 +222,7 @@ int ks_congrad_block_parity_gpu(int nsrc, su3_vector **t_src, su3_vector **t_des
 
 /* mat_invert_uml_field / mat_invert_block_uml (generic_ks/mat_invert.c:328-402,409-475) as one
  * device-resident sequence: M^+ src, even solve, odd reconstruction, odd polish. */
-int mat_invert_block_uml_gpu(int nsrc, su3_vector **src, su3_vector **dst, quark_invert_control *qic, Real mass,
+int mat_invert_block_uml_gpu(su3_vector **src, su3_vector **dst, Real mass, int nsrc, quark_invert_control *qic,
                              imp_ferm_links_t *fn) {
   char myname[] = "mat_invert_block_uml_gpu";
   b200ks_invert_args a;
@@ -272,7 +272,7 @@ int mat_invert_block_uml_gpu(int nsrc, su3_vector **src, su3_vector **dst, quark
 
 int mat_invert_uml_field_gpu(su3_vector *src, su3_vector *dst, quark_invert_control *qic, Real mass,
                              imp_ferm_links_t *fn) {
-  return mat_invert_block_uml_gpu(1, &src, &dst, qic, mass, fn);
+  return mat_invert_block_uml_gpu(&src, &dst, mass, 1, qic, fn);
 }
 
 int ks_multicg_offset_field_gpu(su3_vector *src, su3_vector **psim, ks_param *ksp, int num_offsets,

@@ -64,6 +64,12 @@ def test_uml_sequence_matches_reference_sequence(api, oracle, dims, nsrc, mixed)
         assert np.array_equal(d1, dsts[0])
     else:
         assert np.linalg.norm(d1 - dsts[0]) <= 1e-7 * np.linalg.norm(dsts[0])
+    if nsrc > 1:   # block form, the reference's argument order (mat_invert.c:409-411)
+        dn = [np.zeros_like(s) for s in srcs]
+        qb = api.quark_invert_control(max=500, nrestart=5, resid=resid, mixed_precision=mixed)
+        itb = api.mat_invert_block_uml(srcs, dn, mass, nsrc, qb, fn)
+        assert itb == tot and qb.converged == 1 and qb.final_iters == itb
+        assert all(np.array_equal(a, b) for a, b in zip(dn, dsts))
     ctx.close()
 
 
