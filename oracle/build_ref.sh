@@ -28,6 +28,9 @@ GKS="dslash_fn_dblstore.c fn_links_milc.c d_congrad5_fn_milc.c ks_multicg_offset
 # HISQ link construction: U -> V (fat7) -> W (U(3) projection) -> fat, long
 GEN="$GEN general_staple.c path_product.c gauge_utilities.c project_su3_hit.c reunitarize2.c stout_smear.c"
 GKS="$GKS fermion_links_hisq_load_milc.c fermion_links_fn_load_milc.c ks_action_paths_hisq.c su3_mat_op.c rephase.c"
+# the UML propagator-solve sequence
+GEN="$GEN report_invert_status.c"
+GKS="$GKS mat_invert.c d_congrad5_fn.c"
 
 build_variant() {  # name precision extra-flags
   local name="$1" prec="$2" extra="$3"

@@ -166,6 +166,7 @@ class MilcRef:
         L.milcref_hisq_links.argtypes = [rp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _dp]
         L.milcref_smear.argtypes = [rp, _dp, ro, C.c_void_p]
         L.milcref_unitarize.argtypes = [rp, ro, C.c_long]
+        L.milcref_mat_invert_uml.argtypes = [rp, ro, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, _dp]
         self.dims = tuple(int(d) for d in dims)
         if L.milcref_init(*self.dims) != 0:
             raise RuntimeError("MilcRef: process already initialised with another geometry")
@@ -229,6 +230,14 @@ class MilcRef:
         W = np.zeros_like(V)
         n = self.lib.milcref_unitarize(V, W, V.size // 18)
         return W, n
+
+    def mat_invert_uml(self, srcs, dsts, mass, niter, nrestart, resid):
+        """mat_invert_uml_field (one source) / mat_invert_block_uml (several): srcs, dsts arrays of
+        shape (nsrc, V, 3, 2); dsts = guesses in, solutions out.  Returns (iterations, qic dict)."""
+        srcs = np.ascontiguousarray(srcs, self.dtype)
+        out = np.zeros(7)
+        it = self.lib.milcref_mat_invert_uml(srcs, dsts, srcs.shape[0], mass, niter, nrestart, resid, out)
+        return it, _qic(out)
 
     def time_dslash(self, src, parity, ncalls):
         src = np.ascontiguousarray(src, self.dtype)

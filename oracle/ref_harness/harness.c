@@ -233,3 +233,28 @@ int milcref_unitarize(const Real *V, Real *W, long nlinks) {
     u3_unitarize_analytic(&info, (su3_matrix *)V + k, (su3_matrix *)W + k);
   return INFO_HISQ_SVD_COUNTER(&info);
 }
+
+/* ---- UML propagator solve -----------------------------------------
+ * mat_invert_uml_field / mat_invert_block_uml, generic_ks/mat_invert.c:328-402,409-475: dst =
+ * (D + 2m)^-1 src on all sites.  src/dst: nsrc contiguous fields of sites_on_node su3_vectors
+ * (dst = initial guess in, solution out).  out: 7 doubles (qic after the sequence). */
+int milcref_mat_invert_uml(const Real *src, Real *dst, int nsrc, double m, int max, int nrest, double resid,
+                           double *out) {
+  quark_invert_control qic;
+  su3_vector **s = (su3_vector **)malloc(nsrc * sizeof(*s)), **d = (su3_vector **)malloc(nsrc * sizeof(*d));
+  int k, it;
+  memset(&qic, 0, sizeof(qic));
+  param.eigen_param.Nvecs = 0;
+  qic.prec = MILC_PRECISION; qic.min = 0; qic.max = max; qic.nrestart = nrest;
+  qic.parity = EVENANDODD; qic.start_flag = 1; qic.nsrc = nsrc;
+  qic.resid = resid; qic.relresid = 0; qic.deflate = 0;
+  for (k = 0; k < nsrc; k++) {
+    s[k] = (su3_vector *)src + (size_t)k * sites_on_node;
+    d[k] = (su3_vector *)dst + (size_t)k * sites_on_node;
+  }
+  if (nsrc == 1) it = mat_invert_uml_field(s[0], d[0], &qic, (Real)m, h_fn);
+  else it = mat_invert_block_uml(s, d, (Real)m, nsrc, &qic, h_fn);
+  h_unpack(&qic, out);
+  free(s); free(d);
+  return it;
+}

@@ -52,4 +52,9 @@ EXTERN site *lattice;
 #define N_POINTERS 16
 EXTERN char **gen_pt[N_POINTERS];
 
+/* generic_ks/mat_invert.c names the application's eigenpair storage (ks_spectrum/lattice.h);
+   unused here (param.eigen_param.Nvecs = 0) */
+EXTERN double *eigVal;
+EXTERN su3_vector **eigVec;
+
 #endif /* _LATTICE_H */

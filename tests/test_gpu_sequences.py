@@ -21,7 +21,8 @@ def api():
 
 
 def uml_oracle(o, dims, fat, lng, src, guess, mass, niter, nrestart, resid):
-    """mat_invert_uml_field, generic_ks/mat_invert.c:328-402."""
+    """mat_invert_uml_field, generic_ks/mat_invert.c:328-402 (this composition is pinned on the
+    reference's compiled function in tests/test_oracle.py)."""
     h = src.shape[0] // 2
     tmp = -o.dslash(dims, fat, lng, src, EVENANDODD) + 2 * mass * src        # M^+ src
     dst = guess.copy()

@@ -224,3 +224,50 @@ def test_links_oracle_matches_compiled_reference_live(dims):
     out = subprocess.run([sys.executable, "-c", _LIVE_LINKS % dict(root=ROOT, dims=dims)], capture_output=True,
                          text=True, timeout=600)
     assert "LIVE-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+# ---- UML propagator-solve sequence (row f3): the composition used as the GPU tests' oracle --------
+def uml_from_primitives(o, dims, fat, lng, src, guess, mass, niter, nrestart, resid):
+    """generic_ks/mat_invert.c:328-402 composed from the pinned oracle primitives (the same
+    function body as tests/test_gpu_sequences.py::uml_oracle)."""
+    h = src.shape[0] // 2
+    tmp = -o.dslash(dims, fat, lng, src, EVENANDODD) + 2 * mass * src
+    dst = guess.copy()
+    it_e, _ = o.congrad(dims, fat, lng, tmp, dst, mass, EVEN, niter, nrestart, resid)
+    ttt = o.dslash(dims, fat, lng, dst, ODD)
+    dst[h:] = (src[h:] - ttt[h:]) / (2 * mass)
+    it_o, _ = o.congrad(dims, fat, lng, tmp, dst, mass, ODD, niter, nrestart, resid)
+    return dst, it_e + it_o
+
+
+_LIVE_UML = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, %(root)r + '/tests')
+from milc_qcd_b200 import fields as F
+from oracle.pyoracle import Oracle, MilcRef, EVENANDODD
+from test_oracle import uml_from_primitives
+dims = (6, 6, 6, 8)
+fat, lng = F.make_links(dims, seed=77)
+o, r = Oracle(), MilcRef(dims)
+r.set_links(fat, lng)
+srcs = np.stack([F.make_source(dims, seed=200 + k, parity=EVENANDODD) for k in range(3)])
+for nsrc in (1, 3):
+    dsts = np.zeros_like(srcs[:nsrc])
+    it, q = r.mat_invert_uml(srcs[:nsrc], dsts, 0.1, 300, 5, 1e-9)
+    tot = 0
+    for k in range(nsrc):
+        want, itk = uml_from_primitives(o, dims, fat, lng, srcs[k], np.zeros_like(srcs[k]), 0.1, 300, 5, 1e-9)
+        tot += itk
+        assert np.linalg.norm(dsts[k] - want) <= 1e-8 * np.linalg.norm(want), k
+    assert abs(it - tot) <= 2 * nsrc and q['converged'] == 1, (it, tot)
+print('LIVE-OK')
+"""
+
+
+def test_uml_sequence_oracle_matches_compiled_reference_live():
+    from oracle.pyoracle import ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref/libmilcref.so not built (needs /root/reference)")
+    out = subprocess.run([sys.executable, "-c", _LIVE_UML % dict(root=ROOT)], capture_output=True, text=True, timeout=600)
+    assert "LIVE-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
