@@ -20,29 +20,20 @@
 #include "comm.cuh"
 #include "dslash.cuh"
 #include "half.cuh"
-#include "links.cuh"
 #include "mrhs.cuh"
 #include "synth.cuh"
 
 using namespace b200ks;
 
 // ---------------------------------------------------------------------------------------------
+#include "internal.h"
+using namespace b200ks_host;
+
 static thread_local std::string g_err;
-static int fail(int code, const std::string &msg) {
+int b200ks_host::fail(int code, const std::string &msg) {
   g_err = msg;
   return code;
 }
-#define CU(call)                                                                             \
-  do {                                                                                       \
-    cudaError_t e_ = (call);                                                                 \
-    if (e_ != cudaSuccess)                                                                   \
-      return fail(B200KS_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
-  } while (0)
-#define CHK(call)                  \
-  do {                             \
-    int r_ = (call);               \
-    if (r_ < 0) return r_;         \
-  } while (0)
 
 struct DevVec {          // one colour-vector field, both parities
   void *p[2] = {nullptr, nullptr};
@@ -86,9 +77,8 @@ struct b200ks_ctx {
 };
 
 static size_t real_size(int prec) { return prec == B200KS_PREC_DOUBLE ? 8 : prec == B200KS_PREC_SINGLE ? 4 : 2; }
-static int nblocks(int n) { return (n + kBlock - 1) / kBlock; }
 
-static int dev_alloc(b200ks_ctx *c, void **p, size_t bytes) {
+int b200ks_host::dev_alloc(b200ks_ctx *c, void **p, size_t bytes) {
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess)
     return fail(B200KS_ENOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
@@ -101,6 +91,13 @@ static void dev_free(b200ks_ctx *c, void *p, size_t bytes) {
     c->bytes -= bytes;
   }
 }
+void b200ks_host::dev_release(b200ks_ctx *c, void *p, size_t bytes) { dev_free(c, p, bytes); }
+const Geom &b200ks_host::geom(const b200ks_ctx *c) { return c->g; }
+cudaStream_t b200ks_host::stream(const b200ks_ctx *c) { return c->stream; }
+int b200ks_host::device(const b200ks_ctx *c) { return c->device; }
+bool b200ks_host::partitioned(const b200ks_ctx *c) { return c->comm.active; }
+void b200ks_host::count_launch(b200ks_ctx *c) { c->launches++; }
+void *&b200ks_host::link_work(b200ks_ctx *c) { return c->lw; }
 
 // half (prec 0): 4 planes of 32-bit words (3 colours as 2 x u16 + the site scale), half.cuh
 static size_t vec_bytes(const b200ks_ctx *c, int prec) {
@@ -110,7 +107,7 @@ static size_t link_bytes(const b200ks_ctx *c, int prec, int nc = 9) { return (si
 
 // staging buffer for host<->device re-layout, grown on demand and kept (a cudaMalloc/cudaFree
 // pair per transfer costs more than the transfer at small volumes)
-static int stage_get(b200ks_ctx *c, size_t bytes, void **out) {
+int b200ks_host::stage_get(b200ks_ctx *c, size_t bytes, void **out) {
   if (c->stage_bytes < bytes) {
     if (c->stage) { cudaStreamSynchronize(c->stream); dev_free(c, c->stage, c->stage_bytes); c->stage = nullptr; c->stage_bytes = 0; }
     CHK(dev_alloc(c, &c->stage, bytes));
@@ -248,7 +245,6 @@ extern "C" b200ks_ctx *b200ks_create(const int latsize[4], int device) {
   return create_common(latsize, latsize, part, origin, device);
 }
 
-static void lw_free(b200ks_ctx *c);
 extern "C" void b200ks_destroy(b200ks_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -274,7 +270,7 @@ extern "C" void b200ks_destroy(b200ks_ctx *c) {
   if (c->comm.ev_ready) cudaEventDestroy(c->comm.ev_ready);
   if (c->comm.ev_done) cudaEventDestroy(c->comm.ev_done);
   if (c->comm.stream) cudaStreamDestroy(c->comm.stream);
-  lw_free(c);
+  fermion_links_release(c);
   cudaFree(c->stage);
   cudaFree(c->d_dev);
   cudaFree(c->ws.partials);
@@ -308,7 +304,7 @@ extern "C" size_t b200ks_device_bytes(b200ks_ctx *c) { return c ? c->bytes : 0; 
     (c)->launches++;                                                     \
   } while (0)
 
-static int check_launch(const char *what) {
+int b200ks_host::check_launch(const char *what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(B200KS_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
   return 0;
@@ -2495,215 +2491,3 @@ extern "C" int b200ks_links_download(b200ks_ctx *c, void *fat, void *lng, int ho
   return check_launch("unpack_link_kernel");
 }
 
-// ---------------------------------------------------------------------------------------------
-// HISQ / asqtad fermion-link construction (links.cuh)
-struct LinkWork {       // full-lattice matrix fields (double), allocated on first use and kept
-  double2 *in = nullptr, *v = nullptr, *w = nullptr, *fat = nullptr, *lng = nullptr;   // 36 planes each
-  double2 *staple = nullptr, *temp = nullptr;                                           // 9 planes each
-  unsigned long long *nsvd = nullptr;
-  size_t fstride = 0;
-};
-
-static ReunitParams reunit_params() {
-  // defaults: the reference's RHMC build (ks_imp_rhmc/Make_template:204-206)
-  ReunitParams rp;
-  rp.allow_svd = getenv("B200KS_REUNIT_ALLOW_SVD") ? atoi(getenv("B200KS_REUNIT_ALLOW_SVD")) : 1;
-  rp.svd_rel = getenv("B200KS_REUNIT_SVD_REL_ERROR") ? atof(getenv("B200KS_REUNIT_SVD_REL_ERROR")) : 1e-8;
-  rp.svd_abs = getenv("B200KS_REUNIT_SVD_ABS_ERROR") ? atof(getenv("B200KS_REUNIT_SVD_ABS_ERROR")) : 1e-8;
-  return rp;
-}
-
-static int lw_get(b200ks_ctx *c, LinkWork **out) {
-  if (c->comm.active) return fail(B200KS_ESTATE, "link construction: single-GPU contexts only");
-  if (!c->lw) {
-    LinkWork *w = new LinkWork;
-    const size_t V = 2 * (size_t)c->g.Vh;
-    w->fstride = (V + 63) / 64 * 64;
-    const size_t m4 = 36 * w->fstride * sizeof(double2), m1 = 9 * w->fstride * sizeof(double2);
-    int r = 0;
-    r = r < 0 ? r : dev_alloc(c, (void **)&w->in, m4);
-    r = r < 0 ? r : dev_alloc(c, (void **)&w->v, m4);
-    r = r < 0 ? r : dev_alloc(c, (void **)&w->w, m4);
-    r = r < 0 ? r : dev_alloc(c, (void **)&w->fat, m4);
-    r = r < 0 ? r : dev_alloc(c, (void **)&w->lng, m4);
-    r = r < 0 ? r : dev_alloc(c, (void **)&w->staple, m1);
-    r = r < 0 ? r : dev_alloc(c, (void **)&w->temp, m1);
-    r = r < 0 ? r : dev_alloc(c, (void **)&w->nsvd, sizeof(unsigned long long));
-    if (r < 0) {
-      cudaFree(w->in); cudaFree(w->v); cudaFree(w->w); cudaFree(w->fat); cudaFree(w->lng);
-      cudaFree(w->staple); cudaFree(w->temp); cudaFree(w->nsvd);
-      delete w;
-      return r;
-    }
-    c->lw = w;
-  }
-  *out = (LinkWork *)c->lw;
-  return 0;
-}
-static void lw_free(b200ks_ctx *c) {
-  LinkWork *w = (LinkWork *)c->lw;
-  if (!w) return;
-  cudaFree(w->in); cudaFree(w->v); cudaFree(w->w); cudaFree(w->fat); cudaFree(w->lng);
-  cudaFree(w->staple); cudaFree(w->temp); cudaFree(w->nsvd);
-  delete w;
-  c->lw = nullptr;
-}
-
-// host su3_matrix[4*V] (MILC order) <-> full-lattice matrix fields
-static int links_to_dev(b200ks_ctx *c, const LinkWork &w, double2 *dst, const void *host, int host_prec) {
-  const size_t hs = host_prec == 2 ? 8 : 4;
-  const size_t half_bytes = (size_t)c->g.Vh * 72 * hs;
-  void *stage = nullptr;
-  CHK(stage_get(c, half_bytes, &stage));
-  for (int p = 0; p < 2; p++) {
-    CU(cudaMemcpyAsync(stage, (const char *)host + (size_t)p * half_bytes, half_bytes, cudaMemcpyHostToDevice, c->stream));
-    if (host_prec == 2) LAUNCH(c, (pack_link_kernel<double, double>), nblocks(c->g.Vh), dst + (size_t)p * c->g.Vh, (const double *)stage, (int)w.fstride, c->g.Vh);
-    else LAUNCH(c, (pack_link_kernel<double, float>), nblocks(c->g.Vh), dst + (size_t)p * c->g.Vh, (const float *)stage, (int)w.fstride, c->g.Vh);
-    CU(cudaStreamSynchronize(c->stream));   // the staging buffer is reused for the next half
-  }
-  return check_launch("pack_link_kernel");
-}
-static int links_to_host(b200ks_ctx *c, const LinkWork &w, const double2 *src, void *host, int host_prec) {
-  const size_t hs = host_prec == 2 ? 8 : 4;
-  const size_t half_bytes = (size_t)c->g.Vh * 72 * hs;
-  void *stage = nullptr;
-  CHK(stage_get(c, half_bytes, &stage));
-  for (int p = 0; p < 2; p++) {
-    if (host_prec == 2) LAUNCH(c, (unpack_link_kernel<double, double>), nblocks(c->g.Vh), (double *)stage, src + (size_t)p * c->g.Vh, (int)w.fstride, c->g.Vh);
-    else LAUNCH(c, (unpack_link_kernel<double, float>), nblocks(c->g.Vh), (float *)stage, src + (size_t)p * c->g.Vh, (int)w.fstride, c->g.Vh);
-    CU(cudaMemcpyAsync((char *)host + (size_t)p * half_bytes, stage, half_bytes, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-  }
-  return check_launch("unpack_link_kernel");
-}
-
-// fat (and lng unless null) from `links`: load_fatlinks_cpu + load_lnglinks on the device.
-// coeffs = {one_link, naik, three_staple, five_staple, seven_staple, lepage}
-static int smear_dev(b200ks_ctx *c, const LinkWork &w, const double *coeffs, const double2 *links, double2 *fat, double2 *lng) {
-  const Geom &g = c->g;
-  const int V = 2 * g.Vh;
-  const int grid = nblocks(V);
-  const double one_link = coeffs[0], naik = coeffs[1], three = coeffs[2], five = coeffs[3], seven = coeffs[4], lepage = coeffs[5];
-  LAUNCH(c, onelink_kernel, grid, fat, links, one_link - 6.0 * lepage, w.fstride, V);
-  if (!(three == 0.0 && lepage == 0.0 && five == 0.0)) {
-    for (int dir = 0; dir < 4; dir++)
-      for (int nu = 0; nu < 4; nu++) {
-        if (nu == dir) continue;
-        LAUNCH(c, (staple_kernel<true>), grid, w.staple, links + (size_t)dir * 9 * w.fstride, links, fat, dir, nu, three, g, w.fstride, V);
-        if (lepage != 0.0)   // (a zero coefficient adds nothing: the reference computes it anyway)
-          LAUNCH(c, (staple_kernel<false>), grid, (double2 *)nullptr, w.staple, links, fat, dir, nu, lepage, g, w.fstride, V);
-        for (int rho = 0; rho < 4; rho++) {
-          if (rho == dir || rho == nu) continue;
-          LAUNCH(c, (staple_kernel<true>), grid, w.temp, w.staple, links, fat, dir, rho, five, g, w.fstride, V);
-          for (int sig = 0; sig < 4; sig++) {
-            if (sig == dir || sig == nu || sig == rho) continue;
-            LAUNCH(c, (staple_kernel<false>), grid, (double2 *)nullptr, w.temp, links, fat, dir, sig, seven, g, w.fstride, V);
-          }
-        }
-      }
-  }
-  if (lng) LAUNCH(c, longlink_kernel, nblocks(4 * V), lng, links, naik, g, w.fstride, V);
-  return check_launch("link smearing");
-}
-
-static int unitarize_dev(b200ks_ctx *c, const LinkWork &w, const double2 *V, double2 *W, long long *nsvd) {
-  const int n = 2 * c->g.Vh;
-  CU(cudaMemsetAsync(w.nsvd, 0, sizeof(unsigned long long), c->stream));
-  LAUNCH(c, unitarize_kernel, nblocks(4 * n), W, V, w.fstride, n, reunit_params(), w.nsvd);
-  unsigned long long h = 0;
-  CU(cudaMemcpyAsync(&h, w.nsvd, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  if (nsvd) *nsvd = (long long)h;
-  return check_launch("unitarize_kernel");
-}
-
-static int check_link_args(b200ks_ctx *c, const double *coeffs, int host_prec) {
-  if (!c || !coeffs) return fail(B200KS_EINVAL, "link construction: null argument");
-  if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
-  CU(cudaSetDevice(c->device));
-  return 0;
-}
-
-extern "C" int b200ks_ks_links(b200ks_ctx *c, const double *path_coeff, const void *inlink, void *fatlink, void *longlink,
-                               int host_prec) {
-  CHK(check_link_args(c, path_coeff, host_prec));
-  if (!inlink || !fatlink) return fail(B200KS_EINVAL, "b200ks_ks_links: null field");
-  LinkWork *w = nullptr;
-  CHK(lw_get(c, &w));
-  CHK(links_to_dev(c, *w, w->in, inlink, host_prec));
-  CHK(smear_dev(c, *w, path_coeff, w->in, w->fat, longlink ? w->lng : nullptr));
-  CHK(links_to_host(c, *w, w->fat, fatlink, host_prec));
-  if (longlink) CHK(links_to_host(c, *w, w->lng, longlink, host_prec));
-  return 0;
-}
-
-extern "C" int b200ks_unitarized_links(b200ks_ctx *c, const double *path_coeff, const void *inlink, void *vlink, void *wlink,
-                                       int host_prec, long long *nsvd) {
-  CHK(check_link_args(c, path_coeff, host_prec));
-  if (!inlink || !wlink) return fail(B200KS_EINVAL, "b200ks_unitarized_links: null field");
-  LinkWork *w = nullptr;
-  CHK(lw_get(c, &w));
-  CHK(links_to_dev(c, *w, w->in, inlink, host_prec));
-  CHK(smear_dev(c, *w, path_coeff, w->in, w->v, nullptr));
-  CHK(unitarize_dev(c, *w, w->v, w->w, nsvd));
-  if (vlink) CHK(links_to_host(c, *w, w->v, vlink, host_prec));
-  CHK(links_to_host(c, *w, w->w, wlink, host_prec));
-  return 0;
-}
-
-// the whole chain with the intermediate fields resident: one upload, two (to four) downloads
-extern "C" int b200ks_hisq_links(b200ks_ctx *c, const double *coeff1, const double *coeff2, const void *inlink, void *vlink,
-                                 void *wlink, void *fatlink, void *longlink, int host_prec, long long *nsvd) {
-  CHK(check_link_args(c, coeff1, host_prec));
-  if (!coeff2 || !inlink) return fail(B200KS_EINVAL, "b200ks_hisq_links: null argument");
-  LinkWork *w = nullptr;
-  CHK(lw_get(c, &w));
-  CHK(links_to_dev(c, *w, w->in, inlink, host_prec));
-  CHK(smear_dev(c, *w, coeff1, w->in, w->v, nullptr));
-  CHK(unitarize_dev(c, *w, w->v, w->w, nsvd));
-  CHK(smear_dev(c, *w, coeff2, w->w, w->fat, w->lng));
-  if (vlink) CHK(links_to_host(c, *w, w->v, vlink, host_prec));
-  if (wlink) CHK(links_to_host(c, *w, w->w, wlink, host_prec));
-  if (fatlink) CHK(links_to_host(c, *w, w->fat, fatlink, host_prec));
-  if (longlink) CHK(links_to_host(c, *w, w->lng, longlink, host_prec));
-  return 0;
-}
-
-// Benchmark face: Haar-random thin links generated on the device (seed), the chain run `reps` times
-// with everything resident; *ms = CUDA-event milliseconds per chain.  The input and the four outputs
-// can be read back with b200ks_hisq_links_fetch for the CPU comparison.
-extern "C" int b200ks_hisq_links_time(b200ks_ctx *c, const double *coeff1, const double *coeff2, unsigned long long seed,
-                                      int reps, double *ms, long long *nsvd) {
-  CHK(check_link_args(c, coeff1, 2));
-  if (!coeff2 || !ms || reps <= 0) return fail(B200KS_EINVAL, "b200ks_hisq_links_time: bad argument");
-  LinkWork *w = nullptr;
-  CHK(lw_get(c, &w));
-  const int V = 2 * c->g.Vh;
-  LAUNCH(c, synth_thin_kernel, nblocks(V), w->in, c->g, w->fstride, V, (uint64_t)seed);
-  auto chain = [&]() -> int {
-    CHK(smear_dev(c, *w, coeff1, w->in, w->v, nullptr));
-    CHK(unitarize_dev(c, *w, w->v, w->w, nsvd));
-    CHK(smear_dev(c, *w, coeff2, w->w, w->fat, w->lng));
-    return 0;
-  };
-  CHK(chain());
-  CU(cudaEventRecord(c->ev0, c->stream));
-  for (int k = 0; k < reps; k++) CHK(chain());
-  CU(cudaEventRecord(c->ev1, c->stream));
-  CU(cudaEventSynchronize(c->ev1));
-  float t = 0;
-  CU(cudaEventElapsedTime(&t, c->ev0, c->ev1));
-  *ms = (double)t / reps;
-  return check_launch("hisq link chain");
-}
-
-// which: 0 input thin links, 1 V, 2 W, 3 fat, 4 long (of the last chain run on this context)
-extern "C" int b200ks_hisq_links_fetch(b200ks_ctx *c, int which, void *host, int host_prec) {
-  if (!c || !host || which < 0 || which > 4) return fail(B200KS_EINVAL, "b200ks_hisq_links_fetch: bad argument");
-  if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
-  if (!c->lw) return fail(B200KS_ESTATE, "no link construction has run on this context");
-  CU(cudaSetDevice(c->device));
-  LinkWork *w = (LinkWork *)c->lw;
-  const double2 *src = which == 0 ? w->in : which == 1 ? w->v : which == 2 ? w->w : which == 3 ? w->fat : w->lng;
-  return links_to_host(c, *w, src, host, host_prec);
-}

@@ -7,6 +7,7 @@
 // already-enqueued batch into a no-op.  The host polls the flag once per batch.
 #pragma once
 #include "common.cuh"
+#include "layout.cuh"
 
 namespace b200ks {
 
@@ -527,24 +528,6 @@ unpack_vec_kernel(TH *h, const typename Vec2<T>::type *d, int stride, int n) {
     s[2 * c + 1] = (TH)o.y;
   }
 }
-// Links: host su3_matrix[4*V] as [site][dir][9 complex]  ->  device [dir][9][site].
-// Runs once per gauge field; each thread walks its site's 576 contiguous bytes (the
-// strided reads are absorbed by L1/L2), the SoA writes are coalesced.
-template <typename T, typename TH>
-__global__ void __launch_bounds__(kBlock)
-pack_link_kernel(typename Vec2<T>::type *d, const TH *h, int lstride, int n) {
-  const int i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
-  const TH *s = h + (size_t)72 * i;
-#pragma unroll 6
-  for (int m = 0; m < 36; m++) {  // m = dir*9 + e
-    typename Vec2<T>::type o;
-    o.x = (T)s[2 * m];
-    o.y = (T)s[2 * m + 1];
-    d[(size_t)m * lstride + i] = o;
-  }
-}
-
 // ncomp = 4 * (complex numbers per link): 36 for full matrices, 28 for compressed long links
 template <typename TD, typename TS>
 __global__ void __launch_bounds__(kBlock)

@@ -1,0 +1,40 @@
+// internal.h -- what the translation units of libb200ks share on the host side.  The context
+// itself is private to b200ks.cu; other units reach the few members they need through these
+// accessors.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+
+#include "../../include/b200ks.h"
+#include "common.cuh"
+
+namespace b200ks_host {
+
+int fail(int code, const std::string &msg);          // records the message, returns the code
+int check_launch(const char *what);                  // cudaGetLastError -> B200KS_ECUDA
+int dev_alloc(b200ks_ctx *c, void **p, size_t bytes);  // cudaMalloc + bookkeeping (b200ks_device_bytes)
+void dev_release(b200ks_ctx *c, void *p, size_t bytes);
+int stage_get(b200ks_ctx *c, size_t bytes, void **out);   // persistent re-layout staging buffer
+const b200ks::Geom &geom(const b200ks_ctx *c);
+cudaStream_t stream(const b200ks_ctx *c);
+int device(const b200ks_ctx *c);
+bool partitioned(const b200ks_ctx *c);               // one-rank-per-GPU context with a split direction
+void count_launch(b200ks_ctx *c);
+void *&link_work(b200ks_ctx *c);                     // slot owned by fermion_links.cu
+void fermion_links_release(b200ks_ctx *c);           // fermion_links.cu; called by b200ks_destroy
+
+inline int nblocks(int n) { return (n + b200ks::kBlock - 1) / b200ks::kBlock; }
+
+}  // namespace b200ks_host
+
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return b200ks_host::fail(B200KS_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+#define CHK(call)          \
+  do {                     \
+    int r_ = (call);       \
+    if (r_ < 0) return r_; \
+  } while (0)

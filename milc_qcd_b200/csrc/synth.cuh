@@ -10,6 +10,7 @@
 // (generic_ks/fermion_links_fn_twist_milc.c:137-141, generic_ks/rephase.c:83-115).
 #pragma once
 #include "common.cuh"
+#include "layout.cuh"
 
 namespace b200ks {
 
@@ -176,21 +177,6 @@ synth_vec_kernel(typename Vec2<T>::type *v, Geom g, int par, uint64_t seed) {
     o.x = (T)n.x;
     o.y = (T)n.y;
     v[(size_t)q * g.stride + i] = o;
-  }
-}
-
-// device [dir][9][site] -> host su3_matrix[4*V] layout (inverse of pack_link_kernel)
-template <typename T, typename TH>
-__global__ void __launch_bounds__(kBlock)
-unpack_link_kernel(TH *h, const typename Vec2<T>::type *d, int lstride, int n) {
-  const int i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
-  TH *s = h + (size_t)72 * i;
-#pragma unroll 6
-  for (int m = 0; m < 36; m++) {
-    const auto o = d[(size_t)m * lstride + i];
-    s[2 * m] = (TH)o.x;
-    s[2 * m + 1] = (TH)o.y;
   }
 }
 
