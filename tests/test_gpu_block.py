@@ -168,3 +168,56 @@ def test_block_congrad_mixed_precision(api, oracle, dims, parity, nsrc):
         assert np.linalg.norm(r) <= 2 * resid * np.linalg.norm(srcs[k][sl])
         assert np.linalg.norm(xs[k] - xo) <= 10 * resid / (4 * mass * mass) * np.linalg.norm(xo)
     ctx.close()
+
+
+def test_block_and_sequence_calls_on_a_partitioned_context(api, oracle, monkeypatch):
+    """A partitioned context (here one GPU as its own neighbour) has no K-wide stencil: block and
+    UML calls run the reference's loop of single solves through the halo path and still match the
+    oracle; the K-wide stencil probe and the link construction refuse with a clear error."""
+    from milc_qcd_b200 import fields as F
+    monkeypatch.setenv("B200KS_FORCE_PARTITION", "t")
+    dims = (8, 6, 8, 12)
+    fat, lng, _ = fields_for(dims)
+    ctx = api.Context(dims, grid=(1, 1, 1, 1), rank=0, nranks=1)
+    assert ctx.halo_mode() == 2
+    ctx.load_links(fat, lng)
+    srcs = _sources(dims, 2, EVEN)
+    xs = [np.zeros_like(s) for s in srcs]
+    tot, res = ctx.congrad_block(srcs, xs, 0.05, EVEN, 500, 5, 1e-9)
+    for k in range(2):
+        xo = np.zeros_like(srcs[k])
+        ito, qo = oracle.congrad(dims, fat, lng, srcs[k], xo, 0.05, EVEN, 500, 5, 1e-9)
+        assert res[k]["converged"] == 1 and abs(res[k]["final_iters"] - ito) <= max(2, 0.02 * ito)
+        assert np.linalg.norm(xs[k] - xo) <= 1e-7 * np.linalg.norm(xo)
+    full = F.make_source(dims, seed=77, parity=EVENANDODD)
+    dst = np.zeros_like(full)
+    it, r = ctx.mat_invert_uml([full], [dst], 0.05, 500, 5, 1e-9)
+    resid = oracle.dslash(dims, fat, lng, dst, EVENANDODD) + 0.1 * dst - full
+    assert np.linalg.norm(resid) <= 1e-6 * np.linalg.norm(full)
+    v = [ctx.vec_create() for _ in range(4)]
+    with pytest.raises(Exception, match="single-GPU"):
+        ctx.dslash_block_dev(v[:2], v[2:], EVEN, 2)
+    with pytest.raises(Exception, match="single-GPU"):
+        ctx.hisq_links(F.make_thin_links(dims, seed=5))
+    ctx.close()
+
+
+def test_block_argument_errors(api):
+    dims = (4, 4, 4, 4)
+    fat, lng, src = fields_for(dims)
+    ctx = api.Context(dims)
+    ctx.load_links(fat, lng)
+    v = [ctx.vec_create() for _ in range(6)]
+    with pytest.raises(Exception, match="distinct|different"):
+        ctx.congrad_block_dev([v[0], v[1]], [v[2], v[2]], 0.05, EVEN, 10, 1, 1e-6)      # same solution field twice
+    with pytest.raises(Exception, match="different"):
+        ctx.congrad_block_dev([v[0]], [v[0]], 0.05, EVEN, 10, 1, 1e-6)
+    with pytest.raises(Exception, match="parity"):
+        ctx.congrad_block([src], [np.zeros_like(src)], 0.05, EVENANDODD, 10, 1, 1e-6)
+    with pytest.raises(Exception, match="1..4"):
+        ctx.dslash_block_dev(v[:5], v[:5], EVEN, 2)
+    with pytest.raises(Exception, match="2m"):
+        ctx.mat_invert_uml([src], [np.zeros_like(src)], 0.0, 10, 1, 1e-6)
+    with pytest.raises(Exception, match="path coefficients"):
+        ctx.ks_links(np.zeros((src.shape[0], 4, 3, 3, 2)), (1.0, 2.0))
+    ctx.close()
