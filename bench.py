@@ -593,9 +593,13 @@ def run_block(args):
     for mixed in (0, 1):
         singles = []
         for k in range(kmax):
-            ctx.vec_zero(vx[k], EVEN)
-            ms, (it, res) = timed(lambda: ctx.congrad_dev(vb[k], vx[k], MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=mixed))
-            singles.append((ms, it))
+            best1 = None
+            for rep in range(2):   # best of two: the first solve of a mode also allocates its temporaries
+                ctx.vec_zero(vx[k], EVEN)
+                ms, (it, res) = timed(lambda: ctx.congrad_dev(vb[k], vx[k], MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=mixed))
+                if best1 is None or ms < best1[0]:
+                    best1 = (ms, it)
+            singles.append(best1)
         for k in range(2, kmax + 1):
             best = None
             for rep in range(2):
