@@ -28,6 +28,9 @@ GKS="dslash_fn_dblstore.c fn_links_milc.c d_congrad5_fn_milc.c ks_multicg_offset
 # HISQ link construction: U -> V (fat7) -> W (U(3) projection) -> fat, long
 GEN="$GEN general_staple.c path_product.c gauge_utilities.c project_su3_hit.c reunitarize2.c stout_smear.c"
 GKS="$GKS fermion_links_hisq_load_milc.c fermion_links_fn_load_milc.c ks_action_paths_hisq.c su3_mat_op.c rephase.c"
+# the HISQ fermion force (oracle only so far), ks_imp_rhmc's flags
+# (ks_imp_rhmc/Make_template: -DHISQ_FF_MULTI_WRAPPER -DHISQ_FORCE_FILTER=5.0e-5, KS_MULTIFF=FNMAT)
+GKS="$GKS fermion_force_hisq_multi.c fermion_links_hisq_milc.c fermion_links.c ff_opt.c path_transport.c"
 # the UML propagator-solve sequence
 GEN="$GEN report_invert_status.c"
 GKS="$GKS mat_invert.c d_congrad5_fn.c"
@@ -40,6 +43,7 @@ build_variant() {  # name precision extra-flags
   # (-DHISQ_REUNIT_*: the reunitarisation flags of the RHMC build, ks_imp_rhmc/Make_template:204-206)
   local AF="$CF -DDBLSTORE_FN -DFEWSUMS -DD_FN_GATHER13 -DC_GLOBAL_INLINE -DFN -DHAVE_KS \
             -DHISQ_REUNIT_ALLOW_SVD -DHISQ_REUNIT_SVD_REL_ERROR=1e-8 -DHISQ_REUNIT_SVD_ABS_ERROR=1e-8 \
+            -DKS_MULTIFF=FNMAT -DHISQ_FF_MULTI_WRAPPER -DHISQ_FORCE_FILTER=5.0e-5 \
             -D_FILE_OFFSET_BITS=64 -I$HERE/ref_harness -I$OUT/gen"
   local jobs=()
   for f in $LIBSRC; do

@@ -167,6 +167,7 @@ class MilcRef:
         L.milcref_smear.argtypes = [rp, _dp, ro, C.c_void_p]
         L.milcref_unitarize.argtypes = [rp, ro, C.c_long]
         L.milcref_mat_invert_uml.argtypes = [rp, ro, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, _dp]
+        L.milcref_hisq_force.argtypes = [rp, rp, rp, C.c_int, C.c_double, ro]
         self.dims = tuple(int(d) for d in dims)
         if L.milcref_init(*self.dims) != 0:
             raise RuntimeError("MilcRef: process already initialised with another geometry")
@@ -238,6 +239,17 @@ class MilcRef:
         out = np.zeros(7)
         it = self.lib.milcref_mat_invert_uml(srcs, dsts, srcs.shape[0], mass, niter, nrestart, resid, out)
         return it, _qic(out)
+
+    def hisq_force(self, links, multi_x, residues, eps):
+        """eo_fermion_force_multi (generic_ks/fermion_force_hisq_multi.c:170-216) on thin links with
+        phases in: returns the momentum update as (V,4,10) anti_hermitmat arrays
+        {m01, m02, m12 (re,im), m00im, m11im, m22im, space} and the SVD/filter count."""
+        links = np.ascontiguousarray(links, self.dtype)
+        xs = np.ascontiguousarray(multi_x, self.dtype)
+        res = np.ascontiguousarray(residues, self.dtype)
+        mom = np.zeros((self.vol, 4, 10), dtype=self.dtype)
+        n = self.lib.milcref_hisq_force(links, xs, res, xs.shape[0], eps, mom)
+        return mom, n
 
     def time_dslash(self, src, parity, ncalls):
         src = np.ascontiguousarray(src, self.dtype)

@@ -258,3 +258,43 @@ int milcref_mat_invert_uml(const Real *src, Real *dst, int nsrc, double m, int m
   free(s); free(d);
   return it;
 }
+
+/* ---- HISQ fermion force ---------------------------------------------
+ * eo_fermion_force_multi, generic_ks/fermion_force_hisq_multi.c:170-216 (the wrapper_mx path of the
+ * RHMC build: outer products of the nterms solution vectors, level-2 smearing force, derivative of
+ * the U(3) projection, level-1 smearing force, projection onto the momenta):
+ *     mom_mu(x) += eps * (traceless antihermitian part of the force)
+ * links: thin links su3_matrix[4*V] with phases in; multi_x: nterms contiguous fields of su3_vector
+ * (both parities: even = solution, odd = D solution, as update_h_rhmc.c:75-86 prepares them);
+ * mom: anti_hermitmat[4*V] as 10 Reals each {m01.re,m01.im,m02.re,m02.im,m12.re,m12.im,m00im,m11im,
+ * m22im,space} (include/su3.h), zero on entry here, the update on exit.
+ * Returns the number of links whose force took the SVD / filter branches (sum). */
+int milcref_hisq_force(const Real *links, const Real *multi_x, const Real *residues, int nterms, double eps,
+                       Real *mom) {
+  double eps_naik[1] = {0.0};
+  fermion_links_t *fl;
+  su3_vector **xx = (su3_vector **)malloc(nterms * sizeof(*xx));
+  Real *res = (Real *)malloc(nterms * sizeof(Real));
+  size_t i;
+  int k, dir;
+  if (!h_ready) return -1;
+  for (k = 0; k < nterms; k++) {
+    xx[k] = (su3_vector *)multi_x + (size_t)k * sites_on_node;
+    res[k] = residues[k];
+  }
+  n_order_naik_total = nterms;
+  n_orders_naik[0] = nterms;
+  hisq_svd_counter = 0;
+  hisq_force_filter_counter = 0;
+  for (i = 0; i < sites_on_node; i++) {
+    memcpy(lattice[i].link, (const su3_matrix *)links + 4 * i, 4 * sizeof(su3_matrix));
+    memset(lattice[i].mom, 0, 4 * sizeof(anti_hermitmat));
+  }
+  fl = create_fermion_links_hisq(MILC_PRECISION, 1, eps_naik, phases_in, (su3_matrix *)links);
+  eo_fermion_force_multi((Real)eps, res, xx, nterms, MILC_PRECISION, fl);
+  for (i = 0; i < sites_on_node; i++)
+    for (dir = 0; dir < 4; dir++) memcpy(mom + 10 * (4 * i + dir), &lattice[i].mom[dir], sizeof(anti_hermitmat));
+  destroy_fermion_links_hisq(fl);
+  free(xx); free(res);
+  return hisq_svd_counter + hisq_force_filter_counter;
+}

@@ -25,6 +25,7 @@ typedef struct {
   int space1;
   su3_matrix link[4] ALIGNMENT;
   Real phase[4];
+  anti_hermitmat mom[4] ALIGNMENT;   /* written by the fermion force (generic_ks/fermion_force_hisq_multi.c) */
 } site;
 
 #ifdef CONTROL
@@ -54,6 +55,12 @@ EXTERN char **gen_pt[N_POINTERS];
 
 /* generic_ks/mat_invert.c names the application's eigenpair storage (ks_spectrum/lattice.h);
    unused here (param.eigen_param.Nvecs = 0) */
+/* generic_ks/fermion_force_hisq_multi.c counts into these and reads the per-Naik-epsilon term
+   counts of the RHMC application (ks_imp_rhmc/lattice.h) */
+EXTERN int hisq_svd_counter;
+EXTERN int hisq_force_filter_counter;
+EXTERN int n_order_naik_total;
+EXTERN int n_orders_naik[MAX_NAIK];
 EXTERN double *eigVal;
 EXTERN su3_vector **eigVec;
 

@@ -1,0 +1,44 @@
+"""Generates tests/golden/ref_hisq_force.npz from the REFERENCE ITSELF.
+
+    python tests/golden/make_golden_force.py      # build container: needs oracle/_ref/libmilcref.so
+
+Input: seeded thin links (phases in) on a 4^4 lattice, two "solution" vectors X_j on the even
+sites with their odd sites filled by D X_j through the HISQ links built from those thin links
+(what ks_imp_rhmc/update_h_rhmc.c:75-86 hands to the force), residues (0.7, -0.3), eps = 1.
+Output: the momentum update of the reference's eo_fermion_force_multi
+(generic_ks/fermion_force_hisq_multi.c:170-216, wrapper_mx path, ks_imp_rhmc's build flags) as
+anti_hermitmat arrays.  No CUDA implementation consumes it yet: it pins the oracle for the next row.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from milc_qcd_b200 import fields as F  # noqa: E402
+from oracle.pyoracle import MilcRef, LinksOracle, Oracle, ODD  # noqa: E402
+
+
+def main():
+    dims = (4, 4, 4, 4)
+    V = int(np.prod(dims))
+    h = V // 2
+    ref, lo, o = MilcRef(dims), LinksOracle(), Oracle()
+    U = F.make_thin_links(dims, seed=11, spread=0.5)
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((2, V, 3, 2))
+    X[:, h:] = 0
+    residues = np.array([0.7, -0.3])
+    links = lo.hisq_links(dims, U)
+    for j in range(2):
+        X[j, h:] = o.dslash(dims, links["fat"], links["lng"], X[j], ODD)[h:]
+    mom, n = ref.hisq_force(U, X, residues, 1.0)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_hisq_force.npz")
+    np.savez_compressed(path, dims=np.array(dims), U=U, multi_x=X, residues=residues, eps=1.0, mom=mom, nsvd=n)
+    print("wrote", path, os.path.getsize(path), "bytes; |mom|max", np.abs(mom).max())
+
+
+if __name__ == "__main__":
+    main()

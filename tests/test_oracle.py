@@ -271,3 +271,84 @@ def test_uml_sequence_oracle_matches_compiled_reference_live():
         pytest.skip("oracle/_ref/libmilcref.so not built (needs /root/reference)")
     out = subprocess.run([sys.executable, "-c", _LIVE_UML % dict(root=ROOT)], capture_output=True, text=True, timeout=600)
     assert "LIVE-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+# ---- HISQ fermion force (row f2): the oracle for the next row, pinned ahead of the CUDA work ------
+def _generator(a):
+    T = np.zeros((3, 3), complex)
+    if a == 0:
+        T[0, 1] = T[1, 0] = 1
+    elif a == 1:
+        T[0, 1], T[1, 0] = -1j, 1j
+    elif a == 2:
+        T[0, 0], T[1, 1] = 1, -1
+    elif a == 3:
+        T[0, 2] = T[2, 0] = 1
+    elif a == 4:
+        T[1, 2], T[2, 1] = -1j, 1j
+    else:
+        T[0, 0] = T[1, 1] = 1 / np.sqrt(3)
+        T[2, 2] = -2 / np.sqrt(3)
+    return T
+
+
+def _ahmat(m):
+    """anti_hermitmat -> 3x3 anti-Hermitian matrix (libraries/uncmp_ahmat.c)."""
+    A = np.zeros((3, 3), complex)
+    A[0, 0], A[1, 1], A[2, 2] = 1j * m[6], 1j * m[7], 1j * m[8]
+    A[0, 1], A[1, 0] = m[0] + 1j * m[1], -m[0] + 1j * m[1]
+    A[0, 2], A[2, 0] = m[2] + 1j * m[3], -m[2] + 1j * m[3]
+    A[1, 2], A[2, 1] = m[4] + 1j * m[5], -m[4] + 1j * m[5]
+    return A
+
+
+def test_reference_force_golden_is_the_derivative_of_the_oracle_action(oracle, links_oracle):
+    """The committed output of the reference's eo_fermion_force_multi (tests/golden/
+    make_golden_force.py) against an independent finite-difference derivative built from the
+    pinned oracles: with S(U) = sum_j res_j |D_oe[U] X_j|^2 (HISQ links from ks_links_oracle.c,
+    stencil from ks_oracle.c) and U_mu(x) -> exp(i t T) U_mu(x), the reference's momentum update A
+    (eps = 1) satisfies dS/dt = -Re tr(i T A).  Fixes the convention the CUDA force has to meet."""
+    from scipy.linalg import expm
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force.npz"))
+    dims = tuple(int(d) for d in g["dims"])
+    U, X, res, mom = g["U"], g["multi_x"], g["residues"], g["mom"]
+    h = U.shape[0] // 2
+
+    def action(Ur):
+        L = links_oracle.hisq_links(dims, Ur)
+        return sum(res[j] * np.sum(oracle.dslash(dims, L["fat"], L["lng"], X[j], ODD)[h:] ** 2) for j in range(len(res)))
+
+    Uc = U[..., 0] + 1j * U[..., 1]
+    t = 1e-5
+    for (i, mu, a) in [(17, 2, 2), (40, 3, 3), (100, 0, 4), (201, 1, 0)]:
+        T = _generator(a)
+        s = []
+        for sgn in (1, -1):
+            Up = Uc.copy()
+            Up[i, mu] = expm(1j * sgn * t * T) @ Uc[i, mu]
+            s.append(action(np.ascontiguousarray(np.stack([Up.real, Up.imag], axis=-1))))
+        fd = (s[0] - s[1]) / (2 * t)
+        want = -np.trace(1j * T @ _ahmat(mom[i, mu])).real
+        assert abs(fd - want) <= 1e-6 * max(1.0, abs(want)), (i, mu, a, fd, want)
+    # traceless and anti-Hermitian by construction of the packed format; zero "space" member
+    assert np.abs(mom[..., 6] + mom[..., 7] + mom[..., 8]).max() < 1e-12
+
+
+def test_reference_force_live_matches_golden():
+    from oracle.pyoracle import ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref/libmilcref.so not built (needs /root/reference)")
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from oracle.pyoracle import MilcRef
+g = np.load(%r)
+ref = MilcRef(tuple(int(d) for d in g['dims']))
+mom, n = ref.hisq_force(g['U'], g['multi_x'], g['residues'], float(g['eps']))
+assert np.abs(mom - g['mom']).max() <= 1e-12 * np.abs(g['mom']).max()
+m2, _ = ref.hisq_force(g['U'], g['multi_x'], 2.0 * g['residues'], 0.5)      # linear in eps * residues
+assert np.abs(m2 - g['mom']).max() <= 1e-12 * np.abs(g['mom']).max()
+print('LIVE-OK')
+""" % (ROOT, os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force.npz"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "LIVE-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
