@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200KS_VERSION 100
+#define B200KS_VERSION 110 /* 110: block solve, resident sequences, link construction */
 
 /* parity codes, include/macros.h:68-70 */
 #define B200KS_EVEN 2
@@ -124,6 +124,13 @@ void b200ks_destroy(b200ks_ctx *ctx);
  * 16-byte word the kernels load; 14 keeps 89 % of its traffic saving.) */
 int b200ks_load_links(b200ks_ctx *ctx, const void *fat, const void *lng, int host_prec,
                       int long_recon);
+/* 64-bit content fingerprint of a host array (threaded, memory-bandwidth bound).  The MILC-facing
+ * shims compare it with the fingerprint taken at the last upload to notice in-place edits of the
+ * link arrays that MILC does not announce (boundary_twist_fn,
+ * generic_ks/fermion_links_fn_twist_milc.c:318-400) without re-uploading on every call.  Note: the
+ * result depends on the number of host threads only through how the array is split; it is stable
+ * within a process. */
+unsigned long long b200ks_fingerprint(const void *host, size_t bytes);
 /* Storage chosen for the long links (7 or 9 complex per link) and the worst misfit measured
  * by the load-time test (-1 when long_recon == 18 skipped it). */
 int b200ks_long_link_info(b200ks_ctx *ctx, int *ncomplex_per_link, double *misfit);

@@ -37,6 +37,7 @@ SYMBOLS = [
     ("b200ks_comm_unique_id", C.c_int, [C.c_void_p]),
     ("b200ks_destroy", None, [C.c_void_p]),
     ("b200ks_load_links", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    ("b200ks_fingerprint", C.c_ulonglong, [C.c_void_p, C.c_size_t]),
     ("b200ks_long_link_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     ("b200ks_dslash", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     ("b200ks_congrad", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,

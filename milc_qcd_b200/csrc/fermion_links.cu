@@ -85,7 +85,7 @@ static int links_to_dev(b200ks_ctx *c, const LinkWork &w, double2 *dst, const vo
   void *stage = nullptr;
   CHK(stage_get(c, half_bytes, &stage));
   for (int p = 0; p < 2; p++) {
-    CU(cudaMemcpyAsync(stage, (const char *)host + (size_t)p * half_bytes, half_bytes, cudaMemcpyHostToDevice, stream(c)));
+    CHK(h2d(c, stage, (const char *)host + (size_t)p * half_bytes, half_bytes));
     if (host_prec == 2) LAUNCH(c, (pack_link_kernel<double, double>), nblocks(geom(c).Vh), dst + (size_t)p * geom(c).Vh, (const double *)stage, (int)w.fstride, geom(c).Vh);
     else LAUNCH(c, (pack_link_kernel<double, float>), nblocks(geom(c).Vh), dst + (size_t)p * geom(c).Vh, (const float *)stage, (int)w.fstride, geom(c).Vh);
     CU(cudaStreamSynchronize(stream(c)));   // the staging buffer is reused for the next half
@@ -100,8 +100,7 @@ static int links_to_host(b200ks_ctx *c, const LinkWork &w, const double2 *src, v
   for (int p = 0; p < 2; p++) {
     if (host_prec == 2) LAUNCH(c, (unpack_link_kernel<double, double>), nblocks(geom(c).Vh), (double *)stage, src + (size_t)p * geom(c).Vh, (int)w.fstride, geom(c).Vh);
     else LAUNCH(c, (unpack_link_kernel<double, float>), nblocks(geom(c).Vh), (float *)stage, src + (size_t)p * geom(c).Vh, (int)w.fstride, geom(c).Vh);
-    CU(cudaMemcpyAsync((char *)host + (size_t)p * half_bytes, stage, half_bytes, cudaMemcpyDeviceToHost, stream(c)));
-    CU(cudaStreamSynchronize(stream(c)));
+    CHK(d2h(c, (char *)host + (size_t)p * half_bytes, stage, half_bytes));
   }
   return check_launch("unpack_link_kernel");
 }

@@ -15,6 +15,10 @@ int check_launch(const char *what);                  // cudaGetLastError -> B200
 int dev_alloc(b200ks_ctx *c, void **p, size_t bytes);  // cudaMalloc + bookkeeping (b200ks_device_bytes)
 void dev_release(b200ks_ctx *c, void *p, size_t bytes);
 int stage_get(b200ks_ctx *c, size_t bytes, void **out);   // persistent re-layout staging buffer
+// host <-> device copies that bounce pageable host arrays through pinned buffers (b200ks.cu);
+// h2d is stream-ordered and returns once the host array has been read, d2h returns when it is complete
+int h2d(b200ks_ctx *c, void *dst, const void *src, size_t bytes);
+int d2h(b200ks_ctx *c, void *dst, const void *src, size_t bytes);
 const b200ks::Geom &geom(const b200ks_ctx *c);
 cudaStream_t stream(const b200ks_ctx *c);
 int device(const b200ks_ctx *c);

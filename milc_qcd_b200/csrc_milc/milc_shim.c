@@ -91,12 +91,19 @@ static b200ks_ctx *context(const char *myname) {
   return s_ctx;
 }
 
-/* d_congrad5_fn_gpu.c:121-126: refresh the device links when fn changed or was rebuilt */
+/* d_congrad5_fn_gpu.c:121-126: refresh the device links when fn changed or was rebuilt -- and
+ * also when the arrays were edited in place without notice (boundary_twist_fn,
+ * fermion_links_fn_twist_milc.c:318-400), which a content fingerprint detects */
 static void refresh_links(const char *myname, imp_ferm_links_t *fn) {
-  if (fn != fn_last || fn->notify_quda_new_links) {
+  static unsigned long long fp_fat = 0, fp_lng = 0;
+  const size_t bytes = SITES * 4 * sizeof(su3_matrix);
+  const unsigned long long ff = b200ks_fingerprint(fn->fat, bytes), fl = b200ks_fingerprint(fn->lng, bytes);
+  if (fn != fn_last || fn->notify_quda_new_links || ff != fp_fat || fl != fp_lng) {
     if (b200ks_load_links(context(myname), fn->fat, fn->lng, MILC_PRECISION, 0) < 0) die(myname);
     fn->notify_quda_new_links = 0; /* cancel_quda_notification(fn) */
     fn_last = fn;
+    fp_fat = ff;
+    fp_lng = fl;
   }
 }
 
