@@ -25,7 +25,7 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build_oracle(force=False):
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("ks_oracle.c", "ks_links_oracle.c")]
+    srcs = [os.path.join(HERE, f) for f in ("ks_oracle.c", "ks_links_oracle.c", "ks_force_oracle.c")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", HERE, "-s", "-B", "liboracle.so"])
     return so
@@ -94,6 +94,8 @@ class LinksOracle:
         L.ksl_smear.argtypes = [_ip, _dp, _dp, _dp, C.c_void_p]
         L.ksl_unitarize.restype = C.c_long
         L.ksl_unitarize.argtypes = [_dp, _dp, C.c_long, C.c_int, C.c_double, C.c_double]
+        L.ksf_hisq_force.restype = None
+        L.ksf_hisq_force.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, _dp]
         L.ksl_hisq_links.restype = C.c_long
         L.ksl_hisq_links.argtypes = [_ip, _dp, _dp, _dp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_double, C.c_double]
@@ -115,6 +117,17 @@ class LinksOracle:
         W = np.zeros_like(V)
         n = self.lib.ksl_unitarize(V, W, V.size // 18, int(allow_svd), svd_rel, svd_abs)
         return W, int(n)
+
+    def hisq_force(self, dims, links, multi_x, residues, eps, coeffs1=None, coeffs2=None):
+        """ks_force_oracle.c: the momentum update of eo_fermion_force_multi as (V,4,10) anti_hermitmat arrays."""
+        links = np.ascontiguousarray(links, np.float64)
+        xs = np.ascontiguousarray(multi_x, np.float64)
+        res = np.ascontiguousarray(residues, np.float64)
+        c1 = np.ascontiguousarray(self.FAT7 if coeffs1 is None else coeffs1, np.float64)
+        c2 = np.ascontiguousarray(self.ASQTAD_LIKE if coeffs2 is None else coeffs2, np.float64)
+        mom = np.zeros((links.shape[0], 4, 10))
+        self.lib.ksf_hisq_force(self._dims(dims), c1, c2, links, xs, res, xs.shape[0], eps, mom)
+        return mom
 
     def hisq_links(self, dims, links, coeffs1=None, coeffs2=None, allow_svd=True, svd_rel=1e-8, svd_abs=1e-8):
         links = np.ascontiguousarray(links, np.float64)
