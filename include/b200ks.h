@@ -225,6 +225,24 @@ int b200ks_hisq_links_time(b200ks_ctx *ctx, const double *coeff1, const double *
                            unsigned long long seed, int reps, double *ms_per_chain, long long *nsvd);
 int b200ks_hisq_links_fetch(b200ks_ctx *ctx, int which, void *host, int host_prec);
 
+/* ---- HISQ fermion force ---------------------------------------
+ * momentum = eps * (traceless anti-Hermitian force) for S = sum_j res_j |D_oe X_j|^2, the
+ * increment MILC adds to its momenta.  Replaces fn_fermion_force_multi_hisq_wrapper_mx
+ * (generic_ks/fermion_force_hisq_multi.c:1183-1476) = qudaHisqForce (:2169-2290), whose argument
+ * conventions it keeps:
+ *   coeff[2*j], coeff[2*j+1]  one-hop (2 res_j) and three-hop (naik * 2 res_j) weights of term j
+ *   multi_x[j]                su3_vector[V]: solution on the even sites, D solution on the odd sites
+ *   level2_coeff, fat7_coeff  the six path coefficients of the two smearing levels
+ *   wlink, vlink, ulink       W (unitarised), V (fat7) and U (thin, phases in): su3_matrix[4*V]
+ *   momentum                  out: anti_hermitmat[4*V], 10 reals each (include/su3.h)
+ * Computed as the reverse-mode derivative of the link construction (csrc/force.cuh); double on the
+ * device whatever host_prec is.  Not implemented: several Naik epsilons (num_naik_terms > 0) and
+ * the HISQ_FORCE_FILTER regularisation of links whose V^+V has an eigenvalue below 5e-5.
+ * Single-GPU contexts. */
+int b200ks_hisq_force(b200ks_ctx *ctx, int nterms, const double *coeff, const void *const *multi_x,
+                      const double *level2_coeff, const double *fat7_coeff, const void *wlink,
+                      const void *vlink, const void *ulink, double eps, void *momentum, int host_prec);
+
 /* ---- device-resident interface (benchmarks, resident solve sequences) -------------- */
 
 /* Device colour-vector fields of one context, double precision, both parities. */

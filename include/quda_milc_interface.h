@@ -14,7 +14,8 @@
  * Exactly these symbols are required (link-probed): qudaInit,
  * qudaSetMPICommHandle, qudaFinalize, qudaAllocatePinned, qudaFreePinned, qudaInvert,
  * qudaInvertMsrc, qudaMultishiftInvert, qudaDslash (+ qudaMomAction for ks_imp_rhmc);
- * WANT_FL_GPU=true additionally binds qudaLoadKSLink and qudaLoadUnitarizedLink.
+ * WANT_FL_GPU=true additionally binds qudaLoadKSLink and qudaLoadUnitarizedLink, WANT_FF_GPU=true
+ * qudaHisqParamsInit and qudaHisqForce.
  */
 #ifndef QUDA_MILC_INTERFACE_H
 #define QUDA_MILC_INTERFACE_H
@@ -118,6 +119,24 @@ void qudaLoadKSLink(int precision, QudaFatLinkArgs_t fatlink_args, const double 
  * called by load_hisq_aux_links_gpu with the level-1 (fat7) coefficients. */
 void qudaLoadUnitarizedLink(int precision, QudaFatLinkArgs_t fatlink_args, const double path_coeff[6], void *inlink,
                             void *fatlink, void *ulink);
+
+/* ---- HISQ fermion force (-DUSE_FF_GPU: make WANT_FF_GPU=true, Makefile:458-461) ------------
+ * generic_ks/fermion_force_hisq_multi.c:2169-2290. */
+typedef struct {
+  int reunit_allow_svd;
+  int reunit_svd_only;
+  double reunit_svd_abs_error;
+  double reunit_svd_rel_error;
+  double force_filter;
+} QudaHisqParams_t;
+
+void qudaHisqParamsInit(QudaHisqParams_t hisq_params);
+/* momentum (anti_hermitmat[4*sites], precision reals) = dt * force of num_terms terms; coeff[t][0]
+ * one-hop and coeff[t][1] three-hop weights; quark_field[t] su3_vector[sites] with both parities
+ * filled.  num_naik_terms > 0 (several Naik epsilons) is not supported. */
+void qudaHisqForce(int precision, int num_terms, int num_naik_terms, double dt, double **coeff, void **quark_field,
+                   const double level2_coeff[6], const double fat7_coeff[6], const void *const w_link,
+                   const void *const v_link, const void *const u_link, void *const milc_momentum);
 
 #ifdef __cplusplus
 }

@@ -179,6 +179,23 @@ class Context:
         out["nsvd"] = n.value
         return out
 
+    def hisq_force(self, U, V, W, multi_x, residues, eps, coeffs1=None, coeffs2=None):
+        """b200ks_hisq_force with MILC's weights (one-hop 2 res_j, three-hop naik * 2 res_j,
+        generic_ks/fermion_force_hisq_multi.c:2189-2192): returns the momentum increment as
+        (V,4,10) anti_hermitmat arrays."""
+        c1 = self.HISQ_FAT7 if coeffs1 is None else coeffs1
+        c2 = self.HISQ_ASQTAD_LIKE if coeffs2 is None else coeffs2
+        n = len(multi_x)
+        cf = (C.c_double * (2 * n))()
+        for j, r in enumerate(residues):
+            cf[2 * j] = 2.0 * float(r)
+            cf[2 * j + 1] = float(c2[1]) * 2.0 * float(r)
+        ptrs = (C.c_void_p * n)(*[_ptr(x).value for x in multi_x])
+        mom = np.zeros((self.volume, 4, 10), dtype=U.dtype)
+        check(self.lib.b200ks_hisq_force(self.h, n, cf, ptrs, self._coeffs(c2), self._coeffs(c1), _ptr(W), _ptr(V), _ptr(U),
+                                         eps, _ptr(mom), _host_prec(U)), "b200ks_hisq_force")
+        return mom
+
     def hisq_links_time(self, seed, reps, coeffs1=None, coeffs2=None):
         ms, n = C.c_double(), C.c_longlong(0)
         check(self.lib.b200ks_hisq_links_time(self.h, self._coeffs(self.HISQ_FAT7 if coeffs1 is None else coeffs1),

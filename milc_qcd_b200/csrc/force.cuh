@@ -1,0 +1,402 @@
+// force.cuh -- HISQ fermion force as reverse-mode differentiation of
+// the link construction of links.cuh.
+//
+// What the reference computes (generic_ks/fermion_force_hisq_multi.c:1183-1476; GPU seam
+// qudaHisqForce, :2169-2290): for S = sum_j res_j |D_oe[U] X_j|^2, with the HISQ chain
+// U -> V (fat7) -> W (U(3) projection) -> (fat, long) inside D, the momentum increment
+//     A_mu(x) = -eps * TA( U_mu(x) G_U,mu(x)^+ ),      dS = Re tr(G_U^+ dU),
+// TA = traceless anti-Hermitian part.  The reference walks sorted path tables; here the same
+// derivative is taken by running the forward chain's staple passes backwards ("G_M" below is the
+// gradient matrix of S with respect to M, dS = Re tr(G_M^+ dM)):
+//   1. outer products       G_fat,mu(x) = +-c1_j Z_j(x) Z_j(x+mu)^+ , G_lng,mu(x) = +-c3_j Z_j(x) Z_j(x+3mu)^+
+//                           (Z = X on even sites, D X on odd sites; + on odd x)      cf. :2009-2154
+//   2. level-2 smearing and the Naik product backwards: G_fat, G_lng -> G_W          cf. :1638-1874
+//   3. U(3) projection backwards: G_W -> G_V, exact derivative of V (V^+V)^-1/2 from the
+//      eigen-decomposition of V^+V (Daleckii-Krein)                                   cf. :1877-2006
+//   4. level-1 (fat7) smearing backwards: G_V -> G_U                                  cf. :1638-1874
+//   5. projection onto the momenta                                                    cf. :1433-1470
+// A forward staple pass  S(L)(x) = U_nu(x) L(x+nu) U_nu(x+mu)^+ + U_nu(x-nu)^+ L(x-nu) U_nu(x-nu+mu)
+// (generic/general_staple.c:41-123) has six gradient contributions; written as gathers at the
+// destination site z (no atomics), with H the gradient w.r.t. S(L):
+//   G_L(z)    += U_nu(z-nu)^+ H(z-nu) U_nu(z-nu+mu) + U_nu(z) H(z+nu) U_nu(z+mu)^+
+//   G_Unu(z)  += H(z) U_nu(z+mu) L(z+nu)^+ + H(z-mu)^+ U_nu(z-mu) L(z-mu+nu)
+//              + L(z-mu)^+ U_nu(z-mu) H(z-mu+nu) + L(z) U_nu(z+mu) H(z+nu)^+
+//
+// Every per-site routine is __host__ __device__: tests/host/force_host.cu runs the same bodies in
+// plain host loops against the CPU oracle (oracle/ks_force_oracle.c), so the arithmetic and the
+// neighbour bookkeeping are checked without a GPU; the kernels only add the launch.
+// Layout as links.cuh: matrix fields of 9 double2 planes, plane stride fs, site f = parity*Vh + cb.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stddef.h>
+
+namespace b200ks {
+namespace force {
+
+#define B200KS_HD __host__ __device__ inline
+
+struct FGeom {   // periodic single-GPU lattice; sites in MILC order (even block, then odd block)
+  int L[4];
+  int Vh;
+};
+
+struct Mat { double2 e[9]; };
+
+B200KS_HD Mat ld(const double2 *p, size_t fs, int f) {
+  Mat m;
+  for (int k = 0; k < 9; k++) m.e[k] = p[(size_t)k * fs + f];
+  return m;
+}
+B200KS_HD void st(double2 *p, size_t fs, int f, const Mat &m) {
+  for (int k = 0; k < 9; k++) p[(size_t)k * fs + f] = m.e[k];
+}
+B200KS_HD void acc(double2 *p, size_t fs, int f, double s, const Mat &m) {   // p(f) += s m
+  for (int k = 0; k < 9; k++) {
+    double2 v = p[(size_t)k * fs + f];
+    v.x += s * m.e[k].x;
+    v.y += s * m.e[k].y;
+    p[(size_t)k * fs + f] = v;
+  }
+}
+B200KS_HD Mat nn(const Mat &a, const Mat &b) {
+  Mat c;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double re = 0, im = 0;
+      for (int k = 0; k < 3; k++) {
+        const double2 x = a.e[3 * i + k], y = b.e[3 * k + j];
+        re += x.x * y.x - x.y * y.y;
+        im += x.x * y.y + x.y * y.x;
+      }
+      c.e[3 * i + j] = make_double2(re, im);
+    }
+  return c;
+}
+B200KS_HD Mat dag(const Mat &a) {
+  Mat c;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) c.e[3 * i + j] = make_double2(a.e[3 * j + i].x, -a.e[3 * j + i].y);
+  return c;
+}
+B200KS_HD Mat na(const Mat &a, const Mat &b) { return nn(a, dag(b)); }
+B200KS_HD Mat an(const Mat &a, const Mat &b) { return nn(dag(a), b); }
+B200KS_HD void add(Mat &a, const Mat &b) {
+  for (int k = 0; k < 9; k++) {
+    a.e[k].x += b.e[k].x;
+    a.e[k].y += b.e[k].y;
+  }
+}
+B200KS_HD Mat zero() {
+  Mat m;
+  for (int k = 0; k < 9; k++) m.e[k] = make_double2(0.0, 0.0);
+  return m;
+}
+
+// site f = parity*Vh + cb, cb = lex/2 -> neighbour at +-1 in direction mu (periodic)
+B200KS_HD int nbr(const FGeom &g, int f, int mu, int sign) {
+  const int par = f >= g.Vh ? 1 : 0;
+  const int cb = f - par * g.Vh;
+  const int Lxh = g.L[0] / 2;
+  int r = cb;
+  int c[4];
+  const int xh = r % Lxh;
+  r /= Lxh;
+  c[1] = r % g.L[1];
+  r /= g.L[1];
+  c[2] = r % g.L[2];
+  c[3] = r / g.L[2];
+  c[0] = 2 * xh + ((c[1] + c[2] + c[3] + par) & 1);
+  c[mu] += sign;
+  if (c[mu] >= g.L[mu]) c[mu] -= g.L[mu];
+  if (c[mu] < 0) c[mu] += g.L[mu];
+  const int lex = c[0] + g.L[0] * (c[1] + g.L[1] * (c[2] + g.L[2] * c[3]));
+  return (par ^ 1) * g.Vh + (lex >> 1);
+}
+
+// ---- site functors (operator()(f) for every site f) ------------------------------------------------
+// 1. outer products of one term: z = colour vectors in MILC host order, 6 reals per site
+struct OprodSite {
+  FGeom g;
+  double2 *gfat, *glng;
+  size_t fs;
+  const double *z;
+  double c1, c3;
+  B200KS_HD void operator()(int f) const {
+    const double sgn = f >= g.Vh ? 1.0 : -1.0;
+    for (int mu = 0; mu < 4; mu++) {
+      const int f1 = nbr(g, f, mu, 1), f3 = nbr(g, nbr(g, f1, mu, 1), mu, 1);
+      Mat o1, o3;
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) {
+          const double zr = z[6 * (size_t)f + 2 * a], zi = z[6 * (size_t)f + 2 * a + 1];
+          const double pr = z[6 * (size_t)f1 + 2 * b], pi = z[6 * (size_t)f1 + 2 * b + 1];
+          const double qr = z[6 * (size_t)f3 + 2 * b], qi = z[6 * (size_t)f3 + 2 * b + 1];
+          o1.e[3 * a + b] = make_double2(zr * pr + zi * pi, zi * pr - zr * pi);
+          o3.e[3 * a + b] = make_double2(zr * qr + zi * qi, zi * qr - zr * qi);
+        }
+      acc(gfat + (size_t)mu * 9 * fs, fs, f, sgn * c1, o1);
+      acc(glng + (size_t)mu * 9 * fs, fs, f, sgn * c3, o3);
+    }
+  }
+};
+
+// 2. forward staple (no fat-link accumulation): out = S(link)
+struct StapleFwdSite {
+  FGeom g;
+  double2 *out;
+  const double2 *link, *Unu;   // matrix fields: the mu "link" and the gauge links of direction nu
+  size_t fs;
+  int mu, nu;
+  B200KS_HD void operator()(int f) const {
+    const int fpn = nbr(g, f, nu, 1), fpm = nbr(g, f, mu, 1), fmn = nbr(g, f, nu, -1), fmnpm = nbr(g, fmn, mu, 1);
+    Mat up = nn(ld(Unu, fs, f), na(ld(link, fs, fpn), ld(Unu, fs, fpm)));
+    const Mat low = nn(an(ld(Unu, fs, fmn), ld(link, fs, fmn)), ld(Unu, fs, fmnpm));
+    add(up, low);
+    st(out, fs, f, up);
+  }
+};
+
+// 3. backward staple: H = hs * Hfield is the gradient w.r.t. S(link); adds to glink and gUnu at z
+struct StapleBwdSite {
+  FGeom g;
+  const double2 *H;
+  double hs;
+  const double2 *link, *Unu;
+  double2 *glink, *gUnu;
+  size_t fs;
+  int mu, nu;
+  B200KS_HD void operator()(int z) const {
+    const int zpn = nbr(g, z, nu, 1), zmn = nbr(g, z, nu, -1), zpm = nbr(g, z, mu, 1), zmm = nbr(g, z, mu, -1);
+    const int zmnpm = nbr(g, zmn, mu, 1), zmmpn = nbr(g, zmm, nu, 1);
+    const Mat Uz = ld(Unu, fs, z), Uzpm = ld(Unu, fs, zpm), Uzmm = ld(Unu, fs, zmm);
+    const Mat Hzpn = ld(H, fs, zpn);
+    // gradient of the link field
+    Mat gl = nn(an(ld(Unu, fs, zmn), ld(H, fs, zmn)), ld(Unu, fs, zmnpm));
+    add(gl, na(nn(Uz, Hzpn), Uzpm));
+    acc(glink, fs, z, hs, gl);
+    // gradient of the nu links
+    Mat gu = nn(ld(H, fs, z), na(Uzpm, ld(link, fs, zpn)));
+    add(gu, nn(an(ld(H, fs, zmm), Uzmm), ld(link, fs, zmmpn)));
+    add(gu, nn(an(ld(link, fs, zmm), Uzmm), ld(H, fs, zmmpn)));
+    add(gu, na(nn(ld(link, fs, z), Uzpm), Hzpn));
+    acc(gUnu, fs, z, hs, gu);
+  }
+};
+
+// out(f) += s * in(f) for nplanes planes (one-link term backwards, scaled copies)
+struct AxpySite {
+  double2 *out;
+  const double2 *in;
+  double s;
+  size_t fs;
+  int nplanes;
+  B200KS_HD void operator()(int f) const {
+    for (int k = 0; k < nplanes; k++) {
+      double2 v = out[(size_t)k * fs + f];
+      const double2 w = in[(size_t)k * fs + f];
+      v.x += s * w.x;
+      v.y += s * w.y;
+      out[(size_t)k * fs + f] = v;
+    }
+  }
+};
+struct ZeroSite {
+  double2 *out;
+  size_t fs;
+  int nplanes;
+  B200KS_HD void operator()(int f) const {
+    for (int k = 0; k < nplanes; k++) out[(size_t)k * fs + f] = make_double2(0.0, 0.0);
+  }
+};
+
+// 4. Naik product backwards (lng = s * W W W): gW(z) += s [ G(z) (W1 W2)^+ + W(-1)^+ G(-1) W1^+ + (W(-2) W(-1))^+ G(-2) ]
+struct NaikBwdSite {
+  FGeom g;
+  const double2 *glng, *W;   // four directions, 36 planes each
+  double2 *gW;
+  double s;
+  size_t fs;
+  B200KS_HD void operator()(int z) const {
+    for (int mu = 0; mu < 4; mu++) {
+      const double2 *Wm = W + (size_t)mu * 9 * fs, *Gm = glng + (size_t)mu * 9 * fs;
+      const int p1 = nbr(g, z, mu, 1), p2 = nbr(g, p1, mu, 1), m1 = nbr(g, z, mu, -1), m2 = nbr(g, m1, mu, -1);
+      const Mat W1 = ld(Wm, fs, p1), Wm1 = ld(Wm, fs, m1);
+      Mat r = na(ld(Gm, fs, z), nn(W1, ld(Wm, fs, p2)));
+      add(r, na(an(Wm1, ld(Gm, fs, m1)), W1));
+      add(r, an(nn(ld(Wm, fs, m2), Wm1), ld(Gm, fs, m2)));
+      acc(gW + (size_t)mu * 9 * fs, fs, z, s, r);
+    }
+  }
+};
+
+// Hermitian 3x3 eigen-decomposition by cyclic Jacobi rotations: Q = E diag(g) E^+
+B200KS_HD void herm_eig(const Mat &Q, double (&g)[3], Mat &E) {
+  double2 a[3][3], v[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      a[i][j] = Q.e[3 * i + j];
+      v[i][j] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+    }
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) off += a[p][q].x * a[p][q].x + a[p][q].y * a[p][q].y;
+    if (off < 1e-60) break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        const double ar = a[p][q].x, ai = a[p][q].y, ab = sqrt(ar * ar + ai * ai);
+        if (ab < 1e-300) continue;
+        const double er = ar / ab, ei = ai / ab;
+        const double theta = (a[q][q].x - a[p][p].x) / (2.0 * ab);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(1.0 + theta * theta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int i = 0; i < 3; i++)
+          for (int w = 0; w < 2; w++) {   // columns p, q of a and of v
+            double2 &P = w ? v[i][p] : a[i][p];
+            double2 &R = w ? v[i][q] : a[i][q];
+            const double pr = P.x, pi = P.y, qr = R.x, qi = R.y;
+            const double cqr = er * qr + ei * qi, cqi = er * qi - ei * qr;
+            const double epr = er * pr - ei * pi, epi = er * pi + ei * pr;
+            P = make_double2(c * pr - s * cqr, c * pi - s * cqi);
+            R = make_double2(s * epr + c * qr, s * epi + c * qi);
+          }
+        for (int j = 0; j < 3; j++) {     // rows p, q of a
+          const double pr = a[p][j].x, pi = a[p][j].y, qr = a[q][j].x, qi = a[q][j].y;
+          const double eqr = er * qr - ei * qi, eqi = er * qi + ei * qr;
+          const double cpr = er * pr + ei * pi, cpi = er * pi - ei * pr;
+          a[p][j] = make_double2(c * pr - s * eqr, c * pi - s * eqi);
+          a[q][j] = make_double2(s * cpr + c * qr, s * cpi + c * qi);
+        }
+      }
+  }
+  for (int i = 0; i < 3; i++) g[i] = a[i][i].x;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) E.e[3 * i + j] = v[i][j];
+}
+
+// 5. U(3) projection backwards, one link:  G_V = G_W Q^-1/2 + V (G_Q + G_Q^+),
+//    G_Q = E [phi .* (E^+ (V^+ G_W) E)] E^+,  phi_ij = (g_i^-1/2 - g_j^-1/2)/(g_i - g_j)
+B200KS_HD Mat unit_bwd(const Mat &V, const Mat &GW) {
+  const Mat Q = an(V, V);
+  double g[3];
+  Mat E;
+  herm_eig(Q, g, E);
+  const Mat Ed = dag(E);
+  Mat Rt = nn(Ed, nn(an(V, GW), E));
+  Mat S = zero();
+  for (int i = 0; i < 3; i++) {
+    const double ri = sqrt(g[i]);
+    S.e[4 * i].x = 1.0 / ri;
+    for (int j = 0; j < 3; j++) {
+      const double rj = sqrt(g[j]);
+      const double phi = -1.0 / (ri * rj * (ri + rj));   // = (1/ri - 1/rj)/(g_i - g_j), also at g_i = g_j
+      Rt.e[3 * i + j].x *= phi;
+      Rt.e[3 * i + j].y *= phi;
+    }
+  }
+  Mat Gq = nn(E, nn(Rt, Ed));
+  add(Gq, dag(Gq));
+  Mat r = nn(GW, nn(E, nn(S, Ed)));
+  add(r, nn(V, Gq));
+  return r;
+}
+struct UnitBwdSite {   // index k over 4*nsites links: mu = k / nsites
+  const double2 *V;
+  double2 *gW;         // in: G_W, out: G_V (in place)
+  size_t fs;
+  int nsites;
+  B200KS_HD void operator()(int k) const {
+    const int mu = k / nsites, f = k - mu * nsites;
+    const size_t o = (size_t)mu * 9 * fs;
+    st(gW + o, fs, f, unit_bwd(ld(V + o, fs, f), ld(gW + o, fs, f)));
+  }
+};
+
+// 6. momentum increment A = -eps TA(U G_U^+) as MILC's anti_hermitmat (include/su3.h):
+//    {m01.re, m01.im, m02.re, m02.im, m12.re, m12.im, m00im, m11im, m22im, space}
+template <typename TH>
+struct MomSite {
+  const double2 *U, *gU;
+  TH *mom;             // [site][dir][10]
+  double eps;
+  size_t fs;
+  int nsites;
+  B200KS_HD void operator()(int k) const {
+    const int mu = k / nsites, f = k - mu * nsites;
+    const size_t o = (size_t)mu * 9 * fs;
+    const Mat M = na(ld(U + o, fs, f), ld(gU + o, fs, f));
+    const double tr = (M.e[0].y + M.e[4].y + M.e[8].y) / 3.0;
+    TH *m = mom + 10 * ((size_t)4 * f + mu);
+    m[0] = (TH)(-eps * 0.5 * (M.e[1].x - M.e[3].x));
+    m[1] = (TH)(-eps * 0.5 * (M.e[1].y + M.e[3].y));
+    m[2] = (TH)(-eps * 0.5 * (M.e[2].x - M.e[6].x));
+    m[3] = (TH)(-eps * 0.5 * (M.e[2].y + M.e[6].y));
+    m[4] = (TH)(-eps * 0.5 * (M.e[5].x - M.e[7].x));
+    m[5] = (TH)(-eps * 0.5 * (M.e[5].y + M.e[7].y));
+    m[6] = (TH)(-eps * (M.e[0].y - tr));
+    m[7] = (TH)(-eps * (M.e[4].y - tr));
+    m[8] = (TH)(-eps * (M.e[8].y - tr));
+    m[9] = (TH)0;
+  }
+};
+
+// ---- the chain, written once for any executor X with  template <class F> void X::run(int n, const F &f) ----
+struct ForceBufs {
+  FGeom g;
+  size_t fs;          // plane stride of every matrix field
+  int nsites;
+  double2 *U, *V, *W;             // 36 planes each (inputs)
+  double2 *gfat, *glng, *gW, *gU; // 36 planes each
+  double2 *st3, *st5, *g3, *g5;   // 9 planes each
+};
+
+// reverse of one smearing level (links.cuh smear_dev / load_fatlinks_cpu): gfat -> adds to glinks
+template <class X>
+void smear_bwd(X &x, const ForceBufs &b, const double *coeffs, const double2 *links, const double2 *gfat, double2 *glinks) {
+  const double one_link = coeffs[0], three = coeffs[2], five = coeffs[3], seven = coeffs[4], lepage = coeffs[5];
+  const size_t fs = b.fs, m1 = 9 * fs;
+  const int n = b.nsites;
+  x.run(n, AxpySite{glinks, gfat, one_link - 6.0 * lepage, fs, 36});
+  if (three == 0.0 && lepage == 0.0 && five == 0.0) return;
+  for (int dir = 0; dir < 4; dir++) {
+    const double2 *Gd = gfat + dir * m1;
+    for (int nu = 0; nu < 4; nu++) {
+      if (nu == dir) continue;
+      const double2 *Unu = links + nu * m1;
+      x.run(n, StapleFwdSite{b.g, b.st3, links + dir * m1, Unu, fs, dir, nu});
+      x.run(n, ZeroSite{b.g3, fs, 9});
+      x.run(n, AxpySite{b.g3, Gd, three, fs, 9});
+      if (lepage != 0.0) x.run(n, StapleBwdSite{b.g, Gd, lepage, b.st3, Unu, b.g3, glinks + nu * m1, fs, dir, nu});
+      for (int rho = 0; rho < 4; rho++) {
+        if (rho == dir || rho == nu) continue;
+        const double2 *Urho = links + rho * m1;
+        x.run(n, StapleFwdSite{b.g, b.st5, b.st3, Urho, fs, dir, rho});
+        x.run(n, ZeroSite{b.g5, fs, 9});
+        x.run(n, AxpySite{b.g5, Gd, five, fs, 9});
+        for (int sig = 0; sig < 4; sig++) {
+          if (sig == dir || sig == nu || sig == rho) continue;
+          x.run(n, StapleBwdSite{b.g, Gd, seven, b.st5, links + sig * m1, b.g5, glinks + sig * m1, fs, dir, sig});
+        }
+        x.run(n, StapleBwdSite{b.g, b.g5, 1.0, b.st3, Urho, b.g3, glinks + rho * m1, fs, dir, rho});
+      }
+      x.run(n, StapleBwdSite{b.g, b.g3, 1.0, links + dir * m1, Unu, glinks + dir * m1, glinks + nu * m1, fs, dir, nu});
+    }
+  }
+}
+
+// gfat / glng hold the outer products on entry; on exit gU holds G_U.  naik_in_oprod: the three-hop
+// coefficients already carry the Naik coefficient (qudaHisqForce's convention), else coeffs2[1] is applied here.
+template <class X>
+void force_chain(X &x, const ForceBufs &b, const double *coeffs1, const double *coeffs2, bool naik_in_oprod) {
+  const int n = b.nsites;
+  x.run(n, ZeroSite{b.gW, b.fs, 36});
+  x.run(n, ZeroSite{b.gU, b.fs, 36});
+  smear_bwd(x, b, coeffs2, b.W, b.gfat, b.gW);
+  x.run(n, NaikBwdSite{b.g, b.glng, b.W, b.gW, naik_in_oprod ? 1.0 : coeffs2[1], b.fs});
+  x.run(4 * n, UnitBwdSite{b.V, b.gW, b.fs, n});
+  smear_bwd(x, b, coeffs1, b.U, b.gW, b.gU);
+}
+
+}  // namespace force
+}  // namespace b200ks

@@ -271,6 +271,30 @@ void qudaLoadUnitarizedLink(int precision, QudaFatLinkArgs_t, const double path_
   if (S.verbosity >= QUDA_VERBOSE) printf("qudaLoadUnitarizedLink: %lld links took the SVD branch\n", nsvd);
 }
 
+void qudaHisqParamsInit(QudaHisqParams_t) {
+  // the force takes W and V from the caller, so the reunitarisation switches have nothing to act
+  // on here; the force filter is not implemented (include/b200ks.h)
+}
+
+void qudaHisqForce(int precision, int num_terms, int num_naik_terms, double dt, double **coeff, void **quark_field,
+                   const double level2_coeff[6], const double fat7_coeff[6], const void *const w_link,
+                   const void *const v_link, const void *const u_link, void *const milc_momentum) {
+  static const char where[] = "qudaHisqForce";
+  ensure_ctx(where);
+  if (num_naik_terms != 0) {
+    printf("%s: several Naik epsilons are not supported by libb200ks\n", where);
+    exit(1);
+  }
+  std::vector<double> cf(2 * (size_t)num_terms);
+  for (int t = 0; t < num_terms; t++) {
+    cf[2 * t] = coeff[t][0];
+    cf[2 * t + 1] = coeff[t][1];
+  }
+  if (b200ks_hisq_force(S.ctx, num_terms, cf.data(), (const void *const *)quark_field, level2_coeff, fat7_coeff, w_link, v_link,
+                        u_link, dt, milc_momentum, precision) < 0)
+    die(where);
+}
+
 double qudaMomAction(int precision, QudaMILCSiteArg_t *arg) {
   static const char where[] = "qudaMomAction";
   ensure_ctx(where);

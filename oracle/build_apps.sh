@@ -13,6 +13,8 @@
 #                                                include/quda_milc_interface.h  (route 2)
 #   ks_spectrum_hisq_b200fl su3_rhmc_hisq_b200fl as _b200 plus -DUSE_FL_GPU (WANT_FL_GPU=true): the
 #                                                HISQ links are built on the GPU as well
+#   su3_rhmc_hisq_b200ff                         as _b200fl plus -DUSE_FF_GPU (WANT_FF_GPU=true): the
+#                                                HISQ fermion force on the GPU too
 #
 # It also stages the sample inputs, golden outputs, tolerance files and sample lattices the
 # reference's own regression uses (ks_spectrum/test, ks_imp_rhmc/test, binary_samples) into
@@ -82,6 +84,10 @@ build_app() {  # name appdir flavour(cpu|b200) appfiles generic gks defs
     # links are built through qudaLoadUnitarizedLink / qudaLoadKSLink
     fl="$fl $GPU_FLAGS -DUSE_FL_GPU"; dsl="dslash_fn"; extra_gen="milc_to_quda_utilities"
     extra_gks="d_congrad5_fn_gpu ks_multicg_offset_gpu fermion_links_fn_load_gpu"
+  elif [ "$flav" = "b200ff" ]; then
+    # additionally WANT_FF_GPU=true (Makefile:458-461): the HISQ fermion force goes through qudaHisqForce
+    fl="$fl $GPU_FLAGS -DUSE_FL_GPU -DUSE_FF_GPU"; dsl="dslash_fn"; extra_gen="milc_to_quda_utilities"
+    extra_gks="d_congrad5_fn_gpu ks_multicg_offset_gpu fermion_links_fn_load_gpu"
   else
     fl="$fl $CPU_FLAGS"
   fi
@@ -113,6 +119,8 @@ for flav in cpu b200 b200fl; do
   build_app ks_spectrum_hisq ks_spectrum "$flav" "$SPEC_APP" "$SPEC_GENERIC" "$SPEC_GKS" "$SPEC_DEFS"
   build_app su3_rhmc_hisq ks_imp_rhmc "$flav" "$RHMC_APP" "$RHMC_GENERIC" "$RHMC_GKS" "$RHMC_DEFS"
 done
+# links, solves AND the fermion force on the GPU (RHMC only: spectroscopy has no force)
+build_app su3_rhmc_hisq ks_imp_rhmc b200ff "$RHMC_APP" "$RHMC_GENERIC" "$RHMC_GKS" "$RHMC_DEFS"
 
 # stage the reference's regression fixtures (data, not source)
 S="$OUT/samples"

@@ -1,0 +1,81 @@
+"""CPU test of the CUDA force's arithmetic: the __host__ __device__
+site routines of milc_qcd_b200/csrc/force.cuh and the chain that sequences them, run in host loops
+(tests/host/force_host.cu, compiled with nvcc for the host), against the CPU oracle
+(oracle/ks_force_oracle.c) and the committed output of the reference's eo_fermion_force_multi."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HOST_DIR = os.path.join(ROOT, "tests", "host")
+SO = os.path.join(HOST_DIR, "libforce_host.so")
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def host_force():
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    src = os.path.join(HOST_DIR, "force_host.cu")
+    hdr = os.path.join(ROOT, "milc_qcd_b200", "csrc", "force.cuh")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-x", "cu", "--shared", "-Xcompiler", "-fPIC", "-o", SO, src])
+    lib = C.CDLL(SO)
+    lib.force_host.restype = None
+    lib.force_host.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_int, _dp]
+    return lib
+
+
+def _run(lib, dims, U, V, W, X, c1, c3, eps, naik_in_oprod, coeffs1, coeffs2):
+    mom = np.zeros((U.shape[0], 4, 10))
+    lib.force_host(np.ascontiguousarray(dims, np.int32), np.ascontiguousarray(coeffs1, np.float64),
+                   np.ascontiguousarray(coeffs2, np.float64), np.ascontiguousarray(U), np.ascontiguousarray(V),
+                   np.ascontiguousarray(W), np.ascontiguousarray(X), np.ascontiguousarray(c1, np.float64),
+                   np.ascontiguousarray(c3, np.float64), X.shape[0], eps, int(naik_in_oprod), mom)
+    return mom
+
+
+def test_force_site_routines_match_reference_golden(host_force):
+    from oracle.pyoracle import LinksOracle
+    lo = LinksOracle()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_hisq_force.npz"))
+    dims = tuple(int(d) for d in g["dims"])
+    U, X, res = g["U"], g["multi_x"], g["residues"]
+    L = lo.hisq_links(dims, U)
+    naik = lo.ASQTAD_LIKE[1]
+    # the seam's convention (qudaHisqForce): one-hop 2 res, three-hop naik * 2 res
+    mom = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE)
+    assert np.abs(mom - g["mom"]).max() <= 1e-11 * np.abs(g["mom"]).max()
+    # the other convention: Naik coefficient applied in the chain
+    mom2 = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, 2 * res, float(g["eps"]), False, lo.FAT7, lo.ASQTAD_LIKE)
+    assert np.abs(mom2 - g["mom"]).max() <= 1e-11 * np.abs(g["mom"]).max()
+
+
+@pytest.mark.parametrize("dims,spread", [((4, 6, 2, 4), 0.4), ((2, 2, 4, 6), 0.8)])
+def test_force_site_routines_match_oracle(host_force, dims, spread):
+    """Asymmetric lattices (incl. extents of 2, where +mu and -mu are the same neighbour), other
+    coefficients (tadpole-improved asqtad levels), three terms."""
+    from milc_qcd_b200 import fields as F
+    from oracle.pyoracle import LinksOracle, Oracle, ODD
+    lo, o = LinksOracle(), Oracle()
+    V_ = int(np.prod(dims))
+    h = V_ // 2
+    U = F.make_thin_links(dims, seed=5, spread=spread)
+    u0 = 0.9
+    c2 = (1.0, -1.0 / (24 * u0 ** 2), -1.0 / (16 * u0 ** 2), 1.0 / (64 * u0 ** 4), -1.0 / (384 * u0 ** 6), -1.0 / (8 * u0 ** 4))
+    L = lo.hisq_links(dims, U, lo.FAT7, c2, allow_svd=False)
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((3, V_, 3, 2))
+    X[:, h:] = 0
+    for j in range(3):
+        X[j, h:] = o.dslash(dims, L["fat"], L["lng"], X[j], ODD)[h:]
+    res = np.array([0.4, -1.1, 0.05])
+    want = lo.hisq_force(dims, U, X, res, 0.3, lo.FAT7, c2)
+    got = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, c2[1] * 2 * res, 0.3, True, lo.FAT7, c2)
+    assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()

@@ -1,0 +1,62 @@
+"""GPU parity tests of the HISQ fermion force: b200ks_hisq_force
+through the C ABI against the committed output of the reference's own eo_fermion_force_multi
+(tests/golden/ref_hisq_force.npz) and against the CPU oracle (oracle/ks_force_oracle.c, pinned on
+the reference).  The same site routines are checked on the host in tests/test_force_host.py."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force.npz")
+
+
+@pytest.fixture(scope="module")
+def api():
+    from milc_qcd_b200 import api
+    yield api
+    api.finalize()
+
+
+def test_force_matches_reference_golden(api):
+    g = np.load(GOLDEN)
+    dims = tuple(int(d) for d in g["dims"])
+    U, X, res = g["U"], g["multi_x"], g["residues"]
+    ctx = api.Context(dims)
+    L = ctx.hisq_links(U)                       # V and W built on the device (row f1)
+    mom = ctx.hisq_force(U, L["V"], L["W"], list(X), res, float(g["eps"]))
+    assert np.abs(mom - g["mom"]).max() <= 1e-10 * np.abs(g["mom"]).max()
+    assert np.all(mom[..., 9] == 0) and np.abs(mom[..., 6] + mom[..., 7] + mom[..., 8]).max() < 1e-12
+    # linear in eps * residues
+    mom2 = ctx.hisq_force(U, L["V"], L["W"], list(X), 2.0 * res, 0.5 * float(g["eps"]))
+    assert np.abs(mom2 - mom).max() <= 1e-12 * np.abs(mom).max()
+    # MILC_PRECISION=1 hosts
+    m32 = ctx.hisq_force(U.astype(np.float32), L["V"].astype(np.float32), L["W"].astype(np.float32),
+                         [x.astype(np.float32) for x in X], res, float(g["eps"]))
+    assert m32.dtype == np.float32 and np.abs(m32 - g["mom"]).max() <= 2e-5 * np.abs(g["mom"]).max()
+    ctx.close()
+
+
+@pytest.mark.parametrize("dims,spread", [((4, 6, 2, 4), 0.4), ((8, 4, 4, 6), 0.6)])
+def test_force_matches_oracle(api, oracle, dims, spread):
+    from milc_qcd_b200 import fields as F
+    from oracle.pyoracle import LinksOracle
+    lo = LinksOracle()
+    V_ = int(np.prod(dims))
+    h = V_ // 2
+    U = F.make_thin_links(dims, seed=5, spread=spread)
+    u0 = 0.9
+    c2 = (1.0, -1.0 / (24 * u0 ** 2), -1.0 / (16 * u0 ** 2), 1.0 / (64 * u0 ** 4), -1.0 / (384 * u0 ** 6), -1.0 / (8 * u0 ** 4))
+    L = lo.hisq_links(dims, U, lo.FAT7, c2, allow_svd=False)
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((3, V_, 3, 2))
+    X[:, h:] = 0
+    for j in range(3):
+        X[j, h:] = oracle.dslash(dims, L["fat"], L["lng"], X[j], 1)[h:]
+    res = np.array([0.4, -1.1, 0.05])
+    want = lo.hisq_force(dims, U, X, res, 0.3, lo.FAT7, c2)
+    ctx = api.Context(dims)
+    got = ctx.hisq_force(U, L["V"], L["W"], list(X), res, 0.3, lo.FAT7, c2)
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+    ctx.close()
