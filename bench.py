@@ -747,6 +747,66 @@ def run_links(args):
     return 0
 
 
+def run_force(args):
+    """--workload force: HISQ fermion force through the host-buffer
+    call behind qudaHisqForce on the BASELINE configs[1] lattice: 9 terms (a typical RHMC
+    molecular-dynamics order), thin links generated on the device, V and W from the device link
+    construction.  value: site-terms per second end to end (U, V, W and the 9 vectors H2D, the
+    momenta D2H inside the timed region).  cpu_baseline: the reference's eo_fermion_force_multi
+    (oracle/_ref, OpenMP) on a 16^3x32 lattice of the same ensemble (a bounded sample: the
+    reference needs ~250 us per site on 8 cores)."""
+    import torch
+    from milc_qcd_b200 import api, fields as F
+    local_rank = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local_rank)
+    dims = tuple(args.lattice) if args.lattice else DIMS
+    V = int(np.prod(dims))
+    nterms = 9
+    ctx = api.Context(dims, device=local_rank)
+    ctx.hisq_links_time(1234, 1)
+    U, Vl, W = ctx.hisq_links_fetch(0), ctx.hisq_links_fetch(1), ctx.hisq_links_fetch(2)
+    rng = np.random.default_rng(77)
+    X = [rng.standard_normal((V, 3, 2)) for _ in range(nterms)]
+    res = np.linspace(0.2, 1.0, nterms)
+    times = []
+    for rep in range(max(2, args.steps)):
+        t0 = time.perf_counter()
+        mom = ctx.hisq_force(U, Vl, W, X, res, 0.02)
+        times.append(time.perf_counter() - t0)
+    t_gpu = min(times)
+    bytes_in = 3 * U.nbytes + nterms * X[0].nbytes
+    out = {"metric": "hisq_fermion_force_site_terms_per_s", "unit": "site-terms/s", "n_gpus": 1, "higher_is_better": True,
+           "data": "synthetic", "value": V * nterms / t_gpu, "seconds_per_call": t_gpu, "all_calls_s": times,
+           "us_per_site": 1e6 * t_gpu / V,
+           "config": {"workload": "HISQ fermion force, %d terms, Haar-random thin links %s, host buffers in and out"
+                                  % (nterms, "x".join(map(str, dims))), "lattice": list(dims), "nterms": nterms},
+           "e2e": {"value": V * nterms / t_gpu, "unit": "site-terms/s", "h2d_bytes_per_step": int(bytes_in),
+                   "d2h_bytes_per_step": int(mom.nbytes)},
+           "mom_max": float(np.abs(mom).max()), "device_bytes": ctx.device_bytes()}
+    ctx.close()
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import pyoracle
+            cores = os.cpu_count() or 1
+            os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+            sdims = (16, 16, 16, 32)
+            Vs = int(np.prod(sdims))
+            ref = pyoracle.MilcRef(sdims, "_omp")
+            Us = F.make_thin_links(sdims, seed=11, spread=0.5)
+            Xs = rng.standard_normal((nterms, Vs, 3, 2))
+            t0 = time.perf_counter()
+            ref.hisq_force(Us, Xs, res, 0.02)
+            t_cpu = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": Vs * nterms / t_cpu, "unit": "site-terms/s", "seconds": t_cpu, "cores": cores,
+                                   "kind": "reference", "us_per_site": 1e6 * t_cpu / Vs,
+                                   "sample": "one call of eo_fermion_force_multi (incl. its own link construction) on a "
+                                             "16x16x16x32 lattice, %d terms (oracle/_ref, -O3 -DOMP)" % nterms}
+        except Exception as ex:
+            out["cpu_baseline"] = {"value": None, "kind": "unavailable", "sample": repr(ex)}
+    print(json.dumps(out))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -760,7 +820,7 @@ def main():
     ap.add_argument("--long-recon", type=int, default=0, help="long-link storage: 18, 14 or 0 = decided on the data")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lattice", type=int, nargs=4, default=None, help="override the lattice (nx ny nz nt)")
-    ap.add_argument("--workload", default="cg", choices=["cg", "multishift", "block", "links"],
+    ap.add_argument("--workload", default="cg", choices=["cg", "multishift", "block", "links", "force"],
                     help="cg (default, the driver's line): single-mass CG; multishift: BASELINE configs[2]; "
                          "block: multi-right-hand-side CG (ks_congrad_block_parity seam); "
                          "links: HISQ fermion-link construction (qudaLoadUnitarizedLink / qudaLoadKSLink seam)")
@@ -773,6 +833,8 @@ def main():
         return run_block(args)
     if args.workload == "links":
         return run_links(args)
+    if args.workload == "force":
+        return run_force(args)
     return run_b200(args)
 
 
