@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200KS_VERSION 110 /* 110: block solve, resident sequences, link construction */
+#define B200KS_VERSION 111 /* 110: block solve, resident sequences, link construction; 111: force filter */
 
 /* parity codes, include/macros.h:68-70 */
 #define B200KS_EVEN 2
@@ -234,14 +234,18 @@ int b200ks_hisq_links_fetch(b200ks_ctx *ctx, int which, void *host, int host_pre
  *   multi_x[j]                su3_vector[V]: solution on the even sites, D solution on the odd sites
  *   level2_coeff, fat7_coeff  the six path coefficients of the two smearing levels
  *   wlink, vlink, ulink       W (unitarised), V (fat7) and U (thin, phases in): su3_matrix[4*V]
+ *   force_filter              the reference's HISQ_FORCE_FILTER (generic_ks/su3_mat_op.c:1680-1734; 5e-5 in
+ *                             ks_imp_rhmc's build, QudaHisqParams_t.force_filter at the seam): a link whose
+ *                             V^+V has an eigenvalue below it gets the derivative of V (V^+V + filter)^-1/2;
+ *                             0 = the unregularised derivative
  *   momentum                  out: anti_hermitmat[4*V], 10 reals each (include/su3.h)
  * Computed as the reverse-mode derivative of the link construction (csrc/force.cuh); double on the
- * device whatever host_prec is.  Not implemented: several Naik epsilons (num_naik_terms > 0) and
- * the HISQ_FORCE_FILTER regularisation of links whose V^+V has an eigenvalue below 5e-5.
+ * device whatever host_prec is.  Not implemented: several Naik epsilons (num_naik_terms > 0).
  * Single-GPU contexts. */
 int b200ks_hisq_force(b200ks_ctx *ctx, int nterms, const double *coeff, const void *const *multi_x,
                       const double *level2_coeff, const double *fat7_coeff, const void *wlink,
-                      const void *vlink, const void *ulink, double eps, void *momentum, int host_prec);
+                      const void *vlink, const void *ulink, double eps, double force_filter, void *momentum,
+                      int host_prec);
 
 /* ---- device-resident interface (benchmarks, resident solve sequences) -------------- */
 

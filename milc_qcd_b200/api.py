@@ -179,10 +179,12 @@ class Context:
         out["nsvd"] = n.value
         return out
 
-    def hisq_force(self, U, V, W, multi_x, residues, eps, coeffs1=None, coeffs2=None):
+    HISQ_FORCE_FILTER = 5.0e-5   # ks_imp_rhmc's build value (ks_imp_rhmc/Make_template)
+
+    def hisq_force(self, U, V, W, multi_x, residues, eps, coeffs1=None, coeffs2=None, force_filter=HISQ_FORCE_FILTER):
         """b200ks_hisq_force with MILC's weights (one-hop 2 res_j, three-hop naik * 2 res_j,
         generic_ks/fermion_force_hisq_multi.c:2189-2192): returns the momentum increment as
-        (V,4,10) anti_hermitmat arrays."""
+        (V,4,10) anti_hermitmat arrays.  force_filter = 0: the unregularised derivative."""
         c1 = self.HISQ_FAT7 if coeffs1 is None else coeffs1
         c2 = self.HISQ_ASQTAD_LIKE if coeffs2 is None else coeffs2
         n = len(multi_x)
@@ -193,7 +195,7 @@ class Context:
         ptrs = (C.c_void_p * n)(*[_ptr(x).value for x in multi_x])
         mom = np.zeros((self.volume, 4, 10), dtype=U.dtype)
         check(self.lib.b200ks_hisq_force(self.h, n, cf, ptrs, self._coeffs(c2), self._coeffs(c1), _ptr(W), _ptr(V), _ptr(U),
-                                         eps, _ptr(mom), _host_prec(U)), "b200ks_hisq_force")
+                                         eps, float(force_filter), _ptr(mom), _host_prec(U)), "b200ks_hisq_force")
         return mom
 
     def hisq_links_time(self, seed, reps, coeffs1=None, coeffs2=None):

@@ -70,10 +70,11 @@ int field_to_dev(b200ks_ctx *c, double2 *dst, size_t fs, const void *host, int h
 
 extern "C" int b200ks_hisq_force(b200ks_ctx *c, int nterms, const double *coeff, const void *const *multi_x,
                                  const double *level2_coeff, const double *fat7_coeff, const void *wlink, const void *vlink,
-                                 const void *ulink, double eps, void *momentum, int host_prec) {
+                                 const void *ulink, double eps, double force_filter, void *momentum, int host_prec) {
   if (!c || nterms < 1 || !coeff || !multi_x || !level2_coeff || !fat7_coeff || !wlink || !vlink || !ulink || !momentum)
     return fail(B200KS_EINVAL, "b200ks_hisq_force: null argument");
   if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
+  if (!(force_filter >= 0.0)) return fail(B200KS_EINVAL, "b200ks_hisq_force: negative force filter");
   if (partitioned(c)) return fail(B200KS_ESTATE, "fermion force: single-GPU contexts only");
   CU(cudaSetDevice(device(c)));
   const Geom &g = geom(c);
@@ -124,7 +125,7 @@ extern "C" int b200ks_hisq_force(b200ks_ctx *c, int nterms, const double *coeff,
     x.run(n, force::OprodSite{b.g, b.gfat, b.glng, b.fs, (const double *)vec.p, coeff[2 * j], coeff[2 * j + 1]});
     CU(cudaStreamSynchronize(stream(c)));   // vec.p is reused by the next term
   }
-  force::force_chain(x, b, fat7_coeff, level2_coeff, /*naik_in_oprod=*/true);
+  force::force_chain(x, b, fat7_coeff, level2_coeff, /*naik_in_oprod=*/true, force_filter);
   if (host_prec == 2) x.run(4 * n, force::MomSite<double>{b.U, b.gU, (double *)mom.p, eps, b.fs, n});
   else x.run(4 * n, force::MomSite<float>{b.U, b.gU, (float *)mom.p, eps, b.fs, n});
   CHK(check_launch("fermion force"));

@@ -12,7 +12,9 @@
 //                           (Z = X on even sites, D X on odd sites; + on odd x)      cf. :2009-2154
 //   2. level-2 smearing and the Naik product backwards: G_fat, G_lng -> G_W          cf. :1638-1874
 //   3. U(3) projection backwards: G_W -> G_V, exact derivative of V (V^+V)^-1/2 from the
-//      eigen-decomposition of V^+V (Daleckii-Krein)                                   cf. :1877-2006
+//      eigen-decomposition of V^+V (Daleckii-Krein); with the reference's force filter
+//      (HISQ_FORCE_FILTER, su3_mat_op.c:1680-1734) a link whose smallest eigenvalue of V^+V is
+//      below the filter gets the derivative of V (V^+V + filter)^-1/2 instead             cf. :1877-2006
 //   4. level-1 (fat7) smearing backwards: G_V -> G_U                                  cf. :1638-1874
 //   5. projection onto the momenta                                                    cf. :1433-1470
 // A forward staple pass  S(L)(x) = U_nu(x) L(x+nu) U_nu(x+mu)^+ + U_nu(x-nu)^+ L(x-nu) U_nu(x-nu+mu)
@@ -21,6 +23,13 @@
 //   G_L(z)    += U_nu(z-nu)^+ H(z-nu) U_nu(z-nu+mu) + U_nu(z) H(z+nu) U_nu(z+mu)^+
 //   G_Unu(z)  += H(z) U_nu(z+mu) L(z+nu)^+ + H(z-mu)^+ U_nu(z-mu) L(z-mu+nu)
 //              + L(z-mu)^+ U_nu(z-mu) H(z-mu+nu) + L(z) U_nu(z+mu) H(z+nu)^+
+//
+// The Lepage term is differentiated as the path the reference's force table holds (+nu+nu+mu-nu-nu with
+// the one-link coefficient as given, imp_actions/hisq/hisq_u3_action.h), i.e. the upper staple of the
+// upper 3-staple plus the lower of the lower, not as the fattening computes it (the full staple of the
+// full staple, whose two back-tracking terms the "one_link - 6 lepage" coefficient cancels for
+// unitary links).  The two agree in every direction tangent to the group, so the force is the same;
+// their radial parts differ, and a filtered link of step 3 sees the radial part of G_W.
 //
 // Every per-site routine is __host__ __device__: tests/host/force_host.cu runs the same bodies in
 // plain host loops against the CPU oracle (oracle/ks_force_oracle.c), so the arithmetic and the
@@ -141,23 +150,31 @@ struct OprodSite {
   }
 };
 
-// 2. forward staple (no fat-link accumulation): out = S(link)
+// 2. forward staple (no fat-link accumulation): out = S(link); part 1 = the upper staple only
+//    (U_nu(x) L(x+nu) U_nu(x+mu)^+), 2 = the lower one only, 3 = both
 struct StapleFwdSite {
   FGeom g;
   double2 *out;
   const double2 *link, *Unu;   // matrix fields: the mu "link" and the gauge links of direction nu
   size_t fs;
   int mu, nu;
+  int part = 3;
   B200KS_HD void operator()(int f) const {
-    const int fpn = nbr(g, f, nu, 1), fpm = nbr(g, f, mu, 1), fmn = nbr(g, f, nu, -1), fmnpm = nbr(g, fmn, mu, 1);
-    Mat up = nn(ld(Unu, fs, f), na(ld(link, fs, fpn), ld(Unu, fs, fpm)));
-    const Mat low = nn(an(ld(Unu, fs, fmn), ld(link, fs, fmn)), ld(Unu, fs, fmnpm));
-    add(up, low);
-    st(out, fs, f, up);
+    Mat r = zero();
+    if (part & 1) {
+      const int fpn = nbr(g, f, nu, 1), fpm = nbr(g, f, mu, 1);
+      r = nn(ld(Unu, fs, f), na(ld(link, fs, fpn), ld(Unu, fs, fpm)));
+    }
+    if (part & 2) {
+      const int fmn = nbr(g, f, nu, -1), fmnpm = nbr(g, fmn, mu, 1);
+      add(r, nn(an(ld(Unu, fs, fmn), ld(link, fs, fmn)), ld(Unu, fs, fmnpm)));
+    }
+    st(out, fs, f, r);
   }
 };
 
-// 3. backward staple: H = hs * Hfield is the gradient w.r.t. S(link); adds to glink and gUnu at z
+// 3. backward staple: H = hs * Hfield is the gradient w.r.t. S(link); adds to glink and gUnu at z.
+//    part as in StapleFwdSite: the contributions of the upper staple (1), the lower one (2) or both (3)
 struct StapleBwdSite {
   FGeom g;
   const double2 *H;
@@ -166,20 +183,24 @@ struct StapleBwdSite {
   double2 *glink, *gUnu;
   size_t fs;
   int mu, nu;
+  int part = 3;
   B200KS_HD void operator()(int z) const {
     const int zpn = nbr(g, z, nu, 1), zmn = nbr(g, z, nu, -1), zpm = nbr(g, z, mu, 1), zmm = nbr(g, z, mu, -1);
     const int zmnpm = nbr(g, zmn, mu, 1), zmmpn = nbr(g, zmm, nu, 1);
-    const Mat Uz = ld(Unu, fs, z), Uzpm = ld(Unu, fs, zpm), Uzmm = ld(Unu, fs, zmm);
-    const Mat Hzpn = ld(H, fs, zpn);
-    // gradient of the link field
-    Mat gl = nn(an(ld(Unu, fs, zmn), ld(H, fs, zmn)), ld(Unu, fs, zmnpm));
-    add(gl, na(nn(Uz, Hzpn), Uzpm));
+    const Mat Uzpm = ld(Unu, fs, zpm), Uzmm = ld(Unu, fs, zmm);
+    Mat gl = zero(), gu = zero();
+    if (part & 1) {   // upper staple A B C^+ at x: G_B(x+nu), G_A(x), G_C(x+mu)
+      gl = nn(an(ld(Unu, fs, zmn), ld(H, fs, zmn)), ld(Unu, fs, zmnpm));
+      gu = nn(ld(H, fs, z), na(Uzpm, ld(link, fs, zpn)));
+      add(gu, nn(an(ld(H, fs, zmm), Uzmm), ld(link, fs, zmmpn)));
+    }
+    if (part & 2) {   // lower staple D^+ E F at x, y = x - nu: G_E(y), G_F(y+mu), G_D(y)
+      const Mat Hzpn = ld(H, fs, zpn);
+      add(gl, na(nn(ld(Unu, fs, z), Hzpn), Uzpm));
+      add(gu, nn(an(ld(link, fs, zmm), Uzmm), ld(H, fs, zmmpn)));
+      add(gu, na(nn(ld(link, fs, z), Uzpm), Hzpn));
+    }
     acc(glink, fs, z, hs, gl);
-    // gradient of the nu links
-    Mat gu = nn(ld(H, fs, z), na(Uzpm, ld(link, fs, zpn)));
-    add(gu, nn(an(ld(H, fs, zmm), Uzmm), ld(link, fs, zmmpn)));
-    add(gu, nn(an(ld(link, fs, zmm), Uzmm), ld(H, fs, zmmpn)));
-    add(gu, na(nn(ld(link, fs, z), Uzpm), Hzpn));
     acc(gUnu, fs, z, hs, gu);
   }
 };
@@ -277,11 +298,14 @@ B200KS_HD void herm_eig(const Mat &Q, double (&g)[3], Mat &E) {
 
 // 5. U(3) projection backwards, one link:  G_V = G_W Q^-1/2 + V (G_Q + G_Q^+),
 //    G_Q = E [phi .* (E^+ (V^+ G_W) E)] E^+,  phi_ij = (g_i^-1/2 - g_j^-1/2)/(g_i - g_j)
-B200KS_HD Mat unit_bwd(const Mat &V, const Mat &GW) {
+//    filter > 0: when the smallest g_i is below it, all three are shifted by it (see the header)
+B200KS_HD Mat unit_bwd(const Mat &V, const Mat &GW, double filter) {
   const Mat Q = an(V, V);
   double g[3];
   Mat E;
   herm_eig(Q, g, E);
+  if (filter > 0.0 && fmin(g[0], fmin(g[1], g[2])) < filter)
+    for (int i = 0; i < 3; i++) g[i] += filter;
   const Mat Ed = dag(E);
   Mat Rt = nn(Ed, nn(an(V, GW), E));
   Mat S = zero();
@@ -306,10 +330,11 @@ struct UnitBwdSite {   // index k over 4*nsites links: mu = k / nsites
   double2 *gW;         // in: G_W, out: G_V (in place)
   size_t fs;
   int nsites;
+  double filter;
   B200KS_HD void operator()(int k) const {
     const int mu = k / nsites, f = k - mu * nsites;
     const size_t o = (size_t)mu * 9 * fs;
-    st(gW + o, fs, f, unit_bwd(ld(V + o, fs, f), ld(gW + o, fs, f)));
+    st(gW + o, fs, f, unit_bwd(ld(V + o, fs, f), ld(gW + o, fs, f), filter));
   }
 };
 
@@ -357,7 +382,7 @@ void smear_bwd(X &x, const ForceBufs &b, const double *coeffs, const double2 *li
   const double one_link = coeffs[0], three = coeffs[2], five = coeffs[3], seven = coeffs[4], lepage = coeffs[5];
   const size_t fs = b.fs, m1 = 9 * fs;
   const int n = b.nsites;
-  x.run(n, AxpySite{glinks, gfat, one_link - 6.0 * lepage, fs, 36});
+  x.run(n, AxpySite{glinks, gfat, one_link, fs, 36});
   if (three == 0.0 && lepage == 0.0 && five == 0.0) return;
   for (int dir = 0; dir < 4; dir++) {
     const double2 *Gd = gfat + dir * m1;
@@ -367,7 +392,13 @@ void smear_bwd(X &x, const ForceBufs &b, const double *coeffs, const double2 *li
       x.run(n, StapleFwdSite{b.g, b.st3, links + dir * m1, Unu, fs, dir, nu});
       x.run(n, ZeroSite{b.g3, fs, 9});
       x.run(n, AxpySite{b.g3, Gd, three, fs, 9});
-      if (lepage != 0.0) x.run(n, StapleBwdSite{b.g, Gd, lepage, b.st3, Unu, b.g3, glinks + nu * m1, fs, dir, nu});
+      if (lepage != 0.0)   // straight double staples: upper of upper, lower of lower (st5 / g5 are free here)
+        for (int part = 1; part <= 2; part++) {
+          x.run(n, StapleFwdSite{b.g, b.st5, links + dir * m1, Unu, fs, dir, nu, part});
+          x.run(n, ZeroSite{b.g5, fs, 9});
+          x.run(n, StapleBwdSite{b.g, Gd, lepage, b.st5, Unu, b.g5, glinks + nu * m1, fs, dir, nu, part});
+          x.run(n, StapleBwdSite{b.g, b.g5, 1.0, links + dir * m1, Unu, glinks + dir * m1, glinks + nu * m1, fs, dir, nu, part});
+        }
       for (int rho = 0; rho < 4; rho++) {
         if (rho == dir || rho == nu) continue;
         const double2 *Urho = links + rho * m1;
@@ -388,13 +419,13 @@ void smear_bwd(X &x, const ForceBufs &b, const double *coeffs, const double2 *li
 // gfat / glng hold the outer products on entry; on exit gU holds G_U.  naik_in_oprod: the three-hop
 // coefficients already carry the Naik coefficient (qudaHisqForce's convention), else coeffs2[1] is applied here.
 template <class X>
-void force_chain(X &x, const ForceBufs &b, const double *coeffs1, const double *coeffs2, bool naik_in_oprod) {
+void force_chain(X &x, const ForceBufs &b, const double *coeffs1, const double *coeffs2, bool naik_in_oprod, double filter) {
   const int n = b.nsites;
   x.run(n, ZeroSite{b.gW, b.fs, 36});
   x.run(n, ZeroSite{b.gU, b.fs, 36});
   smear_bwd(x, b, coeffs2, b.W, b.gfat, b.gW);
   x.run(n, NaikBwdSite{b.g, b.glng, b.W, b.gW, naik_in_oprod ? 1.0 : coeffs2[1], b.fs});
-  x.run(4 * n, UnitBwdSite{b.V, b.gW, b.fs, n});
+  x.run(4 * n, UnitBwdSite{b.V, b.gW, b.fs, n, filter});
   smear_bwd(x, b, coeffs1, b.U, b.gW, b.gU);
 }
 

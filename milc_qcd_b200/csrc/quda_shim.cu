@@ -22,6 +22,7 @@ struct ShimState {
   int latsize[4] = {0, 0, 0, 0};
   int device = 0;
   int verbosity = QUDA_SUMMARIZE;
+  double force_filter = 0.0;   // qudaHisqParamsInit
   const void *fat = nullptr, *lng = nullptr;  // identity of the host link arrays on the device
   int link_prec = 0;
   unsigned long long fp_fat = 0, fp_lng = 0;   // content fingerprints at the last upload
@@ -271,9 +272,10 @@ void qudaLoadUnitarizedLink(int precision, QudaFatLinkArgs_t, const double path_
   if (S.verbosity >= QUDA_VERBOSE) printf("qudaLoadUnitarizedLink: %lld links took the SVD branch\n", nsvd);
 }
 
-void qudaHisqParamsInit(QudaHisqParams_t) {
+void qudaHisqParamsInit(QudaHisqParams_t hisq_params) {
   // the force takes W and V from the caller, so the reunitarisation switches have nothing to act
-  // on here; the force filter is not implemented (include/b200ks.h)
+  // on here; the filter goes to every later qudaHisqForce (fermion_force_hisq_multi.c:2258-2266)
+  S.force_filter = hisq_params.force_filter > 0.0 ? hisq_params.force_filter : 0.0;
 }
 
 void qudaHisqForce(int precision, int num_terms, int num_naik_terms, double dt, double **coeff, void **quark_field,
@@ -291,7 +293,7 @@ void qudaHisqForce(int precision, int num_terms, int num_naik_terms, double dt, 
     cf[2 * t + 1] = coeff[t][1];
   }
   if (b200ks_hisq_force(S.ctx, num_terms, cf.data(), (const void *const *)quark_field, level2_coeff, fat7_coeff, w_link, v_link,
-                        u_link, dt, milc_momentum, precision) < 0)
+                        u_link, dt, S.force_filter, milc_momentum, precision) < 0)
     die(where);
 }
 

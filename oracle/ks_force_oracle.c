@@ -1,8 +1,7 @@
 /* oracle/ks_force_oracle.c -- TEST INFRASTRUCTURE, not product code.
  *
  * CPU restatement (plain C, double precision) of the reference's HISQ fermion force (SURVEY.md
- * section 8 row f2), written ahead of the CUDA kernels so that they have a pinned checker from
- * their first line on.  No product code implements this row yet.
+ * section 8 row f2): the checker of milc_qcd_b200/csrc/force.cuh + fermion_force.cu.
  *
  * PARITY PINNED: tests/test_oracle.py checks ksf_hisq_force against the committed output of the
  * reference's own eo_fermion_force_multi (tests/golden/ref_hisq_force.npz, generated from
@@ -26,8 +25,13 @@
  *   4. level-1 (fat7) smearing backwards                            cf. :1638-1874 with the p1 table
  *   5. A = -TA(U G_U^+), packed as anti_hermitmat                    cf. :1433-1470
  * "G_M" is the gradient matrix defined by dS = Re tr(G_M^+ dM).
- * Not restated: the reference's HISQ_FORCE_FILTER regularisation of tiny eigenvalues of Q (it
- * changes the force only on links with eigenvalues below 5e-5) and several Naik epsilons.
+ * HISQ_FORCE_FILTER (su3_mat_op.c:1680-1734, 5e-5 in ks_imp_rhmc's build) is restated: on a link whose
+ * smallest eigenvalue of Q is below the filter, step 3 differentiates V (Q + filter)^-1/2 instead.
+ * That function is not unitary, so on those links the RADIAL part of the level-2 gradient matters,
+ * and with it the form in which the Lepage term is differentiated (see smear_bwd); with both
+ * the restatement meets the reference to 1e-10 on links rough enough to trip the filter
+ * (tests/test_oracle.py, golden ref_hisq_force_rough.npz).
+ * Not restated: several Naik epsilons.
  */
 #include <math.h>
 #include <stdlib.h>
@@ -93,18 +97,24 @@ static void axpy(mat *a, double s, const mat *b) {
       for (r = 0; r < 2; r++) a->e[i][j][r] += s * b->e[i][j][r];
 }
 
-/* forward staple, generic/general_staple.c:41-123 (no accumulation into a fat link here) */
-static void staple_fwd(long vol, int *const *nb, mat *out, int mu, int nu, const mat *link, int stride, const mat *links) {
+/* forward staple, generic/general_staple.c:41-123 (no accumulation into a fat link here);
+   part: 1 = the upper staple only, 2 = the lower one only, 3 = both */
+static void staple_fwd(long vol, int *const *nb, mat *out, int mu, int nu, const mat *link, int stride, const mat *links, int part) {
   long i;
   for (i = 0; i < vol; i++) {
     const long y = nb[4 + nu][i];
     mat t1, up, low;
-    na(&link[(long)stride * nb[nu][i]], &links[4l * nb[mu][i] + nu], &t1);
-    nn(&links[4 * i + nu], &t1, &up);
-    an(&links[4 * y + nu], &link[(long)stride * y], &t1);
-    nn(&t1, &links[4l * nb[mu][y] + nu], &low);
-    out[i] = up;
-    axpy(&out[i], 1.0, &low);
+    memset(&out[i], 0, sizeof(mat));
+    if (part & 1) {
+      na(&link[(long)stride * nb[nu][i]], &links[4l * nb[mu][i] + nu], &t1);
+      nn(&links[4 * i + nu], &t1, &up);
+      axpy(&out[i], 1.0, &up);
+    }
+    if (part & 2) {
+      an(&links[4 * y + nu], &link[(long)stride * y], &t1);
+      nn(&t1, &links[4l * nb[mu][y] + nu], &low);
+      axpy(&out[i], 1.0, &low);
+    }
   }
 }
 
@@ -113,7 +123,7 @@ static void staple_fwd(long vol, int *const *nb, mat *out, int mu, int nu, const
      upper(x) = A B C^+ : A = U_nu(x), B = link(x+nu), C = U_nu(x+mu)
      lower(x) = D^+ E F : D = U_nu(y), E = link(y),  F = U_nu(y+mu),  y = x-nu            */
 static void staple_bwd(long vol, int *const *nb, const mat *H, int mu, int nu, const mat *link, int stride,
-                       const mat *links, mat *g_link, mat *g_links) {
+                       const mat *links, mat *g_link, mat *g_links, int part) {
   long x;
   for (x = 0; x < vol; x++) {
     const long xpn = nb[nu][x], xpm = nb[mu][x], y = nb[4 + nu][x], ypm = nb[mu][y];
@@ -121,54 +131,67 @@ static void staple_bwd(long vol, int *const *nb, const mat *H, int mu, int nu, c
     const mat *D = &links[4 * y + nu], *E = &link[(long)stride * y], *F = &links[4 * ypm + nu];
     const mat *h = &H[x];
     mat t1, t2;
-    /* upper */
-    na(C, B, &t1); nn(h, &t1, &t2); axpy(&g_links[4 * x + nu], 1.0, &t2);          /* G_A += H C B^+ */
-    an(A, h, &t1); nn(&t1, C, &t2); axpy(&g_link[(long)stride * xpn], 1.0, &t2);   /* G_B += A^+ H C */
-    an(h, A, &t1); nn(&t1, B, &t2); axpy(&g_links[4 * xpm + nu], 1.0, &t2);        /* G_C += H^+ A B */
-    /* lower */
-    nn(D, h, &t1); na(&t1, F, &t2); axpy(&g_link[(long)stride * y], 1.0, &t2);     /* G_E += D H F^+ */
-    an(E, D, &t1); nn(&t1, h, &t2); axpy(&g_links[4 * ypm + nu], 1.0, &t2);        /* G_F += E^+ D H */
-    nn(E, F, &t1); na(&t1, h, &t2); axpy(&g_links[4 * y + nu], 1.0, &t2);          /* G_D += E F H^+ */
+    if (part & 1) { /* upper */
+      na(C, B, &t1); nn(h, &t1, &t2); axpy(&g_links[4 * x + nu], 1.0, &t2);          /* G_A += H C B^+ */
+      an(A, h, &t1); nn(&t1, C, &t2); axpy(&g_link[(long)stride * xpn], 1.0, &t2);   /* G_B += A^+ H C */
+      an(h, A, &t1); nn(&t1, B, &t2); axpy(&g_links[4 * xpm + nu], 1.0, &t2);        /* G_C += H^+ A B */
+    }
+    if (part & 2) { /* lower */
+      nn(D, h, &t1); na(&t1, F, &t2); axpy(&g_link[(long)stride * y], 1.0, &t2);     /* G_E += D H F^+ */
+      an(E, D, &t1); nn(&t1, h, &t2); axpy(&g_links[4 * ypm + nu], 1.0, &t2);        /* G_F += E^+ D H */
+      nn(E, F, &t1); na(&t1, h, &t2); axpy(&g_links[4 * y + nu], 1.0, &t2);          /* G_D += E F H^+ */
+    }
   }
 }
 
-/* reverse of ksl_smear: g_fat (and g_lng, may be NULL) -> adds to g_links */
+/* reverse of ksl_smear: g_fat (and g_lng, may be NULL) -> adds to g_links.
+   The Lepage term is differentiated in the form the reference's force walks it (its path table holds the
+   straight double staple +nu+nu+mu-nu-nu only, with the one-link coefficient as given: imp_actions/hisq/
+   hisq_u3_action.h path_coeff_2, fermion_force_hisq_multi.c:1638-1874), not in the form the fattening computes it
+   (staple of the staple in the same direction, whose two back-tracking terms U_nu U_nu^+ U_mu ... are cancelled by
+   the "one_link - 6 lepage" coefficient, fermion_links_fn_load_milc.c:146).  The two functions agree for unitary
+   links and in every direction tangent to the group, so the force is the same; they differ in the radial part of
+   the gradient, which only the filtered links of step 3 can see. */
 static void smear_bwd(const int *n, const double *coeffs, const mat *links, const mat *g_fat, const mat *g_lng, mat *g_links) {
   const long vol = (long)n[0] * n[1] * n[2] * n[3];
   const double one_link = coeffs[0], naik = coeffs[1], three = coeffs[2], five = coeffs[3], seven = coeffs[4],
                lepage = coeffs[5];
   int *nb[8];
-  int d, dir, nu, rho, sig;
+  int d, dir, nu, rho, sig, part;
   long i;
   mat *st3 = (mat *)malloc(sizeof(mat) * vol), *st5 = (mat *)malloc(sizeof(mat) * vol);
   mat *g3 = (mat *)malloc(sizeof(mat) * vol), *g5 = (mat *)malloc(sizeof(mat) * vol), *h = (mat *)malloc(sizeof(mat) * vol);
+  mat *stp = (mat *)malloc(sizeof(mat) * vol), *gp = (mat *)malloc(sizeof(mat) * vol);
   for (d = 0; d < 8; d++) nb[d] = f_build_nb(n, d);
   for (dir = 0; dir < 4; dir++) {
-    for (i = 0; i < vol; i++) axpy(&g_links[4 * i + dir], one_link - 6.0 * lepage, &g_fat[4 * i + dir]);
+    for (i = 0; i < vol; i++) axpy(&g_links[4 * i + dir], one_link, &g_fat[4 * i + dir]);
     if (three == 0.0 && lepage == 0.0 && five == 0.0) continue;
     for (nu = 0; nu < 4; nu++) {
       if (nu == dir) continue;
-      staple_fwd(vol, nb, st3, dir, nu, links + dir, 4, links);
+      staple_fwd(vol, nb, st3, dir, nu, links + dir, 4, links, 3);
       for (i = 0; i < vol; i++) { /* gradient reaching the 3-staple directly: c3 * G_fat */
         memset(&g3[i], 0, sizeof(mat));
         axpy(&g3[i], three, &g_fat[4 * i + dir]);
       }
-      if (lepage != 0.0) { /* fat += lepage * staple(st3; nu) */
-        for (i = 0; i < vol; i++) { memset(&h[i], 0, sizeof(mat)); axpy(&h[i], lepage, &g_fat[4 * i + dir]); }
-        staple_bwd(vol, nb, h, dir, nu, st3, 1, links, g3, g_links);
-      }
+      if (lepage != 0.0) /* fat += lepage * (upper staple of the upper 3-staple + lower of the lower) */
+        for (part = 1; part <= 2; part++) {
+          staple_fwd(vol, nb, stp, dir, nu, links + dir, 4, links, part);
+          for (i = 0; i < vol; i++) { memset(&h[i], 0, sizeof(mat)); axpy(&h[i], lepage, &g_fat[4 * i + dir]); memset(&gp[i], 0, sizeof(mat)); }
+          staple_bwd(vol, nb, h, dir, nu, stp, 1, links, gp, g_links, part);
+          staple_bwd(vol, nb, gp, dir, nu, links + dir, 4, links, g_links + dir, g_links, part);
+        }
       for (rho = 0; rho < 4; rho++) {
         if (rho == dir || rho == nu) continue;
-        staple_fwd(vol, nb, st5, dir, rho, st3, 1, links);
+        staple_fwd(vol, nb, st5, dir, rho, st3, 1, links, 3);
         for (i = 0; i < vol; i++) { memset(&g5[i], 0, sizeof(mat)); axpy(&g5[i], five, &g_fat[4 * i + dir]); }
         for (sig = 0; sig < 4; sig++) {
           if (sig == dir || sig == nu || sig == rho) continue;
           for (i = 0; i < vol; i++) { memset(&h[i], 0, sizeof(mat)); axpy(&h[i], seven, &g_fat[4 * i + dir]); }
-          staple_bwd(vol, nb, h, dir, sig, st5, 1, links, g5, g_links);
+          staple_bwd(vol, nb, h, dir, sig, st5, 1, links, g5, g_links, 3);
         }
-        staple_bwd(vol, nb, g5, dir, rho, st3, 1, links, g3, g_links);
+        staple_bwd(vol, nb, g5, dir, rho, st3, 1, links, g3, g_links, 3);
       }
-      staple_bwd(vol, nb, g3, dir, nu, links + dir, 4, links, g_links + dir, g_links);
+      staple_bwd(vol, nb, g3, dir, nu, links + dir, 4, links, g_links + dir, g_links, 3);
     }
   }
   if (g_lng) /* lng(x) = naik U(x) U(x+mu) U(x+2mu) */
@@ -182,7 +205,7 @@ static void smear_bwd(const int *n, const double *coeffs, const mat *links, cons
         nn(a, b, &t1); an(&t1, g, &t2); axpy(&g_links[4 * i2 + dir], naik, &t2);    /* G_c += naik (a b)^+ G */
       }
   for (d = 0; d < 8; d++) free(nb[d]);
-  free(st3); free(st5); free(g3); free(g5); free(h);
+  free(st3); free(st5); free(g3); free(g5); free(h); free(stp); free(gp);
 }
 
 /* Hermitian 3x3 eigen-decomposition by cyclic Jacobi: Q = sum_k g_k |v_k><v_k|, v_k = column k */
@@ -236,13 +259,19 @@ static void herm_eig(const mat *Q, double g[3], mat *vecs) {
 
 /* reverse of W = V Q^-1/2, Q = V^+ V:  G_V = G_W Q^-1/2 + V (G_Q + G_Q^+),
    G_Q = sum_ij phi_ij P_i R P_j,  R = V^+ G_W,  phi_ij = (g_i^-1/2 - g_j^-1/2)/(g_i - g_j)  (-g^-3/2 / 2 on the diagonal) */
-static void unitarize_bwd(const mat *V, const mat *GW, mat *GV) {
+static void unitarize_bwd(const mat *V, const mat *GW, mat *GV, double filter) {
   mat Q, E, Ed, R, Rt, Gq, Gqd, S, t1, t2;
-  double g[3], phi[3][3];
+  double g[3], phi[3][3], gmin;
   int i, j;
   an(V, V, &Q);
   herm_eig(&Q, g, &E);
   adj(&E, &Ed);
+  /* HISQ_FORCE_FILTER (su3_mat_op.c:1680-1734): when the smallest eigenvalue of Q is below the filter, the
+     reference adds the filter to all three and to Q's diagonal, i.e. it differentiates V (V^+ V + filter)^-1/2 */
+  gmin = g[0] < g[1] ? g[0] : g[1];
+  if (g[2] < gmin) gmin = g[2];
+  if (filter > 0 && gmin < filter)
+    for (i = 0; i < 3; i++) g[i] += filter;
   for (i = 0; i < 3; i++)
     for (j = 0; j < 3; j++) {
       const double si = 1.0 / sqrt(g[i]), sj = 1.0 / sqrt(g[j]);
@@ -266,6 +295,15 @@ static void unitarize_bwd(const mat *V, const mat *GW, mat *GV) {
   *GV = t1;
   axpy(GV, 1.0, &t2);
 }
+
+/* one link of step 3, exported for the tests: G_V from V (9 complex) and G_W */
+void ksf_unitarize_bwd(const double *V, const double *GW, double *GV, double filter) {
+  unitarize_bwd((const mat *)V, (const mat *)GW, (mat *)GV, filter);
+}
+
+/* the reference build's HISQ_FORCE_FILTER (oracle/build_ref.sh, Make_template default 5.0e-5); 0 = unfiltered */
+double ksf_force_filter = 5.0e-5;
+void ksf_set_force_filter(double f) { ksf_force_filter = f; }
 
 /* multi_x: nterms fields of V colour vectors [6 doubles per site] (even sites X_j, odd sites D X_j);
    mom out: anti_hermitmat[4*V] as 10 doubles {m01.re, m01.im, m02.re, m02.im, m12.re, m12.im, m00im, m11im, m22im, 0} */
@@ -304,7 +342,7 @@ void ksf_hisq_force(const int *n, const double *coeffs1, const double *coeffs2, 
   }
   /* 2.-4. the chain backwards */
   smear_bwd(n, coeffs2, W, gfat, glng, gW);
-  for (i = 0; i < 4 * vol; i++) unitarize_bwd(&V[i], &gW[i], &gV[i]);
+  for (i = 0; i < 4 * vol; i++) unitarize_bwd(&V[i], &gW[i], &gV[i], ksf_force_filter);
   smear_bwd(n, coeffs1, U, gV, NULL, gU);
   /* 5. A = -eps TA(U G_U^+) */
   for (i = 0; i < 4 * vol; i++) {

@@ -96,6 +96,10 @@ class LinksOracle:
         L.ksl_unitarize.argtypes = [_dp, _dp, C.c_long, C.c_int, C.c_double, C.c_double]
         L.ksf_hisq_force.restype = None
         L.ksf_hisq_force.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, _dp]
+        L.ksf_set_force_filter.restype = None
+        L.ksf_set_force_filter.argtypes = [C.c_double]
+        L.ksf_unitarize_bwd.restype = None
+        L.ksf_unitarize_bwd.argtypes = [_dp, _dp, _dp, C.c_double]
         L.ksl_hisq_links.restype = C.c_long
         L.ksl_hisq_links.argtypes = [_ip, _dp, _dp, _dp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_double, C.c_double]
@@ -118,8 +122,19 @@ class LinksOracle:
         n = self.lib.ksl_unitarize(V, W, V.size // 18, int(allow_svd), svd_rel, svd_abs)
         return W, int(n)
 
-    def hisq_force(self, dims, links, multi_x, residues, eps, coeffs1=None, coeffs2=None):
-        """ks_force_oracle.c: the momentum update of eo_fermion_force_multi as (V,4,10) anti_hermitmat arrays."""
+    FORCE_FILTER = 5.0e-5   # HISQ_FORCE_FILTER of ks_imp_rhmc's build (ks_imp_rhmc/Make_template)
+
+    def unitarize_bwd(self, V, GW, force_filter=FORCE_FILTER):
+        """One link of the projection's reverse step: G_V from V and G_W, (3,3,2) arrays."""
+        GV = np.zeros((3, 3, 2))
+        self.lib.ksf_unitarize_bwd(np.ascontiguousarray(V, np.float64), np.ascontiguousarray(GW, np.float64), GV,
+                                   force_filter)
+        return GV
+
+    def hisq_force(self, dims, links, multi_x, residues, eps, coeffs1=None, coeffs2=None, force_filter=FORCE_FILTER):
+        """ks_force_oracle.c: the momentum update of eo_fermion_force_multi as (V,4,10) anti_hermitmat arrays.
+        force_filter = 0 gives the unregularised derivative."""
+        self.lib.ksf_set_force_filter(force_filter)
         links = np.ascontiguousarray(links, np.float64)
         xs = np.ascontiguousarray(multi_x, np.float64)
         res = np.ascontiguousarray(residues, np.float64)

@@ -7,7 +7,8 @@ sites with their odd sites filled by D X_j through the HISQ links built from tho
 (what ks_imp_rhmc/update_h_rhmc.c:75-86 hands to the force), residues (0.7, -0.3), eps = 1.
 Output: the momentum update of the reference's eo_fermion_force_multi
 (generic_ks/fermion_force_hisq_multi.c:170-216, wrapper_mx path, ks_imp_rhmc's build flags) as
-anti_hermitmat arrays.  No CUDA implementation consumes it yet: it pins the oracle for the next row.
+anti_hermitmat arrays.  A second file, ref_hisq_force_rough.npz, holds the same for links rough enough
+to trip the reference's eigenvalue filter and SVD branches.
 """
 import os
 import sys
@@ -38,6 +39,19 @@ def main():
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_hisq_force.npz")
     np.savez_compressed(path, dims=np.array(dims), U=U, multi_x=X, residues=residues, eps=1.0, mom=mom, nsvd=n)
     print("wrote", path, os.path.getsize(path), "bytes; |mom|max", np.abs(mom).max())
+
+    # rough links: some eigenvalues of Q = V^+ V fall below HISQ_FORCE_FILTER (5e-5) and below the
+    # SVD thresholds, so the reference takes its filter and SVD branches (count = nsvd)
+    U = F.make_thin_links(dims, seed=11, spread=0.8)
+    links = lo.hisq_links(dims, U)
+    X[:, h:] = 0
+    for j in range(2):
+        X[j, h:] = o.dslash(dims, links["fat"], links["lng"], X[j], ODD)[h:]
+    mom, n = ref.hisq_force(U, X, residues, 1.0)
+    assert n > 0
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_hisq_force_rough.npz")
+    np.savez_compressed(path, dims=np.array(dims), U=U, multi_x=X, residues=residues, eps=1.0, mom=mom, nsvd=n)
+    print("wrote", path, os.path.getsize(path), "bytes; |mom|max", np.abs(mom).max(), "filter+svd links", n)
 
 
 if __name__ == "__main__":

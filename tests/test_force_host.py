@@ -28,16 +28,16 @@ def host_force():
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-x", "cu", "--shared", "-Xcompiler", "-fPIC", "-o", SO, src])
     lib = C.CDLL(SO)
     lib.force_host.restype = None
-    lib.force_host.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_int, _dp]
+    lib.force_host.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_double, _dp]
     return lib
 
 
-def _run(lib, dims, U, V, W, X, c1, c3, eps, naik_in_oprod, coeffs1, coeffs2):
+def _run(lib, dims, U, V, W, X, c1, c3, eps, naik_in_oprod, coeffs1, coeffs2, force_filter=5.0e-5):
     mom = np.zeros((U.shape[0], 4, 10))
     lib.force_host(np.ascontiguousarray(dims, np.int32), np.ascontiguousarray(coeffs1, np.float64),
                    np.ascontiguousarray(coeffs2, np.float64), np.ascontiguousarray(U), np.ascontiguousarray(V),
                    np.ascontiguousarray(W), np.ascontiguousarray(X), np.ascontiguousarray(c1, np.float64),
-                   np.ascontiguousarray(c3, np.float64), X.shape[0], eps, int(naik_in_oprod), mom)
+                   np.ascontiguousarray(c3, np.float64), X.shape[0], eps, int(naik_in_oprod), force_filter, mom)
     return mom
 
 
@@ -57,7 +57,7 @@ def test_force_site_routines_match_reference_golden(host_force):
     assert np.abs(mom2 - g["mom"]).max() <= 1e-11 * np.abs(g["mom"]).max()
 
 
-@pytest.mark.parametrize("dims,spread", [((4, 6, 2, 4), 0.4), ((2, 2, 4, 6), 0.8)])
+@pytest.mark.parametrize("dims,spread", [((4, 6, 2, 4), 0.4), ((2, 2, 4, 6), 0.8), ((8, 4, 4, 6), 0.6)])
 def test_force_site_routines_match_oracle(host_force, dims, spread):
     """Asymmetric lattices (incl. extents of 2, where +mu and -mu are the same neighbour), other
     coefficients (tadpole-improved asqtad levels), three terms."""
@@ -79,3 +79,27 @@ def test_force_site_routines_match_oracle(host_force, dims, spread):
     want = lo.hisq_force(dims, U, X, res, 0.3, lo.FAT7, c2)
     got = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, c2[1] * 2 * res, 0.3, True, lo.FAT7, c2)
     assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
+
+
+def test_force_filter_matches_reference_on_rough_links(host_force):
+    """Links rough enough that eigenvalues of V^+ V fall below the reference's HISQ_FORCE_FILTER (5e-5)
+    and its SVD thresholds: the committed output of the reference's eo_fermion_force_multi
+    (tests/golden/ref_hisq_force_rough.npz, 11 links on the filter / SVD branches).  The reference's
+    own eigenvalues come from the closed-form cubic, hence 1e-9 rather than 1e-11."""
+    from oracle.pyoracle import LinksOracle
+    lo = LinksOracle()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_hisq_force_rough.npz"))
+    dims = tuple(int(d) for d in g["dims"])
+    U, X, res = g["U"], g["multi_x"], g["residues"]
+    assert int(g["nsvd"]) > 0
+    L = lo.hisq_links(dims, U)
+    naik = lo.ASQTAD_LIKE[1]
+    scale = np.abs(g["mom"]).max()
+    mom = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE, 5.0e-5)
+    assert np.abs(mom - g["mom"]).max() <= 1e-9 * scale
+    assert np.abs(mom - lo.hisq_force(dims, U, X, res, float(g["eps"]))).max() <= 1e-11 * scale
+    # the filter is what makes the difference on this input, and switching it off matches the oracle's unfiltered force
+    raw = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE, 0.0)
+    assert np.abs(raw - g["mom"]).max() > 0.1 * scale
+    want = lo.hisq_force(dims, U, X, res, float(g["eps"]), force_filter=0.0)
+    assert np.abs(raw - want).max() <= 1e-10 * np.abs(want).max()

@@ -60,3 +60,25 @@ def test_force_matches_oracle(api, oracle, dims, spread):
     got = ctx.hisq_force(U, L["V"], L["W"], list(X), res, 0.3, lo.FAT7, c2)
     assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
     ctx.close()
+
+
+def test_force_filter_matches_reference_on_rough_links(api):
+    """tests/golden/ref_hisq_force_rough.npz: 11 links on the reference's eigenvalue-filter / SVD branches
+    (HISQ_FORCE_FILTER = 5e-5).  The reference's own eigenvalues come from the closed-form cubic, hence 1e-8."""
+    from oracle.pyoracle import LinksOracle
+    lo = LinksOracle()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force_rough.npz"))
+    dims = tuple(int(d) for d in g["dims"])
+    U, X, res, eps = g["U"], g["multi_x"], g["residues"], float(g["eps"])
+    scale = np.abs(g["mom"]).max()
+    ctx = api.Context(dims)
+    L = ctx.hisq_links(U)
+    assert L["nsvd"] > 0
+    mom = ctx.hisq_force(U, L["V"], L["W"], list(X), res, eps)            # default filter: ks_imp_rhmc's 5e-5
+    assert np.abs(mom - g["mom"]).max() <= 1e-8 * scale
+    assert np.abs(mom - lo.hisq_force(dims, U, X, res, eps)).max() <= 1e-9 * scale
+    raw = ctx.hisq_force(U, L["V"], L["W"], list(X), res, eps, force_filter=0.0)
+    assert np.abs(raw - g["mom"]).max() > 0.1 * scale
+    want = lo.hisq_force(dims, U, X, res, eps, force_filter=0.0)
+    assert np.abs(raw - want).max() <= 1e-6 * np.abs(want).max()    # 1 / g^(3/2) amplification at g = 5e-6
+    ctx.close()

@@ -334,6 +334,49 @@ def test_reference_force_golden_is_the_derivative_of_the_oracle_action(oracle, l
     assert np.abs(mom[..., 6] + mom[..., 7] + mom[..., 8]).max() < 1e-12
 
 
+@pytest.mark.parametrize("name,tol", [("ref_hisq_force.npz", 1e-11), ("ref_hisq_force_rough.npz", 1e-9)])
+def test_force_oracle_matches_reference_golden(links_oracle, name, tol):
+    """ks_force_oracle.c against the committed output of the reference's eo_fermion_force_multi.  The rough
+    file has 11 links on the reference's HISQ_FORCE_FILTER / SVD branches: without the filter the
+    restatement is off by O(1) there.  (1e-9: the reference's eigenvalues come from the closed-form cubic.)"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+    dims = tuple(int(d) for d in g["dims"])
+    scale = np.abs(g["mom"]).max()
+    mom = links_oracle.hisq_force(dims, g["U"], g["multi_x"], g["residues"], float(g["eps"]))
+    assert np.abs(mom - g["mom"]).max() <= tol * scale
+    raw = links_oracle.hisq_force(dims, g["U"], g["multi_x"], g["residues"], float(g["eps"]), force_filter=0.0)
+    if int(g["nsvd"]) == 0:
+        assert np.array_equal(raw, mom)
+    else:
+        assert np.abs(raw - g["mom"]).max() > 0.1 * scale
+
+
+def test_force_filter_is_the_derivative_of_the_shifted_projection(links_oracle):
+    """What HISQ_FORCE_FILTER does to one link (generic_ks/su3_mat_op.c:1680-1734): when the smallest eigenvalue
+    of Q = V^+ V is below the filter, the reverse step is the exact derivative of V (Q + filter)^-1/2, by
+    finite differences; above it, of V Q^-1/2."""
+    rng = np.random.default_rng(12)
+
+    def w(Vc, shift):
+        gq, E = np.linalg.eigh(Vc.conj().T @ Vc + shift * np.eye(3))
+        return Vc @ (E * gq ** -0.5) @ E.conj().T
+
+    for smin, shifted in [(3e-3, True), (2e-2, False)]:          # g_min = 9e-6 and 4e-4
+        A = rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3))
+        u, _, vh = np.linalg.svd(A)
+        Vc = u @ np.diag([1.1, 0.8, smin]) @ vh
+        GW = rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3))
+        dV = (rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3))) * 1e-4 * smin
+        GV = links_oracle.unitarize_bwd(np.stack([Vc.real, Vc.imag], -1), np.stack([GW.real, GW.imag], -1), 5e-5)
+        GV = GV[..., 0] + 1j * GV[..., 1]
+        pred = np.trace(GV.conj().T @ dV).real
+        fd = {}
+        for shift in (0.0, 5e-5):
+            fd[shift] = 0.5 * np.trace(GW.conj().T @ (w(Vc + dV, shift) - w(Vc - dV, shift))).real
+        assert abs(pred - fd[5e-5 if shifted else 0.0]) <= 1e-5 * abs(pred)
+        assert abs(pred - fd[0.0 if shifted else 5e-5]) > 1e-3 * abs(pred)
+
+
 def test_reference_force_live_matches_golden():
     from oracle.pyoracle import ref_available
     if not ref_available():
@@ -348,7 +391,12 @@ mom, n = ref.hisq_force(g['U'], g['multi_x'], g['residues'], float(g['eps']))
 assert np.abs(mom - g['mom']).max() <= 1e-12 * np.abs(g['mom']).max()
 m2, _ = ref.hisq_force(g['U'], g['multi_x'], 2.0 * g['residues'], 0.5)      # linear in eps * residues
 assert np.abs(m2 - g['mom']).max() <= 1e-12 * np.abs(g['mom']).max()
+g = np.load(%r)                                                              # filter / SVD branches
+mom, n = ref.hisq_force(g['U'], g['multi_x'], g['residues'], float(g['eps']))
+assert n == int(g['nsvd']) and n > 0
+assert np.abs(mom - g['mom']).max() <= 1e-12 * np.abs(g['mom']).max()
 print('LIVE-OK')
-""" % (ROOT, os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force.npz"))
+""" % (ROOT, os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force.npz"),
+       os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force_rough.npz"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert "LIVE-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
