@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200KS_VERSION 111 /* 110: block solve, resident sequences, link construction; 111: force filter */
+#define B200KS_VERSION 111 /* 110: block solve, resident sequences, link construction; 111: force filter, Naik epsilons */
 
 /* parity codes, include/macros.h:68-70 */
 #define B200KS_EVEN 2
@@ -230,7 +230,11 @@ int b200ks_hisq_links_fetch(b200ks_ctx *ctx, int which, void *host, int host_pre
  * increment MILC adds to its momenta.  Replaces fn_fermion_force_multi_hisq_wrapper_mx
  * (generic_ks/fermion_force_hisq_multi.c:1183-1476) = qudaHisqForce (:2169-2290), whose argument
  * conventions it keeps:
- *   coeff[2*j], coeff[2*j+1]  one-hop (2 res_j) and three-hop (naik * 2 res_j) weights of term j
+ *   coeff[2*j], coeff[2*j+1]  one-hop (2 res_j) and three-hop (naik * 2 res_j) weights of term j < nterms
+ *   num_naik_terms            several Naik epsilons (:2196-2222): the LAST num_naik_terms of the nterms fields were
+ *                             solved with a Naik epsilon; term i of those (field multi_x[nterms - num_naik_terms
+ *                             + i]) has its extra weights eps_k c1' 2 res and eps_k c3' 2 res (c1', c3' the
+ *                             one-link + Naik table) in coeff[2*(nterms+i)], coeff[2*(nterms+i)+1]; 0 = none
  *   multi_x[j]                su3_vector[V]: solution on the even sites, D solution on the odd sites
  *   level2_coeff, fat7_coeff  the six path coefficients of the two smearing levels
  *   wlink, vlink, ulink       W (unitarised), V (fat7) and U (thin, phases in): su3_matrix[4*V]
@@ -240,9 +244,8 @@ int b200ks_hisq_links_fetch(b200ks_ctx *ctx, int which, void *host, int host_pre
  *                             0 = the unregularised derivative
  *   momentum                  out: anti_hermitmat[4*V], 10 reals each (include/su3.h)
  * Computed as the reverse-mode derivative of the link construction (csrc/force.cuh); double on the
- * device whatever host_prec is.  Not implemented: several Naik epsilons (num_naik_terms > 0).
- * Single-GPU contexts. */
-int b200ks_hisq_force(b200ks_ctx *ctx, int nterms, const double *coeff, const void *const *multi_x,
+ * device whatever host_prec is.  Single-GPU contexts. */
+int b200ks_hisq_force(b200ks_ctx *ctx, int nterms, int num_naik_terms, const double *coeff, const void *const *multi_x,
                       const double *level2_coeff, const double *fat7_coeff, const void *wlink,
                       const void *vlink, const void *ulink, double eps, double force_filter, void *momentum,
                       int host_prec);

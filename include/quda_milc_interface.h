@@ -133,7 +133,8 @@ typedef struct {
 void qudaHisqParamsInit(QudaHisqParams_t hisq_params);
 /* momentum (anti_hermitmat[4*sites], precision reals) = dt * force of num_terms terms; coeff[t][0]
  * one-hop and coeff[t][1] three-hop weights; quark_field[t] su3_vector[sites] with both parities
- * filled.  num_naik_terms > 0 (several Naik epsilons) is not supported. */
+ * filled.  num_naik_terms > 0 (several Naik epsilons): the last num_naik_terms fields carry extra
+ * weights coeff[num_terms + i] (fermion_force_hisq_multi.c:2196-2222). */
 void qudaHisqForce(int precision, int num_terms, int num_naik_terms, double dt, double **coeff, void **quark_field,
                    const double level2_coeff[6], const double fat7_coeff[6], const void *const w_link,
                    const void *const v_link, const void *const u_link, void *const milc_momentum);

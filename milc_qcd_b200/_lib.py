@@ -71,7 +71,7 @@ SYMBOLS = [
     ("b200ks_multicg_rational", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_double),
                                           C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(InvertArgs),
                                           C.POINTER(InvertResult), C.c_int]),
-    ("b200ks_hisq_force", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.POINTER(C.c_double),
+    ("b200ks_hisq_force", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int]),
     ("b200ks_ks_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ("b200ks_unitarized_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

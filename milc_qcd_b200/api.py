@@ -181,21 +181,39 @@ class Context:
 
     HISQ_FORCE_FILTER = 5.0e-5   # ks_imp_rhmc's build value (ks_imp_rhmc/Make_template)
 
-    def hisq_force(self, U, V, W, multi_x, residues, eps, coeffs1=None, coeffs2=None, force_filter=HISQ_FORCE_FILTER):
+    HISQ_NAIK_TABLE = (1.0 / 8.0, -1.0 / 24.0)   # one-link and Naik coefficients of the reference's third path table
+
+    def hisq_force(self, U, V, W, multi_x, residues, eps, coeffs1=None, coeffs2=None, force_filter=HISQ_FORCE_FILTER,
+                   n_orders=None, eps_naik=None, coeffs3=None):
         """b200ks_hisq_force with MILC's weights (one-hop 2 res_j, three-hop naik * 2 res_j,
         generic_ks/fermion_force_hisq_multi.c:2189-2192): returns the momentum increment as
-        (V,4,10) anti_hermitmat arrays.  force_filter = 0: the unregularised derivative."""
+        (V,4,10) anti_hermitmat arrays.  force_filter = 0: the unregularised derivative.
+        Several Naik epsilons (:2196-2222): the terms come in len(n_orders) classes of n_orders[k] terms,
+        class k solved with the links of eps_naik[k] (eps_naik[0] = 0)."""
         c1 = self.HISQ_FAT7 if coeffs1 is None else coeffs1
         c2 = self.HISQ_ASQTAD_LIKE if coeffs2 is None else coeffs2
+        c3 = self.HISQ_NAIK_TABLE if coeffs3 is None else coeffs3
         n = len(multi_x)
-        cf = (C.c_double * (2 * n))()
+        extra = []
+        if n_orders is not None and len(n_orders) > 1:
+            assert sum(n_orders) == n and len(eps_naik) == len(n_orders)
+            j = n_orders[0]
+            for k in range(1, len(n_orders)):
+                for _ in range(n_orders[k]):
+                    extra.append((float(c3[0]) * eps_naik[k] * 2.0 * float(residues[j]),
+                                  float(c3[1]) * eps_naik[k] * 2.0 * float(residues[j])))
+                    j += 1
+        cf = (C.c_double * (2 * (n + len(extra))))()
         for j, r in enumerate(residues):
             cf[2 * j] = 2.0 * float(r)
             cf[2 * j + 1] = float(c2[1]) * 2.0 * float(r)
+        for i, (a, b) in enumerate(extra):
+            cf[2 * (n + i)] = a
+            cf[2 * (n + i) + 1] = b
         ptrs = (C.c_void_p * n)(*[_ptr(x).value for x in multi_x])
         mom = np.zeros((self.volume, 4, 10), dtype=U.dtype)
-        check(self.lib.b200ks_hisq_force(self.h, n, cf, ptrs, self._coeffs(c2), self._coeffs(c1), _ptr(W), _ptr(V), _ptr(U),
-                                         eps, float(force_filter), _ptr(mom), _host_prec(U)), "b200ks_hisq_force")
+        check(self.lib.b200ks_hisq_force(self.h, n, len(extra), cf, ptrs, self._coeffs(c2), self._coeffs(c1), _ptr(W), _ptr(V),
+                                         _ptr(U), eps, float(force_filter), _ptr(mom), _host_prec(U)), "b200ks_hisq_force")
         return mom
 
     def hisq_links_time(self, seed, reps, coeffs1=None, coeffs2=None):

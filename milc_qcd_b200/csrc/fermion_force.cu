@@ -68,13 +68,14 @@ int field_to_dev(b200ks_ctx *c, double2 *dst, size_t fs, const void *host, int h
 
 }  // namespace
 
-extern "C" int b200ks_hisq_force(b200ks_ctx *c, int nterms, const double *coeff, const void *const *multi_x,
+extern "C" int b200ks_hisq_force(b200ks_ctx *c, int nterms, int num_naik_terms, const double *coeff, const void *const *multi_x,
                                  const double *level2_coeff, const double *fat7_coeff, const void *wlink, const void *vlink,
                                  const void *ulink, double eps, double force_filter, void *momentum, int host_prec) {
   if (!c || nterms < 1 || !coeff || !multi_x || !level2_coeff || !fat7_coeff || !wlink || !vlink || !ulink || !momentum)
     return fail(B200KS_EINVAL, "b200ks_hisq_force: null argument");
   if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
   if (!(force_filter >= 0.0)) return fail(B200KS_EINVAL, "b200ks_hisq_force: negative force filter");
+  if (num_naik_terms < 0 || num_naik_terms > nterms) return fail(B200KS_EINVAL, "b200ks_hisq_force: num_naik_terms out of range");
   if (partitioned(c)) return fail(B200KS_ESTATE, "fermion force: single-GPU contexts only");
   CU(cudaSetDevice(device(c)));
   const Geom &g = geom(c);
@@ -110,6 +111,10 @@ extern "C" int b200ks_hisq_force(b200ks_ctx *c, int nterms, const double *coeff,
   DeviceExec x{c};
   x.run(n, force::ZeroSite{b.gfat, b.fs, 36});
   x.run(n, force::ZeroSite{b.glng, b.fs, 36});
+  if (num_naik_terms > 0) {   // the Naik-epsilon terms' outer products go straight to the W level (force_chain)
+    x.run(n, force::ZeroSite{b.gW, b.fs, 36});
+    x.run(n, force::ZeroSite{b.gU, b.fs, 36});
+  }
   // outer products, one term at a time: colour vectors stay in MILC's host order (6 reals per site)
   for (int j = 0; j < nterms; j++) {
     if (!multi_x[j]) return fail(B200KS_EINVAL, "b200ks_hisq_force: null vector");
@@ -123,9 +128,12 @@ extern "C" int b200ks_hisq_force(b200ks_ctx *c, int nterms, const double *coeff,
       count_launch(c);
     }
     x.run(n, force::OprodSite{b.g, b.gfat, b.glng, b.fs, (const double *)vec.p, coeff[2 * j], coeff[2 * j + 1]});
+    const int i = j - (nterms - num_naik_terms);   // the last num_naik_terms fields, weights coeff[nterms + i]
+    if (i >= 0)
+      x.run(n, force::OprodSite{b.g, b.gW, b.gU, b.fs, (const double *)vec.p, coeff[2 * (nterms + i)], coeff[2 * (nterms + i) + 1]});
     CU(cudaStreamSynchronize(stream(c)));   // vec.p is reused by the next term
   }
-  force::force_chain(x, b, fat7_coeff, level2_coeff, /*naik_in_oprod=*/true, force_filter);
+  force::force_chain(x, b, fat7_coeff, level2_coeff, /*naik_in_oprod=*/true, force_filter, num_naik_terms > 0);
   if (host_prec == 2) x.run(4 * n, force::MomSite<double>{b.U, b.gU, (double *)mom.p, eps, b.fs, n});
   else x.run(4 * n, force::MomSite<float>{b.U, b.gU, (float *)mom.p, eps, b.fs, n});
   CHK(check_launch("fermion force"));

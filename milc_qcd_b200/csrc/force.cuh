@@ -418,10 +418,20 @@ void smear_bwd(X &x, const ForceBufs &b, const double *coeffs, const double2 *li
 
 // gfat / glng hold the outer products on entry; on exit gU holds G_U.  naik_in_oprod: the three-hop
 // coefficients already carry the Naik coefficient (qudaHisqForce's convention), else coeffs2[1] is applied here.
+// Several Naik epsilons (fermion_force_hisq_multi.c:1285-1375): every term goes through the level-2 smearing,
+// and the terms solved with a Naik epsilon add  eps_k (c1' G_fat^(k) + Naik product backwards of c3' G_lng^(k))
+// straight to G_W (c1', c3': the reference's one-link + Naik table).  naik_terms: on entry gW holds the sum of
+// their one-hop outer products and gU the sum of their three-hop ones, weights eps_k c1' 2 res_j and
+// eps_k c3' 2 res_j included (the seam's coeff[num_terms + i]); otherwise both are cleared here.
 template <class X>
-void force_chain(X &x, const ForceBufs &b, const double *coeffs1, const double *coeffs2, bool naik_in_oprod, double filter) {
+void force_chain(X &x, const ForceBufs &b, const double *coeffs1, const double *coeffs2, bool naik_in_oprod, double filter,
+                 bool naik_terms = false) {
   const int n = b.nsites;
-  x.run(n, ZeroSite{b.gW, b.fs, 36});
+  if (naik_terms) {
+    x.run(n, NaikBwdSite{b.g, b.gU, b.W, b.gW, 1.0, b.fs});
+  } else {
+    x.run(n, ZeroSite{b.gW, b.fs, 36});
+  }
   x.run(n, ZeroSite{b.gU, b.fs, 36});
   smear_bwd(x, b, coeffs2, b.W, b.gfat, b.gW);
   x.run(n, NaikBwdSite{b.g, b.glng, b.W, b.gW, naik_in_oprod ? 1.0 : coeffs2[1], b.fs});

@@ -283,16 +283,16 @@ void qudaHisqForce(int precision, int num_terms, int num_naik_terms, double dt, 
                    const void *const v_link, const void *const u_link, void *const milc_momentum) {
   static const char where[] = "qudaHisqForce";
   ensure_ctx(where);
-  if (num_naik_terms != 0) {
-    printf("%s: several Naik epsilons are not supported by libb200ks\n", where);
+  if (num_naik_terms < 0 || num_naik_terms > num_terms) {
+    printf("%s: num_naik_terms = %d out of range\n", where, num_naik_terms);
     exit(1);
   }
-  std::vector<double> cf(2 * (size_t)num_terms);
-  for (int t = 0; t < num_terms; t++) {
+  std::vector<double> cf(2 * (size_t)(num_terms + num_naik_terms));
+  for (int t = 0; t < num_terms + num_naik_terms; t++) {
     cf[2 * t] = coeff[t][0];
     cf[2 * t + 1] = coeff[t][1];
   }
-  if (b200ks_hisq_force(S.ctx, num_terms, cf.data(), (const void *const *)quark_field, level2_coeff, fat7_coeff, w_link, v_link,
+  if (b200ks_hisq_force(S.ctx, num_terms, num_naik_terms, cf.data(), (const void *const *)quark_field, level2_coeff, fat7_coeff, w_link, v_link,
                         u_link, dt, S.force_filter, milc_momentum, precision) < 0)
     die(where);
 }

@@ -31,7 +31,8 @@
  * and with it the form in which the Lepage term is differentiated (see smear_bwd); with both
  * the restatement meets the reference to 1e-10 on links rough enough to trip the filter
  * (tests/test_oracle.py, golden ref_hisq_force_rough.npz).
- * Not restated: several Naik epsilons.
+ * Several Naik epsilons: ksf_hisq_force_naik, pinned live against the reference (tests/test_oracle.py) and on
+ * tests/golden/ref_hisq_force_naik.npz.
  */
 #include <math.h>
 #include <stdlib.h>
@@ -305,22 +306,10 @@ void ksf_unitarize_bwd(const double *V, const double *GW, double *GV, double fil
 double ksf_force_filter = 5.0e-5;
 void ksf_set_force_filter(double f) { ksf_force_filter = f; }
 
-/* multi_x: nterms fields of V colour vectors [6 doubles per site] (even sites X_j, odd sites D X_j);
-   mom out: anti_hermitmat[4*V] as 10 doubles {m01.re, m01.im, m02.re, m02.im, m12.re, m12.im, m00im, m11im, m22im, 0} */
-void ksf_hisq_force(const int *n, const double *coeffs1, const double *coeffs2, const double *links_, const double *multi_x,
-                    const double *residues, int nterms, double eps, double *mom) {
-  const long vol = (long)n[0] * n[1] * n[2] * n[3];
-  const mat *U = (const mat *)links_;
-  mat *V = (mat *)malloc(sizeof(mat) * 4 * vol), *W = (mat *)malloc(sizeof(mat) * 4 * vol);
-  mat *gfat = (mat *)calloc(4 * vol, sizeof(mat)), *glng = (mat *)calloc(4 * vol, sizeof(mat));
-  mat *gW = (mat *)calloc(4 * vol, sizeof(mat)), *gV = (mat *)malloc(sizeof(mat) * 4 * vol), *gU = (mat *)calloc(4 * vol, sizeof(mat));
-  int *nbp[4];
+/* outer products of nterms terms, added to gfat (1-hop) and glng (3-hop):  +-2 res_j Z_j(x) Z_j(x+mu)^+ */
+static void oprods(long vol, int *const *nbp, const double *multi_x, const double *residues, int nterms, mat *gfat, mat *glng) {
   int dir, j, a, b;
   long i;
-  for (dir = 0; dir < 4; dir++) nbp[dir] = f_build_nb(n, dir);
-  ksl_smear(n, coeffs1, links_, (double *)V, NULL);
-  ksl_unitarize((const double *)V, (double *)W, 4 * vol, 0, 0.0, 0.0);
-  /* 1. outer products */
   for (j = 0; j < nterms; j++) {
     const double *Z = multi_x + (size_t)j * vol * 6;
     for (i = 0; i < vol; i++) {
@@ -340,8 +329,44 @@ void ksf_hisq_force(const int *n, const double *coeffs1, const double *coeffs2, 
       }
     }
   }
+}
+
+/* multi_x: nterms fields of V colour vectors [6 doubles per site] (even sites X_j, odd sites D X_j);
+   mom out: anti_hermitmat[4*V] as 10 doubles {m01.re, m01.im, m02.re, m02.im, m12.re, m12.im, m00im, m11im, m22im, 0}.
+   Several Naik epsilons (fermion_force_hisq_multi.c:1285-1375; links: fermion_links_hisq_load_milc.c:573-636):
+   the terms come in n_naiks classes of n_orders[k] terms; class k was solved with
+       fat_k = fat_0 + eps_naik[k] * coeffs3[0] * W ,   lng_k = lng_0 + eps_naik[k] * coeffs3[1] * W W W
+   (eps_naik[0] = 0; coeffs3 = the one-link and Naik coefficients of the reference's third path table), so every
+   term goes through the level-2 smearing and the terms of class k >= 1 add
+       G_W += eps_naik[k] * ( coeffs3[0] * G_fat^(k) + Naik product backwards of coeffs3[1] * G_lng^(k) ). */
+void ksf_hisq_force_naik(const int *n, const double *coeffs1, const double *coeffs2, const double *coeffs3, const double *links_,
+                         const double *multi_x, const double *residues, int n_naiks, const int *n_orders,
+                         const double *eps_naik, double eps, double *mom) {
+  const long vol = (long)n[0] * n[1] * n[2] * n[3];
+  const mat *U = (const mat *)links_;
+  mat *V = (mat *)malloc(sizeof(mat) * 4 * vol), *W = (mat *)malloc(sizeof(mat) * 4 * vol);
+  mat *gfat = (mat *)calloc(4 * vol, sizeof(mat)), *glng = (mat *)calloc(4 * vol, sizeof(mat));
+  mat *gW = (mat *)calloc(4 * vol, sizeof(mat)), *gV = (mat *)malloc(sizeof(mat) * 4 * vol), *gU = (mat *)calloc(4 * vol, sizeof(mat));
+  int *nbp[4];
+  int dir, k, nterms = 0, shift;
+  long i;
+  for (dir = 0; dir < 4; dir++) nbp[dir] = f_build_nb(n, dir);
+  for (k = 0; k < n_naiks; k++) nterms += n_orders[k];
+  ksl_smear(n, coeffs1, links_, (double *)V, NULL);
+  ksl_unitarize((const double *)V, (double *)W, 4 * vol, 0, 0.0, 0.0);
+  /* 1. outer products */
+  oprods(vol, nbp, multi_x, residues, nterms, gfat, glng);
   /* 2.-4. the chain backwards */
   smear_bwd(n, coeffs2, W, gfat, glng, gW);
+  shift = n_orders[0];
+  for (k = 1; k < n_naiks; k++) { /* the one-link + Naik table of class k, weighted with its epsilon */
+    const double c3[6] = {eps_naik[k] * coeffs3[0], eps_naik[k] * coeffs3[1], 0, 0, 0, 0};
+    memset(gfat, 0, sizeof(mat) * 4 * vol);
+    memset(glng, 0, sizeof(mat) * 4 * vol);
+    oprods(vol, nbp, multi_x + (size_t)shift * vol * 6, residues + shift, n_orders[k], gfat, glng);
+    smear_bwd(n, c3, W, gfat, glng, gW);
+    shift += n_orders[k];
+  }
   for (i = 0; i < 4 * vol; i++) unitarize_bwd(&V[i], &gW[i], &gV[i], ksf_force_filter);
   smear_bwd(n, coeffs1, U, gV, NULL, gU);
   /* 5. A = -eps TA(U G_U^+) */
@@ -365,4 +390,10 @@ void ksf_hisq_force(const int *n, const double *coeffs1, const double *coeffs2, 
   }
   for (dir = 0; dir < 4; dir++) free(nbp[dir]);
   free(V); free(W); free(gfat); free(glng); free(gW); free(gV); free(gU);
+}
+
+void ksf_hisq_force(const int *n, const double *coeffs1, const double *coeffs2, const double *links_, const double *multi_x,
+                    const double *residues, int nterms, double eps, double *mom) {
+  const double zero = 0.0, c3[2] = {0.0, 0.0};
+  ksf_hisq_force_naik(n, coeffs1, coeffs2, c3, links_, multi_x, residues, 1, &nterms, &zero, eps, mom);
 }

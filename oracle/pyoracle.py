@@ -96,6 +96,8 @@ class LinksOracle:
         L.ksl_unitarize.argtypes = [_dp, _dp, C.c_long, C.c_int, C.c_double, C.c_double]
         L.ksf_hisq_force.restype = None
         L.ksf_hisq_force.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, _dp]
+        L.ksf_hisq_force_naik.restype = None
+        L.ksf_hisq_force_naik.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, _ip, _dp, C.c_double, _dp]
         L.ksf_set_force_filter.restype = None
         L.ksf_set_force_filter.argtypes = [C.c_double]
         L.ksf_unitarize_bwd.restype = None
@@ -142,6 +144,25 @@ class LinksOracle:
         c2 = np.ascontiguousarray(self.ASQTAD_LIKE if coeffs2 is None else coeffs2, np.float64)
         mom = np.zeros((links.shape[0], 4, 10))
         self.lib.ksf_hisq_force(self._dims(dims), c1, c2, links, xs, res, xs.shape[0], eps, mom)
+        return mom
+
+    NAIK_TABLE = (1.0 / 8.0, -1.0 / 24.0)   # one-link and Naik coefficients of the reference's third path table
+
+    def hisq_force_naik(self, dims, links, multi_x, residues, n_orders, eps_naik, eps, coeffs1=None, coeffs2=None,
+                        coeffs3=None, force_filter=FORCE_FILTER):
+        """ksf_hisq_force_naik: several Naik epsilons; the terms come in len(n_orders) classes, class k solved with
+        the links of eps_naik[k] (eps_naik[0] = 0)."""
+        self.lib.ksf_set_force_filter(force_filter)
+        links = np.ascontiguousarray(links, np.float64)
+        xs = np.ascontiguousarray(multi_x, np.float64)
+        assert xs.shape[0] == sum(n_orders) and len(n_orders) == len(eps_naik)
+        c1 = np.ascontiguousarray(self.FAT7 if coeffs1 is None else coeffs1, np.float64)
+        c2 = np.ascontiguousarray(self.ASQTAD_LIKE if coeffs2 is None else coeffs2, np.float64)
+        c3 = np.ascontiguousarray(self.NAIK_TABLE if coeffs3 is None else coeffs3, np.float64)
+        mom = np.zeros((links.shape[0], 4, 10))
+        self.lib.ksf_hisq_force_naik(self._dims(dims), c1, c2, c3, links, xs, np.ascontiguousarray(residues, np.float64),
+                                     len(n_orders), np.ascontiguousarray(n_orders, np.int32),
+                                     np.ascontiguousarray(eps_naik, np.float64), eps, mom)
         return mom
 
     def hisq_links(self, dims, links, coeffs1=None, coeffs2=None, allow_svd=True, svd_rel=1e-8, svd_abs=1e-8):
@@ -196,6 +217,7 @@ class MilcRef:
         L.milcref_unitarize.argtypes = [rp, ro, C.c_long]
         L.milcref_mat_invert_uml.argtypes = [rp, ro, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, _dp]
         L.milcref_hisq_force.argtypes = [rp, rp, rp, C.c_int, C.c_double, ro]
+        L.milcref_hisq_force_naik.argtypes = [rp, rp, rp, C.c_int, _ip, _dp, C.c_double, ro, C.c_void_p]
         self.dims = tuple(int(d) for d in dims)
         if L.milcref_init(*self.dims) != 0:
             raise RuntimeError("MilcRef: process already initialised with another geometry")
@@ -278,6 +300,21 @@ class MilcRef:
         mom = np.zeros((self.vol, 4, 10), dtype=self.dtype)
         n = self.lib.milcref_hisq_force(links, xs, res, xs.shape[0], eps, mom)
         return mom, n
+
+    def hisq_force_naik(self, links, multi_x, residues, n_orders, eps_naik, eps, want_links=False):
+        """The same with several Naik epsilons (fermion_force_hisq_multi.c:1285-1375): terms in classes of
+        n_orders[k], class k belonging to eps_naik[k] (eps_naik[0] = 0).  want_links: also the (fat, long) links
+        of every class, (n_naiks, 2, V, 4, 3, 3, 2)."""
+        links = np.ascontiguousarray(links, self.dtype)
+        xs = np.ascontiguousarray(multi_x, self.dtype)
+        res = np.ascontiguousarray(residues, self.dtype)
+        assert xs.shape[0] == sum(n_orders) and len(n_orders) == len(eps_naik)
+        mom = np.zeros((self.vol, 4, 10), dtype=self.dtype)
+        fl = np.zeros((len(n_orders), 2) + links.shape, dtype=self.dtype) if want_links else None
+        n = self.lib.milcref_hisq_force_naik(links, xs, res, len(n_orders), np.ascontiguousarray(n_orders, np.int32),
+                                             np.ascontiguousarray(eps_naik, np.float64), eps, mom,
+                                             fl.ctypes.data if want_links else None)
+        return (mom, n, fl) if want_links else (mom, n)
 
     def time_dslash(self, src, parity, ncalls):
         src = np.ascontiguousarray(src, self.dtype)

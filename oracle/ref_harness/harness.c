@@ -269,32 +269,60 @@ int milcref_mat_invert_uml(const Real *src, Real *dst, int nsrc, double m, int m
  * mom: anti_hermitmat[4*V] as 10 Reals each {m01.re,m01.im,m02.re,m02.im,m12.re,m12.im,m00im,m11im,
  * m22im,space} (include/su3.h), zero on entry here, the update on exit.
  * Returns the number of links whose force took the SVD / filter branches (sum). */
+int milcref_hisq_force_naik(const Real *links, const Real *multi_x, const Real *residues, int n_naiks,
+                            const int *n_orders, const double *eps_naik_in, double eps, Real *mom, Real *fat_lng);
+
 int milcref_hisq_force(const Real *links, const Real *multi_x, const Real *residues, int nterms, double eps,
                        Real *mom) {
   double eps_naik[1] = {0.0};
+  return milcref_hisq_force_naik(links, multi_x, residues, 1, &nterms, eps_naik, eps, mom, NULL);
+}
+
+/* The same with several Naik epsilons (the charm quark's mass-dependent correction): the terms come in
+ * n_naiks classes of n_orders[k] terms, class k solved with the links of eps_naik[k] (eps_naik[0] = 0);
+ * fermion_force_hisq_multi.c:1285-1375.  fat_lng, if not NULL: [n_naiks][2][4*V] su3_matrix, the fat and
+ * long links of every class (load_hisq_fn_links, fermion_links_hisq_load_milc.c:573-636). */
+int milcref_hisq_force_naik(const Real *links, const Real *multi_x, const Real *residues, int n_naiks,
+                            const int *n_orders, const double *eps_naik_in, double eps, Real *mom, Real *fat_lng) {
+  double eps_naik[MAX_NAIK];
   fermion_links_t *fl;
-  su3_vector **xx = (su3_vector **)malloc(nterms * sizeof(*xx));
-  Real *res = (Real *)malloc(nterms * sizeof(Real));
+  su3_vector **xx;
+  Real *res;
   size_t i;
-  int k, dir;
-  if (!h_ready) return -1;
+  int k, dir, nterms = 0;
+  if (!h_ready || n_naiks < 1 || n_naiks > MAX_NAIK) return -1;
+  for (k = 0; k < n_naiks; k++) {
+    eps_naik[k] = eps_naik_in[k];
+    n_orders_naik[k] = n_orders[k];
+    nterms += n_orders[k];
+  }
+  xx = (su3_vector **)malloc(nterms * sizeof(*xx));
+  res = (Real *)malloc(nterms * sizeof(Real));
   for (k = 0; k < nterms; k++) {
     xx[k] = (su3_vector *)multi_x + (size_t)k * sites_on_node;
     res[k] = residues[k];
   }
   n_order_naik_total = nterms;
-  n_orders_naik[0] = nterms;
   hisq_svd_counter = 0;
   hisq_force_filter_counter = 0;
   for (i = 0; i < sites_on_node; i++) {
     memcpy(lattice[i].link, (const su3_matrix *)links + 4 * i, 4 * sizeof(su3_matrix));
     memset(lattice[i].mom, 0, 4 * sizeof(anti_hermitmat));
   }
-  fl = create_fermion_links_hisq(MILC_PRECISION, 1, eps_naik, phases_in, (su3_matrix *)links);
+  fl = create_fermion_links_hisq(MILC_PRECISION, n_naiks, eps_naik, phases_in, (su3_matrix *)links);
+  if (fat_lng) {
+    const size_t bytes = sizeof(su3_matrix) * 4 * sites_on_node;
+    for (k = 0; k < n_naiks; k++) {
+      fn_links_t *f = get_fm_links(fl)[k];
+      memcpy((char *)fat_lng + (2 * k) * bytes, get_fatlinks(f), bytes);
+      memcpy((char *)fat_lng + (2 * k + 1) * bytes, get_lnglinks(f), bytes);
+    }
+  }
   eo_fermion_force_multi((Real)eps, res, xx, nterms, MILC_PRECISION, fl);
   for (i = 0; i < sites_on_node; i++)
     for (dir = 0; dir < 4; dir++) memcpy(mom + 10 * (4 * i + dir), &lattice[i].mom[dir], sizeof(anti_hermitmat));
   destroy_fermion_links_hisq(fl);
   free(xx); free(res);
+  n_orders_naik[0] = 0;
   return hisq_svd_counter + hisq_force_filter_counter;
 }

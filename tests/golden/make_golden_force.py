@@ -8,7 +8,8 @@ sites with their odd sites filled by D X_j through the HISQ links built from tho
 Output: the momentum update of the reference's eo_fermion_force_multi
 (generic_ks/fermion_force_hisq_multi.c:170-216, wrapper_mx path, ks_imp_rhmc's build flags) as
 anti_hermitmat arrays.  A second file, ref_hisq_force_rough.npz, holds the same for links rough enough
-to trip the reference's eigenvalue filter and SVD branches.
+to trip the reference's eigenvalue filter and SVD branches; a third, ref_hisq_force_naik.npz, five terms in
+three Naik-epsilon classes.
 """
 import os
 import sys
@@ -52,6 +53,26 @@ def main():
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_hisq_force_rough.npz")
     np.savez_compressed(path, dims=np.array(dims), U=U, multi_x=X, residues=residues, eps=1.0, mom=mom, nsvd=n)
     print("wrote", path, os.path.getsize(path), "bytes; |mom|max", np.abs(mom).max(), "filter+svd links", n)
+
+    # several Naik epsilons (the charm quark's mass-dependent correction): three classes of 2, 1 and 2 terms;
+    # class k was solved with fat_k = fat_0 + eps_k/8 W, lng_k = (1 + eps_k) lng_0
+    U = F.make_thin_links(dims, seed=11, spread=0.5)
+    links = lo.hisq_links(dims, U)
+    n_orders, eps_naik, cls = [2, 1, 2], [0.0, -0.0358, -0.2297], [0, 0, 1, 2, 2]
+    X = rng.standard_normal((5, V, 3, 2))
+    X[:, h:] = 0
+    residues = np.array([0.7, -0.3, 0.45, 0.2, -0.6])
+    for j in range(5):
+        e = eps_naik[cls[j]]
+        X[j, h:] = o.dslash(dims, links["fat"] + e * lo.NAIK_TABLE[0] * links["W"], (1 + e) * links["lng"], X[j], ODD)[h:]
+    mom, n, fl = ref.hisq_force_naik(U, X, residues, n_orders, eps_naik, 1.0, want_links=True)
+    for k, e in enumerate(eps_naik):   # the reference's links of every class are what the comment above says
+        assert np.abs(fl[k, 0] - (links["fat"] + e * lo.NAIK_TABLE[0] * links["W"])).max() < 1e-12
+        assert np.abs(fl[k, 1] - (1 + e) * links["lng"]).max() < 1e-12
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_hisq_force_naik.npz")
+    np.savez_compressed(path, dims=np.array(dims), U=U, multi_x=X, residues=residues, eps=1.0, mom=mom, nsvd=n,
+                        n_orders=np.array(n_orders), eps_naik=np.array(eps_naik))
+    print("wrote", path, os.path.getsize(path), "bytes; |mom|max", np.abs(mom).max())
 
 
 if __name__ == "__main__":

@@ -27,7 +27,7 @@ static void to_planes(double2 *dst, const double *src, size_t fs, int nsites) {
 
 extern "C" void force_host(const int *dims, const double *coeffs1, const double *coeffs2, const double *U, const double *V,
                            const double *W, const double *multi_x, const double *c1, const double *c3, int nterms,
-                           double eps, int naik_in_oprod, double filter, double *mom) {
+                           int n_naik_terms, double eps, int naik_in_oprod, double filter, double *mom) {
   ForceBufs b;
   for (int d = 0; d < 4; d++) b.g.L[d] = dims[d];
   const int n = dims[0] * dims[1] * dims[2] * dims[3];
@@ -52,6 +52,9 @@ extern "C" void force_host(const int *dims, const double *coeffs1, const double 
   to_planes(b.W, W, b.fs, n);
   HostExec x;
   for (int j = 0; j < nterms; j++) x.run(n, OprodSite{b.g, b.gfat, b.glng, b.fs, multi_x + (size_t)j * n * 6, c1[j], c3[j]});
-  force_chain(x, b, coeffs1, coeffs2, naik_in_oprod != 0, filter);
+  // the terms solved with a Naik epsilon: the last n_naik_terms fields, weights c1[nterms + i], c3[nterms + i]
+  for (int i = 0; i < n_naik_terms; i++)
+    x.run(n, OprodSite{b.g, b.gW, b.gU, b.fs, multi_x + (size_t)(nterms - n_naik_terms + i) * n * 6, c1[nterms + i], c3[nterms + i]});
+  force_chain(x, b, coeffs1, coeffs2, naik_in_oprod != 0, filter, n_naik_terms > 0);
   x.run(4 * n, MomSite<double>{b.U, b.gU, mom, eps, b.fs, n});
 }

@@ -28,16 +28,16 @@ def host_force():
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-x", "cu", "--shared", "-Xcompiler", "-fPIC", "-o", SO, src])
     lib = C.CDLL(SO)
     lib.force_host.restype = None
-    lib.force_host.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_double, _dp]
+    lib.force_host.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, _dp]
     return lib
 
 
-def _run(lib, dims, U, V, W, X, c1, c3, eps, naik_in_oprod, coeffs1, coeffs2, force_filter=5.0e-5):
+def _run(lib, dims, U, V, W, X, c1, c3, eps, naik_in_oprod, coeffs1, coeffs2, force_filter=5.0e-5, n_naik_terms=0):
     mom = np.zeros((U.shape[0], 4, 10))
     lib.force_host(np.ascontiguousarray(dims, np.int32), np.ascontiguousarray(coeffs1, np.float64),
                    np.ascontiguousarray(coeffs2, np.float64), np.ascontiguousarray(U), np.ascontiguousarray(V),
                    np.ascontiguousarray(W), np.ascontiguousarray(X), np.ascontiguousarray(c1, np.float64),
-                   np.ascontiguousarray(c3, np.float64), X.shape[0], eps, int(naik_in_oprod), force_filter, mom)
+                   np.ascontiguousarray(c3, np.float64), X.shape[0], n_naik_terms, eps, int(naik_in_oprod), force_filter, mom)
     return mom
 
 
@@ -103,3 +103,39 @@ def test_force_filter_matches_reference_on_rough_links(host_force):
     assert np.abs(raw - g["mom"]).max() > 0.1 * scale
     want = lo.hisq_force(dims, U, X, res, float(g["eps"]), force_filter=0.0)
     assert np.abs(raw - want).max() <= 1e-10 * np.abs(want).max()
+
+
+def _naik_weights(res, n_orders, eps_naik, c3):
+    """The seam's coeff[num_terms + i] (fermion_force_hisq_multi.c:2205-2213): one- and three-hop weights of
+    the terms solved with a Naik epsilon."""
+    one, three, j = [], [], n_orders[0]
+    for k in range(1, len(n_orders)):
+        for _ in range(n_orders[k]):
+            one.append(c3[0] * eps_naik[k] * 2 * res[j])
+            three.append(c3[1] * eps_naik[k] * 2 * res[j])
+            j += 1
+    return np.array(one), np.array(three)
+
+
+def test_force_with_naik_epsilons_matches_reference_golden(host_force):
+    """Five terms in three Naik-epsilon classes (tests/golden/ref_hisq_force_naik.npz, from the reference's
+    eo_fermion_force_multi with n_naiks = 3)."""
+    from oracle.pyoracle import LinksOracle
+    lo = LinksOracle()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_hisq_force_naik.npz"))
+    dims = tuple(int(d) for d in g["dims"])
+    U, X, res = g["U"], g["multi_x"], g["residues"]
+    n_orders, eps_naik = [int(v) for v in g["n_orders"]], [float(v) for v in g["eps_naik"]]
+    L = lo.hisq_links(dims, U)
+    naik = lo.ASQTAD_LIKE[1]
+    one, three = _naik_weights(res, n_orders, eps_naik, lo.NAIK_TABLE)
+    c1 = np.concatenate([2 * res, one])
+    c3 = np.concatenate([naik * 2 * res, three])
+    mom = _run(host_force, dims, U, L["V"], L["W"], X, c1, c3, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE,
+               n_naik_terms=len(one))
+    scale = np.abs(g["mom"]).max()
+    assert np.abs(mom - g["mom"]).max() <= 1e-11 * scale
+    assert np.abs(mom - lo.hisq_force_naik(dims, U, X, res, n_orders, eps_naik, float(g["eps"]))).max() <= 1e-11 * scale
+    # the epsilons matter on this input
+    plain = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE)
+    assert np.abs(plain - g["mom"]).max() > 1e-3 * scale

@@ -82,3 +82,23 @@ def test_force_filter_matches_reference_on_rough_links(api):
     want = lo.hisq_force(dims, U, X, res, eps, force_filter=0.0)
     assert np.abs(raw - want).max() <= 1e-6 * np.abs(want).max()    # 1 / g^(3/2) amplification at g = 5e-6
     ctx.close()
+
+
+def test_force_with_naik_epsilons_matches_reference_golden(api):
+    """Several Naik epsilons (qudaHisqForce num_naik_terms > 0): five terms in three classes,
+    tests/golden/ref_hisq_force_naik.npz from the reference's eo_fermion_force_multi with n_naiks = 3."""
+    from oracle.pyoracle import LinksOracle
+    lo = LinksOracle()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force_naik.npz"))
+    dims = tuple(int(d) for d in g["dims"])
+    U, X, res, eps = g["U"], g["multi_x"], g["residues"], float(g["eps"])
+    n_orders, eps_naik = [int(v) for v in g["n_orders"]], [float(v) for v in g["eps_naik"]]
+    scale = np.abs(g["mom"]).max()
+    ctx = api.Context(dims)
+    L = ctx.hisq_links(U)
+    mom = ctx.hisq_force(U, L["V"], L["W"], list(X), res, eps, n_orders=n_orders, eps_naik=eps_naik)
+    assert np.abs(mom - g["mom"]).max() <= 1e-10 * scale
+    assert np.abs(mom - lo.hisq_force_naik(dims, U, X, res, n_orders, eps_naik, eps)).max() <= 1e-10 * scale
+    plain = ctx.hisq_force(U, L["V"], L["W"], list(X), res, eps)
+    assert np.abs(plain - g["mom"]).max() > 1e-3 * scale
+    ctx.close()

@@ -351,6 +351,22 @@ def test_force_oracle_matches_reference_golden(links_oracle, name, tol):
         assert np.abs(raw - g["mom"]).max() > 0.1 * scale
 
 
+def test_force_oracle_with_naik_epsilons_matches_reference_golden(links_oracle):
+    """Several Naik epsilons (fermion_force_hisq_multi.c:1285-1375): five terms in three classes,
+    tests/golden/ref_hisq_force_naik.npz from the reference's eo_fermion_force_multi with n_naiks = 3."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force_naik.npz"))
+    dims = tuple(int(d) for d in g["dims"])
+    scale = np.abs(g["mom"]).max()
+    n_orders, eps_naik = [int(v) for v in g["n_orders"]], [float(v) for v in g["eps_naik"]]
+    mom = links_oracle.hisq_force_naik(dims, g["U"], g["multi_x"], g["residues"], n_orders, eps_naik, float(g["eps"]))
+    assert np.abs(mom - g["mom"]).max() <= 1e-11 * scale
+    plain = links_oracle.hisq_force(dims, g["U"], g["multi_x"], g["residues"], float(g["eps"]))
+    assert np.abs(plain - g["mom"]).max() > 1e-3 * scale
+    # one class is the plain force
+    one = links_oracle.hisq_force_naik(dims, g["U"], g["multi_x"], g["residues"], [5], [0.0], float(g["eps"]))
+    assert np.array_equal(one, plain)
+
+
 def test_force_filter_is_the_derivative_of_the_shifted_projection(links_oracle):
     """What HISQ_FORCE_FILTER does to one link (generic_ks/su3_mat_op.c:1680-1734): when the smallest eigenvalue
     of Q = V^+ V is below the filter, the reverse step is the exact derivative of V (Q + filter)^-1/2, by
@@ -395,8 +411,13 @@ g = np.load(%r)                                                              # f
 mom, n = ref.hisq_force(g['U'], g['multi_x'], g['residues'], float(g['eps']))
 assert n == int(g['nsvd']) and n > 0
 assert np.abs(mom - g['mom']).max() <= 1e-12 * np.abs(g['mom']).max()
+g = np.load(%r)                                                              # three Naik-epsilon classes
+mom, n = ref.hisq_force_naik(g['U'], g['multi_x'], g['residues'], [int(v) for v in g['n_orders']],
+                             [float(v) for v in g['eps_naik']], float(g['eps']))
+assert np.abs(mom - g['mom']).max() <= 1e-12 * np.abs(g['mom']).max()
 print('LIVE-OK')
 """ % (ROOT, os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force.npz"),
-       os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force_rough.npz"))
+       os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force_rough.npz"),
+       os.path.join(os.path.dirname(__file__), "golden", "ref_hisq_force_naik.npz"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert "LIVE-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
