@@ -384,3 +384,52 @@ done_trivial:
   free(beta_i); free(beta_im1); free(alpha); free(ttt); free(cg_p); free(res);
   return iteration;
 }
+
+/* ---- low-mode deflation of a trial solution -------------------------
+ * deflate() + project_out(), generic_ks/mat_invert.c:131-183: on the sites of `parity`
+ *     dst <- dst - sum_j v_j <v_j|dst>            (one vector after the other, j = nvecs-1 .. 0)
+ *     dst <- dst + sum_j v_j <v_j|src> / (eigval_j + 4 m^2)
+ * eigvec: nvecs fields of V colour vectors (both parities filled, orthonormal on each parity),
+ * eigval: the eigenvalues of -D_eo D_oe they belong to.  Gives mat_invert_uml_field / _cg_field
+ * (:186-257,328-402) the exact solution in the span of the vectors as the CG's starting point. */
+void kso_deflate(const int *n, double *dst, const double *src, double mass, int nvecs, const double *eigvec,
+                 const double *eigval, int parity) {
+  const long vol = (long)n[0] * n[1] * n[2] * n[3];
+  long lo, hi, i;
+  int j, c;
+  parity_range(vol, parity, &lo, &hi);
+  for (j = nvecs - 1; j >= 0; j--) {
+    const double *v = eigvec + (size_t)j * vol * 6;
+    double re = 0, im = 0;
+    for (i = lo; i < hi; i++)
+      for (c = 0; c < 3; c++) { /* conj(v) * dst */
+        const double vr = v[6 * i + 2 * c], vi = v[6 * i + 2 * c + 1], dr = dst[6 * i + 2 * c], di = dst[6 * i + 2 * c + 1];
+        re += vr * dr + vi * di;
+        im += vr * di - vi * dr;
+      }
+    for (i = lo; i < hi; i++)
+      for (c = 0; c < 3; c++) {
+        const double vr = v[6 * i + 2 * c], vi = v[6 * i + 2 * c + 1];
+        dst[6 * i + 2 * c] -= re * vr - im * vi;
+        dst[6 * i + 2 * c + 1] -= re * vi + im * vr;
+      }
+  }
+  for (j = 0; j < nvecs; j++) {
+    const double *v = eigvec + (size_t)j * vol * 6;
+    const double den = eigval[j] + 4.0 * mass * mass;
+    double re = 0, im = 0;
+    for (i = lo; i < hi; i++)
+      for (c = 0; c < 3; c++) {
+        const double vr = v[6 * i + 2 * c], vi = v[6 * i + 2 * c + 1], sr = src[6 * i + 2 * c], si = src[6 * i + 2 * c + 1];
+        re += vr * sr + vi * si;
+        im += vr * si - vi * sr;
+      }
+    re /= den; im /= den;
+    for (i = lo; i < hi; i++)
+      for (c = 0; c < 3; c++) {
+        const double vr = v[6 * i + 2 * c], vi = v[6 * i + 2 * c + 1];
+        dst[6 * i + 2 * c] += re * vr - im * vi;
+        dst[6 * i + 2 * c + 1] += re * vi + im * vr;
+      }
+  }
+}

@@ -47,6 +47,8 @@ class Oracle:
         L.kso_congrad.argtypes = [_ip, _dp, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int,
                                   C.c_double, C.c_double, C.c_int, _dp]
         L.kso_multicg.restype = C.c_int
+        L.kso_deflate.restype = None
+        L.kso_deflate.argtypes = [_ip, _dp, _dp, C.c_double, C.c_int, _dp, _dp, C.c_int]
         L.kso_multicg.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_double, C.c_double, _dp]
 
@@ -69,6 +71,14 @@ class Oracle:
         it = self.lib.kso_congrad(self._dims(dims), fat, lng, src, dest, mass, parity, niter,
                                   nrestart, resid, relresid, int(fewsums), out)
         return it, _qic(out)
+
+    def deflate(self, dims, dst, src, mass, eigvec, eigval, parity):
+        """kso_deflate (deflate() + project_out(), generic_ks/mat_invert.c:131-183): dst updated in place on
+        the sites of `parity`; eigvec (nvecs, V, 3, 2) with both parities filled, eigval of -D_eo D_oe."""
+        ev = np.ascontiguousarray(eigvec, np.float64)
+        self.lib.kso_deflate(self._dims(dims), dst, np.ascontiguousarray(src, np.float64), mass, ev.shape[0], ev,
+                             np.ascontiguousarray(eigval, np.float64), parity)
+        return dst
 
     def multicg(self, dims, fat, lng, src, offsets, parity, niter, nrestart, resid, relresid=0.0):
         offsets = np.ascontiguousarray(offsets, dtype=np.float64)
@@ -217,6 +227,7 @@ class MilcRef:
         L.milcref_unitarize.argtypes = [rp, ro, C.c_long]
         L.milcref_mat_invert_uml.argtypes = [rp, ro, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, _dp]
         L.milcref_hisq_force.argtypes = [rp, rp, rp, C.c_int, C.c_double, ro]
+        L.milcref_mat_invert_uml_deflated.argtypes = [rp, ro, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, rp, _dp, _dp]
         L.milcref_hisq_force_naik.argtypes = [rp, rp, rp, C.c_int, _ip, _dp, C.c_double, ro, C.c_void_p]
         self.dims = tuple(int(d) for d in dims)
         if L.milcref_init(*self.dims) != 0:
@@ -288,6 +299,14 @@ class MilcRef:
         srcs = np.ascontiguousarray(srcs, self.dtype)
         out = np.zeros(7)
         it = self.lib.milcref_mat_invert_uml(srcs, dsts, srcs.shape[0], mass, niter, nrestart, resid, out)
+        return it, _qic(out)
+
+    def mat_invert_uml_deflated(self, src, dst, mass, niter, nrestart, resid, eigvec, eigval):
+        """mat_invert_uml_field with qic->deflate = 1 and the given low modes (mat_invert.c:131-183,328-402)."""
+        ev = np.ascontiguousarray(eigvec, self.dtype)
+        out = np.zeros(7)
+        it = self.lib.milcref_mat_invert_uml_deflated(np.ascontiguousarray(src, self.dtype), dst, mass, niter, nrestart, resid,
+                                                      ev.shape[0], ev, np.ascontiguousarray(eigval, np.float64), out)
         return it, _qic(out)
 
     def hisq_force(self, links, multi_x, residues, eps):

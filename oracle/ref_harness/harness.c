@@ -259,6 +259,32 @@ int milcref_mat_invert_uml(const Real *src, Real *dst, int nsrc, double m, int m
   return it;
 }
 
+/* The same with low-mode deflation: eigvec = nvecs contiguous fields of
+ * sites_on_node su3_vectors (both parities), eigval their eigenvalues of -D_eo D_oe; qic.deflate = 1 makes
+ * mat_invert_uml_field start each CG from deflate()'s trial solution (mat_invert.c:131-183,341-383). */
+int milcref_mat_invert_uml_deflated(const Real *src, Real *dst, double m, int max, int nrest, double resid,
+                                    int nvecs, const Real *eigvec, const double *eigval, double *out) {
+  quark_invert_control qic;
+  int k, it;
+  memset(&qic, 0, sizeof(qic));
+  qic.prec = MILC_PRECISION; qic.min = 0; qic.max = max; qic.nrestart = nrest;
+  qic.parity = EVENANDODD; qic.start_flag = 1; qic.nsrc = 1;
+  qic.resid = resid; qic.relresid = 0; qic.deflate = 1;
+  eigVec = (su3_vector **)malloc(nvecs * sizeof(su3_vector *));
+  eigVal = (double *)malloc(nvecs * sizeof(double));
+  for (k = 0; k < nvecs; k++) {
+    eigVec[k] = (su3_vector *)eigvec + (size_t)k * sites_on_node;
+    eigVal[k] = eigval[k];
+  }
+  param.eigen_param.Nvecs = nvecs;
+  it = mat_invert_uml_field((su3_vector *)src, (su3_vector *)dst, &qic, (Real)m, h_fn);
+  h_unpack(&qic, out);
+  param.eigen_param.Nvecs = 0;
+  free(eigVec); free(eigVal);
+  eigVec = NULL; eigVal = NULL;
+  return it;
+}
+
 /* ---- HISQ fermion force ---------------------------------------------
  * eo_fermion_force_multi, generic_ks/fermion_force_hisq_multi.c:170-216 (the wrapper_mx path of the
  * RHMC build: outer products of the nterms solution vectors, level-2 smearing force, derivative of

@@ -273,6 +273,82 @@ def test_uml_sequence_oracle_matches_compiled_reference_live():
     assert "LIVE-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+# ---- low-mode deflation (row f4) -----------------------------------------------------------------
+def uml_deflated_from_primitives(o, dims, fat, lng, src, mass, niter, nrestart, resid, ev, lam):
+    """mat_invert_uml_field with qic->deflate = 1 (generic_ks/mat_invert.c:328-402) from oracle primitives."""
+    from oracle.pyoracle import EVEN, ODD, EVENANDODD
+    h = src.shape[0] // 2
+    dst = np.zeros_like(src)
+    tmp = -o.dslash(dims, fat, lng, src, EVENANDODD) + 2 * mass * src
+    o.deflate(dims, dst, tmp, mass, ev, lam, EVEN)
+    it_e, _ = o.congrad(dims, fat, lng, tmp, dst, mass, EVEN, niter, nrestart, resid)
+    ttt = o.dslash(dims, fat, lng, dst, ODD)
+    dst[h:] = (src[h:] - ttt[h:]) / (2 * mass)
+    o.deflate(dims, dst, tmp, mass, ev, lam, ODD)
+    it_o, _ = o.congrad(dims, fat, lng, tmp, dst, mass, ODD, niter, nrestart, resid)
+    return dst, it_e + it_o
+
+
+def _deflate_case():
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_deflate import low_modes
+    from milc_qcd_b200 import fields as F
+    from oracle.pyoracle import Oracle, EVENANDODD
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_uml_deflated.npz"))
+    dims = tuple(int(d) for d in g["dims"])
+    fat, lng = F.make_links(dims, seed=int(g["link_seed"]))
+    o = Oracle()
+    lam, ev = low_modes(o, dims, fat, lng)
+    src = F.make_source(dims, seed=int(g["src_seed"]), parity=EVENANDODD)
+    return g, dims, fat, lng, o, lam, ev, src
+
+
+def test_deflation_oracle_matches_reference_golden():
+    """kso_deflate inside the UML sequence against the committed output of the reference's
+    mat_invert_uml_field with qic->deflate = 1 (tests/golden/make_golden_deflate.py): same iteration counts
+    (the CG trajectory depends on the trial solution) and solutions, for 8, 48 and all 384 low modes."""
+    g, dims, fat, lng, o, lam, ev, src = _deflate_case()
+    assert np.abs(lam[:48] - g["eigval"]).max() <= 1e-12 * lam[47]
+    args = (float(g["mass"]), int(g["niter"]), int(g["nrestart"]), float(g["resid"]))
+    for k, it_ref, want in zip(g["nvecs"], g["iters"], g["solutions"]):
+        got, it = uml_deflated_from_primitives(o, dims, fat, lng, src, *args, ev[:k], lam[:k])
+        assert abs(it - int(it_ref)) <= 2, (k, it, it_ref)
+        assert np.linalg.norm(got - want) <= 1e-9 * np.linalg.norm(want), k
+    assert int(g["iters"][-1]) == 2 and int(g["iters"][0]) < int(g["iters_plain"]) // 2
+    # orthonormal input: projecting out and adding back are independent of the order of the vectors
+    from oracle.pyoracle import EVEN
+    rng = np.random.default_rng(4)
+    d1 = rng.standard_normal(src.shape)
+    d2 = d1.copy()
+    perm = rng.permutation(16)
+    o.deflate(dims, d1, src, 0.1, ev[:16], lam[:16], EVEN)
+    o.deflate(dims, d2, src, 0.1, ev[:16][perm], lam[:16][perm], EVEN)
+    assert np.abs(d1 - d2).max() <= 1e-12 * np.abs(d1).max()
+
+
+def test_deflation_reference_live_matches_golden():
+    from oracle.pyoracle import ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref/libmilcref.so not built (needs /root/reference)")
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from test_oracle import _deflate_case
+from oracle.pyoracle import MilcRef
+g, dims, fat, lng, o, lam, ev, src = _deflate_case()
+r = MilcRef(dims)
+r.set_links(fat, lng)
+for k, it_ref, want in zip(g['nvecs'], g['iters'], g['solutions']):
+    dst = np.zeros_like(src)
+    it, q = r.mat_invert_uml_deflated(src, dst, float(g['mass']), int(g['niter']), int(g['nrestart']), float(g['resid']), ev[:k], lam[:k])
+    assert abs(it - int(it_ref)) <= 1 and q['converged'] == 1, (k, it, it_ref)
+    assert np.linalg.norm(dst - want) <= 1e-10 * np.linalg.norm(want), k
+print('LIVE-OK')
+""" % (ROOT, os.path.dirname(__file__))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "LIVE-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 # ---- HISQ fermion force (row f2): the oracle for the next row, pinned ahead of the CUDA work ------
 def _generator(a):
     T = np.zeros((3, 3), complex)
