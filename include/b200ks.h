@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200KS_VERSION 111 /* 110: block solve, resident sequences, link construction; 111: force filter, Naik epsilons */
+#define B200KS_VERSION 111 /* 110: block solve, resident sequences, link construction; 111: force filter, Naik epsilons, deflation */
 
 /* parity codes, include/macros.h:68-70 */
 #define B200KS_EVEN 2
@@ -191,6 +191,25 @@ int b200ks_mat_invert_uml_dev(b200ks_ctx *ctx, int nsrc, const int *vsrc, const 
 int b200ks_multicg_rational(b200ks_ctx *ctx, const void *src, void *const *psim, void *dest,
                             const double *offsets, const double *residues, int num_offsets, int fill_other,
                             const b200ks_invert_args *args, b200ks_invert_result *res, int host_prec);
+
+/* ---- low-mode deflation with eigenvectors resident in HBM ------
+ * Replaces deflate() + project_out() (generic_ks/mat_invert.c:131-183), which give the CGs of
+ * mat_invert_uml_field / mat_invert_cg_field (:186-257,328-402; qic->deflate) the exact solution in the
+ * span of the low modes as their starting point: on the sites of one parity
+ *     dst <- dst - sum_j v_j <v_j|dst> + sum_j v_j <v_j|src> / (eigval_j + 4 m^2) .
+ * b200ks_eig_set: declares nvecs device vectors (b200ks_vec_create / b200ks_vec_upload, both parities
+ *   filled, orthonormal on each parity: MILC's eigVec[j]) and their eigenvalues of -D_eo D_oe (MILC's
+ *   eigVal[j]) as the context's low-mode set; nvecs = 0 drops it.  The vectors stay in HBM (48 B per
+ *   site and parity each) and cannot be freed while in the set.  use_in_uml != 0: b200ks_mat_invert_uml
+ *   and _dev deflate their trial solutions before the even and before the odd solve, as the
+ *   reference does with qic->deflate set.
+ * b200ks_deflate_dev: the update above for device vectors, parity EVEN or ODD.
+ * The reference removes the modes from dst one after the other; the batch form used here is identical
+ * for orthonormal vectors.  Single-GPU contexts. */
+int b200ks_eig_set(b200ks_ctx *ctx, int nvecs, const int *vecs, const double *eigval, int use_in_uml);
+int b200ks_eig_count(b200ks_ctx *ctx);
+int b200ks_eig_use_in_uml(b200ks_ctx *ctx, int on);   /* qic->deflate of the next UML sequences */
+int b200ks_deflate_dev(b200ks_ctx *ctx, int vsrc, int vdst, double mass, int parity);
 
 /* ---- fermion-link construction ---------------------------
  * Links are su3_matrix[4*V] in MILC order (link[4*i+dir]) with KS phases and boundary signs

@@ -118,6 +118,9 @@ int mat_invert_uml_field_gpu(su3_vector *src, su3_vector *dst, quark_invert_cont
                              imp_ferm_links_t *fn);
 int mat_invert_block_uml_gpu(su3_vector **src, su3_vector **dst, Real mass, int nsrc, quark_invert_control *qic,
                              imp_ferm_links_t *fn);
+/* Low modes for qic->deflate in the two sequences above (generic_ks/mat_invert.c:131-183): MILC's eigVec, eigVal and
+ * param.eigen_param.Nvecs, handed over once after they were read or computed; kept in HBM.  nvecs = 0 drops them. */
+void b200ks_milc_set_eigenvectors(int nvecs, su3_vector **eigvec, double *eigval);
 imp_ferm_links_t *get_fn_last(void);
 void set_fn_last(imp_ferm_links_t *fn_last_new);
 

@@ -73,6 +73,10 @@ SYMBOLS = [
                                           C.POINTER(InvertResult), C.c_int]),
     ("b200ks_hisq_force", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int]),
+    ("b200ks_eig_set", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int]),
+    ("b200ks_eig_count", C.c_int, [C.c_void_p]),
+    ("b200ks_eig_use_in_uml", C.c_int, [C.c_void_p, C.c_int]),
+    ("b200ks_deflate_dev", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int]),
     ("b200ks_ks_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ("b200ks_unitarized_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.POINTER(C.c_longlong)]),

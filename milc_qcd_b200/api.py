@@ -314,6 +314,21 @@ class Context:
         check(self.lib.b200ks_vec_norm2(self.h, v, parity, C.byref(out)), "b200ks_vec_norm2")
         return out.value
 
+    def eig_set(self, vecs, eigval, use_in_uml=True):
+        """b200ks_eig_set: device vectors `vecs` (both parities uploaded) with eigenvalues `eigval` of -D_eo D_oe
+        become the context's low-mode set (MILC's eigVec / eigVal); an empty list drops it."""
+        n = len(vecs)
+        hv = (C.c_int * max(n, 1))(*[int(v) for v in vecs])
+        ev = (C.c_double * max(n, 1))(*[float(x) for x in eigval])
+        check(self.lib.b200ks_eig_set(self.h, n, hv, ev, int(use_in_uml)), "b200ks_eig_set")
+
+    def eig_count(self):
+        return self.lib.b200ks_eig_count(self.h)
+
+    def deflate_dev(self, vsrc, vdst, mass, parity):
+        """b200ks_deflate_dev: deflate() of generic_ks/mat_invert.c:131-183 on device vectors."""
+        check(self.lib.b200ks_deflate_dev(self.h, vsrc, vdst, mass, parity), "b200ks_deflate_dev")
+
     def dslash_dev(self, vsrc, vdest, parity, prec=2):
         check(self.lib.b200ks_dslash_dev(self.h, vsrc, vdest, parity, prec), "b200ks_dslash_dev")
 

@@ -19,6 +19,7 @@
 #include "../../include/b200ks.h"
 #include "blas.cuh"
 #include "comm.cuh"
+#include "deflate.cuh"
 #include "dslash.cuh"
 #include "half.cuh"
 #include "mrhs.cuh"
@@ -46,6 +47,17 @@ struct Links {           // fat + long links of one precision, both parities
   void *lng[2] = {nullptr, nullptr};
   bool valid = false;
   int lng_nc = 9;        // complex numbers stored per long link: 9 full, 7 = two rows + U(3) factor
+};
+
+struct EigSet {           // low modes resident in HBM (row f4): user vectors, both parities filled
+  int n = 0;
+  std::vector<int> handles;
+  double *d_val = nullptr;                          // eigenvalues of -D_eo D_oe
+  const double2 **d_ptr[2] = {nullptr, nullptr};    // per parity: the n vectors' device pointers
+  double2 *d_coef = nullptr;
+  double *d_part = nullptr;                         // [n][nchunks][4] partial sums
+  int nchunks = 0;
+  bool uml = false;                                 // the resident UML sequences deflate their trial solutions
 };
 
 struct b200ks_ctx {
@@ -77,6 +89,7 @@ struct b200ks_ctx {
   void *lw = nullptr;    // LinkWork: buffers of the fermion-link construction (allocated on first use)
   void *bounce[2] = {nullptr, nullptr};          // pinned bounce buffers for pageable host arrays
   cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+  EigSet eig;
 };
 
 static size_t real_size(int prec) { return prec == B200KS_PREC_DOUBLE ? 8 : prec == B200KS_PREC_SINGLE ? 4 : 2; }
@@ -390,6 +403,11 @@ extern "C" void b200ks_destroy(b200ks_ctx *c) {
   if (c->comm.ev_done) cudaEventDestroy(c->comm.ev_done);
   if (c->comm.stream) cudaStreamDestroy(c->comm.stream);
   fermion_links_release(c);
+  cudaFree(c->eig.d_val);
+  cudaFree((void *)c->eig.d_ptr[0]);
+  cudaFree((void *)c->eig.d_ptr[1]);
+  cudaFree(c->eig.d_coef);
+  cudaFree(c->eig.d_part);
   for (int k = 0; k < 2; k++) {
     if (c->bounce[k]) cudaFreeHost(c->bounce[k]);
     if (c->bounce_ev[k]) cudaEventDestroy(c->bounce_ev[k]);
@@ -1047,6 +1065,8 @@ extern "C" int b200ks_vec_create(b200ks_ctx *c) {
 extern "C" int b200ks_vec_free(b200ks_ctx *c, int h) {
   DevVec *v = uvec(c, h);
   if (!v) return B200KS_EINVAL;
+  if (std::find(c->eig.handles.begin(), c->eig.handles.end(), h) != c->eig.handles.end())
+    return fail(B200KS_ESTATE, "b200ks_vec_free: the vector belongs to the eigenvector set (b200ks_eig_set(ctx, 0, ...) first)");
   cudaStreamSynchronize(c->stream);
   vec_delete(c, v);
   c->user[h] = nullptr;
@@ -2231,6 +2251,85 @@ static void axpby_d(b200ks_ctx *c, DevVec &out, double a, const DevVec &x, doubl
          y ? (const double2 *)y->p[pbit] : (const double2 *)nullptr, c->g.stride, c->g.Vh);
 }
 
+// ---- low-mode deflation (row f4, deflate.cuh) ----------------------------------------------------
+static void eig_release(b200ks_ctx *c) {
+  EigSet &e = c->eig;
+  if (e.n) cudaStreamSynchronize(c->stream);
+  dev_free(c, e.d_val, sizeof(double) * e.n);
+  for (int p = 0; p < 2; p++) dev_free(c, (void *)e.d_ptr[p], sizeof(double2 *) * e.n);
+  dev_free(c, e.d_coef, sizeof(double2) * e.n);
+  dev_free(c, e.d_part, sizeof(double) * 4 * (size_t)e.n * e.nchunks);
+  e = EigSet();
+}
+
+// Declares nvecs user vectors (both parities uploaded, orthonormal on each parity) with their
+// eigenvalues of -D_eo D_oe as the low-mode set of this context; nvecs = 0 drops it.  MILC's eigVec /
+// eigVal / param.eigen_param.Nvecs (generic_ks/mat_invert.c:131-183).  use_in_uml: the resident UML
+// sequences deflate their trial solutions like mat_invert_uml_field does with qic->deflate set.
+extern "C" int b200ks_eig_set(b200ks_ctx *c, int nvecs, const int *vecs, const double *eigval, int use_in_uml) {
+  if (!c || nvecs < 0 || (nvecs > 0 && (!vecs || !eigval))) return fail(B200KS_EINVAL, "b200ks_eig_set: bad argument");
+  if (c->comm.active) return fail(B200KS_ESTATE, "deflation: single-GPU contexts only");
+  CU(cudaSetDevice(c->device));
+  eig_release(c);
+  if (nvecs == 0) return 0;
+  std::vector<const double2 *> hp[2];
+  for (int j = 0; j < nvecs; j++) {
+    DevVec *v = uvec(c, vecs[j]);
+    if (!v) return B200KS_EINVAL;
+    for (int p = 0; p < 2; p++) hp[p].push_back((const double2 *)v->p[p]);
+  }
+  EigSet &e = c->eig;
+  e.nchunks = std::min(nblocks(c->g.Vh), 296);   // two CTAs per SM walk the vectors
+  void *q = nullptr;
+  int r = dev_alloc(c, &q, sizeof(double) * nvecs);
+  e.d_val = (double *)q;
+  for (int p = 0; p < 2 && r == 0; p++) {
+    r = dev_alloc(c, &q, sizeof(double2 *) * nvecs);
+    e.d_ptr[p] = (const double2 **)q;
+  }
+  if (r == 0) { r = dev_alloc(c, &q, sizeof(double2) * nvecs); e.d_coef = (double2 *)q; }
+  if (r == 0) { r = dev_alloc(c, &q, sizeof(double) * 4 * (size_t)nvecs * e.nchunks); e.d_part = (double *)q; }
+  e.n = nvecs;   // (so that eig_release accounts for what was allocated)
+  if (r < 0) { eig_release(c); return r; }
+  // on the library's (non-blocking) stream, which every later kernel is ordered behind
+  CU(cudaMemcpyAsync(e.d_val, eigval, sizeof(double) * nvecs, cudaMemcpyHostToDevice, c->stream));
+  for (int p = 0; p < 2; p++)
+    CU(cudaMemcpyAsync((void *)e.d_ptr[p], hp[p].data(), sizeof(double2 *) * nvecs, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));   // hp and eigval are the caller's / this frame's
+  e.handles.assign(vecs, vecs + nvecs);
+  e.uml = use_in_uml != 0;
+  return 0;
+}
+
+extern "C" int b200ks_eig_count(b200ks_ctx *c) { return c ? c->eig.n : 0; }
+extern "C" int b200ks_eig_use_in_uml(b200ks_ctx *c, int on) {
+  if (!c) return fail(B200KS_EINVAL, "null context");
+  c->eig.uml = on != 0;
+  return 0;
+}
+
+// dst <- dst - sum_j v_j <v_j|dst> + sum_j v_j <v_j|src>/(lambda_j + 4 m^2) on parity bit pbit
+static int deflate_dv(b200ks_ctx *c, DevVec &dst, const DevVec &src, double mass, int pbit) {
+  EigSet &e = c->eig;
+  if (e.n == 0) return fail(B200KS_ESTATE, "deflation: no eigenvector set (b200ks_eig_set)");
+  const int n = c->g.Vh, per = (n + e.nchunks - 1) / e.nchunks;
+  eig_dot_kernel<<<e.nchunks, kBlock, 0, c->stream>>>(e.d_ptr[pbit], e.n, (const double2 *)src.p[pbit], (const double2 *)dst.p[pbit],
+                                                      c->g.stride, n, per, e.d_part);
+  eig_coef_kernel<<<(e.n + 127) / 128, 128, 0, c->stream>>>(e.d_part, e.nchunks, e.d_val, 4.0 * mass * mass, e.n, e.d_coef);
+  eig_axpy_kernel<<<nblocks(n), kBlock, 0, c->stream>>>(e.d_ptr[pbit], e.d_coef, e.n, (double2 *)dst.p[pbit], c->g.stride, n);
+  c->launches += 3;
+  return check_launch("deflation");
+}
+
+extern "C" int b200ks_deflate_dev(b200ks_ctx *c, int vsrc, int vdst, double mass, int parity) {
+  DevVec *s = uvec(c, vsrc), *d = uvec(c, vdst);
+  if (!s || !d) return B200KS_EINVAL;
+  if (s == d) return fail(B200KS_EINVAL, "b200ks_deflate_dev: source and trial solution must be different fields");
+  if (parity != B200KS_EVEN && parity != B200KS_ODD) return fail(B200KS_EINVAL, "b200ks_deflate_dev: parity must be EVEN or ODD");
+  CU(cudaSetDevice(c->device));
+  return deflate_dv(c, *d, *s, mass, parity_bit(parity));
+}
+
 // mat_invert_uml_field / mat_invert_block_uml (generic_ks/mat_invert.c:328-402,409-475) for nsrc
 // sources: tmp = M^+ src (both parities), even solve (M^+ M) dst_e = tmp_e from the guess in dst_e,
 // dst_o = (src_o - D_oe dst_e)/2m, odd solve from that guess ("polish").  res[2*k], res[2*k+1]: the
@@ -2254,6 +2353,9 @@ static int uml_any(b200ks_ctx *c, int nsrc, DevVec *const *src, DevVec *const *d
   b200ks_invert_args args = args_in;
   std::vector<b200ks_invert_result> r(nsrc);
   int total = 0;
+  const bool deflated = c->eig.n > 0 && c->eig.uml;   // mat_invert.c:341-353,376-387
+  if (deflated)
+    for (int k = 0; k < nsrc; k++) CHK(deflate_dv(c, *dst[k], *tmp[k], mass, 0));
   args.parity = B200KS_EVEN;
   int it = congrad_block_any(c, nsrc, tmp.data(), dst, mass, args, r.data());
   if (it < 0) return it;
@@ -2263,6 +2365,7 @@ static int uml_any(b200ks_ctx *c, int nsrc, DevVec *const *src, DevVec *const *d
     Epi e;   // dst_o = (src_o - D dst_e) / 2m
     CHK(dslash_T<double>(c, *dst[k], *ttt, 1, e));
     axpby_d(c, *dst[k], 1.0 / (2.0 * mass), *src[k], -1.0 / (2.0 * mass), ttt, 1);
+    if (deflated) CHK(deflate_dv(c, *dst[k], *tmp[k], mass, 1));
   }
   args.parity = B200KS_ODD;
   it = congrad_block_any(c, nsrc, tmp.data(), dst, mass, args, r.data());

@@ -227,8 +227,36 @@ int ks_congrad_block_parity_gpu(int nsrc, su3_vector **t_src, su3_vector **t_des
   return iters;
 }
 
+/* Low modes for deflation.  MILC keeps them in application globals (eigVec, eigVal,
+ * param.eigen_param.Nvecs: ks_spectrum/lattice.h, params.h) that a library cannot name, so the application hands
+ * them over once after reading or computing them; they are uploaded and stay in HBM until replaced.
+ * eigvec[j]: su3_vector[sites_on_node], both parities filled; eigval[j]: eigenvalue of -D_eo D_oe.  nvecs = 0 drops
+ * them.  The UML sequences below then honour qic->deflate like mat_invert.c:341-353,376-387,428-437 do. */
+static int s_neig = 0;
+static int *s_eig_handle = NULL;
+void b200ks_milc_set_eigenvectors(int nvecs, su3_vector **eigvec, double *eigval) {
+  char myname[] = "b200ks_milc_set_eigenvectors";
+  b200ks_ctx *ctx = context(myname);
+  int j;
+  if (b200ks_eig_set(ctx, 0, NULL, NULL, 0) < 0) die(myname);
+  for (j = 0; j < s_neig; j++)
+    if (b200ks_vec_free(ctx, s_eig_handle[j]) < 0) die(myname);
+  free(s_eig_handle);
+  s_eig_handle = NULL;
+  s_neig = 0;
+  if (nvecs <= 0) return;
+  s_eig_handle = (int *)malloc(nvecs * sizeof(int));
+  for (j = 0; j < nvecs; j++) {
+    s_eig_handle[j] = b200ks_vec_create(ctx);
+    if (s_eig_handle[j] < 0) die(myname);
+    s_neig = j + 1;
+    if (b200ks_vec_upload(ctx, s_eig_handle[j], eigvec[j], EVENANDODD, MILC_PRECISION) < 0) die(myname);
+  }
+  if (b200ks_eig_set(ctx, nvecs, s_eig_handle, eigval, 0) < 0) die(myname);
+}
+
 /* mat_invert_uml_field / mat_invert_block_uml (generic_ks/mat_invert.c:328-402,409-475) as one
- * device-resident sequence: M^+ src, even solve, odd reconstruction, odd polish. */
+ * device-resident sequence: M^+ src, [deflation,] even solve, odd reconstruction, [deflation,] odd polish. */
 int mat_invert_block_uml_gpu(su3_vector **src, su3_vector **dst, Real mass, int nsrc, quark_invert_control *qic,
                              imp_ferm_links_t *fn) {
   char myname[] = "mat_invert_block_uml_gpu";
@@ -261,6 +289,7 @@ int mat_invert_block_uml_gpu(su3_vector **src, su3_vector **dst, Real mass, int 
   a.relresid = qic->relresid;
   a.mixed_precision = (qic->prec == 1) ? (MIXED ? MIXED : 1) : MIXED;
   if (MILC_PRECISION == 2 && qic->prec == 2) a.mixed_precision = MIXED;
+  if (b200ks_eig_use_in_uml(context(myname), qic->deflate && s_neig > 0) < 0) die(myname);
   iters = b200ks_mat_invert_uml(context(myname), nsrc, (const void *const *)src, (void *const *)dst, (double)mass, &a, r,
                                 MILC_PRECISION);
   if (iters < 0) die(myname);
