@@ -20,6 +20,8 @@
  *   kso_congrad         generic_ks/d_congrad5_fn_milc.c:60-407
  *   kso_multicg         generic_ks/ks_multicg_offset.c:63-505
  *   kso_relative_residue generic_ks/d_congrad5_fn_milc.c:37-56
+ *   kso_deflate         generic_ks/mat_invert.c:131-183 (deflate + project_out), pinned through the
+ *                       reference's deflated mat_invert_uml_field (tests/golden/make_golden_deflate.py)
  *
  * Data layout is MILC's host layout: site index i = node_index(x,y,z,t) (all even
  * sites, then all odd sites), vectors v[6*i + 2*c + {re,im}], links
