@@ -807,6 +807,76 @@ def run_force(args):
     return 0
 
 
+def run_deflate(args):
+    """--workload deflate: low-mode deflation of a trial solution with the
+    vectors resident in HBM, on the BASELINE configs[1] lattice.  The set is synthetic (Gaussian vectors and a
+    made-up spectrum: the kernels' traffic does not depend on the values); value = vectors deflated per second,
+    device time by CUDA events on the library's stream; roofline: 2 x 48 B per site and vector against the
+    measured HBM peak.  cpu_baseline: the oracle's restatement of deflate() (mat_invert.c:131-183) on a
+    16^3x32 lattice (the reference's own function is static; the restatement is pinned on its effect)."""
+    import torch
+    from milc_qcd_b200 import api
+    local_rank = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local_rank)
+    dims = tuple(args.lattice) if args.lattice else DIMS
+    V = int(np.prod(dims))
+    nvecs = args.nvecs
+    ctx = api.Context(dims, device=local_rank)
+    stream = torch.cuda.ExternalStream(ctx.lib.b200ks_stream(ctx.h))
+    hs = []
+    for j in range(nvecs):
+        h = ctx.vec_create()
+        ctx.vec_gaussian(h, 3, 1000 + j)
+        hs.append(h)
+    ctx.eig_set(hs, list(np.linspace(1e-4, 1e-2, nvecs)), use_in_uml=False)
+    vs, vd = ctx.vec_create(), ctx.vec_create()
+    ctx.vec_gaussian(vs, 3, 7)
+    ctx.vec_zero(vd, 3)
+    l0 = ctx.launch_count()
+    for _ in range(max(3, args.warmup)):
+        ctx.deflate_dev(vs, vd, 0.05, 2)
+    steps = max(3, args.steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    l1 = ctx.launch_count()
+    e0.record(stream)
+    for _ in range(steps):
+        ctx.deflate_dev(vs, vd, 0.05, 2)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = ctx.launch_count() - l1
+    peak, peak_src = measured_peak()
+    alg_bytes = 2.0 * 48 * (V // 2) * nvecs
+    out = {"metric": "deflation_vectors_per_s", "unit": "vectors/s", "n_gpus": 1, "higher_is_better": True, "data": "synthetic",
+           "value": nvecs / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "dtype": "f64", "gpu_launches": int(launches),
+           "config": {"workload": "deflation of one parity of a trial solution with %d resident vectors, %s (vectors larger than L2)"
+                                  % (nvecs, "x".join(map(str, dims))), "lattice": list(dims), "nvecs": nvecs},
+           "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
+           "device_bytes": ctx.device_bytes()}
+    ctx.close()
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import pyoracle
+            sdims = (16, 16, 16, 32)
+            Vs = int(np.prod(sdims))
+            rng = np.random.default_rng(5)
+            ev = rng.standard_normal((min(nvecs, 32), Vs, 3, 2))
+            src, dst = rng.standard_normal((Vs, 3, 2)), np.zeros((Vs, 3, 2))
+            o = pyoracle.Oracle()
+            t0 = time.perf_counter()
+            o.deflate(sdims, dst, src, 0.05, ev, np.linspace(1e-4, 1e-2, ev.shape[0]), 2)
+            t_cpu = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": ev.shape[0] / t_cpu * (Vs / V), "unit": "vectors/s (scaled to the workload's volume)",
+                                   "cores": 1, "kind": "port",
+                                   "sample": "kso_deflate, %d vectors on a 16x16x16x32 lattice, one thread" % ev.shape[0]}
+        except Exception as ex:
+            out["cpu_baseline"] = {"value": None, "kind": "unavailable", "sample": repr(ex)}
+    print(json.dumps(out))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -820,7 +890,8 @@ def main():
     ap.add_argument("--long-recon", type=int, default=0, help="long-link storage: 18, 14 or 0 = decided on the data")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lattice", type=int, nargs=4, default=None, help="override the lattice (nx ny nz nt)")
-    ap.add_argument("--workload", default="cg", choices=["cg", "multishift", "block", "links", "force"],
+    ap.add_argument("--nvecs", type=int, default=64, help="--workload deflate: number of resident vectors")
+    ap.add_argument("--workload", default="cg", choices=["cg", "multishift", "block", "links", "force", "deflate"],
                     help="cg (default, the driver's line): single-mass CG; multishift: BASELINE configs[2]; "
                          "block: multi-right-hand-side CG (ks_congrad_block_parity seam); "
                          "links: HISQ fermion-link construction (qudaLoadUnitarizedLink / qudaLoadKSLink seam)")
@@ -835,6 +906,8 @@ def main():
         return run_links(args)
     if args.workload == "force":
         return run_force(args)
+    if args.workload == "deflate":
+        return run_deflate(args)
     return run_b200(args)
 
 
