@@ -81,6 +81,10 @@ extern "C" int b200ks_hisq_force(b200ks_ctx *c, int nterms, int num_naik_terms, 
   const Geom &g = geom(c);
   const int n = 2 * g.Vh;
   force::ForceBufs b;
+  {   // A/B switch: the backward staple passes as two kernels with fewer live matrices each (force.cuh)
+    const char *e = getenv("B200KS_FORCE_SPLIT");
+    b.split = e && atoi(e) != 0;
+  }
   for (int d = 0; d < 4; d++) b.g.L[d] = g.L[d];
   b.g.Vh = g.Vh;
   b.nsites = n;

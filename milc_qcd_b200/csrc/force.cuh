@@ -73,10 +73,12 @@ B200KS_HD Mat nn(const Mat &a, const Mat &b) {
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) {
       double re = 0, im = 0;
-      for (int k = 0; k < 3; k++) {
+      for (int k = 0; k < 3; k++) {   // one product per statement: each contracts to a single DFMA on the device
         const double2 x = a.e[3 * i + k], y = b.e[3 * k + j];
-        re += x.x * y.x - x.y * y.y;
-        im += x.x * y.y + x.y * y.x;
+        re += x.x * y.x;
+        re -= x.y * y.y;
+        im += x.x * y.y;
+        im += x.y * y.x;
       }
       c.e[3 * i + j] = make_double2(re, im);
     }
@@ -201,6 +203,56 @@ struct StapleBwdSite {
       add(gu, na(nn(ld(link, fs, z), Uzpm), Hzpn));
     }
     acc(glink, fs, z, hs, gl);
+    acc(gUnu, fs, z, hs, gu);
+  }
+};
+
+// The same pass as two kernels (the gradient of the link field, the gradient of the nu links): two more
+// matrix loads per site in total, but each half keeps far fewer matrices live than the fused body
+// (254 registers + spills).  Selected at run time (ForceBufs::split) for A/B measurements.
+struct StapleBwdLinkSite {
+  FGeom g;
+  const double2 *H;
+  double hs;
+  const double2 *Unu;
+  double2 *glink;
+  size_t fs;
+  int mu, nu;
+  int part = 3;
+  B200KS_HD void operator()(int z) const {
+    Mat gl = zero();
+    if (part & 1) {
+      const int zmn = nbr(g, z, nu, -1), zmnpm = nbr(g, zmn, mu, 1);
+      gl = nn(an(ld(Unu, fs, zmn), ld(H, fs, zmn)), ld(Unu, fs, zmnpm));
+    }
+    if (part & 2) {
+      const int zpn = nbr(g, z, nu, 1), zpm = nbr(g, z, mu, 1);
+      add(gl, na(nn(ld(Unu, fs, z), ld(H, fs, zpn)), ld(Unu, fs, zpm)));
+    }
+    acc(glink, fs, z, hs, gl);
+  }
+};
+struct StapleBwdUSite {
+  FGeom g;
+  const double2 *H;
+  double hs;
+  const double2 *link, *Unu;
+  double2 *gUnu;
+  size_t fs;
+  int mu, nu;
+  int part = 3;
+  B200KS_HD void operator()(int z) const {
+    const int zpn = nbr(g, z, nu, 1), zpm = nbr(g, z, mu, 1), zmm = nbr(g, z, mu, -1), zmmpn = nbr(g, zmm, nu, 1);
+    const Mat Uzpm = ld(Unu, fs, zpm), Uzmm = ld(Unu, fs, zmm);
+    Mat gu = zero();
+    if (part & 1) {
+      gu = nn(ld(H, fs, z), na(Uzpm, ld(link, fs, zpn)));
+      add(gu, nn(an(ld(H, fs, zmm), Uzmm), ld(link, fs, zmmpn)));
+    }
+    if (part & 2) {
+      add(gu, nn(an(ld(link, fs, zmm), Uzmm), ld(H, fs, zmmpn)));
+      add(gu, na(nn(ld(link, fs, z), Uzpm), ld(H, fs, zpn)));
+    }
     acc(gUnu, fs, z, hs, gu);
   }
 };
@@ -374,7 +426,19 @@ struct ForceBufs {
   double2 *U, *V, *W;             // 36 planes each (inputs)
   double2 *gfat, *glng, *gW, *gU; // 36 planes each
   double2 *st3, *st5, *g3, *g5;   // 9 planes each
+  bool split = false;             // backward staple passes as two kernels (StapleBwdLinkSite + StapleBwdUSite)
 };
+
+template <class X>
+void staple_bwd(X &x, const ForceBufs &b, const double2 *H, double hs, const double2 *link, const double2 *Unu, double2 *glink,
+                double2 *gUnu, int mu, int nu, int part = 3) {
+  if (b.split) {
+    x.run(b.nsites, StapleBwdLinkSite{b.g, H, hs, Unu, glink, b.fs, mu, nu, part});
+    x.run(b.nsites, StapleBwdUSite{b.g, H, hs, link, Unu, gUnu, b.fs, mu, nu, part});
+  } else {
+    x.run(b.nsites, StapleBwdSite{b.g, H, hs, link, Unu, glink, gUnu, b.fs, mu, nu, part});
+  }
+}
 
 // reverse of one smearing level (links.cuh smear_dev / load_fatlinks_cpu): gfat -> adds to glinks
 template <class X>
@@ -396,8 +460,8 @@ void smear_bwd(X &x, const ForceBufs &b, const double *coeffs, const double2 *li
         for (int part = 1; part <= 2; part++) {
           x.run(n, StapleFwdSite{b.g, b.st5, links + dir * m1, Unu, fs, dir, nu, part});
           x.run(n, ZeroSite{b.g5, fs, 9});
-          x.run(n, StapleBwdSite{b.g, Gd, lepage, b.st5, Unu, b.g5, glinks + nu * m1, fs, dir, nu, part});
-          x.run(n, StapleBwdSite{b.g, b.g5, 1.0, links + dir * m1, Unu, glinks + dir * m1, glinks + nu * m1, fs, dir, nu, part});
+          staple_bwd(x, b, Gd, lepage, b.st5, Unu, b.g5, glinks + nu * m1, dir, nu, part);
+          staple_bwd(x, b, b.g5, 1.0, links + dir * m1, Unu, glinks + dir * m1, glinks + nu * m1, dir, nu, part);
         }
       for (int rho = 0; rho < 4; rho++) {
         if (rho == dir || rho == nu) continue;
@@ -407,11 +471,11 @@ void smear_bwd(X &x, const ForceBufs &b, const double *coeffs, const double2 *li
         x.run(n, AxpySite{b.g5, Gd, five, fs, 9});
         for (int sig = 0; sig < 4; sig++) {
           if (sig == dir || sig == nu || sig == rho) continue;
-          x.run(n, StapleBwdSite{b.g, Gd, seven, b.st5, links + sig * m1, b.g5, glinks + sig * m1, fs, dir, sig});
+          staple_bwd(x, b, Gd, seven, b.st5, links + sig * m1, b.g5, glinks + sig * m1, dir, sig);
         }
-        x.run(n, StapleBwdSite{b.g, b.g5, 1.0, b.st3, Urho, b.g3, glinks + rho * m1, fs, dir, rho});
+        staple_bwd(x, b, b.g5, 1.0, b.st3, Urho, b.g3, glinks + rho * m1, dir, rho);
       }
-      x.run(n, StapleBwdSite{b.g, b.g3, 1.0, links + dir * m1, Unu, glinks + dir * m1, glinks + nu * m1, fs, dir, nu});
+      staple_bwd(x, b, b.g3, 1.0, links + dir * m1, Unu, glinks + dir * m1, glinks + nu * m1, dir, nu);
     }
   }
 }

@@ -27,8 +27,9 @@ static void to_planes(double2 *dst, const double *src, size_t fs, int nsites) {
 
 extern "C" void force_host(const int *dims, const double *coeffs1, const double *coeffs2, const double *U, const double *V,
                            const double *W, const double *multi_x, const double *c1, const double *c3, int nterms,
-                           int n_naik_terms, double eps, int naik_in_oprod, double filter, double *mom) {
+                           int n_naik_terms, double eps, int naik_in_oprod, double filter, int split, double *mom) {
   ForceBufs b;
+  b.split = split != 0;
   for (int d = 0; d < 4; d++) b.g.L[d] = dims[d];
   const int n = dims[0] * dims[1] * dims[2] * dims[3];
   b.g.Vh = n / 2;

@@ -28,16 +28,16 @@ def host_force():
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-x", "cu", "--shared", "-Xcompiler", "-fPIC", "-o", SO, src])
     lib = C.CDLL(SO)
     lib.force_host.restype = None
-    lib.force_host.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, _dp]
+    lib.force_host.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, _dp]
     return lib
 
 
-def _run(lib, dims, U, V, W, X, c1, c3, eps, naik_in_oprod, coeffs1, coeffs2, force_filter=5.0e-5, n_naik_terms=0):
+def _run(lib, dims, U, V, W, X, c1, c3, eps, naik_in_oprod, coeffs1, coeffs2, force_filter=5.0e-5, n_naik_terms=0, split=False):
     mom = np.zeros((U.shape[0], 4, 10))
     lib.force_host(np.ascontiguousarray(dims, np.int32), np.ascontiguousarray(coeffs1, np.float64),
                    np.ascontiguousarray(coeffs2, np.float64), np.ascontiguousarray(U), np.ascontiguousarray(V),
                    np.ascontiguousarray(W), np.ascontiguousarray(X), np.ascontiguousarray(c1, np.float64),
-                   np.ascontiguousarray(c3, np.float64), X.shape[0], n_naik_terms, eps, int(naik_in_oprod), force_filter, mom)
+                   np.ascontiguousarray(c3, np.float64), X.shape[0], n_naik_terms, eps, int(naik_in_oprod), force_filter, int(split), mom)
     return mom
 
 
@@ -98,6 +98,10 @@ def test_force_filter_matches_reference_on_rough_links(host_force):
     mom = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE, 5.0e-5)
     assert np.abs(mom - g["mom"]).max() <= 1e-9 * scale
     assert np.abs(mom - lo.hisq_force(dims, U, X, res, float(g["eps"]))).max() <= 1e-11 * scale
+    # the two-kernel form of the backward staple passes (ForceBufs::split): the same sums in the same order
+    two = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE,
+               5.0e-5, split=True)
+    assert np.array_equal(two, mom)
     # the filter is what makes the difference on this input, and switching it off matches the oracle's unfiltered force
     raw = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE, 0.0)
     assert np.abs(raw - g["mom"]).max() > 0.1 * scale
