@@ -110,19 +110,22 @@ B200KS_HD int nbr(const FGeom &g, int f, int mu, int sign) {
   const int cb = f - par * g.Vh;
   const int Lxh = g.L[0] / 2;
   int r = cb;
-  int c[4];
   const int xh = r % Lxh;
   r /= Lxh;
-  c[1] = r % g.L[1];
+  const int c1 = r % g.L[1];
   r /= g.L[1];
-  c[2] = r % g.L[2];
-  c[3] = r / g.L[2];
-  c[0] = 2 * xh + ((c[1] + c[2] + c[3] + par) & 1);
-  c[mu] += sign;
-  if (c[mu] >= g.L[mu]) c[mu] -= g.L[mu];
-  if (c[mu] < 0) c[mu] += g.L[mu];
-  const int lex = c[0] + g.L[0] * (c[1] + g.L[1] * (c[2] + g.L[2] * c[3]));
-  return (par ^ 1) * g.Vh + (lex >> 1);
+  const int c2 = r % g.L[2], c3 = r / g.L[2];
+  const int c0 = 2 * xh + ((c1 + c2 + c3 + par) & 1);
+  const int lex = c0 + g.L[0] * (c1 + g.L[1] * (c2 + g.L[2] * c3));
+  // only coordinate mu changes: lex moves by (new - old) * stride_mu; selects instead of an indexed array, which
+  // would live in local memory
+  const int cm = mu == 0 ? c0 : mu == 1 ? c1 : mu == 2 ? c2 : c3;
+  const int Lm = mu == 0 ? g.L[0] : mu == 1 ? g.L[1] : mu == 2 ? g.L[2] : g.L[3];
+  const int sm = mu == 0 ? 1 : mu == 1 ? g.L[0] : mu == 2 ? g.L[0] * g.L[1] : g.L[0] * g.L[1] * g.L[2];
+  int cn = cm + sign;
+  if (cn >= Lm) cn -= Lm;
+  if (cn < 0) cn += Lm;
+  return (par ^ 1) * g.Vh + ((lex + (cn - cm) * sm) >> 1);
 }
 
 // ---- site functors (operator()(f) for every site f) ------------------------------------------------
