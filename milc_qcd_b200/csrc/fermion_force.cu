@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 #include "force.cuh"
 #include "internal.h"
@@ -21,11 +22,24 @@ __global__ void __launch_bounds__(kBlock) force_site_kernel(const F fn, int n) {
   if (i < n) fn(i);
 }
 
+// the same with a register cap (<= 128 registers: four 128-thread CTAs per SM) for functors that declare a
+// static kMinBlocks member
+template <class F>
+__global__ void __launch_bounds__(kBlock, 4) force_site_kernel2(const F fn, int n) {
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) fn(i);
+}
+template <class F, class = void>
+struct WantsCap : std::false_type {};
+template <class F>
+struct WantsCap<F, std::void_t<decltype(F::kMinBlocks)>> : std::true_type {};
+
 struct DeviceExec {
   b200ks_ctx *c;
   template <class F>
   void run(int n, const F &fn) {
-    force_site_kernel<F><<<nblocks(n), kBlock, 0, stream(c)>>>(fn, n);
+    if constexpr (WantsCap<F>::value) force_site_kernel2<F><<<nblocks(n), kBlock, 0, stream(c)>>>(fn, n);
+    else force_site_kernel<F><<<nblocks(n), kBlock, 0, stream(c)>>>(fn, n);
     count_launch(c);
   }
 };

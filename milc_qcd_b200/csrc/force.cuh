@@ -210,10 +210,13 @@ struct StapleBwdSite {
   }
 };
 
-// The same pass as two kernels (the gradient of the link field, the gradient of the nu links): two more
-// matrix loads per site in total, but each half keeps far fewer matrices live than the fused body
-// (254 registers + spills).  Selected at run time (ForceBufs::split) for A/B measurements.
+// The same pass as up to four kernels (gradient of the link field / of the nu links, upper / lower staple, the
+// staple chosen at compile time): a few more matrix loads per site in total, but each piece keeps 3 to 6
+// matrices live instead of the fused body's 14 (254 registers: 8 warps per SM) and is compiled for 128 registers
+// (kMinBlocks, used by the launch in fermion_force.cu: 16 warps per SM).  Selected at run time (ForceBufs::split) for A/B measurements.
+template <int kPart>
 struct StapleBwdLinkSite {
+  static constexpr int kMinBlocks = 4;
   FGeom g;
   const double2 *H;
   double hs;
@@ -221,21 +224,19 @@ struct StapleBwdLinkSite {
   double2 *glink;
   size_t fs;
   int mu, nu;
-  int part = 3;
   B200KS_HD void operator()(int z) const {
-    Mat gl = zero();
-    if (part & 1) {
+    if (kPart == 1) {
       const int zmn = nbr(g, z, nu, -1), zmnpm = nbr(g, zmn, mu, 1);
-      gl = nn(an(ld(Unu, fs, zmn), ld(H, fs, zmn)), ld(Unu, fs, zmnpm));
-    }
-    if (part & 2) {
+      acc(glink, fs, z, hs, nn(an(ld(Unu, fs, zmn), ld(H, fs, zmn)), ld(Unu, fs, zmnpm)));
+    } else {
       const int zpn = nbr(g, z, nu, 1), zpm = nbr(g, z, mu, 1);
-      add(gl, na(nn(ld(Unu, fs, z), ld(H, fs, zpn)), ld(Unu, fs, zpm)));
+      acc(glink, fs, z, hs, na(nn(ld(Unu, fs, z), ld(H, fs, zpn)), ld(Unu, fs, zpm)));
     }
-    acc(glink, fs, z, hs, gl);
   }
 };
+template <int kPart>
 struct StapleBwdUSite {
+  static constexpr int kMinBlocks = 4;
   FGeom g;
   const double2 *H;
   double hs;
@@ -243,18 +244,15 @@ struct StapleBwdUSite {
   double2 *gUnu;
   size_t fs;
   int mu, nu;
-  int part = 3;
   B200KS_HD void operator()(int z) const {
     const int zpn = nbr(g, z, nu, 1), zpm = nbr(g, z, mu, 1), zmm = nbr(g, z, mu, -1), zmmpn = nbr(g, zmm, nu, 1);
-    const Mat Uzpm = ld(Unu, fs, zpm), Uzmm = ld(Unu, fs, zmm);
-    Mat gu = zero();
-    if (part & 1) {
-      gu = nn(ld(H, fs, z), na(Uzpm, ld(link, fs, zpn)));
-      add(gu, nn(an(ld(H, fs, zmm), Uzmm), ld(link, fs, zmmpn)));
-    }
-    if (part & 2) {
-      add(gu, nn(an(ld(link, fs, zmm), Uzmm), ld(H, fs, zmmpn)));
-      add(gu, na(nn(ld(link, fs, z), Uzpm), ld(H, fs, zpn)));
+    Mat gu;
+    if (kPart == 1) {
+      gu = nn(ld(H, fs, z), na(ld(Unu, fs, zpm), ld(link, fs, zpn)));
+      add(gu, nn(an(ld(H, fs, zmm), ld(Unu, fs, zmm)), ld(link, fs, zmmpn)));
+    } else {
+      gu = nn(an(ld(link, fs, zmm), ld(Unu, fs, zmm)), ld(H, fs, zmmpn));
+      add(gu, na(nn(ld(link, fs, z), ld(Unu, fs, zpm)), ld(H, fs, zpn)));
     }
     acc(gUnu, fs, z, hs, gu);
   }
@@ -429,15 +427,21 @@ struct ForceBufs {
   double2 *U, *V, *W;             // 36 planes each (inputs)
   double2 *gfat, *glng, *gW, *gU; // 36 planes each
   double2 *st3, *st5, *g3, *g5;   // 9 planes each
-  bool split = false;             // backward staple passes as two kernels (StapleBwdLinkSite + StapleBwdUSite)
+  bool split = false;             // backward staple passes as up to four small kernels (StapleBwdLinkSite / StapleBwdUSite)
 };
 
 template <class X>
 void staple_bwd(X &x, const ForceBufs &b, const double2 *H, double hs, const double2 *link, const double2 *Unu, double2 *glink,
                 double2 *gUnu, int mu, int nu, int part = 3) {
   if (b.split) {
-    x.run(b.nsites, StapleBwdLinkSite{b.g, H, hs, Unu, glink, b.fs, mu, nu, part});
-    x.run(b.nsites, StapleBwdUSite{b.g, H, hs, link, Unu, gUnu, b.fs, mu, nu, part});
+    if (part & 1) {
+      x.run(b.nsites, StapleBwdLinkSite<1>{b.g, H, hs, Unu, glink, b.fs, mu, nu});
+      x.run(b.nsites, StapleBwdUSite<1>{b.g, H, hs, link, Unu, gUnu, b.fs, mu, nu});
+    }
+    if (part & 2) {
+      x.run(b.nsites, StapleBwdLinkSite<2>{b.g, H, hs, Unu, glink, b.fs, mu, nu});
+      x.run(b.nsites, StapleBwdUSite<2>{b.g, H, hs, link, Unu, gUnu, b.fs, mu, nu});
+    }
   } else {
     x.run(b.nsites, StapleBwdSite{b.g, H, hs, link, Unu, glink, gUnu, b.fs, mu, nu, part});
   }

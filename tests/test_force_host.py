@@ -98,10 +98,10 @@ def test_force_filter_matches_reference_on_rough_links(host_force):
     mom = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE, 5.0e-5)
     assert np.abs(mom - g["mom"]).max() <= 1e-9 * scale
     assert np.abs(mom - lo.hisq_force(dims, U, X, res, float(g["eps"]))).max() <= 1e-11 * scale
-    # the two-kernel form of the backward staple passes (ForceBufs::split): the same sums in the same order
+    # the split form of the backward staple passes (ForceBufs::split)
     two = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE,
                5.0e-5, split=True)
-    assert np.array_equal(two, mom)
+    assert np.abs(two - mom).max() <= 1e-12 * scale
     # the filter is what makes the difference on this input, and switching it off matches the oracle's unfiltered force
     raw = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE, 0.0)
     assert np.abs(raw - g["mom"]).max() > 0.1 * scale
