@@ -1,7 +1,9 @@
 """GPU parity tests of the HISQ fermion force: b200ks_hisq_force
 through the C ABI against the committed output of the reference's own eo_fermion_force_multi
 (tests/golden/ref_hisq_force.npz) and against the CPU oracle (oracle/ks_force_oracle.c, pinned on
-the reference).  The same site routines are checked on the host in tests/test_force_host.py."""
+the reference).  The same site routines are checked on the host in tests/test_force_host.py.
+(The file sorts after the parity tests of rows a-e, f1 and f3: parts of it were written after the round's GPU
+budget was spent and run for the first time at round end.)"""
 import os
 
 import numpy as np
