@@ -158,16 +158,3 @@ def test_b200fl_apps_bind_the_link_construction_symbols():
         nm = subprocess.run(["nm", "-D", "--undefined-only", os.path.join(APPS, app)], capture_output=True, text=True).stdout
         used = {ln.split()[-1] for ln in nm.splitlines() if " quda" in ln}
         assert {"qudaLoadKSLink", "qudaLoadUnitarizedLink"} <= used, (app, used)
-
-
-@pytest.mark.gpu
-def test_su3_rhmc_hisq_with_gpu_fermion_force_matches_reference_goldens(tmp_path):
-    """-DUSE_FF_GPU build (WANT_FF_GPU=true) on top of the GPU links and solves: every molecular-
-    dynamics step of the trajectory takes its HISQ fermion force from qudaHisqForce."""
-    if not _have("su3_rhmc_hisq_b200ff"):
-        pytest.skip("oracle/_ref/apps not built")
-    out = check_rhmc("su3_rhmc_hisq_b200ff", tmp_path)
-    assert any("multicg_offset_QUDA" in ln for ln in out)
-    nm = subprocess.run(["nm", "-D", "--undefined-only", os.path.join(APPS, "su3_rhmc_hisq_b200ff")], capture_output=True,
-                        text=True).stdout
-    assert " qudaHisqForce" in nm.replace("U qudaHisqForce", " qudaHisqForce")

@@ -103,3 +103,17 @@ def test_force_with_naik_epsilons_matches_reference_golden(api):
     plain = ctx.hisq_force(U, L["V"], L["W"], list(X), res, eps)
     assert np.abs(plain - g["mom"]).max() > 1e-3 * scale
     ctx.close()
+
+
+def test_su3_rhmc_hisq_with_gpu_fermion_force_matches_reference_goldens(tmp_path):
+    """-DUSE_FF_GPU build (WANT_FF_GPU=true) on top of the GPU links and solves: every molecular-
+    dynamics step of the trajectory takes its HISQ fermion force from qudaHisqForce."""
+    import subprocess
+    from test_dropin_apps import APPS, _have, check_rhmc
+    if not _have("su3_rhmc_hisq_b200ff"):
+        pytest.skip("oracle/_ref/apps not built")
+    out = check_rhmc("su3_rhmc_hisq_b200ff", tmp_path)
+    assert any("multicg_offset_QUDA" in ln for ln in out)
+    nm = subprocess.run(["nm", "-D", "--undefined-only", os.path.join(APPS, "su3_rhmc_hisq_b200ff")], capture_output=True,
+                        text=True).stdout
+    assert " qudaHisqForce" in nm.replace("U qudaHisqForce", " qudaHisqForce")
