@@ -2279,7 +2279,7 @@ extern "C" int b200ks_eig_set(b200ks_ctx *c, int nvecs, const int *vecs, const d
     for (int p = 0; p < 2; p++) hp[p].push_back((const double2 *)v->p[p]);
   }
   EigSet &e = c->eig;
-  e.nchunks = std::min(nblocks(c->g.Vh), 296);   // two CTAs per SM walk the vectors
+  e.nchunks = std::min(nblocks(c->g.Vh), 1184);   // eight 128-thread CTAs per SM (64 registers each) walk the vectors
   void *q = nullptr;
   int r = dev_alloc(c, &q, sizeof(double) * nvecs);
   e.d_val = (double *)q;

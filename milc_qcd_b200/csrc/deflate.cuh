@@ -8,7 +8,7 @@
 // On the host that is 2 Num sweeps over Num vectors (0.5 s for 500 modes at 32^3 x 64, more than the
 // whole solve takes here); with the vectors resident (50 MB per vector and parity at 32^3 x 64:
 // 500 modes = 50 GB of the 180 GB) it is two passes over them at HBM speed:
-//   eig_dot_kernel   every CTA owns a contiguous chunk of sites and walks the vectors: per vector
+//   eig_dot_kernel   every CTA (8 per SM) owns a contiguous chunk of sites and walks the vectors: per vector
 //                    the four sums re/im <v|src>, re/im <v|dst> over its chunk -> partials[j][chunk][4]
 //   eig_coef_kernel  one thread per vector adds its chunks in order (deterministic) and forms
 //                    c_j = <v_j|src>/(lambda_j + 4 m^2) - <v_j|dst>

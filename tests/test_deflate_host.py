@@ -31,7 +31,7 @@ def host_deflate():
     return lib
 
 
-@pytest.mark.parametrize("nvecs,nchunks", [(1, 1), (16, 7), (48, 296)])
+@pytest.mark.parametrize("nvecs,nchunks", [(1, 1), (16, 7), (48, 296), (8, 1184)])
 def test_deflate_site_routines_match_oracle(host_deflate, nvecs, nchunks):
     import sys
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
