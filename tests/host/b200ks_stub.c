@@ -1,0 +1,124 @@
+/* tests/host/b200ks_stub.c -- TEST INFRASTRUCTURE.  A recording stand-in for the part of the b200ks C ABI
+ * (include/b200ks.h) that milc_qcd_b200/csrc_milc/milc_shim.c calls, so that tests/test_milc_shim_host.py can
+ * exercise the shim's host logic (qic bookkeeping, zero-source shortcut, link-cache decisions, eigenvector
+ * hand-over and the qic->deflate switch) without a GPU.  Nothing here computes physics: the "solvers" copy the
+ * source into the solution on the requested parity and return canned iteration counts and residuals.
+ * Built by the test:  gcc -shared -fPIC -Iinclude milc_shim.c tests/host/b200ks_stub.c -o libmilc_shim_stub.so */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "b200ks.h"
+
+static char s_log[1 << 16];
+static size_t s_len = 0;
+static int s_dims[4];
+static int s_next_vec = 0, s_live_vecs = 0;
+static int s_fail_next = 0;
+
+static void logf_(const char *fmt, ...);
+#include <stdarg.h>
+static void logf_(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  s_len += (size_t)vsnprintf(s_log + s_len, sizeof(s_log) - s_len, fmt, ap);
+  va_end(ap);
+  if (s_len >= sizeof(s_log)) s_len = sizeof(s_log) - 1;
+}
+const char *stub_log(void) { return s_log; }
+void stub_reset(void) { s_len = 0; s_log[0] = 0; }
+void stub_fail_next(int code) { s_fail_next = code; }
+int stub_live_vecs(void) { return s_live_vecs; }
+
+static size_t sites(void) { return (size_t)s_dims[0] * s_dims[1] * s_dims[2] * s_dims[3]; }
+
+b200ks_ctx *b200ks_create(const int latsize[4], int device) {
+  memcpy(s_dims, latsize, sizeof(s_dims));
+  logf_("create %d %d %d %d dev %d\n", latsize[0], latsize[1], latsize[2], latsize[3], device);
+  return (b200ks_ctx *)s_dims;
+}
+void b200ks_destroy(b200ks_ctx *c) { (void)c; logf_("destroy\n"); s_live_vecs = 0; }
+const char *b200ks_last_error(void) { return "stub error"; }
+unsigned long long b200ks_fingerprint(const void *p, size_t bytes) {
+  const unsigned char *b = (const unsigned char *)p;
+  unsigned long long h = 1469598103934665603ull;
+  size_t i;
+  for (i = 0; i < bytes; i++) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+int b200ks_load_links(b200ks_ctx *c, const void *fat, const void *lng, int host_prec, int long_recon) {
+  (void)c; (void)fat; (void)lng;
+  logf_("load_links prec %d recon %d\n", host_prec, long_recon);
+  return 0;
+}
+static void fill(b200ks_invert_result *r, int iters) {
+  memset(r, 0, sizeof(*r));
+  r->final_rsq = 1e-20; r->final_relrsq = 0; r->size_r = 2e-20; r->size_relr = 0;
+  r->final_iters = iters; r->final_restart = 1; r->converged = 1;
+}
+static void copy_parity(void *dst, const void *src, int parity, int host_prec) {
+  const size_t vb = (size_t)6 * (host_prec == 2 ? 8 : 4), h = sites() / 2;
+  if (parity & B200KS_EVEN) memcpy(dst, src, h * vb);
+  if (parity & B200KS_ODD) memcpy((char *)dst + h * vb, (const char *)src + h * vb, h * vb);
+}
+int b200ks_congrad(b200ks_ctx *c, const void *src, void *dest, double mass, const b200ks_invert_args *a,
+                   b200ks_invert_result *r, int host_prec) {
+  (void)c;
+  logf_("congrad mass %g parity %d max %d nrestart %d resid %g relresid %g mixed %d prec %d\n", mass, a->parity, a->max_iter,
+        a->nrestart, a->resid, a->relresid, a->mixed_precision, host_prec);
+  if (s_fail_next) { int e = s_fail_next; s_fail_next = 0; return e; }
+  copy_parity(dest, src, a->parity, host_prec);
+  fill(r, 17);
+  return 17;
+}
+int b200ks_congrad_block(b200ks_ctx *c, int nsrc, const void *const *src, void *const *dest, double mass,
+                         const b200ks_invert_args *a, b200ks_invert_result *r, int host_prec) {
+  int k;
+  (void)c;
+  logf_("congrad_block nsrc %d mass %g parity %d\n", nsrc, mass, a->parity);
+  for (k = 0; k < nsrc; k++) { copy_parity(dest[k], src[k], a->parity, host_prec); fill(&r[k], 10 + k); }
+  return 10 * nsrc + nsrc * (nsrc - 1) / 2;
+}
+int b200ks_multicg(b200ks_ctx *c, const void *src, void *const *psim, const double *offsets, int n,
+                   const b200ks_invert_args *a, b200ks_invert_result *r, int host_prec) {
+  int j;
+  (void)c;
+  logf_("multicg n %d parity %d offsets", n, a->parity);
+  for (j = 0; j < n; j++) { logf_(" %g", offsets[j]); copy_parity(psim[j], src, a->parity, host_prec); fill(&r[j], 23); }
+  logf_("\n");
+  return 23;
+}
+int b200ks_dslash(b200ks_ctx *c, const void *src, void *dest, int parity, int host_prec) {
+  (void)c;
+  logf_("dslash parity %d\n", parity);
+  copy_parity(dest, src, parity, host_prec);
+  return 0;
+}
+int b200ks_mat_invert_uml(b200ks_ctx *c, int nsrc, const void *const *src, void *const *dst, double mass,
+                          const b200ks_invert_args *a, b200ks_invert_result *r, int host_prec) {
+  int k;
+  (void)c; (void)a;
+  logf_("mat_invert_uml nsrc %d mass %g\n", nsrc, mass);
+  for (k = 0; k < nsrc; k++) {
+    copy_parity(dst[k], src[k], B200KS_EVENANDODD, host_prec);
+    fill(&r[2 * k], 30); fill(&r[2 * k + 1], 3);
+  }
+  return 33 * nsrc;
+}
+int b200ks_vec_create(b200ks_ctx *c) { (void)c; s_live_vecs++; logf_("vec_create -> %d\n", s_next_vec); return s_next_vec++; }
+int b200ks_vec_free(b200ks_ctx *c, int v) { (void)c; s_live_vecs--; logf_("vec_free %d\n", v); return 0; }
+int b200ks_vec_upload(b200ks_ctx *c, int v, const void *host, int parity, int host_prec) {
+  (void)c;
+  logf_("vec_upload %d parity %d prec %d first %g\n", v, parity, host_prec,
+        host_prec == 2 ? *(const double *)host : (double)*(const float *)host);
+  return 0;
+}
+int b200ks_eig_set(b200ks_ctx *c, int n, const int *vecs, const double *eigval, int use_in_uml) {
+  int j;
+  (void)c;
+  logf_("eig_set n %d uml %d", n, use_in_uml);
+  for (j = 0; j < n; j++) logf_(" (%d %g)", vecs[j], eigval[j]);
+  logf_("\n");
+  return 0;
+}
+int b200ks_eig_use_in_uml(b200ks_ctx *c, int on) { (void)c; logf_("eig_use_in_uml %d\n", on); return 0; }
