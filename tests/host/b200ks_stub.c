@@ -122,3 +122,30 @@ int b200ks_eig_set(b200ks_ctx *c, int n, const int *vecs, const double *eigval, 
   return 0;
 }
 int b200ks_eig_use_in_uml(b200ks_ctx *c, int on) { (void)c; logf_("eig_use_in_uml %d\n", on); return 0; }
+
+/* ---- the rest of what csrc/quda_shim.cu (route 2) calls ---------------------------------------------- */
+int b200ks_device_count(void) { return 1; }
+int b200ks_hisq_force(b200ks_ctx *c, int nterms, int num_naik_terms, const double *coeff, const void *const *multi_x,
+                      const double *level2_coeff, const double *fat7_coeff, const void *wlink, const void *vlink,
+                      const void *ulink, double eps, double force_filter, void *momentum, int host_prec) {
+  int j;
+  (void)c; (void)wlink; (void)vlink; (void)ulink; (void)momentum;
+  logf_("hisq_force nterms %d naik %d eps %g filter %g prec %d coeff", nterms, num_naik_terms, eps, force_filter, host_prec);
+  for (j = 0; j < 2 * (nterms + num_naik_terms); j++) logf_(" %g", coeff[j]);
+  logf_(" x0");
+  for (j = 0; j < nterms; j++) logf_(" %g", host_prec == 2 ? *(const double *)multi_x[j] : (double)*(const float *)multi_x[j]);
+  logf_(" l2 %g %g f7 %g %g\n", level2_coeff[0], level2_coeff[5], fat7_coeff[0], fat7_coeff[2]);
+  return 0;
+}
+int b200ks_ks_links(b200ks_ctx *c, const double *coeffs, const void *links, void *fat, void *lng, int host_prec) {
+  (void)c; (void)links; (void)fat;
+  logf_("ks_links c0 %g naik %g long %d prec %d\n", coeffs[0], coeffs[1], lng != NULL, host_prec);
+  return 0;
+}
+int b200ks_unitarized_links(b200ks_ctx *c, const double *coeffs, const void *links, void *vlink, void *wlink, int host_prec,
+                            long long *nsvd) {
+  (void)c; (void)links; (void)wlink;
+  logf_("unitarized_links c0 %g v %d prec %d\n", coeffs[0], vlink != NULL, host_prec);
+  if (nsvd) *nsvd = 0;
+  return 0;
+}
