@@ -112,3 +112,61 @@ l = call()
 assert 'filter 5e-05' in l[0], l
 print('HOST-OK')
 """)
+
+
+def test_multishift_block_dslash_and_link_construction_marshalling(shim_so):
+    _run(shim_so, r"""
+class FatLinkArgs(C.Structure):
+    _fields_ = [("su3_source", C.c_int)]
+rng = np.random.default_rng(2)
+fat, lng = rng.standard_normal((V, 4, 18)), rng.standard_normal((V, 4, 18))
+src = rng.standard_normal((V, 6))
+# multi-shift: the cap is the product (no restarts), convergence on target_residual[0], one residual per shift
+n = 3
+off = (C.c_double * n)(0.01, 0.04, 0.25)
+tr = (C.c_double * n)(1e-6, 1e-5, 1e-4)
+trf = (C.c_double * n)(0, 0, 0)
+sols = [np.zeros((V, 6)) for _ in range(n)]
+sp = (C.c_void_p * n)(*[s.ctypes.data for s in sols])
+fr, ffr, it = (C.c_double * n)(), (C.c_double * n)(), C.c_int(-1)
+lib.qudaMultishiftInvert.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), InvertArgs, C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+lib.qudaMultishiftInvert(2, 2, n, off, InvertArgs(2500, 0, 0), tr, trf, fat.ctypes.data, lng.ctypes.data, src.ctypes.data, sp,
+                         fr, ffr, C.byref(it))
+l = log()
+assert any(x == 'multicg n 3 parity 2 offsets 0.01 0.04 0.25' for x in l), l
+assert it.value == 23 and all(abs(fr[j] - 1e-10) < 1e-24 and ffr[j] == 0 for j in range(n))
+assert all(np.array_equal(s[:V // 2], src[:V // 2]) for s in sols)
+# block solve: every source to b200ks_congrad_block, worst residual and the total iteration count back
+ns = 3
+srcs = [rng.standard_normal((V, 6)) for _ in range(ns)]
+dsts = [np.zeros((V, 6)) for _ in range(ns)]
+sa = (C.c_void_p * ns)(*[s.ctypes.data for s in srcs])
+da = (C.c_void_p * ns)(*[d.ctypes.data for d in dsts])
+res, rel = C.c_double(), C.c_double()
+lib.qudaInvertMsrc.argtypes = [C.c_int, C.c_int, C.c_double, InvertArgs, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                               C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                               C.POINTER(C.c_int), C.c_int]
+lib.qudaInvertMsrc(2, 2, 0.1, InvertArgs(1000, 0, 0), 1e-8, 0.0, fat.ctypes.data, lng.ctypes.data, sa, da, C.byref(res),
+                   C.byref(rel), C.byref(it), ns)
+l = log()
+assert any(x == 'congrad_block nsrc 3 mass 0.1 parity 2' for x in l) and not any(x.startswith('load_links') for x in l), l
+assert it.value == 33 and abs(res.value - 1e-10) < 1e-24
+# dslash
+out = np.zeros((V, 6))
+lib.qudaDslash.argtypes = [C.c_int, C.c_int, InvertArgs, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+lib.qudaDslash(2, 2, InvertArgs(0, 1, 0), fat.ctypes.data, lng.ctypes.data, src.ctypes.data, out.ctypes.data, C.byref(it))
+assert 'dslash parity 1' in log() and it.value == 0
+# link construction: coefficients and the optional outputs pass through
+coef = (C.c_double * 6)(1.0, -1 / 24, -1 / 16, 1 / 64, -1 / 384, -1 / 8)
+U, F, L = (np.zeros((V, 4, 18)) for _ in range(3))
+lib.qudaLoadKSLink.argtypes = [C.c_int, FatLinkArgs, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p]
+lib.qudaLoadKSLink(2, FatLinkArgs(1), coef, U.ctypes.data, F.ctypes.data, L.ctypes.data)
+lib.qudaLoadKSLink(1, FatLinkArgs(1), coef, U.ctypes.data, F.ctypes.data, None)
+lib.qudaLoadUnitarizedLink.argtypes = lib.qudaLoadKSLink.argtypes
+lib.qudaLoadUnitarizedLink(2, FatLinkArgs(1), coef, U.ctypes.data, None, L.ctypes.data)
+assert log() == ['ks_links c0 1 naik -0.0416667 long 1 prec 2', 'ks_links c0 1 naik -0.0416667 long 0 prec 1',
+                 'unitarized_links c0 1 v 0 prec 2']
+print('HOST-OK')
+""")
