@@ -42,7 +42,9 @@ def shim():
     srcs = [os.path.join(ROOT, "milc_qcd_b200", "csrc_milc", "milc_shim.c"), os.path.join(HOST_DIR, "b200ks_stub.c")]
     deps = srcs + [os.path.join(ROOT, "include", f) for f in ("b200ks.h", "b200ks_milc.h")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(f) for f in deps):
-        subprocess.check_call(["gcc", "-O1", "-fPIC", "-shared", "-std=gnu99", "-Wall", "-DMILC_PRECISION=2",
+        # -Bsymbolic: the shim's calls bind to the stub in this .so even if the real libb200ks.so is already
+        # loaded globally in the test process (it would fail without a GPU and terminate the run, as designed)
+        subprocess.check_call(["gcc", "-O1", "-fPIC", "-shared", "-std=gnu99", "-Wall", "-Wl,-Bsymbolic", "-DMILC_PRECISION=2",
                                "-I", os.path.join(ROOT, "include"), "-o", SO] + srcs)
     lib = C.CDLL(SO)
     lib.stub_log.restype = C.c_char_p

@@ -27,7 +27,7 @@ def shim_so():
         obj = os.path.join(HOST_DIR, "b200ks_stub.o")
         subprocess.check_call(["gcc", "-O1", "-fPIC", "-std=gnu99", "-I", os.path.join(ROOT, "include"), "-c", stub, "-o", obj])
         subprocess.check_call(["nvcc", "-O1", "-std=c++17", "-x", "cu", "--shared", "-Xcompiler", "-fPIC",
-                               "-Wno-deprecated-gpu-targets", "-o", SO, src, "-Xlinker", obj])
+                               "-Wno-deprecated-gpu-targets", "-Xlinker", "-Bsymbolic", "-o", SO, src, "-Xlinker", obj])
     return SO
 
 
