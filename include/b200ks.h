@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define B200KS_VERSION 111 /* 110: block solve, resident sequences, link construction; 111: force filter, Naik epsilons, deflation */
+#define B200KS_VERSION 120 /* 110: block solve, resident sequences, link construction; 111: force filter, Naik epsilons, deflation;
+                              120: single-process multi-GPU contexts, b200ks_links_sync, flag-based reductions */
 
 /* parity codes, include/macros.h:68-70 */
 #define B200KS_EVEN 2
@@ -100,6 +101,22 @@ b200ks_ctx *b200ks_create(const int latsize[4], int device);
 b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4], int rank, int nranks,
                                const void *nccl_unique_id, int device);
 int b200ks_comm_unique_id(void *out128);
+
+/* Single-process multi-GPU context ("single process / N devices, MILC runs as
+ * one vanilla rank and never sees the decomposition"; the reference hands QUDA its machine grid in
+ * generic/milc_to_quda_utilities.c:13-36, the split itself is generic/layout_hyper_prime.c:186-229).
+ * The lattice is split over ngpu devices (devices[0..ngpu-1], NULL = 0..ngpu-1) in t first (up to 4
+ * ways), then z; local extents must be even and >= 6.  Every device gets an ordinary partitioned
+ * context driven by its own host thread -- the same kernels, peer-to-peer halo pushes and flag-based
+ * reductions as the one-rank-per-GPU form, over plain peer access instead of CUDA IPC, no NCCL.  The
+ * returned context takes the SAME host arrays as a single-GPU context (MILC's global layout): every
+ * device reads and writes its own sub-lattice straight from / to them.  Solves, dslash, the resident
+ * sequences and the device-vector interface run decomposed; link construction and the fermion force
+ * run on a full-lattice context on devices[0]; deflation is refused.
+ * B200KS_NGPU=N in the environment makes b200ks_create (what both MILC-facing shims call) behave as
+ * b200ks_create_multi(latsize, N, {device, device+1, ...}). */
+b200ks_ctx *b200ks_create_multi(const int latsize[4], int ngpu, const int *devices);
+int b200ks_num_gpus(b200ks_ctx *ctx);
 /* How this context exchanges halos: 0 = nothing partitioned, 1 = ncclSend/ncclRecv,
  * 2 = peer-to-peer pushes into the neighbours' mapped ghost buffers (default; set
  * B200KS_HALO=nccl to force 1).  B200KS_FORCE_PARTITION=z|t|zt makes b200ks_create_dist treat
@@ -124,13 +141,25 @@ void b200ks_destroy(b200ks_ctx *ctx);
  * 16-byte word the kernels load; 14 keeps 89 % of its traffic saving.) */
 int b200ks_load_links(b200ks_ctx *ctx, const void *fat, const void *lng, int host_prec,
                       int long_recon);
-/* 64-bit content fingerprint of a host array (threaded, memory-bandwidth bound).  The MILC-facing
- * shims compare it with the fingerprint taken at the last upload to notice in-place edits of the
- * link arrays that MILC does not announce (boundary_twist_fn,
- * generic_ks/fermion_links_fn_twist_milc.c:318-400) without re-uploading on every call.  Note: the
- * result depends on the number of host threads only through how the array is split; it is stable
- * within a process. */
+/* 64-bit content fingerprint of a host array (threaded, memory-bandwidth bound; every word passes a
+ * non-linear mixing step, so whole time slices of sign flips -- boundary_twist_fn -- are seen). */
 unsigned long long b200ks_fingerprint(const void *host, size_t bytes);
+/* Keeps the device links in step with MILC's host arrays; what both shims call before every solve
+ * instead of b200ks_load_links.  Replaces the refresh logic of the QUDA seam
+ * (generic_ks/d_congrad5_fn_gpu.c:121-126: fn pointer + notify flag), which misses the in-place edits of
+ * boundary_twist_fn (generic_ks/fermion_links_fn_twist_milc.c:318-400).
+ *   changed_hint != 0, other arrays or precision than at the last sync, or nothing loaded: upload now
+ *   (fingerprints taken beside the upload); returns 1.
+ *   otherwise, by mode:
+ *     0  trust the hint (the reference's own behaviour); returns 0
+ *     1  upload anyway; returns 1
+ *     2  verify in the background: host threads fingerprint both arrays WHILE the next host-buffer call
+ *        (b200ks_congrad, _congrad_block, _multicg, _dslash, _mat_invert_uml, _multicg_rational) computes on
+ *        the resident links; that call joins the verification before it hands anything back and, if the
+ *        arrays did change, uploads them and repeats its computation.  Returns 0.
+ *     3  verify now (blocking); returns 1 if the links had changed and were uploaded. */
+int b200ks_links_sync(b200ks_ctx *ctx, const void *fat, const void *lng, int host_prec, int changed_hint, int mode);
+int b200ks_links_sync_stats(b200ks_ctx *ctx, long long *uploads, long long *verifications);
 /* Storage chosen for the long links (7 or 9 complex per link) and the worst misfit measured
  * by the load-time test (-1 when long_recon == 18 skipped it). */
 int b200ks_long_link_info(b200ks_ctx *ctx, int *ncomplex_per_link, double *misfit);

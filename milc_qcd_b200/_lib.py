@@ -35,6 +35,10 @@ SYMBOLS = [
     ("b200ks_create_dist", C.c_void_p, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int,
                                         C.c_void_p, C.c_int]),
     ("b200ks_comm_unique_id", C.c_int, [C.c_void_p]),
+    ("b200ks_create_multi", C.c_void_p, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
+    ("b200ks_num_gpus", C.c_int, [C.c_void_p]),
+    ("b200ks_links_sync", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    ("b200ks_links_sync_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     ("b200ks_destroy", None, [C.c_void_p]),
     ("b200ks_load_links", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     ("b200ks_fingerprint", C.c_ulonglong, [C.c_void_p, C.c_size_t]),

@@ -12,6 +12,9 @@
 #include <cstring>
 #include <cmath>
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -60,6 +63,21 @@ struct EigSet {           // low modes resident in HBM (row f4): user vectors, b
   bool uml = false;                                 // the resident UML sequences deflate their trial solutions
 };
 
+// Host link arrays the device links mirror (b200ks_links_sync): identity, content fingerprints at
+// the last upload, and the verification of the current content that runs on host threads while a
+// solve iterates.
+struct LinkWatch {
+  const void *fat = nullptr, *lng = nullptr;
+  int host_prec = 0, long_recon = 0;
+  size_t bytes = 0;
+  unsigned long long fp[2] = {0, 0};
+  bool have = false;
+  std::thread th;
+  bool pending = false;
+  unsigned long long now[2] = {0, 0};
+  long long reloads = 0, verifications = 0;
+};
+
 struct b200ks_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -90,7 +108,95 @@ struct b200ks_ctx {
   void *bounce[2] = {nullptr, nullptr};          // pinned bounce buffers for pageable host arrays
   cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
   EigSet eig;
+  LinkWatch watch;
+  // where this context's sub-lattice sits in the host arrays it is handed, in sites of one parity
+  // block (HostRows below): a plain context owns the whole block; a member of a multi-GPU context
+  // owns hv_nrows runs of hv_row_sites sites inside MILC's global array
+  size_t hv_row_sites = 0, hv_nrows = 1, hv_pitch_sites = 0, hv_offset_sites = 0, hv_parity_sites = 0;
+  // single-process multi-GPU context (b200ks_create_multi): the leader owns one member context
+  // per device, each driven by its own host thread
+  std::vector<b200ks_ctx *> sub;
+  struct MultiState *multi = nullptr;   // leader: worker threads; member: the shared bootstrap area
+  b200ks_ctx *aux = nullptr;            // leader: full-lattice context on the first device for the
+                                        // operations that do not run partitioned yet (links, force)
+  int member_rank = -1;                 // >= 0: member of a multi-GPU context
 };
+
+// ---- single-process multi-GPU contexts (b200ks_create_multi) -------------------------------------
+// MILC runs as ONE vanilla rank and never sees the decomposition.  The
+// leader context owns one member context per device; every member is an ordinary partitioned
+// context (the same kernels, peer-to-peer halos and flag-based reductions as a one-rank-per-GPU run)
+// driven by its own host thread, and reads / writes ITS sub-lattice straight from / to MILC's
+// global host arrays (HostRows).  run_all hands one closure to all member threads and returns
+// member 0's result (the solver scalars are bit-identical on every member) or the first error.
+struct HostBarrier {
+  std::mutex mu;
+  std::condition_variable cv;
+  int n = 1, waiting = 0;
+  unsigned long long phase = 0;
+  bool aborted = false;
+  // false: some member failed and will never arrive (abort()); the caller must fail too
+  bool arrive_and_wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    if (aborted) return false;
+    const unsigned long long ph = phase;
+    if (++waiting == n) { waiting = 0; phase++; cv.notify_all(); }
+    else cv.wait(lk, [&] { return phase != ph || aborted; });
+    return !aborted;
+  }
+  void abort() {
+    std::unique_lock<std::mutex> lk(mu);
+    aborted = true;
+    cv.notify_all();
+  }
+};
+#define MEET(ms)                                                                                              \
+  do {                                                                                                        \
+    if (!(ms)->barrier.arrive_and_wait())                                                                     \
+      return fail(B200KS_ECOMM, "another member of the multi-GPU context failed");                            \
+  } while (0)
+
+struct MultiState {
+  int n = 0;
+  std::vector<int> devices;
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  std::function<int(b200ks_ctx *, int)> task;
+  unsigned long long gen = 0;
+  int remaining = 0;
+  bool quit = false;
+  std::vector<int> rc;
+  std::vector<std::string> err;
+  // in-process replacement for the NCCL / CUDA-IPC handshakes of the one-rank-per-GPU bootstrap
+  std::vector<void *> slot;
+  HostBarrier barrier;
+};
+
+static void watch_join_thread(b200ks_ctx *c);
+static int nmembers(const b200ks_ctx *c) { return c->sub.empty() ? 1 : (int)c->sub.size(); }
+
+template <typename F>
+static int run_all(b200ks_ctx *c, F f) {
+  if (c->sub.empty()) return f(c, 0);
+  MultiState *ms = c->multi;
+  std::unique_lock<std::mutex> lk(ms->mu);
+  ms->task = f;
+  ms->remaining = ms->n;
+  ms->gen++;
+  ms->cv_go.notify_all();
+  ms->cv_done.wait(lk, [&] { return ms->remaining == 0; });
+  ms->task = nullptr;
+  for (int r = 0; r < ms->n; r++)
+    if (ms->rc[r] < 0) return fail(ms->rc[r], "[GPU " + std::to_string(ms->devices[r]) + "] " + ms->err[r]);
+  return ms->rc[0];
+}
+// forwards an entry point to every member (the body names the member `c`, its rank `r_`)
+#define MULTI(c, expr)                                                            \
+  do {                                                                            \
+    if ((c) && !(c)->sub.empty())                                                 \
+      return run_all((c), [&](b200ks_ctx *c, int r_) -> int { (void)r_; return (expr); }); \
+  } while (0)
 
 static size_t real_size(int prec) { return prec == B200KS_PREC_DOUBLE ? 8 : prec == B200KS_PREC_SINGLE ? 4 : 2; }
 
@@ -113,6 +219,15 @@ cudaStream_t b200ks_host::stream(const b200ks_ctx *c) { return c->stream; }
 int b200ks_host::device(const b200ks_ctx *c) { return c->device; }
 bool b200ks_host::partitioned(const b200ks_ctx *c) { return c->comm.active; }
 void b200ks_host::count_launch(b200ks_ctx *c) { c->launches++; }
+static b200ks_ctx *create_common(const int latsize[4], const int local[4], const int part[4], const int origin[4], int device);
+b200ks_ctx *b200ks_host::single_gpu_ctx(b200ks_ctx *c) {
+  if (!c || c->sub.empty()) return c;
+  if (!c->aux) {
+    const int part[4] = {0, 0, 0, 0}, origin[4] = {0, 0, 0, 0};
+    c->aux = create_common(c->global, c->global, part, origin, c->device);
+  }
+  return c->aux;
+}
 void *&b200ks_host::link_work(b200ks_ctx *c) { return c->lw; }
 
 // half (prec 0): 4 planes of 32-bit words (3 colours as 2 x u16 + the site scale), half.cuh
@@ -140,21 +255,6 @@ int b200ks_host::stage_get(b200ks_ctx *c, size_t bytes, void **out) {
 // DMA of the other buffer.  Pinned (qudaAllocatePinned / cudaHostRegister'ed) arrays go direct.
 constexpr size_t kBounceBytes = (size_t)32 << 20;
 
-static void parallel_memcpy(void *dst, const void *src, size_t n) {
-  static const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
-  const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, n >> 20));
-  if (nt <= 1) { memcpy(dst, src, n); return; }
-  std::vector<std::thread> th;
-  const size_t per = (n / nt + 63) & ~(size_t)63;
-  for (unsigned t = 0; t < nt; t++) {
-    const size_t o = (size_t)t * per;
-    if (o >= n) break;
-    const size_t m = std::min(per, n - o);
-    th.emplace_back([=]() { memcpy((char *)dst + o, (const char *)src + o, m); });
-  }
-  for (auto &t : th) t.join();
-}
-
 static bool host_is_pinned(const void *p) {
   cudaPointerAttributes at;
   const cudaError_t e = cudaPointerGetAttributes(&at, p);
@@ -171,10 +271,69 @@ static int bounce_get(b200ks_ctx *c) {
   return 0;
 }
 
+// A host field as this context sees it: `nrows` runs of `row_bytes` bytes, `pitch_bytes` apart.
+// A single-GPU context reads one run (the parity block).  A member of a single-process multi-GPU
+// context (b200ks_create_multi) reads ITS sub-lattice straight out of MILC's global array: local
+// cb index = r + S2h*(z + Lz*t) sits at global cb index r + S2h*((z+oz) + Gz*(t+ot)), i.e. one run
+// of Lz*S2h sites per local time slice, Gz*S2h sites apart (one run in all for a pure t split).
+struct HostRows {
+  size_t row_bytes, nrows, pitch_bytes;
+  size_t total() const { return row_bytes * nrows; }
+};
+
+// parity block `p` (0 even, 1 odd) of a host field with `site_bytes` bytes per site, as context c sees it
+static const char *host_half(const b200ks_ctx *c, const void *base, int p, size_t site_bytes, HostRows &hr) {
+  hr.row_bytes = c->hv_row_sites * site_bytes;
+  hr.nrows = c->hv_nrows;
+  hr.pitch_bytes = c->hv_pitch_sites * site_bytes;
+  return (const char *)base + ((size_t)p * c->hv_parity_sites + c->hv_offset_sites) * site_bytes;
+}
+
+// copies bytes [off, off+n) of the virtual concatenation of the rows to / from a contiguous buffer
+static void rows_gather(void *dst, const char *base, const HostRows &hr, size_t off, size_t n) {
+  char *d = (char *)dst;
+  while (n > 0) {
+    const size_t row = off / hr.row_bytes, in = off - row * hr.row_bytes;
+    const size_t m = std::min(n, hr.row_bytes - in);
+    memcpy(d, base + row * hr.pitch_bytes + in, m);
+    d += m; off += m; n -= m;
+  }
+}
+static void rows_scatter(char *base, const HostRows &hr, size_t off, const void *src, size_t n) {
+  const char *s = (const char *)src;
+  while (n > 0) {
+    const size_t row = off / hr.row_bytes, in = off - row * hr.row_bytes;
+    const size_t m = std::min(n, hr.row_bytes - in);
+    memcpy(base + row * hr.pitch_bytes + in, s, m);
+    s += m; off += m; n -= m;
+  }
+}
+// the same, split over a few host threads (one bounce chunk)
+template <typename F>
+static void parallel_chunks(size_t n, F f) {
+  static const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, n >> 20));
+  if (nt <= 1) { f((size_t)0, n); return; }
+  std::vector<std::thread> th;
+  const size_t per = (n / nt + 63) & ~(size_t)63;
+  for (unsigned t = 0; t < nt; t++) {
+    const size_t o = (size_t)t * per;
+    if (o >= n) break;
+    const size_t m = std::min(per, n - o);
+    th.emplace_back([=]() { f(o, m); });
+  }
+  for (auto &t : th) t.join();
+}
+
 // stream-ordered on c->stream; returns after the host array has been read completely
-int b200ks_host::h2d(b200ks_ctx *c, void *dst, const void *src, size_t bytes) {
+// (pinned host arrays: after the copy has been enqueued -- the caller keeps them alive until the
+// next synchronisation of the stream, which every entry point reaches before it returns)
+static int h2d_rows(b200ks_ctx *c, void *dst, const void *src, const HostRows &hr) {
+  const size_t bytes = hr.total();
+  const bool one = hr.nrows == 1 || hr.row_bytes == hr.pitch_bytes;
   if (bytes < (kBounceBytes >> 2) || host_is_pinned(src) || bounce_get(c) < 0) {
-    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (one) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    else CU(cudaMemcpy2DAsync(dst, hr.row_bytes, src, hr.pitch_bytes, hr.row_bytes, hr.nrows, cudaMemcpyHostToDevice, c->stream));
     return 0;
   }
   size_t off = 0;
@@ -182,17 +341,25 @@ int b200ks_host::h2d(b200ks_ctx *c, void *dst, const void *src, size_t bytes) {
     const int b = k & 1;
     const size_t n = std::min(kBounceBytes, bytes - off);
     CU(cudaEventSynchronize(c->bounce_ev[b]));   // the last DMA out of this buffer (this call's or an earlier one's)
-    parallel_memcpy(c->bounce[b], (const char *)src + off, n);
+    char *bb = (char *)c->bounce[b];
+    const char *base = (const char *)src;
+    parallel_chunks(n, [&, off](size_t o, size_t m) { rows_gather(bb + o, base, hr, off + o, m); });
     CU(cudaMemcpyAsync((char *)dst + off, c->bounce[b], n, cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->bounce_ev[b], c->stream));
   }
   return 0;
 }
+int b200ks_host::h2d(b200ks_ctx *c, void *dst, const void *src, size_t bytes) {
+  return h2d_rows(c, dst, src, HostRows{bytes, 1, bytes});
+}
 
 // returns after the host array is complete (synchronises the stream)
-int b200ks_host::d2h(b200ks_ctx *c, void *dst, const void *src, size_t bytes) {
+static int d2h_rows(b200ks_ctx *c, void *dst, const void *src, const HostRows &hr) {
+  const size_t bytes = hr.total();
+  const bool one = hr.nrows == 1 || hr.row_bytes == hr.pitch_bytes;
   if (bytes < (kBounceBytes >> 2) || host_is_pinned(dst) || bounce_get(c) < 0) {
-    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (one) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    else CU(cudaMemcpy2DAsync(dst, hr.pitch_bytes, src, hr.row_bytes, hr.row_bytes, hr.nrows, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
   }
@@ -206,22 +373,31 @@ int b200ks_host::d2h(b200ks_ctx *c, void *dst, const void *src, size_t bytes) {
     if (k >= 1) {       // ... while the host threads drain chunk k - 1
       const size_t off = (k - 1) * kBounceBytes, n = std::min(kBounceBytes, bytes - off);
       CU(cudaEventSynchronize(c->bounce_ev[(k - 1) & 1]));
-      parallel_memcpy((char *)dst + off, c->bounce[(k - 1) & 1], n);
+      const char *bb = (const char *)c->bounce[(k - 1) & 1];
+      char *base = (char *)dst;
+      parallel_chunks(n, [&, off](size_t o, size_t m) { rows_scatter(base, hr, off + o, bb + o, m); });
     }
   }
   return 0;
 }
+int b200ks_host::d2h(b200ks_ctx *c, void *dst, const void *src, size_t bytes) {
+  return d2h_rows(c, dst, src, HostRows{bytes, 1, bytes});
+}
 
-// 64-bit content fingerprint of a host array (multiplicative polynomial hash over 64-bit words,
-// eight interleaved lanes per thread, threads over contiguous chunks; memory-bandwidth bound).
+// 64-bit content fingerprint of a host array (eight interleaved lanes per thread, threads over
+// contiguous chunks; memory-bandwidth bound).  Every word goes through a NON-LINEAR step
+// (xor, odd multiply, xor-shift): a hash that is linear mod 2^64 in the words -- h = h*K + w --
+// cannot see an even number of sign-bit flips in one lane (each adds 2^63 * K^m = 2^63), which is
+// exactly what boundary_twist_fn does when it negates whole time slices of links.
 // The MILC-facing shims use it to notice in-place edits of the link arrays that MILC does not
 // announce (boundary_twist_fn, generic_ks/fermion_links_fn_twist_milc.c:318-400) without
-// re-uploading 2.4 GB on every call.
+// re-uploading 2.4 GB on every call.  The chunking is fixed (kFpThreads), so the value does not
+// depend on the machine.
+constexpr unsigned kFpThreads = 16;
 extern "C" unsigned long long b200ks_fingerprint(const void *p, size_t bytes) {
   if (!p || bytes == 0) return 0;
-  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   const size_t nwords = bytes / 8;
-  const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, nwords >> 17));
+  const unsigned nt = (unsigned)std::min<size_t>(kFpThreads, std::max<size_t>(1, nwords >> 17));
   std::vector<unsigned long long> part(nt, 0);
   const unsigned long long *w = (const unsigned long long *)p;
   auto work = [&](unsigned t) {
@@ -230,8 +406,14 @@ extern "C" unsigned long long b200ks_fingerprint(const void *p, size_t bytes) {
     unsigned long long h[8] = {1, 2, 3, 4, 5, 6, 7, 8};
     size_t i = lo;
     for (; i + 8 <= hi; i += 8)
-      for (int l = 0; l < 8; l++) h[l] = h[l] * K + w[i + l];
-    for (; i < hi; i++) h[0] = h[0] * K + w[i];
+      for (int l = 0; l < 8; l++) {
+        unsigned long long x = (h[l] ^ w[i + l]) * K;
+        h[l] = x ^ (x >> 29);
+      }
+    for (; i < hi; i++) {
+      unsigned long long x = (h[0] ^ w[i]) * K;
+      h[0] = x ^ (x >> 29);
+    }
     unsigned long long r = 0;
     for (int l = 0; l < 8; l++) r = (r ^ h[l]) * 0xD6E8FEB86659FD93ull + (r >> 29);
     part[t] = r;
@@ -318,6 +500,10 @@ static int setup_geom(b200ks_ctx *c, const int local[4], const int part[4], cons
       g.lghost[d] = lsites; lsites += 3 * g.faceh[d];
     }
   }
+  g.S2 = g.Lxh * g.L[1];
+  g.zi = g.part[2] ? g.L[2] - 6 : g.L[2];
+  g.dS2 = make_fastdiv(g.S2);
+  g.dZi = make_fastdiv(std::max(1, g.zi));
   g.stride = (g.Vh + 63) / 64 * 64;
   g.gstride = (gsites + 63) / 64 * 64;
   g.lstride = (lsites + 63) / 64 * 64;
@@ -344,6 +530,9 @@ static b200ks_ctx *create_common(const int latsize[4], const int local[4], const
   c->device = device;
   memcpy(c->global, latsize, sizeof(c->global));
   if (setup_geom(c, local, part, origin) < 0) { delete c; return nullptr; }
+  c->hv_row_sites = c->hv_pitch_sites = c->hv_parity_sites = (size_t)c->g.Vh;
+  c->hv_nrows = 1;
+  c->hv_offset_sites = 0;
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
   c->max_blocks = nblocks(c->g.Vh) + 8;
   void *p = nullptr;
@@ -372,13 +561,40 @@ static b200ks_ctx *create_common(const int latsize[4], const int local[4], const
   return c;
 }
 
+extern "C" b200ks_ctx *b200ks_create_multi(const int latsize[4], int ngpu, const int *devices);
+// B200KS_NGPU=N in the environment turns every b200ks_create -- the call both MILC-facing shims make --
+// into b200ks_create_multi on devices device .. device+N-1: the application stays one vanilla rank.
 extern "C" b200ks_ctx *b200ks_create(const int latsize[4], int device) {
+  const char *e = getenv("B200KS_NGPU");
+  const int ngpu = e ? atoi(e) : 1;
+  if (ngpu > 1) {
+    std::vector<int> devs(ngpu);
+    for (int r = 0; r < ngpu; r++) devs[r] = device + r;
+    return b200ks_create_multi(latsize, ngpu, devs.data());
+  }
   const int part[4] = {0, 0, 0, 0}, origin[4] = {0, 0, 0, 0};
   return create_common(latsize, latsize, part, origin, device);
 }
 
 extern "C" void b200ks_destroy(b200ks_ctx *c) {
   if (!c) return;
+  watch_join_thread(c);
+  if (c->multi && c->member_rank < 0) {   // leader of a multi-GPU context
+    MultiState *ms = c->multi;
+    if (c->aux) b200ks_destroy(c->aux);
+    // nobody may still be pushing into a block that is about to be freed
+    run_all(c, [&](b200ks_ctx *m, int) -> int { if (m) { cudaSetDevice(m->device); cudaDeviceSynchronize(); } return 0; });
+    run_all(c, [&](b200ks_ctx *m, int) -> int { if (m) b200ks_destroy(m); return 0; });
+    {
+      std::unique_lock<std::mutex> lk(ms->mu);
+      ms->quit = true;
+      ms->cv_go.notify_all();
+    }
+    for (auto &t : ms->workers) t.join();
+    delete ms;
+    delete c;
+    return;
+  }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto v : c->user) vec_delete(c, v);
@@ -391,7 +607,7 @@ extern "C" void b200ks_destroy(b200ks_ctx *c) {
   }
   if (c->comm.halo) nccl().CommDestroy(c->comm.halo);
   if (c->comm.red) nccl().CommDestroy(c->comm.red);
-  for (int k = 0; k < 4; k++)
+  for (int k = 0; k < kMaxRanks; k++)
     if (c->comm.p2p.opened[k]) cudaIpcCloseMemHandle(c->comm.p2p.opened[k]);
   cudaFree(c->comm.p2p.block);
   cudaFree(c->comm.p2p.ticket);
@@ -430,9 +646,20 @@ extern "C" void b200ks_destroy(b200ks_ctx *c) {
   delete c;
 }
 
-extern "C" long long b200ks_launch_count(b200ks_ctx *c) { return c ? c->launches : 0; }
-extern "C" void *b200ks_stream(b200ks_ctx *c) { return c ? (void *)c->stream : nullptr; }
-extern "C" size_t b200ks_device_bytes(b200ks_ctx *c) { return c ? c->bytes : 0; }
+extern "C" long long b200ks_launch_count(b200ks_ctx *c) {
+  if (!c) return 0;
+  long long n = c->launches + (c->aux ? c->aux->launches : 0);
+  for (auto m : c->sub) n += m->launches;
+  return n;
+}
+extern "C" void *b200ks_stream(b200ks_ctx *c) { return !c ? nullptr : c->sub.empty() ? (void *)c->stream : (void *)c->sub[0]->stream; }
+extern "C" size_t b200ks_device_bytes(b200ks_ctx *c) {
+  if (!c) return 0;
+  size_t n = c->bytes + (c->aux ? c->aux->bytes : 0);
+  for (auto m : c->sub) n += m->bytes;
+  return n;
+}
+extern "C" int b200ks_num_gpus(b200ks_ctx *c) { return c ? nmembers(c) : 0; }
 
 #define LAUNCH(c, kern, grid, ...)                                       \
   do {                                                                   \
@@ -452,22 +679,43 @@ int b200ks_host::check_launch(const char *what) {
 }
 
 // second stage of a two-stage reduction (blas.cuh reduce_finish_kernel): one CTA per slot
-static void launch_finish(b200ks_ctx *c, const FinishArg &a, int nslots) {
-  reduce_finish_kernel<<<nslots, kFinishThreads, 0, c->stream>>>(a);
+constexpr long long kHaloTimeoutCycles = 20000000000ll;   // ~10 s at 2 GHz
+
+static RedComm red_comm(const b200ks_ctx *c) {
+  RedComm rc;
+  memset(&rc, 0, sizeof(rc));
+  const Comm &cm = c->comm;
+  for (int q = 0; q < cm.nranks; q++) rc.box[q] = (RedBox *)(cm.p2p.peer_all[q] + kP2PFlagBytes);
+  rc.rank = cm.rank;
+  rc.nranks = cm.nranks;
+  rc.err = cm.p2p.err;
+  rc.timeout = kHaloTimeoutCycles;
+  return rc;
+}
+static bool p2p_reductions(const b200ks_ctx *c) { return c->comm.active && c->comm.p2p.on; }
+
+static void launch_finish(b200ks_ctx *c, const FinishArg &a, int nslots, bool comm = false) {
+  if (comm && c->comm.nranks > 1) reduce_finish_kernel<true><<<1, kFinishThreads, 0, c->stream>>>(a, red_comm(c));
+  else reduce_finish_kernel<false><<<nslots, kFinishThreads, 0, c->stream>>>(a, RedComm());
   c->launches++;
 }
 static FinishSlot finish_slot(const double *partials, int stride, int nval, double *out, CgState *st, const int *stop) {
   FinishSlot f;
   f.partials = partials; f.stride = stride; f.nval = nval; f.out = out; f.st = st; f.stop = stop;
+  f.extra = nullptr; f.nextra = 0;
   return f;
 }
-// the stencil's three fused dot products of one right-hand side
-static void finish_dots(b200ks_ctx *c, int nblk, double *red, const int *stop) {
+// the stencil's three fused dot products of one right-hand side.  Partitioned contexts (peer-to-peer):
+// all-reduced over the ranks inside the same kernel, together with `extra` (this rank's share of
+// the previous update's sums, CgState::upd).
+static void finish_dots(b200ks_ctx *c, int nblk, double *red, const int *stop, double *extra = nullptr, int nextra = 0) {
   FinishArg f;
   memset(&f, 0, sizeof(f));
   f.s[0] = finish_slot(c->ws.partials, 3, 3, red, nullptr, stop);
+  f.s[0].extra = extra;
+  f.s[0].nextra = nextra;
   f.nblk = nblk;
-  launch_finish(c, f, 1);
+  launch_finish(c, f, 1, p2p_reductions(c));
 }
 // the update kernel's sums of state `st` + its scalar recurrence (flags as cg_update_kernel's fuse_scalar)
 static void finish_update(b200ks_ctx *c, int nblk, CgState *st, int flags) {
@@ -481,6 +729,7 @@ static void finish_update(b200ks_ctx *c, int nblk, CgState *st, int flags) {
 
 // ---------------------------------------------------------------------------------------------
 // links
+static void watch_join_thread(b200ks_ctx *c);
 static int links_alloc(b200ks_ctx *c, int prec, int nc) {
   Links &L = c->links[prec];
   for (int p = 0; p < 2; p++) {
@@ -512,9 +761,18 @@ static int links_alloc(b200ks_ctx *c, int prec, int nc) {
                                     (nccl().GetErrorString ? nccl().GetErrorString(e_) : "NCCL error")); \
   } while (0)
 
-static int allreduce(b200ks_ctx *c, double *dptr, int n) {
+// sum (max) of n <= 8 device doubles over the ranks, in place, on the compute stream: flag-based
+// exchange over the peer mappings (blas.cuh), NCCL when the halos go through NCCL too
+static int allreduce(b200ks_ctx *c, double *dptr, int n, bool take_max = false, const int *stop = nullptr) {
   if (c->comm.nranks == 1) return 0;
-  NC(nccl().AllReduce(dptr, dptr, (size_t)n, ncclDouble, ncclSum, c->comm.red, c->stream));
+  if (c->comm.p2p.on) {
+    if (n > 8) return fail(B200KS_EINVAL, "allreduce: at most 8 values");
+    if (take_max) p2p_allreduce_kernel<true><<<1, kAllreduceThreads, 0, c->stream>>>(dptr, n, red_comm(c), stop);
+    else p2p_allreduce_kernel<false><<<1, kAllreduceThreads, 0, c->stream>>>(dptr, n, red_comm(c), stop);
+    c->launches++;
+    return 0;
+  }
+  NC(nccl().AllReduce(dptr, dptr, (size_t)n, ncclDouble, take_max ? ncclMax : ncclSum, c->comm.red, c->stream));
   return 0;
 }
 
@@ -527,6 +785,7 @@ static int exchange_link_ghosts_T(b200ks_ctx *c, int prec) {
   const Geom &g = c->g;
   Comm &cm = c->comm;
   if (!cm.active) return 0;
+  MultiState *ms = c->member_rank >= 0 ? c->multi : nullptr;
   for (int d = 2; d < 4; d++) {
     if (!g.part[d]) continue;
     const size_t face3 = (size_t)3 * g.faceh[d];
@@ -538,6 +797,22 @@ static int exchange_link_ghosts_T(b200ks_ctx *c, int prec) {
         T2 *U = (T2 *)(which ? c->links[prec].lng[p] : c->links[prec].fat[p]);
         if (d == 2)
           LAUNCH(c, (pack_zhigh_links_kernel<T>), nblocks((int)(9 * face3)), buf, U, g, d);
+        if (ms && !self) {
+          // one process: publish where our high slices are, then PULL the backward neighbour's over
+          // its peer mapping (all members have the same local geometry, so offsets are ours)
+          CU(cudaStreamSynchronize(c->stream));
+          ms->slot[cm.rank] = (d == 3) ? (void *)U : (void *)buf;
+          MEET(ms);
+          const T2 *peer = (const T2 *)ms->slot[cm.nbr[d][0]];
+          for (int e = 0; e < 9; e++) {
+            T2 *comp = U + (size_t)(d * 9 + e) * g.lstride;
+            const T2 *src = (d == 3) ? peer + (size_t)(d * 9 + e) * g.lstride + (size_t)(g.L[3] - 3) * g.faceh[3] : peer + e * face3;
+            CU(cudaMemcpyPeerAsync(comp + g.lghost[d], c->device, src, ms->devices[cm.nbr[d][0]], face3 * sizeof(T2), c->stream));
+          }
+          CU(cudaStreamSynchronize(c->stream));
+          MEET(ms);   // the forward neighbour has pulled: buf / U may change again
+          continue;
+        }
         if (!self) NC(nccl().GroupStart());
         for (int e = 0; e < 9; e++) {
           T2 *comp = U + (size_t)(d * 9 + e) * g.lstride;
@@ -596,7 +871,7 @@ static int compress_long(b200ks_ctx *c, int prec, int long_recon) {
   if (c->comm.nranks > 1) {  // every rank must take the same decision
     double *d = c->d_scal;
     CU(cudaMemcpyAsync(d, &dev, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    NC(nccl().AllReduce(d, d, 1, ncclDouble, ncclMax, c->comm.red, c->stream));
+    CHK(allreduce(c, d, 1, true));
     CU(cudaMemcpyAsync(&dev, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
@@ -622,6 +897,7 @@ static int compress_long(b200ks_ctx *c, int prec, int long_recon) {
 
 extern "C" int b200ks_long_link_info(b200ks_ctx *c, int *ncomplex, double *misfit) {
   if (!c) return fail(B200KS_EINVAL, "null context");
+  if (!c->sub.empty()) c = c->sub[0];
   if (c->link_master == 0) return fail(B200KS_ESTATE, "links not loaded");
   if (ncomplex) *ncomplex = c->links[c->link_master].lng_nc;
   if (misfit) *misfit = c->long_dev;
@@ -632,6 +908,12 @@ extern "C" int b200ks_load_links(b200ks_ctx *c, const void *fat, const void *lng
   if (!c || !fat || !lng) return fail(B200KS_EINVAL, "b200ks_load_links: null argument");
   if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
   CHK(check_recon(long_recon));
+  if (c->member_rank < 0) {   // whatever b200ks_links_sync knew about the device links is void now
+    watch_join_thread(c);
+    c->watch.pending = false;
+    c->watch.have = false;
+  }
+  MULTI(c, b200ks_load_links(c, fat, lng, host_prec, long_recon));
   CU(cudaSetDevice(c->device));
   const int prec = host_prec;  // master copy at the caller's precision
   CHK(links_alloc(c, prec, 9));
@@ -640,9 +922,10 @@ extern "C" int b200ks_load_links(b200ks_ctx *c, const void *fat, const void *lng
   void *stage = nullptr;
   CHK(stage_get(c, half_bytes, &stage));
   for (int which = 0; which < 2; which++) {
-    const char *h = (const char *)(which == 0 ? fat : lng);
     for (int p = 0; p < 2; p++) {
-      CHK(h2d(c, stage, h + (size_t)p * half_bytes, half_bytes));
+      HostRows hr;
+      const char *h = host_half(c, which == 0 ? fat : lng, p, 72 * hs, hr);
+      CHK(h2d_rows(c, stage, h, hr));
       void *dst = which == 0 ? c->links[prec].fat[p] : c->links[prec].lng[p];
       if (prec == 2) pack_links_T<double, double>(c, dst, stage);
       else pack_links_T<float, float>(c, dst, stage);
@@ -654,6 +937,103 @@ extern "C" int b200ks_load_links(b200ks_ctx *c, const void *fat, const void *lng
   c->link_master = prec;
   for (int k = 0; k < 3; k++) c->links[k].valid = (k == prec);
   return compress_long(c, prec, long_recon);
+}
+
+// ---- keeping the device links in step with MILC's host arrays ------------------------------------
+// MILC announces rebuilt links (fn pointer, notify flag) but not the in-place sign flips of
+// boundary_twist_fn (generic_ks/fermion_links_fn_twist_milc.c:318-400), so the shims compare a
+// content fingerprint of the two host arrays with the one taken at the last upload.  One pass over
+// 2.4 GB costs ~70 ms at 32^3x64 -- a third of a solve -- and it almost always says "unchanged".
+// It therefore runs on host threads WHILE the solve iterates on the resident links (the calling
+// thread only polls the device then); the entry point that launched the solve joins it before it
+// hands any result back, and on a mismatch re-uploads the links and repeats the solve.
+static void watch_join_thread(b200ks_ctx *c) {
+  if (c->watch.th.joinable()) c->watch.th.join();
+}
+
+// returns 0: links were up to date (or nothing was pending); 1: they had changed and were re-uploaded
+static int load_links_fp(b200ks_ctx *c, const void *fat, const void *lng, int host_prec, int long_recon,
+                         const unsigned long long *fp_known);
+static int watch_join(b200ks_ctx *c) {
+  LinkWatch &w = c->watch;
+  if (!w.pending) return 0;
+  watch_join_thread(c);
+  w.pending = false;
+  w.verifications++;
+  if (w.now[0] == w.fp[0] && w.now[1] == w.fp[1]) return 0;
+  CHK(load_links_fp(c, w.fat, w.lng, w.host_prec, w.long_recon, w.now));
+  return 1;
+}
+
+static int load_links_fp(b200ks_ctx *c, const void *fat, const void *lng, int host_prec, int long_recon,
+                         const unsigned long long *fp_known) {
+  LinkWatch &w = c->watch;
+  watch_join_thread(c);
+  w.pending = false;
+  const size_t bytes = (size_t)c->global[0] * c->global[1] * c->global[2] * c->global[3] * 72 * (host_prec == 2 ? 8 : 4);
+  unsigned long long fp[2] = {0, 0};
+  std::thread hasher;
+  if (fp_known) { fp[0] = fp_known[0]; fp[1] = fp_known[1]; }
+  else hasher = std::thread([&]() { fp[0] = b200ks_fingerprint(fat, bytes); fp[1] = b200ks_fingerprint(lng, bytes); });
+  const int r = b200ks_load_links(c, fat, lng, host_prec, long_recon);
+  if (hasher.joinable()) hasher.join();
+  w.have = false;
+  if (r < 0) return r;
+  w.fat = fat; w.lng = lng; w.host_prec = host_prec; w.long_recon = long_recon; w.bytes = bytes;
+  w.fp[0] = fp[0]; w.fp[1] = fp[1];
+  w.have = true;
+  w.reloads++;
+  return 0;
+}
+
+// Runs `body` (upload + compute of a host-buffer entry point; results not yet handed back) and
+// repeats it once if the verification that ran beside it found the host links changed.
+template <typename F>
+static int with_verified_links(b200ks_ctx *c, F body) {
+  int r = body();
+  if (r < 0) {
+    watch_join_thread(c);
+    c->watch.pending = false;
+    return r;
+  }
+  const int ch = watch_join(c);
+  if (ch < 0) return ch;
+  if (ch == 1) r = body();
+  return r;
+}
+
+extern "C" int b200ks_links_sync(b200ks_ctx *c, const void *fat, const void *lng, int host_prec, int changed_hint, int mode) {
+  if (!c || !fat || !lng) return fail(B200KS_EINVAL, "b200ks_links_sync: null argument");
+  if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
+  if (mode < 0 || mode > 3) return fail(B200KS_EINVAL, "b200ks_links_sync: mode must be 0..3");
+  LinkWatch &w = c->watch;   // (a multi-GPU leader verifies once for all of its members)
+  CHK(watch_join(c));   // a verification nobody waited for (device-resident calls in between)
+  const bool same = w.have && !changed_hint && fat == w.fat && lng == w.lng && host_prec == w.host_prec;
+  if (!same || mode == 1) {
+    CHK(load_links_fp(c, fat, lng, host_prec, 0, nullptr));
+    return 1;
+  }
+  if (mode == 0) return 0;
+  if (mode == 3) {   // blocking comparison (what round 1 did on every call)
+    w.now[0] = b200ks_fingerprint(fat, w.bytes);
+    w.now[1] = b200ks_fingerprint(lng, w.bytes);
+    w.pending = true;
+    return watch_join(c);
+  }
+  w.pending = true;
+  w.th = std::thread([c]() {
+    LinkWatch &ww = c->watch;
+    ww.now[0] = b200ks_fingerprint(ww.fat, ww.bytes);
+    ww.now[1] = b200ks_fingerprint(ww.lng, ww.bytes);
+  });
+  return 0;
+}
+
+extern "C" int b200ks_links_sync_stats(b200ks_ctx *c, long long *reloads, long long *verifications) {
+  if (!c) return fail(B200KS_EINVAL, "null context");
+  if (reloads) *reloads = c->watch.reloads;
+  if (verifications) *verifications = c->watch.verifications;
+  return 0;
 }
 
 // 16-bit copy of the master links: one scale per field (fat components, long rows, long factor),
@@ -687,7 +1067,7 @@ static int links_quantize(b200ks_ctx *c, int m, int nc) {
   }
   if (c->comm.nranks > 1) {
     CU(cudaMemcpyAsync(c->d_scal, mx, sizeof(mx), cudaMemcpyHostToDevice, c->stream));
-    NC(nccl().AllReduce(c->d_scal, c->d_scal, 3, ncclDouble, ncclMax, c->comm.red, c->stream));
+    CHK(allreduce(c, c->d_scal, 3, true));
     CU(cudaMemcpyAsync(mx, c->d_scal, sizeof(mx), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
@@ -736,7 +1116,6 @@ static int links_ensure(b200ks_ctx *c, int prec) {
 
 // ---------------------------------------------------------------------------------------------
 // dslash launcher.  par_out = parity bit of the output sites.
-constexpr long long kHaloTimeoutCycles = 20000000000ll;   // ~10 s at 2 GHz
 
 struct Epi {
   int kind = 0;            // 0 store, 1 xpay, 2 xpay + dots
@@ -744,7 +1123,9 @@ struct Epi {
   const DevVec *w = nullptr;
   const DevVec *r = nullptr;
   double *red = nullptr;      // reduction slots (interior pass / single GPU)
-  double *red_ext = nullptr;  // reduction slots of the exterior pass (multi-GPU)
+  double *red_ext = nullptr;  // reduction slots of the exterior pass (multi-GPU, NCCL halos)
+  double *extra = nullptr;    // partitioned, peer-to-peer: nextra local values that join the all-reduce of
+  int nextra = 0;             // the three dots and are replaced by their sums (CgState::upd)
   const int *stop = nullptr;
 };
 
@@ -881,8 +1262,10 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
     a.halo_seq = pp.seq;
     a.halo_mask = (c->g.part[2] ? 3 : 0) | (c->g.part[3] ? 12 : 0);
     a.halo_err = pp.err;
+    a.red = nullptr;   // two-stage reduction: partial sums only, finish_dots adds them up and all-reduces
     DSLASH_LAUNCH(1, a.nb_int + nb_ext);
     CU(cudaStreamWaitEvent(c->stream, c->comm.ev_done, 0));
+    if (e.kind == 2) finish_dots(c, a.nb_int + nb_ext, e.red, e.stop, e.extra, e.nextra);
     return 0;
   }
   // NCCL halos: interior launch || exchange, stream event, boundary launch (its reductions go
@@ -900,7 +1283,7 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
 // 16-bit stencil (half.cuh).  kind 0: out_h (half) = D in.  kind 2: out_f (float) = D in + s*w_h
 // with the three fused dot products against w_h (half) and r (float).
 static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *out_f, int par_out, int kind, double s_,
-                       const DevVec *w_h, const DevVec *r, double *red, const int *stop) {
+                       const DevVec *w_h, const DevVec *r, double *red, const int *stop, double *extra = nullptr, int nextra = 0) {
   const Links &L = c->links[0];
   DslashHArg a;
   memset(&a, 0, sizeof(a));
@@ -952,8 +1335,10 @@ static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *o
   a.halo_seq = pp.seq;
   a.halo_mask = (c->g.part[2] ? 3 : 0) | (c->g.part[3] ? 12 : 0);
   a.halo_err = pp.err;
+  a.red = nullptr;   // two-stage reduction, see dslash_T
   DSLASH_H_LAUNCH(1, a.nb_int + nblocks(c->comm.n_ext));
   CU(cudaStreamWaitEvent(c->stream, c->comm.ev_done, 0));
+  if (kind == 2) finish_dots(c, a.nb_int + nblocks(c->comm.n_ext), red, stop, extra, nextra);
 #undef DSLASH_H_LAUNCH
   return 0;
 }
@@ -988,7 +1373,8 @@ static void unpack_vec_T(b200ks_ctx *c, void *st, const void *d) {
   LAUNCH(c, (unpack_vec_kernel<T, TH>), nblocks(c->g.Vh), (TH *)st, (const typename Vec2<T>::type *)d, c->g.stride, c->g.Vh);
 }
 
-static int upload(b200ks_ctx *c, DevVec &v, const void *host, int parity, int host_prec) {
+// sync = false: the caller reaches a stream synchronisation before it returns to ITS caller
+static int upload(b200ks_ctx *c, DevVec &v, const void *host, int parity, int host_prec, bool sync = true) {
   if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
   const size_t hs = host_prec == 2 ? 8 : 4;
   const size_t half_bytes = (size_t)c->g.Vh * 6 * hs;
@@ -997,13 +1383,15 @@ static int upload(b200ks_ctx *c, DevVec &v, const void *host, int parity, int ho
   for (int p = 0; p < 2; p++) {
     if (!((parity == B200KS_EVENANDODD) || (parity == B200KS_EVEN && p == 0) || (parity == B200KS_ODD && p == 1))) continue;
     void *stage = stage2 + (size_t)p * half_bytes;
-    CHK(h2d(c, stage, (const char *)host + (size_t)p * half_bytes, half_bytes));
+    HostRows hr;
+    const char *h = host_half(c, host, p, 6 * hs, hr);
+    CHK(h2d_rows(c, stage, h, hr));
     if (v.prec == 2 && host_prec == 2) pack_vec_T<double, double>(c, v.p[p], stage);
     else if (v.prec == 2 && host_prec == 1) pack_vec_T<double, float>(c, v.p[p], stage);
     else if (v.prec == 1 && host_prec == 2) pack_vec_T<float, double>(c, v.p[p], stage);
     else pack_vec_T<float, float>(c, v.p[p], stage);
   }
-  CU(cudaStreamSynchronize(c->stream));
+  if (sync) CU(cudaStreamSynchronize(c->stream));
   return check_launch("pack_vec_kernel");
 }
 
@@ -1020,7 +1408,9 @@ static int download(b200ks_ctx *c, const DevVec &v, void *host, int parity, int 
     else if (v.prec == 2 && host_prec == 1) unpack_vec_T<double, float>(c, stage, v.p[p]);
     else if (v.prec == 1 && host_prec == 2) unpack_vec_T<float, double>(c, stage, v.p[p]);
     else unpack_vec_T<float, float>(c, stage, v.p[p]);
-    CHK(d2h(c, (char *)host + (size_t)p * half_bytes, stage, half_bytes));
+    HostRows hr;
+    char *h = (char *)host_half(c, host, p, 6 * hs, hr);
+    CHK(d2h_rows(c, h, stage, hr));
   }
   CU(cudaStreamSynchronize(c->stream));
   return check_launch("unpack_vec_kernel");
@@ -1054,6 +1444,7 @@ static DevVec *uvec(b200ks_ctx *c, int h) {
 }
 extern "C" int b200ks_vec_create(b200ks_ctx *c) {
   if (!c) return fail(B200KS_EINVAL, "null context");
+  MULTI(c, b200ks_vec_create(c));   // members allocate in lockstep: the same handle everywhere
   CU(cudaSetDevice(c->device));
   DevVec *v = nullptr;
   CHK(vec_new(c, 2, &v));
@@ -1063,6 +1454,7 @@ extern "C" int b200ks_vec_create(b200ks_ctx *c) {
   return (int)c->user.size() - 1;
 }
 extern "C" int b200ks_vec_free(b200ks_ctx *c, int h) {
+  MULTI(c, b200ks_vec_free(c, h));
   DevVec *v = uvec(c, h);
   if (!v) return B200KS_EINVAL;
   if (std::find(c->eig.handles.begin(), c->eig.handles.end(), h) != c->eig.handles.end())
@@ -1073,18 +1465,21 @@ extern "C" int b200ks_vec_free(b200ks_ctx *c, int h) {
   return 0;
 }
 extern "C" int b200ks_vec_upload(b200ks_ctx *c, int h, const void *host, int parity, int host_prec) {
+  MULTI(c, b200ks_vec_upload(c, h, host, parity, host_prec));
   DevVec *v = uvec(c, h);
   if (!v || !host) return fail(B200KS_EINVAL, "b200ks_vec_upload: bad argument");
   CU(cudaSetDevice(c->device));
   return upload(c, *v, host, parity, host_prec);
 }
 extern "C" int b200ks_vec_download(b200ks_ctx *c, int h, void *host, int parity, int host_prec) {
+  MULTI(c, b200ks_vec_download(c, h, host, parity, host_prec));
   DevVec *v = uvec(c, h);
   if (!v || !host) return fail(B200KS_EINVAL, "b200ks_vec_download: bad argument");
   CU(cudaSetDevice(c->device));
   return download(c, *v, host, parity, host_prec);
 }
 extern "C" int b200ks_vec_zero(b200ks_ctx *c, int h, int parity) {
+  MULTI(c, b200ks_vec_zero(c, h, parity));
   DevVec *v = uvec(c, h);
   if (!v) return B200KS_EINVAL;
   if (parity & B200KS_EVEN) CHK(zero_half(c, *v, 0));
@@ -1092,6 +1487,13 @@ extern "C" int b200ks_vec_zero(b200ks_ctx *c, int h, int parity) {
   return 0;
 }
 extern "C" int b200ks_vec_norm2(b200ks_ctx *c, int h, int parity, double *out) {
+  if (c && !c->sub.empty()) {   // global norm, the same on every member
+    if (!out) return fail(B200KS_EINVAL, "b200ks_vec_norm2: bad argument");
+    std::vector<double> o(c->sub.size(), 0.0);
+    CHK(run_all(c, [&](b200ks_ctx *c, int r) -> int { return b200ks_vec_norm2(c, h, parity, &o[r]); }));
+    *out = o[0];
+    return 0;
+  }
   DevVec *v = uvec(c, h);
   if (!v || !out) return fail(B200KS_EINVAL, "b200ks_vec_norm2: bad argument");
   double s = 0, t = 0;
@@ -1115,6 +1517,7 @@ static int dslash_parity(b200ks_ctx *c, const DevVec &in, DevVec &out, int parit
 }
 
 extern "C" int b200ks_dslash_dev(b200ks_ctx *c, int vsrc, int vdest, int parity, int prec) {
+  MULTI(c, b200ks_dslash_dev(c, vsrc, vdest, parity, prec));
   DevVec *s = uvec(c, vsrc), *d = uvec(c, vdest);
   if (!s || !d) return B200KS_EINVAL;
   if (prec != B200KS_PREC_DOUBLE && prec != B200KS_PREC_SINGLE && prec != B200KS_PREC_HALF)
@@ -1152,21 +1555,37 @@ extern "C" int b200ks_dslash_dev(b200ks_ctx *c, int vsrc, int vdest, int parity,
 
 extern "C" int b200ks_dslash(b200ks_ctx *c, const void *src, void *dest, int parity, int host_prec) {
   if (!c || !src || !dest) return fail(B200KS_EINVAL, "b200ks_dslash: null argument");
-  CU(cudaSetDevice(c->device));
-  DevVec *in = nullptr, *out = nullptr;
+  if (parity != B200KS_EVEN && parity != B200KS_ODD && parity != B200KS_EVENANDODD) return fail(B200KS_EINVAL, "unrecognised parity");
   const int prec = host_prec == 1 ? 1 : 2;
-  CHK(pool_get(c, prec, 0, &in));
-  CHK(pool_get(c, prec, 1, &out));
   const int src_par = parity == B200KS_EVENANDODD ? B200KS_EVENANDODD : (parity == B200KS_EVEN ? B200KS_ODD : B200KS_EVEN);
-  CHK(upload(c, *in, src, src_par, host_prec));
-  CHK(dslash_parity(c, *in, *out, parity));
-  CHK(check_launch("dslash_kernel"));
-  return download(c, *out, dest, parity, host_prec);
+  CHK(with_verified_links(c, [&]() {
+    return run_all(c, [&](b200ks_ctx *c, int) -> int {
+      CU(cudaSetDevice(c->device));
+      DevVec *in = nullptr, *out = nullptr;
+      CHK(pool_get(c, prec, 0, &in));
+      CHK(pool_get(c, prec, 1, &out));
+      CHK(upload(c, *in, src, src_par, host_prec, false));
+      CHK(dslash_parity(c, *in, *out, parity));
+      CHK(halo_check(c));
+      return check_launch("dslash_kernel");
+    });
+  }));
+  return run_all(c, [&](b200ks_ctx *c, int) -> int {
+    DevVec *out = nullptr;
+    CHK(pool_get(c, prec, 1, &out));
+    return download(c, *out, dest, parity, host_prec);
+  });
 }
 
 extern "C" int b200ks_dslash_time(b200ks_ctx *c, int prec, int parity, int n, double *ms) {
   if (!c || !ms || n <= 0) return fail(B200KS_EINVAL, "b200ks_dslash_time: bad argument");
   if (prec != 0 && prec != 1 && prec != 2) return fail(B200KS_EINVAL, "b200ks_dslash_time: prec must be 0, 1 or 2");
+  if (!c->sub.empty()) {   // slowest member
+    std::vector<double> t(c->sub.size(), 0.0);
+    CHK(run_all(c, [&](b200ks_ctx *c, int r) -> int { return b200ks_dslash_time(c, prec, parity, n, &t[r]); }));
+    *ms = *std::max_element(t.begin(), t.end());
+    return 0;
+  }
   CU(cudaSetDevice(c->device));
   DevVec *in = nullptr, *out = nullptr;
   CHK(pool_get(c, prec, 0, &in));
@@ -1315,16 +1734,20 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
     // iterate until the device raises the stop flag (restart interval or recursive
     // residual under target), polling once per batch
     // single GPU: two-stage reductions (bit 3), the finish kernel runs the scalar recurrence
-    const int fuse = (multi && rel) ? 0 : (1 | (rel ? 2 : 0) | (prec == 1 ? 4 : 0) | (multi ? 0 : 8));
+    // partitioned with peer-to-peer halos: two-stage as well, the all-reduce of {pkp, c_tr, c_tt} + the
+    // last update's |r|^2 happens inside the stencil's finish kernel (no NCCL launch per iteration)
+    const bool p2p = p2p_reductions(c);
+    const int fuse = (multi && rel) ? 0 : (1 | (rel ? 2 : 0) | (prec == 1 ? 4 : 0) | ((!multi || p2p) ? 8 : 0));
     CHK(run_batches(c, batch, "cg iterate", [&]() -> int {
       Epi e0, e1;
       e0.stop = &c->d_state->stop;
       CHK(dslash_T<T>(c, *p, *ttt, ob, e0));
       e1.kind = 2; e1.s = -msq_x4; e1.w = p; e1.r = r; e1.red = c->d_state->red; e1.red_ext = c->d_state->red_ext;
       e1.stop = &c->d_state->stop;
+      if (p2p && !rel) { e1.extra = c->d_state->upd; e1.nextra = 2; }
       CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
-      if (multi) {  // one all-reduce per iteration: {pkp, c_tr, c_tt} + last update's |r|^2
-        if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 3);
+      if (multi && !p2p) {  // NCCL halos: one all-reduce per iteration: {pkp, c_tr, c_tt} + last update's |r|^2
+        LAUNCH1(c, combine_red_kernel, c->d_state, 3);
         CHK(allreduce(c, c->d_state->red, rel ? 3 : 5));
       }
       if (rel)
@@ -1335,7 +1758,7 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
                g.stride, g.Vh, c->d_state, c->ws, fuse);
       if (fuse & 8) finish_update(c, grid, c->d_state, fuse);
       if (!fuse) {   // the relative residual needs its own all-reduce before the scalar step
-        CHK(allreduce(c, c->d_state->upd_next, 2));
+        CHK(allreduce(c, c->d_state->upd_next, 2, false, &c->d_state->stop));
         LAUNCH1(c, cg_scalar_kernel, c->d_state, rel ? 1 : 0, prec == 1 ? 1 : 0);
       }
       return 0;
@@ -1462,22 +1885,25 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
     h.stop = 0;
     CHK(state_push(c));
     CHK(run_batches(c, batch, "mixed cg iterate", [&]() -> int {
+      const bool p2p = p2p_reductions(c);
       if (half) {
         CHK(dslash_half(c, *p_h, t_h, nullptr, ob, 0, 0.0, nullptr, nullptr, nullptr, &c->d_state->stop));
-        CHK(dslash_half(c, *t_h, nullptr, ttt_lo, pb, 2, -msq_x4, p_h, r_lo, c->d_state->red, &c->d_state->stop));
+        CHK(dslash_half(c, *t_h, nullptr, ttt_lo, pb, 2, -msq_x4, p_h, r_lo, c->d_state->red, &c->d_state->stop,
+                        p2p ? c->d_state->upd : nullptr, p2p ? 2 : 0));
       } else {
         Epi f0, f1;
         f0.stop = &c->d_state->stop;
         CHK(dslash_T<float>(c, *p_lo, *ttt_lo, ob, f0));
         f1.kind = 2; f1.s = -msq_x4; f1.w = p_lo; f1.r = r_lo; f1.red = c->d_state->red; f1.red_ext = c->d_state->red_ext;
         f1.stop = &c->d_state->stop;
+        if (p2p) { f1.extra = c->d_state->upd; f1.nextra = 2; }
         CHK(dslash_T<float>(c, *ttt_lo, *ttt_lo, pb, f1));
       }
-      if (multi) {
-        if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 3);
+      if (multi && !p2p) {
+        LAUNCH1(c, combine_red_kernel, c->d_state, 3);
         CHK(allreduce(c, c->d_state->red, 5));
       }
-      const int fuse = 1 | 4 | (multi ? 0 : 8);
+      const int fuse = 1 | 4 | ((!multi || p2p) ? 8 : 0);
       if (half)
         LAUNCH(c, cg_update_half_kernel, grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (uint32_t *)p_h->p[pb],
                (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse);
@@ -1537,6 +1963,13 @@ static int congrad_any(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, c
 
 extern "C" int b200ks_congrad_dev(b200ks_ctx *c, int vsrc, int vdest, double mass, const b200ks_invert_args *args,
                                   b200ks_invert_result *res) {
+  if (c && !c->sub.empty()) {
+    if (!res) return fail(B200KS_EINVAL, "b200ks_congrad_dev: bad argument");
+    std::vector<b200ks_invert_result> rr(c->sub.size());
+    const int it = run_all(c, [&](b200ks_ctx *c, int r) -> int { return b200ks_congrad_dev(c, vsrc, vdest, mass, args, &rr[r]); });
+    if (it >= 0) *res = rr[0];
+    return it;
+  }
   DevVec *b = uvec(c, vsrc), *x = uvec(c, vdest);
   if (!b || !x || !res) return fail(B200KS_EINVAL, "b200ks_congrad_dev: bad argument");
   if (b == x) return fail(B200KS_EINVAL, "source and solution must be different fields");
@@ -1549,15 +1982,25 @@ extern "C" int b200ks_congrad(b200ks_ctx *c, const void *src, void *dest, double
                               b200ks_invert_result *res, int host_prec) {
   if (!c || !src || !dest || !res) return fail(B200KS_EINVAL, "b200ks_congrad: null argument");
   CHK(check_args(args));
-  CU(cudaSetDevice(c->device));
-  DevVec *b = nullptr, *x = nullptr;
-  CHK(pool_get(c, 2, 0, &b));
-  CHK(pool_get(c, 2, 1, &x));
-  CHK(upload(c, *b, src, args->parity, host_prec));
-  CHK(upload(c, *x, dest, args->parity, host_prec));
-  int it = congrad_any(c, *b, *x, mass, *args, *res);
+  std::vector<b200ks_invert_result> rr(nmembers(c));
+  const int it = with_verified_links(c, [&]() {
+    return run_all(c, [&](b200ks_ctx *c, int r) -> int {
+      CU(cudaSetDevice(c->device));
+      DevVec *b = nullptr, *x = nullptr;
+      CHK(pool_get(c, 2, 0, &b));
+      CHK(pool_get(c, 2, 1, &x));
+      CHK(upload(c, *b, src, args->parity, host_prec, false));
+      CHK(upload(c, *x, dest, args->parity, host_prec, false));
+      return congrad_any(c, *b, *x, mass, *args, rr[r]);
+    });
+  });
   if (it < 0) return it;
-  CHK(download(c, *x, dest, args->parity, host_prec));
+  CHK(run_all(c, [&](b200ks_ctx *c, int) -> int {
+    DevVec *x = nullptr;
+    CHK(pool_get(c, 2, 1, &x));
+    return download(c, *x, dest, args->parity, host_prec);
+  }));
+  *res = rr[0];
   return it;
 }
 
@@ -1949,6 +2392,14 @@ extern "C" int b200ks_congrad_block_dev(b200ks_ctx *c, int nsrc, const int *vsrc
                                         const b200ks_invert_args *args, b200ks_invert_result *res) {
   if (!c || !res || nsrc < 0 || (nsrc > 0 && (!vsrc || !vdest))) return fail(B200KS_EINVAL, "b200ks_congrad_block_dev: bad argument");
   CHK(check_args(args));
+  if (!c->sub.empty()) {
+    std::vector<b200ks_invert_result> rr(c->sub.size() * (size_t)std::max(nsrc, 1));
+    const int it = run_all(c, [&](b200ks_ctx *c, int r) -> int {
+      return b200ks_congrad_block_dev(c, nsrc, vsrc, vdest, mass, args, rr.data() + (size_t)r * std::max(nsrc, 1));
+    });
+    if (it >= 0) for (int k = 0; k < nsrc; k++) res[k] = rr[k];
+    return it;
+  }
   std::vector<DevVec *> b(nsrc), x(nsrc);
   for (int k = 0; k < nsrc; k++) {
     b[k] = uvec(c, vsrc[k]);
@@ -1966,21 +2417,36 @@ extern "C" int b200ks_congrad_block(b200ks_ctx *c, int nsrc, const void *const *
                                     const b200ks_invert_args *args, b200ks_invert_result *res, int host_prec) {
   if (!c || !res || nsrc < 0 || (nsrc > 0 && (!src || !dest))) return fail(B200KS_EINVAL, "b200ks_congrad_block: null argument");
   CHK(check_args(args));
-  CU(cudaSetDevice(c->device));
+  for (int k = 0; k < nsrc; k++)
+    if (!src[k] || !dest[k]) return fail(B200KS_EINVAL, "b200ks_congrad_block: null field");
   int total = 0;
+  const int nm = nmembers(c);
+  std::vector<b200ks_invert_result> rr((size_t)nm * kMaxRhs);
   for (int k0 = 0; k0 < nsrc; k0 += kMaxRhs) {   // host staging vectors are reused group by group
     const int n = std::min(kMaxRhs, nsrc - k0);
-    DevVec *b[kMaxRhs], *x[kMaxRhs];
-    for (int q = 0; q < n; q++) {
-      if (!src[k0 + q] || !dest[k0 + q]) return fail(B200KS_EINVAL, "b200ks_congrad_block: null field");
-      CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q, &b[q]));
-      CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q + 1, &x[q]));
-      CHK(upload(c, *b[q], src[k0 + q], args->parity, host_prec));
-      CHK(upload(c, *x[q], dest[k0 + q], args->parity, host_prec));
-    }
-    const int it = congrad_block_any(c, n, b, x, mass, *args, res + k0);
+    const int it = with_verified_links(c, [&]() {
+      return run_all(c, [&](b200ks_ctx *c, int r) -> int {
+        CU(cudaSetDevice(c->device));
+        DevVec *b[kMaxRhs], *x[kMaxRhs];
+        for (int q = 0; q < n; q++) {
+          CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q, &b[q]));
+          CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q + 1, &x[q]));
+          CHK(upload(c, *b[q], src[k0 + q], args->parity, host_prec, false));
+          CHK(upload(c, *x[q], dest[k0 + q], args->parity, host_prec, false));
+        }
+        return congrad_block_any(c, n, b, x, mass, *args, rr.data() + (size_t)r * kMaxRhs);
+      });
+    });
     if (it < 0) return it;
-    for (int q = 0; q < n; q++) CHK(download(c, *x[q], dest[k0 + q], args->parity, host_prec));
+    CHK(run_all(c, [&](b200ks_ctx *c, int) -> int {
+      for (int q = 0; q < n; q++) {
+        DevVec *x = nullptr;
+        CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q + 1, &x));
+        CHK(download(c, *x, dest[k0 + q], args->parity, host_prec));
+      }
+      return 0;
+    }));
+    for (int q = 0; q < n; q++) res[k0 + q] = rr[q];
     total += it;
   }
   return total;
@@ -1989,6 +2455,7 @@ extern "C" int b200ks_congrad_block(b200ks_ctx *c, int nsrc, const void *const *
 // D applied to nrhs device vectors at once (double or single stencil on converted copies)
 extern "C" int b200ks_dslash_block_dev(b200ks_ctx *c, int nrhs, const int *vsrc, const int *vdest, int parity, int prec) {
   if (!c || nrhs < 1 || nrhs > kMaxRhs || !vsrc || !vdest) return fail(B200KS_EINVAL, "b200ks_dslash_block_dev: 1..4 fields");
+  MULTI(c, b200ks_dslash_block_dev(c, nrhs, vsrc, vdest, parity, prec));
   if (prec != B200KS_PREC_DOUBLE && prec != B200KS_PREC_SINGLE) return fail(B200KS_EINVAL, "b200ks_dslash_block_dev: double or single");
   if (parity != B200KS_EVEN && parity != B200KS_ODD && parity != B200KS_EVENANDODD) return fail(B200KS_EINVAL, "unrecognised parity");
   CU(cudaSetDevice(c->device));
@@ -2026,6 +2493,7 @@ extern "C" int b200ks_dslash_block_dev(b200ks_ctx *c, int nrhs, const int *vsrc,
 
 extern "C" int b200ks_dslash_block_time(b200ks_ctx *c, int prec, int nrhs, int parity, int n, double *ms) {
   if (!c || !ms || n <= 0 || nrhs < 1 || nrhs > kMaxRhs) return fail(B200KS_EINVAL, "b200ks_dslash_block_time: bad argument");
+  if (!c->sub.empty()) return fail(B200KS_ESTATE, "b200ks_dslash_block_time: single-GPU contexts only");
   if (prec != 1 && prec != 2) return fail(B200KS_EINVAL, "b200ks_dslash_block_time: prec must be 1 or 2");
   CU(cudaSetDevice(c->device));
   CHK(links_ensure(c, prec));
@@ -2128,12 +2596,12 @@ static int multicg_T(b200ks_ctx *c, const DevVec &b, DevVec *const *psim, const 
     e1.kind = 2; e1.s = shift0; e1.w = cgp; e1.r = nullptr; e1.red = c->d_state->red; e1.red_ext = c->d_state->red_ext;
     e1.stop = &c->d_state->stop;
     CHK(dslash_T<T>(c, *ttt, *ttt, pb, e1));
-    if (c->comm.active) {
-      if (!c->comm.p2p.on) LAUNCH1(c, combine_red_kernel, c->d_state, 1);
+    if (c->comm.active && !c->comm.p2p.on) {   // (peer-to-peer: all-reduced inside the stencil's finish kernel)
+      LAUNCH1(c, combine_red_kernel, c->d_state, 1);
       CHK(allreduce(c, c->d_state->red, 1));
     }
     LAUNCH(c, (ms_resid_kernel<T>), grid, (T2 *)r->p[pb], (const T2 *)ttt->p[pb], g.stride, g.Vh, c->d_state, c->ws);
-    CHK(allreduce(c, &c->d_state->rsq_new, 1));
+    CHK(allreduce(c, &c->d_state->rsq_new, 1, false, &c->d_state->stop));
     LAUNCH1(c, ms_scalar_kernel, c->d_state);
     LAUNCH(c, (ms_update_kernel<T>), grid, ptrs, (const T2 *)r->p[pb], g.stride, g.Vh, c->d_state);
     LAUNCH1(c, ms_scroll_kernel, c->d_state);
@@ -2213,6 +2681,14 @@ extern "C" int b200ks_multicg_dev(b200ks_ctx *c, int vsrc, const int *vpsim, con
   if (!c || !res || (n > 0 && (!vpsim || !offsets))) return fail(B200KS_EINVAL, "b200ks_multicg_dev: bad argument");
   CHK(check_ms_args(offsets, n, args));
   if (n == 0) return 0;
+  if (!c->sub.empty()) {
+    std::vector<b200ks_invert_result> rr(c->sub.size() * (size_t)n);
+    const int it = run_all(c, [&](b200ks_ctx *c, int r) -> int {
+      return b200ks_multicg_dev(c, vsrc, vpsim, offsets, n, args, rr.data() + (size_t)r * n);
+    });
+    if (it >= 0) for (int j = 0; j < n; j++) res[j] = rr[j];
+    return it;
+  }
   DevVec *b = uvec(c, vsrc);
   if (!b) return B200KS_EINVAL;
   std::vector<DevVec *> ps(n);
@@ -2229,16 +2705,32 @@ extern "C" int b200ks_multicg(b200ks_ctx *c, const void *src, void *const *psim,
   if (!c || !src || !res || (n > 0 && (!psim || !offsets))) return fail(B200KS_EINVAL, "b200ks_multicg: null argument");
   CHK(check_ms_args(offsets, n, args));
   if (n == 0) return 0;
-  CU(cudaSetDevice(c->device));
-  CHK(links_ensure(c, 2));
-  DevVec *b = nullptr;
-  CHK(pool_get(c, 2, 0, &b));
-  CHK(upload(c, *b, src, args->parity, host_prec));
-  std::vector<DevVec *> ps(n);
-  for (int j = 0; j < n; j++) CHK(pool_get(c, 2, 5 + B200KS_MAX_SHIFTS + j, &ps[j]));
-  int it = multicg_any(c, *b, ps.data(), offsets, n, *args, res);
+  for (int j = 0; j < n; j++)
+    if (!psim[j]) return fail(B200KS_EINVAL, "b200ks_multicg: null solution field");
+  const int nm = nmembers(c);
+  std::vector<b200ks_invert_result> rr((size_t)nm * n);
+  const int it = with_verified_links(c, [&]() {
+    return run_all(c, [&](b200ks_ctx *c, int r) -> int {
+      CU(cudaSetDevice(c->device));
+      CHK(links_ensure(c, 2));
+      DevVec *b = nullptr;
+      CHK(pool_get(c, 2, 0, &b));
+      CHK(upload(c, *b, src, args->parity, host_prec, false));
+      std::vector<DevVec *> ps(n);
+      for (int j = 0; j < n; j++) CHK(pool_get(c, 2, 5 + B200KS_MAX_SHIFTS + j, &ps[j]));
+      return multicg_any(c, *b, ps.data(), offsets, n, *args, rr.data() + (size_t)r * n);
+    });
+  });
   if (it < 0) return it;
-  for (int j = 0; j < n; j++) CHK(download(c, *ps[j], psim[j], args->parity, host_prec));
+  CHK(run_all(c, [&](b200ks_ctx *c, int) -> int {
+    for (int j = 0; j < n; j++) {
+      DevVec *ps = nullptr;
+      CHK(pool_get(c, 2, 5 + B200KS_MAX_SHIFTS + j, &ps));
+      CHK(download(c, *ps, psim[j], args->parity, host_prec));
+    }
+    return 0;
+  }));
+  for (int j = 0; j < n; j++) res[j] = rr[j];
   return it;
 }
 
@@ -2268,6 +2760,7 @@ static void eig_release(b200ks_ctx *c) {
 // sequences deflate their trial solutions like mat_invert_uml_field does with qic->deflate set.
 extern "C" int b200ks_eig_set(b200ks_ctx *c, int nvecs, const int *vecs, const double *eigval, int use_in_uml) {
   if (!c || nvecs < 0 || (nvecs > 0 && (!vecs || !eigval))) return fail(B200KS_EINVAL, "b200ks_eig_set: bad argument");
+  if (!c->sub.empty()) return nvecs == 0 ? 0 : fail(B200KS_ESTATE, "deflation: single-GPU contexts only");
   if (c->comm.active) return fail(B200KS_ESTATE, "deflation: single-GPU contexts only");
   CU(cudaSetDevice(c->device));
   eig_release(c);
@@ -2304,6 +2797,7 @@ extern "C" int b200ks_eig_set(b200ks_ctx *c, int nvecs, const int *vecs, const d
 extern "C" int b200ks_eig_count(b200ks_ctx *c) { return c ? c->eig.n : 0; }
 extern "C" int b200ks_eig_use_in_uml(b200ks_ctx *c, int on) {
   if (!c) return fail(B200KS_EINVAL, "null context");
+  if (!c->sub.empty()) return on ? fail(B200KS_ESTATE, "deflation: single-GPU contexts only") : 0;
   c->eig.uml = on != 0;
   return 0;
 }
@@ -2322,6 +2816,7 @@ static int deflate_dv(b200ks_ctx *c, DevVec &dst, const DevVec &src, double mass
 }
 
 extern "C" int b200ks_deflate_dev(b200ks_ctx *c, int vsrc, int vdst, double mass, int parity) {
+  if (c && !c->sub.empty()) return fail(B200KS_ESTATE, "deflation: single-GPU contexts only");
   DevVec *s = uvec(c, vsrc), *d = uvec(c, vdst);
   if (!s || !d) return B200KS_EINVAL;
   if (s == d) return fail(B200KS_EINVAL, "b200ks_deflate_dev: source and trial solution must be different fields");
@@ -2380,6 +2875,14 @@ extern "C" int b200ks_mat_invert_uml_dev(b200ks_ctx *c, int nsrc, const int *vsr
                                          const b200ks_invert_args *args, b200ks_invert_result *res) {
   if (!c || !res || nsrc < 1 || !vsrc || !vdst || !args) return fail(B200KS_EINVAL, "b200ks_mat_invert_uml_dev: bad argument");
   if (args->max_iter <= 0 || args->nrestart <= 0) return fail(B200KS_EINVAL, "max_iter and nrestart must be positive");
+  if (!c->sub.empty()) {
+    std::vector<b200ks_invert_result> rr(c->sub.size() * (size_t)(2 * nsrc));
+    const int it = run_all(c, [&](b200ks_ctx *c, int r) -> int {
+      return b200ks_mat_invert_uml_dev(c, nsrc, vsrc, vdst, mass, args, rr.data() + (size_t)r * 2 * nsrc);
+    });
+    if (it >= 0) for (int k = 0; k < 2 * nsrc; k++) res[k] = rr[k];
+    return it;
+  }
   std::vector<DevVec *> s(nsrc), d(nsrc);
   for (int k = 0; k < nsrc; k++) {
     s[k] = uvec(c, vsrc[k]);
@@ -2395,21 +2898,36 @@ extern "C" int b200ks_mat_invert_uml(b200ks_ctx *c, int nsrc, const void *const 
                                      const b200ks_invert_args *args, b200ks_invert_result *res, int host_prec) {
   if (!c || !res || nsrc < 1 || !src || !dst || !args) return fail(B200KS_EINVAL, "b200ks_mat_invert_uml: bad argument");
   if (args->max_iter <= 0 || args->nrestart <= 0) return fail(B200KS_EINVAL, "max_iter and nrestart must be positive");
-  CU(cudaSetDevice(c->device));
+  for (int k = 0; k < nsrc; k++)
+    if (!src[k] || !dst[k]) return fail(B200KS_EINVAL, "b200ks_mat_invert_uml: null field");
   int total = 0;
+  const int nm = nmembers(c);
+  std::vector<b200ks_invert_result> rr((size_t)nm * 2 * kMaxRhs);
   for (int k0 = 0; k0 < nsrc; k0 += kMaxRhs) {
     const int n = std::min(kMaxRhs, nsrc - k0);
-    DevVec *s[kMaxRhs], *d[kMaxRhs];
-    for (int q = 0; q < n; q++) {
-      if (!src[k0 + q] || !dst[k0 + q]) return fail(B200KS_EINVAL, "b200ks_mat_invert_uml: null field");
-      CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q, &s[q]));
-      CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q + 1, &d[q]));
-      CHK(upload(c, *s[q], src[k0 + q], B200KS_EVENANDODD, host_prec));
-      CHK(upload(c, *d[q], dst[k0 + q], B200KS_EVENANDODD, host_prec));
-    }
-    const int it = uml_any(c, n, s, d, mass, *args, res + 2 * k0);
+    const int it = with_verified_links(c, [&]() {
+      return run_all(c, [&](b200ks_ctx *c, int r) -> int {
+        CU(cudaSetDevice(c->device));
+        DevVec *s[kMaxRhs], *d[kMaxRhs];
+        for (int q = 0; q < n; q++) {
+          CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q, &s[q]));
+          CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q + 1, &d[q]));
+          CHK(upload(c, *s[q], src[k0 + q], B200KS_EVENANDODD, host_prec, false));
+          CHK(upload(c, *d[q], dst[k0 + q], B200KS_EVENANDODD, host_prec, false));
+        }
+        return uml_any(c, n, s, d, mass, *args, rr.data() + (size_t)r * 2 * kMaxRhs);
+      });
+    });
     if (it < 0) return it;
-    for (int q = 0; q < n; q++) CHK(download(c, *d[q], dst[k0 + q], B200KS_EVENANDODD, host_prec));
+    CHK(run_all(c, [&](b200ks_ctx *c, int) -> int {
+      for (int q = 0; q < n; q++) {
+        DevVec *d = nullptr;
+        CHK(pool_get(c, 2, kBlockPool + 4 * kMaxRhs + 2 * q + 1, &d));
+        CHK(download(c, *d, dst[k0 + q], B200KS_EVENANDODD, host_prec));
+      }
+      return 0;
+    }));
+    for (int q = 0; q < 2 * n; q++) res[2 * k0 + q] = rr[q];
     total += it;
   }
   return total;
@@ -2427,33 +2945,52 @@ extern "C" int b200ks_multicg_rational(b200ks_ctx *c, const void *src, void *con
   if (!c || !src || !res || n < 1 || !offsets) return fail(B200KS_EINVAL, "b200ks_multicg_rational: bad argument");
   if (residues && !dest) return fail(B200KS_EINVAL, "b200ks_multicg_rational: residues without dest");
   CHK(check_ms_args(offsets, n, args));
-  CU(cudaSetDevice(c->device));
-  CHK(links_ensure(c, 2));
-  const int pb = parity_bit(args->parity);
-  DevVec *b = nullptr, *acc = nullptr;
-  CHK(pool_get(c, 2, 0, &b));
-  CHK(upload(c, *b, src, args->parity, host_prec));
-  std::vector<DevVec *> ps(n);
-  for (int j = 0; j < n; j++) CHK(pool_get(c, 2, 5 + B200KS_MAX_SHIFTS + j, &ps[j]));
-  const int it = multicg_any(c, *b, ps.data(), offsets, n, *args, res);
-  if (it < 0) return it;
-  if (residues) {
-    CHK(pool_get(c, 2, 1, &acc));
-    axpby_d(c, *acc, residues[0], *b, 0.0, nullptr, pb);
-    for (int j = 0; j < n; j++) axpby_d(c, *acc, 1.0, *acc, residues[j + 1], ps[j], pb);
-    CHK(download(c, *acc, dest, args->parity, host_prec));
-  }
-  if (psim) {
-    if (fill_other) {
-      Epi e;
-      for (int j = 0; j < n; j++) CHK(dslash_T<double>(c, *ps[j], *ps[j], pb ^ 1, e));
-      CHK(halo_check(c));
-    }
-    for (int j = 0; j < n; j++) {
+  if (psim)
+    for (int j = 0; j < n; j++)
       if (!psim[j]) return fail(B200KS_EINVAL, "b200ks_multicg_rational: null solution field");
-      CHK(download(c, *ps[j], psim[j], fill_other ? B200KS_EVENANDODD : args->parity, host_prec));
+  const int pb = parity_bit(args->parity);
+  const int nm = nmembers(c);
+  std::vector<b200ks_invert_result> rr((size_t)nm * n);
+  const int it = with_verified_links(c, [&]() {
+    return run_all(c, [&](b200ks_ctx *c, int r) -> int {
+      CU(cudaSetDevice(c->device));
+      CHK(links_ensure(c, 2));
+      DevVec *b = nullptr, *acc = nullptr;
+      CHK(pool_get(c, 2, 0, &b));
+      CHK(upload(c, *b, src, args->parity, host_prec, false));
+      std::vector<DevVec *> ps(n);
+      for (int j = 0; j < n; j++) CHK(pool_get(c, 2, 5 + B200KS_MAX_SHIFTS + j, &ps[j]));
+      const int it = multicg_any(c, *b, ps.data(), offsets, n, *args, rr.data() + (size_t)r * n);
+      if (it < 0) return it;
+      if (residues) {
+        CHK(pool_get(c, 2, 1, &acc));
+        axpby_d(c, *acc, residues[0], *b, 0.0, nullptr, pb);
+        for (int j = 0; j < n; j++) axpby_d(c, *acc, 1.0, *acc, residues[j + 1], ps[j], pb);
+      }
+      if (psim && fill_other) {
+        Epi e;
+        for (int j = 0; j < n; j++) CHK(dslash_T<double>(c, *ps[j], *ps[j], pb ^ 1, e));
+        CHK(halo_check(c));
+      }
+      return it;
+    });
+  });
+  if (it < 0) return it;
+  CHK(run_all(c, [&](b200ks_ctx *c, int) -> int {
+    if (residues) {
+      DevVec *acc = nullptr;
+      CHK(pool_get(c, 2, 1, &acc));
+      CHK(download(c, *acc, dest, args->parity, host_prec));
     }
-  }
+    if (psim)
+      for (int j = 0; j < n; j++) {
+        DevVec *ps = nullptr;
+        CHK(pool_get(c, 2, 5 + B200KS_MAX_SHIFTS + j, &ps));
+        CHK(download(c, *ps, psim[j], fill_other ? B200KS_EVENANDODD : args->parity, host_prec));
+      }
+    return 0;
+  }));
+  for (int j = 0; j < n; j++) res[j] = rr[j];
   return it;
 }
 
@@ -2471,10 +3008,13 @@ extern "C" int b200ks_comm_unique_id(void *out128) {
 // Ghost buffers, boundary-site list, peer mappings: everything a context with at least one
 // partitioned direction needs.  Peer-to-peer halos are the default; B200KS_HALO=nccl selects
 // the ncclSend/ncclRecv path (also the fallback when the peer mapping cannot be set up).
+// Members of a single-process multi-GPU context (c->member_rank >= 0) exchange their block
+// pointers through the leader's bootstrap area and enable plain peer access -- no NCCL, no IPC.
 static int comm_setup(b200ks_ctx *c) {
   Comm &cm = c->comm;
   const Geom &g = c->g;
   cm.active = true;
+  if (cm.nranks > kMaxRanks) return fail(B200KS_EINVAL, "at most " + std::to_string(kMaxRanks) + " ranks");
   int lo = 0, hi = 0;
   CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   CU(cudaStreamCreateWithPriority(&cm.stream, cudaStreamNonBlocking, hi));
@@ -2498,12 +3038,13 @@ static int comm_setup(b200ks_ctx *c) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   cm.push_ctas = getenv("B200KS_PUSH_CTAS") ? std::max(1, atoi(getenv("B200KS_PUSH_CTAS"))) : sms;
   const char *mode = getenv("B200KS_HALO");
-  const bool want_p2p = !(mode && strcmp(mode, "nccl") == 0);
+  const bool member = c->member_rank >= 0;
+  const bool want_p2p = member || !(mode && strcmp(mode, "nccl") == 0);
   if (cm.nranks == 1 && !want_p2p) return fail(B200KS_EINVAL, "a self-partitioned single rank needs the peer-to-peer halo path");
   P2P &pp = cm.p2p;
   if (want_p2p) {
     pp.ghost_bytes = (size_t)3 * g.gstride * sizeof(double2);
-    const size_t bytes = kP2PFlagBytes + 2 * pp.ghost_bytes;
+    const size_t bytes = kP2PHeaderBytes + 2 * pp.ghost_bytes;
     CHK(dev_alloc(c, (void **)&pp.block, bytes));
     CU(cudaMemset(pp.block, 0, bytes));
     void *q = nullptr;
@@ -2513,9 +3054,31 @@ static int comm_setup(b200ks_ctx *c) {
     pp.err = (int *)q;
     CU(cudaMemset(pp.ticket, 0, sizeof(unsigned)));
     CU(cudaMemset(pp.err, 0, sizeof(int)));
+    CU(cudaDeviceSynchronize());
     bool ok = true;
-    std::vector<cudaIpcMemHandle_t> handles(cm.nranks);
-    if (cm.nranks > 1) {
+    pp.peer_all[cm.rank] = pp.block;
+    if (member) {
+      MultiState *ms = c->multi;
+      ms->slot[cm.rank] = pp.block;
+      MEET(ms);
+      for (int r = 0; r < cm.nranks; r++) {
+        if (r == cm.rank) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, c->device, ms->devices[r]) != cudaSuccess || !can) { cudaGetLastError(); ok = false; continue; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(ms->devices[r], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+        cudaGetLastError();
+        pp.peer_all[r] = (char *)ms->slot[r];
+      }
+      // all or nothing (there is no NCCL fallback inside one process)
+      MEET(ms);   // (everybody has read the block pointers)
+      ms->slot[cm.rank] = ok ? pp.block : nullptr;
+      MEET(ms);
+      for (int r = 0; r < cm.nranks; r++) ok = ok && ms->slot[r] != nullptr;
+      MEET(ms);
+      if (!ok) return fail(B200KS_ECOMM, "peer access between the devices of a multi-GPU context is not available");
+    } else if (cm.nranks > 1) {
+      std::vector<cudaIpcMemHandle_t> handles(cm.nranks);
       cudaIpcMemHandle_t mine;
       ok = cudaIpcGetMemHandle(&mine, pp.block) == cudaSuccess;
       if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
@@ -2536,31 +3099,19 @@ static int comm_setup(b200ks_ctx *c) {
         memcpy(&handles[r], all.data() + hb * r, sizeof(cudaIpcMemHandle_t));
         ok = ok && all[hb * r + sizeof(cudaIpcMemHandle_t)] == 1;
       }
-    }
-    int nopen = 0;
-    int opened_rank[4];
-    for (int d = 2; d < 4 && ok; d++)
-      for (int side = 0; side < 2 && ok; side++) {
-        const int r = cm.nbr[d][side];
-        if (!g.part[d]) continue;
-        if (r == cm.rank) { pp.peer_block[d - 2][side] = pp.block; continue; }
-        char *ptr = nullptr;
-        for (int k = 0; k < nopen; k++)
-          if (opened_rank[k] == r) ptr = (char *)pp.opened[k];
-        if (!ptr) {
-          void *vp = nullptr;
-          if (cudaIpcOpenMemHandle(&vp, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-            cudaGetLastError();
-            ok = false;
-            break;
-          }
-          pp.opened[nopen] = vp;
-          opened_rank[nopen++] = r;
-          ptr = (char *)vp;
+      // every rank maps every other rank's block: neighbours for the halos, all for the reductions
+      for (int r = 0; r < cm.nranks && ok; r++) {
+        if (r == cm.rank) continue;
+        void *vp = nullptr;
+        if (cudaIpcOpenMemHandle(&vp, handles[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = false;
+          break;
         }
-        pp.peer_block[d - 2][side] = ptr;
+        pp.opened[r] = vp;
+        pp.peer_all[r] = (char *)vp;
       }
-    if (cm.nranks > 1) {  // all or nothing: a rank that could not map a neighbour sends everyone to NCCL
+      // all or nothing: a rank that could not map a peer sends everyone to NCCL
       double flag = ok ? 0.0 : 1.0;
       CU(cudaMemcpy(c->d_scal, &flag, sizeof(double), cudaMemcpyHostToDevice));
       NC(nccl().AllReduce(c->d_scal, c->d_scal, 1, ncclDouble, ncclSum, cm.red, c->stream));
@@ -2568,6 +3119,10 @@ static int comm_setup(b200ks_ctx *c) {
       CU(cudaMemcpy(&flag, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost));
       ok = flag == 0.0;
     }
+    if (ok)
+      for (int d = 2; d < 4; d++)
+        for (int side = 0; side < 2; side++)
+          if (g.part[d]) pp.peer_block[d - 2][side] = pp.peer_all[cm.nbr[d][side]];
     pp.on = ok;
     if (!ok && cm.nranks == 1) return fail(B200KS_ECOMM, "peer-to-peer halo setup failed");
   }
@@ -2581,11 +3136,14 @@ static int comm_setup(b200ks_ctx *c) {
 
 extern "C" int b200ks_halo_mode(b200ks_ctx *c) {
   if (!c) return fail(B200KS_EINVAL, "null context");
+  if (!c->sub.empty()) c = c->sub[0];
   return !c->comm.active ? 0 : c->comm.p2p.on ? 2 : 1;
 }
 
-extern "C" b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4], int rank, int nranks,
-                                          const void *nccl_unique_id, int device) {
+// One rank of a decomposed lattice: its own process (nccl_unique_id != NULL: NCCL bootstrap, CUDA IPC)
+// or one member of a single-process multi-GPU context (ms != NULL: in-process bootstrap).
+static b200ks_ctx *create_rank(const int latsize[4], const int grid[4], int rank, int nranks, const void *nccl_unique_id,
+                               int device, MultiState *ms) {
   if (!latsize || !grid) { fail(B200KS_EINVAL, "b200ks_create_dist: null argument"); return nullptr; }
   if (grid[0] != 1 || grid[1] != 1 || grid[2] < 1 || grid[3] < 1 || grid[2] * grid[3] != nranks || rank < 0 || rank >= nranks) {
     fail(B200KS_EINVAL, "b200ks_create_dist: grid must be {1,1,gz,gt} with gz*gt == nranks");
@@ -2605,7 +3163,7 @@ extern "C" b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4
     origin[d] = coord[d] * local[d];
   }
   if (!any) return create_common(latsize, local, part, origin, device);
-  if (nranks > 1) {
+  if (nranks > 1 && !ms) {
     if (!nccl_unique_id) { fail(B200KS_EINVAL, "b200ks_create_dist: null nccl_unique_id"); return nullptr; }
     if (!nccl().ok) { fail(B200KS_ECOMM, "libnccl.so.2 could not be loaded"); return nullptr; }
   }
@@ -2614,6 +3172,10 @@ extern "C" b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4
   Comm &cm = c->comm;
   cm.rank = rank;
   cm.nranks = nranks;
+  if (ms) {
+    c->multi = ms;
+    c->member_rank = rank;
+  }
   for (int d = 0; d < 4; d++) { cm.grid[d] = grid[d]; cm.coord[d] = coord[d]; }
   auto rank_of = [&](int zc, int tc) { return ((tc + grid[3]) % grid[3]) * grid[2] + (zc + grid[2]) % grid[2]; };
   cm.nbr[2][0] = rank_of(coord[2] - 1, coord[3]);
@@ -2621,7 +3183,7 @@ extern "C" b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4
   cm.nbr[3][0] = rank_of(coord[2], coord[3] - 1);
   cm.nbr[3][1] = rank_of(coord[2], coord[3] + 1);
   auto init = [&]() -> int {
-    if (nranks > 1) {
+    if (nranks > 1 && !ms) {
       ncclUniqueId ids[2];
       memcpy(ids, nccl_unique_id, sizeof(ncclUniqueId));
       // the second communicator (all-reduces) gets its id from rank 0 over the first one
@@ -2655,9 +3217,126 @@ extern "C" b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4
   return c;
 }
 
+extern "C" b200ks_ctx *b200ks_create_dist(const int latsize[4], const int grid[4], int rank, int nranks,
+                                          const void *nccl_unique_id, int device) {
+  return create_rank(latsize, grid, rank, nranks, nccl_unique_id, device, nullptr);
+}
+
+// ---- single-process multi-GPU context ---------------------------------------------------------
+static void multi_worker(b200ks_ctx *leader, int r) {
+  MultiState *ms = leader->multi;
+  cudaSetDevice(ms->devices[r]);
+  unsigned long long seen = 0;
+  for (;;) {
+    std::function<int(b200ks_ctx *, int)> task;
+    {
+      std::unique_lock<std::mutex> lk(ms->mu);
+      ms->cv_go.wait(lk, [&] { return ms->quit || ms->gen != seen; });
+      if (ms->quit) return;
+      seen = ms->gen;
+      task = ms->task;
+    }
+    g_err.clear();
+    const int rc = task(r < (int)leader->sub.size() ? leader->sub[r] : nullptr, r);
+    {
+      std::unique_lock<std::mutex> lk(ms->mu);
+      ms->rc[r] = rc;
+      ms->err[r] = rc < 0 ? g_err : std::string();
+      if (--ms->remaining == 0) ms->cv_done.notify_all();
+    }
+  }
+}
+
+static void multi_grid(int ngpu, int grid[4]) {   // t first (up to 4 ways), then z: north_star's decomposition
+  int gt = 1;
+  while (gt < 4 && ngpu % (gt * 2) == 0) gt *= 2;
+  grid[0] = grid[1] = 1;
+  grid[3] = gt;
+  grid[2] = ngpu / gt;
+}
+
+extern "C" b200ks_ctx *b200ks_create_multi(const int latsize[4], int ngpu, const int *devices) {
+  if (!latsize || ngpu < 1) { fail(B200KS_EINVAL, "b200ks_create_multi: bad argument"); return nullptr; }
+  if (ngpu == 1) return create_common(latsize, latsize, std::vector<int>(4, 0).data(), std::vector<int>(4, 0).data(), devices ? devices[0] : 0);
+  if (ngpu > kMaxRanks) { fail(B200KS_EINVAL, "b200ks_create_multi: too many GPUs"); return nullptr; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    fail(B200KS_ECUDA, "no CUDA device: libb200ks has no CPU fallback");
+    return nullptr;
+  }
+  int grid[4];
+  multi_grid(ngpu, grid);
+  for (int d = 2; d < 4; d++) {
+    const int l = latsize[d] / grid[d];
+    if (latsize[d] % grid[d] || (grid[d] > 1 && (l < 6 || (l & 1)))) {
+      fail(B200KS_EINVAL, "b200ks_create_multi: lattice " + std::to_string(latsize[2]) + " x " + std::to_string(latsize[3]) +
+                              " (z x t) cannot be split " + std::to_string(grid[2]) + " x " + std::to_string(grid[3]) +
+                              " ways (local extents must be even and >= 6)");
+      return nullptr;
+    }
+  }
+  if (grid[2] * grid[3] != ngpu) { fail(B200KS_EINVAL, "b200ks_create_multi: unsupported GPU count"); return nullptr; }
+  b200ks_ctx *L = new b200ks_ctx;
+  memcpy(L->global, latsize, sizeof(L->global));
+  MultiState *ms = new MultiState;
+  L->multi = ms;
+  ms->n = ngpu;
+  for (int r = 0; r < ngpu; r++) {
+    const int dev = devices ? devices[r] : r;
+    if (dev < 0 || dev >= ndev) {
+      fail(B200KS_EINVAL, "b200ks_create_multi: device " + std::to_string(dev) + " of " + std::to_string(ndev) + " does not exist");
+      delete ms;
+      delete L;
+      return nullptr;
+    }
+    ms->devices.push_back(dev);
+  }
+  L->device = ms->devices[0];
+  ms->rc.assign(ngpu, 0);
+  ms->err.assign(ngpu, std::string());
+  ms->slot.assign(ngpu, nullptr);
+  ms->barrier.n = ngpu;
+  L->sub.assign(ngpu, nullptr);
+  for (int r = 0; r < ngpu; r++) ms->workers.emplace_back(multi_worker, L, r);
+  // every member is created by its own thread (the bootstrap meets at barriers)
+  bool any_failed = false;
+  {
+    std::vector<b200ks_ctx *> made(ngpu, nullptr);
+    const int rc = run_all(L, [&](b200ks_ctx *, int r) -> int {
+      made[r] = create_rank(latsize, grid, r, ngpu, nullptr, ms->devices[r], ms);
+      if (!made[r]) {
+        ms->barrier.abort();   // the others must not wait for this member at the bootstrap barriers
+        return B200KS_ECUDA;
+      }
+      return 0;
+    });
+    for (int r = 0; r < ngpu; r++) L->sub[r] = made[r];
+    any_failed = rc < 0;
+  }
+  if (any_failed) {
+    const std::string why = g_err;
+    b200ks_destroy(L);
+    fail(B200KS_ECUDA, "b200ks_create_multi: " + why);
+    return nullptr;
+  }
+  // host view of each member: its runs inside MILC's global arrays
+  const size_t S2h = (size_t)latsize[0] * latsize[1] / 2;
+  size_t GVh = S2h * latsize[2] * latsize[3];
+  for (int r = 0; r < ngpu; r++) {
+    b200ks_ctx *m = L->sub[r];
+    m->hv_row_sites = (size_t)m->g.L[2] * S2h;
+    m->hv_nrows = (size_t)m->g.L[3];
+    m->hv_pitch_sites = (size_t)latsize[2] * S2h;
+    m->hv_offset_sites = S2h * ((size_t)m->g.origin[2] + (size_t)latsize[2] * m->g.origin[3]);
+    m->hv_parity_sites = GVh;
+  }
+  return L;
+}
+
 // ---------------------------------------------------------------------------------------------
 // synthetic fields on the device, link read-back
 extern "C" int b200ks_vec_gaussian(b200ks_ctx *c, int h, int parity, unsigned long long seed) {
+  MULTI(c, b200ks_vec_gaussian(c, h, parity, seed));
   DevVec *v = uvec(c, h);
   if (!v) return B200KS_EINVAL;
   CU(cudaSetDevice(c->device));
@@ -2671,6 +3350,8 @@ extern "C" int b200ks_vec_gaussian(b200ks_ctx *c, int h, int parity, unsigned lo
 extern "C" int b200ks_links_synthetic(b200ks_ctx *c, unsigned long long seed, int long_recon) {
   if (!c) return fail(B200KS_EINVAL, "null context");
   CHK(check_recon(long_recon));
+  if (c->member_rank < 0) { watch_join_thread(c); c->watch.pending = false; c->watch.have = false; }
+  MULTI(c, b200ks_links_synthetic(c, seed, long_recon));
   CU(cudaSetDevice(c->device));
   CHK(links_alloc(c, 2, 9));
   int lsites = c->g.Vh;
@@ -2689,6 +3370,7 @@ extern "C" int b200ks_links_synthetic(b200ks_ctx *c, unsigned long long seed, in
 extern "C" int b200ks_links_download(b200ks_ctx *c, void *fat, void *lng, int host_prec) {
   if (!c || !fat || !lng) return fail(B200KS_EINVAL, "b200ks_links_download: null argument");
   if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
+  MULTI(c, b200ks_links_download(c, fat, lng, host_prec));
   if (c->link_master == 0) return fail(B200KS_ESTATE, "links not loaded");
   CU(cudaSetDevice(c->device));
   const int m = c->link_master;
@@ -2710,8 +3392,9 @@ extern "C" int b200ks_links_download(b200ks_ctx *c, void *fat, void *lng, int ho
       else if (m == 2 && host_prec == 1) LAUNCH(c, (unpack_link_kernel<double, float>), grid, (float *)stage, (const double2 *)src, c->g.lstride, c->g.Vh);
       else if (m == 1 && host_prec == 2) LAUNCH(c, (unpack_link_kernel<float, double>), grid, (double *)stage, (const float2 *)src, c->g.lstride, c->g.Vh);
       else LAUNCH(c, (unpack_link_kernel<float, float>), grid, (float *)stage, (const float2 *)src, c->g.lstride, c->g.Vh);
-      char *h = (char *)(which ? lng : fat);
-      CHK(d2h(c, h + (size_t)p * half_bytes, stage, half_bytes));
+      HostRows hr;
+      char *h = (char *)host_half(c, which ? lng : fat, p, 72 * hs, hr);
+      CHK(d2h_rows(c, h, stage, hr));
     }
   CU(cudaStreamSynchronize(c->stream));
   return check_launch("unpack_link_kernel");

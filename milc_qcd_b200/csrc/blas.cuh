@@ -7,6 +7,7 @@
 // already-enqueued batch into a no-op.  The host polls the flag once per batch.
 #pragma once
 #include "common.cuh"
+#include "comm.cuh"
 #include "layout.cuh"
 
 namespace b200ks {
@@ -189,17 +190,86 @@ struct FinishSlot {
   double *out;
   CgState *st;             // scalar step target (scalar_flags != 0)
   const int *stop;
+  double *extra;           // partitioned contexts: nextra more values (this rank's share, e.g. the previous
+  int nextra;              // update's |r|^2) that ride along in the all-reduce and are replaced by their sums
 };
 struct FinishArg {
   FinishSlot s[kMaxRhs];
   int nblk;
   int scalar_flags;        // 0: sums only; else bit 0 on, bit 1 use_rel, bit 2 single (cg_scalar_step)
 };
+
+// ---- flag-based all-reduce over the ranks of a partitioned context (comm.cuh RedBox) -----------
+// Block-wide: v[0..n) in shared memory holds this rank's values on entry and the sums (kMax: the
+// maxima) over all ranks on return, bit-identical on every rank.  n <= 8, blockDim >= 8 * nranks.
+template <bool kMax>
+__device__ __forceinline__ void p2p_allreduce_block(double *v, int n, const RedComm &rc) {
+  RedBox *own = rc.box[rc.rank];
+  __shared__ unsigned long long s_seq;
+  if (threadIdx.x == 0) s_seq = own->count + 1;
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int buf = (int)(seq & 1ull);
+  const int t = threadIdx.x;
+  if (t < rc.nranks * 8) {
+    const int q = t >> 3, k = t & 7;
+    if (k < n) {
+      volatile double *dst = &rc.box[q]->val[buf][rc.rank][k];
+      *dst = v[k];
+    }
+  }
+  __threadfence_system();   // every thread's mailbox stores before ...
+  __syncthreads();          // ... the flag stores below (other threads')
+  if (t < rc.nranks) {
+    unsigned long long *f = &rc.box[t]->flag[rc.rank];
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
+    const unsigned long long *mine = &own->flag[t];
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long x;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(x) : "l"(mine) : "memory");
+      if (x >= seq) break;
+      if (clock64() - t0 > rc.timeout) {
+        *rc.err = 100 + t;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (t < n) {
+    double s = kMax ? -1.7976931348623157e308 : 0.0;
+    for (int q = 0; q < rc.nranks; q++) {
+      const volatile double *src = &own->val[buf][q][t];
+      const double x = *src;
+      s = kMax ? fmax(s, x) : s + x;
+    }
+    v[t] = s;
+  }
+  if (t == 0) own->count = seq;
+  __syncthreads();
+}
+
+// stand-alone form: d[0..n) <- sum (max) over ranks
+constexpr int kAllreduceThreads = 128;
+template <bool kMax>
+__global__ void __launch_bounds__(kAllreduceThreads) p2p_allreduce_kernel(double *d, int n, const RedComm rc, const int *stop) {
+  if (stop != nullptr && *stop) return;
+  __shared__ double v[8];
+  if (threadIdx.x < 8) v[threadIdx.x] = threadIdx.x < n ? d[threadIdx.x] : 0.0;
+  __syncthreads();
+  p2p_allreduce_block<kMax>(v, n, rc);
+  if (threadIdx.x < n) d[threadIdx.x] = v[threadIdx.x];
+}
+
 constexpr int kFinishThreads = 1024;
-__global__ void __launch_bounds__(kFinishThreads) reduce_finish_kernel(const FinishArg a) {
+// kComm: the context is partitioned; slot 0's sums (and its `extra` values) are all-reduced over the
+// ranks before they are stored (one slot per launch).
+template <bool kComm>
+__global__ void __launch_bounds__(kFinishThreads) reduce_finish_kernel(const FinishArg a, const RedComm rc) {
   const FinishSlot &f = a.s[blockIdx.x];
   if (f.stop != nullptr && *f.stop) return;
   __shared__ double sm[3][kFinishThreads / 32];
+  __shared__ double tot[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double s[3] = {0, 0, 0};
   for (int b0 = threadIdx.x; b0 < a.nblk; b0 += 4 * kFinishThreads) {
@@ -228,9 +298,21 @@ __global__ void __launch_bounds__(kFinishThreads) reduce_finish_kernel(const Fin
       double v = sm[k][lane];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && k < f.nval) f.out[k] = v;
+      if (lane == 0) tot[k] = v;
     }
-    if (a.scalar_flags && lane == 0) cg_scalar_step(f.st, (a.scalar_flags >> 1) & 1, (a.scalar_flags >> 2) & 1);
+  }
+  if (kComm) {
+    if (threadIdx.x < f.nextra) tot[f.nval + threadIdx.x] = f.extra[threadIdx.x];
+    __syncthreads();
+    p2p_allreduce_block<false>(tot, f.nval + f.nextra, rc);
+    if (threadIdx.x < f.nextra) f.extra[threadIdx.x] = tot[f.nval + threadIdx.x];
+  } else {
+    __syncthreads();
+  }
+  if (threadIdx.x < f.nval) f.out[threadIdx.x] = tot[threadIdx.x];
+  if (a.scalar_flags) {
+    __syncthreads();   // the scalar step reads what the threads above have just stored
+    if (threadIdx.x == 0) cg_scalar_step(f.st, (a.scalar_flags >> 1) & 1, (a.scalar_flags >> 2) & 1);
   }
 }
 

@@ -62,22 +62,51 @@ inline NcclApi &nccl() {
   return api;
 }
 
-// Peer-to-peer halo state.  One cudaMalloc block per rank, exported by cudaIpcGetMemHandle:
-//   [ arrival flags: 4 x u64 (z-behind, z-ahead, t-behind, t-ahead), padded to 256 B ]
+// Peer-to-peer state.  One cudaMalloc block per rank, mapped by EVERY other rank (CUDA IPC between
+// processes, plain peer access inside one process):
+//   [ halo arrival flags: 4 x u64 (z-behind, z-ahead, t-behind, t-ahead), padded to 256 B ]
+//   [ RedBox: mailboxes of the flag-based all-reduce, up to kP2PHeaderBytes ]
 //   [ ghost buffer 0 ][ ghost buffer 1 ]     each 3 colours x gstride sites x sizeof(double2)
 // Ghost buffers alternate by exchange sequence number: a neighbour can be at most one
 // exchange ahead (its next push needs our halo of the current one), so two buffers suffice.
+//
+// All-reduce without a collective library (blas.cuh p2p_allreduce_block): every rank stores its
+// <= 8 partial values into slot [its rank] of EVERY rank's mailbox over NVLink, then raises
+// flag[its rank] there to the reduction's sequence number; it then waits until all of its own
+// flags have reached that number and adds the nranks slots in rank order -- the same order on
+// every rank, so all ranks hold bit-identical sums.  Two mailbox sets alternate by sequence
+// number: completing reduction k needs every rank's delivery of k, which a rank makes only after
+// it has finished reading k-1, so a rank is never more than one reduction ahead of another.
+constexpr int kMaxRanks = 16;
+struct RedBox {
+  unsigned long long flag[kMaxRanks];   // flag[q]: number of reductions rank q has delivered here
+  unsigned long long count;             // reductions this rank has completed (only its own kernels write it)
+  unsigned long long pad_[15];
+  double val[2][kMaxRanks][8];
+};
+constexpr size_t kP2PFlagBytes = 256;
+constexpr size_t kP2PHeaderBytes = 4096;
+static_assert(kP2PFlagBytes + sizeof(RedBox) <= kP2PHeaderBytes, "RedBox does not fit the block header");
+
 struct P2P {
   bool on = false;
   char *block = nullptr;            // own block
   size_t ghost_bytes = 0;           // bytes of one ghost buffer
+  char *peer_all[kMaxRanks] = {};   // every rank's block as mapped here (own rank: block)
   char *peer_block[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [d-2][0 backward | 1 forward] neighbour's block
-  void *opened[4] = {nullptr, nullptr, nullptr, nullptr};              // cudaIpcOpenMemHandle results to close
+  void *opened[kMaxRanks] = {};     // cudaIpcOpenMemHandle results to close
   unsigned long long seq = 0;       // exchange sequence number (host mirror)
   unsigned *ticket = nullptr;       // push-kernel CTA ticket
-  int *err = nullptr;               // device word: nonzero = a halo wait timed out
+  int *err = nullptr;               // device word: nonzero = a halo or reduction wait timed out
 };
-constexpr size_t kP2PFlagBytes = 256;
+
+// kernel argument of the flag-based all-reduce
+struct RedComm {
+  RedBox *box[kMaxRanks];
+  int rank, nranks;
+  int *err;
+  long long timeout;
+};
 
 struct Comm {
   bool active = false;   // some direction is partitioned (nranks > 1, or a forced self-partition)

@@ -59,6 +59,8 @@ struct Geom {
   int origin[4];   // global coordinates of the local origin (even in every direction)
   int G[4];        // global extents
   FastDiv dLxh, dL1, dL2;   // division by Lxh, L[1], L[2]
+  int S2, zi;               // Lxh*L[1]; z extent of the interior region (L[2] - 6 when z is partitioned)
+  FastDiv dS2, dZi;
 };
 
 struct Coord { int x, y, z, t, xh; };

@@ -154,12 +154,11 @@ __device__ __forceinline__ void hop_dir(const DslashArg<T> &a, int idx, const Co
 
 // k-th interior site (kMode 1): z and t run over [3, L-3) in partitioned directions
 __device__ __forceinline__ int interior_site(const Geom &g, int k) {
-  const int S2 = g.Lxh * g.L[1];
-  const int zi = g.part[2] ? g.L[2] - 6 : g.L[2];
-  const int r = k % S2, q = k / S2;
-  const int z = q % zi + (g.part[2] ? 3 : 0);
-  const int t = q / zi + (g.part[3] ? 3 : 0);
-  return (t * g.L[2] + z) * S2 + r;
+  const int q = fast_div(k, g.dS2), r = k - q * g.S2;
+  const int tq = fast_div(q, g.dZi);
+  const int z = q - tq * g.zi + (g.part[2] ? 3 : 0);
+  const int t = tq + (g.part[3] ? 3 : 0);
+  return (t * g.L[2] + z) * g.S2 + r;
 }
 
 // kEpi: 0 plain store, 1 xpay, 2 xpay + 3 fused dots.  kMode: see the header comment.
@@ -245,8 +244,8 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? 5 : 8) dslash_kernel(
       a.out[(size_t)q * a.g.stride + idx] = o;
     }
   }
-  if (kEpi == 2) {   // single GPU (kMode 0): two-stage, reduce_finish_kernel follows; partitioned: in-kernel
-    if (kMode == 0) block_partials<3>(red, a.ws.partials);
+  if (kEpi == 2) {   // two-stage (reduce_finish_kernel follows) unless the NCCL-halo path asks for in-kernel sums
+    if (kMode == 0 || a.red == nullptr) block_partials<3>(red, a.ws.partials);
     else grid_reduce<3>(red, a.ws, a.red);
   }
 }

@@ -85,6 +85,7 @@ int field_to_dev(b200ks_ctx *c, double2 *dst, size_t fs, const void *host, int h
 extern "C" int b200ks_hisq_force(b200ks_ctx *c, int nterms, int num_naik_terms, const double *coeff, const void *const *multi_x,
                                  const double *level2_coeff, const double *fat7_coeff, const void *wlink, const void *vlink,
                                  const void *ulink, double eps, double force_filter, void *momentum, int host_prec) {
+  if (c && !(c = single_gpu_ctx(c))) return B200KS_ECUDA;   // (multi-GPU leader: its full-lattice context)
   if (!c || nterms < 1 || !coeff || !multi_x || !level2_coeff || !fat7_coeff || !wlink || !vlink || !ulink || !momentum)
     return fail(B200KS_EINVAL, "b200ks_hisq_force: null argument");
   if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");

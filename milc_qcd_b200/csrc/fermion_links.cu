@@ -154,6 +154,7 @@ static int check_link_args(b200ks_ctx *c, const double *coeffs, int host_prec) {
 
 extern "C" int b200ks_ks_links(b200ks_ctx *c, const double *path_coeff, const void *inlink, void *fatlink, void *longlink,
                                int host_prec) {
+  if (c && !(c = single_gpu_ctx(c))) return B200KS_ECUDA;   // (multi-GPU leader: its full-lattice context)
   CHK(check_link_args(c, path_coeff, host_prec));
   if (!inlink || !fatlink) return fail(B200KS_EINVAL, "b200ks_ks_links: null field");
   LinkWork *w = nullptr;
@@ -167,6 +168,7 @@ extern "C" int b200ks_ks_links(b200ks_ctx *c, const double *path_coeff, const vo
 
 extern "C" int b200ks_unitarized_links(b200ks_ctx *c, const double *path_coeff, const void *inlink, void *vlink, void *wlink,
                                        int host_prec, long long *nsvd) {
+  if (c && !(c = single_gpu_ctx(c))) return B200KS_ECUDA;   // (multi-GPU leader: its full-lattice context)
   CHK(check_link_args(c, path_coeff, host_prec));
   if (!inlink || !wlink) return fail(B200KS_EINVAL, "b200ks_unitarized_links: null field");
   LinkWork *w = nullptr;
@@ -182,6 +184,7 @@ extern "C" int b200ks_unitarized_links(b200ks_ctx *c, const double *path_coeff, 
 // the whole chain with the intermediate fields resident: one upload, two (to four) downloads
 extern "C" int b200ks_hisq_links(b200ks_ctx *c, const double *coeff1, const double *coeff2, const void *inlink, void *vlink,
                                  void *wlink, void *fatlink, void *longlink, int host_prec, long long *nsvd) {
+  if (c && !(c = single_gpu_ctx(c))) return B200KS_ECUDA;   // (multi-GPU leader: its full-lattice context)
   CHK(check_link_args(c, coeff1, host_prec));
   if (!coeff2 || !inlink) return fail(B200KS_EINVAL, "b200ks_hisq_links: null argument");
   LinkWork *w = nullptr;
@@ -202,6 +205,7 @@ extern "C" int b200ks_hisq_links(b200ks_ctx *c, const double *coeff1, const doub
 // can be read back with b200ks_hisq_links_fetch for the CPU comparison.
 extern "C" int b200ks_hisq_links_time(b200ks_ctx *c, const double *coeff1, const double *coeff2, unsigned long long seed,
                                       int reps, double *ms, long long *nsvd) {
+  if (c && !(c = single_gpu_ctx(c))) return B200KS_ECUDA;   // (multi-GPU leader: its full-lattice context)
   CHK(check_link_args(c, coeff1, 2));
   if (!coeff2 || !ms || reps <= 0) return fail(B200KS_EINVAL, "b200ks_hisq_links_time: bad argument");
   LinkWork *w = nullptr;
@@ -227,6 +231,7 @@ extern "C" int b200ks_hisq_links_time(b200ks_ctx *c, const double *coeff1, const
 
 // which: 0 input thin links, 1 V, 2 W, 3 fat, 4 long (of the last chain run on this context)
 extern "C" int b200ks_hisq_links_fetch(b200ks_ctx *c, int which, void *host, int host_prec) {
+  if (c && !(c = single_gpu_ctx(c))) return B200KS_ECUDA;   // (multi-GPU leader: its full-lattice context)
   if (!c || !host || which < 0 || which > 4) return fail(B200KS_EINVAL, "b200ks_hisq_links_fetch: bad argument");
   if (host_prec != 1 && host_prec != 2) return fail(B200KS_EINVAL, "host_prec must be 1 or 2");
   if (!link_work(c)) return fail(B200KS_ESTATE, "no link construction has run on this context");

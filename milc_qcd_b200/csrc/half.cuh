@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
       red[2] = s2;
     }
   }
-  if (kEpi == 2) {   // single GPU (kMode 0): two-stage, reduce_finish_kernel follows; partitioned: in-kernel
-    if (kMode == 0) block_partials<3>(red, a.ws.partials);
+  if (kEpi == 2) {   // two-stage (reduce_finish_kernel follows) unless the NCCL-halo path asks for in-kernel sums
+    if (kMode == 0 || a.red == nullptr) block_partials<3>(red, a.ws.partials);
     else grid_reduce<3>(red, a.ws, a.red);
   }
 }

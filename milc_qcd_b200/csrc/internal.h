@@ -23,6 +23,10 @@ const b200ks::Geom &geom(const b200ks_ctx *c);
 cudaStream_t stream(const b200ks_ctx *c);
 int device(const b200ks_ctx *c);
 bool partitioned(const b200ks_ctx *c);               // one-rank-per-GPU context with a split direction
+// The context an operation without a partitioned implementation (link construction, fermion force) runs on:
+// c itself, or -- for the leader of a single-process multi-GPU context -- a full-lattice context on
+// its first device, created on first use.  nullptr + error message on failure.
+b200ks_ctx *single_gpu_ctx(b200ks_ctx *c);
 void count_launch(b200ks_ctx *c);
 void *&link_work(b200ks_ctx *c);                     // slot owned by fermion_links.cu
 void fermion_links_release(b200ks_ctx *c);           // fermion_links.cu; called by b200ks_destroy

@@ -23,9 +23,6 @@ struct ShimState {
   int device = 0;
   int verbosity = QUDA_SUMMARIZE;
   double force_filter = 0.0;   // qudaHisqParamsInit
-  const void *fat = nullptr, *lng = nullptr;  // identity of the host link arrays on the device
-  int link_prec = 0;
-  unsigned long long fp_fat = 0, fp_lng = 0;   // content fingerprints at the last upload
   bool inited = false;
 } S;
 
@@ -54,29 +51,17 @@ void ensure_ctx(const char *where) {
 
 // The QUDA seam signals new links with *num_iters == -1 (d_congrad5_fn_gpu.c:121-126); that
 // flag is not set when boundary_twist_fn edits the links in place
-// (fermion_links_fn_twist_milc.c:318-400).  B200KS_ALWAYS_RELOAD_LINKS selects what to do about it:
-//   unset / 2  compare a content fingerprint of the two host arrays with the one taken at the last
-//              upload (threaded, ~30 ms for 2.4 GB) and re-upload only when something changed;
+// (fermion_links_fn_twist_milc.c:318-400).  B200KS_ALWAYS_RELOAD_LINKS selects what to do about it
+// (b200ks_links_sync modes):
+//   unset / 2  fingerprint the two host arrays on host threads WHILE the solve runs on the resident
+//              links; re-upload and repeat the solve only if they did change;
+//   3          fingerprint before the solve (blocking, ~70 ms per call at 32^3x64);
 //   1          re-upload on every call;
 //   0          trust the flag, as the reference's own QUDA path does.
 void ensure_links(const char *where, const void *fat, const void *lng, int ext_prec, int *num_iters) {
   static const int mode = env_int("B200KS_ALWAYS_RELOAD_LINKS", 2);
-  bool fresh = (num_iters && *num_iters == -1) || fat != S.fat || lng != S.lng || ext_prec != S.link_prec;
-  const size_t bytes = (size_t)S.latsize[0] * S.latsize[1] * S.latsize[2] * S.latsize[3] * 4 * 18 * (ext_prec == 2 ? 8 : 4);
-  unsigned long long ff = 0, fl = 0;
-  if (mode == 2) {
-    ff = b200ks_fingerprint(fat, bytes);
-    fl = b200ks_fingerprint(lng, bytes);
-    fresh = fresh || ff != S.fp_fat || fl != S.fp_lng;
-  }
-  if (fresh || mode == 1) {
-    if (b200ks_load_links(S.ctx, fat, lng, ext_prec, 0) < 0) die(where);
-    S.fat = fat;
-    S.lng = lng;
-    S.link_prec = ext_prec;
-    S.fp_fat = ff;
-    S.fp_lng = fl;
-  }
+  const int hint = (num_iters && *num_iters == -1) ? 1 : 0;
+  if (b200ks_links_sync(S.ctx, fat, lng, ext_prec, hint, mode < 0 || mode > 3 ? 2 : mode) < 0) die(where);
 }
 
 int milc_parity(QudaParity p, const char *where) {
@@ -89,12 +74,13 @@ int milc_parity(QudaParity p, const char *where) {
 // The seam only carries qic->max * qic->nrestart (d_congrad5_fn_gpu.c:104); the CPU
 // algorithm needs the two factors.  MILC inputs conventionally use 5 restarts
 // (max_cg_restarts 5 in the shipped samples); override with B200KS_NRESTART.
+// The product never exceeds the cap the seam was given.
 void split_iters(int total, b200ks_invert_args *a) {
   int nr = env_int("B200KS_NRESTART", 5);
   if (nr < 1) nr = 1;
   if (total < nr) nr = 1;
   a->nrestart = nr;
-  a->max_iter = (total + nr - 1) / nr;
+  a->max_iter = total / nr > 0 ? total / nr : 1;
 }
 
 __global__ void mom_action_kernel(const char *site, size_t mom_offset, size_t size, long nsites, int prec,
@@ -126,10 +112,14 @@ void qudaInit(QudaInitArgs_t input) {
   for (int d = 0; d < 4; d++) S.latsize[d] = input.layout.latsize[d];
   S.device = input.layout.device;
   S.verbosity = (int)input.verbosity;
+  // One MILC rank drives all GPUs: the machine grid MILC reports
+  // (generic/milc_to_quda_utilities.c:13-36) is that of its MPI ranks and must be 1x1x1x1; the number
+  // of devices behind the seam is B200KS_NGPU (b200ks_create -> b200ks_create_multi).
   if (input.layout.machsize)
     for (int d = 0; d < 4; d++)
       if (input.layout.machsize[d] != 1) {
-        printf("qudaInit: libb200ks is driven by one MILC rank (machine grid must be 1x1x1x1)\n");
+        printf("qudaInit: libb200ks is driven by ONE MILC rank (machine grid must be 1x1x1x1); set B200KS_NGPU=N to "
+               "spread the lattice over N GPUs behind it\n");
         exit(1);
       }
   if (b200ks_device_count() < 1) {
@@ -178,7 +168,9 @@ void qudaInvert(int external_precision, int quda_precision, double mass, QudaInv
   const int it = b200ks_congrad(S.ctx, source, solution, mass, &a, &r, external_precision);
   if (it < 0) die(where);
   *final_residual = sqrt(r.final_rsq);
-  *final_fermilab_residual = r.final_relrsq;
+  // MILC's glue squares what it gets back (d_congrad5_fn_gpu.c:150-151); the CPU path leaves
+  // relative_residue() itself in qic->final_relrsq (d_congrad5_fn_milc.c:37-56,218-221)
+  *final_fermilab_residual = sqrt(r.final_relrsq);
   *num_iters = it;
   if (S.verbosity >= QUDA_VERBOSE)
     printf("qudaInvert: %d iterations, true |r|/|b| = %e, %.3e s on device\n", it, *final_residual, r.device_seconds);
@@ -208,7 +200,7 @@ void qudaInvertMsrc(int external_precision, int quda_precision, double mass, Qud
   double worst = 0, worst_rel = 0;
   for (int k = 0; k < num_src; k++) {
     worst = std::max(worst, sqrt(r[k].final_rsq));
-    worst_rel = std::max(worst_rel, r[k].final_relrsq);
+    worst_rel = std::max(worst_rel, sqrt(r[k].final_relrsq));
   }
   *final_residual = worst;
   *final_fermilab_residual = worst_rel;

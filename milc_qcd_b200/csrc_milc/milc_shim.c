@@ -85,7 +85,8 @@ static b200ks_ctx *context(const char *myname) {
   if (s_ctx == NULL) {
     int dims[4];
     dims[0] = NX; dims[1] = NY; dims[2] = NZ; dims[3] = NT;
-    s_ctx = b200ks_create(dims, 0);
+    /* B200KS_DEVICE: first device; B200KS_NGPU=N (read by b200ks_create): spread the lattice over N devices */
+    s_ctx = b200ks_create(dims, getenv("B200KS_DEVICE") ? atoi(getenv("B200KS_DEVICE")) : 0);
     if (s_ctx == NULL) die(myname);
   }
   return s_ctx;
@@ -93,26 +94,30 @@ static b200ks_ctx *context(const char *myname) {
 
 /* d_congrad5_fn_gpu.c:121-126: refresh the device links when fn changed or was rebuilt -- and
  * also when the arrays were edited in place without notice (boundary_twist_fn,
- * fermion_links_fn_twist_milc.c:318-400), which a content fingerprint detects */
+ * fermion_links_fn_twist_milc.c:318-400).  b200ks_links_sync checks the content fingerprints on host
+ * threads while the solve runs (B200KS_ALWAYS_RELOAD_LINKS: 0 trust MILC's flag, 1 upload always,
+ * 2 = default, 3 check before the solve). */
 static void refresh_links(const char *myname, imp_ferm_links_t *fn) {
-  static unsigned long long fp_fat = 0, fp_lng = 0;
-  const size_t bytes = SITES * 4 * sizeof(su3_matrix);
-  const unsigned long long ff = b200ks_fingerprint(fn->fat, bytes), fl = b200ks_fingerprint(fn->lng, bytes);
-  if (fn != fn_last || fn->notify_quda_new_links || ff != fp_fat || fl != fp_lng) {
-    if (b200ks_load_links(context(myname), fn->fat, fn->lng, MILC_PRECISION, 0) < 0) die(myname);
-    fn->notify_quda_new_links = 0; /* cancel_quda_notification(fn) */
-    fn_last = fn;
-    fp_fat = ff;
-    fp_lng = fl;
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("B200KS_ALWAYS_RELOAD_LINKS");
+    mode = e ? atoi(e) : 2;
+    if (mode < 0 || mode > 3) mode = 2;
   }
+  if (b200ks_links_sync(context(myname), fn->fat, fn->lng, MILC_PRECISION, fn != fn_last || fn->notify_quda_new_links, mode) < 0)
+    die(myname);
+  fn->notify_quda_new_links = 0; /* cancel_quda_notification(fn) */
+  fn_last = fn;
 }
 
-static double source_norm(const su3_vector *v, int parity) {
+/* the reference's trivial-solution test (d_congrad5_fn_gpu.c:63-89) only needs to know whether the
+ * source vanishes: stop at the first nonzero number (a 50 MB norm on one host thread is 10 % of a solve) */
+static int source_is_zero(const su3_vector *v, int parity) {
   size_t lo = (parity == ODD) ? SITES / 2 : 0, hi = (parity == EVEN) ? SITES / 2 : SITES, i;
-  double s = 0;
   const Real *r = (const Real *)v;
-  for (i = 6 * lo; i < 6 * hi; i++) s += (double)r[i] * (double)r[i];
-  return s;
+  for (i = 6 * lo; i < 6 * hi; i++)
+    if (r[i] != 0) return 0;
+  return 1;
 }
 
 int ks_congrad_parity_gpu(su3_vector *t_src, su3_vector *t_dest, quark_invert_control *qic, Real mass,
@@ -139,7 +144,7 @@ int ks_congrad_parity_gpu(su3_vector *t_src, su3_vector *t_dest, quark_invert_co
     FATAL(2);
   }
   /* trivial solution (d_congrad5_fn_gpu.c:63-89) */
-  if (source_norm(t_src, qic->parity) == 0.0) {
+  if (source_is_zero(t_src, qic->parity)) {
     size_t lo = (qic->parity == ODD) ? SITES / 2 : 0;
     memset(t_dest + lo, 0, (SITES / 2) * sizeof(su3_vector));
     return 0;
@@ -186,13 +191,23 @@ int ks_congrad_block_parity_gpu(int nsrc, su3_vector **t_src, su3_vector **t_des
   qic->final_rsq = 0.;
   qic->final_relrsq = 0.;
   if (nsrc <= 0) return 0;
-  if (nsrc > B200KS_MAX_BLOCK) { /* very wide blocks: in chunks */
+  if (nsrc > B200KS_MAX_BLOCK) { /* very wide blocks: in chunks, qic = worst of all chunks */
     int done = 0, tot = 0;
+    quark_invert_control acc = *qic, q;
     while (done < nsrc) {
       int n = nsrc - done < B200KS_MAX_BLOCK ? nsrc - done : B200KS_MAX_BLOCK;
-      tot += ks_congrad_block_parity_gpu(n, t_src + done, t_dest + done, qic, mass, fn);
+      q = *qic;
+      tot += ks_congrad_block_parity_gpu(n, t_src + done, t_dest + done, &q, mass, fn);
+      if (q.final_rsq > acc.final_rsq) acc.final_rsq = q.final_rsq;
+      if (q.final_relrsq > acc.final_relrsq) acc.final_relrsq = q.final_relrsq;
+      if (q.size_r > acc.size_r) acc.size_r = q.size_r;
+      if (q.size_relr > acc.size_relr) acc.size_relr = q.size_relr;
+      if (q.final_restart > acc.final_restart) acc.final_restart = q.final_restart;
+      if (!q.converged) acc.converged = 0;
       done += n;
     }
+    acc.final_iters = tot;
+    *qic = acc;
     return tot;
   }
   if (fn == NULL) {
@@ -356,7 +371,7 @@ int ks_multicg_offset_field_gpu(su3_vector *src, su3_vector **psim, ks_param *ks
     }
     offsets[j] = ksp[j].offset;
   }
-  if (source_norm(src, qic[0].parity) == 0.0) {
+  if (source_is_zero(src, qic[0].parity)) {
     size_t lo = (qic[0].parity == ODD) ? SITES / 2 : 0;
     for (j = 0; j < num_offsets; j++) memset(psim[j] + lo, 0, (SITES / 2) * sizeof(su3_vector));
     return 0;

@@ -51,6 +51,24 @@ int b200ks_load_links(b200ks_ctx *c, const void *fat, const void *lng, int host_
   logf_("load_links prec %d recon %d\n", host_prec, long_recon);
   return 0;
 }
+/* the link cache of the real library without its concurrency: upload when told or when the pointers,
+ * the precision or the content changed (every verifying mode compares right away) */
+int b200ks_links_sync(b200ks_ctx *c, const void *fat, const void *lng, int host_prec, int changed_hint, int mode) {
+  static const void *s_fat = NULL, *s_lng = NULL;
+  static int s_prec = 0;
+  static unsigned long long s_ff = 0, s_fl = 0;
+  const size_t bytes = sites() * 72 * (host_prec == 2 ? 8 : 4);
+  int load = changed_hint || fat != s_fat || lng != s_lng || host_prec != s_prec || mode == 1;
+  unsigned long long ff = 0, fl = 0;
+  if (mode >= 2 || load) {
+    ff = b200ks_fingerprint(fat, bytes);
+    fl = b200ks_fingerprint(lng, bytes);
+    if (mode >= 2 && (ff != s_ff || fl != s_fl)) load = 1;
+  }
+  if (!load) return 0;
+  s_fat = fat; s_lng = lng; s_prec = host_prec; s_ff = ff; s_fl = fl;
+  return b200ks_load_links(c, fat, lng, host_prec, 0) < 0 ? -1 : 1;
+}
 static void fill(b200ks_invert_result *r, int iters) {
   memset(r, 0, sizeof(*r));
   r->final_rsq = 1e-20; r->final_relrsq = 0; r->size_r = 2e-20; r->size_relr = 0;
