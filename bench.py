@@ -142,13 +142,29 @@ def make_workload(dims):
     return fat, lng, src
 
 
+def omp_all_cores():
+    """The reference arm uses every host core whatever the launcher exported: torchrun sets
+    OMP_NUM_THREADS=1 for its children, which made round 1's N > 1 reference lines single-threaded.
+    Sets the environment (read by libgomp when oracle/_ref/libmilcref_omp.so pulls it in) AND the runtime's
+    own setting, and returns the thread count the OpenMP runtime reports."""
+    import ctypes
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1", mode=ctypes.RTLD_GLOBAL)
+        gomp.omp_set_num_threads(cores)
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return cores
+
+
 # ---------------------------------------------------------------------------------------------
 def cpu_reference_sample(dims, fat, lng, src, iters, repeats=1):
     """Times the reference's CPU CG (oracle/_ref, OpenMP over all host cores; or the oracle
     port if _ref was not built) for a fixed number of iterations.  Returns (gflops, meta)."""
     from oracle import pyoracle
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = omp_all_cores()
     V = int(np.prod(dims))
     times = []
     if pyoracle.ref_available("_omp"):
@@ -214,6 +230,162 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
+def seam_e2e(dims, fat, lng, b, steps, mixed, ngpu, resid=RESID):
+    """The end-to-end leg: the call a MILC binary makes.  ks_congrad_parity_gpu from the COMPILED route-1
+    library (libb200ks_milc.so, include/b200ks_milc.h) on plain pageable host arrays in MILC's layout --
+    source and zero guess H2D, solution D2H, link-cache check, qic bookkeeping all inside the timed call
+    (what MILC's own dtimec brackets, generic_ks/d_congrad5_fn_gpu.c:43-161).  ngpu > 1: the library
+    spreads the lattice over ngpu devices behind the same call (B200KS_NGPU, one process)."""
+    import ctypes as C
+    from milc_qcd_b200 import milc_abi, _lib
+    V = int(np.prod(dims))
+    os.environ["B200KS_NGPU"] = str(ngpu)
+    shim = milc_abi.load()
+    shim.b200ks_milc_finalize()
+    shim.b200ks_milc_setup(*dims, mixed)
+    fn = milc_abi.fn_links(fat, lng, 1)
+    src = np.array(b, copy=True)                      # plain malloc'ed memory, as MILC's create_v_field gives
+    dst = np.zeros_like(src)
+    lib = _lib.load()
+
+    def call():
+        dst[:V // 2] = 0
+        q = milc_abi.qic(EVEN, resid, NITER, NRESTART)
+        t0 = time.perf_counter()
+        it = shim.ks_congrad_parity_gpu(src.ctypes.data, dst.ctypes.data, C.byref(q), MASS, C.byref(fn))
+        return time.perf_counter() - t0, it, q
+
+    t_first, it, q = call()                           # first call: link upload + re-layout + fingerprints
+    call()
+    times, iters, prof = [], 0, np.zeros(8)
+    acc = np.zeros(8)
+    for _ in range(steps):
+        t, it, q = call()
+        times.append(t)
+        iters += it
+        lib.b200ks_call_profile(shim.b200ks_milc_context(), prof.ctypes.data_as(C.POINTER(C.c_double)))
+        acc += prof
+    ctxp = shim.b200ks_milc_context()
+    st_up, st_ver = C.c_longlong(0), C.c_longlong(0)
+    lib.b200ks_links_sync_stats(ctxp, C.byref(st_up), C.byref(st_ver))
+    out = {"seconds": times, "iters": iters, "first_call_s": t_first, "final_rsq": q.final_rsq, "converged": q.converged,
+           "num_gpus": lib.b200ks_num_gpus(ctxp), "link_uploads": st_up.value, "link_verifications": st_ver.value,
+           "launches": int(lib.b200ks_launch_count(ctxp)),
+           "profile_ms": {"h2d_source_and_guess_host_side": 1e3 * acc[0] / steps, "solve_wall": 1e3 * acc[1] / steps,
+                          "solve_device": 1e3 * acc[6] / steps, "wait_for_link_verification": 1e3 * acc[2] / steps,
+                          "d2h_solution": 1e3 * acc[3] / steps, "library_call": 1e3 * acc[4] / steps,
+                          "passes": acc[5] / steps}}
+    sol = dst.copy()
+    shim.b200ks_milc_finalize()
+    os.environ.pop("B200KS_NGPU", None)
+    return out, sol
+
+
+def multishift_summary(api, dist, torch, dims, world, rank, local_rank, long_recon):
+    """BASELINE configs[2]: RHMC multi-shift CG (ks_multicg_offset, 12 shifts) on 48^3x96, t-split over the
+    ranks; molecular-dynamics (1e-6) and action (1e-10) tolerances, the reference's algorithm in double and the
+    mixed form; MILC's (1205 + 15 N) flop convention (generic_ks/ks_multicg_offset.c:156); roofline of
+    ms_update_kernel from its algorithmic bytes (48 + 192 N per site) and the time it takes inside the solve."""
+    from milc_qcd_b200 import fields as F
+    multi = world > 1
+    V = int(np.prod(dims))
+    grid = (1, 1, 1, world)
+    if multi:
+        ids = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx = api.Context(dims, device=local_rank, grid=grid, rank=rank, nranks=world, nccl_id=ids[0])
+    else:
+        ctx = api.Context(dims, device=local_rank)
+    ctx.links_synthetic(1234, long_recon)
+    nshift = 12
+    offsets = F.rhmc_offsets(nshift, MASS)
+    vb = ctx.vec_create()
+    vps = [ctx.vec_create() for _ in range(nshift)]
+    ctx.vec_gaussian(vb, EVEN, 5678)
+    stream = torch.cuda.ExternalStream(ctx.lib.b200ks_stream(ctx.h))
+    rows = []
+    for resid, mixed in ((1e-6, 0), (1e-6, 1), (1e-10, 0)):
+        best = None
+        for rep in range(2):
+            torch.cuda.synchronize()
+            if multi:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            it, res = ctx.multicg_dev(vb, vps, offsets, EVEN, 5000, 1, resid, mixed_precision=mixed)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if multi:
+                t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            if rep > 0 or best is None:
+                best = (ms, it, res)
+        ms, it, res = best
+        row = {"resid": resid, "mixed_precision": mixed, "iterations_total": it, "seconds": ms * 1e-3,
+               "worst_final_rsq": max(r["final_rsq"] for r in res), "converged": min(r["converged"] for r in res)}
+        if mixed == 0:
+            row["gflops_milc_convention"] = (1205.0 + 15.0 * nshift) * V * it / (ms * 1e-3) / 1e9
+            # per-iteration algorithmic bytes per parity site, double: 2 stencils + resid (144) + update (48 + 192 N)
+            long_reals = 2 * ctx.long_link_info()[0]
+            per_site = 2 * dslash_bytes_per_site(2, long_reals) + 96 + 144 + 48 + 192 * nshift
+            row["achieved_gbs_per_gpu"] = per_site * (V / 2) * it / (ms * 1e-3) / 1e9 / world
+        rows.append(row)
+    out = {"workload": "RHMC multi-shift CG, 12 shifts (4m^2 + geometric ladder), synthetic random-SU(3) %s, BASELINE configs[2]"
+                       % "x".join(map(str, dims)), "lattice": list(dims), "rank_grid": list(grid), "n_gpus": world, "rows": rows,
+           "device_bytes_per_gpu": ctx.device_bytes()}
+    ctx.close()
+    return out
+
+
+def single_solve_point(api, dist, torch, dims, world, rank, local_rank, grid, long_recon, mixed, label):
+    """One mixed CG solve on `dims` decomposed over the ranks (fields generated on the device): the
+    strong-scaling anchor on one GPU (world 1) and BASELINE configs[4]'s 96^3x192 point on 8."""
+    multi = world > 1
+    V = int(np.prod(dims))
+    if multi:
+        ids = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx = api.Context(dims, device=local_rank, grid=grid, rank=rank, nranks=world, nccl_id=ids[0])
+    else:
+        ctx = api.Context(dims, device=local_rank)
+    ctx.links_synthetic(1234, long_recon)
+    vb, vx = ctx.vec_create(), ctx.vec_create()
+    ctx.vec_gaussian(vb, EVEN, 5678)
+    stream = torch.cuda.ExternalStream(ctx.lib.b200ks_stream(ctx.h))
+    best = None
+    for rep in range(2):
+        ctx.vec_zero(vx, EVEN)
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        it, res = ctx.congrad_dev(vb, vx, MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=mixed)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if multi:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        best = (ms, it, res)
+    ms, it, res = best
+    # independent true residual on the device operator
+    vt = ctx.vec_create()
+    ctx.dslash_dev(vx, vt, ODD)
+    ctx.dslash_dev(vt, vt, EVEN)
+    # r = b - (4m^2 x - D^2 x): norms by the library (global)
+    bb = ctx.vec_norm2(vb, EVEN)
+    out = {"workload": label, "lattice": list(dims), "rank_grid": list(grid), "n_gpus": world, "mixed_precision": mixed,
+           "cg_iters": it, "seconds": ms * 1e-3, "value": CG_FLOP_PER_SITE * V * it / (ms * 1e-3) / 1e9, "unit": "GFLOP/s",
+           "final_rsq_true": res["final_rsq"], "converged": res["converged"], "source_norm2": bb,
+           "device_bytes_per_gpu": ctx.device_bytes()}
+    ctx.close()
+    return out
+
+
 def run_b200(args):
     import torch
     from milc_qcd_b200 import api, dist as D
@@ -226,6 +398,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     multi = world > 1
+    dist = None
     if multi:
         import torch.distributed as dist
         dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local_rank))
@@ -259,6 +432,11 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def cpu_barrier():   # (no NCCL kernel: the GPUs stay free for the rank that works)
+        if multi:
+            t = torch.zeros(1)
+            dist.all_reduce(t)
+
     def max_over_ranks(x):
         if not multi:
             return x
@@ -269,16 +447,6 @@ def run_b200(args):
     def solve_resident(mixed=args.mixed):
         ctx.vec_zero(vx, EVEN)
         return ctx.congrad_dev(vb, vx, MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=mixed)
-
-    # pinned host buffers (local sub-lattice, MILC order) for the end-to-end leg
-    pin_b = torch.zeros((Vl, 3, 2), dtype=torch.float64).pin_memory()
-    pin_x = torch.zeros((Vl, 3, 2), dtype=torch.float64).pin_memory()
-    hb, hx = pin_b.numpy(), pin_x.numpy()
-    ctx.vec_download(vb, hb, EVEN)
-
-    def solve_host():
-        hx[:Vlh] = 0
-        return ctx.congrad(hb, hx, MASS, EVEN, NITER, NRESTART, RESID, mixed_precision=args.mixed)
 
     for _ in range(args.warmup):
         it, res = solve_resident()
@@ -298,6 +466,9 @@ def run_b200(args):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count() - l0
+    final_rsq_timed = res["final_rsq"]
+    if not (res["converged"] == 1 and final_rsq_timed < RESID ** 2):
+        raise SystemExit("bench.py: the timed solve did not converge (final_rsq %.3e): no number" % final_rsq_timed)
 
     # the other precision modes of the same solve, for the record (not the headline)
     others = []
@@ -359,73 +530,129 @@ def run_b200(args):
         for v in vbs[1:] + vxs:
             ctx.vec_free(v)
 
-    # end-to-end leg (host buffers through the ks_congrad_parity_gpu-style call)
-    solve_host()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e2.record(stream)
-    t_w = time.perf_counter()
-    it_e2e = 0
-    for _ in range(args.steps):
-        it, res_h = solve_host()
-        it_e2e += it
-    e3.record(stream)
-    barrier()
-    t_w = time.perf_counter() - t_w
-    ms_e2e = max_over_ranks(max(e2.elapsed_time(e3), 1e3 * t_w))
-    # where the end-to-end time goes: the same three phases issued as separate calls (diagnostic)
+    # what the copies of one end-to-end step cost on their own (diagnostic, pageable arrays like MILC's)
+    hb = np.zeros((Vl, 3, 2))
+    hx = np.zeros((Vl, 3, 2))
+    ctx.vec_download(vb, hb, EVEN)
     vu = ctx.vec_create()
+    ctx.vec_upload(vu, hb, EVEN)
     t0 = time.perf_counter(); ctx.vec_upload(vu, hb, EVEN); ctx.vec_upload(vu, hx, EVEN); t_up = time.perf_counter() - t0
     t0 = time.perf_counter(); ctx.vec_download(vu, hx, EVEN); t_dn = time.perf_counter() - t0
-    t0 = time.perf_counter(); hx[:Vlh] = 0; t_zero = time.perf_counter() - t0
     ctx.vec_free(vu)
-    solve_host()
+    copies_ms = max_over_ranks(1e3 * (t_up + t_dn))
 
-    # independent true-residual check of the last host solution (device operator, global norms)
-    vt, vr = ctx.vec_create(), ctx.vec_create()
-    ctx.vec_upload(vr, hx, EVEN)
-    ctx.dslash_dev(vr, vt, ODD)
-    ctx.dslash_dev(vt, vt, EVEN)
-    tt = np.zeros((Vl, 3, 2))
-    ctx.vec_download(vt, tt, EVEN)
-    r = hb[:Vlh] - (4 * MASS * MASS * hx[:Vlh] - tt[:Vlh])
-    rr, bb = float(np.sum(r * r)), float(np.sum(hb[:Vlh] ** 2))
-    if multi:
-        t2 = torch.tensor([rr, bb], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t2)
-        rr, bb = float(t2[0]), float(t2[1])
-    true_resid = (rr / bb) ** 0.5
-
-    value = CG_FLOP_PER_SITE * V * iters_total / (ms_total * 1e-3) / 1e9
-    e2e_value = CG_FLOP_PER_SITE * V * it_e2e / (ms_e2e * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     kp = {0: 2, 1: 1, 2: 0}[args.mixed]   # storage precision of the stencil that dominates the timed solve
     bps = {p: dslash_bytes_per_site(p, long_reals) for p in (0, 1, 2)}
     ach = {p: bps[p] * Vlh / (ds_ms[p] * 1e-3) / 1e9 for p in (0, 1, 2)}   # per GPU
-    half_bytes = Vlh * 6 * 8
+    half_bytes = (V // 2) * 6 * 8
 
+    # host copies of the inputs for the seam-level e2e leg and the CPU baseline (N = 1: read back from this
+    # context; N > 1: regenerated below by the single process that drives all GPUs)
     cpu = None
     t_links = None
-    if not args.no_cpu_baseline and not multi and rank == 0:
-        try:
-            fat, lng = ctx.links_download()
-            times, meta = cpu_reference_sample(dims, fat, lng, hb, 10, repeats=2)
-            t, itc = times[-1]
-            # what a first call through the seam adds: MILC-layout host links -> device (re-layout,
-            # long-link compression test, down-conversions happen on demand later)
-            t0 = time.perf_counter()
-            ctx.load_links(fat, lng, args.long_recon)
-            torch.cuda.synchronize()
-            t_links = time.perf_counter() - t0
-            cpu = {"value": CG_FLOP_PER_SITE * V * itc / t / 1e9, "unit": "GFLOP/s", "cores": meta["cores"],
-                   "kind": meta["kind"],
-                   "sample": "CG capped at 10 iterations (%d counted) on the full %s workload, same links and source, %s"
-                             % (itc, "x".join(map(str, dims)), meta["impl"])}
-        except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
-            cpu = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
+    fat = lng = None
+    if not multi:
+        fat, lng = ctx.links_download()
+        if not args.no_cpu_baseline:
+            try:
+                times, meta = cpu_reference_sample(dims, fat, lng, hb, 10, repeats=2)
+                t, itc = times[-1]
+                cpu = {"value": CG_FLOP_PER_SITE * V * itc / t / 1e9, "unit": "GFLOP/s", "cores": meta["cores"],
+                       "kind": meta["kind"],
+                       "sample": "CG capped at 10 iterations (%d counted) on the full %s workload, same links and source, %s"
+                                 % (itc, "x".join(map(str, dims)), meta["impl"])}
+            except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
+                cpu = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
+    device_bytes = ctx.device_bytes()
+    halo_mode = ctx.halo_mode()
+    local_dims = list(ctx.dims)
+    ctx.close()
+    barrier()
 
+    # ---- end-to-end through the drop-in symbol: ONE process (rank 0), all N GPUs behind it ---------
+    e2e, true_resid, seam_err = None, None, None
     if rank == 0:
+        try:
+            if multi:
+                gen = api.Context(dims, ngpu=world)
+                gen.links_synthetic(1234, args.long_recon)
+                fat, lng = gen.links_download()
+                gv = gen.vec_create()
+                gen.vec_gaussian(gv, EVEN, 5678)
+                hb = np.zeros((V, 3, 2))
+                gen.vec_download(gv, hb, EVEN)
+                gen.close()
+            seam, sol = seam_e2e(dims, fat, lng, hb, args.steps, args.mixed, world)
+            ms_e2e = 1e3 * sum(seam["seconds"]) / args.steps
+            e2e_value = CG_FLOP_PER_SITE * V * seam["iters"] / sum(seam["seconds"]) / 1e9
+            # independent true residual of the solution the seam returned (single-process context again)
+            chk = api.Context(dims, ngpu=world) if multi else api.Context(dims, device=local_rank)
+            chk.load_links(fat, lng, args.long_recon)
+            t_links = None
+            if not multi:
+                t0 = time.perf_counter()
+                chk.load_links(fat, lng, args.long_recon)
+                torch.cuda.synchronize()
+                t_links = time.perf_counter() - t0
+            tt = np.zeros_like(sol)
+            chk.dslash(sol, tt, ODD)
+            t2 = np.zeros_like(sol)
+            chk.dslash(tt, t2, EVEN)
+            chk.close()
+            h = V // 2
+            r = hb[:h] - (4 * MASS * MASS * sol[:h] - t2[:h])
+            true_resid = float(np.sqrt(np.sum(r * r) / np.sum(hb[:h] ** 2)))
+            e2e = {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": 2 * half_bytes, "d2h_bytes_per_step": half_bytes,
+                   "ms_per_step": ms_e2e,
+                   "through": "ks_congrad_parity_gpu of libb200ks_milc.so (MILC's prototype, include/b200ks_milc.h) on pageable "
+                              "host arrays in MILC's layout; one process driving %d GPU(s) (B200KS_NGPU)" % world,
+                   "num_gpus_behind_the_call": seam["num_gpus"], "cg_iters_per_solve": seam["iters"] / args.steps,
+                   "final_rsq": seam["final_rsq"], "converged": seam["converged"], "true_residual_of_returned_solution": true_resid,
+                   "profile_ms": seam["profile_ms"], "link_uploads": seam["link_uploads"],
+                   "link_verifications": seam["link_verifications"], "gpu_launches_whole_leg": seam["launches"],
+                   "first_call_s_incl_link_upload": seam["first_call_s"],
+                   "copies_alone_ms": copies_ms,
+                   "overhead_vs_resident_plus_copies": ms_e2e / (ms_total / args.steps + copies_ms) - 1.0,
+                   "first_call_link_upload_ms": None if t_links is None else 1e3 * t_links,
+                   "first_call_link_upload_bytes": 2 * 4 * 18 * 8 * V}
+            if not (seam["converged"] == 1 and true_resid < 10 * RESID):
+                raise RuntimeError("seam solve not converged: final_rsq %.3e, true residual %.3e" % (seam["final_rsq"], true_resid))
+        except Exception as ex:
+            seam_err = repr(ex)
+    fat = lng = None
+    cpu_barrier()
+
+    # ---- same-lattice strong-scaling anchor: the 64^3x96 solve on ONE GPU (25.8 GB), measured in this run ----
+    anchor = None
+    if rank == 0 and not args.lattice and not args.no_extras:
+        try:
+            anchor = single_solve_point(api, None, torch, (64, 64, 64, 96), 1, 0, local_rank, (1, 1, 1, 1), args.long_recon, args.mixed,
+                                        "HISQ single-mass CG 64x64x64x96 on ONE GPU (strong-scaling anchor, BASELINE configs[3])")
+        except Exception as ex:
+            anchor = {"error": repr(ex)}
+    cpu_barrier()
+
+    # ---- BASELINE configs[2] (N = 1, 2, 4) and configs[4] (N = 8) as part of the driver's line ----
+    multishift, weak = None, None
+    if not args.lattice and not args.no_extras:
+        try:
+            if world in (1, 2, 4):
+                multishift = multishift_summary(api, dist, torch, (48, 48, 48, 96), world, rank, local_rank, args.long_recon)
+            if world == 8:
+                weak = single_solve_point(api, dist, torch, (96, 96, 96, 192), world, rank, local_rank, grid, args.long_recon, args.mixed,
+                                          "HISQ single-mass CG 96x96x96x192 on 8 GPUs (BASELINE configs[4], fields generated on the device)")
+        except Exception as ex:
+            multishift = {"error": repr(ex)}
+
+    value = CG_FLOP_PER_SITE * V * iters_total / (ms_total * 1e-3) / 1e9
+    if rank == 0:
+        if e2e is None:
+            raise SystemExit("bench.py: the end-to-end leg through the drop-in symbol failed: %s" % seam_err)
         lat = "x".join(map(str, dims))
+        eff = None
+        if multi and anchor and "value" in anchor:
+            eff = value / (world * anchor["value"])
         line = {
             "metric": "hisq_cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -436,15 +663,17 @@ def run_b200(args):
             "config": {"workload": "HISQ single-mass CG, mass 0.05, resid 1e-10, synthetic random-SU(3) %s (%s)"
                                    % (lat, "BASELINE configs[1]" if dims == DIMS else "BASELINE configs[3], strong scaling"
                                       if dims == (64, 64, 64, 96) else "custom lattice"),
-                       "lattice": list(dims), "rank_grid": list(grid), "local_lattice": list(ctx.dims),
+                       "lattice": list(dims), "rank_grid": list(grid), "local_lattice": local_dims,
                        "l2": "links streamed by every dslash (%.2f GB per GPU at the inner precision) exceed the 126 MB L2; no flush needed"
                              % ({0: 8, 1: 4, 2: 2}[args.mixed] * (18 + long_reals) * 4 * Vl / 1e9),
                        "flop_convention": "MILC 1187 flop/site/iteration", "mixed_precision": args.mixed,
                        "halo": {0: "none", 1: "depth-3 ghosts, NCCL send/recv overlapped with the interior launch",
                                 2: "depth-3 ghosts pushed into the neighbours' peer-mapped ghost buffers (NVLink stores), "
-                                   "interior-first single-launch stencil acquiring arrival flags"}[ctx.halo_mode()]},
+                                   "interior-first single-launch stencil acquiring arrival flags; CG scalars all-reduced "
+                                   "through peer-mapped mailboxes inside the finish kernel"}[halo_mode]},
             "cg_iters_per_solve": iters_total / args.steps, "cg_time_to_solution_s": ms_total * 1e-3 / args.steps,
-            "cg_device_seconds": dev_s / args.steps, "true_residual": true_resid, "converged": res["converged"],
+            "cg_device_seconds": dev_s / args.steps, "final_rsq_true_device": final_rsq_timed, "true_residual": true_resid,
+            "converged": res["converged"],
             "dslash_gflops": {"f64": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[2] * 1e-3) / 1e9,
                               "f32": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[1] * 1e-3) / 1e9,
                               "16bit": DSLASH_FLOP_PER_SITE * V / 2 / (ds_ms[0] * 1e-3) / 1e9},
@@ -466,16 +695,15 @@ def run_b200(args):
             "other_precision_modes": others,
             "block_solve": block,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": 2 * half_bytes * world,
-                    "d2h_bytes_per_step": half_bytes * world, "ms_per_step": ms_e2e / args.steps,
-                    "phases_ms": {"h2d_src_and_guess": 1e3 * t_up, "d2h_solution": 1e3 * t_dn, "host_zero_guess": 1e3 * t_zero},
-                    "first_call_link_upload_ms": None if t_links is None else 1e3 * t_links,
-                    "first_call_link_upload_bytes": 2 * 4 * 18 * 8 * Vl},
+            "e2e": e2e,
+            "strong_scaling_anchor": anchor,
+            "efficiency_same_lattice": eff,
+            "multishift": multishift,
+            "weak_point": weak,
             "gpu_launches": launches, "clocks": clocks,
-            "setup": {"gen_fields_s": t_gen, "device_bytes": ctx.device_bytes()},
+            "setup": {"gen_fields_s": t_gen, "device_bytes": device_bytes},
         }
         print(json.dumps(line))
-    ctx.close()
     if multi:
         dist.barrier()
         dist.destroy_process_group()
@@ -718,8 +946,7 @@ def run_links(args):
     if not args.no_cpu_baseline:
         try:
             from oracle import pyoracle
-            cores = os.cpu_count() or 1
-            os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+            cores = omp_all_cores()
             if pyoracle.ref_available("_omp"):
                 ref = pyoracle.MilcRef(dims, "_omp")
                 t0 = time.perf_counter()
@@ -787,8 +1014,7 @@ def run_force(args):
     if not args.no_cpu_baseline:
         try:
             from oracle import pyoracle
-            cores = os.cpu_count() or 1
-            os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+            cores = omp_all_cores()
             sdims = (16, 16, 16, 32)
             Vs = int(np.prod(sdims))
             ref = pyoracle.MilcRef(sdims, "_omp")
@@ -889,6 +1115,8 @@ def main():
                          "half-precision inner solve') additionally 16-bit links and search direction in the stencil")
     ap.add_argument("--long-recon", type=int, default=0, help="long-link storage: 18, 14 or 0 = decided on the data")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the strong-scaling anchor, the multi-shift summary and the 96^3x192 point")
     ap.add_argument("--lattice", type=int, nargs=4, default=None, help="override the lattice (nx ny nz nt)")
     ap.add_argument("--nvecs", type=int, default=64, help="--workload deflate: number of resident vectors")
     ap.add_argument("--workload", default="cg", choices=["cg", "multishift", "block", "links", "force", "deflate"],

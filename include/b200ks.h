@@ -337,6 +337,11 @@ int b200ks_dslash_block_time(b200ks_ctx *ctx, int prec, int nrhs, int parity, in
  * stream; returns milliseconds per launch in *ms_per_launch. */
 int b200ks_dslash_time(b200ks_ctx *ctx, int prec, int parity, int n, double *ms_per_launch);
 
+/* Where the wall time of the last b200ks_congrad call went, seconds: out8[0] host side of the two uploads,
+ * [1] solve (device time + polling), [2] what waiting for the link verification (b200ks_links_sync mode 2)
+ * added after the solve, [3] download of the solution, [4] whole call, [5] passes (2 = the links had
+ * changed and the solve was repeated), [6] CUDA-event time of the solve proper. */
+int b200ks_call_profile(b200ks_ctx *ctx, double *out8);
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 long long b200ks_launch_count(b200ks_ctx *ctx);
 /* Raw CUDA stream (cudaStream_t) the library launches on, for external event timing. */

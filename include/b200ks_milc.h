@@ -94,6 +94,7 @@ extern "C" {
 void b200ks_milc_setup(int nx, int ny, int nz, int nt, int mixed_precision);
 void b200ks_milc_finalize(void);
 int b200ks_milc_total_iters(void);
+struct b200ks_ctx *b200ks_milc_context(void); /* the library context behind the symbols (diagnostics) */
 #ifdef __cplusplus
 }
 #endif

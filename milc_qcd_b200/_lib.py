@@ -91,6 +91,7 @@ SYMBOLS = [
     ("b200ks_hisq_links_fetch", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     ("b200ks_dslash_time", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     ("b200ks_halo_mode", C.c_int, [C.c_void_p]),
+    ("b200ks_call_profile", C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     ("b200ks_launch_count", C.c_longlong, [C.c_void_p]),
     ("b200ks_stream", C.c_void_p, [C.c_void_p]),
     ("b200ks_device_bytes", C.c_size_t, [C.c_void_p]),

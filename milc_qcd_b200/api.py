@@ -84,14 +84,20 @@ def _ptr(a):
 class Context:
     """One lattice on one GPU (``b200ks_create``)."""
 
-    def __init__(self, dims, device=0, grid=None, rank=0, nranks=1, nccl_id=None):
+    def __init__(self, dims, device=0, grid=None, rank=0, nranks=1, nccl_id=None, ngpu=None, devices=None):
         """Single GPU: Context(dims).  One rank per GPU: Context(global_dims, device, grid, rank,
         nranks, nccl_id) with nccl_id from :func:`comm_unique_id` on rank 0, broadcast by the
-        caller; host arrays are then the LOCAL sub-lattice (see milc_qcd_b200.dist)."""
+        caller; host arrays are then the LOCAL sub-lattice (see milc_qcd_b200.dist).
+        One process, several GPUs: Context(dims, ngpu=N[, devices=[...]]) (``b200ks_create_multi``):
+        host arrays stay MILC's GLOBAL arrays, exactly as for a single GPU."""
         self.lib = _lib.load()
         self.global_dims = tuple(int(d) for d in dims)
         arr = (C.c_int * 4)(*self.global_dims)
-        if grid is None:
+        if ngpu is not None and grid is None:
+            self.dims = self.global_dims
+            devs = None if devices is None else (C.c_int * int(ngpu))(*[int(d) for d in devices])
+            self.h = self.lib.b200ks_create_multi(arr, int(ngpu), devs)
+        elif grid is None:
             self.dims = self.global_dims
             self.h = self.lib.b200ks_create(arr, device)
         else:
@@ -103,6 +109,19 @@ class Context:
             raise _lib.B200KSError("b200ks_create failed: %s" % self.lib.b200ks_last_error().decode())
         self.volume = int(np.prod(self.dims))
         self._links_of = None
+
+    def num_gpus(self):
+        return self.lib.b200ks_num_gpus(self.h)
+
+    def links_sync(self, fat, lng, changed_hint=0, mode=2):
+        """b200ks_links_sync: what the MILC-facing shims call before every solve."""
+        return check(self.lib.b200ks_links_sync(self.h, _ptr(fat), _ptr(lng), _host_prec(fat), int(changed_hint), int(mode)),
+                     "b200ks_links_sync")
+
+    def links_sync_stats(self):
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        check(self.lib.b200ks_links_sync_stats(self.h, C.byref(a), C.byref(b)), "b200ks_links_sync_stats")
+        return {"uploads": a.value, "verifications": b.value}
 
     def close(self):
         if getattr(self, "h", None):

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <cmath>
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -120,6 +121,7 @@ struct b200ks_ctx {
   b200ks_ctx *aux = nullptr;            // leader: full-lattice context on the first device for the
                                         // operations that do not run partitioned yet (links, force)
   int member_rank = -1;                 // >= 0: member of a multi-GPU context
+  double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // b200ks_call_profile
 };
 
 // ---- single-process multi-GPU contexts (b200ks_create_multi) -------------------------------------
@@ -181,6 +183,11 @@ static int run_all(b200ks_ctx *c, F f) {
   if (c->sub.empty()) return f(c, 0);
   MultiState *ms = c->multi;
   std::unique_lock<std::mutex> lk(ms->mu);
+  {   // all workers are idle here: a barrier a failed member broke in the previous call is whole again
+    std::unique_lock<std::mutex> bl(ms->barrier.mu);
+    ms->barrier.aborted = false;
+    ms->barrier.waiting = 0;
+  }
   ms->task = f;
   ms->remaining = ms->n;
   ms->gen++;
@@ -200,16 +207,37 @@ static int run_all(b200ks_ctx *c, F f) {
 
 static size_t real_size(int prec) { return prec == B200KS_PREC_DOUBLE ? 8 : prec == B200KS_PREC_SINGLE ? 4 : 2; }
 
+// Members of a single-process multi-GPU context run kernels that wait for their peers' kernels (halo
+// flags, reduction mailboxes).  A device memory (or page-locked host memory) allocation or release is
+// an implicit synchronisation point of the CUDA runtime: issued by one member while another member's
+// kernel is waiting for a kernel the first one has yet to launch, it can deadlock.  All members make
+// the same allocations in the same order, so each one is bracketed by host barriers: everybody drains
+// its stream and meets, everybody allocates, everybody meets again, and only then does anyone launch.
+static bool member_quiesce(b200ks_ctx *c) {
+  if (c->member_rank < 0 || !c->multi) return true;
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  return c->multi->barrier.arrive_and_wait();
+}
+static bool member_resume(b200ks_ctx *c) {
+  if (c->member_rank < 0 || !c->multi) return true;
+  return c->multi->barrier.arrive_and_wait();
+}
+
 int b200ks_host::dev_alloc(b200ks_ctx *c, void **p, size_t bytes) {
+  if (!member_quiesce(c)) return fail(B200KS_ECOMM, "another member of the multi-GPU context failed");
   cudaError_t e = cudaMalloc(p, bytes);
+  const bool ok = member_resume(c);
   if (e != cudaSuccess)
     return fail(B200KS_ENOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+  if (!ok) return fail(B200KS_ECOMM, "another member of the multi-GPU context failed");
   c->bytes += bytes;
   return 0;
 }
 static void dev_free(b200ks_ctx *c, void *p, size_t bytes) {
   if (p) {
+    member_quiesce(c);
     cudaFree(p);
+    member_resume(c);
     c->bytes -= bytes;
   }
 }
@@ -263,12 +291,16 @@ static bool host_is_pinned(const void *p) {
 }
 
 static int bounce_get(b200ks_ctx *c) {
-  for (int k = 0; k < 2; k++) {
+  if (c->bounce[0] && c->bounce[1]) return 0;
+  if (!member_quiesce(c)) return -1;
+  int rc = 0;
+  for (int k = 0; k < 2 && rc == 0; k++) {
     if (c->bounce[k]) continue;
-    if (cudaMallocHost(&c->bounce[k], kBounceBytes) != cudaSuccess) { cudaGetLastError(); c->bounce[k] = nullptr; return -1; }
-    if (cudaEventCreateWithFlags(&c->bounce_ev[k], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (cudaMallocHost(&c->bounce[k], kBounceBytes) != cudaSuccess) { cudaGetLastError(); c->bounce[k] = nullptr; rc = -1; }
+    else if (cudaEventCreateWithFlags(&c->bounce_ev[k], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); rc = -1; }
   }
-  return 0;
+  if (!member_resume(c)) rc = -1;
+  return rc;
 }
 
 // A host field as this context sees it: `nrows` runs of `row_bytes` bytes, `pitch_bytes` apart.
@@ -494,7 +526,7 @@ static int setup_geom(b200ks_ctx *c, const int local[4], const int part[4], cons
     g.lghost[d] = 0;
     if (g.part[d]) {
       if (d < 2) return fail(B200KS_EINVAL, "only z and t may be partitioned");
-      if (g.L[d] < 6) return fail(B200KS_EINVAL, "partitioned extent must be >= 6 (depth-3 ghost zones)");
+      if (g.L[d] < 4) return fail(B200KS_EINVAL, "partitioned extent must be >= 4 (depth-3 ghost zones come from ONE neighbour)");
       g.ghost[d][0] = g.Vh + gsites; gsites += 3 * g.faceh[d];
       g.ghost[d][1] = g.Vh + gsites; gsites += 3 * g.faceh[d];
       g.lghost[d] = lsites; lsites += 3 * g.faceh[d];
@@ -568,8 +600,13 @@ extern "C" b200ks_ctx *b200ks_create(const int latsize[4], int device) {
   const char *e = getenv("B200KS_NGPU");
   const int ngpu = e ? atoi(e) : 1;
   if (ngpu > 1) {
+    // B200KS_NGPU_OVERSUBSCRIBE=1 (testing on fewer GPUs, SMALL lattices only: all members' kernels must
+    // fit the device together): members wrap around the visible devices
+    int ndev = 0;
+    cudaGetDeviceCount(&ndev);
+    const bool over = getenv("B200KS_NGPU_OVERSUBSCRIBE") && atoi(getenv("B200KS_NGPU_OVERSUBSCRIBE")) != 0 && ndev > 0;
     std::vector<int> devs(ngpu);
-    for (int r = 0; r < ngpu; r++) devs[r] = device + r;
+    for (int r = 0; r < ngpu; r++) devs[r] = over ? (device + r) % ndev : device + r;
     return b200ks_create_multi(latsize, ngpu, devs.data());
   }
   const int part[4] = {0, 0, 0, 0}, origin[4] = {0, 0, 0, 0};
@@ -595,6 +632,7 @@ extern "C" void b200ks_destroy(b200ks_ctx *c) {
     delete c;
     return;
   }
+  c->member_rank = -1;   // (a member being destroyed frees without the allocation barriers)
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto v : c->user) vec_delete(c, v);
@@ -732,6 +770,18 @@ static void finish_update(b200ks_ctx *c, int nblk, CgState *st, int flags) {
 static void watch_join_thread(b200ks_ctx *c);
 static int links_alloc(b200ks_ctx *c, int prec, int nc) {
   Links &L = c->links[prec];
+  if (prec == B200KS_PREC_HALF) {   // one array of site records per parity (half.cuh), kept in fat[p]
+    for (int p = 0; p < 2; p++) {
+      if (L.fat[p] && L.lng_nc != nc) {
+        CU(cudaStreamSynchronize(c->stream));
+        dev_free(c, L.fat[p], half_link_bytes(c->g.Vh, L.lng_nc));
+        L.fat[p] = nullptr;
+      }
+      if (!L.fat[p]) CHK(dev_alloc(c, &L.fat[p], half_link_bytes(c->g.Vh, nc)));
+    }
+    L.lng_nc = nc;
+    return 0;
+  }
   for (int p = 0; p < 2; p++) {
     if (!L.fat[p]) {
       CHK(dev_alloc(c, &L.fat[p], link_bytes(c, prec)));
@@ -1036,25 +1086,19 @@ extern "C" int b200ks_links_sync_stats(b200ks_ctx *c, long long *reloads, long l
   return 0;
 }
 
-// 16-bit copy of the master links: one scale per field (fat components, long rows, long factor),
-// the same on every rank so that a ghost link and its owner's copy dequantise identically.
-static int links_quantize(b200ks_ctx *c, int m, int nc) {
+// 16-bit copy of the master links as site records (half.cuh): one scale per field (fat components,
+// long components, long factor), the same on every rank so that a ghost link and its owner's copy
+// dequantise identically.
+template <typename T, int kNc>
+static int links_quantize_T(b200ks_ctx *c, int m) {
+  using T2 = typename Vec2<T>::type;
   const Geom &g = c->g;
   unsigned *d_max = nullptr;
   CHK(dev_alloc(c, (void **)&d_max, 3 * sizeof(unsigned)));
   CU(cudaMemsetAsync(d_max, 0, 3 * sizeof(unsigned), c->stream));
-  const int grid = nblocks(g.lstride);
-  for (int p = 0; p < 2; p++) {
-    if (m == 2) {
-      LAUNCH(c, (link_absmax_kernel<double>), grid, (const double2 *)c->links[m].fat[p], g.lstride, g.lstride, 9, 0, 9, d_max + 0);
-      LAUNCH(c, (link_absmax_kernel<double>), grid, (const double2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, 0, nc == 7 ? 6 : 9, d_max + 1);
-      if (nc == 7) LAUNCH(c, (link_absmax_kernel<double>), grid, (const double2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, 6, 7, d_max + 2);
-    } else {
-      LAUNCH(c, (link_absmax_kernel<float>), grid, (const float2 *)c->links[m].fat[p], g.lstride, g.lstride, 9, 0, 9, d_max + 0);
-      LAUNCH(c, (link_absmax_kernel<float>), grid, (const float2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, 0, nc == 7 ? 6 : 9, d_max + 1);
-      if (nc == 7) LAUNCH(c, (link_absmax_kernel<float>), grid, (const float2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, 6, 7, d_max + 2);
-    }
-  }
+  for (int p = 0; p < 2; p++)
+    LAUNCH(c, (half_absmax_kernel<T, kNc>), nblocks(g.lstride), (const T2 *)c->links[m].fat[p], (const T2 *)c->links[m].lng[p],
+           g.lstride, g.lstride, d_max);
   unsigned bits[3];
   CU(cudaMemcpyAsync(bits, d_max, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -1076,18 +1120,17 @@ static int links_quantize(b200ks_ctx *c, int m, int nc) {
     c->half_k[k] = (float)(mx[k] / 32767.0);
     inv[k] = mx[k] > 0 ? (float)(32767.0 / mx[k]) : 0.f;
   }
-  for (int p = 0; p < 2; p++) {
-    if (m == 2) {
-      LAUNCH(c, (quantize_link_kernel<double>), grid, (uint32_t *)c->links[0].fat[p], (const double2 *)c->links[m].fat[p], g.lstride, g.lstride, 9, inv[0], inv[0]);
-      LAUNCH(c, (quantize_link_kernel<double>), grid, (uint32_t *)c->links[0].lng[p], (const double2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, inv[1], inv[2]);
-    } else {
-      LAUNCH(c, (quantize_link_kernel<float>), grid, (uint32_t *)c->links[0].fat[p], (const float2 *)c->links[m].fat[p], g.lstride, g.lstride, 9, inv[0], inv[0]);
-      LAUNCH(c, (quantize_link_kernel<float>), grid, (uint32_t *)c->links[0].lng[p], (const float2 *)c->links[m].lng[p], g.lstride, g.lstride, nc, inv[1], inv[2]);
-    }
-  }
-  CHK(check_launch("quantize_link_kernel"));
+  for (int p = 0; p < 2; p++)
+    LAUNCH(c, (half_records_kernel<T, kNc>), nblocks(g.Vh), (uint4 *)c->links[0].fat[p], (const T2 *)c->links[m].fat[p],
+           (const T2 *)c->links[m].lng[p], (const T2 *)c->links[m].fat[p ^ 1], (const T2 *)c->links[m].lng[p ^ 1], g, p, inv[0], inv[1],
+           inv[2]);
+  CHK(check_launch("half_records_kernel"));
   c->links[0].valid = true;
   return 0;
+}
+static int links_quantize(b200ks_ctx *c, int m, int nc) {
+  if (m == 2) return nc == 7 ? links_quantize_T<double, 7>(c, m) : links_quantize_T<double, 9>(c, m);
+  return nc == 7 ? links_quantize_T<float, 7>(c, m) : links_quantize_T<float, 9>(c, m);
 }
 
 // make sure links exist at precision `prec` (device-side down-conversion of the master copy)
@@ -1134,7 +1177,7 @@ struct Epi {
 // interior pass runs on the compute stream.
 static unsigned long long *p2p_flags(char *block) { return (unsigned long long *)block; }
 static char *p2p_ghost(const P2P &pp, char *block, unsigned long long seq) {
-  return block + kP2PFlagBytes + (size_t)(seq & 1ull) * pp.ghost_bytes;
+  return block + kP2PHeaderBytes + (size_t)(seq & 1ull) * pp.ghost_bytes;
 }
 
 // Peer-to-peer exchange `seq`: one push kernel on the (high-priority) comm stream, concurrent
@@ -1289,17 +1332,14 @@ static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *o
   memset(&a, 0, sizeof(a));
   a.g = c->g;
   a.par = par_out;
-  for (int p = 0; p < 2; p++) {
-    a.L.fat[p] = (const uint32_t *)L.fat[p];
-    a.L.lng[p] = (const uint32_t *)L.lng[p];
-  }
+  for (int p = 0; p < 2; p++) a.L.rec[p] = (const uint4 *)L.fat[p];
   a.L.fat_k = c->half_k[0];
   a.L.lng_k = c->half_k[1];
   a.L.f_k = c->half_k[2];
-  a.in = (const uint32_t *)in.p[par_out ^ 1];
-  a.out_h = out_h ? (uint32_t *)out_h->p[par_out] : nullptr;
+  a.in = (const uint4 *)in.p[par_out ^ 1];
+  a.out_h = out_h ? (uint4 *)out_h->p[par_out] : nullptr;
   a.out_f = out_f ? (float2 *)out_f->p[par_out] : nullptr;
-  a.w_h = w_h ? (const uint32_t *)w_h->p[par_out] : nullptr;
+  a.w_h = w_h ? (const uint4 *)w_h->p[par_out] : nullptr;
   a.r = r ? (const float2 *)r->p[par_out] : nullptr;
   a.s = (float)s_;
   a.ws = c->ws;
@@ -1328,9 +1368,9 @@ static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *o
     return 0;
   }
   if (!c->comm.p2p.on) return fail(B200KS_ESTATE, "16-bit stencil needs the peer-to-peer halo path");
-  CHK((halo_push<uint32_t, 4, true>(c, in, par_out ^ 1, stop)));
+  CHK((halo_push<uint4, 1, false>(c, in, par_out ^ 1, stop)));
   P2P &pp = c->comm.p2p;
-  a.gin = (const uint32_t *)p2p_ghost(pp, pp.block, pp.seq);
+  a.gin = (const uint4 *)p2p_ghost(pp, pp.block, pp.seq);
   a.halo_flags = p2p_flags(pp.block);
   a.halo_seq = pp.seq;
   a.halo_mask = (c->g.part[2] ? 3 : 0) | (c->g.part[3] ? 12 : 0);
@@ -1543,9 +1583,9 @@ extern "C" int b200ks_dslash_dev(b200ks_ctx *c, int vsrc, int vdest, int parity,
         CHK(dslash_T<float>(c, *in, *out, pbit, e));
         LAUNCH(c, (convert_kernel<double, float>), grid, (double2 *)d->p[pbit], (const float2 *)out->p[pbit], c->g.stride, c->g.Vh);
       } else {
-        LAUNCH(c, vec_d2h_kernel, grid, (uint32_t *)in->p[ib], (const double2 *)s->p[ib], c->g.stride, c->g.Vh);
+        LAUNCH(c, vec_d2h_kernel, grid, (uint4 *)in->p[ib], (const double2 *)s->p[ib], c->g.stride, c->g.Vh);
         CHK(dslash_half(c, *in, out, nullptr, pbit, 0, 0.0, nullptr, nullptr, nullptr, nullptr));
-        LAUNCH(c, vec_h2d_kernel, grid, (double2 *)d->p[pbit], (const uint32_t *)out->p[pbit], c->g.stride, c->g.Vh);
+        LAUNCH(c, vec_h2d_kernel, grid, (double2 *)d->p[pbit], (const uint4 *)out->p[pbit], c->g.stride, c->g.Vh);
       }
     }
   }
@@ -1846,7 +1886,7 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
     CHK(dslash_T<double>(c, *ttt_d, *ttt_d, pb, e1));
     if (half)
       LAUNCH(c, mixed_reliable_half_kernel, grid, (const double2 *)b.p[pb], (const double2 *)ttt_d->p[pb], (float2 *)r_lo->p[pb],
-             (uint32_t *)p_h->p[pb], g.stride, g.Vh, first ? 1 : 0, c->ws, c->d_scal);
+             (uint4 *)p_h->p[pb], g.stride, g.Vh, first ? 1 : 0, c->ws, c->d_scal);
     else
       LAUNCH(c, mixed_reliable_kernel, grid, (const double2 *)b.p[pb], (const double2 *)ttt_d->p[pb], (float2 *)r_lo->p[pb],
              (float2 *)p_lo->p[pb], g.stride, g.Vh, first ? 1 : 0, c->ws, c->d_scal);
@@ -1905,7 +1945,7 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
       }
       const int fuse = 1 | 4 | ((!multi || p2p) ? 8 : 0);
       if (half)
-        LAUNCH(c, cg_update_half_kernel, grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (uint32_t *)p_h->p[pb],
+        LAUNCH(c, cg_update_half_kernel, grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (uint4 *)p_h->p[pb],
                (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse);
       else
         LAUNCH(c, (cg_update_kernel<float, false>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
@@ -1982,26 +2022,53 @@ extern "C" int b200ks_congrad(b200ks_ctx *c, const void *src, void *dest, double
                               b200ks_invert_result *res, int host_prec) {
   if (!c || !src || !dest || !res) return fail(B200KS_EINVAL, "b200ks_congrad: null argument");
   CHK(check_args(args));
+  using clk = std::chrono::steady_clock;
+  auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  const auto t0 = clk::now();
+  double t_up = 0, t_solve = 0;
+  int passes = 0;
   std::vector<b200ks_invert_result> rr(nmembers(c));
   const int it = with_verified_links(c, [&]() {
+    passes++;
     return run_all(c, [&](b200ks_ctx *c, int r) -> int {
       CU(cudaSetDevice(c->device));
+      const auto a0 = clk::now();
       DevVec *b = nullptr, *x = nullptr;
       CHK(pool_get(c, 2, 0, &b));
       CHK(pool_get(c, 2, 1, &x));
       CHK(upload(c, *b, src, args->parity, host_prec, false));
       CHK(upload(c, *x, dest, args->parity, host_prec, false));
-      return congrad_any(c, *b, *x, mass, *args, rr[r]);
+      const auto a1 = clk::now();
+      const int it = congrad_any(c, *b, *x, mass, *args, rr[r]);
+      if (r == 0) { t_up = secs(a0, a1); t_solve = secs(a1, clk::now()); }
+      return it;
     });
   });
   if (it < 0) return it;
+  const auto t1 = clk::now();
   CHK(run_all(c, [&](b200ks_ctx *c, int) -> int {
     DevVec *x = nullptr;
     CHK(pool_get(c, 2, 1, &x));
     return download(c, *x, dest, args->parity, host_prec);
   }));
+  const auto t2 = clk::now();
   *res = rr[0];
+  // where the call's wall time went (last pass): host side of the uploads, solve (device + polling), whatever
+  // the link verification added after the solve, download, total, number of passes (2 = links had changed)
+  c->prof[0] = t_up;
+  c->prof[1] = t_solve;
+  c->prof[2] = secs(t0, t1) - passes * (t_up + t_solve);
+  c->prof[3] = secs(t1, t2);
+  c->prof[4] = secs(t0, t2);
+  c->prof[5] = passes;
+  c->prof[6] = rr[0].device_seconds;
   return it;
+}
+
+extern "C" int b200ks_call_profile(b200ks_ctx *c, double *out8) {
+  if (!c || !out8) return fail(B200KS_EINVAL, "b200ks_call_profile: null argument");
+  memcpy(out8, c->prof, sizeof(c->prof));
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -3063,6 +3130,10 @@ static int comm_setup(b200ks_ctx *c) {
       MEET(ms);
       for (int r = 0; r < cm.nranks; r++) {
         if (r == cm.rank) continue;
+        if (ms->devices[r] == c->device) {   // oversubscribed (testing): several members on one device
+          pp.peer_all[r] = (char *)ms->slot[r];
+          continue;
+        }
         int can = 0;
         if (cudaDeviceCanAccessPeer(&can, c->device, ms->devices[r]) != cudaSuccess || !can) { cudaGetLastError(); ok = false; continue; }
         const cudaError_t e = cudaDeviceEnablePeerAccess(ms->devices[r], 0);
@@ -3238,6 +3309,7 @@ static void multi_worker(b200ks_ctx *leader, int r) {
     }
     g_err.clear();
     const int rc = task(r < (int)leader->sub.size() ? leader->sub[r] : nullptr, r);
+    if (rc < 0) ms->barrier.abort();   // the others must not wait for this member at a barrier
     {
       std::unique_lock<std::mutex> lk(ms->mu);
       ms->rc[r] = rc;
@@ -3247,12 +3319,20 @@ static void multi_worker(b200ks_ctx *leader, int r) {
   }
 }
 
-static void multi_grid(int ngpu, int grid[4]) {   // t first (up to 4 ways), then z: north_star's decomposition
-  int gt = 1;
-  while (gt < 4 && ngpu % (gt * 2) == 0) gt *= 2;
-  grid[0] = grid[1] = 1;
-  grid[3] = gt;
-  grid[2] = ngpu / gt;
+// t first (up to 4 ways), then z: north_star's decomposition -- with fewer cuts in t when the local
+// extents would not stay even and >= 4 (small test lattices).  false: no admissible split.
+static bool multi_grid(const int latsize[4], int ngpu, int grid[4]) {
+  auto ok = [](int ext, int cuts) { return ext % cuts == 0 && (cuts == 1 || ((ext / cuts) >= 4 && (ext / cuts) % 2 == 0)); };
+  for (int gt = 4; gt >= 1; gt >>= 1) {
+    if (ngpu % gt) continue;
+    const int gz = ngpu / gt;
+    if (!ok(latsize[3], gt) || !ok(latsize[2], gz)) continue;
+    grid[0] = grid[1] = 1;
+    grid[2] = gz;
+    grid[3] = gt;
+    return true;
+  }
+  return false;
 }
 
 extern "C" b200ks_ctx *b200ks_create_multi(const int latsize[4], int ngpu, const int *devices) {
@@ -3265,17 +3345,11 @@ extern "C" b200ks_ctx *b200ks_create_multi(const int latsize[4], int ngpu, const
     return nullptr;
   }
   int grid[4];
-  multi_grid(ngpu, grid);
-  for (int d = 2; d < 4; d++) {
-    const int l = latsize[d] / grid[d];
-    if (latsize[d] % grid[d] || (grid[d] > 1 && (l < 6 || (l & 1)))) {
-      fail(B200KS_EINVAL, "b200ks_create_multi: lattice " + std::to_string(latsize[2]) + " x " + std::to_string(latsize[3]) +
-                              " (z x t) cannot be split " + std::to_string(grid[2]) + " x " + std::to_string(grid[3]) +
-                              " ways (local extents must be even and >= 6)");
-      return nullptr;
-    }
+  if (!multi_grid(latsize, ngpu, grid)) {
+    fail(B200KS_EINVAL, "b200ks_create_multi: lattice " + std::to_string(latsize[2]) + " x " + std::to_string(latsize[3]) +
+                            " (z x t) cannot be split over " + std::to_string(ngpu) + " GPUs (local extents must be even and >= 4)");
+    return nullptr;
   }
-  if (grid[2] * grid[3] != ngpu) { fail(B200KS_EINVAL, "b200ks_create_multi: unsupported GPU count"); return nullptr; }
   b200ks_ctx *L = new b200ks_ctx;
   memcpy(L->global, latsize, sizeof(L->global));
   MultiState *ms = new MultiState;

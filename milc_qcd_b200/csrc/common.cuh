@@ -82,7 +82,8 @@ __device__ __forceinline__ Coord site_coord(const Geom &g, int idx, int par) {
 // h in direction D (h = +-1, +-3).  Non-partitioned directions wrap periodically
 // (generic/com_vanilla.c:619-645, ks_spectrum/setup.c:1427-1445).  Partitioned
 // directions index the ghost zone.  kLink selects link-field ghosts (backward only).
-template <int D, bool kLink = false>
+// kPart = false: the caller knows that no direction is partitioned (single-GPU kernels).
+template <int D, bool kLink = false, bool kPart = true>
 __device__ __forceinline__ int neighbor(const Geom &g, int idx, const Coord &c, int h) {
   // (h is a compile-time constant at every call site: only the wrap on its side survives)
   if (D == 0) {
@@ -100,7 +101,7 @@ __device__ __forceinline__ int neighbor(const Geom &g, int idx, const Coord &c, 
   const int ext = g.L[D];
   const int sstride = (D == 1) ? g.Lxh : (D == 2) ? g.Lxh * g.L[1] : g.Lxh * g.L[1] * g.L[2];
   int cn = coord + h;
-  if (D >= 2 && g.part[D]) {
+  if (kPart && D >= 2 && g.part[D]) {
     if (cn < 0) {
       // slice -3,-2,-1 -> ghost slice 0,1,2 ; position inside the slice = idx minus this
       // site's own slice offset

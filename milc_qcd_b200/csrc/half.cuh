@@ -5,18 +5,18 @@
 // double, the inner iteration streams 16-bit links and a 16-bit search direction.  All
 // arithmetic is fp32; only the STORAGE of the two stencil operands is 16 bit:
 //
-//   colour vector : 4 planes of 32-bit words per parity half, plane c < 3 = colour c as two
-//                   offset-binary u16 (re | im << 16), plane 3 = the site's scale (float bits):
-//                   value = (q - 32768) * scale / 32767.                       16 B/site
-//   fat link      : 9 words per direction, one scale for the whole field        36 B/link
+//   colour vector : one 16-byte word per site, {c0, c1, c2, scale}: colour c as two offset-binary
+//                   u16 (re | im << 16), scale = the site's max |component| (float bits):
+//                   value = (q - 32768) * scale / 32767.                         16 B/site
+//   fat link      : 9 words, one scale for the whole field                       36 B/link
 //   long link     : compressed form (rows 1,2 + U(3) factor f) = 7 words with one scale for
 //                   the rows and one for f, or 9 words when the links are not compressible
-//                                                                               28 B/link
+//                                                                                28 B/link
 //   => 8*36 + 8*28 + 16 + 16 = 544 B per output site per stencil (float: 1072, double: 2144).
 //
-// At 544 B/site the kernel is no longer purely HBM-bound: instruction issue matters (first
-// version: 2687 instructions per site, 64 % issue utilisation at 52 % of DRAM peak, ncu).  Three
-// things keep the count down:
+// At 544 B/site the kernel is no longer purely HBM-bound: instruction issue matters (round 1:
+// 1714 warp instructions per 32 sites at 72 % of the measured HBM peak, of which 193 were 4-byte
+// loads with their own address arithmetic).  What keeps the count down:
 //   * u16 -> float costs one PRMT and one packed FADD per PAIR of numbers (no conversion-pipe
 //     instruction): the 16 bits are dropped into the mantissa of 2^23 and the offset is
 //     subtracted exactly, giving integer-valued floats; the scales (one per site for vectors,
@@ -24,9 +24,17 @@
 //   * sm_100 packed fp32 (FFMA2/FADD2/FMUL2): hops are processed two at a time -- the same hop
 //     type (fat/long, forward/backward) in two directions, one per lane of a float2 -- so the
 //     whole matrix-vector product, the row rebuild and the conversions issue half as often;
-//   * tiled layout: words are stored [site/32][plane][site%32], so the planes of one site are
-//     compile-time offsets (plane*128 B) from one address instead of one 64-bit address
-//     computation per plane, and a warp still reads whole 128-byte lines.
+//   * 16-BYTE LOADS ONLY (round 2).  The links of one output site are ONE record of 32 (36)
+//     16-byte words, stored [site/32][word][site%32] so that a warp reads 512 contiguous bytes per
+//     load.  The record holds everything the site multiplies with: its 4 forward fat links, its 4
+//     forward long links, and -- stored a second time, already adjointed and negated, like the
+//     reference's own fatback/lngback arrays (generic_ks/fn_links_milc.c:114-199) -- the 4 + 4
+//     links of its backward neighbours.  Backward hops therefore need no neighbour index for the
+//     link, no ghost links and no adjoint code path, and all 16 products are acc += U v.  Inside a
+//     hop type the words are ordered [direction pair][element][direction of the pair], which is the
+//     order the packed arithmetic consumes them in.  A colour vector is one 16-byte word.
+//     Per site: 36 + 16 loads of 16 bytes instead of 193 of 4 bytes; traffic unchanged
+//     (the 16-bit link copy doubles to 2 x 0.27 GB at 32^3x64, of 180 GB).
 #pragma once
 #include "dslash.cuh"
 
@@ -34,9 +42,12 @@ namespace b200ks {
 
 constexpr float kHalfBias = 8388608.0f + 32768.0f;   // 2^23 + offset-binary zero
 
-// word index of plane 0 of site i in a tiled array with npl planes; plane p is at +32*p
-__device__ __forceinline__ unsigned tile_base(int i, int npl) { return ((unsigned)i >> 5) * (unsigned)(npl * 32) + ((unsigned)i & 31u); }
-inline size_t tile_words(size_t nsites, int npl) { return (nsites + 31) / 32 * 32 * (size_t)npl; }
+// 16-byte words per site record: [fwd fat 9][fwd long nq][back fat 9][back long nq], nq = 7 | 9
+__host__ __device__ constexpr int half_long_quads(int nc) { return nc == 7 ? 7 : 9; }
+__host__ __device__ constexpr int half_record_quads(int nc) { return 2 * (9 + half_long_quads(nc)); }
+inline size_t half_link_bytes(size_t nsites, int nc) { return (nsites + 31) / 32 * 32 * (size_t)half_record_quads(nc) * 16; }
+// first 16-byte word of site i's record; word q is at + 32*q
+__device__ __forceinline__ size_t record_base(int i, int nq) { return (size_t)((unsigned)i >> 5) * (unsigned)(nq * 32) + ((unsigned)i & 31u); }
 
 __device__ __forceinline__ float magic_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
 __device__ __forceinline__ float magic_hi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
@@ -54,39 +65,41 @@ __device__ __forceinline__ uint32_t pack_h(float re, float im, float inv) {   //
   return (uint32_t)a | ((uint32_t)b << 16);
 }
 
-// quantise one site's colour vector (6 floats) into its 4 planes (tiled layout)
-__device__ __forceinline__ void store_vec_h(uint32_t *v, int i, const float (&x)[6]) {
+// quantise one site's colour vector (6 floats) into its 16-byte word
+__device__ __forceinline__ void store_vec_h(uint4 *v, int i, const float (&x)[6]) {
   float m = 0.f;
 #pragma unroll
   for (int k = 0; k < 6; k++) m = fmaxf(m, fabsf(x[k]));
   const float inv = m > 0.f ? 32767.0f / m : 0.f;
-  uint32_t *p = v + tile_base(i, 4);
-#pragma unroll
-  for (int c = 0; c < 3; c++) p[32 * c] = pack_h(x[2 * c], x[2 * c + 1], inv);
-  p[96] = __float_as_uint(m);
+  uint4 o;
+  o.x = pack_h(x[0], x[1], inv);
+  o.y = pack_h(x[2], x[3], inv);
+  o.z = pack_h(x[4], x[5], inv);
+  o.w = __float_as_uint(m);
+  v[i] = o;
 }
-__device__ __forceinline__ void load_vec_h(const uint32_t *v, int i, float2 (&o)[3]) {
-  const uint32_t *p = v + tile_base(i, 4);
-  const float k = __uint_as_float(__ldg(p + 96)) * (1.0f / 32767.0f);
-#pragma unroll
-  for (int c = 0; c < 3; c++) o[c] = unpack_h(__ldg(p + 32 * c), k);
+__device__ __forceinline__ void load_vec_h(const uint4 *v, int i, float2 (&o)[3]) {
+  const uint4 w = __ldg(v + i);
+  const float k = __uint_as_float(w.w) * (1.0f / 32767.0f);
+  o[0] = unpack_h(w.x, k);
+  o[1] = unpack_h(w.y, k);
+  o[2] = unpack_h(w.z, k);
 }
 
 struct HalfLinks {
-  const uint32_t *fat[2];   // [parity] 36 planes, tiled
-  const uint32_t *lng[2];   // [parity] 4*nc planes, tiled
-  float fat_k, lng_k, f_k;  // scale/32767 of fat components, long rows, long factor
+  const uint4 *rec[2];      // [parity] site records (see the header comment)
+  float fat_k, lng_k, f_k;  // scale/32767 of fat components, long-link components, long factor
 };
 
 struct DslashHArg {
   Geom g;
   int par;
   HalfLinks L;
-  const uint32_t *in;    // half colour vector, opposite parity
-  const uint32_t *gin;   // ghost buffer (4 planes, tiled)
-  uint32_t *out_h;       // kEpi 0: half output
+  const uint4 *in;       // half colour vector, opposite parity
+  const uint4 *gin;      // ghost buffer, index = neighbour index - Vh
+  uint4 *out_h;          // kEpi 0: half output
   float2 *out_f;         // kEpi 2: float output (A p, consumed by the float update kernel)
-  const uint32_t *w_h;   // kEpi 2: xpay operand (the half search direction, output parity)
+  const uint4 *w_h;      // kEpi 2: xpay operand (the half search direction, output parity)
   const float2 *r;       // kEpi 2: residual (float)
   float s;
   ReduceWs ws;
@@ -105,50 +118,63 @@ struct DslashHArg {
 __device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+// negation folds into the operand modifiers of the consuming FFMA2 / FADD2 (no instruction)
+__device__ __forceinline__ float2 pneg(float2 a) { return make_float2(-a.x, -a.y); }
 
-// Two hops at once: the same hop type in directions DA (lane x) and DB (lane y).
-//   kBack false: acc += U(x) v(x + h)          kBack true: acc -= U(x - h)^dagger v(x - h)
+__device__ __forceinline__ uint4 ld_rec(const uint4 *p) { return __ldcs(p); }   // links: streamed once per stencil
+
+// Two hops at once: hop type (kLong, kBack) in directions 2P (lane x) and 2P+1 (lane y).
+// acc += U v in both lanes; the record already holds -U(x-h)^dagger for the backward types.
 // acc[j] holds real number j (re0, im0, re1, ...) of the two lanes' partial sums.
-template <int DA, int DB, bool kBack, bool kLong, int kMode, int kNc>
-__device__ __forceinline__ void hop_pair_h(const DslashHArg &a, int idx, const Coord &c, bool bnd, float2 (&acc)[6]) {
+template <int P, bool kBack, bool kLong, int kMode, int kNc>
+__device__ __forceinline__ void hop_pair_h(const DslashHArg &a, const uint4 *rec, int idx, const Coord &c, bool bnd, float2 (&acc)[6]) {
   const Geom &g = a.g;
+  constexpr int DA = 2 * P, DB = 2 * P + 1;
   constexpr int nc = kLong ? kNc : 9;
+  constexpr int nql = half_long_quads(kNc);
+  constexpr int q0 = (kBack ? 9 + nql : 0) + (kLong ? 9 : 0);   // first 16-byte word of this hop type
+  constexpr int w0 = P * 2 * nc;                                // first 4-byte word of this pair inside it
+  constexpr int qa = w0 / 4, qb = (w0 + 2 * nc - 1) / 4;        // 16-byte words to load
+  constexpr int off = w0 - 4 * qa;
   const int h = (kLong ? 3 : 1) * (kBack ? -1 : 1);
   const bool partA = (kMode == 1) && (DA >= 2) && bnd && g.part[DA];
   const bool partB = (kMode == 1) && (DB >= 2) && bnd && g.part[DB];
-  const int nA = neighbor<DA, false>(g, idx, c, h), nB = neighbor<DB, false>(g, idx, c, h);
-  const uint32_t *vA = (partA && nA >= g.Vh) ? a.gin + tile_base(nA - g.Vh, 4) : a.in + tile_base(nA, 4);
-  const uint32_t *vB = (partB && nB >= g.Vh) ? a.gin + tile_base(nB - g.Vh, 4) : a.in + tile_base(nB, 4);
-  const int lA = !kBack ? idx : partA ? neighbor<DA, true>(g, idx, c, h) : nA;
-  const int lB = !kBack ? idx : partB ? neighbor<DB, true>(g, idx, c, h) : nB;
-  const uint32_t *links = kLong ? a.L.lng[kBack ? a.par ^ 1 : a.par] : a.L.fat[kBack ? a.par ^ 1 : a.par];
-#ifdef B200KS_PROBE_NOLINKLOAD   // diagnostic build: every site reads the links of tile 0 (L1-resident) => compute time only
-  const uint32_t *uA = links + (threadIdx.x & 31) + DA * nc * 32;
-  const uint32_t *uB = links + (threadIdx.x & 31) + DB * nc * 32;
-#else
-  const uint32_t *uA = links + tile_base(lA, 4 * nc) + DA * nc * 32;
-  const uint32_t *uB = links + tile_base(lB, 4 * nc) + DB * nc * 32;
-#endif
-
-  const float2 mB = make_float2(-kHalfBias, -kHalfBias), pB = make_float2(kHalfBias, kHalfBias);
-  const float2 neg1 = make_float2(-1.f, -1.f);
-  // neighbour vectors; the negated copy supplies the minus sign of the complex product
-  float2 vre[3], vim[3], vneg[3];
+  const int nA = neighbor<DA, false, kMode != 0>(g, idx, c, h), nB = neighbor<DB, false, kMode != 0>(g, idx, c, h);
+  const uint4 *vA = (partA && nA >= g.Vh) ? a.gin + (nA - g.Vh) : a.in + nA;
+  const uint4 *vB = (partB && nB >= g.Vh) ? a.gin + (nB - g.Vh) : a.in + nB;
+  const uint4 va = __ldg(vA), vb = __ldg(vB);
+  uint32_t w[4 * (qb - qa + 1)];
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const uint32_t wa = __ldg(vA + 32 * k), wb = __ldg(vB + 32 * k);
-    const float2 lo = make_float2(magic_lo(wa), magic_lo(wb)), hi = make_float2(magic_hi(wa), magic_hi(wb));
-    vre[k] = padd(lo, mB);
-    vim[k] = padd(hi, mB);
-    vneg[k] = kBack ? pfma(lo, neg1, pB) : pfma(hi, neg1, pB);   // backward: -re, forward: -im
+  for (int q = qa; q <= qb; q++) {
+#ifdef B200KS_PROBE_NOLINKLOAD   // diagnostic build: every site reads record 0 (L1-resident) => compute time only
+    const uint4 x = __ldg(a.L.rec[a.par] + (threadIdx.x & 31) + 32 * (q0 + q));
+#else
+    const uint4 x = ld_rec(rec + 32 * (q0 + q));
+#endif
+    w[4 * (q - qa) + 0] = x.x;
+    w[4 * (q - qa) + 1] = x.y;
+    w[4 * (q - qa) + 2] = x.z;
+    w[4 * (q - qa) + 3] = x.w;
   }
-  const float kvA = __uint_as_float(__ldg(vA + 96)), kvB = __uint_as_float(__ldg(vB + 96));
+  const float2 mB = make_float2(-kHalfBias, -kHalfBias);
+  // neighbour vectors
+  float2 vre[3], vim[3];
+  {
+    const uint32_t wa[3] = {va.x, va.y, va.z}, wb[3] = {vb.x, vb.y, vb.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float2 lo = make_float2(magic_lo(wa[k]), magic_lo(wb[k])), hi = make_float2(magic_hi(wa[k]), magic_hi(wb[k]));
+      vre[k] = padd(lo, mB);
+      vim[k] = padd(hi, mB);
+    }
+  }
+  const float kvA = __uint_as_float(va.w), kvB = __uint_as_float(vb.w);
   // links as integer-valued floats
   float2 ure[9], uim[9];
   constexpr int nload = (nc == 7) ? 6 : 9;
 #pragma unroll
   for (int e = 0; e < nload; e++) {
-    const uint32_t wa = __ldcs(uA + 32 * e), wb = __ldcs(uB + 32 * e);
+    const uint32_t wa = w[off + 2 * e], wb = w[off + 2 * e + 1];
     ure[e] = padd(make_float2(magic_lo(wa), magic_lo(wb)), mB);
     uim[e] = padd(make_float2(magic_hi(wa), magic_hi(wb)), mB);
   }
@@ -159,16 +185,13 @@ __device__ __forceinline__ void hop_pair_h(const DslashHArg &a, int idx, const C
     for (int e = 0; e < nload; e++) sum = padd(sum, padd(ure[e], uim[e]));
 #pragma unroll
     for (int k = 0; k < 3; k++) sum = padd(sum, padd(vre[k], vim[k]));
-    if (nc == 7) {
-      const uint32_t wa = __ldcs(uA + 32 * 6), wb = __ldcs(uB + 32 * 6);
-      sum = padd(sum, make_float2(magic_lo(wa), magic_lo(wb)));
-    }
+    if (nc == 7) sum = padd(sum, make_float2(magic_lo(w[off + 12]), magic_lo(w[off + 13])));
     acc[0] = pfma(make_float2(kvA, kvB), sum, acc[0]);
     return;
   }
 #endif
   if (nc == 7) {  // row3 = f * conj(row1 x row2), f brought to the rows' integer grid
-    const uint32_t wa = __ldcs(uA + 32 * 6), wb = __ldcs(uB + 32 * 6);
+    const uint32_t wa = w[off + 12], wb = w[off + 13];
     const float fk = a.L.f_k * a.L.lng_k;
     const float2 fk2 = make_float2(fk, fk);
     const float2 fre = pmul(padd(make_float2(magic_lo(wa), magic_lo(wb)), mB), fk2);
@@ -178,39 +201,32 @@ __device__ __forceinline__ void hop_pair_h(const DslashHArg &a, int idx, const C
       const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
       // d = U[k1]*U[3+k2] - U[k2]*U[3+k1] ;  c = conj(d)
       float2 dre = pmul(ure[k1], ure[3 + k2]);
-      dre = pfma(pmul(uim[k1], neg1), uim[3 + k2], dre);
-      dre = pfma(pmul(ure[k2], neg1), ure[3 + k1], dre);
+      dre = pfma(pneg(uim[k1]), uim[3 + k2], dre);
+      dre = pfma(pneg(ure[k2]), ure[3 + k1], dre);
       dre = pfma(uim[k2], uim[3 + k1], dre);
       float2 dim = pmul(ure[k1], uim[3 + k2]);
       dim = pfma(uim[k1], ure[3 + k2], dim);
-      dim = pfma(pmul(ure[k2], neg1), uim[3 + k1], dim);
-      dim = pfma(pmul(uim[k2], neg1), ure[3 + k1], dim);
+      dim = pfma(pneg(ure[k2]), uim[3 + k1], dim);
+      dim = pfma(pneg(uim[k2]), ure[3 + k1], dim);
       // f * (dre - i dim) = (fre*dre + fim*dim) + i (fim*dre - fre*dim)
       ure[6 + k] = pfma(fre, dre, pmul(fim, dim));
-      uim[6 + k] = pfma(fim, dre, pmul(pmul(fre, neg1), dim));
+      uim[6 + k] = pfma(fim, dre, pmul(pneg(fre), dim));
     }
   }
-  // t = U v (forward) or U^dagger v (backward)
+  // t = U v : (ure + i uim)(vre + i vim)
   const float2 zero = make_float2(0.f, 0.f);
   float2 t[6] = {zero, zero, zero, zero, zero, zero};
 #pragma unroll
   for (int r = 0; r < 3; r++)
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      const int e = kBack ? 3 * k + r : 3 * r + k;
-      if (!kBack) {   // (ure + i uim)(vre + i vim)
-        t[2 * r] = pfma(ure[e], vre[k], t[2 * r]);
-        t[2 * r] = pfma(uim[e], vneg[k], t[2 * r]);
-        t[2 * r + 1] = pfma(ure[e], vim[k], t[2 * r + 1]);
-        t[2 * r + 1] = pfma(uim[e], vre[k], t[2 * r + 1]);
-      } else {        // (ure - i uim)(vre + i vim)
-        t[2 * r] = pfma(ure[e], vre[k], t[2 * r]);
-        t[2 * r] = pfma(uim[e], vim[k], t[2 * r]);
-        t[2 * r + 1] = pfma(ure[e], vim[k], t[2 * r + 1]);
-        t[2 * r + 1] = pfma(uim[e], vneg[k], t[2 * r + 1]);
-      }
+      const int e = 3 * r + k;
+      t[2 * r] = pfma(ure[e], vre[k], t[2 * r]);
+      t[2 * r] = pfma(pneg(uim[e]), vim[k], t[2 * r]);
+      t[2 * r + 1] = pfma(ure[e], vim[k], t[2 * r + 1]);
+      t[2 * r + 1] = pfma(uim[e], vre[k], t[2 * r + 1]);
     }
-  const float ku = (kLong ? a.L.lng_k : a.L.fat_k) * (kBack ? -1.0f / 32767.0f : 1.0f / 32767.0f);
+  const float ku = (kLong ? a.L.lng_k : a.L.fat_k) * (1.0f / 32767.0f);
   const float2 sc = make_float2(ku * kvA, ku * kvB);
 #pragma unroll
   for (int j = 0; j < 6; j++) acc[j] = pfma(sc, t[j], acc[j]);
@@ -245,16 +261,17 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
   if (active) {
     const int idx = (kMode == 0) ? k : bnd ? a.sites[k] : interior_site(a.g, k);
     const Coord c = site_coord(a.g, idx, a.par);
+    const uint4 *rec = a.L.rec[a.par] + record_base(idx, half_record_quads(kNc));
     const float2 zero = make_float2(0.f, 0.f);
     float2 acc2[6] = {zero, zero, zero, zero, zero, zero};
-    hop_pair_h<0, 1, false, false, kMode, kNc>(a, idx, c, bnd, acc2);
-    hop_pair_h<2, 3, false, false, kMode, kNc>(a, idx, c, bnd, acc2);
-    hop_pair_h<0, 1, false, true, kMode, kNc>(a, idx, c, bnd, acc2);
-    hop_pair_h<2, 3, false, true, kMode, kNc>(a, idx, c, bnd, acc2);
-    hop_pair_h<0, 1, true, false, kMode, kNc>(a, idx, c, bnd, acc2);
-    hop_pair_h<2, 3, true, false, kMode, kNc>(a, idx, c, bnd, acc2);
-    hop_pair_h<0, 1, true, true, kMode, kNc>(a, idx, c, bnd, acc2);
-    hop_pair_h<2, 3, true, true, kMode, kNc>(a, idx, c, bnd, acc2);
+    hop_pair_h<0, false, false, kMode, kNc>(a, rec, idx, c, bnd, acc2);
+    hop_pair_h<1, false, false, kMode, kNc>(a, rec, idx, c, bnd, acc2);
+    hop_pair_h<0, false, true, kMode, kNc>(a, rec, idx, c, bnd, acc2);
+    hop_pair_h<1, false, true, kMode, kNc>(a, rec, idx, c, bnd, acc2);
+    hop_pair_h<0, true, false, kMode, kNc>(a, rec, idx, c, bnd, acc2);
+    hop_pair_h<1, true, false, kMode, kNc>(a, rec, idx, c, bnd, acc2);
+    hop_pair_h<0, true, true, kMode, kNc>(a, rec, idx, c, bnd, acc2);
+    hop_pair_h<1, true, true, kMode, kNc>(a, rec, idx, c, bnd, acc2);
     float acc[6];
 #pragma unroll
     for (int j = 0; j < 6; j++) acc[j] = acc2[j].x + acc2[j].y;
@@ -289,7 +306,7 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
 
 // x += a p ; r += a ttt ; p = r + b p (re-quantised) ; sum |r|^2.   x, r, ttt float; p half.
 __global__ void __launch_bounds__(kBlock)
-cg_update_half_kernel(float2 *x, float2 *r, uint32_t *p_h, const float2 *ttt, int stride, int n, CgState *st, ReduceWs ws,
+cg_update_half_kernel(float2 *x, float2 *r, uint4 *p_h, const float2 *ttt, int stride, int n, CgState *st, ReduceWs ws,
                       int fuse_scalar) {
   if (st->stop) return;
   const double rsq = st->rsq, oldrsq = st->upd[0];
@@ -332,7 +349,7 @@ cg_update_half_kernel(float2 *x, float2 *r, uint32_t *p_h, const float2 *ttt, in
 
 // Reliable update with a half search direction (see mixed_reliable_kernel in blas.cuh).
 __global__ void __launch_bounds__(kBlock)
-mixed_reliable_half_kernel(const double2 *b, const double2 *ttt, float2 *r_lo, uint32_t *p_h, int stride, int n, int first,
+mixed_reliable_half_kernel(const double2 *b, const double2 *ttt, float2 *r_lo, uint4 *p_h, int stride, int n, int first,
                            ReduceWs ws, double *out) {
   const int i = blockIdx.x * kBlock + threadIdx.x;
   double s[2] = {0, 0};
@@ -358,7 +375,7 @@ mixed_reliable_half_kernel(const double2 *b, const double2 *ttt, float2 *r_lo, u
 }
 
 // double <-> 16-bit colour vectors (tests, timing probes)
-__global__ void __launch_bounds__(kBlock) vec_d2h_kernel(uint32_t *h, const double2 *d, int stride, int n) {
+__global__ void __launch_bounds__(kBlock) vec_d2h_kernel(uint4 *h, const double2 *d, int stride, int n) {
   const int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   float x[6];
@@ -370,7 +387,7 @@ __global__ void __launch_bounds__(kBlock) vec_d2h_kernel(uint32_t *h, const doub
   }
   store_vec_h(h, i, x);
 }
-__global__ void __launch_bounds__(kBlock) vec_h2d_kernel(double2 *d, const uint32_t *h, int stride, int n) {
+__global__ void __launch_bounds__(kBlock) vec_h2d_kernel(double2 *d, const uint4 *h, int stride, int n) {
   const int i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   float2 v[3];
@@ -379,35 +396,120 @@ __global__ void __launch_bounds__(kBlock) vec_h2d_kernel(double2 *d, const uint3
   for (int c = 0; c < 3; c++) d[(size_t)c * stride + i] = make_double2((double)v[c].x, (double)v[c].y);
 }
 
-// ---- link quantisation ---------------------------------------------------------------------------
-// max |component| of planes [p0, p1) of every link direction (ncomp planes per direction)
-template <typename T>
-__global__ void __launch_bounds__(kBlock)
-link_absmax_kernel(const typename Vec2<T>::type *U, int lstride, int n, int nc, int p0, int p1, unsigned *out) {
-  const int i = blockIdx.x * kBlock + threadIdx.x;
-  float m = 0.f;
-  if (i < n)
-    for (int mu = 0; mu < 4; mu++)
-      for (int e = p0; e < p1; e++) {
-        const auto v = U[(size_t)(mu * nc + e) * lstride + i];
-        m = fmaxf(m, fmaxf(fabsf((float)v.x), fabsf((float)v.y)));
-      }
+// ---- building the site records from the master links (double or single SoA, ghost tails filled) ----
+// Loads link mu of `field` at site index i (nc = 7: rows 1, 2 and the factor; row 3 rebuilt).
+template <typename T, int kNc>
+__device__ __forceinline__ void load_master(const typename Vec2<T>::type *field, int lstride, int mu, int i,
+                                            typename Vec2<T>::type (&U)[9]) {
+  using T2 = typename Vec2<T>::type;
+  const T2 *p = field + (size_t)mu * kNc * lstride + i;
+  if (kNc == 9) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+    for (int e = 0; e < 9; e++) U[e] = p[(size_t)e * lstride];
+  } else {
+#pragma unroll
+    for (int e = 0; e < 6; e++) U[e] = p[(size_t)e * lstride];
+    reconstruct_row3<T, T2>(U, p[(size_t)6 * lstride]);
+  }
+}
+// B = -U^dagger
+template <typename T2>
+__device__ __forceinline__ void neg_adjoint(const T2 (&U)[9], T2 (&B)[9]) {
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      B[3 * r + k].x = -U[3 * k + r].x;
+      B[3 * r + k].y = U[3 * k + r].y;
+    }
 }
 
-template <typename T>
+// max |component| of the fat links (out[0]), of the FULL long links incl. the rebuilt third row
+// (out[1]; the backward copies store columns as rows) and of the U(3) factors (out[2]; a link's
+// factor and its adjoint's have the same modulus), over n sites (ghost tails included)
+template <typename T, int kNc>
 __global__ void __launch_bounds__(kBlock)
-quantize_link_kernel(uint32_t *dst, const typename Vec2<T>::type *U, int lstride, int n, int nc, float inv_rows, float inv_f) {
+half_absmax_kernel(const typename Vec2<T>::type *fat, const typename Vec2<T>::type *lng, int lstride, int n, unsigned *out) {
+  using T2 = typename Vec2<T>::type;
   const int i = blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
-  for (int mu = 0; mu < 4; mu++)
-    for (int e = 0; e < nc; e++) {
-      const auto v = U[(size_t)(mu * nc + e) * lstride + i];
-      const float inv = (nc == 7 && e == 6) ? inv_f : inv_rows;
-      dst[tile_base(i, 4 * nc) + (mu * nc + e) * 32] = pack_h((float)v.x, (float)v.y, inv);
+  float m[3] = {0.f, 0.f, 0.f};
+  if (i < n)
+    for (int mu = 0; mu < 4; mu++) {
+      T2 U[9];
+      load_master<T, 9>(fat, lstride, mu, i, U);
+#pragma unroll
+      for (int e = 0; e < 9; e++) m[0] = fmaxf(m[0], fmaxf(fabsf((float)U[e].x), fabsf((float)U[e].y)));
+      load_master<T, kNc>(lng, lstride, mu, i, U);
+#pragma unroll
+      for (int e = 0; e < 9; e++) m[1] = fmaxf(m[1], fmaxf(fabsf((float)U[e].x), fabsf((float)U[e].y)));
+      if (kNc == 7) {
+        const T2 f = lng[(size_t)(mu * 7 + 6) * lstride + i];
+        m[2] = fmaxf(m[2], fmaxf(fabsf((float)f.x), fabsf((float)f.y)));
+      }
     }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m[k] = fmaxf(m[k], __shfl_xor_sync(0xffffffffu, m[k], o));
+    if ((threadIdx.x & 31) == 0 && m[k] > 0.f) atomicMax(out + k, __float_as_uint(m[k]));
+  }
+}
+
+// 4-byte word `wi` of a hop type that starts at 16-byte word q0 of the record at `out`
+__device__ __forceinline__ void put_word(uint32_t *out, int q0, int wi, uint32_t word) {
+  out[(size_t)128 * (q0 + (wi >> 2)) + (wi & 3)] = word;
+}
+// one link of direction mu into the hop type at q0 (kLong: a long link, stored with kNc words)
+template <typename T, int kNc, bool kLong>
+__device__ __forceinline__ void put_link(uint32_t *out, int q0, int mu, const typename Vec2<T>::type (&U)[9], float inv, float inv_f) {
+  constexpr int nc = kLong ? kNc : 9;
+  const int base = (mu >> 1) * 2 * nc + (mu & 1);   // word of element e: base + 2*e
+  if (!kLong || kNc == 9) {
+#pragma unroll
+    for (int e = 0; e < 9; e++) put_word(out, q0, base + 2 * e, pack_h((float)U[e].x, (float)U[e].y, inv));
+  } else {
+    double fx, fy, dev;
+    long_factor<T>(U, fx, fy, dev);
+#pragma unroll
+    for (int e = 0; e < 6; e++) put_word(out, q0, base + 2 * e, pack_h((float)U[e].x, (float)U[e].y, inv));
+    put_word(out, q0, base + 12, pack_h((float)fx, (float)fy, inv_f));
+  }
+}
+
+// One thread per output site of parity `par`: writes the site's record.  this_* = master links of the
+// output parity (forward hops), other_* = of the opposite parity (backward hops: the link stored at
+// the backward neighbour, or in the backward-ghost tail of the field on a partitioned lattice).
+template <typename T, int kNc, int MU>
+__device__ __forceinline__ void record_dir(uint32_t *out, const typename Vec2<T>::type *fat_this, const typename Vec2<T>::type *lng_this,
+                                           const typename Vec2<T>::type *fat_other, const typename Vec2<T>::type *lng_other,
+                                           const Geom &g, int idx, const Coord &c, float inv_fat, float inv_lng, float inv_f) {
+  using T2 = typename Vec2<T>::type;
+  constexpr int nql = half_long_quads(kNc);
+  T2 U[9], B[9];
+  load_master<T, 9>(fat_this, g.lstride, MU, idx, U);
+  put_link<T, kNc, false>(out, 0, MU, U, inv_fat, inv_f);
+  load_master<T, kNc>(lng_this, g.lstride, MU, idx, U);
+  put_link<T, kNc, true>(out, 9, MU, U, inv_lng, inv_f);
+  load_master<T, 9>(fat_other, g.lstride, MU, neighbor<MU, true>(g, idx, c, -1), U);
+  neg_adjoint<T2>(U, B);
+  put_link<T, kNc, false>(out, 9 + nql, MU, B, inv_fat, inv_f);
+  load_master<T, kNc>(lng_other, g.lstride, MU, neighbor<MU, true>(g, idx, c, -3), U);
+  neg_adjoint<T2>(U, B);
+  put_link<T, kNc, true>(out, 18 + nql, MU, B, inv_lng, inv_f);
+}
+template <typename T, int kNc>
+__global__ void __launch_bounds__(kBlock)
+half_records_kernel(uint4 *rec, const typename Vec2<T>::type *fat_this, const typename Vec2<T>::type *lng_this,
+                    const typename Vec2<T>::type *fat_other, const typename Vec2<T>::type *lng_other, const Geom g, int par,
+                    float inv_fat, float inv_lng, float inv_f) {
+  const int idx = blockIdx.x * kBlock + threadIdx.x;
+  if (idx >= g.Vh) return;
+  const Coord c = site_coord(g, idx, par);
+  uint32_t *out = (uint32_t *)(rec + record_base(idx, half_record_quads(kNc)));
+  record_dir<T, kNc, 0>(out, fat_this, lng_this, fat_other, lng_other, g, idx, c, inv_fat, inv_lng, inv_f);
+  record_dir<T, kNc, 1>(out, fat_this, lng_this, fat_other, lng_other, g, idx, c, inv_fat, inv_lng, inv_f);
+  record_dir<T, kNc, 2>(out, fat_this, lng_this, fat_other, lng_other, g, idx, c, inv_fat, inv_lng, inv_f);
+  record_dir<T, kNc, 3>(out, fat_this, lng_this, fat_other, lng_other, g, idx, c, inv_fat, inv_lng, inv_f);
 }
 
 }  // namespace b200ks

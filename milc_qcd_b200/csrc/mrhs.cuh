@@ -51,7 +51,7 @@ __device__ __forceinline__ void hop_dir_m(const DslashMArg<T, K> &a, int idx, co
   for (int hop = 0; hop < 4; hop++) {
     const int h = (hop == 0) ? 1 : (hop == 1) ? 3 : (hop == 2) ? -1 : -3;
     const bool lng = (hop & 1);
-    const int n = neighbor<D, false>(g, idx, c, h);
+    const int n = neighbor<D, false, false>(g, idx, c, h);   // (single-GPU kernel: nothing partitioned)
     if (hop < 2) {
       if (lng) load_long<T, T2, kNc>(a.lng_this, g.lstride, D, idx, U);
       else load_link<T, T2>(a.fat_this, g.lstride, D, idx, U);

@@ -74,6 +74,7 @@ void b200ks_milc_finalize(void) {
   fn_last = NULL;
 }
 int b200ks_milc_total_iters(void) { return s_total_iters; }
+b200ks_ctx *b200ks_milc_context(void) { return s_ctx; } /* diagnostics: b200ks_call_profile, b200ks_launch_count, ... */
 #endif
 
 static void die(const char *myname) {

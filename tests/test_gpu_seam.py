@@ -1,0 +1,291 @@
+"""GPU tests of the drop-in seam itself (round 2):
+
+* route 1's COMPILED symbols (milc_qcd_b200/libb200ks_milc.so: ks_congrad_parity_gpu, ks_congrad_block_parity_gpu,
+  ks_multicg_offset_field_gpu, dslash_fn_field) called through ctypes on plain pageable numpy arrays in
+  MILC's layout, against the oracle -- what a MILC binary built with these objects executes;
+* the link cache: in-place edits MILC does not announce (boundary_twist_fn negating whole time slices,
+  generic_ks/fermion_links_fn_twist_milc.c:318-400) are seen by the background verification and the solve is
+  repeated on the new links;
+* the Fermilab relative residual on one GPU (d_congrad5_fn_milc.c:37-56);
+* the single-process multi-GPU context (b200ks_create_multi) behind the same host-array call surface.  On a
+  1-GPU box its members share the device (small lattices only), which still runs every line of the multi-GPU
+  host path: member threads, strided access to the global arrays, the in-process bootstrap, peer-mapped halo
+  pushes and the flag-based all-reduce.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, fields_for
+
+pytestmark = pytest.mark.gpu
+
+EVEN, ODD, EVENANDODD = 2, 1, 3
+DSLASH_TOL = 1e-13
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+from milc_qcd_b200.milc_abi import quark_invert_control as Qic, ks_param as KsParam, fn_links_t as FnLinks  # noqa: E402
+
+
+def _qic(parity, resid=1e-9, relresid=0.0, mx=500, nrestart=5):
+    q = Qic()
+    q.prec, q.max, q.nrestart, q.parity, q.resid, q.relresid = 2, mx, nrestart, parity, resid, relresid
+    return q
+
+
+def twist_time_slices(fat, lng, dims):
+    """What boundary_twist_fn's switch_time_apbc does: negate the t links that cross the time boundary --
+    fat links of the last slice, long links of the last three -- in place, no notification."""
+    V = fat.shape[0]
+    sl = V // 2 // dims[3]
+    for blk in (0, V // 2):
+        fat[blk + V // 2 - sl: blk + V // 2, 3] *= -1
+        lng[blk + V // 2 - 3 * sl: blk + V // 2, 3] *= -1
+
+
+@pytest.fixture()
+def shim():
+    """The compiled route-1 library against the REAL libb200ks.so."""
+    from milc_qcd_b200 import build, milc_abi
+    build.build_all()
+    lib = milc_abi.load()
+    yield lib
+    lib.b200ks_milc_finalize()
+
+
+@pytest.mark.parametrize("mixed", [0, 2])
+def test_route1_compiled_symbols_match_oracle_and_follow_in_place_link_edits(shim, oracle, mixed):
+    dims = (8, 8, 8, 12)
+    fat0, lng0, src = fields_for(dims)
+    fat, lng = fat0.copy(), lng0.copy()          # plain pageable arrays, like MILC's malloc'ed fields
+    V = src.shape[0]
+    shim.b200ks_milc_setup(*dims, mixed)
+    fn = FnLinks()
+    fn.fat, fn.lng, fn.notify_quda_new_links = fat.ctypes.data, lng.ctypes.data, 1
+    mass, resid = 0.05, 1e-9
+    b = src.copy()
+    b[V // 2:] = 0
+
+    def solve():
+        x = np.zeros_like(b)
+        q = _qic(EVEN, resid)
+        it = shim.ks_congrad_parity_gpu(b.ctypes.data, x.ctypes.data, C.byref(q), mass, C.byref(fn))
+        return it, q, x
+
+    def check(it, q, x, f, l):
+        xo = np.zeros_like(b)
+        ito, qo = oracle.congrad(dims, f, l, b, xo, mass, EVEN, 500, 5, resid)
+        assert q.converged == 1 and q.final_iters == it and q.final_rsq < resid ** 2
+        assert abs(it - ito) <= (max(2, 0.02 * ito) if mixed == 0 else 1.5 * ito)
+        assert np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
+        assert np.all(x[V // 2:] == 0)       # only qic->parity sites are written
+
+    it, q, x = solve()
+    check(it, q, x, fat, lng)
+    assert fn.notify_quda_new_links == 0
+    # in-place edit without notice: the resident links are stale, the verification running beside the solve
+    # must notice and the call must return the solution for the NEW links
+    twist_time_slices(fat, lng, dims)
+    it, q, x = solve()
+    check(it, q, x, fat, lng)
+    xs = np.zeros_like(b)
+    oracle.congrad(dims, fat0, lng0, b, xs, mass, EVEN, 500, 5, resid)
+    assert np.linalg.norm(x - xs) > 1e-3 * np.linalg.norm(xs)     # (the edit does change the answer)
+    # and back
+    twist_time_slices(fat, lng, dims)
+    it, q, x = solve()
+    check(it, q, x, fat0, lng0)
+
+    # dslash_fn_field
+    got = np.zeros_like(src)
+    shim.dslash_fn_field(src.ctypes.data, got.ctypes.data, EVENANDODD, C.byref(fn))
+    assert rel_err(got, oracle.dslash(dims, fat, lng, src, EVENANDODD)) <= DSLASH_TOL
+
+    # ks_multicg_offset_field_gpu
+    from milc_qcd_b200 import fields as F
+    offsets = np.roll(F.rhmc_offsets(5, mass), 2)
+    ksp = (KsParam * len(offsets))()
+    for j, o in enumerate(offsets):
+        ksp[j].offset = float(o)
+    qs = (Qic * len(offsets))(*[_qic(EVEN, 1e-8, mx=3000, nrestart=1) for _ in offsets])
+    ps = [np.full_like(b, -2.0) for _ in offsets]
+    pp = (C.c_void_p * len(offsets))(*[p.ctypes.data for p in ps])
+    itm = shim.ks_multicg_offset_field_gpu(b.ctypes.data, pp, ksp, len(offsets), qs, C.byref(fn))
+    itmo, pso, _ = oracle.multicg(dims, fat, lng, b, offsets, EVEN, 3000, 1, 1e-8)
+    assert abs(itm - itmo) <= (max(2, 0.02 * itmo) if mixed == 0 else 3 * itmo)
+    for j in range(len(offsets)):
+        assert np.linalg.norm(ps[j][:V // 2] - pso[j][:V // 2]) <= 1e-6 * np.linalg.norm(pso[j][:V // 2])
+        assert np.all(ps[j][V // 2:] == -2.0) and qs[j].converged == 1
+
+    # ks_congrad_block_parity_gpu, 3 sources (the colours of a point source in ks_spectrum)
+    srcs = [F.make_source(dims, seed=77 + k, parity=EVEN) for k in range(3)]
+    dsts = [np.zeros_like(s) for s in srcs]
+    sp = (C.c_void_p * 3)(*[s.ctypes.data for s in srcs])
+    dp = (C.c_void_p * 3)(*[d.ctypes.data for d in dsts])
+    q = _qic(EVEN, resid)
+    tot = shim.ks_congrad_block_parity_gpu(3, sp, dp, C.byref(q), mass, C.byref(fn))
+    ref_tot = 0
+    for k in range(3):
+        xo = np.zeros_like(srcs[k])
+        ito, _ = oracle.congrad(dims, fat, lng, srcs[k], xo, mass, EVEN, 500, 5, resid)
+        ref_tot += ito
+        assert np.linalg.norm(dsts[k] - xo) <= 1e-7 * np.linalg.norm(xo)
+    assert q.converged == 1 and q.final_iters == tot
+    if mixed == 0:
+        assert abs(tot - ref_tot) <= max(4, 0.02 * ref_tot)
+    assert shim.b200ks_milc_total_iters() > 0
+
+
+def test_links_sync_modes_and_counters(oracle):
+    from milc_qcd_b200 import api
+    dims = (8, 8, 8, 8)
+    fat0, lng0, src = fields_for(dims)
+    fat, lng = fat0.copy(), lng0.copy()
+    V = src.shape[0]
+    b = src.copy()
+    b[V // 2:] = 0
+    ctx = api.Context(dims)
+    assert ctx.links_sync(fat, lng) == 1                      # nothing resident yet: upload
+    assert ctx.links_sync(fat, lng) == 0                      # verification started, nothing uploaded
+    x = np.zeros_like(b)
+    ctx.congrad(b, x, 0.05, EVEN, 500, 5, 1e-9)               # joins it
+    st = ctx.links_sync_stats()
+    assert st["uploads"] == 1 and st["verifications"] >= 1
+    twist_time_slices(fat, lng, dims)
+    assert ctx.links_sync(fat, lng, mode=0) == 0              # trusting the flag: stale links, by request
+    assert ctx.links_sync(fat, lng, mode=3) == 1              # blocking comparison sees the edit
+    assert ctx.links_sync(fat, lng, mode=3) == 0
+    twist_time_slices(fat, lng, dims)
+    assert ctx.links_sync(fat, lng, mode=2) == 0              # in the background ...
+    x = np.zeros_like(b)
+    it, res = ctx.congrad(b, x, 0.05, EVEN, 500, 5, 1e-9)     # ... the solve is repeated on the new links
+    xo = np.zeros_like(b)
+    ito, _ = oracle.congrad(dims, fat0, lng0, b, xo, 0.05, EVEN, 500, 5, 1e-9)
+    assert abs(it - ito) <= 2 and np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
+    assert ctx.links_sync_stats()["uploads"] == 3
+    assert ctx.links_sync(fat, lng, changed_hint=1) == 1      # MILC's own notification
+    assert ctx.links_sync(fat.copy(), lng, mode=0) == 1       # other arrays
+    ctx.close()
+
+
+@pytest.mark.parametrize("dims,parity", [((8, 8, 8, 8), EVEN), ((8, 12, 6, 10), ODD)])
+def test_fermilab_relative_residual_single_gpu(oracle, dims, parity):
+    """qic->relresid != 0 (d_congrad5_fn_milc.c:37-56,177-180,234-237): cg_restart_kernel<T,true> /
+    cg_update_kernel<T,true> against the oracle's restatement."""
+    from milc_qcd_b200 import api
+    fat, lng, src = fields_for(dims)
+    V = src.shape[0]
+    b = src.copy()
+    sl = slice(0, V // 2) if parity == EVEN else slice(V // 2, V)
+    other = slice(V // 2, V) if parity == EVEN else slice(0, V // 2)
+    b[other] = 0
+    ctx = api.Context(dims)
+    ctx.load_links(fat, lng)
+    for resid, relresid in ((1e-9, 1e-3), (0.0, 1e-4), (1e-6, 1e-6)):
+        x = np.zeros_like(b)
+        it, res = ctx.congrad(b, x, 0.05, parity, 500, 5, resid, relresid=relresid)
+        xo = np.zeros_like(b)
+        ito, qo = oracle.congrad(dims, fat, lng, b, xo, 0.05, parity, 500, 5, resid, relresid=relresid)
+        assert abs(it - ito) <= max(2, 0.02 * ito), (resid, relresid, it, ito)
+        assert res["converged"] == qo["converged"] == 1
+        # the value at exit depends on the exit iteration (+-1): same magnitude, both under target
+        assert 0.5 < res["final_relrsq"] / qo["final_relrsq"] < 2.0
+        assert res["final_relrsq"] < relresid ** 2 or res["final_relrsq"] < relresid
+        assert np.linalg.norm(x[sl] - xo[sl]) <= 1e-2 * max(resid, relresid) / (4 * 0.05 ** 2) * np.linalg.norm(xo[sl]) + 1e-7 * np.linalg.norm(xo[sl])
+    ctx.close()
+
+
+def _devices(n):
+    import torch
+    have = torch.cuda.device_count()
+    return list(range(n)) if have >= n else [k % have for k in range(n)]
+
+
+@pytest.mark.parametrize("ngpu,dims", [(2, (8, 8, 8, 16)), (4, (8, 8, 8, 16)), (4, (8, 6, 16, 8)), (8, (4, 8, 16, 16)), (2, (8, 8, 8, 8))])
+def test_single_process_multi_gpu_context_matches_oracle(oracle, ngpu, dims):
+    """b200ks_create_multi: the same calls on the same GLOBAL MILC-order arrays as a single-GPU context."""
+    from milc_qcd_b200 import api, fields as F
+    fat, lng, src = fields_for(dims)
+    V = src.shape[0]
+    ctx = api.Context(dims, ngpu=ngpu, devices=_devices(ngpu))
+    assert ctx.num_gpus() == ngpu and ctx.halo_mode() == 2
+    assert ctx.links_sync(fat, lng) == 1
+    for parity in (EVEN, ODD, EVENANDODD):
+        got = np.full_like(src, 3.0)
+        ctx.dslash(src, got, parity)
+        want = oracle.dslash(dims, fat, lng, src, parity)
+        sl = slice(0, V // 2) if parity == EVEN else slice(V // 2, V) if parity == ODD else slice(0, V)
+        assert rel_err(got[sl], want[sl]) <= DSLASH_TOL
+        if parity != EVENANDODD:
+            ot = slice(V // 2, V) if parity == EVEN else slice(0, V // 2)
+            assert np.all(got[ot] == 3.0)
+    b = src.copy()
+    b[V // 2:] = 0
+    for mixed in (0, 1, 2):
+        x = np.zeros_like(b)
+        it, res = ctx.congrad(b, x, 0.05, EVEN, 500, 5, 1e-9, mixed_precision=mixed)
+        xo = np.zeros_like(b)
+        ito, qo = oracle.congrad(dims, fat, lng, b, xo, 0.05, EVEN, 500, 5, 1e-9)
+        assert res["converged"] == 1
+        assert abs(it - ito) <= (max(2, 0.02 * ito) if mixed == 0 else 0.25 * ito if mixed == 1 else 1.5 * ito)
+        assert np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
+    # relative residual (its own all-reduce path)
+    x = np.zeros_like(b)
+    it, res = ctx.congrad(b, x, 0.05, EVEN, 500, 5, 1e-9, relresid=1e-3)
+    xo = np.zeros_like(b)
+    ito, qo = oracle.congrad(dims, fat, lng, b, xo, 0.05, EVEN, 500, 5, 1e-9, relresid=1e-3)
+    assert abs(it - ito) <= max(2, 0.02 * ito)
+    offsets = np.roll(F.rhmc_offsets(5, 0.05), 2)
+    ps = [np.zeros_like(b) for _ in offsets]
+    itm, resm = ctx.multicg(b, ps, offsets, EVEN, 3000, 1, 1e-8)
+    itmo, pso, qmo = oracle.multicg(dims, fat, lng, b, offsets, EVEN, 3000, 1, 1e-8)
+    assert abs(itm - itmo) <= max(2, 0.02 * itmo)
+    for j in range(len(offsets)):
+        assert np.linalg.norm(ps[j][:V // 2] - pso[j][:V // 2]) <= 1e-6 * np.linalg.norm(pso[j][:V // 2])
+    # block solve (a loop on partitioned contexts) and the resident UML sequence, both parities
+    srcs = [F.make_source(dims, seed=91 + k, parity=EVENANDODD) for k in range(2)]
+    dsts = [np.zeros_like(s) for s in srcs]
+    tot, rr = ctx.mat_invert_uml(srcs, dsts, 0.05, 500, 5, 1e-9)
+    for k in range(2):
+        # M dst = src with M = D + 2m
+        chk = oracle.dslash(dims, fat, lng, dsts[k], EVENANDODD) + 2 * 0.05 * dsts[k]
+        assert np.linalg.norm(chk - srcs[k]) <= 1e-7 * np.linalg.norm(srcs[k])
+    # in-place link edit between two calls, seen by the leader's background verification
+    fat2, lng2 = fat.copy(), lng.copy()
+    assert ctx.links_sync(fat2, lng2) == 1
+    twist_time_slices(fat2, lng2, dims)
+    assert ctx.links_sync(fat2, lng2) == 0
+    x = np.zeros_like(b)
+    it, res = ctx.congrad(b, x, 0.05, EVEN, 500, 5, 1e-9)
+    xo = np.zeros_like(b)
+    ito, qo = oracle.congrad(dims, fat2, lng2, b, xo, 0.05, EVEN, 500, 5, 1e-9)
+    assert abs(it - ito) <= max(2, 0.02 * ito) and np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
+    # device-resident interface: global norms, device-generated fields independent of the decomposition
+    v = ctx.vec_create()
+    ctx.vec_upload(v, src)
+    assert abs(ctx.vec_norm2(v) - float(np.sum(src * src))) <= 1e-12 * float(np.sum(src * src))
+    back = np.zeros_like(src)
+    ctx.vec_download(v, back)
+    assert np.array_equal(back, src)
+    ctx.links_synthetic(4242)
+    sf, sl_ = ctx.links_download()
+    one = api.Context(dims)
+    one.links_synthetic(4242)
+    of, ol = one.links_download()
+    assert np.array_equal(sf, of) and np.array_equal(sl_, ol)
+    one.close()
+    ctx.close()
+
+
+def test_multi_gpu_context_refuses_what_it_cannot_split():
+    from milc_qcd_b200 import api, _lib
+    with pytest.raises(_lib.B200KSError):
+        api.Context((8, 8, 6, 6), ngpu=2, devices=_devices(2))      # local extent 3 is odd
+    with pytest.raises(_lib.B200KSError):
+        api.Context((8, 8, 4, 4), ngpu=4, devices=_devices(4))      # local extent 2 < 4
