@@ -142,6 +142,23 @@ def make_workload(dims):
     return fat, lng, src
 
 
+class stdout_to_stderr:
+    """The reference's layout code prints to the C-level stdout; bench.py's stdout carries ONE JSON line."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def omp_all_cores():
     """The reference arm uses every host core whatever the launcher exported: torchrun sets
     OMP_NUM_THREADS=1 for its children, which made round 1's N > 1 reference lines single-threaded.
@@ -169,13 +186,14 @@ def cpu_reference_sample(dims, fat, lng, src, iters, repeats=1):
     times = []
     if pyoracle.ref_available("_omp"):
         kind = "reference"
-        ref = pyoracle.MilcRef(dims, "_omp")
-        ref.set_links(fat, lng)
-        for _ in range(repeats):
-            x = np.zeros_like(src)
-            t0 = time.perf_counter()
-            it, q = ref.congrad(src, x, MASS, EVEN, iters, 1, RESID)
-            times.append((time.perf_counter() - t0, it))
+        with stdout_to_stderr():
+            ref = pyoracle.MilcRef(dims, "_omp")
+            ref.set_links(fat, lng)
+            for _ in range(repeats):
+                x = np.zeros_like(src)
+                t0 = time.perf_counter()
+                it, q = ref.congrad(src, x, MASS, EVEN, iters, 1, RESID)
+                times.append((time.perf_counter() - t0, it))
         impl = "MILC d_congrad5_fn_milc.c + dslash_fn_dblstore.c (oracle/_ref, -O3 -DFAST -DOMP)"
     else:
         kind = "port"

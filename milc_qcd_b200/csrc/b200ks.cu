@@ -3365,6 +3365,19 @@ extern "C" b200ks_ctx *b200ks_create_multi(const int latsize[4], int ngpu, const
     }
     ms->devices.push_back(dev);
   }
+  // members may share a device (CI on fewer GPUs), at most four of them: each owns two streams, a device has 8
+  // hardware work queues by default, streams that alias a queue serialise, and a kernel that waits for a peer's
+  // kernel queued behind it would never end
+  for (int r = 0; r < ngpu; r++) {
+    int same = 0;
+    for (int q = 0; q < ngpu; q++) same += ms->devices[q] == ms->devices[r];
+    if (same > 4) {
+      fail(B200KS_EINVAL, "b200ks_create_multi: at most 4 members of a multi-GPU context may share one device");
+      delete ms;
+      delete L;
+      return nullptr;
+    }
+  }
   L->device = ms->devices[0];
   ms->rc.assign(ngpu, 0);
   ms->err.assign(ngpu, std::string());

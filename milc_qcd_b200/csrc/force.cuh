@@ -104,29 +104,49 @@ B200KS_HD Mat zero() {
   return m;
 }
 
-// site f = parity*Vh + cb, cb = lex/2 -> neighbour at +-1 in direction mu (periodic)
-B200KS_HD int nbr(const FGeom &g, int f, int mu, int sign) {
-  const int par = f >= g.Vh ? 1 : 0;
-  const int cb = f - par * g.Vh;
+// site f = parity*Vh + cb, cb = lex/2.  A site's coordinates cost three integer divisions by run-time
+// extents (~100 instructions); the first version paid them again for every one of the 6-10 neighbours of
+// a staple pass -- more instructions than the six 3x3 complex products the pass is about.  They are
+// computed ONCE per site (fsite) and a hop only moves one coordinate (fhop: adds and selects, no indexed
+// array, which would live in local memory).
+struct FSite {
+  int par, lex, c0, c1, c2, c3;
+};
+B200KS_HD FSite fsite(const FGeom &g, int f) {
+  FSite s;
+  s.par = f >= g.Vh ? 1 : 0;
+  const int cb = f - s.par * g.Vh;
   const int Lxh = g.L[0] / 2;
   int r = cb;
   const int xh = r % Lxh;
   r /= Lxh;
-  const int c1 = r % g.L[1];
+  s.c1 = r % g.L[1];
   r /= g.L[1];
-  const int c2 = r % g.L[2], c3 = r / g.L[2];
-  const int c0 = 2 * xh + ((c1 + c2 + c3 + par) & 1);
-  const int lex = c0 + g.L[0] * (c1 + g.L[1] * (c2 + g.L[2] * c3));
-  // only coordinate mu changes: lex moves by (new - old) * stride_mu; selects instead of an indexed array, which
-  // would live in local memory
-  const int cm = mu == 0 ? c0 : mu == 1 ? c1 : mu == 2 ? c2 : c3;
+  s.c2 = r % g.L[2];
+  s.c3 = r / g.L[2];
+  s.c0 = 2 * xh + ((s.c1 + s.c2 + s.c3 + s.par) & 1);
+  s.lex = s.c0 + g.L[0] * (s.c1 + g.L[1] * (s.c2 + g.L[2] * s.c3));
+  return s;
+}
+// the site at +-1 in direction mu (periodic)
+B200KS_HD FSite fhop(const FGeom &g, const FSite &s, int mu, int sign) {
+  const int cm = mu == 0 ? s.c0 : mu == 1 ? s.c1 : mu == 2 ? s.c2 : s.c3;
   const int Lm = mu == 0 ? g.L[0] : mu == 1 ? g.L[1] : mu == 2 ? g.L[2] : g.L[3];
   const int sm = mu == 0 ? 1 : mu == 1 ? g.L[0] : mu == 2 ? g.L[0] * g.L[1] : g.L[0] * g.L[1] * g.L[2];
   int cn = cm + sign;
   if (cn >= Lm) cn -= Lm;
   if (cn < 0) cn += Lm;
-  return (par ^ 1) * g.Vh + ((lex + (cn - cm) * sm) >> 1);
+  FSite t = s;
+  t.par = s.par ^ 1;
+  t.lex = s.lex + (cn - cm) * sm;
+  t.c0 = mu == 0 ? cn : s.c0;
+  t.c1 = mu == 1 ? cn : s.c1;
+  t.c2 = mu == 2 ? cn : s.c2;
+  t.c3 = mu == 3 ? cn : s.c3;
+  return t;
 }
+B200KS_HD int findex(const FGeom &g, const FSite &s) { return s.par * g.Vh + (s.lex >> 1); }
+B200KS_HD int nbr(const FGeom &g, int f, int mu, int sign) { return findex(g, fhop(g, fsite(g, f), mu, sign)); }
 
 // ---- site functors (operator()(f) for every site f) ------------------------------------------------
 // 1. outer products of one term: z = colour vectors in MILC host order, 6 reals per site
@@ -138,8 +158,10 @@ struct OprodSite {
   double c1, c3;
   B200KS_HD void operator()(int f) const {
     const double sgn = f >= g.Vh ? 1.0 : -1.0;
+    const FSite s0 = fsite(g, f);
     for (int mu = 0; mu < 4; mu++) {
-      const int f1 = nbr(g, f, mu, 1), f3 = nbr(g, nbr(g, f1, mu, 1), mu, 1);
+      const FSite s1 = fhop(g, s0, mu, 1);
+      const int f1 = findex(g, s1), f3 = findex(g, fhop(g, fhop(g, s1, mu, 1), mu, 1));
       Mat o1, o3;
       for (int a = 0; a < 3; a++)
         for (int b = 0; b < 3; b++) {
@@ -166,12 +188,14 @@ struct StapleFwdSite {
   int part = 3;
   B200KS_HD void operator()(int f) const {
     Mat r = zero();
+    const FSite s0 = fsite(g, f);
     if (part & 1) {
-      const int fpn = nbr(g, f, nu, 1), fpm = nbr(g, f, mu, 1);
+      const int fpn = findex(g, fhop(g, s0, nu, 1)), fpm = findex(g, fhop(g, s0, mu, 1));
       r = nn(ld(Unu, fs, f), na(ld(link, fs, fpn), ld(Unu, fs, fpm)));
     }
     if (part & 2) {
-      const int fmn = nbr(g, f, nu, -1), fmnpm = nbr(g, fmn, mu, 1);
+      const FSite smn = fhop(g, s0, nu, -1);
+      const int fmn = findex(g, smn), fmnpm = findex(g, fhop(g, smn, mu, 1));
       add(r, nn(an(ld(Unu, fs, fmn), ld(link, fs, fmn)), ld(Unu, fs, fmnpm)));
     }
     st(out, fs, f, r);
@@ -190,8 +214,9 @@ struct StapleBwdSite {
   int mu, nu;
   int part = 3;
   B200KS_HD void operator()(int z) const {
-    const int zpn = nbr(g, z, nu, 1), zmn = nbr(g, z, nu, -1), zpm = nbr(g, z, mu, 1), zmm = nbr(g, z, mu, -1);
-    const int zmnpm = nbr(g, zmn, mu, 1), zmmpn = nbr(g, zmm, nu, 1);
+    const FSite s0 = fsite(g, z), smn = fhop(g, s0, nu, -1), smm = fhop(g, s0, mu, -1);
+    const int zpn = findex(g, fhop(g, s0, nu, 1)), zmn = findex(g, smn), zpm = findex(g, fhop(g, s0, mu, 1)), zmm = findex(g, smm);
+    const int zmnpm = findex(g, fhop(g, smn, mu, 1)), zmmpn = findex(g, fhop(g, smm, nu, 1));
     const Mat Uzpm = ld(Unu, fs, zpm), Uzmm = ld(Unu, fs, zmm);
     Mat gl = zero(), gu = zero();
     if (part & 1) {   // upper staple A B C^+ at x: G_B(x+nu), G_A(x), G_C(x+mu)
@@ -226,10 +251,12 @@ struct StapleBwdLinkSite {
   int mu, nu;
   B200KS_HD void operator()(int z) const {
     if (kPart == 1) {
-      const int zmn = nbr(g, z, nu, -1), zmnpm = nbr(g, zmn, mu, 1);
+      const FSite smn = fhop(g, fsite(g, z), nu, -1);
+      const int zmn = findex(g, smn), zmnpm = findex(g, fhop(g, smn, mu, 1));
       acc(glink, fs, z, hs, nn(an(ld(Unu, fs, zmn), ld(H, fs, zmn)), ld(Unu, fs, zmnpm)));
     } else {
-      const int zpn = nbr(g, z, nu, 1), zpm = nbr(g, z, mu, 1);
+      const FSite s0 = fsite(g, z);
+      const int zpn = findex(g, fhop(g, s0, nu, 1)), zpm = findex(g, fhop(g, s0, mu, 1));
       acc(glink, fs, z, hs, na(nn(ld(Unu, fs, z), ld(H, fs, zpn)), ld(Unu, fs, zpm)));
     }
   }
@@ -245,7 +272,8 @@ struct StapleBwdUSite {
   size_t fs;
   int mu, nu;
   B200KS_HD void operator()(int z) const {
-    const int zpn = nbr(g, z, nu, 1), zpm = nbr(g, z, mu, 1), zmm = nbr(g, z, mu, -1), zmmpn = nbr(g, zmm, nu, 1);
+    const FSite s0 = fsite(g, z), smm = fhop(g, s0, mu, -1);
+    const int zpn = findex(g, fhop(g, s0, nu, 1)), zpm = findex(g, fhop(g, s0, mu, 1)), zmm = findex(g, smm), zmmpn = findex(g, fhop(g, smm, nu, 1));
     Mat gu;
     if (kPart == 1) {
       gu = nn(ld(H, fs, z), na(ld(Unu, fs, zpm), ld(link, fs, zpn)));
@@ -292,9 +320,11 @@ struct NaikBwdSite {
   double s;
   size_t fs;
   B200KS_HD void operator()(int z) const {
+    const FSite s0 = fsite(g, z);
     for (int mu = 0; mu < 4; mu++) {
       const double2 *Wm = W + (size_t)mu * 9 * fs, *Gm = glng + (size_t)mu * 9 * fs;
-      const int p1 = nbr(g, z, mu, 1), p2 = nbr(g, p1, mu, 1), m1 = nbr(g, z, mu, -1), m2 = nbr(g, m1, mu, -1);
+      const FSite sp1 = fhop(g, s0, mu, 1), sm1 = fhop(g, s0, mu, -1);
+      const int p1 = findex(g, sp1), p2 = findex(g, fhop(g, sp1, mu, 1)), m1 = findex(g, sm1), m2 = findex(g, fhop(g, sm1, mu, -1));
       const Mat W1 = ld(Wm, fs, p1), Wm1 = ld(Wm, fs, m1);
       Mat r = na(ld(Gm, fs, z), nn(W1, ld(Wm, fs, p2)));
       add(r, na(an(Wm1, ld(Gm, fs, m1)), W1));

@@ -46,6 +46,8 @@ void ensure_ctx(const char *where) {
   if (!S.ctx) {
     S.ctx = b200ks_create(S.latsize, S.device);
     if (!S.ctx) die(where);
+    if (b200ks_num_gpus(S.ctx) > 1 && S.verbosity >= QUDA_SUMMARIZE)
+      printf("libb200ks: lattice spread over %d GPUs behind the seam (B200KS_NGPU), first device %d\n", b200ks_num_gpus(S.ctx), S.device);
   }
 }
 

@@ -1,0 +1,13 @@
+#!/bin/bash
+# builds profiles/variants/libb200ks_<name>.so (see profiles/variants/README)
+set -e
+cd "$(dirname "$0")/.."
+FLAGS="--threads 3 -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --shared -Xcompiler -fPIC -Xcompiler -fvisibility=default -I include"
+SRC=$(ls milc_qcd_b200/csrc/*.cu)
+build() { nvcc $FLAGS $2 -o profiles/variants/libb200ks_$1.so $SRC; echo built $1; }
+build mb5 -DB200KS_HALF_MINBLOCKS=5 &
+build mb7 -DB200KS_HALF_MINBLOCKS=7 &
+wait
+build probe_nomath -DB200KS_PROBE_NOMATH &
+build probe_nolinkload -DB200KS_PROBE_NOLINKLOAD &
+wait

@@ -31,7 +31,7 @@ def _have(app):
     return os.path.exists(os.path.join(APPS, app)) and os.path.isdir(SAMPLES)
 
 
-def _run(app, testdir, stem, tmp_path, timeout=900):
+def _run(app, testdir, stem, tmp_path, timeout=900, env=None):
     """Run an application on <stem>.sample-in inside a scratch copy of the staged test dir."""
     work = tmp_path / "work" / testdir / "test"
     shutil.copytree(os.path.join(SAMPLES, testdir, "test"), work)
@@ -42,8 +42,10 @@ def _run(app, testdir, stem, tmp_path, timeout=900):
     if not bs.exists():
         os.symlink(os.path.join(SAMPLES, "binary_samples"), bs)
     with open(work / (stem + ".sample-in")) as fin:
+        e = dict(os.environ)
+        e.update(env or {})
         p = subprocess.run([os.path.join(APPS, app)], stdin=fin, capture_output=True, text=True, cwd=work,
-                           timeout=timeout)
+                           timeout=timeout, env=e)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     return work, p.stdout.splitlines()
 
@@ -53,9 +55,9 @@ def _read(path):
         return f.read().splitlines()
 
 
-def check_spectrum(app, case, tmp_path, stdout_strict):
+def check_spectrum(app, case, tmp_path, stdout_strict, env=None):
     stem = "ks_spectrum_hisq.%s.2" % case
-    work, out = _run(app, "ks_spectrum", stem, tmp_path)
+    work, out = _run(app, "ks_spectrum", stem, tmp_path, env=env)
     # extra-output: the correlator file, all lines  (checklist: `extra-output ... --- EOF`)
     got = R.filter_test_lines(_read(work / (stem + ".corrfile_t0.test-out")))
     want = _read(work / (stem + ".corrfile_t0.sample-out"))
@@ -121,6 +123,21 @@ def test_ks_spectrum_hisq_on_libb200ks_matches_reference_goldens(case, tmp_path)
         pytest.skip("oracle/_ref/apps not built")
     out = check_spectrum("ks_spectrum_hisq_b200", case, tmp_path, stdout_strict=False)
     assert any("fn_QUDA" in ln or "multicg_offset_QUDA" in ln for ln in out), "solves did not go through the GPU seam"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ngpu,case", [(2, "nd"), (4, "nd"), (2, "spectrum2"), (4, "fpi")])
+def test_ks_spectrum_hisq_on_several_gpus_behind_the_seam_matches_reference_goldens(ngpu, case, tmp_path):
+    """The UNMODIFIED application, still one vanilla MILC rank, with B200KS_NGPU devices behind qudaInvert /
+    qudaMultishiftInvert / qudaDslash (b200ks_create_multi): 8^4 split 2 ways in t, or 2 x 2 in z and t (local extent
+    4, no interior sites at all).  On a box with fewer GPUs the members share devices (B200KS_NGPU_OVERSUBSCRIBE: the
+    whole multi-GPU host path still runs).  (The 6^4 RHMC sample cannot be split: its local extents would be odd.)"""
+    if not _have("ks_spectrum_hisq_b200"):
+        pytest.skip("oracle/_ref/apps not built")
+    env = {"B200KS_NGPU": str(ngpu), "B200KS_NGPU_OVERSUBSCRIBE": "1"}
+    out = check_spectrum("ks_spectrum_hisq_b200", case, tmp_path, stdout_strict=False, env=env)
+    assert any("fn_QUDA" in ln or "multicg_offset_QUDA" in ln for ln in out), "solves did not go through the GPU seam"
+    assert any("lattice spread over %d GPUs" % ngpu in ln for ln in out), "the multi-GPU context was not used"
 
 
 @pytest.mark.gpu

@@ -148,8 +148,12 @@ def test_congrad_matches_oracle(api, oracle, dims, parity):
     assert abs(it - it_ref) <= max(2, 0.02 * it_ref)          # iterations within 2%
     assert qic.final_iters == it
     assert qic.final_rsq < resid ** 2
-    # solution agrees to within 10x the requested residual (relative to |x|)
-    assert np.linalg.norm(x - x_ref) <= 10 * resid * np.linalg.norm(x_ref) * _cond(mass)
+    # north_star: "the converged solution agrees to within 10x the requested residual" -- taken literally,
+    # relative to |x| (no condition-number allowance: the pure-double solver follows the reference's
+    # arithmetic iteration by iteration)
+    err = np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref)
+    print("pure double: |x - x_ref| / |x_ref| = %.2e (bound %.0e), iterations %d vs %d" % (err, 10 * resid, it, it_ref))
+    assert err <= 10 * resid
     # independent true-residual check with the oracle's operator
     V = src.shape[0]
     sl = slice(0, V // 2) if parity == EVEN else slice(V // 2, V)
@@ -186,7 +190,11 @@ def test_mixed_precision_congrad_reaches_double_residual(api, oracle, dims, pari
     t = oracle.dslash(dims, fat, lng, t, parity)
     r = src[sl] - (4 * mass * mass * x[sl] - t[sl])
     assert np.linalg.norm(r) / np.linalg.norm(src[sl]) <= 10 * resid
-    assert np.linalg.norm(x - x_ref) <= 10 * resid * np.linalg.norm(x_ref) * _cond(mass)
+    # two different Krylov trajectories that both meet |r|/|b| < resid differ by up to 2 resid |A^-1| |b|:
+    # the bound on the solutions carries the conditioning 1/(4 m^2); the achieved figure is printed
+    err = np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref)
+    print("mixed: |x - x_ref| / |x_ref| = %.2e (bound %.0e)" % (err, 10 * resid * _cond(mass)))
+    assert err <= 10 * resid * _cond(mass)
 
 
 def _cond(mass):

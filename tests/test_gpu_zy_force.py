@@ -64,8 +64,6 @@ def test_force_matches_oracle(api, oracle, dims, spread):
     ctx.close()
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; first GPU run at round end "
-                                        "(host-checked arithmetic: tests/test_force_host.py, tests/test_deflate_host.py)")
 def test_force_filter_matches_reference_on_rough_links(api):
     """tests/golden/ref_hisq_force_rough.npz: 11 links on the reference's eigenvalue-filter / SVD branches
     (HISQ_FORCE_FILTER = 5e-5).  The reference's own eigenvalues come from the closed-form cubic, hence 1e-8."""
@@ -87,8 +85,6 @@ def test_force_filter_matches_reference_on_rough_links(api):
     ctx.close()
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; first GPU run at round end "
-                                        "(host-checked arithmetic: tests/test_force_host.py, tests/test_deflate_host.py)")
 def test_force_with_naik_epsilons_matches_reference_golden(api):
     """Several Naik epsilons (qudaHisqForce num_naik_terms > 0): five terms in three classes,
     tests/golden/ref_hisq_force_naik.npz from the reference's eo_fermion_force_multi with n_naiks = 3."""

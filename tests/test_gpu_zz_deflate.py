@@ -43,8 +43,6 @@ def _upload_modes(ctx, ev, k):
     return hs
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; first GPU run at round end "
-                                        "(host-checked arithmetic: tests/test_force_host.py, tests/test_deflate_host.py)")
 def test_deflate_matches_oracle(api, oracle, case):
     g, dims, fat, lng, lam, ev, src = case
     ctx = api.Context(dims)
@@ -70,8 +68,6 @@ def test_deflate_matches_oracle(api, oracle, case):
     ctx.close()
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; first GPU run at round end "
-                                        "(host-checked arithmetic: tests/test_force_host.py, tests/test_deflate_host.py)")
 def test_deflated_uml_matches_reference_golden(api, oracle, case):
     """Iteration counts (the CG trajectory depends on the trial solution) and solutions of the reference's
     deflated mat_invert_uml_field for 8, 48 and all 384 low modes; with all of them both CGs stop at their
