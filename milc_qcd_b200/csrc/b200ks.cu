@@ -390,6 +390,7 @@ static int d2h_rows(b200ks_ctx *c, void *dst, const void *src, const HostRows &h
   const size_t bytes = hr.total();
   const bool one = hr.nrows == 1 || hr.row_bytes == hr.pitch_bytes;
   if (bytes < (kBounceBytes >> 2) || host_is_pinned(dst) || bounce_get(c) < 0) {
+    CU(cudaStreamSynchronize(c->stream));   // (a copy into pageable memory blocks inside the driver: see read_back)
     if (one) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     else CU(cudaMemcpy2DAsync(dst, hr.pitch_bytes, src, hr.row_bytes, hr.row_bytes, hr.nrows, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -813,6 +814,25 @@ static int links_alloc(b200ks_ctx *c, int prec, int nc) {
 
 // sum (max) of n <= 8 device doubles over the ranks, in place, on the compute stream: flag-based
 // exchange over the peer mappings (blas.cuh), NCCL when the halos go through NCCL too
+// Small device -> host reads go through the pinned scratch (h_scal[32..63]) and an explicit stream
+// synchronisation.  A copy into PAGEABLE memory blocks inside the driver until the stream has drained; when the
+// stream holds a kernel that waits for a peer's kernel (flag-based all-reduce, halo flags) and the peer is another
+// host thread of this process, that thread may need the same driver lock to launch it.
+static int read_back(b200ks_ctx *c, void *host, const void *dev, size_t bytes) {
+  if (bytes > 32 * sizeof(double)) return fail(B200KS_EINVAL, "read_back: too large");
+  CU(cudaMemcpyAsync(c->h_scal + 32, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  memcpy(host, c->h_scal + 32, bytes);
+  return 0;
+}
+static int write_small(b200ks_ctx *c, void *dev, const void *host, size_t bytes) {
+  if (bytes > 16 * sizeof(double)) return fail(B200KS_EINVAL, "write_small: too large");
+  CU(cudaStreamSynchronize(c->stream));   // (the pinned scratch may still be the source of an earlier copy)
+  memcpy(c->h_scal + 16, host, bytes);
+  CU(cudaMemcpyAsync(dev, c->h_scal + 16, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
 static int allreduce(b200ks_ctx *c, double *dptr, int n, bool take_max = false, const int *stop = nullptr) {
   if (c->comm.nranks == 1) return 0;
   if (c->comm.p2p.on) {
@@ -913,17 +933,15 @@ static int compress_long(b200ks_ctx *c, int prec, int long_recon) {
     else LAUNCH(c, (long_deviation_kernel<float>), nblocks(g.lstride), (const float2 *)L.lng[p], g.lstride, g.lstride, c->d_dev);
   }
   unsigned long long bits = 0;
-  CU(cudaMemcpyAsync(&bits, c->d_dev, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CHK(read_back(c, &bits, c->d_dev, sizeof(bits)));
   CHK(check_launch("long_deviation_kernel"));
   double dev;
   memcpy(&dev, &bits, sizeof(dev));
   if (c->comm.nranks > 1) {  // every rank must take the same decision
     double *d = c->d_scal;
-    CU(cudaMemcpyAsync(d, &dev, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CHK(write_small(c, d, &dev, sizeof(double)));
     CHK(allreduce(c, d, 1, true));
-    CU(cudaMemcpyAsync(&dev, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CHK(read_back(c, &dev, d, sizeof(double)));
   }
   c->long_dev = dev;
   const double tol = prec == 2 ? 1e-13 : 5e-6;
@@ -1100,8 +1118,7 @@ static int links_quantize_T(b200ks_ctx *c, int m) {
     LAUNCH(c, (half_absmax_kernel<T, kNc>), nblocks(g.lstride), (const T2 *)c->links[m].fat[p], (const T2 *)c->links[m].lng[p],
            g.lstride, g.lstride, d_max);
   unsigned bits[3];
-  CU(cudaMemcpyAsync(bits, d_max, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CHK(read_back(c, bits, d_max, sizeof(bits)));
   dev_free(c, d_max, 3 * sizeof(unsigned));
   double mx[3];
   for (int k = 0; k < 3; k++) {
@@ -1110,10 +1127,9 @@ static int links_quantize_T(b200ks_ctx *c, int m) {
     mx[k] = f;
   }
   if (c->comm.nranks > 1) {
-    CU(cudaMemcpyAsync(c->d_scal, mx, sizeof(mx), cudaMemcpyHostToDevice, c->stream));
+    CHK(write_small(c, c->d_scal, mx, sizeof(mx)));
     CHK(allreduce(c, c->d_scal, 3, true));
-    CU(cudaMemcpyAsync(mx, c->d_scal, sizeof(mx), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CHK(read_back(c, mx, c->d_scal, sizeof(mx)));
   }
   float inv[3];
   for (int k = 0; k < 3; k++) {
@@ -1394,8 +1410,7 @@ static int dslash_any(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out,
 static int halo_check(b200ks_ctx *c) {
   if (!c->comm.p2p.on) return 0;
   int e = 0;
-  CU(cudaMemcpyAsync(&e, c->comm.p2p.err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CHK(read_back(c, &e, c->comm.p2p.err, sizeof(int)));
   if (e) return fail(B200KS_ECOMM, "halo exchange timed out waiting for face " + std::to_string(e - 1) + " (a neighbour rank stopped?)");
   return 0;
 }
@@ -2876,7 +2891,7 @@ static int deflate_dv(b200ks_ctx *c, DevVec &dst, const DevVec &src, double mass
   const int n = c->g.Vh, per = (n + e.nchunks - 1) / e.nchunks;
   eig_dot_kernel<<<e.nchunks, kBlock, 0, c->stream>>>(e.d_ptr[pbit], e.n, (const double2 *)src.p[pbit], (const double2 *)dst.p[pbit],
                                                       c->g.stride, n, per, e.d_part);
-  eig_coef_kernel<<<(e.n + 127) / 128, 128, 0, c->stream>>>(e.d_part, e.nchunks, e.d_val, 4.0 * mass * mass, e.n, e.d_coef);
+  eig_coef_kernel<<<(e.n + 3) / 4, 128, 0, c->stream>>>(e.d_part, e.nchunks, e.d_val, 4.0 * mass * mass, e.n, e.d_coef);
   eig_axpy_kernel<<<nblocks(n), kBlock, 0, c->stream>>>(e.d_ptr[pbit], e.d_coef, e.n, (double2 *)dst.p[pbit], c->g.stride, n);
   c->launches += 3;
   return check_launch("deflation");

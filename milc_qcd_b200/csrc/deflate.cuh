@@ -60,28 +60,50 @@ __host__ __device__ inline void eig_axpy_site(const double2 *const *vecs, const 
 }
 
 #ifdef __CUDACC__
-// CTA b covers the sites [b*per, min(n, (b+1)*per)) for every vector
+// CTA b covers the sites [b*per, min(n, (b+1)*per)) for every vector.  kG vectors per pass: the loads of kG
+// vectors are in flight together and src/dst are read once per pass (one vector at a time ran at 2.4 TB/s:
+// seven sites per thread and a barrier per vector left the memory system idle most of the time).
+constexpr int kEigGroup = 4;
 __global__ void __launch_bounds__(kBlock)
 eig_dot_kernel(const double2 *const *vecs, int nvecs, const double2 *src, const double2 *dst, int stride, int n, int per,
                double *partials) {
   const int lo = blockIdx.x * per, hi = min(n, lo + per);
-  for (int j = 0; j < nvecs; j++) {
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    const double2 *v = vecs[j];
-    for (int f = lo + threadIdx.x; f < hi; f += kBlock) eig_dot_site(v, src, dst, (size_t)stride, f, acc);
-    block_partials<4>(acc, partials + (size_t)j * gridDim.x * 4);
-    __syncthreads();   // block_partials' shared scratch is reused by the next vector
+  for (int j0 = 0; j0 < nvecs; j0 += kEigGroup) {
+    double acc[kEigGroup][4];
+    const double2 *v[kEigGroup];
+#pragma unroll
+    for (int g = 0; g < kEigGroup; g++) {
+      v[g] = vecs[min(j0 + g, nvecs - 1)];
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[g][k] = 0.0;
+    }
+    for (int f = lo + threadIdx.x; f < hi; f += kBlock) {
+#pragma unroll
+      for (int g = 0; g < kEigGroup; g++) eig_dot_site(v[g], src, dst, (size_t)stride, f, acc[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < kEigGroup; g++) {
+      if (j0 + g < nvecs) block_partials<4>(acc[g], partials + (size_t)(j0 + g) * gridDim.x * 4);
+      __syncthreads();   // block_partials' shared scratch is reused by the next vector
+    }
   }
 }
 
-__global__ void eig_coef_kernel(const double *partials, int nchunks, const double *eigval, double four_m2, int nvecs,
-                                double2 *coef) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per vector adds its chunks (lane l: chunks l, l+32, ...; then the warp tree: a fixed order) and forms
+// c_j = <v_j|src>/(lambda_j + 4 m^2) - <v_j|dst>
+__global__ void __launch_bounds__(128)
+eig_coef_kernel(const double *partials, int nchunks, const double *eigval, double four_m2, int nvecs, double2 *coef) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (j >= nvecs) return;
   double s[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int b = 0; b < nchunks; b++)
+  for (int b = lane; b < nchunks; b += 32)
+#pragma unroll
     for (int k = 0; k < 4; k++) s[k] += partials[((size_t)j * nchunks + b) * 4 + k];
-  coef[j] = eig_coef(s, eigval[j] + four_m2);
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+  if (lane == 0) coef[j] = eig_coef(s, eigval[j] + four_m2);
 }
 
 __global__ void __launch_bounds__(kBlock)

@@ -126,17 +126,18 @@ __device__ __forceinline__ void adj_mat_vec_sub(const T2 (&U)[9], const T2 (&v)[
   for (int k = 0; k < 6; k++) acc[k] -= t[k];
 }
 
-template <typename T, int D, int kMode, int kNc>
-__device__ __forceinline__ void hop_dir(const DslashArg<T> &a, int idx, const Coord &c, bool bnd, T (&acc)[6]) {
+// kPart: the site may have neighbours in the ghost zones (boundary site of a partitioned lattice)
+template <typename T, int D, bool kPart, int kNc>
+__device__ __forceinline__ void hop_dir(const DslashArg<T> &a, int idx, const Coord &c, T (&acc)[6]) {
   using T2 = typename Vec2<T>::type;
   const Geom &g = a.g;
   T2 U[9], v[3];
-  const bool part = (kMode == 1) && (D >= 2) && bnd && g.part[D];
+  const bool part = kPart && (D >= 2) && g.part[D];
 #pragma unroll
   for (int hop = 0; hop < 4; hop++) {
     const int h = (hop == 0) ? 1 : (hop == 1) ? 3 : (hop == 2) ? -1 : -3;
     const bool lng = (hop & 1);
-    const int n = neighbor<D, false, kMode != 0>(g, idx, c, h);
+    const int n = neighbor<D, false, kPart>(g, idx, c, h);
     if (hop < 2) {
       if (lng) load_long<T, T2, kNc>(a.lng_this, g.lstride, D, idx, U);
       else load_link<T, T2>(a.fat_this, g.lstride, D, idx, U);
@@ -182,6 +183,47 @@ __device__ __forceinline__ void acquire_halo(const unsigned long long *flags, un
   }
 }
 
+// one output site: the 16 hops and the epilogue
+template <typename T, int kEpi, bool kPart, int kNc>
+__device__ __forceinline__ void dslash_site(const DslashArg<T> &a, int idx, double (&red)[3]) {
+  using T2 = typename Vec2<T>::type;
+  const Coord c = site_coord(a.g, idx, a.par);
+  T acc[6] = {0, 0, 0, 0, 0, 0};
+  hop_dir<T, 0, kPart, kNc>(a, idx, c, acc);
+  hop_dir<T, 1, kPart, kNc>(a, idx, c, acc);
+  hop_dir<T, 2, kPart, kNc>(a, idx, c, acc);
+  hop_dir<T, 3, kPart, kNc>(a, idx, c, acc);
+  if (kEpi >= 1) {
+    // per-site sums in the working precision (MILC's su3_rdot / magsq_su3vec return Real),
+    // accumulated over sites in double (d_congrad5_fn_milc.c:210,293)
+    T s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const T2 wv = a.w[(size_t)q * a.g.stride + idx];
+      acc[2 * q] = fma(a.s, wv.x, acc[2 * q]);
+      acc[2 * q + 1] = fma(a.s, wv.y, acc[2 * q + 1]);
+      if (kEpi == 2) {
+        s0 = fma(wv.x, acc[2 * q], fma(wv.y, acc[2 * q + 1], s0));
+        s2 = fma(acc[2 * q], acc[2 * q], fma(acc[2 * q + 1], acc[2 * q + 1], s2));
+        if (a.r != nullptr) {
+          const T2 rv = a.r[(size_t)q * a.g.stride + idx];
+          s1 = fma(rv.x, acc[2 * q], fma(rv.y, acc[2 * q + 1], s1));
+        }
+      }
+    }
+    red[0] = s0;
+    red[1] = s1;
+    red[2] = s2;
+  }
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    T2 o;
+    o.x = acc[2 * q];
+    o.y = acc[2 * q + 1];
+    a.out[(size_t)q * a.g.stride + idx] = o;
+  }
+}
+
 // (register caps keep 5 CTAs per SM in double and 8 in float whatever epilogue is compiled in)
 template <typename T, int kEpi, int kMode, int kNc>
 __global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? 5 : 8) dslash_kernel(const DslashArg<T> a) {
@@ -208,41 +250,9 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? 5 : 8) dslash_kernel(
   double red[3] = {0, 0, 0};
   if (active) {
     const int idx = (kMode == 0) ? k : bnd ? a.sites[k] : interior_site(a.g, k);
-    const Coord c = site_coord(a.g, idx, a.par);
-    T acc[6] = {0, 0, 0, 0, 0, 0};
-    hop_dir<T, 0, kMode, kNc>(a, idx, c, bnd, acc);
-    hop_dir<T, 1, kMode, kNc>(a, idx, c, bnd, acc);
-    hop_dir<T, 2, kMode, kNc>(a, idx, c, bnd, acc);
-    hop_dir<T, 3, kMode, kNc>(a, idx, c, bnd, acc);
-    if (kEpi >= 1) {
-      // per-site sums in the working precision (MILC's su3_rdot / magsq_su3vec return Real),
-      // accumulated over sites in double (d_congrad5_fn_milc.c:210,293)
-      T s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-      for (int q = 0; q < 3; q++) {
-        const T2 wv = a.w[(size_t)q * a.g.stride + idx];
-        acc[2 * q] = fma(a.s, wv.x, acc[2 * q]);
-        acc[2 * q + 1] = fma(a.s, wv.y, acc[2 * q + 1]);
-        if (kEpi == 2) {
-          s0 = fma(wv.x, acc[2 * q], fma(wv.y, acc[2 * q + 1], s0));
-          s2 = fma(acc[2 * q], acc[2 * q], fma(acc[2 * q + 1], acc[2 * q + 1], s2));
-          if (a.r != nullptr) {
-            const T2 rv = a.r[(size_t)q * a.g.stride + idx];
-            s1 = fma(rv.x, acc[2 * q], fma(rv.y, acc[2 * q + 1], s1));
-          }
-        }
-      }
-      red[0] = s0;
-      red[1] = s1;
-      red[2] = s2;
-    }
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-      T2 o;
-      o.x = acc[2 * q];
-      o.y = acc[2 * q + 1];
-      a.out[(size_t)q * a.g.stride + idx] = o;
-    }
+    // interior sites of a partitioned lattice run the unpartitioned instruction stream
+    if (kMode == 1 && bnd) dslash_site<T, kEpi, true, kNc>(a, idx, red);
+    else dslash_site<T, kEpi, false, kNc>(a, idx, red);
   }
   if (kEpi == 2) {   // two-stage (reduce_finish_kernel follows) unless the NCCL-halo path asks for in-kernel sums
     if (kMode == 0 || a.red == nullptr) block_partials<3>(red, a.ws.partials);

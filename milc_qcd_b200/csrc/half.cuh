@@ -126,8 +126,10 @@ __device__ __forceinline__ uint4 ld_rec(const uint4 *p) { return __ldcs(p); }   
 // Two hops at once: hop type (kLong, kBack) in directions 2P (lane x) and 2P+1 (lane y).
 // acc += U v in both lanes; the record already holds -U(x-h)^dagger for the backward types.
 // acc[j] holds real number j (re0, im0, re1, ...) of the two lanes' partial sums.
-template <int P, bool kBack, bool kLong, int kMode, int kNc>
-__device__ __forceinline__ void hop_pair_h(const DslashHArg &a, const uint4 *rec, int idx, const Coord &c, bool bnd, float2 (&acc)[6]) {
+// kPart: the site may have neighbours in the ghost zones (a boundary site of a partitioned lattice);
+// interior sites and unpartitioned lattices take the plain periodic index arithmetic.
+template <int P, bool kBack, bool kLong, bool kPart, int kNc>
+__device__ __forceinline__ void hop_pair_h(const DslashHArg &a, const uint4 *rec, int idx, const Coord &c, float2 (&acc)[6]) {
   const Geom &g = a.g;
   constexpr int DA = 2 * P, DB = 2 * P + 1;
   constexpr int nc = kLong ? kNc : 9;
@@ -137,9 +139,9 @@ __device__ __forceinline__ void hop_pair_h(const DslashHArg &a, const uint4 *rec
   constexpr int qa = w0 / 4, qb = (w0 + 2 * nc - 1) / 4;        // 16-byte words to load
   constexpr int off = w0 - 4 * qa;
   const int h = (kLong ? 3 : 1) * (kBack ? -1 : 1);
-  const bool partA = (kMode == 1) && (DA >= 2) && bnd && g.part[DA];
-  const bool partB = (kMode == 1) && (DB >= 2) && bnd && g.part[DB];
-  const int nA = neighbor<DA, false, kMode != 0>(g, idx, c, h), nB = neighbor<DB, false, kMode != 0>(g, idx, c, h);
+  const bool partA = kPart && (DA >= 2) && g.part[DA];
+  const bool partB = kPart && (DB >= 2) && g.part[DB];
+  const int nA = neighbor<DA, false, kPart>(g, idx, c, h), nB = neighbor<DB, false, kPart>(g, idx, c, h);
   const uint4 *vA = (partA && nA >= g.Vh) ? a.gin + (nA - g.Vh) : a.in + nA;
   const uint4 *vB = (partB && nB >= g.Vh) ? a.gin + (nB - g.Vh) : a.in + nB;
   const uint4 va = __ldg(vA), vb = __ldg(vB);
@@ -232,9 +234,52 @@ __device__ __forceinline__ void hop_pair_h(const DslashHArg &a, const uint4 *rec
   for (int j = 0; j < 6; j++) acc[j] = pfma(sc, t[j], acc[j]);
 }
 
+// one output site: the 16 hops and the epilogue
+template <int kEpi, bool kPart, int kNc>
+__device__ __forceinline__ void half_site(const DslashHArg &a, int idx, double (&red)[3]) {
+  const Coord c = site_coord(a.g, idx, a.par);
+  const uint4 *rec = a.L.rec[a.par] + record_base(idx, half_record_quads(kNc));
+  const float2 zero = make_float2(0.f, 0.f);
+  float2 acc2[6] = {zero, zero, zero, zero, zero, zero};
+  hop_pair_h<0, false, false, kPart, kNc>(a, rec, idx, c, acc2);
+  hop_pair_h<1, false, false, kPart, kNc>(a, rec, idx, c, acc2);
+  hop_pair_h<0, false, true, kPart, kNc>(a, rec, idx, c, acc2);
+  hop_pair_h<1, false, true, kPart, kNc>(a, rec, idx, c, acc2);
+  hop_pair_h<0, true, false, kPart, kNc>(a, rec, idx, c, acc2);
+  hop_pair_h<1, true, false, kPart, kNc>(a, rec, idx, c, acc2);
+  hop_pair_h<0, true, true, kPart, kNc>(a, rec, idx, c, acc2);
+  hop_pair_h<1, true, true, kPart, kNc>(a, rec, idx, c, acc2);
+  float acc[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) acc[j] = acc2[j].x + acc2[j].y;
+  if (kEpi == 0) {
+    store_vec_h(a.out_h, idx, acc);
+  } else {
+    float2 w[3];
+    load_vec_h(a.w_h, idx, w);
+    // per-site sums in fp32 (what MILC's single-precision su3_rdot / magsq_su3vec return),
+    // accumulated over sites in double (d_congrad5_fn_milc.c:210,293)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      acc[2 * q] = fmaf(a.s, w[q].x, acc[2 * q]);
+      acc[2 * q + 1] = fmaf(a.s, w[q].y, acc[2 * q + 1]);
+      const float2 rv = a.r[(size_t)q * a.g.stride + idx];
+      s0 = fmaf(w[q].x, acc[2 * q], fmaf(w[q].y, acc[2 * q + 1], s0));
+      s1 = fmaf(rv.x, acc[2 * q], fmaf(rv.y, acc[2 * q + 1], s1));
+      s2 = fmaf(acc[2 * q], acc[2 * q], fmaf(acc[2 * q + 1], acc[2 * q + 1], s2));
+      a.out_f[(size_t)q * a.g.stride + idx] = make_float2(acc[2 * q], acc[2 * q + 1]);
+    }
+    red[0] = s0;
+    red[1] = s1;
+    red[2] = s2;
+  }
+}
+
 // kEpi 0: out_h = D in.   kEpi 2: out_f = D in + s*w_h, red = {<w|out>, <out|r>, |out|^2}.
 #ifndef B200KS_HALF_MINBLOCKS
-#define B200KS_HALF_MINBLOCKS 6   // CTAs per SM the register allocation is held to (80 registers)
+#define B200KS_HALF_MINBLOCKS 5   // CTAs per SM the register allocation is held to (96 registers: no spills;
+                                  // measured 0.0862 ms per launch at 32^3x64 against 0.0925 with 6 and 0.0974 with 7)
 #endif
 template <int kEpi, int kMode, int kNc>
 __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_kernel(const DslashHArg a) {
@@ -260,43 +305,10 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
   double red[3] = {0, 0, 0};
   if (active) {
     const int idx = (kMode == 0) ? k : bnd ? a.sites[k] : interior_site(a.g, k);
-    const Coord c = site_coord(a.g, idx, a.par);
-    const uint4 *rec = a.L.rec[a.par] + record_base(idx, half_record_quads(kNc));
-    const float2 zero = make_float2(0.f, 0.f);
-    float2 acc2[6] = {zero, zero, zero, zero, zero, zero};
-    hop_pair_h<0, false, false, kMode, kNc>(a, rec, idx, c, bnd, acc2);
-    hop_pair_h<1, false, false, kMode, kNc>(a, rec, idx, c, bnd, acc2);
-    hop_pair_h<0, false, true, kMode, kNc>(a, rec, idx, c, bnd, acc2);
-    hop_pair_h<1, false, true, kMode, kNc>(a, rec, idx, c, bnd, acc2);
-    hop_pair_h<0, true, false, kMode, kNc>(a, rec, idx, c, bnd, acc2);
-    hop_pair_h<1, true, false, kMode, kNc>(a, rec, idx, c, bnd, acc2);
-    hop_pair_h<0, true, true, kMode, kNc>(a, rec, idx, c, bnd, acc2);
-    hop_pair_h<1, true, true, kMode, kNc>(a, rec, idx, c, bnd, acc2);
-    float acc[6];
-#pragma unroll
-    for (int j = 0; j < 6; j++) acc[j] = acc2[j].x + acc2[j].y;
-    if (kEpi == 0) {
-      store_vec_h(a.out_h, idx, acc);
-    } else {
-      float2 w[3];
-      load_vec_h(a.w_h, idx, w);
-      // per-site sums in fp32 (what MILC's single-precision su3_rdot / magsq_su3vec return),
-      // accumulated over sites in double (d_congrad5_fn_milc.c:210,293)
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int q = 0; q < 3; q++) {
-        acc[2 * q] = fmaf(a.s, w[q].x, acc[2 * q]);
-        acc[2 * q + 1] = fmaf(a.s, w[q].y, acc[2 * q + 1]);
-        const float2 rv = a.r[(size_t)q * a.g.stride + idx];
-        s0 = fmaf(w[q].x, acc[2 * q], fmaf(w[q].y, acc[2 * q + 1], s0));
-        s1 = fmaf(rv.x, acc[2 * q], fmaf(rv.y, acc[2 * q + 1], s1));
-        s2 = fmaf(acc[2 * q], acc[2 * q], fmaf(acc[2 * q + 1], acc[2 * q + 1], s2));
-        a.out_f[(size_t)q * a.g.stride + idx] = make_float2(acc[2 * q], acc[2 * q + 1]);
-      }
-      red[0] = s0;
-      red[1] = s1;
-      red[2] = s2;
-    }
+    // interior sites of a partitioned lattice never leave the local volume: they run the same instruction stream
+    // as an unpartitioned lattice (the ghost-index arithmetic of the boundary sites cost every site ~10 %)
+    if (kMode == 1 && bnd) half_site<kEpi, true, kNc>(a, idx, red);
+    else half_site<kEpi, false, kNc>(a, idx, red);
   }
   if (kEpi == 2) {   // two-stage (reduce_finish_kernel follows) unless the NCCL-halo path asks for in-kernel sums
     if (kMode == 0 || a.red == nullptr) block_partials<3>(red, a.ws.partials);

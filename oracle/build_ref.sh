@@ -35,6 +35,16 @@ GKS="$GKS fermion_force_hisq_multi.c fermion_links_hisq_milc.c fermion_links.c f
 GEN="$GEN report_invert_status.c"
 GKS="$GKS mat_invert.c d_congrad5_fn.c"
 
+# incremental eigCG: generic_ks/inc_eigcg.c needs LAPACK/BLAS; the image has none
+# installed system-wide, but the OpenBLAS inside its Python packages exports the plain Fortran symbols
+LAPACK_LIB="${MILC_REF_LAPACK:-$(ls /opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs/libopenblas*.so 2>/dev/null | head -1)}"
+if [ -n "$LAPACK_LIB" ] && [ -f "$LAPACK_LIB" ]; then
+  echo "eigCG reference: linking $LAPACK_LIB"
+else
+  LAPACK_LIB=""
+  echo "eigCG reference: no LAPACK found, inc_eigcg.c left out (eigCG oracle unpinned)"
+fi
+
 build_variant() {  # name precision extra-flags
   local name="$1" prec="$2" extra="$3"
   local obj="$OUT/obj_$name"
@@ -52,9 +62,15 @@ build_variant() {  # name precision extra-flags
   for f in $GEN; do echo "gcc -c $AF -I$REF/generic $REF/generic/$f -o $obj/gen_${f%.c}.o"; done >> "$obj/cmds.txt"
   for f in $GKS; do echo "gcc -c $AF -I$REF/generic_ks $REF/generic_ks/$f -o $obj/gks_${f%.c}.o"; done >> "$obj/cmds.txt"
   echo "gcc -c $AF -I$REF/generic_ks $HERE/ref_harness/harness.c -o $obj/harness.o" >> "$obj/cmds.txt"
+  local lapack=""
+  if [ -n "$LAPACK_LIB" ] && [ "$prec" = "2" ]; then   # (inc_eigcg.c requires double precision)
+    echo "gcc -c $AF -I$REF/generic_ks $REF/generic_ks/inc_eigcg.c -o $obj/gks_inc_eigcg.o" >> "$obj/cmds.txt"
+    echo "gcc -c $AF -I$REF/generic_ks $HERE/ref_harness/eigcg_harness.c -o $obj/eigcg_harness.o" >> "$obj/cmds.txt"
+    lapack="$LAPACK_LIB -Wl,--disable-new-dtags -Wl,-rpath,$(dirname "$LAPACK_LIB")"   # (DT_RPATH: also for OpenBLAS's own libgfortran)
+  fi
   # a few library files are platform-specific and may not compile; they are not on the path
   xargs -P "$(nproc)" -I{} sh -c '{} 2>/dev/null || echo "skip: {}" | cut -c1-200 >&2' < "$obj/cmds.txt"
-  gcc -shared $extra -o "$OUT/libmilcref$name.so" "$obj"/*.o -lm
+  gcc -shared $extra -o "$OUT/libmilcref$name.so" "$obj"/*.o $lapack -lm
   echo "built $OUT/libmilcref$name.so"
 }
 

@@ -229,6 +229,12 @@ class MilcRef:
         L.milcref_hisq_force.argtypes = [rp, rp, rp, C.c_int, C.c_double, ro]
         L.milcref_mat_invert_uml_deflated.argtypes = [rp, ro, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, rp, _dp, _dp]
         L.milcref_hisq_force_naik.argtypes = [rp, rp, rp, C.c_int, _ip, _dp, C.c_double, ro, C.c_void_p]
+        self.has_eigcg = hasattr(L, "milcref_eigcg")   # inc_eigcg.c needs a LAPACK at build time (oracle/build_ref.sh)
+        if self.has_eigcg:
+            L.milcref_eigcg.argtypes = [rp, ro, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _dp, ro, _dp]
+            L.milcref_inc_eigcg_init.argtypes = [C.c_int, C.c_int, C.c_int]
+            L.milcref_inc_eigcg.argtypes = [rp, ro, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, _dp, C.POINTER(C.c_int)]
+            L.milcref_eigcg_pairs.argtypes = [C.c_int, _dp, ro, C.c_void_p]
         self.dims = tuple(int(d) for d in dims)
         if L.milcref_init(*self.dims) != 0:
             raise RuntimeError("MilcRef: process already initialised with another geometry")
@@ -334,6 +340,33 @@ class MilcRef:
                                              np.ascontiguousarray(eps_naik, np.float64), eps, mom,
                                              fl.ctypes.data if want_links else None)
         return (mom, n, fl) if want_links else (mom, n)
+
+    # ---- eigCG (generic_ks/inc_eigcg.c) ---------------------------------------------------------------------
+    def eigcg(self, src, dest, mass, parity, niter, nrestart, resid, m, nvecs):
+        """ks_eigCG_parity: returns (iterations, eigVal[nvecs] of -D^2, eigVec (nvecs, V, 3, 2), qic)."""
+        out, val = np.zeros(7), np.zeros(m)
+        vec = np.zeros((max(nvecs, 1), self.vol, 3, 2))
+        it = self.lib.milcref_eigcg(np.ascontiguousarray(src, self.dtype), dest, mass, parity, niter, nrestart, resid, m, nvecs,
+                                    val, vec, out)
+        return it, val[:nvecs].copy(), vec[:nvecs], _qic(out)
+
+    def inc_eigcg_init(self, m, nvecs, nvecs_max):
+        self._inc_max = nvecs_max
+        self.lib.milcref_inc_eigcg_init(m, nvecs, nvecs_max)
+
+    def inc_eigcg(self, src, dest, mass, parity, niter, nrestart, resid):
+        """ks_inc_eigCG_parity: returns (iterations, qic, eigenvectors accumulated so far)."""
+        out, n = np.zeros(7), C.c_int(0)
+        it = self.lib.milcref_inc_eigcg(np.ascontiguousarray(src, self.dtype), dest, mass, parity, niter, nrestart, resid, out,
+                                        C.byref(n))
+        return it, _qic(out), n.value
+
+    def eigcg_pairs(self, parity, ncurr):
+        """calc_eigenpairs: (eigVal[ncurr] of -D^2 ascending, eigVec (ncurr, V, 3, 2))."""
+        val = np.zeros(self._inc_max)
+        vec = np.zeros((max(ncurr, 1), self.vol, 3, 2))
+        n = self.lib.milcref_eigcg_pairs(parity, val, vec, None)
+        return val[:n].copy(), vec[:n]
 
     def time_dslash(self, src, parity, ncalls):
         src = np.ascontiguousarray(src, self.dtype)

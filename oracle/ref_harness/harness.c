@@ -45,6 +45,7 @@ static void h_third_neighbor(int x, int y, int z, int t, int *dirpt, int FB,
   }
 }
 
+fn_links_t *milcref_fn(void) { return h_fn; }   /* eigcg_harness.c */
 int milcref_precision(void) { return MILC_PRECISION; }
 int milcref_sizeof_real(void) { return (int)sizeof(Real); }
 

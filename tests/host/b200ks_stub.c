@@ -38,6 +38,7 @@ b200ks_ctx *b200ks_create(const int latsize[4], int device) {
   return (b200ks_ctx *)s_dims;
 }
 void b200ks_destroy(b200ks_ctx *c) { (void)c; logf_("destroy\n"); s_live_vecs = 0; }
+int b200ks_num_gpus(b200ks_ctx *c) { (void)c; return 1; }
 const char *b200ks_last_error(void) { return "stub error"; }
 unsigned long long b200ks_fingerprint(const void *p, size_t bytes) {
   const unsigned char *b = (const unsigned char *)p;
