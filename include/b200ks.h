@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 #define B200KS_VERSION 120 /* 110: block solve, resident sequences, link construction; 111: force filter, Naik epsilons, deflation;
-                              120: single-process multi-GPU contexts, b200ks_links_sync, flag-based reductions */
+                              120: single-process multi-GPU contexts, b200ks_links_sync, flag-based reductions, eigCG */
 
 /* parity codes, include/macros.h:68-70 */
 #define B200KS_EVEN 2
@@ -239,6 +239,33 @@ int b200ks_eig_set(b200ks_ctx *ctx, int nvecs, const int *vecs, const double *ei
 int b200ks_eig_count(b200ks_ctx *ctx);
 int b200ks_eig_use_in_uml(b200ks_ctx *ctx, int on);   /* qic->deflate of the next UML sequences */
 int b200ks_deflate_dev(b200ks_ctx *ctx, int vsrc, int vdst, double mass, int parity);
+
+/* ---- eigCG: solve and harvest low modes in the same Krylov space ----------
+ * Replaces ks_eigCG_parity / ks_inc_eigCG_parity / calc_eigenpairs (generic_ks/inc_eigcg.c:377-850, 851-950,
+ * 282-300; A. Stathopoulos and K. Orginos, arXiv:0707.0131), what mat_invert_uml_field calls for its even-site
+ * solve when MILC is built with EIGMODE = EIGCG (generic_ks/mat_invert.c:361-363).
+ * b200ks_eigcg_init: starts an incremental sequence with MILC's eigcg_params (include/imp_ferm_links.h:410-416):
+ *   a search window of m vectors, nvecs Ritz pairs harvested per solve, at most nvecs_max accumulated.  The
+ *   window and the accumulated vectors live in HBM, one parity half each (24 B x lattice volume per vector).
+ * b200ks_inc_eigcg[_dev]: one solve of the sequence: the trial solution is first improved by the accumulated
+ *   vectors, x += U (H + 4 m^2)^-1 U^+ (b - A x) (initCG); then the context's pure-double CG runs -- iteration
+ *   for iteration the arithmetic of b200ks_congrad -- while its coefficients build the Lanczos matrix and its
+ *   normalised residuals fill the window, which is compressed to the 2 nvecs Ritz vectors of T_m and T_{m-1}
+ *   whenever it is full; the nvecs lowest Ritz vectors are orthogonalised against the accumulated set and
+ *   H = -U^+ D^2 U is extended.  Returns iterations like b200ks_congrad; res likewise.
+ * b200ks_eigcg_pairs: Rayleigh-Ritz on everything accumulated; eigval (may be NULL, room for nmax_out) receives
+ *   the Ritz values of -D_eo D_oe in ascending order; returns their number.
+ * b200ks_eigcg_count / _vec_download / _H: what has been accumulated, for MILC's eigVec[] / eigcgp->H.
+ * Single-GPU contexts. */
+int b200ks_eigcg_init(b200ks_ctx *ctx, int m, int nvecs, int nvecs_max);
+int b200ks_inc_eigcg(b200ks_ctx *ctx, const void *src, void *dest, double mass, const b200ks_invert_args *args,
+                     b200ks_invert_result *res, int host_prec);
+int b200ks_inc_eigcg_dev(b200ks_ctx *ctx, int vsrc, int vdest, double mass, const b200ks_invert_args *args,
+                         b200ks_invert_result *res);
+int b200ks_eigcg_pairs(b200ks_ctx *ctx, double *eigval, int nmax_out);
+int b200ks_eigcg_count(b200ks_ctx *ctx);
+int b200ks_eigcg_vec_download(b200ks_ctx *ctx, int j, void *host, int host_prec);
+int b200ks_eigcg_hmatrix(b200ks_ctx *ctx, double *H_out);
 
 /* ---- fermion-link construction ---------------------------
  * Links are su3_matrix[4*V] in MILC order (link[4*i+dir]) with KS phases and boundary signs

@@ -86,6 +86,16 @@ typedef struct {
 } fn_links_t;
 typedef fn_links_t imp_ferm_links_t;
 
+/* include/imp_ferm_links.h:410-416 */
+typedef struct { double real; double imag; } b200ks_double_complex;
+typedef struct {
+  int m;          /* Number of vectors kept for the Lanczos part before restart */
+  int Nvecs;      /* Number of eigenpairs computed per inversion */
+  int Nvecs_curr; /* Number of eigenpairs currently computed */
+  int Nvecs_max;  /* Maximum number of eigenpairs computed in entire incremental eigCG */
+  b200ks_double_complex *H; /* H = -U^+ Dslash^2 U, column-major with leading dimension Nvecs_max */
+} eigcg_params;
+
 /* the globals a MILC application owns (ks_spectrum/lattice.h:63-124); the standalone
  * library keeps its own copies, set by b200ks_milc_setup */
 #ifdef __cplusplus
@@ -122,6 +132,14 @@ int mat_invert_block_uml_gpu(su3_vector **src, su3_vector **dst, Real mass, int 
 /* Low modes for qic->deflate in the two sequences above (generic_ks/mat_invert.c:131-183): MILC's eigVec, eigVal and
  * param.eigen_param.Nvecs, handed over once after they were read or computed; kept in HBM.  nvecs = 0 drops them. */
 void b200ks_milc_set_eigenvectors(int nvecs, su3_vector **eigvec, double *eigval);
+/* Incremental eigCG on the device (generic_ks/inc_eigcg.c:851-950, 282-300), MILC's prototypes
+ * (include/imp_ferm_links.h:417-424).  The search window and the accumulated vectors stay in HBM; after every solve
+ * the NEW vectors are copied into eigVec[] and eigcgp (Nvecs_curr, Nvecs, H) is brought up to date, so MILC code that
+ * reads them afterwards (calc_eigenpairs, the eigenvector files) keeps working.  Mapped by a maintainer under
+ * USE_CG_GPU like the UML sequences. */
+int ks_inc_eigCG_parity_gpu(su3_vector *src, su3_vector *dest, double *eigVal, su3_vector **eigVec, eigcg_params *eigcgp,
+                            quark_invert_control *qic, Real mass, imp_ferm_links_t *fn);
+void calc_eigenpairs_gpu(double *eigVal, su3_vector **eigVec, eigcg_params *eigcgp, int parity);
 imp_ferm_links_t *get_fn_last(void);
 void set_fn_last(imp_ferm_links_t *fn_last_new);
 

@@ -81,6 +81,13 @@ SYMBOLS = [
     ("b200ks_eig_count", C.c_int, [C.c_void_p]),
     ("b200ks_eig_use_in_uml", C.c_int, [C.c_void_p, C.c_int]),
     ("b200ks_deflate_dev", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int]),
+    ("b200ks_eigcg_init", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    ("b200ks_inc_eigcg", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(InvertArgs), C.POINTER(InvertResult), C.c_int]),
+    ("b200ks_inc_eigcg_dev", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(InvertArgs), C.POINTER(InvertResult)]),
+    ("b200ks_eigcg_pairs", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
+    ("b200ks_eigcg_count", C.c_int, [C.c_void_p]),
+    ("b200ks_eigcg_vec_download", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    ("b200ks_eigcg_hmatrix", C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     ("b200ks_ks_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ("b200ks_unitarized_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.POINTER(C.c_longlong)]),

@@ -344,6 +344,39 @@ class Context:
     def eig_count(self):
         return self.lib.b200ks_eig_count(self.h)
 
+    # -- eigCG (generic_ks/inc_eigcg.c) ------------------------------------------------------------
+    def eigcg_init(self, m, nvecs, nvecs_max):
+        check(self.lib.b200ks_eigcg_init(self.h, m, nvecs, nvecs_max), "b200ks_eigcg_init")
+
+    def inc_eigcg(self, src, dest, mass, parity, max_iter, nrestart, resid):
+        """ks_inc_eigCG_parity: one solve of the incremental sequence; returns (iterations, result dict)."""
+        args = InvertArgs(parity, max_iter, nrestart, resid, 0.0, 0, 0)
+        res = InvertResult()
+        it = check(self.lib.b200ks_inc_eigcg(self.h, _ptr(src), _ptr(dest), mass, C.byref(args), C.byref(res), _host_prec(src)),
+                   "b200ks_inc_eigcg")
+        return it, res.as_dict()
+
+    def inc_eigcg_dev(self, vsrc, vdest, mass, parity, max_iter, nrestart, resid):
+        args = InvertArgs(parity, max_iter, nrestart, resid, 0.0, 0, 0)
+        res = InvertResult()
+        it = check(self.lib.b200ks_inc_eigcg_dev(self.h, vsrc, vdest, mass, C.byref(args), C.byref(res)), "b200ks_inc_eigcg_dev")
+        return it, res.as_dict()
+
+    def eigcg_count(self):
+        return self.lib.b200ks_eigcg_count(self.h)
+
+    def eigcg_pairs(self):
+        """calc_eigenpairs: Ritz values of -D^2 (ascending) of everything accumulated; rotates the vectors."""
+        n = self.eigcg_count()
+        out = (C.c_double * max(n, 1))()
+        n = check(self.lib.b200ks_eigcg_pairs(self.h, out, n), "b200ks_eigcg_pairs")
+        return np.array(out[:n])
+
+    def eigcg_vec(self, j, dtype=np.float64):
+        out = np.zeros((self.volume, 3, 2), dtype=dtype)
+        check(self.lib.b200ks_eigcg_vec_download(self.h, j, _ptr(out), _host_prec(out)), "b200ks_eigcg_vec_download")
+        return out
+
     def deflate_dev(self, vsrc, vdst, mass, parity):
         """b200ks_deflate_dev: deflate() of generic_ks/mat_invert.c:131-183 on device vectors."""
         check(self.lib.b200ks_deflate_dev(self.h, vsrc, vdst, mass, parity), "b200ks_deflate_dev")

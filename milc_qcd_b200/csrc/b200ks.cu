@@ -122,6 +122,7 @@ struct b200ks_ctx {
                                         // operations that do not run partitioned yet (links, force)
   int member_rank = -1;                 // >= 0: member of a multi-GPU context
   double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // b200ks_call_profile
+  void *eigcg = nullptr;                // EigCGState (eigcg.inl): search window + accumulated low modes in HBM
 };
 
 // ---- single-process multi-GPU contexts (b200ks_create_multi) -------------------------------------
@@ -176,6 +177,7 @@ struct MultiState {
 };
 
 static void watch_join_thread(b200ks_ctx *c);
+static void eigcg_release(b200ks_ctx *c);
 static int nmembers(const b200ks_ctx *c) { return c->sub.empty() ? 1 : (int)c->sub.size(); }
 
 template <typename F>
@@ -658,6 +660,7 @@ extern "C" void b200ks_destroy(b200ks_ctx *c) {
   if (c->comm.ev_done) cudaEventDestroy(c->comm.ev_done);
   if (c->comm.stream) cudaStreamDestroy(c->comm.stream);
   fermion_links_release(c);
+  eigcg_release(c);
   cudaFree(c->eig.d_val);
   cudaFree((void *)c->eig.d_ptr[0]);
   cudaFree((void *)c->eig.d_ptr[1]);
@@ -3502,3 +3505,4 @@ extern "C" int b200ks_links_download(b200ks_ctx *c, void *fat, void *lng, int ho
   return check_launch("unpack_link_kernel");
 }
 
+#include "eigcg.inl"

@@ -327,6 +327,97 @@ int mat_invert_uml_field_gpu(su3_vector *src, su3_vector *dst, quark_invert_cont
   return mat_invert_block_uml_gpu(&src, &dst, mass, 1, qic, fn);
 }
 
+/* Incremental eigCG (generic_ks/inc_eigcg.c:851-950): one solve of the sequence on the device, then eigVec[],
+ * eigVal[] (untouched, as in the reference, until calc_eigenpairs) and eigcgp are brought up to date on the host. */
+#ifdef B200KS_IN_MILC
+typedef double_complex b200ks_double_complex;
+#endif
+static int s_eigcg_m = 0, s_eigcg_nvecs = 0, s_eigcg_max = 0;
+int ks_inc_eigCG_parity_gpu(su3_vector *src, su3_vector *dest, double *eigVal, su3_vector **eigVec, eigcg_params *eigcgp,
+                            quark_invert_control *qic, Real mass, imp_ferm_links_t *fn) {
+  char myname[] = "ks_inc_eigCG_parity_gpu";
+  b200ks_invert_args a;
+  b200ks_invert_result r;
+  b200ks_ctx *ctx;
+  int iters, j, k, n_old, n_new, ld;
+  double *Hdev;
+  (void)eigVal;
+
+  qic->size_r = 0;
+  qic->size_relr = 1.;
+  qic->final_iters = 0;
+  qic->final_restart = 0;
+  qic->converged = 1;
+  qic->final_rsq = 0.;
+  qic->final_relrsq = 0.;
+  if (fn == NULL) {
+    printf("%s(0): Called with NULL fn\n", myname);
+    FATAL(1);
+  }
+  if (qic->parity != EVEN && qic->parity != ODD) {
+    printf("%s: Unrecognised parity\n", myname);
+    FATAL(2);
+  }
+  ctx = context(myname);
+  refresh_links(myname, fn);
+  n_old = eigcgp->Nvecs_curr;
+  ld = eigcgp->Nvecs_max;
+  if (n_old == 0 || eigcgp->m != s_eigcg_m || ld != s_eigcg_max || b200ks_eigcg_count(ctx) != n_old) {
+    /* a new sequence (inc_eigcg.c:868-873 allocates H here) */
+    if (b200ks_eigcg_init(ctx, eigcgp->m, eigcgp->Nvecs, ld) < 0) die(myname);
+    s_eigcg_m = eigcgp->m; s_eigcg_nvecs = eigcgp->Nvecs; s_eigcg_max = ld;
+    if (eigcgp->H != NULL) free(eigcgp->H);
+    eigcgp->H = (b200ks_double_complex *)calloc((size_t)ld * ld, sizeof(b200ks_double_complex));
+    n_old = 0;
+  }
+  memset(&a, 0, sizeof(a));
+  a.parity = qic->parity;
+  a.max_iter = qic->max;
+  a.nrestart = qic->nrestart;
+  a.resid = qic->resid;
+  a.relresid = qic->relresid;
+  iters = b200ks_inc_eigcg(ctx, src, dest, (double)mass, &a, &r, MILC_PRECISION);
+  if (iters < 0) die(myname);
+  qic->final_rsq = (Real)r.final_rsq;
+  qic->final_relrsq = (Real)r.final_relrsq;
+  qic->size_r = (Real)r.size_r;
+  qic->size_relr = (Real)r.size_relr;
+  qic->final_iters = r.final_iters;
+  qic->final_restart = r.final_restart;
+  qic->converged = r.converged;
+  TOTAL_ITERS += iters;
+  n_new = b200ks_eigcg_count(ctx);
+  for (j = n_old; j < n_new; j++)
+    if (b200ks_eigcg_vec_download(ctx, j, eigVec[j], MILC_PRECISION) < 0) die(myname);
+  Hdev = (double *)malloc(sizeof(double) * 2 * (size_t)ld * ld);
+  if (b200ks_eigcg_hmatrix(ctx, Hdev) < 0) die(myname);
+  for (j = 0; j < n_new; j++)      /* row-major [k][j] -> MILC's column-major H[k + ld*j] */
+    for (k = 0; k < n_new; k++) {
+      eigcgp->H[k + (size_t)ld * j].real = Hdev[2 * ((size_t)k * ld + j)];
+      eigcgp->H[k + (size_t)ld * j].imag = Hdev[2 * ((size_t)k * ld + j) + 1];
+    }
+  free(Hdev);
+  eigcgp->Nvecs_curr = n_new;
+  eigcgp->Nvecs = (ld - n_new < eigcgp->Nvecs) ? (ld - n_new) : eigcgp->Nvecs;
+  return iters;
+}
+
+/* calc_eigenpairs (inc_eigcg.c:282-300): Rayleigh-Ritz on the accumulated vectors; eigVal[], eigVec[] and H follow */
+void calc_eigenpairs_gpu(double *eigVal, su3_vector **eigVec, eigcg_params *eigcgp, int parity) {
+  char myname[] = "calc_eigenpairs_gpu";
+  b200ks_ctx *ctx = context(myname);
+  int j, k, n, ld = eigcgp->Nvecs_max;
+  (void)parity;
+  n = b200ks_eigcg_pairs(ctx, eigVal, eigcgp->Nvecs_curr);
+  if (n < 0) die(myname);
+  for (j = 0; j < n; j++) {
+    if (b200ks_eigcg_vec_download(ctx, j, eigVec[j], MILC_PRECISION) < 0) die(myname);
+    for (k = 0; k < j; k++) eigcgp->H[k + (size_t)ld * j].real = eigcgp->H[k + (size_t)ld * j].imag = 0.;
+    eigcgp->H[j + (size_t)ld * j].real = eigVal[j];
+    eigcgp->H[j + (size_t)ld * j].imag = 0.;
+  }
+}
+
 int ks_multicg_offset_field_gpu(su3_vector *src, su3_vector **psim, ks_param *ksp, int num_offsets,
                                 quark_invert_control *qic, imp_ferm_links_t *fn) {
   char myname[] = "ks_multicg_offset_field_gpu";

@@ -39,6 +39,28 @@ b200ks_ctx *b200ks_create(const int latsize[4], int device) {
 }
 void b200ks_destroy(b200ks_ctx *c) { (void)c; logf_("destroy\n"); s_live_vecs = 0; }
 int b200ks_num_gpus(b200ks_ctx *c) { (void)c; return 1; }
+static void fill(b200ks_invert_result *r, int iters);
+static void copy_parity(void *dst, const void *src, int parity, int host_prec);
+static int s_eig_n = 0, s_eig_add = 0, s_eig_max = 0;
+int b200ks_eigcg_init(b200ks_ctx *c, int m, int nvecs, int nmax) { (void)c; logf_("eigcg_init m %d nvecs %d max %d\n", m, nvecs, nmax); s_eig_n = 0; s_eig_add = nvecs; s_eig_max = nmax; return 0; }
+int b200ks_eigcg_count(b200ks_ctx *c) { (void)c; return s_eig_n; }
+int b200ks_inc_eigcg(b200ks_ctx *c, const void *src, void *dest, double mass, const b200ks_invert_args *a, b200ks_invert_result *r, int host_prec) {
+  (void)c;
+  logf_("inc_eigcg mass %g parity %d\n", mass, a->parity);
+  copy_parity(dest, src, a->parity, host_prec);
+  fill(r, 41);
+  s_eig_n += s_eig_add;
+  if (s_eig_n > s_eig_max) s_eig_n = s_eig_max;
+  return 41;
+}
+int b200ks_eigcg_vec_download(b200ks_ctx *c, int j, void *host, int host_prec) {
+  (void)c;
+  logf_("eigcg_vec_download %d\n", j);
+  if (host_prec == 2) ((double *)host)[0] = 100.0 + j; else ((float *)host)[0] = 100.0f + j;
+  return 0;
+}
+int b200ks_eigcg_hmatrix(b200ks_ctx *c, double *H) { int k; (void)c; for (k = 0; k < 2 * s_eig_max * s_eig_max; k++) H[k] = 0.5 * k; return s_eig_max; }
+int b200ks_eigcg_pairs(b200ks_ctx *c, double *val, int n) { int j; (void)c; logf_("eigcg_pairs %d\n", n); for (j = 0; j < n && j < s_eig_n; j++) val[j] = 0.001 * (j + 1); return s_eig_n; }
 const char *b200ks_last_error(void) { return "stub error"; }
 unsigned long long b200ks_fingerprint(const void *p, size_t bytes) {
   const unsigned char *b = (const unsigned char *)p;

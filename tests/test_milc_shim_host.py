@@ -164,3 +164,46 @@ def test_eigenvector_hand_over_and_deflate_switch(shim):
     assert shim.stub_live_vecs() == 1
     shim.b200ks_milc_set_eigenvectors(0, None, None)
     assert shim.stub_live_vecs() == 0
+
+
+def test_incremental_eigcg_bookkeeping(shim):
+    """ks_inc_eigCG_parity_gpu / calc_eigenpairs_gpu keep MILC's eigcg_params, eigVec[] and H in step with the device
+    (generic_ks/inc_eigcg.c:851-950, 282-300): new sequence when Nvecs_curr == 0, only the NEW vectors are copied
+    back, Nvecs shrinks when the set is nearly full, H arrives in MILC's column-major layout."""
+    class DC(C.Structure):
+        _fields_ = [("real", C.c_double), ("imag", C.c_double)]
+
+    class EigcgParams(C.Structure):
+        _fields_ = [("m", C.c_int), ("Nvecs", C.c_int), ("Nvecs_curr", C.c_int), ("Nvecs_max", C.c_int), ("H", C.POINTER(DC))]
+
+    rng = np.random.default_rng(2)
+    fat, lng = rng.standard_normal((V, 4, 3, 3, 2)), rng.standard_normal((V, 4, 3, 3, 2))
+    fn = _fn(fat, lng)
+    src, dst = rng.standard_normal((V, 3, 2)), np.zeros((V, 3, 2))
+    nmax = 10
+    vecs = [np.zeros((V, 3, 2)) for _ in range(nmax + 20)]
+    pv = (C.c_void_p * len(vecs))(*[v.ctypes.data for v in vecs])
+    val = np.zeros(len(vecs))
+    ep = EigcgParams(20, 4, 0, nmax, None)
+    shim.ks_inc_eigCG_parity_gpu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(EigcgParams),
+                                             C.POINTER(Qic), C.c_double, C.POINTER(FnLinks)]
+    shim.calc_eigenpairs_gpu.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(EigcgParams), C.c_int]
+    expect = [(4, 4), (8, 2), (10, 0)]
+    for call, (ncurr, nvecs_next) in enumerate(expect):
+        q = _qic(EVEN)
+        it = shim.ks_inc_eigCG_parity_gpu(src.ctypes.data, dst.ctypes.data, val.ctypes.data, pv, C.byref(ep), C.byref(q), 0.05,
+                                          C.byref(fn))
+        log = _log(shim)
+        assert it == 41 and q.final_iters == 41 and q.converged == 1
+        assert any(ln.startswith("eigcg_init m 20 nvecs 4 max 10") for ln in log) == (call == 0)
+        assert ep.Nvecs_curr == ncurr and ep.Nvecs == nvecs_next
+        got = [int(ln.split()[1]) for ln in log if ln.startswith("eigcg_vec_download")]
+        assert got == list(range(0 if call == 0 else expect[call - 1][0], ncurr))      # only the new ones
+        assert all(vecs[j][0, 0, 0] == 100.0 + j for j in range(ncurr))
+        # H[k + ld*j] = H_{k,j}; the stub's row-major entry (k, j) has real part 0.5 * 2 * (k*ld + j)
+        assert ep.H[1 + nmax * 2].real == 0.5 * 2 * (1 * nmax + 2) and ep.H[1 + nmax * 2].imag == 0.5 * (2 * (1 * nmax + 2) + 1)
+    shim.calc_eigenpairs_gpu(val.ctypes.data, pv, C.byref(ep), EVEN)
+    log = _log(shim)
+    assert log[0] == "eigcg_pairs 10" and val[3] == 0.004 and ep.H[3 + nmax * 3].real == 0.004 and ep.H[2 + nmax * 3].real == 0.0
+    assert len([ln for ln in log if ln.startswith("eigcg_vec_download")]) == 10
+    assert shim.b200ks_milc_total_iters() >= 3 * 41
