@@ -1142,6 +1142,11 @@ def main():
                          "block: multi-right-hand-side CG (ks_congrad_block_parity seam); "
                          "links: HISQ fermion-link construction (qudaLoadUnitarizedLink / qudaLoadKSLink seam)")
     args = ap.parse_args()
+    # stdout carries the JSON line and nothing else: whatever libraries write to the C-level stdout (NCCL's version
+    # banner, the reference's layout chatter) goes to stderr; Python's sys.stdout keeps the real one
+    sys.stdout.flush()
+    sys.stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "multishift":
