@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200KS_VERSION 120 /* 110: block solve, resident sequences, link construction; 111: force filter, Naik epsilons, deflation;
+#define B200KS_VERSION 121 /* 110: block solve, resident sequences, link construction; 111: force filter, Naik epsilons, deflation;
                               120: single-process multi-GPU contexts, b200ks_links_sync, flag-based reductions, eigCG */
 
 /* parity codes, include/macros.h:68-70 */
@@ -266,6 +266,28 @@ int b200ks_eigcg_pairs(b200ks_ctx *ctx, double *eigval, int nmax_out);
 int b200ks_eigcg_count(b200ks_ctx *ctx);
 int b200ks_eigcg_vec_download(b200ks_ctx *ctx, int j, void *host, int host_prec);
 int b200ks_eigcg_hmatrix(b200ks_ctx *ctx, double *H_out);
+
+/* ---- meson tie-ups: two propagators -> momentum-projected time-slice correlators ----
+ * Replaces the site loops of ks_meson_cont_mom (generic_ks/ks_meson_mom.c:160-437) for ONE sink spin-taste
+ * assignment g of its table:
+ *     corr[t][p] = sum_{x in time slice t} s(x - r0) <antiquark(x) | quark(x)> ftfact_p(x - r0),   t < nt, p < nmom
+ *   <a|b> = su3_dot(a, b) (:349-363); ftfact_p = product over x, y, z of cos / i sin / exp(i .) of
+ *   2 pi (x_d - r0_d) mom[3p+d] / n_d chosen by mom_parity[3p+d] = B200KS_EVEN / _ODD / _EVENANDODD (MILC's
+ *   q_momstore[p], q_parity[p]; ff(), :137-157); s = the site sign of a LOCAL sink operator applied to the
+ *   antiquark (local(), generic_ks/spin_taste_ops.c:172-263): spin = its gamma bits 0..15 (gamma_hex of the
+ *   operator's spin index: pion5 = 15, pion05 = 0, rhox = 1, rhoy = 2, rhoz = 4, rhox0 = 9, ...), or spin = -1 when
+ *   the caller has applied the sink operator to `antiquark` itself (the one-link and FN-shifted operators, which
+ *   MILC builds from fat-link shifts on the host).
+ * corr: nt x nmom complex numbers (re, im), OVERWRITTEN; nt is the GLOBAL time extent.  The correlator phase and
+ * factor (norm_v, :100-131) and the accumulation into prop[corr_index][t] stay with the caller (csrc_milc/milc_shim.c
+ * ks_meson_cont_mom_gpu).  Both propagators are read once whatever nmom is (nmom <= 128 per call).
+ * _dev: device vectors (b200ks_vec_create; e.g. the solutions of b200ks_mat_invert_uml_dev, never leaving HBM).
+ * Multi-GPU contexts (b200ks_create_multi): every member contracts its sub-lattice, the shares are added on the
+ * host in member order. */
+int b200ks_meson_mom_dev(b200ks_ctx *ctx, int vantiquark, int vquark, int spin, const int *r0, int nmom, const int *mom,
+                         const char *mom_parity, double *corr);
+int b200ks_meson_mom(b200ks_ctx *ctx, const void *antiquark, const void *quark, int host_prec, int spin, const int *r0,
+                     int nmom, const int *mom, const char *mom_parity, double *corr);
 
 /* ---- fermion-link construction ---------------------------
  * Links are su3_matrix[4*V] in MILC order (link[4*i+dir]) with KS phases and boundary signs

@@ -26,6 +26,7 @@
 #include "deflate.cuh"
 #include "dslash.cuh"
 #include "half.cuh"
+#include "meson.cuh"
 #include "mrhs.cuh"
 #include "synth.cuh"
 
@@ -3506,3 +3507,4 @@ extern "C" int b200ks_links_download(b200ks_ctx *c, void *fat, void *lng, int ho
 }
 
 #include "eigcg.inl"
+#include "meson.inl"
