@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 #define B200KS_VERSION 121 /* 110: block solve, resident sequences, link construction; 111: force filter, Naik epsilons, deflation;
-                              120: single-process multi-GPU contexts, b200ks_links_sync, flag-based reductions, eigCG */
+                              120: single-process multi-GPU contexts, b200ks_links_sync, flag-based reductions, eigCG; 121: meson tie-ups */
 
 /* parity codes, include/macros.h:68-70 */
 #define B200KS_EVEN 2

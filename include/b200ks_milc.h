@@ -32,6 +32,7 @@ typedef double Real;
 #endif
 
 typedef struct { Real real; Real imag; } b200ks_complex;
+#define B200KS_MILC_COMPLEX b200ks_complex   /* MILC's `complex` (include/complex.h:177-180) */
 typedef struct { b200ks_complex c[3]; } su3_vector;
 typedef struct { b200ks_complex e[3][3]; } su3_matrix;
 
@@ -109,6 +110,8 @@ struct b200ks_ctx *b200ks_milc_context(void); /* the library context behind the 
 }
 #endif
 
+#else
+#define B200KS_MILC_COMPLEX complex
 #endif /* !B200KS_IN_MILC */
 
 #ifdef __cplusplus
@@ -140,6 +143,15 @@ void b200ks_milc_set_eigenvectors(int nvecs, su3_vector **eigvec, double *eigval
 int ks_inc_eigCG_parity_gpu(su3_vector *src, su3_vector *dest, double *eigVal, su3_vector **eigVec, eigcg_params *eigcgp,
                             quark_invert_control *qic, Real mass, imp_ferm_links_t *fn);
 void calc_eigenpairs_gpu(double *eigVal, su3_vector **eigVec, eigcg_params *eigcgp, int parity);
+/* Meson tie-ups on the device, prototype of ks_meson_cont_mom (generic_ks/ks_meson_mom.c:160-178; mapped by a
+ * maintainer like the sequences above).  The two propagators go up once per sink spin-taste assignment and are
+ * contracted there for all of its momenta; LOCAL sink operators (site signs, generic_ks/spin_taste_ops.c:172-263) are
+ * applied inside the kernel, every other operator by MILC's own spin_taste_op_fn on the host first (inside a MILC
+ * tree; a standalone build refuses them).  norm_v and the accumulation into prop[m][t] as in the reference. */
+void ks_meson_cont_mom_gpu(B200KS_MILC_COMPLEX **prop, su3_vector *src1, su3_vector *src2, int no_q_momenta, int **q_momstore,
+                           char **q_parity, int no_spin_taste_corr, int num_corr_mom[], int **corr_table, int p_index[],
+                           imp_ferm_links_t *fn_src1, imp_ferm_links_t *fn_src2, int spin_taste_snk[], int meson_phase[],
+                           Real meson_factor[], int corr_index[], int r0[]);
 imp_ferm_links_t *get_fn_last(void);
 void set_fn_last(imp_ferm_links_t *fn_last_new);
 

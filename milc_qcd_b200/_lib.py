@@ -88,6 +88,10 @@ SYMBOLS = [
     ("b200ks_eigcg_count", C.c_int, [C.c_void_p]),
     ("b200ks_eigcg_vec_download", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     ("b200ks_eigcg_hmatrix", C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    ("b200ks_meson_mom_dev", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int),
+                                       C.c_char_p, C.POINTER(C.c_double)]),
+    ("b200ks_meson_mom", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,
+                                   C.POINTER(C.c_int), C.c_char_p, C.POINTER(C.c_double)]),
     ("b200ks_ks_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ("b200ks_unitarized_links", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.POINTER(C.c_longlong)]),

@@ -377,6 +377,33 @@ class Context:
         check(self.lib.b200ks_eigcg_vec_download(self.h, j, _ptr(out), _host_prec(out)), "b200ks_eigcg_vec_download")
         return out
 
+    # -- meson tie-ups (generic_ks/ks_meson_mom.c) --------------------------------------------------
+    def _meson_args(self, r0, mom, mom_parity):
+        mom = np.ascontiguousarray(mom, dtype=np.int32).reshape(-1, 3)
+        par = np.ascontiguousarray(mom_parity, dtype=np.int8).reshape(-1, 3)
+        assert par.shape == mom.shape
+        nmom = mom.shape[0]
+        r0a = (C.c_int * 4)(*[int(v) for v in r0])
+        out = np.zeros((self.global_dims[3], nmom, 2))
+        return nmom, r0a, mom, par, out
+
+    def meson_mom(self, antiquark, quark, spin, r0, mom, mom_parity):
+        """The site loops of ks_meson_cont_mom for one sink spin-taste assignment: corr[t][p] (complex), host fields in
+        MILC's layout.  spin = gamma bits of a local sink operator (15 = pion5, 0 = pion05, ...) or -1 (already applied)."""
+        nmom, r0a, mom, par, out = self._meson_args(r0, mom, mom_parity)
+        assert _host_prec(antiquark) == _host_prec(quark)
+        check(self.lib.b200ks_meson_mom(self.h, _ptr(antiquark), _ptr(quark), _host_prec(quark), int(spin), r0a, nmom,
+                                        mom.ctypes.data_as(C.POINTER(C.c_int)), par.tobytes(),
+                                        out.ctypes.data_as(C.POINTER(C.c_double))), "b200ks_meson_mom")
+        return out[..., 0] + 1j * out[..., 1]
+
+    def meson_mom_dev(self, vantiquark, vquark, spin, r0, mom, mom_parity):
+        nmom, r0a, mom, par, out = self._meson_args(r0, mom, mom_parity)
+        check(self.lib.b200ks_meson_mom_dev(self.h, vantiquark, vquark, int(spin), r0a, nmom,
+                                            mom.ctypes.data_as(C.POINTER(C.c_int)), par.tobytes(),
+                                            out.ctypes.data_as(C.POINTER(C.c_double))), "b200ks_meson_mom_dev")
+        return out[..., 0] + 1j * out[..., 1]
+
     def deflate_dev(self, vsrc, vdst, mass, parity):
         """b200ks_deflate_dev: deflate() of generic_ks/mat_invert.c:131-183 on device vectors."""
         check(self.lib.b200ks_deflate_dev(self.h, vsrc, vdst, mass, parity), "b200ks_deflate_dev")

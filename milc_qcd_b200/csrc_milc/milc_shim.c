@@ -418,6 +418,123 @@ void calc_eigenpairs_gpu(double *eigVal, su3_vector **eigVec, eigcg_params *eigc
   }
 }
 
+/* ---- meson tie-ups (generic_ks/ks_meson_mom.c:160-437) ------------------------------------------------------ */
+/* gamma bits of a LOCAL sink operator, -1 when the operator needs link shifts.  Compatibility indices: enum
+ * spin_taste_type (generic_ks/spin_taste_ops.c:805-853; pion5 = 0, pion05 = 1, rhoi = 8 ... rhoz0 = 15) with the
+ * operators spin_taste_op_links gives them (:1205-1270); gamma-gamma indices (>= 128, :960-973) are local when spin
+ * and taste agree; bits = gamma_hex_value (generic_wilson/gammas.c:21-22). */
+static int local_spin_bits(int index) {
+  static const int hex[16] = {1, 2, 4, 8, 15, 6, 5, 3, 9, 10, 12, 14, 13, 11, 7, 0};
+  if (index >= 128) {
+    int s = (index - 128) / 16, t = (index - 128) % 16;
+    return (s == t && s < 16) ? hex[s] : -1;
+  }
+  switch (index) {
+  case 0: return 15;            /* pion5: gamma_5 x gamma_5 */
+  case 1: return 0;             /* pion05: 1 x 1 */
+  case 9: return 1;             /* rhox */
+  case 10: return 2;            /* rhoy */
+  case 8: case 11: return 4;    /* rhoi, rhoz */
+  case 13: return 9;            /* rhox0: gamma_x gamma_t */
+  case 14: return 10;           /* rhoy0 */
+  case 12: case 15: return 12;  /* rhoi0, rhoz0 */
+  default: return -1;
+  }
+}
+/* spin_taste_ops.c:983-1035: rhoxsfn .. rhotsfn = 22..25, ffn 26..29, bfn 30..33, ape 34..37, fape 38..41, bape 42..45 */
+static int st_is_rhosfn(int i) { return (i >= 22 && i <= 25) || (i >= 34 && i <= 37); }
+static int st_is_rhosffn(int i) { return (i >= 26 && i <= 29) || (i >= 38 && i <= 41); }
+static int st_is_rhosbfn(int i) { return (i >= 30 && i <= 33) || (i >= 42 && i <= 45); }
+static int st_forward(int i) { return st_is_rhosfn(i) ? i + 4 : -1; }    /* forward_index(), :1041-1064 */
+static int st_backward(int i) { return st_is_rhosfn(i) ? i + 8 : -1; }   /* backward_index(), :1067-1090 */
+
+#ifdef B200KS_IN_MILC
+#define SINK_OP(fn, index, r0, dest, src) spin_taste_op_fn(fn, index, r0, dest, src)
+#else
+static void SINK_OP(imp_ferm_links_t *fn, int index, int r0[], su3_vector *dest, su3_vector *src) {
+  (void)fn; (void)r0; (void)dest; (void)src;
+  printf("ks_meson_cont_mom_gpu: sink operator %d needs MILC's spin_taste_op_fn (build inside the MILC tree)\n", index);
+  FATAL(1);
+}
+#endif
+
+void ks_meson_cont_mom_gpu(B200KS_MILC_COMPLEX **prop, su3_vector *src1, su3_vector *src2, int no_q_momenta, int **q_momstore,
+                           char **q_parity, int no_spin_taste_corr, int num_corr_mom[], int **corr_table, int p_index[],
+                           imp_ferm_links_t *fn_src1, imp_ferm_links_t *fn_src2, int spin_taste_snk[], int meson_phase[],
+                           Real meson_factor[], int corr_index[], int r0[]) {
+  char myname[] = "meson_cont_mom";
+  b200ks_ctx *ctx = context(myname);
+  const int nt_ = NT;
+  int g, k, t, d;
+  int *mom;
+  char *par;
+  double *corr, *corr2 = NULL;
+  su3_vector *work = NULL;
+
+  if (no_q_momenta > 100) { /* MAXQ, ks_meson_mom.c:225-230 */
+    printf("%s(%d): no_q_momenta %d exceeds max %d\n", myname, 0, no_q_momenta, 100);
+    FATAL(1);
+  }
+  mom = (int *)malloc(3 * sizeof(int) * (size_t)(no_q_momenta > 0 ? no_q_momenta : 1));
+  par = (char *)malloc(3 * (size_t)(no_q_momenta > 0 ? no_q_momenta : 1));
+  corr = (double *)malloc(2 * sizeof(double) * (size_t)nt_ * (no_q_momenta > 0 ? no_q_momenta : 1));
+  if (mom == NULL || par == NULL || corr == NULL) {
+    printf("%s(%d): No room for meson\n", myname, 0);
+    FATAL(1);
+  }
+  for (g = 0; g < no_spin_taste_corr; g++) {
+    const int nk = num_corr_mom[g];
+    const int st = spin_taste_snk[corr_table[g][0]];
+    const int bits = local_spin_bits(st);
+    int rc;
+    if (nk < 1) continue;
+    for (k = 0; k < nk; k++) {
+      const int p = p_index[corr_table[g][k]];
+      for (d = 0; d < 3; d++) { mom[3 * k + d] = q_momstore[p][d]; par[3 * k + d] = q_parity[p][d]; }
+    }
+    if (bits >= 0) {
+      rc = b200ks_meson_mom(ctx, src1, src2, MILC_PRECISION, bits, r0, nk, mom, par, corr);
+    } else {
+      if (work == NULL) work = (su3_vector *)malloc(SITES * sizeof(su3_vector));
+      if (work == NULL) { printf("%s(%d): No room for meson\n", myname, 0); FATAL(1); }
+      if (st_is_rhosfn(st)) { /* (db + df)/2, ks_meson_mom.c:296-312, 349-356 */
+        if (corr2 == NULL) corr2 = (double *)malloc(2 * sizeof(double) * (size_t)nt_ * no_q_momenta);
+        SINK_OP(fn_src1, st_backward(st), r0, work, src1);
+        rc = b200ks_meson_mom(ctx, work, src2, MILC_PRECISION, -1, r0, nk, mom, par, corr);
+        if (rc >= 0) {
+          SINK_OP(fn_src2, st_forward(st), r0, work, src2);
+          rc = b200ks_meson_mom(ctx, src1, work, MILC_PRECISION, -1, r0, nk, mom, par, corr2);
+          for (k = 0; k < 2 * nt_ * nk; k++) corr[k] = 0.5 * (corr[k] + corr2[k]);
+        }
+      } else if (st_is_rhosffn(st)) {
+        SINK_OP(fn_src2, st_forward(st), r0, work, src2);
+        rc = b200ks_meson_mom(ctx, src1, work, MILC_PRECISION, -1, r0, nk, mom, par, corr);
+      } else {
+        SINK_OP(fn_src1, st_is_rhosbfn(st) ? st_backward(st) : st, r0, work, src1);
+        rc = b200ks_meson_mom(ctx, work, src2, MILC_PRECISION, -1, r0, nk, mom, par, corr);
+      }
+    }
+    if (rc < 0) die(myname);
+    /* norm_v (ks_meson_mom.c:100-131) and the accumulation behind it (:405-419) */
+    for (t = 0; t < nt_; t++)
+      for (k = 0; k < nk; k++) {
+        const int c = corr_table[g][k];
+        const double re = corr[2 * ((size_t)t * nk + k)], im = corr[2 * ((size_t)t * nk + k) + 1];
+        const Real fact = meson_factor[c];
+        double zr, zi;
+        switch (meson_phase[c]) {
+        case 0: zr = re; zi = im; break;
+        case 1: zr = -im; zi = re; break;     /* TIMESPLUSI */
+        case 2: zr = -re; zi = -im; break;    /* TIMESMINUSONE */
+        default: zr = im; zi = -re; break;    /* TIMESMINUSI */
+        }
+        prop[corr_index[c]][t].real += (Real)(zr * fact);
+        prop[corr_index[c]][t].imag += (Real)(zi * fact);
+      }
+  }
+  free(mom); free(par); free(corr); free(corr2); free(work);
+}
+
 int ks_multicg_offset_field_gpu(su3_vector *src, su3_vector **psim, ks_param *ksp, int num_offsets,
                                 quark_invert_control *qic, imp_ferm_links_t *fn) {
   char myname[] = "ks_multicg_offset_field_gpu";

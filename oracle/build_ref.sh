@@ -31,6 +31,9 @@ GKS="$GKS fermion_links_hisq_load_milc.c fermion_links_fn_load_milc.c ks_action_
 # the HISQ fermion force (oracle only so far), ks_imp_rhmc's flags
 # (ks_imp_rhmc/Make_template: -DHISQ_FF_MULTI_WRAPPER -DHISQ_FORCE_FILTER=5.0e-5, KS_MULTIFF=FNMAT)
 GKS="$GKS fermion_force_hisq_multi.c fermion_links_hisq_milc.c fermion_links.c ff_opt.c path_transport.c"
+# meson tie-ups: the contraction and the sink spin-taste operators
+GKS="$GKS ks_meson_mom.c spin_taste_ops.c"
+GWI="gammas.c"
 # the UML propagator-solve sequence
 GEN="$GEN report_invert_status.c"
 GKS="$GKS mat_invert.c d_congrad5_fn.c"
@@ -61,6 +64,8 @@ build_variant() {  # name precision extra-flags
   done > "$obj/cmds.txt"
   for f in $GEN; do echo "gcc -c $AF -I$REF/generic $REF/generic/$f -o $obj/gen_${f%.c}.o"; done >> "$obj/cmds.txt"
   for f in $GKS; do echo "gcc -c $AF -I$REF/generic_ks $REF/generic_ks/$f -o $obj/gks_${f%.c}.o"; done >> "$obj/cmds.txt"
+  for f in $GWI; do echo "gcc -c $AF -I$REF/generic_wilson $REF/generic_wilson/$f -o $obj/gwi_${f%.c}.o"; done >> "$obj/cmds.txt"
+  echo "gcc -c $AF -I$REF/generic_ks $HERE/ref_harness/meson_harness.c -o $obj/meson_harness.o" >> "$obj/cmds.txt"
   echo "gcc -c $AF -I$REF/generic_ks $HERE/ref_harness/harness.c -o $obj/harness.o" >> "$obj/cmds.txt"
   local lapack=""
   if [ -n "$LAPACK_LIB" ] && [ "$prec" = "2" ]; then   # (inc_eigcg.c requires double precision)

@@ -22,6 +22,9 @@
  *   kso_relative_residue generic_ks/d_congrad5_fn_milc.c:37-56
  *   kso_deflate         generic_ks/mat_invert.c:131-183 (deflate + project_out), pinned through the
  *                       reference's deflated mat_invert_uml_field (tests/golden/make_golden_deflate.py)
+ *   kso_meson_mom       generic_ks/ks_meson_mom.c:160-437 (site loops), generic_ks/spin_taste_ops.c:172-263
+ *                       (local sink operators); pinned on the reference's ks_meson_cont_mom
+ *                       (tests/golden/make_golden_meson.py)
  *
  * Data layout is MILC's host layout: site index i = node_index(x,y,z,t) (all even
  * sites, then all odd sites), vectors v[6*i + 2*c + {re,im}], links
@@ -433,5 +436,56 @@ void kso_deflate(const int *n, double *dst, const double *src, double mass, int 
         dst[6 * i + 2 * c] += re * vr - im * vi;
         dst[6 * i + 2 * c + 1] += re * vi + im * vr;
       }
+  }
+}
+
+/* ---- meson tie-ups ---------------------------------------------------
+ * The site loops of ks_meson_cont_mom (generic_ks/ks_meson_mom.c:160-437) for ONE sink spin-taste
+ * assignment with a LOCAL sink operator (spin >= 0: local(), generic_ks/spin_taste_ops.c:172-263,
+ * applied to the antiquark) or none (spin < 0: the caller has applied it):
+ *   ftfact_p(x) = ff(2 pi/nx (x - r0x) px, ex, ff-chain ...)          (:137-157, :262-283)
+ *   meson(x)    = su3_dot(antiquark(x), quark(x))                     (:349-363)
+ *   corr[t][p] += meson(x) ftfact_p(x)  over the sites of slice t, in node-index order (:364-383)
+ * mom[3p + d], mpar[3p + d] (KSO_EVEN / KSO_ODD / KSO_EVENANDODD) as q_momstore / q_parity;
+ * corr[(t*nmom + p)*2 + {re,im}] is overwritten.  norm_v and the prop[] accumulation stay with the caller. */
+static void kso_ff(double theta, int parity, double *re, double *im) {
+  const double tr = *re, ti = *im;
+  if (parity == KSO_EVEN) { *re = tr * cos(theta); *im = ti * cos(theta); }
+  else if (parity == KSO_ODD) { *re = -ti * sin(theta); *im = tr * sin(theta); }
+  else { *re = tr * cos(theta) - ti * sin(theta); *im = ti * cos(theta) + tr * sin(theta); }
+}
+
+void kso_meson_mom(const int *n, const double *antiquark, const double *quark, int spin, const int *r0, int nmom,
+                   const int *mom, const char *mpar, double *corr) {
+  const double PI_ = 3.14159265358979323846;
+  const double fx = 2.0 * PI_ / (1.0 * n[0]), fy = 2.0 * PI_ / (1.0 * n[1]), fz = 2.0 * PI_ / (1.0 * n[2]);
+  int x, y, z, t, p, c;
+  memset(corr, 0, sizeof(double) * 2 * (size_t)n[3] * nmom);
+  for (t = 0; t < n[3]; t++) for (z = 0; z < n[2]; z++) for (y = 0; y < n[1]; y++) for (x = 0; x < n[0]; x++) {
+    const long i = kso_node_index(n, x, y, z, t);
+    double re = 0, im = 0, sign = 1.0;
+    for (c = 0; c < 3; c++) { /* su3_dot: conj(a) * b */
+      const double ar = antiquark[6 * i + 2 * c], ai = antiquark[6 * i + 2 * c + 1];
+      const double br = quark[6 * i + 2 * c], bi = quark[6 * i + 2 * c + 1];
+      re += ar * br + ai * bi;
+      im += ar * bi - ai * br;
+    }
+    if (spin >= 0) {
+      /* spin_sign(): for each gamma_mu bit a factor (-)^(x_mu - r0_mu) eps(x - r0); antiquark_sign_flip(): eps */
+      const int h[4] = {(x - r0[0]) & 1, (y - r0[1]) & 1, (z - r0[2]) & 1, (t - r0[3]) & 1};
+      const int hp = (h[0] + h[1] + h[2] + h[3]) & 1;
+      int j;
+      for (j = 0; j < 4; j++) if ((spin & (1 << j)) && (hp ^ h[j])) sign = -sign;
+      if (hp) sign = -sign;
+    }
+    re *= sign; im *= sign;
+    for (p = 0; p < nmom; p++) {
+      double fr = 1.0, fi = 0.0;
+      kso_ff(fx * (x - r0[0]) * mom[3 * p + 0], mpar[3 * p + 0], &fr, &fi);
+      kso_ff(fy * (y - r0[1]) * mom[3 * p + 1], mpar[3 * p + 1], &fr, &fi);
+      kso_ff(fz * (z - r0[2]) * mom[3 * p + 2], mpar[3 * p + 2], &fr, &fi);
+      corr[(t * (size_t)nmom + p) * 2] += re * fr - im * fi;
+      corr[(t * (size_t)nmom + p) * 2 + 1] += re * fi + im * fr;
+    }
   }
 }

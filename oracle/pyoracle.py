@@ -51,6 +51,8 @@ class Oracle:
         L.kso_deflate.argtypes = [_ip, _dp, _dp, C.c_double, C.c_int, _dp, _dp, C.c_int]
         L.kso_multicg.argtypes = [_ip, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_double, C.c_double, _dp]
+        L.kso_meson_mom.restype = None
+        L.kso_meson_mom.argtypes = [_ip, _dp, _dp, C.c_int, _ip, C.c_int, _ip, C.c_char_p, _dp]
 
     @staticmethod
     def _dims(dims):
@@ -79,6 +81,17 @@ class Oracle:
         self.lib.kso_deflate(self._dims(dims), dst, np.ascontiguousarray(src, np.float64), mass, ev.shape[0], ev,
                              np.ascontiguousarray(eigval, np.float64), parity)
         return dst
+
+    def meson_mom(self, dims, antiquark, quark, spin, r0, mom, mom_parity):
+        """kso_meson_mom (site loops of ks_meson_cont_mom, generic_ks/ks_meson_mom.c:160-437, one sink spin-taste
+        assignment): corr[t][p] complex.  spin = gamma bits of a local sink operator, -1 = none."""
+        mom = np.ascontiguousarray(mom, dtype=np.int32).reshape(-1, 3)
+        par = np.ascontiguousarray(mom_parity, dtype=np.int8).reshape(-1, 3)
+        out = np.zeros((int(dims[3]), mom.shape[0], 2))
+        self.lib.kso_meson_mom(self._dims(dims), np.ascontiguousarray(antiquark, np.float64),
+                               np.ascontiguousarray(quark, np.float64), int(spin), np.ascontiguousarray(r0, dtype=np.int32),
+                               mom.shape[0], mom, par.tobytes(), out)
+        return out[..., 0] + 1j * out[..., 1]
 
     def multicg(self, dims, fat, lng, src, offsets, parity, niter, nrestart, resid, relresid=0.0):
         offsets = np.ascontiguousarray(offsets, dtype=np.float64)
@@ -235,6 +248,13 @@ class MilcRef:
             L.milcref_inc_eigcg_init.argtypes = [C.c_int, C.c_int, C.c_int]
             L.milcref_inc_eigcg.argtypes = [rp, ro, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, _dp, C.POINTER(C.c_int)]
             L.milcref_eigcg_pairs.argtypes = [C.c_int, _dp, ro, C.c_void_p]
+        self.has_meson = hasattr(L, "milcref_meson_cont_mom")
+        if self.has_meson:
+            L.milcref_set_ape_links.argtypes = [rp]
+            L.milcref_spin_taste_index.argtypes = [C.c_char_p]
+            L.milcref_spin_taste_op.restype = None
+            L.milcref_spin_taste_op.argtypes = [C.c_int, _ip, ro, rp]
+            L.milcref_meson_cont_mom.argtypes = [rp, rp, C.c_int, _ip, C.c_char_p, C.c_int, _ip, _ip, _ip, _dp, _ip, C.c_int, _ip, _dp]
         self.dims = tuple(int(d) for d in dims)
         if L.milcref_init(*self.dims) != 0:
             raise RuntimeError("MilcRef: process already initialised with another geometry")
@@ -340,6 +360,35 @@ class MilcRef:
                                              np.ascontiguousarray(eps_naik, np.float64), eps, mom,
                                              fl.ctypes.data if want_links else None)
         return (mom, n, fl) if want_links else (mom, n)
+
+    # ---- meson tie-ups (generic_ks/ks_meson_mom.c, spin_taste_ops.c) ------------------------------------------
+    def set_ape_links(self, links):
+        """ks_spectrum's ape_links global: the links the one-link sink operators shift with."""
+        self.lib.milcref_set_ape_links(np.ascontiguousarray(links, self.dtype))
+
+    def spin_taste_index(self, label):
+        return self.lib.milcref_spin_taste_index(label.encode())
+
+    def spin_taste_op(self, index, r0, src):
+        """spin_taste_op_fn on the links of set_links."""
+        src = np.ascontiguousarray(src, self.dtype)
+        dest = np.zeros_like(src)
+        self.lib.milcref_spin_taste_op(int(index), np.ascontiguousarray(r0, dtype=np.int32), dest, src)
+        return dest
+
+    def meson_cont_mom(self, src1, src2, mom, mom_parity, spin_taste, p_index, phase, factor, corr_index, nprop, r0, prop=None):
+        """ks_meson_cont_mom: prop[m][t] (complex), accumulated onto `prop` when given.  Correlators with the same sink
+        operator must be consecutive (one group of the reference's corr_table each)."""
+        mom = np.ascontiguousarray(mom, dtype=np.int32).reshape(-1, 3)
+        par = np.ascontiguousarray(mom_parity, dtype=np.int8).reshape(-1, 3)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        out = np.zeros((nprop, self.dims[3], 2))
+        if prop is not None:
+            out[..., 0], out[..., 1] = prop.real, prop.imag
+        self.lib.milcref_meson_cont_mom(np.ascontiguousarray(src1, self.dtype), np.ascontiguousarray(src2, self.dtype),
+                                        mom.shape[0], mom, par.tobytes(), len(spin_taste), i32(spin_taste), i32(p_index),
+                                        i32(phase), np.ascontiguousarray(factor, np.float64), i32(corr_index), nprop, i32(r0), out)
+        return out[..., 0] + 1j * out[..., 1]
 
     # ---- eigCG (generic_ks/inc_eigcg.c) ---------------------------------------------------------------------
     def eigcg(self, src, dest, mass, parity, niter, nrestart, resid, m, nvecs):

@@ -63,5 +63,6 @@ EXTERN int n_order_naik_total;
 EXTERN int n_orders_naik[MAX_NAIK];
 EXTERN double *eigVal;
 EXTERN su3_vector **eigVec;
+EXTERN su3_matrix *ape_links;   /* spin_taste_ops.c (the *ape sink operators; unused here) */
 
 #endif /* _LATTICE_H */

@@ -190,3 +190,19 @@ int b200ks_unitarized_links(b200ks_ctx *c, const double *coeffs, const void *lin
   if (nsvd) *nsvd = 0;
   return 0;
 }
+
+/* meson tie-ups: corr[t][k] = (1000 spin + 10 t + k) + i (mx + 2 my + 4 mz + 0.125 (ex + ey + ez)) of momentum k */
+int b200ks_meson_mom(b200ks_ctx *c, const void *antiquark, const void *quark, int host_prec, int spin, const int *r0, int nmom,
+                     const int *mom, const char *mpar, double *corr) {
+  int t, k;
+  (void)c;
+  if (s_fail_next) { int f = s_fail_next; s_fail_next = 0; return f; }
+  logf_("meson_mom spin %d nmom %d r0 %d %d %d %d same %d prec %d\n", spin, nmom, r0[0], r0[1], r0[2], r0[3],
+        antiquark == quark, host_prec);
+  for (t = 0; t < s_dims[3]; t++)
+    for (k = 0; k < nmom; k++) {
+      corr[2 * (t * nmom + k)] = 1000.0 * spin + 10.0 * t + k;
+      corr[2 * (t * nmom + k) + 1] = mom[3 * k] + 2 * mom[3 * k + 1] + 4 * mom[3 * k + 2] + 0.125 * (mpar[3 * k] + mpar[3 * k + 1] + mpar[3 * k + 2]);
+    }
+  return 0;
+}

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) == bound, (set(declared) ^ bound)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.b200ks_version() == 120
+    assert lib.b200ks_version() == 121
 
 
 def test_no_cpu_fallback_without_gpu():

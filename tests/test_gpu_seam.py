@@ -314,6 +314,12 @@ def check_multi_gpu_context(oracle, ngpu, dims):
     back = np.zeros_like(src)
     ctx.vec_download(v, back)
     assert np.array_equal(back, src)
+    # meson tie-ups: every member contracts its sub-lattice, shares added on the host (time slices split in z too)
+    q = F.make_source(dims, seed=77, parity=EVENANDODD)
+    mom, par = [[0, 0, 0], [1, 0, 1], [0, 2, 1]], [[3, 3, 3], [2, 3, 1], [3, 1, 3]]
+    for spin in (15, 9, -1):
+        want = oracle.meson_mom(dims, src, q, spin, (1, 0, 2, 3), mom, par)
+        assert rel_err(ctx.meson_mom(src, q, spin, (1, 0, 2, 3), mom, par), want) <= 1e-13
     ctx.links_synthetic(4242)
     sf, sl_ = ctx.links_download()
     one = api.Context(dims)

@@ -207,3 +207,53 @@ def test_incremental_eigcg_bookkeeping(shim):
     assert log[0] == "eigcg_pairs 10" and val[3] == 0.004 and ep.H[3 + nmax * 3].real == 0.004 and ep.H[2 + nmax * 3].real == 0.0
     assert len([ln for ln in log if ln.startswith("eigcg_vec_download")]) == 10
     assert shim.b200ks_milc_total_iters() >= 3 * 41
+
+
+def test_meson_cont_mom_grouping_and_normalisation(shim):
+    """ks_meson_cont_mom_gpu around the device contraction (generic_ks/ks_meson_mom.c:160-437): one call per sink
+    spin-taste assignment with ITS momenta, local operators as gamma bits, norm_v's phase and factor, accumulation
+    into prop[corr_index][t]; a link-shift operator is refused outside a MILC tree (it needs spin_taste_op_fn)."""
+    class Cx(C.Structure):
+        _fields_ = [("real", C.c_double), ("imag", C.c_double)]
+    nt = DIMS[3]
+    rng = np.random.default_rng(3)
+    s1, s2 = rng.standard_normal((V, 3, 2)), rng.standard_normal((V, 3, 2))
+    mom = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 1]], dtype=np.int32)
+    par = np.array([[3, 3, 3], [2, 3, 3], [3, 1, 2]], dtype=np.int8)
+    pm = (C.POINTER(C.c_int) * 3)(*[mom[k].ctypes.data_as(C.POINTER(C.c_int)) for k in range(3)])
+    pp = (C.c_char_p * 3)(*[par[k].tobytes() for k in range(3)])
+    # correlators: pion5 (index 0) with momenta 0, 2; rhox0 (13) with momentum 1; G5-G5 (128 + 4*16 + 4) with 0
+    spin_taste = [0, 0, 13, 196]
+    p_index = [0, 2, 1, 0]
+    phase = [0, 1, 2, 3]
+    factor = [1.0, 2.0, 0.5, 4.0]
+    corr_index = [0, 1, 1, 0]
+    groups = [[0, 1], [2], [3]]
+    ct = (C.POINTER(C.c_int) * 3)(*[(C.c_int * len(g))(*g) for g in groups])
+    nprop = 2
+    rows = [(Cx * nt)() for _ in range(nprop)]
+    for m in range(nprop):
+        for t in range(nt):
+            rows[m][t].real, rows[m][t].imag = 0.25 * m, -1.0      # accumulated onto, not overwritten
+    prop = (C.POINTER(Cx) * nprop)(*[C.cast(r, C.POINTER(Cx)) for r in rows])
+    ia = lambda a: (C.c_int * len(a))(*a)
+    shim.ks_meson_cont_mom_gpu.restype = None
+    shim.ks_meson_cont_mom_gpu(prop, s1.ctypes.data_as(C.c_void_p), s2.ctypes.data_as(C.c_void_p), 3, pm, pp, 3, ia([2, 1, 1]), ct,
+                               ia(p_index), None, None, ia(spin_taste), ia(phase), (C.c_double * 4)(*factor), ia(corr_index),
+                               ia([1, 0, 1, 0]))
+    log = _log(shim)
+    calls = [ln for ln in log if ln.startswith("meson_mom")]
+    assert calls == ["meson_mom spin 15 nmom 2 r0 1 0 1 0 same 0 prec 2", "meson_mom spin 9 nmom 1 r0 1 0 1 0 same 0 prec 2",
+                     "meson_mom spin 15 nmom 1 r0 1 0 1 0 same 0 prec 2"]
+    want = np.zeros((nprop, nt), complex)
+    want[0] += 0.0 - 1j
+    want[1] += 0.25 - 1j
+    ph = [1, 1j, -1, -1j]
+    for g, spin in zip(groups, (15, 9, 15)):
+        for k, c in enumerate(g):
+            p = p_index[c]
+            im = mom[p, 0] + 2 * mom[p, 1] + 4 * mom[p, 2] + 0.125 * par[p].sum()
+            for t in range(nt):
+                want[corr_index[c], t] += ph[phase[c]] * factor[c] * complex(1000.0 * spin + 10.0 * t + k, im)
+    got = np.array([[complex(rows[m][t].real, rows[m][t].imag) for t in range(nt)] for m in range(nprop)])
+    assert np.allclose(got, want, rtol=0, atol=1e-12)
