@@ -1121,6 +1121,95 @@ def run_deflate(args):
     return 0
 
 
+def run_meson(args):
+    """Meson tie-ups (ks_meson_cont_mom's site loops, generic_ks/ks_meson_mom.c:160-437) on the configs[1] lattice:
+    two propagators -> nt x nmom complex numbers.  `value`: resident propagators (b200ks_meson_mom_dev; the call's wall
+    time includes the upload of the phase tables and the read-back of the result); `e2e`: host propagators in MILC's
+    layout through b200ks_meson_mom (2 x 100 MB up per call).  roofline: 96 B per site whatever the number of momenta.
+    cpu_baseline: the reference's own ks_meson_cont_mom (oracle/_ref, OpenMP) with the same momenta on a 16^3 x 32
+    sample, scaled by volume."""
+    import torch
+    from milc_qcd_b200 import api
+    local_rank = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local_rank)
+    dims = tuple(args.lattice) if args.lattice else DIMS
+    V = int(np.prod(dims))
+    nmom = max(1, min(args.nmom, 100))
+    rng = np.random.default_rng(3)
+    mom = rng.integers(-2, 3, size=(nmom, 3))
+    mom[0] = 0
+    par = np.full((nmom, 3), 3)
+    r0 = (0, 0, 0, 0)
+    ctx = api.Context(dims, device=local_rank)
+    va, vq = ctx.vec_create(), ctx.vec_create()
+    ctx.vec_gaussian(va, 3, 11)
+    ctx.vec_gaussian(vq, 3, 12)
+    stream = torch.cuda.ExternalStream(ctx.lib.b200ks_stream(ctx.h))
+    for _ in range(max(3, args.warmup)):
+        ctx.meson_mom_dev(va, vq, 15, r0, mom, par)
+    steps = max(5, args.steps)
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        corr = ctx.meson_mom_dev(va, vq, 15, r0, mom, par)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    launches = ctx.launch_count() - l0
+    # kernel time alone (CUDA events around the same calls include the host work between launches; keep both)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ctx.meson_mom_dev(va, vq, 15, r0, mom, par)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_dev = e0.elapsed_time(e1)
+    ha, hq = np.zeros((V, 3, 2)), np.zeros((V, 3, 2))
+    ctx.vec_download(va, ha)
+    ctx.vec_download(vq, hq)
+    ctx.meson_mom(ha, hq, 15, r0, mom, par)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        corr_h = ctx.meson_mom(ha, hq, 15, r0, mom, par)
+    ms_e2e = (time.perf_counter() - t0) / steps * 1e3
+    peak, peak_src = measured_peak()
+    alg = 96.0 * V
+    out = {"metric": "meson_tieup_site_momenta_per_s", "unit": "site-momenta/s", "n_gpus": 1, "higher_is_better": True,
+           "data": "synthetic", "value": V * nmom / (ms * 1e-3), "ms_per_step": ms, "ms_device_events": ms_dev, "steps": steps,
+           "dtype": "f64", "gpu_launches": int(launches),
+           "config": {"workload": "meson tie-up of two resident propagators, %s, %d momenta, local sink operator"
+                                  % ("x".join(map(str, dims)), nmom), "lattice": list(dims), "nmom": nmom},
+           "roofline": {"bound": "hbm", "achieved": alg / (ms_dev * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (ms_dev * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                        "note": "96 B per site (two colour vectors read once) over the event-timed call; FP64 issue takes "
+                                "over from HBM as the number of momenta grows"},
+           "e2e": {"value": V * nmom / (ms_e2e * 1e-3), "unit": "site-momenta/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": 2 * V * 48, "d2h_bytes_per_step": int(dims[3] * nmom * 16),
+                   "through": "b200ks_meson_mom on pageable host propagators in MILC's layout"},
+           "agreement_resident_vs_host": float(np.abs(corr - corr_h).max() / np.abs(corr).max()),
+           "device_bytes": ctx.device_bytes()}
+    ctx.close()
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import pyoracle
+            cores = omp_all_cores()
+            sdims = (16, 16, 16, 32)
+            Vs = int(np.prod(sdims))
+            with stdout_to_stderr():
+                ref = pyoracle.MilcRef(sdims, "_omp")
+                ref.set_ape_links(np.zeros((Vs, 4, 3, 3, 2)))
+                s1, s2 = rng.standard_normal((Vs, 3, 2)), rng.standard_normal((Vs, 3, 2))
+                idx = ref.spin_taste_index("pion5")
+                t0 = time.perf_counter()
+                ref.meson_cont_mom(s1, s2, mom, par, [idx] * nmom, list(range(nmom)), [0] * nmom, [1.0] * nmom, [0] * nmom, 1, r0)
+                t_cpu = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": Vs * nmom / t_cpu, "unit": "site-momenta/s", "cores": cores, "kind": "reference",
+                                   "sample": "ks_meson_cont_mom (oracle/_ref, -DOMP) with the same %d momenta on a 16^3x32 lattice" % nmom}
+        except Exception as ex:
+            out["cpu_baseline"] = {"value": None, "kind": "unavailable", "sample": repr(ex)}
+    print(json.dumps(out))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -1137,7 +1226,8 @@ def main():
                     help="skip the strong-scaling anchor, the multi-shift summary and the 96^3x192 point")
     ap.add_argument("--lattice", type=int, nargs=4, default=None, help="override the lattice (nx ny nz nt)")
     ap.add_argument("--nvecs", type=int, default=64, help="--workload deflate: number of resident vectors")
-    ap.add_argument("--workload", default="cg", choices=["cg", "multishift", "block", "links", "force", "deflate"],
+    ap.add_argument("--nmom", type=int, default=20, help="--workload meson: number of momenta")
+    ap.add_argument("--workload", default="cg", choices=["cg", "multishift", "block", "links", "force", "deflate", "meson"],
                     help="cg (default, the driver's line): single-mass CG; multishift: BASELINE configs[2]; "
                          "block: multi-right-hand-side CG (ks_congrad_block_parity seam); "
                          "links: HISQ fermion-link construction (qudaLoadUnitarizedLink / qudaLoadKSLink seam)")
@@ -1159,6 +1249,8 @@ def main():
         return run_force(args)
     if args.workload == "deflate":
         return run_deflate(args)
+    if args.workload == "meson":
+        return run_meson(args)
     return run_b200(args)
 
 
