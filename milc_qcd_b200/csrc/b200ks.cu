@@ -123,6 +123,7 @@ struct b200ks_ctx {
                                         // operations that do not run partitioned yet (links, force)
   int member_rank = -1;                 // >= 0: member of a multi-GPU context
   double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // b200ks_call_profile
+  bool pdl = true;                      // programmatic dependent launch in the solver loops (B200KS_PDL)
   void *eigcg = nullptr;                // EigCGState (eigcg.inl): search window + accumulated low modes in HBM
 };
 
@@ -594,6 +595,7 @@ static b200ks_ctx *create_common(const int latsize[4], const int local[4], const
     return nullptr;
   }
   memset(c->h_state, 0, sizeof(CgState) * kMaxRhs);
+  c->pdl = !(getenv("B200KS_PDL") && atoi(getenv("B200KS_PDL")) == 0);
   return c;
 }
 
@@ -709,6 +711,30 @@ extern "C" int b200ks_num_gpus(b200ks_ctx *c) { return c ? nmembers(c) : 0; }
     kern<<<(grid), kBlock, 0, (c)->stream>>>(__VA_ARGS__);               \
     (c)->launches++;                                                     \
   } while (0)
+// Solver-loop kernels that open with pdl_wait() (common.cuh): launched with programmatic stream serialisation on
+// unpartitioned contexts, so that the launch latency and the ramp of each of the five kernel boundaries of a CG
+// iteration overlap the tail of the kernel before (B200KS_PDL=0: ordinary launches, for A/B measurements).
+template <typename... KArgs, typename... Args>
+static inline void launch_k(b200ks_ctx *c, void (*kern)(KArgs...), int grid, int block, Args &&...args) {
+  if (c->pdl && !c->comm.active) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at;
+    memset(&at, 0, sizeof(at));
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  } else {
+    kern<<<grid, block, 0, c->stream>>>(args...);
+  }
+  c->launches++;
+}
+#define LAUNCHP(c, kern, grid, ...) launch_k((c), kern, (grid), kBlock, __VA_ARGS__)
 #define LAUNCH1(c, kern, ...)                                            \
   do {                                                                   \
     kern<<<1, 1, 0, (c)->stream>>>(__VA_ARGS__);                         \
@@ -739,7 +765,7 @@ static bool p2p_reductions(const b200ks_ctx *c) { return c->comm.active && c->co
 
 static void launch_finish(b200ks_ctx *c, const FinishArg &a, int nslots, bool comm = false) {
   if (comm && c->comm.nranks > 1) reduce_finish_kernel<true><<<1, kFinishThreads, 0, c->stream>>>(a, red_comm(c));
-  else reduce_finish_kernel<false><<<nslots, kFinishThreads, 0, c->stream>>>(a, RedComm());
+  else { launch_k(c, reduce_finish_kernel<false>, nslots, kFinishThreads, a, RedComm()); return; }
   c->launches++;
 }
 static FinishSlot finish_slot(const double *partials, int stride, int nval, double *out, CgState *st, const int *stop) {
@@ -1300,13 +1326,13 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
 #define DSLASH_LAUNCH(kMode, grid_)                                                        \
   do {                                                                                     \
     if (z7) {                                                                              \
-      if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, kMode, 7>), grid_, a);               \
-      else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, kMode, 7>), grid_, a);          \
-      else LAUNCH(c, (dslash_kernel<T, 2, kMode, 7>), grid_, a);                           \
+      if (e.kind == 0) LAUNCHP(c, (dslash_kernel<T, 0, kMode, 7>), grid_, a);              \
+      else if (e.kind == 1) LAUNCHP(c, (dslash_kernel<T, 1, kMode, 7>), grid_, a);         \
+      else LAUNCHP(c, (dslash_kernel<T, 2, kMode, 7>), grid_, a);                          \
     } else {                                                                               \
-      if (e.kind == 0) LAUNCH(c, (dslash_kernel<T, 0, kMode, 9>), grid_, a);               \
-      else if (e.kind == 1) LAUNCH(c, (dslash_kernel<T, 1, kMode, 9>), grid_, a);          \
-      else LAUNCH(c, (dslash_kernel<T, 2, kMode, 9>), grid_, a);                           \
+      if (e.kind == 0) LAUNCHP(c, (dslash_kernel<T, 0, kMode, 9>), grid_, a);              \
+      else if (e.kind == 1) LAUNCHP(c, (dslash_kernel<T, 1, kMode, 9>), grid_, a);         \
+      else LAUNCHP(c, (dslash_kernel<T, 2, kMode, 9>), grid_, a);                          \
     }                                                                                      \
   } while (0)
   if (!c->comm.active) {
@@ -1375,11 +1401,11 @@ static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *o
 #define DSLASH_H_LAUNCH(kMode, grid_)                                                       \
   do {                                                                                      \
     if (z7) {                                                                               \
-      if (kind == 0) LAUNCH(c, (dslash_half_kernel<0, kMode, 7>), grid_, a);                \
-      else LAUNCH(c, (dslash_half_kernel<2, kMode, 7>), grid_, a);                          \
+      if (kind == 0) LAUNCHP(c, (dslash_half_kernel<0, kMode, 7>), grid_, a);               \
+      else LAUNCHP(c, (dslash_half_kernel<2, kMode, 7>), grid_, a);                         \
     } else {                                                                                \
-      if (kind == 0) LAUNCH(c, (dslash_half_kernel<0, kMode, 9>), grid_, a);                \
-      else LAUNCH(c, (dslash_half_kernel<2, kMode, 9>), grid_, a);                          \
+      if (kind == 0) LAUNCHP(c, (dslash_half_kernel<0, kMode, 9>), grid_, a);               \
+      else LAUNCHP(c, (dslash_half_kernel<2, kMode, 9>), grid_, a);                         \
     }                                                                                       \
   } while (0)
   if (!c->comm.active) {
@@ -1810,10 +1836,10 @@ static int congrad_T(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, con
         CHK(allreduce(c, c->d_state->red, rel ? 3 : 5));
       }
       if (rel)
-        LAUNCH(c, (cg_update_kernel<T, true>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
+        LAUNCHP(c, (cg_update_kernel<T, true>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
                g.stride, g.Vh, c->d_state, c->ws, fuse);
       else
-        LAUNCH(c, (cg_update_kernel<T, false>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
+        LAUNCHP(c, (cg_update_kernel<T, false>), grid, (T2 *)x.p[pb], (T2 *)r->p[pb], (T2 *)p->p[pb], (const T2 *)ttt->p[pb],
                g.stride, g.Vh, c->d_state, c->ws, fuse);
       if (fuse & 8) finish_update(c, grid, c->d_state, fuse);
       if (!fuse) {   // the relative residual needs its own all-reduce before the scalar step
@@ -1964,10 +1990,10 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
       }
       const int fuse = 1 | 4 | ((!multi || p2p) ? 8 : 0);
       if (half)
-        LAUNCH(c, cg_update_half_kernel, grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (uint4 *)p_h->p[pb],
+        LAUNCHP(c, cg_update_half_kernel, grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (uint4 *)p_h->p[pb],
                (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse);
       else
-        LAUNCH(c, (cg_update_kernel<float, false>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
+        LAUNCHP(c, (cg_update_kernel<float, false>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
                (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse);
       if (fuse & 8) finish_update(c, grid, c->d_state, fuse);
       return 0;

@@ -266,6 +266,8 @@ constexpr int kFinishThreads = 1024;
 // ranks before they are stored (one slot per launch).
 template <bool kComm>
 __global__ void __launch_bounds__(kFinishThreads) reduce_finish_kernel(const FinishArg a, const RedComm rc) {
+  pdl_launch_dependents();
+  pdl_wait();
   const FinishSlot &f = a.s[blockIdx.x];
   if (f.stop != nullptr && *f.stop) return;
   __shared__ double sm[3][kFinishThreads / 32];
@@ -326,6 +328,8 @@ __global__ void __launch_bounds__(kBlock)
 cg_update_kernel(typename Vec2<T>::type *x, typename Vec2<T>::type *r, typename Vec2<T>::type *p,
                  const typename Vec2<T>::type *ttt, int stride, int n, CgState *st, ReduceWs ws, int fuse_scalar) {
   using T2 = typename Vec2<T>::type;
+  pdl_launch_dependents();
+  pdl_wait();
   if (st->stop) return;
   const double rsq = st->rsq, oldrsq = st->upd[0];
   const double pkp = st->red[0], c_tr = st->red[1], c_tt = st->red[2];

@@ -63,6 +63,16 @@ struct Geom {
   FastDiv dS2, dZi;
 };
 
+// Programmatic dependent launch (sm_90+).  A kernel launched with the programmatic-stream-serialisation attribute
+// (b200ks.cu launch_k) may be scheduled while its predecessor in the stream is still draining: its CTAs become resident
+// as slots free up and stop at pdl_wait() until the predecessor grid has completed and its writes are visible.  What
+// that buys the solver loops is the launch latency and the ramp of every kernel boundary (five per CG iteration).
+// pdl_launch_dependents() at the top of a kernel lets ITS successor be scheduled as soon as all of this kernel's CTAs
+// have started.  Both are no-ops for a kernel launched the ordinary way.  Rule: nothing that reads or writes global
+// memory may precede pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct Coord { int x, y, z, t, xh; };
 
 // cb index -> local coordinates, for a site of the given local parity bit (0 even, 1 odd).

@@ -228,6 +228,8 @@ __device__ __forceinline__ void dslash_site(const DslashArg<T> &a, int idx, doub
 template <typename T, int kEpi, int kMode, int kNc>
 __global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? 5 : 8) dslash_kernel(const DslashArg<T> a) {
   using T2 = typename Vec2<T>::type;
+  pdl_launch_dependents();
+  pdl_wait();
   if (a.stop != nullptr && *a.stop) return;
   int k = blockIdx.x * kBlock + threadIdx.x;
   bool active = k < a.nsites;

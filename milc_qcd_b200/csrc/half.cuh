@@ -283,6 +283,8 @@ __device__ __forceinline__ void half_site(const DslashHArg &a, int idx, double (
 #endif
 template <int kEpi, int kMode, int kNc>
 __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_kernel(const DslashHArg a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (a.stop != nullptr && *a.stop) return;
   int k = blockIdx.x * kBlock + threadIdx.x;
   bool active = k < a.nsites;
@@ -320,6 +322,8 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
 __global__ void __launch_bounds__(kBlock)
 cg_update_half_kernel(float2 *x, float2 *r, uint4 *p_h, const float2 *ttt, int stride, int n, CgState *st, ReduceWs ws,
                       int fuse_scalar) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (st->stop) return;
   const double rsq = st->rsq, oldrsq = st->upd[0];
   const double pkp = st->red[0], c_tr = st->red[1], c_tt = st->red[2];
