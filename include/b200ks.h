@@ -61,7 +61,8 @@ typedef struct {
   int max_iter;        /* iterations per restart (qic->max)                          */
   int nrestart;        /* max restarts (qic->nrestart)                               */
   double resid;        /* target sqrt(|r|^2/|b|^2), NOT squared (qic->resid)         */
-  double relresid;     /* Fermilab relative residual target, 0 = unused              */
+  double relresid;     /* Fermilab relative residual target, 0 = unused (d_congrad5_fn_milc.c:37-56; with
+                          mixed_precision != 0 on a partitioned context the solve runs in pure double) */
   int mixed_precision; /* 0 pure double; 1 double solution/true residuals + single-precision
                           Krylov vectors (HALF_MIXED); 2 additionally 16-bit links and search
                           direction in the stencil (MAX_MIXED); both with reliable updates    */

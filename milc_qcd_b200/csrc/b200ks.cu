@@ -1885,7 +1885,12 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
   const bool multi = c->comm.active;
   const int batch = args.check_interval > 0 ? args.check_interval : 8;
   const double delta = 0.1;
-  if (args.relresid != 0) return fail(B200KS_EINVAL, "mixed precision: Fermilab relative residual not supported");
+  // Fermilab relative residual (d_congrad5_fn_milc.c:37-56,177-179,217-237): the sum over sites of |r_s|^2/|x_s|^2 needs
+  // the whole solution, x = x(double) + x_lo, in every update sweep (CgState::xrel: +48 B per site and iteration); the
+  // true values come with every reliable update.  Unpartitioned contexts (congrad_any sends the rest to the pure solver).
+  const bool rel = args.relresid != 0;
+  const double relrsqmin = args.relresid * args.relresid;
+  if (rel && multi) return fail(B200KS_EINVAL, "mixed precision: Fermilab relative residual on partitioned contexts not supported");
 
   res = b200ks_invert_result();
   res.converged = 1;
@@ -1914,8 +1919,10 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
   memset(&h, 0, sizeof(h));
   h.source_norm = source_norm;
   h.rsqmin = rsqmin;
+  h.relrsqmin = relrsqmin;
   h.size_relr = 1.0;
   h.niter = niter;
+  h.xrel = rel ? (const double2 *)x.p[pb] : nullptr;
   h.delta2 = delta * delta;
   h.half_volume = 0.5 * (double)c->global[0] * c->global[1] * c->global[2] * c->global[3];
 
@@ -1931,18 +1938,23 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
     CHK(dslash_T<double>(c, *ttt_d, *ttt_d, pb, e1));
     if (half)
       LAUNCH(c, mixed_reliable_half_kernel, grid, (const double2 *)b.p[pb], (const double2 *)ttt_d->p[pb], (float2 *)r_lo->p[pb],
-             (uint4 *)p_h->p[pb], g.stride, g.Vh, first ? 1 : 0, c->ws, c->d_scal);
+             (uint4 *)p_h->p[pb], g.stride, g.Vh, first ? 1 : 0, c->ws, c->d_scal, h.xrel);
     else
       LAUNCH(c, mixed_reliable_kernel, grid, (const double2 *)b.p[pb], (const double2 *)ttt_d->p[pb], (float2 *)r_lo->p[pb],
-             (float2 *)p_lo->p[pb], g.stride, g.Vh, first ? 1 : 0, c->ws, c->d_scal);
+             (float2 *)p_lo->p[pb], g.stride, g.Vh, first ? 1 : 0, c->ws, c->d_scal, h.xrel);
     CHK(allreduce(c, c->d_scal, 2));
     CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CHK(check_launch("mixed reliable update"));
     const double rsq = c->h_scal[0];
     res.final_rsq = rsq / source_norm;
+    if (rel) res.final_relrsq = sqrt(c->h_scal[1] / h.half_volume);
     iteration++;
-    const bool hit = (rsqmin <= 0 || rsqmin > res.final_rsq);
+    static const bool trace = getenv("B200KS_TRACE") && atoi(getenv("B200KS_TRACE")) != 0;
+    if (trace && c->comm.rank == 0)   // one line per reliable update (diagnostics)
+      fprintf(stderr, "b200ks mixed cg: %s inner, iteration %d, reliable update %d, true |r|^2/|b|^2 %.3e\n",
+              half ? "16-bit" : "single", iteration, nupdates, res.final_rsq);
+    const bool hit = (rsqmin <= 0 || rsqmin > res.final_rsq) && (relrsqmin <= 0 || relrsqmin > res.final_relrsq);
     if (iteration >= max_cg || hit) break;
     nupdates++;
     if (half) {
@@ -1968,6 +1980,7 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
     h.reliable = 0;
     h.iter = iteration;
     h.stop = 0;
+    if (rel) h.size_relr = res.final_relrsq;
     CHK(state_push(c));
     CHK(run_batches(c, batch, "mixed cg iterate", [&]() -> int {
       const bool p2p = p2p_reductions(c);
@@ -1988,9 +2001,12 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
         LAUNCH1(c, combine_red_kernel, c->d_state, 3);
         CHK(allreduce(c, c->d_state->red, 5));
       }
-      const int fuse = 1 | 4 | ((!multi || p2p) ? 8 : 0);
+      const int fuse = 1 | (rel ? 2 : 0) | 4 | ((!multi || p2p) ? 8 : 0);
       if (half)
         LAUNCHP(c, cg_update_half_kernel, grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (uint4 *)p_h->p[pb],
+               (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse);
+      else if (rel)
+        LAUNCHP(c, (cg_update_kernel<float, true>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
                (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse);
       else
         LAUNCHP(c, (cg_update_kernel<float, false>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
@@ -2007,11 +2023,12 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
       g1.kind = 1; g1.s = -msq_x4; g1.w = &x;
       CHK(dslash_T<double>(c, *ttt_d, *ttt_d, pb, g1));
       LAUNCH(c, mixed_reliable_kernel, grid, (const double2 *)b.p[pb], (const double2 *)ttt_d->p[pb], (float2 *)r_lo->p[pb],
-             (float2 *)p_lo->p[pb], g.stride, g.Vh, 1, c->ws, c->d_scal);   // (p_lo is scratch here)
+             (float2 *)p_lo->p[pb], g.stride, g.Vh, 1, c->ws, c->d_scal, h.xrel);   // (p_lo is scratch here)
       CHK(allreduce(c, c->d_scal, 2));
       CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       CU(cudaStreamSynchronize(c->stream));
       res.final_rsq = c->h_scal[0] / source_norm;
+      if (rel) res.final_relrsq = sqrt(c->h_scal[1] / h.half_volume);
       break;
     }
   }
@@ -2022,7 +2039,7 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
   res.device_seconds = ms * 1e-3;
   res.final_iters = iteration;
   res.final_restart = nupdates;
-  res.converged = (rsqmin <= 0 || rsqmin > res.final_rsq) ? 1 : 0;
+  res.converged = ((rsqmin <= 0 || rsqmin > res.final_rsq) && (relrsqmin <= 0 || relrsqmin > res.final_relrsq)) ? 1 : 0;
   return iteration;
 }
 
@@ -2039,7 +2056,8 @@ static int congrad_any(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass, c
   CHK(links_ensure(c, 2));
   // mixed_precision 1: single-precision inner iteration; 2: 16-bit stencil operands (needs
   // peer-to-peer halos when the lattice is partitioned, else it runs as 1)
-  if (args.mixed_precision != 0 && args.relresid == 0) {
+  // (the Fermilab relative residual in the mixed solvers: unpartitioned contexts; otherwise the pure-double solver)
+  if (args.mixed_precision != 0 && (args.relresid == 0 || !c->comm.active)) {
     const bool half = args.mixed_precision >= 2 && (!c->comm.active || c->comm.p2p.on);
     return congrad_mixed(c, b, x, mass, args, res, half);
   }
@@ -2360,7 +2378,8 @@ static int congrad_block_mixed(b200ks_ctx *c, int n, BlockRhs *rhs, double mass,
       e1.kind = 1; e1.s = -msq_x4; e1.w = rhs[k].x;
       CHK(dslash_T<double>(c, *ttt_d, *ttt_d, pb, e1));
       LAUNCH(c, mixed_reliable_kernel, grid, (const double2 *)rhs[k].b->p[pb], (const double2 *)ttt_d->p[pb],
-             (float2 *)rhs[k].r->p[pb], (float2 *)rhs[k].p->p[pb], g.stride, g.Vh, rhs[k].first ? 1 : 0, c->ws, c->d_scal + 2 * k);
+             (float2 *)rhs[k].r->p[pb], (float2 *)rhs[k].p->p[pb], g.stride, g.Vh, rhs[k].first ? 1 : 0, c->ws, c->d_scal + 2 * k,
+             (const double2 *)nullptr);
       rhs[k].first = false;
     }
     CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * kMaxRhs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

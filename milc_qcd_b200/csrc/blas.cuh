@@ -42,6 +42,8 @@ struct CgState {
   double delta2;       // reliable-update threshold squared
   int reliable;        // 1 => host must perform a reliable update
   int pad_;
+  const double2 *xrel; // mixed solvers with the Fermilab relative residue: the double part of the solution
+                       // (x = xrel + x_lo enters sum |r_s|^2/|x_s|^2); nullptr otherwise
   // multi-shift: per-shift freeze.  The residual of shift j is zeta_j * r, so once
   // zeta_j^2 |r|^2 <= freeze * rsqstop the shift is finished and its two vectors drop out of
   // the update sweep (freeze = 0: never -- the reference iterates every shift to the end,
@@ -337,9 +339,11 @@ cg_update_kernel(typename Vec2<T>::type *x, typename Vec2<T>::type *r, typename 
   const double rsq_new = oldrsq + 2.0 * (double)a * c_tr + (double)a * (double)a * c_tt;
   const T bb = (T)(rsq_new / oldrsq);
   const int i = blockIdx.x * kBlock + threadIdx.x;
+  const double2 *xrel = kRel ? st->xrel : nullptr;
   double s[2] = {0, 0};
   if (i < n) {
     T rn = 0, xn = 0;   // per-site sums in the working precision, summed over sites in double
+    double xn2 = 0;     // mixed solvers: |x_double + x_lo|^2
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       const size_t o = (size_t)c * stride + i;
@@ -355,10 +359,21 @@ cg_update_kernel(typename Vec2<T>::type *x, typename Vec2<T>::type *r, typename 
       r[o] = rv;
       p[o] = pv;
       rn = fma(rv.x, rv.x, fma(rv.y, rv.y, rn));
-      if (kRel) xn = fma(xv.x, xv.x, fma(xv.y, xv.y, xn));
+      if (kRel) {
+        if (xrel != nullptr) {
+          const double2 xd = xrel[o];
+          const double tx = xd.x + (double)xv.x, ty = xd.y + (double)xv.y;
+          xn2 += tx * tx + ty * ty;
+        } else {
+          xn = fma(xv.x, xv.x, fma(xv.y, xv.y, xn));
+        }
+      }
     }
     s[0] = rn;
-    if (kRel) s[1] = (xn == 0) ? 1.0 : (double)rn / (double)xn;
+    if (kRel) {
+      if (xrel != nullptr) s[1] = (xn2 == 0) ? 1.0 : (double)rn / xn2;
+      else s[1] = (xn == 0) ? 1.0 : (double)rn / (double)xn;
+    }
   }
   // safe although other CTAs read st->upd at their start: the last ticket is taken only
   // after every CTA has passed that read.  For the same reason the CTA that writes the totals
@@ -406,10 +421,11 @@ mixed_accumulate_kernel(double2 *x, float2 *x_lo, int stride, int n) {
 // first != 0: start of the solve, p = r.
 __global__ void __launch_bounds__(kBlock)
 mixed_reliable_kernel(const double2 *b, const double2 *ttt, float2 *r_lo, float2 *p_lo, int stride, int n,
-                      int first, ReduceWs ws, double *out) {
+                      int first, ReduceWs ws, double *out, const double2 *xrel) {
   const int i = blockIdx.x * kBlock + threadIdx.x;
   double s[2] = {0, 0};
   if (i < n) {
+    double num = 0, den = 0;   // xrel != nullptr: the Fermilab relative residue of the TRUE residual (d_congrad5_fn_milc.c:37-56)
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       const size_t o = (size_t)c * stride + i;
@@ -427,7 +443,13 @@ mixed_reliable_kernel(const double2 *b, const double2 *ttt, float2 *r_lo, float2
         p_lo[o] = pv;
       }
       s[0] += rx * rx + ry * ry;
+      if (xrel != nullptr) {
+        const double2 xv = xrel[o];
+        num += rx * rx + ry * ry;
+        den += xv.x * xv.x + xv.y * xv.y;
+      }
     }
+    if (xrel != nullptr) s[1] = (den == 0) ? 1.0 : num / den;
   }
   grid_reduce<2>(s, ws, out);
 }

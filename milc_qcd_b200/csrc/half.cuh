@@ -331,12 +331,14 @@ cg_update_half_kernel(float2 *x, float2 *r, uint4 *p_h, const float2 *ttt, int s
   const double rsq_new = oldrsq + 2.0 * (double)a * c_tr + (double)a * (double)a * c_tt;
   const float bb = (float)(rsq_new / oldrsq);
   const int i = blockIdx.x * kBlock + threadIdx.x;
+  const double2 *xrel = (fuse_scalar & 2) ? st->xrel : nullptr;   // Fermilab relative residue wanted (CgState::xrel)
   double s[2] = {0, 0};
   if (i < n) {
     float2 pv[3];
     load_vec_h(p_h, i, pv);
     float pn[6];
     float rn = 0.f;
+    double xn2 = 0;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       const size_t o = (size_t)c * stride + i;
@@ -351,9 +353,15 @@ cg_update_half_kernel(float2 *x, float2 *r, uint4 *p_h, const float2 *ttt, int s
       x[o] = xv;
       r[o] = rv;
       rn = fmaf(rv.x, rv.x, fmaf(rv.y, rv.y, rn));
+      if (xrel != nullptr) {
+        const double2 xd = xrel[o];
+        const double tx = xd.x + (double)xv.x, ty = xd.y + (double)xv.y;
+        xn2 += tx * tx + ty * ty;
+      }
     }
     store_vec_h(p_h, i, pn);
     s[0] = rn;
+    if (xrel != nullptr) s[1] = (xn2 == 0) ? 1.0 : (double)rn / xn2;
   }
   if (fuse_scalar & 8) {   // two-stage: reduce_finish_kernel sums the partials and advances the recurrence
     block_partials<2>(s, ws.partials);
@@ -366,13 +374,14 @@ cg_update_half_kernel(float2 *x, float2 *r, uint4 *p_h, const float2 *ttt, int s
 // Reliable update with a half search direction (see mixed_reliable_kernel in blas.cuh).
 __global__ void __launch_bounds__(kBlock)
 mixed_reliable_half_kernel(const double2 *b, const double2 *ttt, float2 *r_lo, uint4 *p_h, int stride, int n, int first,
-                           ReduceWs ws, double *out) {
+                           ReduceWs ws, double *out, const double2 *xrel) {
   const int i = blockIdx.x * kBlock + threadIdx.x;
   double s[2] = {0, 0};
   if (i < n) {
     float2 pv[3];
     if (!first) load_vec_h(p_h, i, pv);
     float pn[6];
+    double num = 0, den = 0;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       const size_t o = (size_t)c * stride + i;
@@ -384,8 +393,14 @@ mixed_reliable_half_kernel(const double2 *b, const double2 *ttt, float2 *r_lo, u
       pn[2 * c] = first ? rn.x : pv[c].x + (rn.x - ro.x);
       pn[2 * c + 1] = first ? rn.y : pv[c].y + (rn.y - ro.y);
       s[0] += rx * rx + ry * ry;
+      if (xrel != nullptr) {
+        const double2 xv = xrel[o];
+        num += rx * rx + ry * ry;
+        den += xv.x * xv.x + xv.y * xv.y;
+      }
     }
     store_vec_h(p_h, i, pn);
+    if (xrel != nullptr) s[1] = (den == 0) ? 1.0 : num / den;
   }
   grid_reduce<2>(s, ws, out);
 }

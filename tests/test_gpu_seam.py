@@ -198,6 +198,16 @@ def test_fermilab_relative_residual_single_gpu(oracle, dims, parity):
         assert 0.5 < res["final_relrsq"] / qo["final_relrsq"] < 2.0
         assert res["final_relrsq"] < relresid ** 2 or res["final_relrsq"] < relresid
         assert np.linalg.norm(x[sl] - xo[sl]) <= 1e-2 * max(resid, relresid) / (4 * 0.05 ** 2) * np.linalg.norm(xo[sl]) + 1e-7 * np.linalg.norm(xo[sl])
+        # the mixed solvers (single-precision / 16-bit inner iteration): same stopping rule on the TRUE double residuals
+        # of the reliable updates, the relative residue of the recursion from x(double) + x(inner)
+        for mixed in (1, 2):
+            xm = np.zeros_like(b)
+            itm, resm = ctx.congrad(b, xm, 0.05, parity, 500, 5, resid, relresid=relresid, mixed_precision=mixed)
+            assert resm["converged"] == 1, (mixed, resid, relresid, resm)
+            assert resm["final_relrsq"] < relresid ** 2 and (resid == 0 or resm["final_rsq"] < resid ** 2)
+            assert itm <= (1.5 if mixed == 1 else 3.0) * ito + 10, (mixed, itm, ito)
+            assert np.linalg.norm(xm[sl] - xo[sl]) <= 1e-2 * max(resid, relresid) / (4 * 0.05 ** 2) * np.linalg.norm(xo[sl]) + 1e-7 * np.linalg.norm(xo[sl])
+            assert np.all(xm[other] == 0)
     ctx.close()
 
 
