@@ -1259,6 +1259,32 @@ static int halo_push(b200ks_ctx *c, const DevVec &in, int pin, const int *stop) 
   return 0;
 }
 
+// Fused push (dslash.cuh push_site_h): the kernel launched next on the compute stream PRODUCES `vec` (parity half
+// `pin`, 16-bit) and stores its boundary sites into the neighbours' ghost buffers as exchange ++seq; the stencil that
+// reads `vec` next finds the exchange under way (P2P::fused_ptr) and launches no push kernel.
+static void fused_push_arg(b200ks_ctx *c, const void *vec, PushArg &a) {
+  const Geom &g = c->g;
+  P2P &pp = c->comm.p2p;
+  pp.seq++;
+  memset(&a, 0, sizeof(a));
+  for (int d = 2; d < 4; d++) {
+    if (!g.part[d]) continue;
+    for (int side = 0; side < 2; side++) {
+      char *peer = pp.peer_block[d - 2][side];
+      a.dst[d - 2][side] = p2p_ghost(pp, peer, pp.seq);
+      a.flag[d - 2][side] = p2p_flags(peer) + (d - 2) * 2 + (side ? 0 : 1);
+    }
+  }
+  a.seq = pp.seq;
+  a.ticket = pp.ticket + 1;
+  a.stop = nullptr;
+  pp.fused_ptr = vec;
+}
+static bool fused_push_wanted(const b200ks_ctx *c) {
+  static const bool off = getenv("B200KS_FUSED_PUSH") && atoi(getenv("B200KS_FUSED_PUSH")) == 0;
+  return !off && c->comm.active && c->comm.p2p.on;
+}
+
 template <typename T>
 static int halo_start(b200ks_ctx *c, const DevVec &in, int pin, const int *stop) {
   using T2 = typename Vec2<T>::type;
@@ -1372,7 +1398,8 @@ static int dslash_T(b200ks_ctx *c, const DevVec &in, DevVec &out, int par_out, c
 // 16-bit stencil (half.cuh).  kind 0: out_h (half) = D in.  kind 2: out_f (float) = D in + s*w_h
 // with the three fused dot products against w_h (half) and r (float).
 static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *out_f, int par_out, int kind, double s_,
-                       const DevVec *w_h, const DevVec *r, double *red, const int *stop, double *extra = nullptr, int nextra = 0) {
+                       const DevVec *w_h, const DevVec *r, double *red, const int *stop, double *extra = nullptr, int nextra = 0,
+                       bool push_out = false) {
   const Links &L = c->links[0];
   DslashHArg a;
   memset(&a, 0, sizeof(a));
@@ -1414,16 +1441,23 @@ static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *o
     return 0;
   }
   if (!c->comm.p2p.on) return fail(B200KS_ESTATE, "16-bit stencil needs the peer-to-peer halo path");
-  CHK((halo_push<uint4, 1, false>(c, in, par_out ^ 1, stop)));
   P2P &pp = c->comm.p2p;
+  // the halo of `in`: already on its way if the kernel that produced `in` pushed it (fused), else a push kernel
+  const bool in_pushed = pp.fused_ptr != nullptr && pp.fused_ptr == in.p[par_out ^ 1];
+  pp.fused_ptr = nullptr;
+  if (!in_pushed) CHK((halo_push<uint4, 1, false>(c, in, par_out ^ 1, stop)));
   a.gin = (const uint4 *)p2p_ghost(pp, pp.block, pp.seq);
   a.halo_flags = p2p_flags(pp.block);
   a.halo_seq = pp.seq;
   a.halo_mask = (c->g.part[2] ? 3 : 0) | (c->g.part[3] ? 12 : 0);
   a.halo_err = pp.err;
   a.red = nullptr;   // two-stage reduction, see dslash_T
+  if (push_out && kind == 0 && out_h != nullptr && nblocks(c->comm.n_ext) > 0 && fused_push_wanted(c)) {
+    fused_push_arg(c, out_h->p[par_out], a.push);   // (the OUTPUT's exchange: ++seq after the input's was read above)
+    a.push_on = 1;
+  }
   DSLASH_H_LAUNCH(1, a.nb_int + nblocks(c->comm.n_ext));
-  CU(cudaStreamWaitEvent(c->stream, c->comm.ev_done, 0));
+  if (!in_pushed) CU(cudaStreamWaitEvent(c->stream, c->comm.ev_done, 0));
   if (kind == 2) finish_dots(c, a.nb_int + nblocks(c->comm.n_ext), red, stop, extra, nextra);
 #undef DSLASH_H_LAUNCH
   return 0;
@@ -1931,6 +1965,7 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
   CU(cudaEventRecord(c->ev0, c->stream));
   for (bool first = true;; first = false) {
     // reliable update = true residual in double
+    c->comm.p2p.fused_ptr = nullptr;   // (the reliable kernel rewrites the search direction: a halo pushed by the last update is stale)
     if (!first) LAUNCH(c, mixed_accumulate_kernel, grid, (double2 *)x.p[pb], (float2 *)x_lo->p[pb], g.stride, g.Vh);
     Epi e0, e1;
     CHK(dslash_T<double>(c, x, *ttt_d, ob, e0));
@@ -1985,7 +2020,7 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
     CHK(run_batches(c, batch, "mixed cg iterate", [&]() -> int {
       const bool p2p = p2p_reductions(c);
       if (half) {
-        CHK(dslash_half(c, *p_h, t_h, nullptr, ob, 0, 0.0, nullptr, nullptr, nullptr, &c->d_state->stop));
+        CHK(dslash_half(c, *p_h, t_h, nullptr, ob, 0, 0.0, nullptr, nullptr, nullptr, &c->d_state->stop, nullptr, 0, true));
         CHK(dslash_half(c, *t_h, nullptr, ttt_lo, pb, 2, -msq_x4, p_h, r_lo, c->d_state->red, &c->d_state->stop,
                         p2p ? c->d_state->upd : nullptr, p2p ? 2 : 0));
       } else {
@@ -2002,9 +2037,18 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
         CHK(allreduce(c, c->d_state->red, 5));
       }
       const int fuse = 1 | (rel ? 2 : 0) | 4 | ((!multi || p2p) ? 8 : 0);
-      if (half)
+      if (half) {
+        HalfPush hp;
+        memset(&hp, 0, sizeof(hp));
+        if (fused_push_wanted(c) && c->comm.n_ext > 0) {   // the next stencil's halo leaves with this kernel's stores
+          fused_push_arg(c, p_h->p[pb], hp.a);
+          hp.g = g;
+          hp.par = pb;
+          hp.on = 1;
+        }
         LAUNCHP(c, cg_update_half_kernel, grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (uint4 *)p_h->p[pb],
-               (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse);
+               (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse, hp);
+      }
       else if (rel)
         LAUNCHP(c, (cg_update_kernel<float, true>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
                (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse);
@@ -3179,11 +3223,11 @@ static int comm_setup(b200ks_ctx *c) {
     CHK(dev_alloc(c, (void **)&pp.block, bytes));
     CU(cudaMemset(pp.block, 0, bytes));
     void *q = nullptr;
-    CHK(dev_alloc(c, &q, sizeof(unsigned)));
+    CHK(dev_alloc(c, &q, 2 * sizeof(unsigned)));
     pp.ticket = (unsigned *)q;
     CHK(dev_alloc(c, &q, sizeof(int)));
     pp.err = (int *)q;
-    CU(cudaMemset(pp.ticket, 0, sizeof(unsigned)));
+    CU(cudaMemset(pp.ticket, 0, 2 * sizeof(unsigned)));
     CU(cudaMemset(pp.err, 0, sizeof(int)));
     CU(cudaDeviceSynchronize());
     bool ok = true;

@@ -66,7 +66,7 @@ __device__ __forceinline__ uint32_t pack_h(float re, float im, float inv) {   //
 }
 
 // quantise one site's colour vector (6 floats) into its 16-byte word
-__device__ __forceinline__ void store_vec_h(uint4 *v, int i, const float (&x)[6]) {
+__device__ __forceinline__ uint4 store_vec_h(uint4 *v, int i, const float (&x)[6]) {
   float m = 0.f;
 #pragma unroll
   for (int k = 0; k < 6; k++) m = fmaxf(m, fabsf(x[k]));
@@ -77,6 +77,7 @@ __device__ __forceinline__ void store_vec_h(uint4 *v, int i, const float (&x)[6]
   o.z = pack_h(x[4], x[5], inv);
   o.w = __float_as_uint(m);
   v[i] = o;
+  return o;
 }
 __device__ __forceinline__ void load_vec_h(const uint4 *v, int i, float2 (&o)[3]) {
   const uint4 w = __ldg(v + i);
@@ -112,6 +113,8 @@ struct DslashHArg {
   int halo_mask;
   int *halo_err;
   long long halo_timeout;
+  PushArg push;          // kEpi 0, kMode 1, push_on: the boundary sites of the OUTPUT go straight to the neighbours'
+  int push_on;           // ghost buffers (fused halo push, dslash.cuh push_site_h), for the stencil that reads it next
 };
 
 // ---- packed fp32 helpers (sm_100 FFMA2 / FADD2 / FMUL2) -------------------------------------------
@@ -236,7 +239,7 @@ __device__ __forceinline__ void hop_pair_h(const DslashHArg &a, const uint4 *rec
 
 // one output site: the 16 hops and the epilogue
 template <int kEpi, bool kPart, int kNc>
-__device__ __forceinline__ void half_site(const DslashHArg &a, int idx, double (&red)[3]) {
+__device__ __forceinline__ void half_site(const DslashHArg &a, int idx, double (&red)[3], bool &pushed) {
   const Coord c = site_coord(a.g, idx, a.par);
   const uint4 *rec = a.L.rec[a.par] + record_base(idx, half_record_quads(kNc));
   const float2 zero = make_float2(0.f, 0.f);
@@ -253,7 +256,8 @@ __device__ __forceinline__ void half_site(const DslashHArg &a, int idx, double (
 #pragma unroll
   for (int j = 0; j < 6; j++) acc[j] = acc2[j].x + acc2[j].y;
   if (kEpi == 0) {
-    store_vec_h(a.out_h, idx, acc);
+    const uint4 o = store_vec_h(a.out_h, idx, acc);
+    if (kPart && a.push_on) pushed = push_site_h(a.push, a.g, idx, c.z, c.t, o);
   } else {
     float2 w[3];
     load_vec_h(a.w_h, idx, w);
@@ -305,23 +309,35 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
     }
   }
   double red[3] = {0, 0, 0};
+  bool pushed = false;
   if (active) {
     const int idx = (kMode == 0) ? k : bnd ? a.sites[k] : interior_site(a.g, k);
     // interior sites of a partitioned lattice never leave the local volume: they run the same instruction stream
     // as an unpartitioned lattice (the ghost-index arithmetic of the boundary sites cost every site ~10 %)
-    if (kMode == 1 && bnd) half_site<kEpi, true, kNc>(a, idx, red);
-    else half_site<kEpi, false, kNc>(a, idx, red);
+    if (kMode == 1 && bnd) half_site<kEpi, true, kNc>(a, idx, red, pushed);
+    else half_site<kEpi, false, kNc>(a, idx, red, pushed);
   }
+  // fused halo push of the output: the boundary CTAs hold exactly the sites the neighbours need
+  if (kEpi == 0 && kMode == 1 && a.push_on && bnd) push_signal(a.push, a.g, pushed, gridDim.x - (unsigned)a.nb_int);
   if (kEpi == 2) {   // two-stage (reduce_finish_kernel follows) unless the NCCL-halo path asks for in-kernel sums
     if (kMode == 0 || a.red == nullptr) block_partials<3>(red, a.ws.partials);
     else grid_reduce<3>(red, a.ws, a.red);
   }
 }
 
+// fused halo push of the update kernel's new search direction (on != 0: partitioned context, peer-to-peer halos): the
+// next stencil's exchange is under way before this kernel has ended (dslash.cuh push_site_h / push_signal)
+struct HalfPush {
+  PushArg a;
+  Geom g;
+  int par;   // parity bit of the sites this launch updates
+  int on;
+};
+
 // x += a p ; r += a ttt ; p = r + b p (re-quantised) ; sum |r|^2.   x, r, ttt float; p half.
 __global__ void __launch_bounds__(kBlock)
 cg_update_half_kernel(float2 *x, float2 *r, uint4 *p_h, const float2 *ttt, int stride, int n, CgState *st, ReduceWs ws,
-                      int fuse_scalar) {
+                      int fuse_scalar, const HalfPush hp) {
   pdl_launch_dependents();
   pdl_wait();
   if (st->stop) return;
@@ -333,6 +349,7 @@ cg_update_half_kernel(float2 *x, float2 *r, uint4 *p_h, const float2 *ttt, int s
   const int i = blockIdx.x * kBlock + threadIdx.x;
   const double2 *xrel = (fuse_scalar & 2) ? st->xrel : nullptr;   // Fermilab relative residue wanted (CgState::xrel)
   double s[2] = {0, 0};
+  bool pushed = false;
   if (i < n) {
     float2 pv[3];
     load_vec_h(p_h, i, pv);
@@ -359,10 +376,15 @@ cg_update_half_kernel(float2 *x, float2 *r, uint4 *p_h, const float2 *ttt, int s
         xn2 += tx * tx + ty * ty;
       }
     }
-    store_vec_h(p_h, i, pn);
+    const uint4 o = store_vec_h(p_h, i, pn);
+    if (hp.on) {
+      const Coord c = site_coord(hp.g, i, hp.par);
+      pushed = push_site_h(hp.a, hp.g, i, c.z, c.t, o);
+    }
     s[0] = rn;
     if (xrel != nullptr) s[1] = (xn2 == 0) ? 1.0 : (double)rn / xn2;
   }
+  if (hp.on) push_signal(hp.a, hp.g, pushed, gridDim.x);
   if (fuse_scalar & 8) {   // two-stage: reduce_finish_kernel sums the partials and advances the recurrence
     block_partials<2>(s, ws.partials);
     return;

@@ -30,6 +30,8 @@ for force in ("", "zt"):
         ctx.vec_zero(vx, EVEN)
         it, res = ctx.congrad_dev(vb, vx, 0.05, EVEN, 2000, 10, 1e-10, mixed_precision=mixed)
         row["cg_mixed%d" % mixed] = {"iters": it, "seconds": res["device_seconds"], "us_per_iter": 1e6 * res["device_seconds"] / it}
+    row["fused_push"] = os.environ.get("B200KS_FUSED_PUSH", "1")
+    row["pdl"] = os.environ.get("B200KS_PDL", "1")
     out[force or "none"] = row
     ctx.close()
 print(json.dumps(out, indent=1))

@@ -364,12 +364,13 @@ def test_golden_reference_vectors(api):
 
 
 @pytest.mark.parametrize("force,dims", [("t", (8, 6, 8, 12)), ("z", (8, 6, 8, 12)), ("zt", (8, 6, 8, 12)),
-                                        ("zt", (4, 4, 6, 6)), ("t", (6, 4, 14, 6))])
+                                        ("zt", (4, 4, 6, 6)), ("t", (6, 4, 14, 6)), ("zt", (8, 8, 4, 4))])
 def test_forced_self_partition_runs_the_halo_path_on_one_gpu(api, oracle, force, dims, monkeypatch):
     """B200KS_FORCE_PARTITION makes one GPU its own neighbour: ghost links, the peer-to-peer push
     kernel, arrival flags, the interior/exterior split and the split reductions all run, and must
     reproduce the oracle exactly as the unpartitioned kernels do."""
-    monkeypatch.setenv("B200KS_FORCE_PARTITION", force)   # extent 6 = no interior sites at all
+    monkeypatch.setenv("B200KS_FORCE_PARTITION", force)   # extent 6 = no interior sites at all; extent 4: a site can be in
+    # the low AND the high band of a face (both neighbours need it)
     fat, lng, src = fields_for(dims)
     ctx = api.Context(dims, grid=(1, 1, 1, 1), rank=0, nranks=1)
     assert ctx.halo_mode() == 2
