@@ -762,6 +762,13 @@ static RedComm red_comm(const b200ks_ctx *c) {
   return rc;
 }
 static bool p2p_reductions(const b200ks_ctx *c) { return c->comm.active && c->comm.p2p.on; }
+// fused halo push (fused_push_arg below): the kernel launched next raises the arrival flags of the exchange the
+// kernel before it pushed
+static HaloRaise take_pending_raise(b200ks_ctx *c) {
+  HaloRaise h = c->comm.p2p.pending;
+  c->comm.p2p.pending.seq = 0;
+  return h;
+}
 
 static void launch_finish(b200ks_ctx *c, const FinishArg &a, int nslots, bool comm = false) {
   if (comm && c->comm.nranks > 1) reduce_finish_kernel<true><<<1, kFinishThreads, 0, c->stream>>>(a, red_comm(c));
@@ -793,6 +800,7 @@ static void finish_update(b200ks_ctx *c, int nblk, CgState *st, int flags) {
   f.s[0] = finish_slot(c->ws.partials, 2, 2, st->upd_next, st, &st->stop);
   f.nblk = nblk;
   f.scalar_flags = flags & 7;
+  if (c->comm.active) f.raise = take_pending_raise(c);   // the update kernel's fused halo push (half.cuh HalfPush)
   launch_finish(c, f, 1);
 }
 
@@ -1279,7 +1287,10 @@ static void fused_push_arg(b200ks_ctx *c, const void *vec, PushArg &a) {
   a.ticket = pp.ticket + 1;
   a.stop = nullptr;
   pp.fused_ptr = vec;
+  for (int k = 0; k < 4; k++) pp.pending.flag[k] = a.flag[k >> 1][k & 1];
+  pp.pending.seq = pp.seq;
 }
+
 static bool fused_push_wanted(const b200ks_ctx *c) {
   static const bool off = getenv("B200KS_FUSED_PUSH") && atoi(getenv("B200KS_FUSED_PUSH")) == 0;
   return !off && c->comm.active && c->comm.p2p.on;
@@ -1452,6 +1463,7 @@ static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *o
   a.halo_mask = (c->g.part[2] ? 3 : 0) | (c->g.part[3] ? 12 : 0);
   a.halo_err = pp.err;
   a.red = nullptr;   // two-stage reduction, see dslash_T
+  a.raise = take_pending_raise(c);
   if (push_out && kind == 0 && out_h != nullptr && nblocks(c->comm.n_ext) > 0 && fused_push_wanted(c)) {
     fused_push_arg(c, out_h->p[par_out], a.push);   // (the OUTPUT's exchange: ++seq after the input's was read above)
     a.push_on = 1;
@@ -1966,6 +1978,7 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
   for (bool first = true;; first = false) {
     // reliable update = true residual in double
     c->comm.p2p.fused_ptr = nullptr;   // (the reliable kernel rewrites the search direction: a halo pushed by the last update is stale)
+    c->comm.p2p.pending.seq = 0;
     if (!first) LAUNCH(c, mixed_accumulate_kernel, grid, (double2 *)x.p[pb], (float2 *)x_lo->p[pb], g.stride, g.Vh);
     Epi e0, e1;
     CHK(dslash_T<double>(c, x, *ttt_d, ob, e0));

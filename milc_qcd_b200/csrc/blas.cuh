@@ -199,6 +199,7 @@ struct FinishArg {
   FinishSlot s[kMaxRhs];
   int nblk;
   int scalar_flags;        // 0: sums only; else bit 0 on, bit 1 use_rel, bit 2 single (cg_scalar_step)
+  HaloRaise raise;         // arrival flags of the halo the kernel before this one pushed (common.cuh)
 };
 
 // ---- flag-based all-reduce over the ranks of a partitioned context (comm.cuh RedBox) -----------
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(kFinishThreads) reduce_finish_kernel(const Fin
   pdl_wait();
   const FinishSlot &f = a.s[blockIdx.x];
   if (f.stop != nullptr && *f.stop) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) raise_halo_flags(a.raise);
   __shared__ double sm[3][kFinishThreads / 32];
   __shared__ double tot[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -98,6 +98,8 @@ struct P2P {
   unsigned long long seq = 0;       // exchange sequence number (host mirror)
   unsigned *ticket = nullptr;       // CTA tickets: [0] push_halo_kernel, [1] fused pushes (dslash.cuh push_signal)
   const void *fused_ptr = nullptr;  // vector half whose halo its PRODUCER has already pushed as exchange `seq`
+  HaloRaise pending = {{nullptr, nullptr, nullptr, nullptr}, 0};   // ... and whose arrival flags the next kernel on the
+                                                                   // compute stream has to raise (common.cuh)
   int *err = nullptr;               // device word: nonzero = a halo or reduction wait timed out
 };
 

@@ -73,6 +73,23 @@ struct Geom {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Deferred arrival flags of a fused halo push (dslash.cuh push_site_h): the kernel that produced a vector stored its
+// boundary sites into the neighbours' ghost buffers with plain (posted) stores; the NEXT kernel on the stream raises
+// the neighbours' arrival flags with its first thread.  The kernel boundary in between is what orders the data before
+// the flag (a completed grid's writes, peer writes included, are performed system-wide), so the producer needs no
+// fence and no ticket -- per-CTA system fences in the producer cost more than the exchange they announced.
+struct HaloRaise {
+  unsigned long long *flag[4];   // nullptr: direction not partitioned
+  unsigned long long seq;        // 0: nothing to raise
+};
+__device__ __forceinline__ void raise_halo_flags(const HaloRaise &h) {
+  if (h.seq == 0) return;
+  __threadfence_system();
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (h.flag[k] != nullptr) atomicMax_system(h.flag[k], h.seq);   // flags only ever move forward
+}
+
 struct Coord { int x, y, z, t, xh; };
 
 // cb index -> local coordinates, for a site of the given local parity bit (0 even, 1 odd).

@@ -115,6 +115,7 @@ struct DslashHArg {
   long long halo_timeout;
   PushArg push;          // kEpi 0, kMode 1, push_on: the boundary sites of the OUTPUT go straight to the neighbours'
   int push_on;           // ghost buffers (fused halo push, dslash.cuh push_site_h), for the stencil that reads it next
+  HaloRaise raise;       // arrival flags of the halo the kernel BEFORE this one pushed (its input's, common.cuh)
 };
 
 // ---- packed fp32 helpers (sm_100 FFMA2 / FADD2 / FMUL2) -------------------------------------------
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
   pdl_launch_dependents();
   pdl_wait();
   if (a.stop != nullptr && *a.stop) return;
+  if (kMode == 1 && blockIdx.x == 0 && threadIdx.x == 0) raise_halo_flags(a.raise);   // (before this CTA waits for anything)
   int k = blockIdx.x * kBlock + threadIdx.x;
   bool active = k < a.nsites;
   bool bnd = false;
@@ -317,8 +319,9 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
     if (kMode == 1 && bnd) half_site<kEpi, true, kNc>(a, idx, red, pushed);
     else half_site<kEpi, false, kNc>(a, idx, red, pushed);
   }
-  // fused halo push of the output: the boundary CTAs hold exactly the sites the neighbours need
-  if (kEpi == 0 && kMode == 1 && a.push_on && bnd) push_signal(a.push, a.g, pushed, gridDim.x - (unsigned)a.nb_int);
+  // (fused halo push of the output, half_site: the boundary CTAs hold exactly the sites the neighbours need; the
+  // arrival flags are raised by the next kernel on the stream, HaloRaise)
+  (void)pushed;
   if (kEpi == 2) {   // two-stage (reduce_finish_kernel follows) unless the NCCL-halo path asks for in-kernel sums
     if (kMode == 0 || a.red == nullptr) block_partials<3>(red, a.ws.partials);
     else grid_reduce<3>(red, a.ws, a.red);
@@ -384,7 +387,7 @@ cg_update_half_kernel(float2 *x, float2 *r, uint4 *p_h, const float2 *ttt, int s
     s[0] = rn;
     if (xrel != nullptr) s[1] = (xn2 == 0) ? 1.0 : (double)rn / xn2;
   }
-  if (hp.on) push_signal(hp.a, hp.g, pushed, gridDim.x);
+  (void)pushed;   // (the finish kernel that follows raises the arrival flags, FinishArg::raise)
   if (fuse_scalar & 8) {   // two-stage: reduce_finish_kernel sums the partials and advances the recurrence
     block_partials<2>(s, ws.partials);
     return;
