@@ -124,6 +124,8 @@ struct b200ks_ctx {
   int member_rank = -1;                 // >= 0: member of a multi-GPU context
   double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // b200ks_call_profile
   bool pdl = true;                      // programmatic dependent launch in the solver loops (B200KS_PDL)
+  bool pdl_part_ok = false;             // partitioned contexts: set around launches of an iteration whose halos travel by
+                                        // fused pushes (no push kernel, no cross-stream event between the kernels)
   void *eigcg = nullptr;                // EigCGState (eigcg.inl): search window + accumulated low modes in HBM
 };
 
@@ -716,7 +718,7 @@ extern "C" int b200ks_num_gpus(b200ks_ctx *c) { return c ? nmembers(c) : 0; }
 // iteration overlap the tail of the kernel before (B200KS_PDL=0: ordinary launches, for A/B measurements).
 template <typename... KArgs, typename... Args>
 static inline void launch_k(b200ks_ctx *c, void (*kern)(KArgs...), int grid, int block, Args &&...args) {
-  if (c->pdl && !c->comm.active) {
+  if (c->pdl && (!c->comm.active || c->pdl_part_ok)) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
@@ -771,9 +773,8 @@ static HaloRaise take_pending_raise(b200ks_ctx *c) {
 }
 
 static void launch_finish(b200ks_ctx *c, const FinishArg &a, int nslots, bool comm = false) {
-  if (comm && c->comm.nranks > 1) reduce_finish_kernel<true><<<1, kFinishThreads, 0, c->stream>>>(a, red_comm(c));
-  else { launch_k(c, reduce_finish_kernel<false>, nslots, kFinishThreads, a, RedComm()); return; }
-  c->launches++;
+  if (comm && c->comm.nranks > 1) launch_k(c, reduce_finish_kernel<true>, 1, kFinishThreads, a, red_comm(c));
+  else launch_k(c, reduce_finish_kernel<false>, nslots, kFinishThreads, a, RedComm());
 }
 static FinishSlot finish_slot(const double *partials, int stride, int nval, double *out, CgState *st, const int *stop) {
   FinishSlot f;
@@ -1468,9 +1469,13 @@ static int dslash_half(b200ks_ctx *c, const DevVec &in, DevVec *out_h, DevVec *o
     fused_push_arg(c, out_h->p[par_out], a.push);   // (the OUTPUT's exchange: ++seq after the input's was read above)
     a.push_on = 1;
   }
+  const bool part_ok = c->pdl_part_ok;
+  c->pdl_part_ok = part_ok && in_pushed;   // (a push kernel and its events sit between this launch and the one before)
   DSLASH_H_LAUNCH(1, a.nb_int + nblocks(c->comm.n_ext));
   if (!in_pushed) CU(cudaStreamWaitEvent(c->stream, c->comm.ev_done, 0));
+  c->pdl_part_ok = part_ok && in_pushed;   // the finish kernel follows the stencil directly only then
   if (kind == 2) finish_dots(c, a.nb_int + nblocks(c->comm.n_ext), red, stop, extra, nextra);
+  c->pdl_part_ok = part_ok;
 #undef DSLASH_H_LAUNCH
   return 0;
 }
@@ -2032,6 +2037,8 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
     CHK(state_push(c));
     CHK(run_batches(c, batch, "mixed cg iterate", [&]() -> int {
       const bool p2p = p2p_reductions(c);
+      // partitioned + fused halo pushes: the iteration is five plain kernels on one stream, like the unpartitioned one
+      c->pdl_part_ok = half && fused_push_wanted(c);
       if (half) {
         CHK(dslash_half(c, *p_h, t_h, nullptr, ob, 0, 0.0, nullptr, nullptr, nullptr, &c->d_state->stop, nullptr, 0, true));
         CHK(dslash_half(c, *t_h, nullptr, ttt_lo, pb, 2, -msq_x4, p_h, r_lo, c->d_state->red, &c->d_state->stop,
@@ -2069,8 +2076,10 @@ static int congrad_mixed(b200ks_ctx *c, const DevVec &b, DevVec &x, double mass,
         LAUNCHP(c, (cg_update_kernel<float, false>), grid, (float2 *)x_lo->p[pb], (float2 *)r_lo->p[pb], (float2 *)p_lo->p[pb],
                (const float2 *)ttt_lo->p[pb], g.stride, g.Vh, c->d_state, c->ws, fuse);
       if (fuse & 8) finish_update(c, grid, c->d_state, fuse);
+      c->pdl_part_ok = false;
       return 0;
     }));
+    c->pdl_part_ok = false;
     iteration = h.iter;
     res.size_r = h.size_r;
     if (iteration >= max_cg) {  // budget exhausted: one last true residual for the report

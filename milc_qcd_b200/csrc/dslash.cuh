@@ -183,6 +183,41 @@ __device__ __forceinline__ void acquire_halo(const unsigned long long *flags, un
   }
 }
 
+// The same for a whole CTA (every thread calls it; ends with a CTA barrier).  B200KS_ACQ selects how the flags are
+// polled (A/B builds, profiles/variants):
+//   0  thread 0 polls the faces one after the other with ld.acquire.sys (round 1)
+//   1  lanes 0..3 poll one face each, ld.acquire.sys
+//   2  lanes 0..3 poll one face each with ld.relaxed.sys; no fence: the ghost words are read after the barrier, through
+//      L1 lines that cannot be stale (nothing reads a ghost buffer before its flag has been seen, and the L1 starts
+//      every kernel empty), and the data reached this GPU's L2 before the flag did (the writer's release)
+//   3  as 2 + fence.acq_rel.sys in the polling lanes (the formal acquire pattern)
+// Measured with the GPU as its own neighbour at the 8-GPU local volume (profiles/run_r02k.sh): 16-bit stencil 0.1675 /
+// 0.1644 / 0.1495 / 0.1595 ms for 0 / 1 / 2 / 3 (unpartitioned: 0.131-0.137).  ld.acquire.sys and the system fence
+// compile to CCTL.IVALL -- every boundary CTA emptied its SM's L1, which the resident CTAs' neighbour-vector reuse lives in.
+#ifndef B200KS_ACQ
+#define B200KS_ACQ 2
+#endif
+__device__ __forceinline__ void acquire_halo_cta(const unsigned long long *flags, unsigned long long seq, int mask, int *err,
+                                                 long long max_cycles) {
+  if (B200KS_ACQ == 0) {
+    if (threadIdx.x == 0) acquire_halo(flags, seq, mask, err, max_cycles);
+  } else if (threadIdx.x < 4 && ((mask >> threadIdx.x) & 1)) {
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      if (B200KS_ACQ == 1) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+      else asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+      if (v >= seq) break;
+      if (clock64() - t0 > max_cycles) {
+        *err = 1 + threadIdx.x;
+        break;
+      }
+    }
+    if (B200KS_ACQ == 3) asm volatile("fence.acq_rel.sys;" ::: "memory");
+  }
+  __syncthreads();
+}
+
 // one output site: the 16 hops and the epilogue
 template <typename T, int kEpi, bool kPart, int kNc>
 __device__ __forceinline__ void dslash_site(const DslashArg<T> &a, int idx, double (&red)[3]) {
@@ -240,10 +275,7 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? 5 : 8) dslash_kernel(
     if (bnd) {
       k = (b - a.nb_int) * kBlock + threadIdx.x;
       active = k < a.n_ext;
-      if (a.halo_flags != nullptr) {
-        if (threadIdx.x == 0) acquire_halo(a.halo_flags, a.halo_seq, a.halo_mask, a.halo_err, a.halo_timeout);
-        __syncthreads();
-      }
+      if (a.halo_flags != nullptr) acquire_halo_cta(a.halo_flags, a.halo_seq, a.halo_mask, a.halo_err, a.halo_timeout);
     } else {
       k = b * kBlock + threadIdx.x;
       active = k < a.n_int;

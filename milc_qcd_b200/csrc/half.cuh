@@ -301,10 +301,7 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
     if (bnd) {
       k = (b - a.nb_int) * kBlock + threadIdx.x;
       active = k < a.n_ext;
-      if (a.halo_flags != nullptr) {
-        if (threadIdx.x == 0) acquire_halo(a.halo_flags, a.halo_seq, a.halo_mask, a.halo_err, a.halo_timeout);
-        __syncthreads();
-      }
+      if (a.halo_flags != nullptr) acquire_halo_cta(a.halo_flags, a.halo_seq, a.halo_mask, a.halo_err, a.halo_timeout);
     } else {
       k = b * kBlock + threadIdx.x;
       active = k < a.n_int;

@@ -11,3 +11,6 @@ wait
 build probe_nomath -DB200KS_PROBE_NOMATH &
 build probe_nolinkload -DB200KS_PROBE_NOLINKLOAD &
 wait
+# how boundary CTAs of a partitioned stencil poll the arrival flags (dslash.cuh acquire_halo_cta)
+for a in 0 1 2 3; do build acq$a -DB200KS_ACQ=$a & done
+wait
