@@ -90,6 +90,18 @@ def main():
         check("cg converged", res["converged"] == 1 and res["final_rsq"] < resid ** 2, "final_rsq %.2e" % res["final_rsq"])
         e = np.linalg.norm(x - xo) / np.linalg.norm(xo)
         check("cg solution", e <= 10 * resid / (4 * mass * mass), "rel diff %.2e" % e)
+    # the mixed solvers: single-precision inner iteration, and the 16-bit one (fused halo pushes, deferred arrival
+    # flags, programmatic dependent launch across the partitioned iteration) -- same system, double true residuals
+    for mixed in (1, 2):
+        lxm = np.zeros_like(lb)
+        itm_, resm_ = ctx.congrad(lb, lxm, mass, EVEN, 500, 5, resid, mixed_precision=mixed)
+        xm = gather(lxm)
+        if rank == 0:
+            check("cg mixed_precision %d converged" % mixed, resm_["converged"] == 1 and resm_["final_rsq"] < resid ** 2,
+                  "%d iterations (oracle %d), final_rsq %.2e" % (itm_, ito, resm_["final_rsq"]))
+            e = np.linalg.norm(xm - xo) / np.linalg.norm(xo)
+            check("cg mixed_precision %d solution" % mixed, e <= 10 * resid / (4 * mass * mass), "rel diff %.2e" % e)
+            check("cg mixed_precision %d iterations" % mixed, itm_ <= (1.25 if mixed == 1 else 2.5) * ito, "%d vs oracle %d" % (itm_, ito))
     # with the Fermilab relative residual switched on (extra all-reduce path)
     lx2 = np.zeros_like(lb)
     it2, res2 = ctx.congrad(lb, lx2, mass, EVEN, 500, 5, resid, relresid=1e-3)
