@@ -22,10 +22,10 @@ __global__ void __launch_bounds__(kBlock) force_site_kernel(const F fn, int n) {
   if (i < n) fn(i);
 }
 
-// the same with a register cap (<= 128 registers: four 128-thread CTAs per SM) for functors that declare a
-// static kMinBlocks member
+// the same with a register cap (kMinBlocks 128-thread CTAs per SM: 4 = 128 registers, 3 = 168) for functors that
+// declare a static kMinBlocks member
 template <class F>
-__global__ void __launch_bounds__(kBlock, 4) force_site_kernel2(const F fn, int n) {
+__global__ void __launch_bounds__(kBlock, F::kMinBlocks) force_site_kernel2(const F fn, int n) {
   const int i = blockIdx.x * kBlock + threadIdx.x;
   if (i < n) fn(i);
 }

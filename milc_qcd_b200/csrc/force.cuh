@@ -204,7 +204,11 @@ struct StapleFwdSite {
 
 // 3. backward staple: H = hs * Hfield is the gradient w.r.t. S(link); adds to glink and gUnu at z.
 //    part as in StapleFwdSite: the contributions of the upper staple (1), the lower one (2) or both (3)
+#ifndef B200KS_FORCE_BWD_MINB
+#define B200KS_FORCE_BWD_MINB 2   // CTAs per SM the fused backward staple body is compiled for (A/B: profiles/variants)
+#endif
 struct StapleBwdSite {
+  static constexpr int kMinBlocks = B200KS_FORCE_BWD_MINB;
   FGeom g;
   const double2 *H;
   double hs;
