@@ -269,12 +269,14 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? 5 : 8) dslash_kernel(
   int k = blockIdx.x * kBlock + threadIdx.x;
   bool active = k < a.nsites;
   bool bnd = false;
+  int bsite = 0;
   if (kMode == 1) {
     const int b = blockIdx.x + a.blk0;
     bnd = b >= a.nb_int;
     if (bnd) {
       k = (b - a.nb_int) * kBlock + threadIdx.x;
       active = k < a.n_ext;
+      if (active) bsite = __ldg(a.sites + k);   // (in flight while the flags are polled)
       if (a.halo_flags != nullptr) acquire_halo_cta(a.halo_flags, a.halo_seq, a.halo_mask, a.halo_err, a.halo_timeout);
     } else {
       k = b * kBlock + threadIdx.x;
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? 5 : 8) dslash_kernel(
   }
   double red[3] = {0, 0, 0};
   if (active) {
-    const int idx = (kMode == 0) ? k : bnd ? a.sites[k] : interior_site(a.g, k);
+    const int idx = (kMode == 0) ? k : bnd ? bsite : interior_site(a.g, k);
     // interior sites of a partitioned lattice run the unpartitioned instruction stream
     if (kMode == 1 && bnd) dslash_site<T, kEpi, true, kNc>(a, idx, red);
     else dslash_site<T, kEpi, false, kNc>(a, idx, red);

@@ -1,0 +1,17 @@
+#!/bin/bash
+# GPU-box script, final 1-GPU pass of round 2: the whole GPU suite as the driver runs it, smoke, reference arm, the default
+# bench line, and the ncu launch list of the same bench command.
+tag=${1:-r02n}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu --durations=8 > gpurun_out/pytest_${tag}.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_${tag}.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${tag}.log 2>&1
+echo "smoke rc=$?" >> gpurun_out/smoke_${tag}.log
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${tag}_n1_reference.json 2> gpurun_out/bench_${tag}_n1_reference.err
+timeout 900 python bench.py > gpurun_out/bench_${tag}_n1.json 2> gpurun_out/bench_${tag}_n1.err
+echo "bench rc=$?" >> gpurun_out/bench_${tag}_n1.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1000 -c 600 --csv \
+    --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras \
+    > gpurun_out/bench_under_ncu_${tag}.log 2>&1
+grep -v "^\s*$" gpurun_out/pytest_${tag}.log | tail -n 14
+cat gpurun_out/smoke_${tag}.log; tail -c 200 gpurun_out/bench_${tag}_n1.err; head -c 500 gpurun_out/bench_${tag}_n1.json
