@@ -1237,12 +1237,15 @@ static char *p2p_ghost(const P2P &pp, char *block, unsigned long long seq) {
 
 // Peer-to-peer exchange `seq`: one push kernel on the (high-priority) comm stream, concurrent
 // with the interior pass.  Returns the ghost buffer the stencil kernels of this exchange read.
+// sub / nsub: vector `sub` of an exchange that carries nsub vectors (K-wide stencil): its own slice of the ghost
+// buffer, one sequence number for all, the arrival flags raised by the last one (the comm stream runs them in order).
 template <typename E, int NP, bool kTile>
-static int halo_push(b200ks_ctx *c, const DevVec &in, int pin, const int *stop) {
+static int halo_push(b200ks_ctx *c, const DevVec &in, int pin, const int *stop, int sub = 0, int nsub = 1) {
   const Geom &g = c->g;
   Comm &cm = c->comm;
   P2P &pp = cm.p2p;
-  pp.seq++;
+  if (sub == 0) pp.seq++;
+  const size_t sub_off = (size_t)sub * NP * g.gstride * sizeof(E);
   PushArg a;
   memset(&a, 0, sizeof(a));
   int n = 0;
@@ -1251,15 +1254,17 @@ static int halo_push(b200ks_ctx *c, const DevVec &in, int pin, const int *stop) 
     n += 6 * g.faceh[d];
     for (int side = 0; side < 2; side++) {
       char *peer = pp.peer_block[d - 2][side];
-      a.dst[d - 2][side] = p2p_ghost(pp, peer, pp.seq);
-      a.flag[d - 2][side] = p2p_flags(peer) + (d - 2) * 2 + (side ? 0 : 1);
+      a.dst[d - 2][side] = p2p_ghost(pp, peer, pp.seq) + sub_off;
+      a.flag[d - 2][side] = (sub == nsub - 1) ? p2p_flags(peer) + (d - 2) * 2 + (side ? 0 : 1) : nullptr;
     }
   }
   a.seq = pp.seq;
   a.ticket = pp.ticket;
   a.stop = stop;
-  CU(cudaEventRecord(cm.ev_ready, c->stream));
-  CU(cudaStreamWaitEvent(cm.stream, cm.ev_ready, 0));
+  if (sub == 0) {
+    CU(cudaEventRecord(cm.ev_ready, c->stream));
+    CU(cudaStreamWaitEvent(cm.stream, cm.ev_ready, 0));
+  }
   const int pgrid = std::min((n + kPushBlock - 1) / kPushBlock, cm.push_ctas);
   push_halo_kernel<E, NP, kTile><<<pgrid, kPushBlock, 0, cm.stream>>>(a, (const E *)in.p[pin], g);
   c->launches++;
@@ -2210,6 +2215,8 @@ struct MSlot {
   const DevVec *w = nullptr, *r = nullptr;
   double *red = nullptr;
   const int *stop = nullptr;
+  double *extra = nullptr;   // partitioned contexts, kind 2: this rank's share of the previous update's two sums
+                             // (CgState::upd), all-reduced together with the three dots
 };
 
 template <typename T, int K>
@@ -2234,20 +2241,66 @@ static int dslash_mrhs_K(b200ks_ctx *c, const MSlot *sl, int par_out, int kind, 
   a.s = (T)s;
   a.ws = c->ws;
   a.nsites = c->g.Vh;
-  const int grid = nblocks(c->g.Vh);
-  if (L.lng_nc == 7) {
-    if (kind == 0) LAUNCH(c, (dslash_mrhs_kernel<T, 0, K, 7>), grid, a);
-    else LAUNCH(c, (dslash_mrhs_kernel<T, 2, K, 7>), grid, a);
-  } else {
-    if (kind == 0) LAUNCH(c, (dslash_mrhs_kernel<T, 0, K, 9>), grid, a);
-    else LAUNCH(c, (dslash_mrhs_kernel<T, 2, K, 9>), grid, a);
+  for (int k = 0; k < K; k++) a.gin[k] = nullptr;
+  a.sites = c->comm.ext_sites;
+  a.n_int = c->comm.n_int;
+  a.n_ext = c->comm.n_ext;
+  a.nb_int = nblocks(c->comm.n_int);
+  a.halo_flags = nullptr;
+  a.halo_seq = 0;
+  a.halo_mask = 0;
+  a.halo_err = nullptr;
+  a.halo_timeout = kHaloTimeoutCycles;
+  int grid = nblocks(c->g.Vh);
+#define MRHS_LAUNCH(kMode)                                                               \
+  do {                                                                                   \
+    if (L.lng_nc == 7) {                                                                 \
+      if (kind == 0) LAUNCH(c, (dslash_mrhs_kernel<T, 0, K, 7, kMode>), grid, a);        \
+      else LAUNCH(c, (dslash_mrhs_kernel<T, 2, K, 7, kMode>), grid, a);                  \
+    } else {                                                                             \
+      if (kind == 0) LAUNCH(c, (dslash_mrhs_kernel<T, 0, K, 9, kMode>), grid, a);        \
+      else LAUNCH(c, (dslash_mrhs_kernel<T, 2, K, 9, kMode>), grid, a);                  \
+    }                                                                                    \
+  } while (0)
+  if (!c->comm.active) {
+    MRHS_LAUNCH(0);
+    if (kind == 2) {   // slot k's three sums: values 3k..3k+2 of every CTA's 3K partials
+      FinishArg f;
+      memset(&f, 0, sizeof(f));
+      for (int k = 0; k < K; k++) f.s[k] = finish_slot(c->ws.partials + 3 * k, 3 * K, 3, sl[k].red, nullptr, sl[k].stop);
+      f.nblk = grid;
+      launch_finish(c, f, K);
+    }
+    return 0;
   }
-  if (kind == 2) {   // slot k's three sums: values 3k..3k+2 of every CTA's 3K partials
-    FinishArg f;
-    memset(&f, 0, sizeof(f));
-    for (int k = 0; k < K; k++) f.s[k] = finish_slot(c->ws.partials + 3 * k, 3 * K, 3, sl[k].red, nullptr, sl[k].stop);
-    f.nblk = grid;
-    launch_finish(c, f, K);
+  // partitioned lattice: ONE exchange for the K inputs (K push kernels into K slices of its ghost buffer, the last one
+  // raises the arrival flags; all K travel whatever their stop flags say, so that the flags always go up), one launch
+  // with the interior CTAs first, one finish kernel per right-hand side (its three sums + the previous update's two are
+  // all-reduced in it, like finish_dots does for a single solve)
+  P2P &pp = c->comm.p2p;
+  if (!pp.on) return fail(B200KS_ESTATE, "multi-right-hand-side stencil on a partitioned lattice needs the peer-to-peer halo path");
+  pp.fused_ptr = nullptr;
+  for (int k = 0; k < K; k++) CHK((halo_push<T2, 3, false>(c, *sl[k].in, par_out ^ 1, nullptr, k, K)));
+  const size_t sub = (size_t)3 * c->g.gstride * sizeof(T2);
+  for (int k = 0; k < K; k++) a.gin[k] = (const T2 *)(p2p_ghost(pp, pp.block, pp.seq) + (size_t)k * sub);
+  a.halo_flags = p2p_flags(pp.block);
+  a.halo_seq = pp.seq;
+  a.halo_mask = (c->g.part[2] ? 3 : 0) | (c->g.part[3] ? 12 : 0);
+  a.halo_err = pp.err;
+  grid = a.nb_int + nblocks(c->comm.n_ext);
+  MRHS_LAUNCH(1);
+#undef MRHS_LAUNCH
+  CU(cudaStreamWaitEvent(c->stream, c->comm.ev_done, 0));
+  if (kind == 2) {
+    for (int k = 0; k < K; k++) {
+      FinishArg f;
+      memset(&f, 0, sizeof(f));
+      f.s[0] = finish_slot(c->ws.partials + 3 * k, 3 * K, 3, sl[k].red, nullptr, sl[k].stop);
+      f.s[0].extra = sl[k].extra;
+      f.s[0].nextra = sl[k].extra ? 2 : 0;
+      f.nblk = grid;
+      launch_finish(c, f, 1, true);
+    }
   }
   return 0;
 }
@@ -2255,7 +2308,6 @@ static int dslash_mrhs_K(b200ks_ctx *c, const MSlot *sl, int par_out, int kind, 
 // kind 0: out_k = D in_k ; kind 2: out_k = D in_k + s w_k with the three fused dots per slot
 template <typename T>
 static int dslash_mrhs(b200ks_ctx *c, const MSlot *sl, int n, int par_out, int kind, double s) {
-  if (c->comm.active) return fail(B200KS_ESTATE, "multi-right-hand-side stencil: single-GPU contexts only");
   if (kind != 0 && kind != 2) return fail(B200KS_EINVAL, "dslash_mrhs: kind must be 0 or 2");
   switch (n) {
     case 1: {
@@ -2299,6 +2351,7 @@ static int congrad_block_T(b200ks_ctx *c, int n, BlockRhs *rhs, double mass, con
   const double msq_x4 = 4.0 * mass * mass;
   const int max_cg = max_restarts * niter;
   const int batch = args.check_interval > 0 ? args.check_interval : 8;
+  const bool multi = c->comm.active;   // (peer-to-peer halos: congrad_block_any)
   CgState *h = c->h_state;
   memset(h, 0, sizeof(CgState) * kMaxRhs);
   for (int k = 0; k < n; k++) {
@@ -2310,6 +2363,7 @@ static int congrad_block_T(b200ks_ctx *c, int n, BlockRhs *rhs, double mass, con
   for (;;) {
     // (re)start every live right-hand side from its true residual, d_congrad5_fn_milc.c:177-240
     int nlive = 0;
+    if (multi) CU(cudaMemsetAsync(c->d_scal, 0, 2 * kMaxRhs * sizeof(double), c->stream));   // (all slots are all-reduced below)
     for (int k = 0; k < n; k++) {
       if (rhs[k].done) continue;
       Epi e0, e1;
@@ -2319,6 +2373,7 @@ static int congrad_block_T(b200ks_ctx *c, int n, BlockRhs *rhs, double mass, con
       LAUNCH(c, (cg_restart_kernel<T, false>), grid, (const T2 *)rhs[k].b->p[pb], (const T2 *)rhs[k].ttt->p[pb],
              (const T2 *)rhs[k].x->p[pb], (T2 *)rhs[k].r->p[pb], (T2 *)rhs[k].p->p[pb], g.stride, g.Vh, c->ws, c->d_scal + 2 * k);
     }
+    CHK(allreduce(c, c->d_scal, 2 * kMaxRhs));
     CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * kMaxRhs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CHK(check_launch("block cg restart"));
@@ -2342,7 +2397,8 @@ static int congrad_block_T(b200ks_ctx *c, int n, BlockRhs *rhs, double mass, con
       h[k].niter = niter;
       h[k].half_volume = 0.5 * (double)c->global[0] * c->global[1] * c->global[2] * c->global[3];
       h[k].rsq = rsq;
-      h[k].upd[0] = rsq;
+      // partitioned: upd[] is all-reduced together with red[] inside the iteration, so only rank 0 carries the value
+      h[k].upd[0] = (multi && c->comm.rank != 0) ? 0.0 : rsq;
       h[k].upd[1] = 0;
       h[k].iter = rhs[k].iteration;
       h[k].stop = 0;
@@ -2355,6 +2411,7 @@ static int congrad_block_T(b200ks_ctx *c, int n, BlockRhs *rhs, double mass, con
       s0[ns].in = rhs[k].p; s0[ns].out = rhs[k].ttt; s0[ns].stop = &c->d_state[k].stop;
       s1[ns].in = rhs[k].ttt; s1[ns].out = rhs[k].ttt; s1[ns].w = rhs[k].p; s1[ns].r = rhs[k].r;
       s1[ns].red = c->d_state[k].red; s1[ns].stop = &c->d_state[k].stop;
+      s1[ns].extra = multi ? c->d_state[k].upd : nullptr;
       slot_rhs[ns++] = k;
     }
     CHK(state_push(c, n));
@@ -2420,6 +2477,7 @@ static int congrad_block_mixed(b200ks_ctx *c, int n, BlockRhs *rhs, double mass,
   const int max_cg = max_restarts * niter;
   const int batch = args.check_interval > 0 ? args.check_interval : 8;
   const double delta = 0.1;
+  const bool multi = c->comm.active;   // (peer-to-peer halos: congrad_block_any)
   CHK(links_ensure(c, 1));
   DevVec *ttt_d = nullptr;
   CHK(pool_get(c, 2, 2, &ttt_d));
@@ -2435,6 +2493,7 @@ static int congrad_block_mixed(b200ks_ctx *c, int n, BlockRhs *rhs, double mass,
   CU(cudaEventRecord(c->ev0, c->stream));
   for (;;) {
     // joint reliable update: x += x_lo, r = b - A x in double, p shifted by the correction
+    if (multi) CU(cudaMemsetAsync(c->d_scal, 0, 2 * kMaxRhs * sizeof(double), c->stream));   // (all slots are all-reduced below)
     for (int k = 0; k < n; k++) {
       if (rhs[k].done) continue;
       if (!rhs[k].first)
@@ -2448,6 +2507,7 @@ static int congrad_block_mixed(b200ks_ctx *c, int n, BlockRhs *rhs, double mass,
              (const double2 *)nullptr);
       rhs[k].first = false;
     }
+    CHK(allreduce(c, c->d_scal, 2 * kMaxRhs));
     CU(cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * kMaxRhs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CHK(check_launch("block mixed reliable update"));
@@ -2472,7 +2532,7 @@ static int congrad_block_mixed(b200ks_ctx *c, int n, BlockRhs *rhs, double mass,
       h[k].delta2 = delta * delta;
       h[k].half_volume = 0.5 * (double)c->global[0] * c->global[1] * c->global[2] * c->global[3];
       h[k].rsq = rsq;
-      h[k].upd[0] = rsq;
+      h[k].upd[0] = (multi && c->comm.rank != 0) ? 0.0 : rsq;
       h[k].upd[1] = 0;
       h[k].maxrr = rsq;
       h[k].reliable = 0;
@@ -2487,6 +2547,7 @@ static int congrad_block_mixed(b200ks_ctx *c, int n, BlockRhs *rhs, double mass,
       s0[ns].in = rhs[k].p; s0[ns].out = rhs[k].ttt; s0[ns].stop = &c->d_state[k].stop;
       s1[ns].in = rhs[k].ttt; s1[ns].out = rhs[k].ttt; s1[ns].w = rhs[k].p; s1[ns].r = rhs[k].r;
       s1[ns].red = c->d_state[k].red; s1[ns].stop = &c->d_state[k].stop;
+      s1[ns].extra = multi ? c->d_state[k].upd : nullptr;
       slot_rhs[ns++] = k;
     }
     CHK(state_push(c, n));
@@ -2543,7 +2604,7 @@ static int congrad_block_any(b200ks_ctx *c, int nsrc, DevVec *const *b, DevVec *
   CHK(links_ensure(c, 2));
   const int pb = parity_bit(args.parity);
   int total = 0;
-  if (c->comm.active || args.relresid != 0) {
+  if ((c->comm.active && !c->comm.p2p.on) || args.relresid != 0) {   // (NCCL-halo fallback path: no K-wide exchange)
     for (int k = 0; k < nsrc; k++) {
       const int it = congrad_any(c, *b[k], *x[k], mass, args, res[k]);
       if (it < 0) return it;
@@ -3240,7 +3301,7 @@ static int comm_setup(b200ks_ctx *c) {
   if (cm.nranks == 1 && !want_p2p) return fail(B200KS_EINVAL, "a self-partitioned single rank needs the peer-to-peer halo path");
   P2P &pp = cm.p2p;
   if (want_p2p) {
-    pp.ghost_bytes = (size_t)3 * g.gstride * sizeof(double2);
+    pp.ghost_bytes = (size_t)kMaxRhs * 3 * g.gstride * sizeof(double2);   // K-wide stencils exchange up to kMaxRhs vectors at once
     const size_t bytes = kP2PHeaderBytes + 2 * pp.ghost_bytes;
     CHK(dev_alloc(c, (void **)&pp.block, bytes));
     CU(cudaMemset(pp.block, 0, bytes));

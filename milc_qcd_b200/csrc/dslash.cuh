@@ -378,7 +378,7 @@ __device__ __forceinline__ void push_signal(const PushArg &a, const Geom &g, boo
   if (threadIdx.x < 4) {
     const int d2 = threadIdx.x >> 1, side = threadIdx.x & 1;
     __threadfence_system();
-    if (g.part[d2 + 2]) atomicMax_system(a.flag[d2][side], a.seq);
+    if (g.part[d2 + 2] && a.flag[d2][side] != nullptr) atomicMax_system(a.flag[d2][side], a.seq);
   }
   if (threadIdx.x == 0) *a.ticket = 0;
 }
@@ -446,7 +446,7 @@ push_halo_kernel(const PushArg a, const E *v, const Geom g) {
     __threadfence_system();
     // atomicMax, not a store: flags only ever move forward, whatever order two exchanges'
     // updates reach the neighbour in
-    if (g.part[d2 + 2]) atomicMax_system(a.flag[d2][side], a.seq);
+    if (g.part[d2 + 2] && a.flag[d2][side] != nullptr) atomicMax_system(a.flag[d2][side], a.seq);
   }
   if (threadIdx.x == 0) *a.ticket = 0;
 }

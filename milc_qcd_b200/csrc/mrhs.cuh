@@ -16,7 +16,10 @@
 // block_partials + reduce_finish_kernel) use the same summation tree, so a block solve reproduces
 // K single solves bit for bit.
 //
-// Single GPU (kMode 0) only: a partitioned context runs block solves as a loop.
+// kMode 1 (round 2): partitioned contexts.  One exchange carries the halos of all K inputs (K push kernels into K
+// sub-buffers of the exchange's ghost buffer, the last one raises the arrival flags); the launch is ordered
+// interior-first like dslash_kernel's, boundary CTAs acquire the flags and read ghost vectors / ghost links where a
+// hop crosses a face.
 #pragma once
 #include "blas.cuh"
 #include "dslash.cuh"
@@ -39,30 +42,46 @@ struct DslashMArg {
   T s;
   ReduceWs ws;          // kEpi 2: per-CTA partial sums [CTA][3*K] (slot k: values 3k..3k+2)
   int nsites;
+  // kMode 1 (partitioned lattice): ghost zone of every input, site lists, arrival flags as in DslashArg
+  const T2 *gin[K];
+  const int *sites;
+  int n_int, n_ext, nb_int;
+  const unsigned long long *halo_flags;
+  unsigned long long halo_seq;
+  int halo_mask;
+  int *halo_err;
+  long long halo_timeout;
 };
 
 // the four hops of direction D for all K right-hand sides: each link is loaded once
-template <typename T, int D, int K, int kNc>
+// kPart: the site may have neighbours in the ghost zones (a boundary site of a partitioned lattice)
+template <typename T, int D, int K, int kNc, bool kPart>
 __device__ __forceinline__ void hop_dir_m(const DslashMArg<T, K> &a, int idx, const Coord &c, T (&acc)[K][6]) {
   using T2 = typename Vec2<T>::type;
   const Geom &g = a.g;
   T2 U[9], v[3];
+  const bool part = kPart && (D >= 2) && g.part[D];
 #pragma unroll
   for (int hop = 0; hop < 4; hop++) {
     const int h = (hop == 0) ? 1 : (hop == 1) ? 3 : (hop == 2) ? -1 : -3;
     const bool lng = (hop & 1);
-    const int n = neighbor<D, false, false>(g, idx, c, h);   // (single-GPU kernel: nothing partitioned)
+    const int n = neighbor<D, false, kPart>(g, idx, c, h);
     if (hop < 2) {
       if (lng) load_long<T, T2, kNc>(a.lng_this, g.lstride, D, idx, U);
       else load_link<T, T2>(a.fat_this, g.lstride, D, idx, U);
     } else {
-      if (lng) load_long<T, T2, kNc>(a.lng_other, g.lstride, D, n, U);
-      else load_link<T, T2>(a.fat_other, g.lstride, D, n, U);
+      const int nl = part ? neighbor<D, true>(g, idx, c, h) : n;   // backward links of ghost sites: tail of the link field
+      if (lng) load_long<T, T2, kNc>(a.lng_other, g.lstride, D, nl, U);
+      else load_link<T, T2>(a.fat_other, g.lstride, D, nl, U);
     }
+    const bool ghost = part && n >= g.Vh;
+    const int nv = ghost ? n - g.Vh : n;
+    const int vst = ghost ? g.gstride : g.stride;
 #pragma unroll
     for (int k = 0; k < K; k++) {
+      const T2 *base = ghost ? a.gin[k] : a.in[k];
 #pragma unroll
-      for (int q = 0; q < 3; q++) v[q] = ld_keep(a.in[k] + (size_t)q * g.stride + n);
+      for (int q = 0; q < 3; q++) v[q] = ld_keep(base + (size_t)q * vst + nv);
       if (hop < 2) mat_vec_add<T, T2>(U, v, acc[k]);
       else adj_mat_vec_sub<T, T2>(U, v, acc[k]);
     }
@@ -83,7 +102,16 @@ __device__ __forceinline__ void hop_dir_m(const DslashMArg<T, K> &a, int idx, co
 #ifndef B200KS_MRHS_MINB_F
 #define B200KS_MRHS_MINB_F 5
 #endif
-template <typename T, int kEpi, int K, int kNc>
+// the 16 hops of one output site for all K right-hand sides
+template <typename T, int K, int kNc, bool kPart>
+__device__ __forceinline__ void mrhs_site(const DslashMArg<T, K> &a, int idx, const Coord &c, T (&acc)[K][6]) {
+  hop_dir_m<T, 0, K, kNc, kPart>(a, idx, c, acc);
+  hop_dir_m<T, 1, K, kNc, kPart>(a, idx, c, acc);
+  hop_dir_m<T, 2, K, kNc, kPart>(a, idx, c, acc);
+  hop_dir_m<T, 3, K, kNc, kPart>(a, idx, c, acc);
+}
+
+template <typename T, int kEpi, int K, int kNc, int kMode>
 __global__ void __launch_bounds__(kBlock, sizeof(T) == 8 ? B200KS_MRHS_MINB_D : (K == 4 ? B200KS_MRHS_MINB_F4 : B200KS_MRHS_MINB_F))
 dslash_mrhs_kernel(const DslashMArg<T, K> a) {
   using T2 = typename Vec2<T>::type;
@@ -95,21 +123,35 @@ dslash_mrhs_kernel(const DslashMArg<T, K> a) {
     any = any || live[k];
   }
   if (!any) return;
-  const int idx = blockIdx.x * kBlock + threadIdx.x;
+  int idx = blockIdx.x * kBlock + threadIdx.x;
+  bool active = idx < a.nsites;
+  bool bnd = false;
+  if (kMode == 1) {   // interior CTAs first, then the boundary-site list behind the arrival flags (dslash_kernel)
+    const int b = blockIdx.x;
+    bnd = b >= a.nb_int;
+    if (bnd) {
+      const int k = (b - a.nb_int) * kBlock + threadIdx.x;
+      active = k < a.n_ext;
+      idx = active ? __ldg(a.sites + k) : 0;
+      if (a.halo_flags != nullptr) acquire_halo_cta(a.halo_flags, a.halo_seq, a.halo_mask, a.halo_err, a.halo_timeout);
+    } else {
+      const int k = b * kBlock + threadIdx.x;
+      active = k < a.n_int;
+      idx = active ? interior_site(a.g, k) : 0;
+    }
+  }
   double red[3 * K];
 #pragma unroll
   for (int j = 0; j < 3 * K; j++) red[j] = 0;
-  if (idx < a.nsites) {
+  if (active) {
     const Coord c = site_coord(a.g, idx, a.par);
     T acc[K][6];
 #pragma unroll
     for (int k = 0; k < K; k++)
 #pragma unroll
       for (int j = 0; j < 6; j++) acc[k][j] = 0;
-    hop_dir_m<T, 0, K, kNc>(a, idx, c, acc);
-    hop_dir_m<T, 1, K, kNc>(a, idx, c, acc);
-    hop_dir_m<T, 2, K, kNc>(a, idx, c, acc);
-    hop_dir_m<T, 3, K, kNc>(a, idx, c, acc);
+    if (kMode == 1 && bnd) mrhs_site<T, K, kNc, true>(a, idx, c, acc);
+    else mrhs_site<T, K, kNc, false>(a, idx, c, acc);
 #pragma unroll
     for (int k = 0; k < K; k++) {
       if (!live[k]) continue;

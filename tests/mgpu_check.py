@@ -102,6 +102,24 @@ def main():
             e = np.linalg.norm(xm - xo) / np.linalg.norm(xo)
             check("cg mixed_precision %d solution" % mixed, e <= 10 * resid / (4 * mass * mass), "rel diff %.2e" % e)
             check("cg mixed_precision %d iterations" % mixed, itm_ <= (1.25 if mixed == 1 else 2.5) * ito, "%d vs oracle %d" % (itm_, ito))
+    # block solve: K-wide stencil with one exchange for the K halos; pure double reproduces the single solve's bits
+    lbs = [lb, D.scatter_field(F.make_source(dims, seed=6789, parity=EVEN), dims, grid, rank), 3.0 * lb]
+    lxs = [np.zeros_like(v) for v in lbs]
+    totb, resb = ctx.congrad_block(lbs, lxs, mass, EVEN, 500, 5, resid)
+    same = bool(np.array_equal(lxs[0], lx)) and resb[0]["final_iters"] == it
+    flags = [None] * world
+    dist.all_gather_object(flags, same)
+    if rank == 0:
+        check("block cg (3 sources) reproduces the single solve bit for bit on every rank", all(flags),
+              "iterations %s" % [r["final_iters"] for r in resb])
+        check("block cg converged", all(r["converged"] == 1 for r in resb))
+    lxm = [np.zeros_like(v) for v in lbs]
+    totm, resbm = ctx.congrad_block(lbs, lxm, mass, EVEN, 500, 5, resid, mixed_precision=1)
+    xbm = gather(lxm[0])
+    if rank == 0:
+        e = np.linalg.norm(xbm - xo) / np.linalg.norm(xo)
+        check("block cg mixed precision", all(r["converged"] == 1 for r in resbm) and e <= 10 * resid / (4 * mass * mass),
+              "rel diff %.2e" % e)
     # with the Fermilab relative residual switched on (extra all-reduce path)
     lx2 = np.zeros_like(lb)
     it2, res2 = ctx.congrad(lb, lx2, mass, EVEN, 500, 5, resid, relresid=1e-3)

@@ -170,33 +170,70 @@ def test_block_congrad_mixed_precision(api, oracle, dims, parity, nsrc):
     ctx.close()
 
 
-def test_block_and_sequence_calls_on_a_partitioned_context(api, oracle, monkeypatch):
-    """A partitioned context (here one GPU as its own neighbour) has no K-wide stencil: block and
-    UML calls run the reference's loop of single solves through the halo path and still match the
-    oracle; the K-wide stencil probe and the link construction refuse with a clear error."""
+@pytest.mark.parametrize("force,dims", [("t", (8, 6, 8, 12)), ("zt", (8, 6, 8, 12)), ("zt", (4, 4, 6, 6)), ("zt", (8, 8, 4, 4))])
+def test_block_and_sequence_calls_on_a_partitioned_context(api, oracle, monkeypatch, force, dims):
+    """A partitioned context (here one GPU as its own neighbour: push kernels, ghost buffers, arrival flags, split
+    reductions all run) applies the K-wide stencil too (round 2): one exchange carries the halos of all K inputs.  The
+    block stencil gives the single-source stencil's bits, the pure-double block CG the single solves' bits, the mixed
+    block CG meets the double true residual; the UML sequence of several sources goes through it.  The link
+    construction still refuses a partitioned context with a clear error."""
     from milc_qcd_b200 import fields as F
-    monkeypatch.setenv("B200KS_FORCE_PARTITION", "t")
-    dims = (8, 6, 8, 12)
+    monkeypatch.setenv("B200KS_FORCE_PARTITION", force)
     fat, lng, _ = fields_for(dims)
     ctx = api.Context(dims, grid=(1, 1, 1, 1), rank=0, nranks=1)
     assert ctx.halo_mode() == 2
     ctx.load_links(fat, lng)
-    srcs = _sources(dims, 2, EVEN)
+    V = int(np.prod(dims))
+    # K-wide stencil on the partitioned lattice: oracle, and the single-source kernel's bits
+    full = _sources(dims, 4, EVENANDODD, seed0=900)
+    vs = [ctx.vec_create() for _ in range(4)]
+    vd = [ctx.vec_create() for _ in range(4)]
+    v1 = ctx.vec_create()
+    for k in range(4):
+        ctx.vec_upload(vs[k], full[k])
+    want = [oracle.dslash(dims, fat, lng, f, EVENANDODD) for f in full]
+    for prec, tol in ((2, DSLASH_TOL), (1, 2e-6)):
+        for nrhs in (2, 3, 4):
+            for parity in (EVEN, ODD):
+                for k in range(nrhs):
+                    ctx.vec_zero(vd[k])
+                ctx.dslash_block_dev(vs[:nrhs], vd[:nrhs], parity, prec)
+                sl = slice(0, V // 2) if parity == EVEN else slice(V // 2, V)
+                for k in range(nrhs):
+                    got = np.zeros_like(full[k])
+                    ctx.vec_download(vd[k], got)
+                    assert rel_err(got[sl], want[k][sl]) <= tol, (prec, nrhs, parity, k)
+                    ctx.vec_zero(v1)
+                    ctx.dslash_dev(vs[k], v1, parity, prec)
+                    one = np.zeros_like(full[k])
+                    ctx.vec_download(v1, one)
+                    assert np.array_equal(got, one), (prec, nrhs, parity, k)
+    # block CG
+    srcs = _sources(dims, 3, EVEN)
+    srcs[1] = 37.0 * srcs[1]
     xs = [np.zeros_like(s) for s in srcs]
     tot, res = ctx.congrad_block(srcs, xs, 0.05, EVEN, 500, 5, 1e-9)
-    for k in range(2):
+    for k in range(3):
+        x1 = np.zeros_like(srcs[k])
+        it1, r1 = ctx.congrad(srcs[k], x1, 0.05, EVEN, 500, 5, 1e-9)
+        assert res[k]["final_iters"] == it1 and res[k]["final_rsq"] == r1["final_rsq"] and res[k]["converged"] == 1
+        assert np.array_equal(xs[k], x1)
         xo = np.zeros_like(srcs[k])
         ito, qo = oracle.congrad(dims, fat, lng, srcs[k], xo, 0.05, EVEN, 500, 5, 1e-9)
-        assert res[k]["converged"] == 1 and abs(res[k]["final_iters"] - ito) <= max(2, 0.02 * ito)
+        assert abs(res[k]["final_iters"] - ito) <= max(2, 0.02 * ito)
         assert np.linalg.norm(xs[k] - xo) <= 1e-7 * np.linalg.norm(xo)
-    full = F.make_source(dims, seed=77, parity=EVENANDODD)
-    dst = np.zeros_like(full)
-    it, r = ctx.mat_invert_uml([full], [dst], 0.05, 500, 5, 1e-9)
-    resid = oracle.dslash(dims, fat, lng, dst, EVENANDODD) + 0.1 * dst - full
-    assert np.linalg.norm(resid) <= 1e-6 * np.linalg.norm(full)
-    v = [ctx.vec_create() for _ in range(4)]
-    with pytest.raises(Exception, match="single-GPU"):
-        ctx.dslash_block_dev(v[:2], v[2:], EVEN, 2)
+    xm = [np.zeros_like(s) for s in srcs]
+    tot, resm = ctx.congrad_block(srcs, xm, 0.05, EVEN, 500, 5, 1e-9, mixed_precision=1)
+    for k in range(3):
+        assert resm[k]["converged"] == 1 and resm[k]["final_rsq"] < 1e-18
+        assert np.linalg.norm(xm[k] - xs[k]) <= 1e-7 * np.linalg.norm(xs[k])
+    # the resident UML sequence with several sources (block solver underneath)
+    fulls = [F.make_source(dims, seed=77 + k, parity=EVENANDODD) for k in range(2)]
+    dsts = [np.zeros_like(f) for f in fulls]
+    it, r = ctx.mat_invert_uml(fulls, dsts, 0.05, 500, 5, 1e-9)
+    for k in range(2):
+        resid = oracle.dslash(dims, fat, lng, dsts[k], EVENANDODD) + 0.1 * dsts[k] - fulls[k]
+        assert np.linalg.norm(resid) <= 1e-6 * np.linalg.norm(fulls[k])
     with pytest.raises(Exception, match="single-GPU"):
         ctx.hisq_links(F.make_thin_links(dims, seed=5))
     ctx.close()

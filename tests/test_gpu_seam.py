@@ -302,7 +302,15 @@ def check_multi_gpu_context(oracle, ngpu, dims):
     assert abs(itm - itmo) <= max(2, 0.02 * itmo)
     for j in range(len(offsets)):
         assert np.linalg.norm(ps[j][:V // 2] - pso[j][:V // 2]) <= 1e-6 * np.linalg.norm(pso[j][:V // 2])
-    # block solve (a loop on partitioned contexts) and the resident UML sequence, both parities
+    # block solve (K-wide stencil, one exchange for the K halos) against single solves: the same bits in pure double
+    bs = [F.make_source(dims, seed=191 + k, parity=EVEN) for k in range(3)]
+    xb = [np.zeros_like(s) for s in bs]
+    tot, rb = ctx.congrad_block(bs, xb, 0.05, EVEN, 500, 5, 1e-9)
+    for k in range(3):
+        x1 = np.zeros_like(bs[k])
+        it1, r1 = ctx.congrad(bs[k], x1, 0.05, EVEN, 500, 5, 1e-9)
+        assert rb[k]["final_iters"] == it1 and rb[k]["converged"] == 1 and np.array_equal(xb[k], x1)
+    # the resident UML sequence, both parities
     srcs = [F.make_source(dims, seed=91 + k, parity=EVENANDODD) for k in range(2)]
     dsts = [np.zeros_like(s) for s in srcs]
     tot, rr = ctx.mat_invert_uml(srcs, dsts, 0.05, 500, 5, 1e-9)
