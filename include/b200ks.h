@@ -187,8 +187,8 @@ int b200ks_congrad(b200ks_ctx *ctx, const void *src, void *dest, double mass,
  * (a right-hand side that stops early idles until the others have); with mixed_precision != 0
  * single-precision Krylov vectors with joint reliable updates.  res has nsrc entries
  * (device_seconds = time of the group of <= 4 the source was solved in).  Returns the total
- * number of iterations like the reference loop.  Partitioned (multi-GPU) contexts and the
- * Fermilab relative residual run the loop. */
+ * number of iterations like the reference loop.  Multi-GPU contexts run it K-wide as well (one halo exchange for
+ * the K inputs); the Fermilab relative residual runs the loop. */
 int b200ks_congrad_block(b200ks_ctx *ctx, int nsrc, const void *const *src, void *const *dest,
                          double mass, const b200ks_invert_args *args, b200ks_invert_result *res,
                          int host_prec);

@@ -45,7 +45,7 @@ for mixed in (1, 0):
     V = 1
     for d in dims:
         V *= d
-    row["block_gflops_milc_convention"] = 1187.0 * (V / 2) * tot / row["block_seconds"] / 1e9
+    row["block_gflops_milc_convention"] = 1187.0 * V * tot / row["block_seconds"] / 1e9   # (bench.py's convention)
     out["mixed_precision_%d" % mixed] = row
 if rank == 0:
     print(json.dumps(out))
