@@ -1290,7 +1290,7 @@ static void fused_push_arg(b200ks_ctx *c, const void *vec, PushArg &a) {
     }
   }
   a.seq = pp.seq;
-  a.ticket = pp.ticket + 1;
+  a.ticket = nullptr;   // (no ticket: the next kernel raises the flags)
   a.stop = nullptr;
   pp.fused_ptr = vec;
   for (int k = 0; k < 4; k++) pp.pending.flag[k] = a.flag[k >> 1][k & 1];

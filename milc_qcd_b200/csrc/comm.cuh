@@ -96,7 +96,7 @@ struct P2P {
   char *peer_block[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [d-2][0 backward | 1 forward] neighbour's block
   void *opened[kMaxRanks] = {};     // cudaIpcOpenMemHandle results to close
   unsigned long long seq = 0;       // exchange sequence number (host mirror)
-  unsigned *ticket = nullptr;       // CTA tickets: [0] push_halo_kernel, [1] fused pushes (dslash.cuh push_signal)
+  unsigned *ticket = nullptr;       // CTA ticket of push_halo_kernel
   const void *fused_ptr = nullptr;  // vector half whose halo its PRODUCER has already pushed as exchange `seq`
   HaloRaise pending = {{nullptr, nullptr, nullptr, nullptr}, 0};   // ... and whose arrival flags the next kernel on the
                                                                    // compute stream has to raise (common.cuh)

@@ -334,55 +334,31 @@ struct PushArg {
 // The kernel that PRODUCES a vector stores the words of its boundary sites straight into the neighbours' ghost
 // buffers (NVLink stores from the registers that hold the result) instead of leaving them to push_halo_kernel, which
 // would have to wait for the producer to end, be launched behind an event on another stream and read the words back:
-// the transfer overlaps the producer's own work tile by tile and the arrival flags go up with the producer's last CTA.
-// push_site_h: site idx (local coordinates z, t) of the produced parity; returns whether anything left the GPU.
+// the transfer overlaps the producer's own work tile by tile, and the kernel launched next raises the arrival flags
+// (common.cuh HaloRaise: no fence and no ticket in the producer).
+// push_site_h: site idx (local coordinates z, t) of the produced parity.
 // Offsets as in push_halo_kernel: low slices land in the backward neighbour's "ahead" zone, high slices in the
 // forward neighbour's "behind" zone; with extents below 6 a site can be in both bands.
-__device__ __forceinline__ bool push_site_h(const PushArg &a, const Geom &g, int idx, int z, int t, const uint4 w) {
-  bool any = false;
+__device__ __forceinline__ void push_site_h(const PushArg &a, const Geom &g, int idx, int z, int t, const uint4 w) {
   if (g.part[3]) {
     const int within = idx - t * g.faceh[3];
     if (t < 3) {
       ((uint4 *)a.dst[1][0])[(g.ghost[3][1] - g.Vh) + t * g.faceh[3] + within] = w;
-      any = true;
     }
     if (t >= g.L[3] - 3) {
       ((uint4 *)a.dst[1][1])[(g.ghost[3][0] - g.Vh) + (t - (g.L[3] - 3)) * g.faceh[3] + within] = w;
-      any = true;
     }
   }
   if (g.part[2]) {
     const int within = idx - (t * g.L[2] + z) * g.S2 + t * g.S2;   // t*S2 + (y*Lxh + xh)
     if (z < 3) {
       ((uint4 *)a.dst[0][0])[(g.ghost[2][1] - g.Vh) + z * g.faceh[2] + within] = w;
-      any = true;
     }
     if (z >= g.L[2] - 3) {
       ((uint4 *)a.dst[0][1])[(g.ghost[2][0] - g.Vh) + (z - (g.L[2] - 3)) * g.faceh[2] + within] = w;
-      any = true;
     }
   }
-  return any;
 }
-// Every thread of each of the `nctas` CTAs that take part calls this once, after its stores.  Release as in
-// push_halo_kernel: CTA barrier, system fence (only where something left the GPU), ticket; the last CTA raises the flags.
-__device__ __forceinline__ void push_signal(const PushArg &a, const Geom &g, bool pushed, unsigned nctas) {
-  const int any = __syncthreads_or(pushed ? 1 : 0);
-  __shared__ bool last_cta;
-  if (threadIdx.x == 0) {
-    if (any) __threadfence_system();
-    last_cta = (atomicAdd(a.ticket, 1u) == nctas - 1);
-  }
-  __syncthreads();
-  if (!last_cta) return;
-  if (threadIdx.x < 4) {
-    const int d2 = threadIdx.x >> 1, side = threadIdx.x & 1;
-    __threadfence_system();
-    if (g.part[d2 + 2] && a.flag[d2][side] != nullptr) atomicMax_system(a.flag[d2][side], a.seq);
-  }
-  if (threadIdx.x == 0) *a.ticket = 0;
-}
-
 constexpr int kPushBlock = 256;
 
 // A few long-lived CTAs (one per SM at most) with a grid-stride loop: remote stores are

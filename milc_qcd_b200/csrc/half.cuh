@@ -240,7 +240,7 @@ __device__ __forceinline__ void hop_pair_h(const DslashHArg &a, const uint4 *rec
 
 // one output site: the 16 hops and the epilogue
 template <int kEpi, bool kPart, int kNc>
-__device__ __forceinline__ void half_site(const DslashHArg &a, int idx, double (&red)[3], bool &pushed) {
+__device__ __forceinline__ void half_site(const DslashHArg &a, int idx, double (&red)[3]) {
   const Coord c = site_coord(a.g, idx, a.par);
   const uint4 *rec = a.L.rec[a.par] + record_base(idx, half_record_quads(kNc));
   const float2 zero = make_float2(0.f, 0.f);
@@ -258,7 +258,7 @@ __device__ __forceinline__ void half_site(const DslashHArg &a, int idx, double (
   for (int j = 0; j < 6; j++) acc[j] = acc2[j].x + acc2[j].y;
   if (kEpi == 0) {
     const uint4 o = store_vec_h(a.out_h, idx, acc);
-    if (kPart && a.push_on) pushed = push_site_h(a.push, a.g, idx, c.z, c.t, o);
+    if (kPart && a.push_on) push_site_h(a.push, a.g, idx, c.z, c.t, o);   // (fused halo push of the output)
   } else {
     float2 w[3];
     load_vec_h(a.w_h, idx, w);
@@ -310,17 +310,15 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
     }
   }
   double red[3] = {0, 0, 0};
-  bool pushed = false;
   if (active) {
     const int idx = (kMode == 0) ? k : bnd ? bsite : interior_site(a.g, k);
     // interior sites of a partitioned lattice never leave the local volume: they run the same instruction stream
     // as an unpartitioned lattice (the ghost-index arithmetic of the boundary sites cost every site ~10 %)
-    if (kMode == 1 && bnd) half_site<kEpi, true, kNc>(a, idx, red, pushed);
-    else half_site<kEpi, false, kNc>(a, idx, red, pushed);
+    if (kMode == 1 && bnd) half_site<kEpi, true, kNc>(a, idx, red);
+    else half_site<kEpi, false, kNc>(a, idx, red);
   }
-  // (fused halo push of the output, half_site: the boundary CTAs hold exactly the sites the neighbours need; the
-  // arrival flags are raised by the next kernel on the stream, HaloRaise)
-  (void)pushed;
+  // (the boundary CTAs hold exactly the sites the neighbours need: half_site pushed them; the arrival flags are raised
+  // by the next kernel on the stream, HaloRaise)
   if (kEpi == 2) {   // two-stage (reduce_finish_kernel follows) unless the NCCL-halo path asks for in-kernel sums
     if (kMode == 0 || a.red == nullptr) block_partials<3>(red, a.ws.partials);
     else grid_reduce<3>(red, a.ws, a.red);
@@ -351,7 +349,6 @@ cg_update_half_kernel(float2 *x, float2 *r, uint4 *p_h, const float2 *ttt, int s
   const int i = blockIdx.x * kBlock + threadIdx.x;
   const double2 *xrel = (fuse_scalar & 2) ? st->xrel : nullptr;   // Fermilab relative residue wanted (CgState::xrel)
   double s[2] = {0, 0};
-  bool pushed = false;
   if (i < n) {
     float2 pv[3];
     load_vec_h(p_h, i, pv);
@@ -381,12 +378,12 @@ cg_update_half_kernel(float2 *x, float2 *r, uint4 *p_h, const float2 *ttt, int s
     const uint4 o = store_vec_h(p_h, i, pn);
     if (hp.on) {
       const Coord c = site_coord(hp.g, i, hp.par);
-      pushed = push_site_h(hp.a, hp.g, i, c.z, c.t, o);
+      push_site_h(hp.a, hp.g, i, c.z, c.t, o);
     }
     s[0] = rn;
     if (xrel != nullptr) s[1] = (xn2 == 0) ? 1.0 : (double)rn / xn2;
   }
-  (void)pushed;   // (the finish kernel that follows raises the arrival flags, FinishArg::raise)
+  // (the finish kernel that follows raises the arrival flags of the push above, FinishArg::raise)
   if (fuse_scalar & 8) {   // two-stage: reduce_finish_kernel sums the partials and advances the recurrence
     block_partials<2>(s, ws.partials);
     return;
