@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kBlock, B200KS_HALF_MINBLOCKS) dslash_half_ker
 }
 
 // fused halo push of the update kernel's new search direction (on != 0: partitioned context, peer-to-peer halos): the
-// next stencil's exchange is under way before this kernel has ended (dslash.cuh push_site_h / push_signal)
+// next stencil's exchange is under way before this kernel has ended (dslash.cuh push_site_h)
 struct HalfPush {
   PushArg a;
   Geom g;
