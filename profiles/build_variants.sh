@@ -14,3 +14,6 @@ wait
 # how boundary CTAs of a partitioned stencil poll the arrival flags (dslash.cuh acquire_halo_cta)
 for a in 0 1 2 3; do build acq$a -DB200KS_ACQ=$a & done
 wait
+# fused backward staple body of the fermion force compiled for 2 / 3 / 4 CTAs per SM (254 / 168 / 128 registers)
+for mb in 2 3 4; do build fbwd$mb -DB200KS_FORCE_BWD_MINB=$mb & done
+wait
