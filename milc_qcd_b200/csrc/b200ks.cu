@@ -366,12 +366,14 @@ static void parallel_chunks(size_t n, F f) {
 // stream-ordered on c->stream; returns after the host array has been read completely
 // (pinned host arrays: after the copy has been enqueued -- the caller keeps them alive until the
 // next synchronisation of the stream, which every entry point reaches before it returns)
-static int h2d_rows(b200ks_ctx *c, void *dst, const void *src, const HostRows &hr) {
+// (on: another stream of the same device, for uploads that overlap work queued on c->stream -- fermion_force.cu)
+static int h2d_rows(b200ks_ctx *c, void *dst, const void *src, const HostRows &hr, cudaStream_t on = nullptr) {
   const size_t bytes = hr.total();
   const bool one = hr.nrows == 1 || hr.row_bytes == hr.pitch_bytes;
+  const cudaStream_t st = on ? on : c->stream;
   if (bytes < (kBounceBytes >> 2) || host_is_pinned(src) || bounce_get(c) < 0) {
-    if (one) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
-    else CU(cudaMemcpy2DAsync(dst, hr.row_bytes, src, hr.pitch_bytes, hr.row_bytes, hr.nrows, cudaMemcpyHostToDevice, c->stream));
+    if (one) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemcpy2DAsync(dst, hr.row_bytes, src, hr.pitch_bytes, hr.row_bytes, hr.nrows, cudaMemcpyHostToDevice, st));
     return 0;
   }
   size_t off = 0;
@@ -382,13 +384,16 @@ static int h2d_rows(b200ks_ctx *c, void *dst, const void *src, const HostRows &h
     char *bb = (char *)c->bounce[b];
     const char *base = (const char *)src;
     parallel_chunks(n, [&, off](size_t o, size_t m) { rows_gather(bb + o, base, hr, off + o, m); });
-    CU(cudaMemcpyAsync((char *)dst + off, c->bounce[b], n, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaEventRecord(c->bounce_ev[b], c->stream));
+    CU(cudaMemcpyAsync((char *)dst + off, c->bounce[b], n, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->bounce_ev[b], st));
   }
   return 0;
 }
 int b200ks_host::h2d(b200ks_ctx *c, void *dst, const void *src, size_t bytes) {
   return h2d_rows(c, dst, src, HostRows{bytes, 1, bytes});
+}
+int b200ks_host::h2d_on(b200ks_ctx *c, cudaStream_t on, void *dst, const void *src, size_t bytes) {
+  return h2d_rows(c, dst, src, HostRows{bytes, 1, bytes}, on);
 }
 
 // returns after the host array is complete (synchronises the stream)

@@ -21,6 +21,23 @@ constexpr int kBlock = 128;           // threads per CTA for site kernels
 constexpr int kMaxShifts = 32;
 constexpr int kMaxRhs = 4;            // right-hand sides per pass of the block solver (mrhs.cuh)
 
+// Launch order of FULL-lattice kernels (both parities, site f = parity*Vh + cb) whose sites gather from
+// neighbours: the link construction's staple passes and the fermion force.  In the plain order (thread i = site i)
+// the grid walks all even sites, then all odd ones.  Every hop changes parity, so the even half of the grid streams
+// the odd halves of its input fields from HBM (as neighbours) and the even halves (as the sites themselves and their
+// two-hop neighbours), and the odd half of the grid streams all of it again, a gigabyte later, long after the L2 has
+// lost it: an input field that is read at both parities costs 2 x 144 B per site instead of 144.  Interleaved, a CTA
+// takes kBlock/2 even sites and the kBlock/2 odd sites of the same checkerboard range (warp-uniform parity), the two
+// uses of a matrix are a few CTAs apart and the second one hits in L2.
+// Returns the site of launch index i, -1 past the end; the grid is interleaved_blocks(Vh) CTAs of kBlock threads.
+__host__ __device__ inline int interleaved_site(int i, int Vh) {
+  const int blk = i / kBlock, t = i - blk * kBlock;
+  const int par = t >= kBlock / 2 ? 1 : 0;
+  const int cb = blk * (kBlock / 2) + t - par * (kBlock / 2);
+  return cb < Vh ? par * Vh + cb : -1;
+}
+inline int interleaved_blocks(int Vh) { return (Vh + kBlock / 2 - 1) / (kBlock / 2); }
+
 template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };

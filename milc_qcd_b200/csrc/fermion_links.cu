@@ -111,21 +111,23 @@ static int smear_dev(b200ks_ctx *c, const LinkWork &w, const double *coeffs, con
   const Geom &g = geom(c);
   const int V = 2 * g.Vh;
   const int grid = nblocks(V);
+  const int il = site_order();                                 // staple passes: parities interleaved CTA by CTA
+  const int sgrid = il ? interleaved_blocks(g.Vh) : grid;
   const double one_link = coeffs[0], naik = coeffs[1], three = coeffs[2], five = coeffs[3], seven = coeffs[4], lepage = coeffs[5];
   LAUNCH(c, onelink_kernel, grid, fat, links, one_link - 6.0 * lepage, w.fstride, V);
   if (!(three == 0.0 && lepage == 0.0 && five == 0.0)) {
     for (int dir = 0; dir < 4; dir++)
       for (int nu = 0; nu < 4; nu++) {
         if (nu == dir) continue;
-        LAUNCH(c, (staple_kernel<true>), grid, w.staple, links + (size_t)dir * 9 * w.fstride, links, fat, dir, nu, three, g, w.fstride, V);
+        LAUNCH(c, (staple_kernel<true>), sgrid, w.staple, links + (size_t)dir * 9 * w.fstride, links, fat, dir, nu, three, g, w.fstride, V, il);
         if (lepage != 0.0)   // (a zero coefficient adds nothing: the reference computes it anyway)
-          LAUNCH(c, (staple_kernel<false>), grid, (double2 *)nullptr, w.staple, links, fat, dir, nu, lepage, g, w.fstride, V);
+          LAUNCH(c, (staple_kernel<false>), sgrid, (double2 *)nullptr, w.staple, links, fat, dir, nu, lepage, g, w.fstride, V, il);
         for (int rho = 0; rho < 4; rho++) {
           if (rho == dir || rho == nu) continue;
-          LAUNCH(c, (staple_kernel<true>), grid, w.temp, w.staple, links, fat, dir, rho, five, g, w.fstride, V);
+          LAUNCH(c, (staple_kernel<true>), sgrid, w.temp, w.staple, links, fat, dir, rho, five, g, w.fstride, V, il);
           for (int sig = 0; sig < 4; sig++) {
             if (sig == dir || sig == nu || sig == rho) continue;
-            LAUNCH(c, (staple_kernel<false>), grid, (double2 *)nullptr, w.temp, links, fat, dir, sig, seven, g, w.fstride, V);
+            LAUNCH(c, (staple_kernel<false>), sgrid, (double2 *)nullptr, w.temp, links, fat, dir, sig, seven, g, w.fstride, V, il);
           }
         }
       }

@@ -290,6 +290,71 @@ struct StapleBwdUSite {
   }
 };
 
+// The full pass as two ROLES of one kernel (fermion_force.cu force_pair_kernel): two threads per site, each with three
+// of the six contributions and ONE of the two outputs, so that a role keeps about half of the fused body's matrices
+// live and compiles for 128 registers without spilling (16 warps per SM instead of 8; the fused body at 128 registers
+// spills 2 KB per thread; the roles spill 0.2 KB).  Unlike the four-kernel split the two roles of a site run in the same CTA at the same
+// time: the matrices both of them load (U_nu(z+mu), H(z+nu)) and the neighbours' reloads meet in L1/L2, not in HBM.
+//   role_link: both contributions to the gradient of the link field -> glink(z); returns the sixth contribution
+//              (L(z) U_nu(z+mu) H(z+nu)^+, whose factors it holds anyway), handed over through shared memory
+//   role_u:    the other three contributions to the gradient of the nu links; finish_u adds the sixth, -> gUnu(z)
+// Same products, same order of summation as StapleBwdSite with part = 3: the results are identical.
+template <int kMB>   // CTAs per SM the kernel is compiled for: 4 = 128 registers (16 warps per SM), 3 = 168 (12 warps)
+struct StapleBwdPairSite {
+  static constexpr int kMinBlocks = kMB;
+  FGeom g;
+  const double2 *H;
+  double hs;
+  const double2 *link, *Unu;
+  double2 *glink, *gUnu;
+  size_t fs;
+  int mu, nu;
+  // hand(t4) is called as soon as the sixth contribution is formed (nothing of it stays live afterwards)
+  template <class Hand>
+  B200KS_HD void role_link(int z, const Hand &hand) const {
+    const FSite s0 = fsite(g, z), smn = fhop(g, s0, nu, -1);
+    const int zpn = findex(g, fhop(g, s0, nu, 1)), zpm = findex(g, fhop(g, s0, mu, 1));
+    const int zmn = findex(g, smn), zmnpm = findex(g, fhop(g, smn, mu, 1));
+    hand(na(nn(ld(link, fs, z), ld(Unu, fs, zpm)), ld(H, fs, zpn)));
+    Mat gl = na(nn(ld(Unu, fs, z), ld(H, fs, zpn)), ld(Unu, fs, zpm));
+    const Mat up = nn(an(ld(Unu, fs, zmn), ld(H, fs, zmn)), ld(Unu, fs, zmnpm));
+    for (int k = 0; k < 9; k++) {   // upper + lower, the fused body's order
+      gl.e[k].x = up.e[k].x + gl.e[k].x;
+      gl.e[k].y = up.e[k].y + gl.e[k].y;
+    }
+    acc(glink, fs, z, hs, gl);
+  }
+  // sum(term) is called with the three contributions one after the other (the device sums them in shared memory: a
+  // 3x3 accumulator held in registers across the terms is what does not fit into 128 of them)
+  template <class Sum>
+  B200KS_HD void role_u(int z, const Sum &sum) const {
+    const FSite s0 = fsite(g, z), smm = fhop(g, s0, mu, -1);
+    const int zpn = findex(g, fhop(g, s0, nu, 1)), zpm = findex(g, fhop(g, s0, mu, 1));
+    const int zmm = findex(g, smm), zmmpn = findex(g, fhop(g, smm, nu, 1));
+    sum(nn(ld(H, fs, z), na(ld(Unu, fs, zpm), ld(link, fs, zpn))));
+    sum(nn(an(ld(H, fs, zmm), ld(Unu, fs, zmm)), ld(link, fs, zmmpn)));
+    sum(nn(an(ld(link, fs, zmm), ld(Unu, fs, zmm)), ld(H, fs, zmmpn)));
+  }
+  B200KS_HD void finish_u(int z, Mat gu, const Mat &t4) const {
+    add(gu, t4);
+    acc(gUnu, fs, z, hs, gu);
+  }
+  struct Keep {   // (host executor: hand-over and sum are local variables)
+    Mat *m;
+    B200KS_HD void operator()(const Mat &t) const { *m = t; }
+  };
+  struct Add {
+    Mat *m;
+    B200KS_HD void operator()(const Mat &t) const { add(*m, t); }
+  };
+  B200KS_HD void operator()(int z) const {   // (host executor; the device runs the roles on two threads)
+    Mat t4, gu = zero();
+    role_link(z, Keep{&t4});
+    role_u(z, Add{&gu});
+    finish_u(z, gu, t4);
+  }
+};
+
 // out(f) += s * in(f) for nplanes planes (one-link term backwards, scaled copies)
 struct AxpySite {
   double2 *out;
@@ -462,6 +527,7 @@ struct ForceBufs {
   double2 *gfat, *glng, *gW, *gU; // 36 planes each
   double2 *st3, *st5, *g3, *g5;   // 9 planes each
   bool split = false;             // backward staple passes as up to four small kernels (StapleBwdLinkSite / StapleBwdUSite)
+  int pair = 0;                   // full backward staple passes as two roles of one kernel (StapleBwdPairSite<pair>: 3 or 4)
 };
 
 template <class X>
@@ -476,6 +542,10 @@ void staple_bwd(X &x, const ForceBufs &b, const double2 *H, double hs, const dou
       x.run(b.nsites, StapleBwdLinkSite<2>{b.g, H, hs, Unu, glink, b.fs, mu, nu});
       x.run(b.nsites, StapleBwdUSite<2>{b.g, H, hs, link, Unu, gUnu, b.fs, mu, nu});
     }
+  } else if (b.pair == 4 && part == 3) {
+    x.run(b.nsites, StapleBwdPairSite<4>{b.g, H, hs, link, Unu, glink, gUnu, b.fs, mu, nu});
+  } else if (b.pair == 3 && part == 3) {
+    x.run(b.nsites, StapleBwdPairSite<3>{b.g, H, hs, link, Unu, glink, gUnu, b.fs, mu, nu});
   } else {
     x.run(b.nsites, StapleBwdSite{b.g, H, hs, link, Unu, glink, gUnu, b.fs, mu, nu, part});
   }
@@ -528,9 +598,11 @@ void smear_bwd(X &x, const ForceBufs &b, const double *coeffs, const double2 *li
 // straight to G_W (c1', c3': the reference's one-link + Naik table).  naik_terms: on entry gW holds the sum of
 // their one-hop outer products and gU the sum of their three-hop ones, weights eps_k c1' 2 res_j and
 // eps_k c3' 2 res_j included (the seam's coeff[num_terms + i]); otherwise both are cleared here.
+// In two phases, so that the host side can bring V and U to the device while the first one runs:
+//   force_chain_w   needs W only (level-2 smearing and the Naik products backwards): G_fat, G_lng -> G_W
+//   force_chain_vu  needs V, then U (projection and level-1 smearing backwards):     G_W -> G_V -> G_U
 template <class X>
-void force_chain(X &x, const ForceBufs &b, const double *coeffs1, const double *coeffs2, bool naik_in_oprod, double filter,
-                 bool naik_terms = false) {
+void force_chain_w(X &x, const ForceBufs &b, const double *coeffs2, bool naik_in_oprod, bool naik_terms = false) {
   const int n = b.nsites;
   if (naik_terms) {
     x.run(n, NaikBwdSite{b.g, b.gU, b.W, b.gW, 1.0, b.fs});
@@ -540,8 +612,17 @@ void force_chain(X &x, const ForceBufs &b, const double *coeffs1, const double *
   x.run(n, ZeroSite{b.gU, b.fs, 36});
   smear_bwd(x, b, coeffs2, b.W, b.gfat, b.gW);
   x.run(n, NaikBwdSite{b.g, b.glng, b.W, b.gW, naik_in_oprod ? 1.0 : coeffs2[1], b.fs});
-  x.run(4 * n, UnitBwdSite{b.V, b.gW, b.fs, n, filter});
+}
+template <class X>
+void force_chain_vu(X &x, const ForceBufs &b, const double *coeffs1, double filter) {
+  x.run(4 * b.nsites, UnitBwdSite{b.V, b.gW, b.fs, b.nsites, filter});
   smear_bwd(x, b, coeffs1, b.U, b.gW, b.gU);
+}
+template <class X>
+void force_chain(X &x, const ForceBufs &b, const double *coeffs1, const double *coeffs2, bool naik_in_oprod, double filter,
+                 bool naik_terms = false) {
+  force_chain_w(x, b, coeffs2, naik_in_oprod, naik_terms);
+  force_chain_vu(x, b, coeffs1, filter);
 }
 
 }  // namespace force

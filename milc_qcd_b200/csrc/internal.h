@@ -3,6 +3,7 @@
 // accessors.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/b200ks.h"
@@ -19,6 +20,7 @@ int stage_get(b200ks_ctx *c, size_t bytes, void **out);   // persistent re-layou
 // h2d is stream-ordered and returns once the host array has been read, d2h returns when it is complete
 int h2d(b200ks_ctx *c, void *dst, const void *src, size_t bytes);
 int d2h(b200ks_ctx *c, void *dst, const void *src, size_t bytes);
+int h2d_on(b200ks_ctx *c, cudaStream_t on, void *dst, const void *src, size_t bytes);   // h2d on another stream of the device
 const b200ks::Geom &geom(const b200ks_ctx *c);
 cudaStream_t stream(const b200ks_ctx *c);
 int device(const b200ks_ctx *c);
@@ -32,6 +34,15 @@ void *&link_work(b200ks_ctx *c);                     // slot owned by fermion_li
 void fermion_links_release(b200ks_ctx *c);           // fermion_links.cu; called by b200ks_destroy
 
 inline int nblocks(int n) { return (n + b200ks::kBlock - 1) / b200ks::kBlock; }
+
+// Launch order of the full-lattice gather kernels (link construction, fermion force): 1 = the two parities interleaved
+// CTA by CTA (common.cuh interleaved_site), 0 = all even sites, then all odd ones.  Read per call: B200KS_SITE_ORDER
+// is an A/B switch (profiles/run_r02u.sh).
+constexpr int kDefaultSiteOrder = 0;
+inline int site_order() {
+  const char *e = getenv("B200KS_SITE_ORDER");
+  return e ? (atoi(e) != 0 ? 1 : 0) : kDefaultSiteOrder;
+}
 
 }  // namespace b200ks_host
 

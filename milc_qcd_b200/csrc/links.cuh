@@ -141,9 +141,11 @@ onelink_kernel(double2 *fat, const double2 *links, double c1, size_t fstride, in
 template <bool kSave>
 __global__ void __launch_bounds__(kBlock)
 staple_kernel(double2 *staple_out, const double2 *link, const double2 *links, double2 *fat, int mu, int nu, double coef,
-              const Geom g, size_t fstride, int nsites) {
-  const int f = blockIdx.x * kBlock + threadIdx.x;
-  if (f >= nsites) return;
+              const Geom g, size_t fstride, int nsites, int interleaved) {
+  int f = blockIdx.x * kBlock + threadIdx.x;
+  if (interleaved) f = interleaved_site(f, g.Vh);   // (common.cuh: both uses of a matrix a few CTAs apart)
+  else if (f >= nsites) f = -1;
+  if (f < 0) return;
   const double2 *Unu = links + (size_t)nu * 9 * fstride;
   const int f_pnu = full_neighbor(g, f, nu, 1), f_pmu = full_neighbor(g, f, mu, 1);
   const int f_mnu = full_neighbor(g, f, nu, -1), f_mnu_pmu = full_neighbor(g, f_mnu, mu, 1);

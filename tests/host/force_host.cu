@@ -29,7 +29,8 @@ extern "C" void force_host(const int *dims, const double *coeffs1, const double 
                            const double *W, const double *multi_x, const double *c1, const double *c3, int nterms,
                            int n_naik_terms, double eps, int naik_in_oprod, double filter, int split, double *mom) {
   ForceBufs b;
-  b.split = split != 0;
+  b.split = split == 1;   // 1: the four-kernel form of the backward staple passes, 2: the two-role form (StapleBwdPairSite)
+  b.pair = split == 2 ? 4 : split == 3 ? 3 : 0;
   for (int d = 0; d < 4; d++) b.g.L[d] = dims[d];
   const int n = dims[0] * dims[1] * dims[2] * dims[3];
   b.g.Vh = n / 2;

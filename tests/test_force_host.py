@@ -102,6 +102,10 @@ def test_force_filter_matches_reference_on_rough_links(host_force):
     two = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE,
                5.0e-5, split=True)
     assert np.abs(two - mom).max() <= 1e-12 * scale
+    # the two-role form of the full passes (ForceBufs::pair): same products, same order of summation
+    pair = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE,
+                5.0e-5, split=2)
+    assert np.array_equal(pair, mom)
     # the filter is what makes the difference on this input, and switching it off matches the oracle's unfiltered force
     raw = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE, 0.0)
     assert np.abs(raw - g["mom"]).max() > 0.1 * scale

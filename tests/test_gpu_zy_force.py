@@ -105,6 +105,54 @@ def test_force_with_naik_epsilons_matches_reference_golden(api):
     ctx.close()
 
 
+@pytest.mark.parametrize("order,form,overlap", [(0, 0, 0), (1, 0, 0), (0, 2, 0), (1, 2, 1), (1, 3, 1), (1, 1, 1), (0, 0, 1)])
+def test_force_launch_variants_give_the_same_force(api, monkeypatch, order, form, overlap):
+    """The A/B switches of the force (read per call): B200KS_SITE_ORDER (parities interleaved CTA by CTA, also in the
+    link construction), B200KS_FORCE_SPLIT (backward staple passes fused / four kernels / two roles of one kernel at
+    128 or 168 registers), B200KS_FORCE_OVERLAP (V and U uploaded on a second stream while the W-level chain runs).
+    Every combination must reproduce the reference golden; the two-role form sums in the fused body's order, the
+    four-kernel form in another (1e-13).  Lattices whose half volume is not a multiple of the CTA's
+    site count exercise the tail of the interleaved orders."""
+    from milc_qcd_b200 import fields as F
+    g = np.load(GOLDEN)
+    dims = tuple(int(d) for d in g["dims"])
+    U, X, res = g["U"], g["multi_x"], g["residues"]
+    ctx = api.Context(dims)
+    for k in ("B200KS_SITE_ORDER", "B200KS_FORCE_SPLIT", "B200KS_FORCE_OVERLAP"):
+        monkeypatch.setenv(k, "0")
+    L0 = ctx.hisq_links(U)
+    base = ctx.hisq_force(U, L0["V"], L0["W"], list(X), res, float(g["eps"]))
+    monkeypatch.setenv("B200KS_SITE_ORDER", str(order))
+    monkeypatch.setenv("B200KS_FORCE_SPLIT", str(form))
+    monkeypatch.setenv("B200KS_FORCE_OVERLAP", str(overlap))
+    L = ctx.hisq_links(U)
+    for k in ("V", "W", "fat", "lng"):
+        assert np.array_equal(L[k], L0[k]), k
+    mom = ctx.hisq_force(U, L["V"], L["W"], list(X), res, float(g["eps"]))
+    assert np.abs(mom - g["mom"]).max() <= 1e-10 * np.abs(g["mom"]).max()
+    assert np.abs(mom - base).max() <= (1e-13 if form == 1 else 1e-15) * np.abs(base).max()
+    ctx.close()
+    # odd shapes: Vh = 96 (a partly filled last CTA in every order) and Vh = 24 (less than one CTA)
+    for d2 in ((4, 6, 2, 4), (2, 4, 2, 6)):
+        Ur = F.make_thin_links(d2, seed=21, spread=0.5)
+        rng = np.random.default_rng(4)
+        Xr = [rng.standard_normal((int(np.prod(d2)), 3, 2)) for _ in range(2)]
+        c2 = api.Context(d2)
+        for k in ("B200KS_SITE_ORDER", "B200KS_FORCE_SPLIT", "B200KS_FORCE_OVERLAP"):
+            monkeypatch.setenv(k, "0")
+        La = c2.hisq_links(Ur)
+        ma = c2.hisq_force(Ur, La["V"], La["W"], Xr, [0.7, -0.2], 0.1)
+        monkeypatch.setenv("B200KS_SITE_ORDER", str(order))
+        monkeypatch.setenv("B200KS_FORCE_SPLIT", str(form))
+        monkeypatch.setenv("B200KS_FORCE_OVERLAP", str(overlap))
+        Lb = c2.hisq_links(Ur)
+        for k in ("V", "W", "fat", "lng"):
+            assert np.array_equal(La[k], Lb[k]), (d2, k)
+        mb = c2.hisq_force(Ur, La["V"], La["W"], Xr, [0.7, -0.2], 0.1)
+        assert np.abs(mb - ma).max() <= 1e-13 * np.abs(ma).max(), d2
+        c2.close()
+
+
 def test_su3_rhmc_hisq_with_gpu_fermion_force_matches_reference_goldens(tmp_path):
     """-DUSE_FF_GPU build (WANT_FF_GPU=true) on top of the GPU links and solves: every molecular-
     dynamics step of the trajectory takes its HISQ fermion force from qudaHisqForce."""
