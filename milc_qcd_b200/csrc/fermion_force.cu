@@ -15,9 +15,12 @@ using namespace b200ks_host;
 
 namespace {
 
-// Defaults of the A/B switches read in b200ks_hisq_force (measured: profiles/run_r02u.sh)
-constexpr int kDefaultForceForm = 0;        // B200KS_FORCE_SPLIT
-constexpr bool kDefaultForceOverlap = false; // B200KS_FORCE_OVERLAP
+// Defaults of the A/B switches read in b200ks_hisq_force.  Measured at 32^3 x 64, 9 terms (profiles/force_ab_r02u.json,
+// profiles/ncu_fbwd_r02v.txt): uploading V and U beside the W-level chain takes 0.09 s off a 0.42 s call; the two-role
+// form of the backward staple pass runs in 847 us against the fused body's 868 (both with the interleaved site order),
+// i.e. doubling the resident warps buys 2 % -- the pass is not waiting for occupancy -- so the fused body stays.
+constexpr int kDefaultForceForm = 0;         // B200KS_FORCE_SPLIT
+constexpr bool kDefaultForceOverlap = true;  // B200KS_FORCE_OVERLAP
 
 // one thread per site: the kernel is the __host__ __device__ site functor of force.cuh plus the launch.
 // vh_il != 0 (functors over the 2 Vh sites only): the two parities interleaved CTA by CTA (common.cuh interleaved_site)

@@ -37,8 +37,10 @@ inline int nblocks(int n) { return (n + b200ks::kBlock - 1) / b200ks::kBlock; }
 
 // Launch order of the full-lattice gather kernels (link construction, fermion force): 1 = the two parities interleaved
 // CTA by CTA (common.cuh interleaved_site), 0 = all even sites, then all odd ones.  Read per call: B200KS_SITE_ORDER
-// is an A/B switch (profiles/run_r02u.sh).
-constexpr int kDefaultSiteOrder = 0;
+// is an A/B switch.  Measured at 32^3 x 64 (profiles/force_ab_r02u.json, ncu_staple_r02u.txt): DRAM traffic of a staple
+// pass of the link construction 867 -> 709 B per site, 270 -> 236 us, the whole chain 41.4 -> 36.7 ms; backward staple
+// pass of the force 1446 -> 1007 B per site, 930 -> 843 us.
+constexpr int kDefaultSiteOrder = 1;
 inline int site_order() {
   const char *e = getenv("B200KS_SITE_ORDER");
   return e ? (atoi(e) != 0 ? 1 : 0) : kDefaultSiteOrder;

@@ -6,7 +6,7 @@ force call per variant (9 terms, host buffers in and out, like bench.py --worklo
 every variant's momenta from the baseline variant's.
 
     python profiles/force_ab.py                 # all variants
-    python profiles/force_ab.py --only 1,2,0    # one variant, one call, 3 terms (profiling target for ncu)
+    python profiles/force_ab.py --only 0,0,0:1,0,0    # one 3-term call per listed variant (profiling target for ncu)
 """
 import argparse
 import json
@@ -38,15 +38,17 @@ def main():
     V = int(np.prod(dims))
     ctx = api.Context(dims)
     out = {"lattice": list(dims), "switches": list(KEYS)}
-    if args.only:
-        v = tuple(int(x) for x in args.only.split(","))
-        set_variant(v)
+    if args.only:   # "o,f,v" or several of them separated by ":" -- one 3-term force call each, in this order
+        vs = [tuple(int(x) for x in w.split(",")) for w in args.only.split(":")]
+        set_variant(vs[0])
         ms, _ = ctx.hisq_links_time(1234, 1)
         U, Vl, W = ctx.hisq_links_fetch(0), ctx.hisq_links_fetch(1), ctx.hisq_links_fetch(2)
         rng = np.random.default_rng(1)
         X = [rng.standard_normal((V, 3, 2)) for _ in range(3)]
-        mom = ctx.hisq_force(U, Vl, W, X, [0.3, 0.5, 0.7], 0.02)
-        print(json.dumps({"variant": v, "links_chain_ms": ms, "mom_max": float(np.abs(mom).max())}))
+        for v in vs:
+            set_variant(v)
+            mom = ctx.hisq_force(U, Vl, W, X, [0.3, 0.5, 0.7], 0.02)
+            print(json.dumps({"variant": v, "links_chain_ms": ms, "mom_max": float(np.abs(mom).max())}))
         ctx.close()
         return
     links = {}

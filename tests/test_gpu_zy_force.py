@@ -105,7 +105,7 @@ def test_force_with_naik_epsilons_matches_reference_golden(api):
     ctx.close()
 
 
-@pytest.mark.parametrize("order,form,overlap", [(0, 0, 0), (1, 0, 0), (0, 2, 0), (1, 2, 1), (1, 3, 1), (1, 1, 1), (0, 0, 1)])
+@pytest.mark.parametrize("order,form,overlap", [(0, 0, 0), (1, 0, 0), (1, 0, 1), (0, 2, 0), (1, 2, 1), (1, 3, 1), (1, 1, 1), (0, 0, 1)])
 def test_force_launch_variants_give_the_same_force(api, monkeypatch, order, form, overlap):
     """The A/B switches of the force (read per call): B200KS_SITE_ORDER (parities interleaved CTA by CTA, also in the
     link construction), B200KS_FORCE_SPLIT (backward staple passes fused / four kernels / two roles of one kernel at
