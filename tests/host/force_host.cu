@@ -60,3 +60,12 @@ extern "C" void force_host(const int *dims, const double *coeffs1, const double 
   force_chain(x, b, coeffs1, coeffs2, naik_in_oprod != 0, filter, n_naik_terms > 0);
   x.run(4 * n, MomSite<double>{b.U, b.gU, mom, eps, b.fs, n});
 }
+
+// launch order of the full-lattice gather kernels (common.cuh): out[i] = site of launch index i (-1 past the end),
+// i < interleaved_blocks(Vh) * kBlock; returns that count
+#include "../../milc_qcd_b200/csrc/common.cuh"
+extern "C" int interleaved_order(int Vh, int *out, int cap) {
+  const int n = b200ks::interleaved_blocks(Vh) * b200ks::kBlock;
+  for (int i = 0; i < n && i < cap; i++) out[i] = b200ks::interleaved_site(i, Vh);
+  return n;
+}

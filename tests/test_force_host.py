@@ -147,3 +147,28 @@ def test_force_with_naik_epsilons_matches_reference_golden(host_force):
     # the epsilons matter on this input
     plain = _run(host_force, dims, U, L["V"], L["W"], X, 2 * res, naik * 2 * res, float(g["eps"]), True, lo.FAT7, lo.ASQTAD_LIKE)
     assert np.abs(plain - g["mom"]).max() > 1e-3 * scale
+
+
+@pytest.mark.parametrize("Vh", [1, 24, 63, 64, 65, 96, 648, 1 << 14])
+def test_interleaved_launch_order_visits_every_site_once(host_force, Vh):
+    """common.cuh interleaved_site (launch order of the staple passes of the link construction and of the force):
+    a bijection from the live launch indices onto the 2 Vh sites, parity uniform within every warp, and the even and
+    the odd sites of one CTA cover the same checkerboard range."""
+    cap = (Vh // 64 + 2) * 128
+    out = np.full(cap, -7, dtype=np.int32)
+    host_force.interleaved_order.restype = C.c_int
+    host_force.interleaved_order.argtypes = [C.c_int, _ip, C.c_int]
+    n = host_force.interleaved_order(Vh, out, cap)
+    assert n % 128 == 0 and n <= cap and n >= 2 * Vh
+    got = out[:n]
+    live = got[got >= 0]
+    assert sorted(live.tolist()) == list(range(2 * Vh))
+    for w in range(n // 32):
+        lane = got[32 * w:32 * w + 32]
+        lane = lane[lane >= 0]
+        assert len(set((lane >= Vh).tolist())) <= 1
+    for b in range(n // 128):
+        cta = got[128 * b:128 * b + 128]
+        ev, od = cta[:64], cta[64:]
+        assert np.all((ev < Vh)) and np.all((od < 0) | (od >= Vh))
+        assert np.array_equal(ev[ev >= 0], od[od >= 0] - Vh)
