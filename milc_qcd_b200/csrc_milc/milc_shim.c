@@ -235,6 +235,7 @@ int ks_congrad_block_parity_gpu(int nsrc, su3_vector **t_src, su3_vector **t_des
     if (r[k].final_rsq > qic->final_rsq) qic->final_rsq = (Real)r[k].final_rsq;
     if (r[k].final_relrsq > qic->final_relrsq) qic->final_relrsq = (Real)r[k].final_relrsq;
     if (r[k].size_r > qic->size_r) qic->size_r = (Real)r[k].size_r;
+    if (r[k].size_relr > qic->size_relr) qic->size_relr = (Real)r[k].size_relr;
     if (r[k].final_restart > qic->final_restart) qic->final_restart = r[k].final_restart;
     if (!r[k].converged) qic->converged = 0;
   }
@@ -313,6 +314,7 @@ int mat_invert_block_uml_gpu(su3_vector **src, su3_vector **dst, Real mass, int 
     if (r[k].final_rsq > qic->final_rsq) qic->final_rsq = (Real)r[k].final_rsq;
     if (r[k].final_relrsq > qic->final_relrsq) qic->final_relrsq = (Real)r[k].final_relrsq;
     if (r[k].size_r > qic->size_r) qic->size_r = (Real)r[k].size_r;
+    if (r[k].size_relr > qic->size_relr) qic->size_relr = (Real)r[k].size_relr;
     if (r[k].final_restart > qic->final_restart) qic->final_restart = r[k].final_restart;
     if (!r[k].converged) qic->converged = 0;
   }
