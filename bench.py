@@ -404,6 +404,39 @@ def single_solve_point(api, dist, torch, dims, world, rank, local_rank, grid, lo
     return out
 
 
+def links_force_summary(api, dims, local_rank):
+    """Rows f1 / f2 of SURVEY.md section 8 in the driver's line (N = 1): the HISQ link chain U -> V -> W -> (fat, long)
+    with everything resident (CUDA events, b200ks_hisq_links_time) and the HISQ fermion force through the host-buffer
+    call behind qudaHisqForce (9 terms; U, V, W and the vectors H2D, the momenta D2H inside the clock) -- the numbers
+    --workload links / --workload force report in full, with the reference timed beside them."""
+    V = int(np.prod(dims))
+    ctx = api.Context(dims, device=local_rank)
+    try:
+        ctx.hisq_links_time(1234, 1)
+        ms, nsvd = ctx.hisq_links_time(1234, 3)
+        flop = (2 * 61632.0 + 1728.0) * V
+        out = {"links": {"ms_per_chain": ms, "value": flop / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "svd_branch_links": nsvd,
+                         "note": "Haar-random thin links generated on the device, resident chain; MILC's 2 x 61632 + 1728 "
+                                 "flop per site convention"}}
+        U, Vl, W = ctx.hisq_links_fetch(0), ctx.hisq_links_fetch(1), ctx.hisq_links_fetch(2)
+        rng = np.random.default_rng(77)
+        nterms = 9
+        X = [rng.standard_normal((V, 3, 2)) for _ in range(nterms)]
+        res = np.linspace(0.2, 1.0, nterms)
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            mom = ctx.hisq_force(U, Vl, W, X, res, 0.02)
+            times.append(time.perf_counter() - t0)
+        out["force"] = {"seconds_per_call": min(times), "all_calls_s": times, "us_per_site": 1e6 * min(times) / V,
+                        "nterms": nterms, "h2d_bytes_per_call": int(3 * U.nbytes + nterms * X[0].nbytes),
+                        "d2h_bytes_per_call": int(mom.nbytes), "mom_max": float(np.abs(mom).max()),
+                        "note": "b200ks_hisq_force on pageable host arrays in MILC's layout, best of three calls"}
+        return out
+    finally:
+        ctx.close()
+
+
 def run_b200(args):
     import torch
     from milc_qcd_b200 import api, dist as D
@@ -667,6 +700,14 @@ def run_b200(args):
         except Exception as ex:
             multishift = {"error": repr(ex)}
 
+    # ---- rows f1 / f2 (link construction, fermion force) at N = 1: a reported extra, never a reason to lose the line ----
+    links_force = None
+    if not multi and not args.lattice and not args.no_extras:
+        try:
+            links_force = links_force_summary(api, dims, local_rank)
+        except Exception as ex:
+            links_force = {"error": repr(ex)}
+
     value = CG_FLOP_PER_SITE * V * iters_total / (ms_total * 1e-3) / 1e9
     if rank == 0:
         if e2e is None:
@@ -722,6 +763,7 @@ def run_b200(args):
             "efficiency_same_lattice": eff,
             "multishift": multishift,
             "weak_point": weak,
+            "links_force": links_force,
             "gpu_launches": launches, "clocks": clocks,
             "setup": {"gen_fields_s": t_gen, "device_bytes": device_bytes},
         }
